@@ -1,0 +1,436 @@
+// Implicit-GEMM convolution on tcgen05 (sm_100a).
+//
+//   out[m, n] = sum_{seg, tap, c} src_seg[pix(m, tap), c] * w[n, k(seg, tap, c)]
+//
+// One persistent CTA per SM walks (m-tile, n-tile) pairs.  Warp roles:
+//   warp 0   : TMA producer  - one 5-D tiled TMA per K block for the activation patch (the 3x3 taps are the same
+//              box shifted by (dh, dw); TMA zero-fills the halo), one 2-D TMA for the packed weights
+//   warp 1   : MMA issuer    - lane 0 issues tcgen05.mma (M=128, N=block_n, K=16) into a double-buffered TMEM
+//              accumulator; tcgen05.commit releases smem stages / publishes the accumulator
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      - tcgen05.ld (one pixel row per thread), optional bias / accumulate, per-channel
+//              sum / sum^2 (BatchNorm batch statistics) by a shuffle transpose-reduce, 16-byte stores
+// Both operands are K-major, 128-byte swizzled: a pixel's 64 channels (128 B) form one swizzle row.
+#include "common.cuh"
+#include <algorithm>
+#include <mutex>
+
+namespace dfcsa {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kMaxStages = 8;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;                 // TMEM columns between the two accumulators
+
+struct ConvTcArgs {
+  int n_seg;
+  int seg_kb[3];    // channels / 64
+  int seg_mode[3];
+  int total_kb;
+  int tiles_w, tiles_h, tiles_b, w_t, h_t;
+  int H, W;         // output grid as seen by the tile walker (B merged into H when there is no halo)
+  int n_tiles_n, block_n, N;
+  int stages;
+  int a_box_bytes;  // bytes one activation TMA delivers
+  void* out;
+  long long ld_out;
+  int out_dtype, out_mode, accumulate;
+  const float* bias;
+  double* stats;
+  int convt_co, convt_h, convt_w;
+  uint32_t idesc;
+};
+
+struct TileCoord { int nt, w0, h0, tb; };
+
+__device__ __forceinline__ TileCoord tile_coord(const ConvTcArgs& a, int tile) {
+  TileCoord t;
+  t.nt = tile % a.n_tiles_n;
+  int mt = tile / a.n_tiles_n;
+  t.w0 = (mt % a.tiles_w) * a.w_t;
+  int r = mt / a.tiles_w;
+  t.h0 = (r % a.tiles_h) * a.h_t;
+  t.tb = r / a.tiles_h;
+  return t;
+}
+
+template <typename TOut>
+__device__ __forceinline__ void store_chunk(TOut* dst, float (&v)[32], int ncols, bool accumulate) {
+  // ncols is a multiple of 8; dst is 16-byte aligned
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (g * 8 < ncols) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = v[g * 8 + i];
+      if (accumulate) {
+        float o[8];
+        load8<TOut>(dst + g * 8, o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t[i] += o[i];
+      }
+      store8<TOut>(dst + g * 8, t);
+    }
+  }
+}
+
+// lane j ends with sum over the 32 lanes of v[j]
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      float send = upper ? v[i] : v[i + off];
+      float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(256, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ ConvTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_stats[2][256];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stage_bytes = kABytes + a.block_n * 128;
+  const int total_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.n_tiles_n;
+
+  // Rows a partial activation box never writes must read as zero for the MMA.
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* p = reinterpret_cast<uint4*>(smem);
+    const int n16 = a.stages * stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = z;
+    s_stats[0][threadIdx.x] = 0.f;
+    s_stats[1][threadIdx.x] = 0.f;
+    fence_proxy_async();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a0);
+    if (a.n_seg > 1) tma_prefetch_desc(&map_a1);
+    if (a.n_seg > 2) tma_prefetch_desc(&map_a2);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(a.a_box_bytes + a.block_n * 128);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(a, tile);
+      int kb_global = 0;
+      for (int s = 0; s < a.n_seg; ++s) {
+        const CUtensorMap* ma = (s == 0) ? &map_a0 : (s == 1) ? &map_a1 : &map_a2;
+        const int mode = a.seg_mode[s];
+        const int taps = (mode == DFCSA_TAP_1x1) ? 1 : (mode == DFCSA_TAP_3x3) ? 9 : 4;
+        for (int t = 0; t < taps; ++t) {
+          int c1, c2, c3, c4;
+          if (mode == DFCSA_TAP_2x2S2) { c1 = t & 1; c2 = tc.w0; c3 = t >> 1; c4 = tc.h0; }
+          else if (mode == DFCSA_TAP_3x3) { c1 = tc.w0 + (t % 3) - 1; c2 = tc.h0 + (t / 3) - 1; c3 = tc.tb; c4 = 0; }
+          else { c1 = tc.w0; c2 = tc.h0; c3 = tc.tb; c4 = 0; }
+          for (int kb = 0; kb < a.seg_kb[s]; ++kb) {
+            if (lane == 0) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              uint8_t* sa = smem + stage * stage_bytes;
+              tma_load_5d(sa, ma, &full_bar[stage], kb * kBlockK, c1, c2, c3, c4);
+              tma_load_2d(sa + kABytes, &map_b, &full_bar[stage], kb_global * kBlockK, tc.nt * a.block_n);
+            }
+            __syncwarp();
+            ++kb_global;
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    int as = 0; uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * kAccStride;
+      for (int kb = 0; kb < a.total_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_f16(d_tmem, da, db, a.idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == a.total_kb - 1) umma_commit(&tmem_full_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      as ^= 1; if (as == 0) aphase ^= 1;
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;              // == warp % 4: the TMEM lane quarter this warp may read
+    const int r = ew * 32 + lane;         // tile row == TMEM lane
+    const int et = threadIdx.x - 128;
+    const bool flush_each = a.n_tiles_n > 1;
+    int as = 0; uint32_t aphase = 0;
+    int last_nt = 0;
+    bool have_stats = false;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord tc = tile_coord(a, tile);
+      const int dw = r % a.w_t, dh = r / a.w_t;
+      const int w = tc.w0 + dw, h = tc.h0 + dh;
+      const bool valid = (r < a.w_t * a.h_t) && (w < a.W) && (h < a.H);
+      long long row_off;
+      if (a.out_mode == DFCSA_OUT_CONVT2x2) {
+        // flattened input pixel m -> (b, i, j); quadrant added per chunk below
+        const long long m = (static_cast<long long>(tc.tb) * a.H + h) * a.W + w;
+        const int j = static_cast<int>(m % a.convt_w);
+        const long long t2 = m / a.convt_w;
+        const int i = static_cast<int>(t2 % a.convt_h);
+        const long long b = t2 / a.convt_h;
+        row_off = ((b * 2 * a.convt_h + 2 * i) * (2LL * a.convt_w) + 2 * j);  // pixel index of quadrant (0,0)
+      } else {
+        row_off = (static_cast<long long>(tc.tb) * a.H + h) * a.W + w;
+      }
+      mbar_wait(&tmem_full_bar[as], aphase);
+      tc_fence_after();
+      const int nchunks = a.block_n / 32;
+      for (int ch = 0; ch < nchunks; ++ch) {
+        const int n0 = tc.nt * a.block_n + ch * 32;
+        if (n0 >= a.N) break;
+        const int ncols = min(32, a.N - n0);
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + as * kAccStride + ch * 32 + (static_cast<uint32_t>(ew * 32) << 16), raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(raw[i]);
+        long long pix = row_off;
+        int cn = n0;
+        if (a.out_mode == DFCSA_OUT_CONVT2x2) {
+          const int q = n0 / a.convt_co;
+          cn = n0 - q * a.convt_co;
+          pix += (q >> 1) * (2LL * a.convt_w) + (q & 1);
+        }
+        if (a.bias != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(a.bias + cn + i);
+        }
+        if (valid) {
+          if (a.out_dtype == DFCSA_F16)
+            store_chunk<__half>(reinterpret_cast<__half*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
+          else if (a.out_dtype == DFCSA_BF16)
+            store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
+          else
+            store_chunk<float>(reinterpret_cast<float*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
+        }
+        if (a.stats != nullptr) {
+          float sq[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+          const float s1 = transpose_reduce32(v, lane);
+          const float s2 = transpose_reduce32(sq, lane);
+          atomicAdd(&s_stats[0][ch * 32 + lane], s1);
+          atomicAdd(&s_stats[1][ch * 32 + lane], s2);
+          have_stats = true;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      as ^= 1; if (as == 0) aphase ^= 1;
+      last_nt = tc.nt;
+      if (a.stats != nullptr && flush_each) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int c = et; c < a.block_n; c += 128) {
+          const int n = last_nt * a.block_n + c;
+          if (n < a.N) {
+            atomicAdd(a.stats + n, static_cast<double>(s_stats[0][c]));
+            atomicAdd(a.stats + a.N + n, static_cast<double>(s_stats[1][c]));
+          }
+          s_stats[0][c] = 0.f; s_stats[1][c] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+    (void)have_stats;
+  }
+  // final per-CTA flush of the BatchNorm partial sums (single n-tile case)
+  tc_fence_before();
+  __syncthreads();
+  if (a.stats != nullptr && a.n_tiles_n == 1 && blockIdx.x < total_tiles) {
+    for (int c = threadIdx.x; c < a.block_n; c += blockDim.x) {
+      if (c < a.N) {
+        atomicAdd(a.stats + c, static_cast<double>(s_stats[0][c]));
+        atomicAdd(a.stats + a.N + c, static_cast<double>(s_stats[1][c]));
+      }
+    }
+  }
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+std::once_flag g_attr_once;
+
+void pick_spatial_tile(int H, int W, int& w_t, int& h_t) {
+  double best = -1.0;
+  w_t = 1; h_t = 1;
+  for (int wt = 1; wt <= std::min(W, kBlockM); ++wt) {
+    int ht = std::min(H, kBlockM / wt);
+    if (ht < 1) continue;
+    long long tiles = static_cast<long long>((W + wt - 1) / wt) * ((H + ht - 1) / ht);
+    double eff = static_cast<double>(H) * W / (static_cast<double>(tiles) * kBlockM);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && wt > w_t)) { best = eff; w_t = wt; h_t = ht; }
+  }
+}
+
+}  // namespace
+
+int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
+  DFCSA_CHECK_ARG(p->n_seg >= 1 && p->n_seg <= 3, "conv_gemm_tc: n_seg must be 1..3");
+  DFCSA_CHECK_ARG(p->src_dtype != DFCSA_F32 && p->w_dtype != DFCSA_F32, "conv_gemm_tc: 16-bit operands required");
+  DFCSA_CHECK_ARG(p->N % 8 == 0 && p->ld_out % 8 == 0, "conv_gemm_tc: N and ld_out must be multiples of 8");
+  DFCSA_CHECK_ARG((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
+                  "conv_gemm_tc: out / w must be 16-byte aligned");
+  const long long Mtot = static_cast<long long>(p->B) * p->H * p->W;
+  DFCSA_CHECK_ARG(Mtot > 0, "conv_gemm_tc: empty problem");
+  bool any3 = false, any2 = false;
+  int ktot = 0;
+  for (int s = 0; s < p->n_seg; ++s) {
+    const dfcsa_seg_t& sg = p->seg[s];
+    DFCSA_CHECK_ARG(sg.channels > 0 && sg.channels % 64 == 0, "conv_gemm_tc: segment channels must be a multiple of 64 (got %d)", sg.channels);
+    DFCSA_CHECK_ARG(sg.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(sg.ptr) & 15) == 0, "conv_gemm_tc: segment pitch/alignment");
+    any3 |= sg.tap_mode == DFCSA_TAP_3x3;
+    any2 |= sg.tap_mode == DFCSA_TAP_2x2S2;
+    ktot += sg.channels * (sg.tap_mode == DFCSA_TAP_1x1 ? 1 : sg.tap_mode == DFCSA_TAP_3x3 ? 9 : 4);
+  }
+  DFCSA_CHECK_ARG(!(any2 && (any3 || p->n_seg != 1)), "conv_gemm_tc: a 2x2s2 segment must be the only segment");
+  if (p->out_mode == DFCSA_OUT_CONVT2x2) {
+    DFCSA_CHECK_ARG(!any3 && !any2 && p->N % 4 == 0 && (p->N / 4) % 32 == 0 && !p->accumulate,
+                    "conv_gemm_tc: ConvT output needs 1x1 taps and Co %% 32 == 0");
+  }
+
+  ConvTcArgs a{};
+  a.n_seg = p->n_seg;
+  a.total_kb = ktot / 64;
+  a.N = p->N;
+  // ---- tile geometry ----
+  if (any3) {
+    a.H = p->H; a.W = p->W; a.tiles_b = p->B;
+    pick_spatial_tile(p->H, p->W, a.w_t, a.h_t);
+  } else if (any2) {
+    a.H = p->B * p->H; a.W = p->W; a.tiles_b = 1;
+    pick_spatial_tile(a.H, a.W, a.w_t, a.h_t);
+  } else {
+    DFCSA_CHECK_ARG(Mtot < (1LL << 31), "conv_gemm_tc: too many pixels");
+    a.H = 1; a.W = static_cast<int>(Mtot); a.tiles_b = 1; a.w_t = kBlockM; a.h_t = 1;
+  }
+  a.tiles_w = (a.W + a.w_t - 1) / a.w_t;
+  a.tiles_h = (a.H + a.h_t - 1) / a.h_t;
+  a.a_box_bytes = a.w_t * a.h_t * 128;
+  const long long m_tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
+
+  // ---- n tiling ----
+  const int sms = num_sms();
+  int block_n;
+  if (p->N <= 256) block_n = (p->N + 31) / 32 * 32;
+  else {
+    int best_pad = 1 << 30; block_n = 256;
+    for (int bn = 256; bn >= 128; bn -= 32) {
+      int pad = (p->N + bn - 1) / bn * bn;
+      if (pad < best_pad) { best_pad = pad; block_n = bn; }
+    }
+  }
+  while (block_n > 64 && block_n % 64 == 0 && m_tiles * ((p->N + block_n - 1) / block_n) < sms) block_n /= 2;
+  a.block_n = block_n;
+  a.n_tiles_n = (p->N + block_n - 1) / block_n;
+  const int stage_bytes = kABytes + block_n * 128;
+  a.stages = std::min(kMaxStages, (kSmemBudget - 2048) / stage_bytes);
+  a.idesc = umma_idesc_f16(kBlockM, block_n, umma_fmt(p->src_dtype), umma_fmt(p->w_dtype), 0, 0);
+
+  // ---- tensor maps ----
+  CUtensorMap maps[3];
+  for (int s = 0; s < 3; ++s) {
+    const dfcsa_seg_t& sg = p->seg[s < p->n_seg ? s : 0];
+    a.seg_kb[s] = sg.channels / 64;
+    a.seg_mode[s] = sg.tap_mode;
+    const uint64_t ldb = static_cast<uint64_t>(sg.ld) * 2;
+    uint64_t dims[5], strides[4];
+    uint32_t box[5];
+    if (sg.tap_mode == DFCSA_TAP_2x2S2) {
+      // source grid (B, 2H, 2W): (c, dj, j, di, b*H+i)
+      dims[0] = sg.channels; dims[1] = 2; dims[2] = p->W; dims[3] = 2; dims[4] = static_cast<uint64_t>(p->B) * p->H;
+      strides[0] = ldb; strides[1] = 2 * ldb; strides[2] = 2ull * p->W * ldb; strides[3] = 4ull * p->W * ldb;
+      box[0] = 64; box[1] = 1; box[2] = a.w_t; box[3] = 1; box[4] = a.h_t;
+    } else if (any3) {
+      dims[0] = sg.channels; dims[1] = p->W; dims[2] = p->H; dims[3] = p->B; dims[4] = 1;
+      strides[0] = ldb; strides[1] = static_cast<uint64_t>(p->W) * ldb; strides[2] = static_cast<uint64_t>(p->H) * p->W * ldb;
+      strides[3] = static_cast<uint64_t>(p->B) * p->H * p->W * ldb;
+      box[0] = 64; box[1] = a.w_t; box[2] = a.h_t; box[3] = 1; box[4] = 1;
+    } else {
+      dims[0] = sg.channels; dims[1] = static_cast<uint64_t>(Mtot); dims[2] = 1; dims[3] = 1; dims[4] = 1;
+      strides[0] = ldb; strides[1] = static_cast<uint64_t>(Mtot) * ldb; strides[2] = strides[1]; strides[3] = strides[1];
+      box[0] = 64; box[1] = kBlockM; box[2] = 1; box[3] = 1; box[4] = 1;
+    }
+    int rc = encode_tensor_map(&maps[s], p->src_dtype, 5, sg.ptr, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  CUtensorMap map_b;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(p->N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(block_n)};
+    int rc = encode_tensor_map(&map_b, p->w_dtype, 2, p->w, dims, strides, box, true);
+    if (rc) return rc;
+  }
+
+  a.out = p->out; a.ld_out = p->ld_out; a.out_dtype = p->out_dtype; a.out_mode = p->out_mode;
+  a.accumulate = p->accumulate; a.bias = p->bias; a.stats = p->stats;
+  if (p->out_mode == DFCSA_OUT_CONVT2x2) { a.convt_co = p->N / 4; a.convt_h = p->H; a.convt_w = p->W; }
+
+  const int smem_bytes = a.stages * stage_bytes + 1024;
+  std::call_once(g_attr_once, [] {
+    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  });
+  const long long total_tiles = m_tiles * a.n_tiles_n;
+  const int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
+  conv_tc_kernel<<<grid, 256, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
+  DFCSA_LAUNCH_CHECK("conv_tc_kernel");
+  return DFCSA_OK;
+}
+
+}  // namespace dfcsa

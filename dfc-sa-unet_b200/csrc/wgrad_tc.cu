@@ -1,0 +1,274 @@
+// Convolution weight gradient on tcgen05 (sm_100a).
+//
+//   dw[n, t*C + c] += alpha * sum_m dy[pix_dy(m, t), n] * x[pix_x(m, t), c]
+//
+// The reduction runs over pixels, which are the *rows* of the NHWC tensors, so both operands are MN-major:
+// a TMA box of (64 channels x <=64 pixels) lands as <=64 swizzled 128-byte rows (row = pixel = UMMA K index,
+// 64 contiguous channels = UMMA M/N index).  The 3x3 taps shift the x box by (dh, dw); TMA zero-fills the halo.
+// One CTA per (tap, 128-wide n tile, c tile, pixel split); fp32 partials leave through atomics.
+//   warps 0-3: epilogue (TMEM -> atomicAdd),  warp 4: TMA producer,  warp 5: TMEM alloc + MMA issuer
+#include "common.cuh"
+#include <algorithm>
+#include <mutex>
+
+namespace dfcsa {
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBoxBytes = 64 * 128;          // one (64 ch x 64 px) box
+constexpr int kABytes = 2 * kBoxBytes;       // 128 n
+constexpr int kBMaxBytes = 4 * kBoxBytes;    // up to 256 c
+constexpr int kStageBytes = kABytes + kBMaxBytes;
+
+struct WgradTcArgs {
+  int taps, n_tiles, c_tiles, splits;
+  int block_c;             // multiple of 64, <= 256
+  int N, C;
+  int tiles_w, tiles_h, tiles_b, w_t, h_t;   // pixel-block geometry
+  long long pix_blocks, blocks_per_split;
+  int x_mode, dy_mode;
+  int box_bytes;           // bytes one TMA box delivers (w_t*h_t*128)
+  float* dw; long long ld_dw;
+  const float* alpha;
+  uint32_t idesc;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(192, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                const __grid_constant__ WgradTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  // work item
+  int id = blockIdx.x;
+  const int split = id % a.splits; id /= a.splits;
+  const int ct = id % a.c_tiles;   id /= a.c_tiles;
+  const int nt = id % a.n_tiles;   id /= a.n_tiles;
+  const int tap = id;
+  const int n0 = nt * 128;
+  const int c0 = ct * a.block_c;
+  const long long pb_beg = split * a.blocks_per_split;
+  const long long pb_end = min(a.pix_blocks, pb_beg + a.blocks_per_split);
+  const int n_boxes_a = (a.N - n0 > 64) ? 2 : 1;
+  const int n_boxes_b = min(a.block_c, a.C - c0) / 64;
+
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* p = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += blockDim.x) p[i] = z;
+    fence_proxy_async();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    mbar_init(&done_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 5) tmem_alloc(&tmem_base_smem, a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>((n_boxes_a + n_boxes_b) * a.box_bytes);
+    for (long long pb = pb_beg; pb < pb_end; ++pb) {
+      const int tw = static_cast<int>(pb % a.tiles_w);
+      const long long r = pb / a.tiles_w;
+      const int th = static_cast<int>(r % a.tiles_h);
+      const int tb = static_cast<int>(r / a.tiles_h);
+      const int w0 = tw * a.w_t, h0 = th * a.h_t;
+      if (lane == 0) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+        uint8_t* sa = smem + stage * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        for (int j = 0; j < n_boxes_a; ++j) {
+          if (a.dy_mode == DFCSA_TAP_2x2S2)
+            tma_load_5d(sa + j * kBoxBytes, &map_dy, &full_bar[stage], n0 + j * 64, tap & 1, w0, tap >> 1, h0);
+          else
+            tma_load_5d(sa + j * kBoxBytes, &map_dy, &full_bar[stage], n0 + j * 64, w0, h0, tb, 0);
+        }
+        for (int j = 0; j < n_boxes_b; ++j) {
+          if (a.x_mode == DFCSA_TAP_3x3)
+            tma_load_5d(sb + j * kBoxBytes, &map_x, &full_bar[stage], c0 + j * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, tb, 0);
+          else
+            tma_load_5d(sb + j * kBoxBytes, &map_x, &full_bar[stage], c0 + j * 64, w0, h0, tb, 0);
+        }
+      }
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    bool first = true;
+    for (long long pb = pb_beg; pb < pb_end; ++pb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // 16 pixels (rows) per instruction = 2 KiB
+          const uint64_t da = umma_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
+          const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
+          umma_f16(tmem_base, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      first = false;
+      __syncwarp();
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0) umma_commit(&done_bar);
+    __syncwarp();
+  } else {
+    // ===================== epilogue =====================
+    if (pb_end > pb_beg) {
+      mbar_wait(&done_bar, 0);
+      tc_fence_after();
+      const int n = n0 + warp * 32 + lane;
+      const float alpha = a.alpha ? __ldg(a.alpha) : 1.f;
+      const int ccols = min(a.block_c, a.C - c0);
+      for (int ch = 0; ch * 32 < ccols; ++ch) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + ch * 32 + (static_cast<uint32_t>(warp * 32) << 16), raw);
+        tmem_ld_wait();
+        if (n < a.N) {
+          float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap) * a.C + c0 + ch * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (ch * 32 + i < ccols) atomicAdd(dst + i, alpha * __uint_as_float(raw[i]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, a.tmem_cols);
+  }
+}
+
+std::once_flag g_attr_once;
+
+void pick_patch(int H, int W, int& w_t, int& h_t) {
+  double best = -1.0;
+  w_t = 1; h_t = 1;
+  for (int wt = 1; wt <= std::min(W, 64); ++wt) {
+    int ht = std::min(H, 64 / wt);
+    if (ht < 1) continue;
+    long long tiles = static_cast<long long>((W + wt - 1) / wt) * ((H + ht - 1) / ht);
+    double eff = static_cast<double>(H) * W / (static_cast<double>(tiles) * 64);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && wt > w_t)) { best = eff; w_t = wt; h_t = ht; }
+  }
+}
+
+}  // namespace
+
+int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
+  DFCSA_CHECK_ARG(p->x_dtype != DFCSA_F32 && p->dy_dtype != DFCSA_F32, "conv_wgrad_tc: 16-bit operands required");
+  DFCSA_CHECK_ARG(p->C % 64 == 0 && p->N % 8 == 0, "conv_wgrad_tc: C must be a multiple of 64 and N of 8 (C=%d N=%d)", p->C, p->N);
+  DFCSA_CHECK_ARG(p->ld_x % 8 == 0 && p->ld_dy % 8 == 0, "conv_wgrad_tc: pitches must be multiples of 8");
+  DFCSA_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->dy) & 15) == 0,
+                  "conv_wgrad_tc: operands must be 16-byte aligned");
+  const long long Mtot = static_cast<long long>(p->B) * p->H * p->W;
+  DFCSA_CHECK_ARG(Mtot > 0 && Mtot < (1LL << 31), "conv_wgrad_tc: bad pixel count");
+
+  WgradTcArgs a{};
+  a.N = p->N; a.C = p->C;
+  a.x_mode = p->x_tap_mode; a.dy_mode = p->dy_tap_mode;
+  a.taps = p->x_tap_mode == DFCSA_TAP_3x3 ? 9 : (p->dy_tap_mode == DFCSA_TAP_2x2S2 ? 4 : 1);
+  a.n_tiles = (p->N + 127) / 128;
+  if (p->C <= 256) a.block_c = p->C;
+  else {
+    int best_pad = 1 << 30; a.block_c = 256;
+    for (int bc = 256; bc >= 128; bc -= 64) {
+      int pad = (p->C + bc - 1) / bc * bc;
+      if (pad < best_pad) { best_pad = pad; a.block_c = bc; }
+    }
+  }
+  a.c_tiles = (p->C + a.block_c - 1) / a.block_c;
+
+  // ---- pixel-block geometry and tensor maps ----
+  CUtensorMap map_dy, map_x;
+  const uint64_t ldx = static_cast<uint64_t>(p->ld_x) * 2, ldy = static_cast<uint64_t>(p->ld_dy) * 2;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+  if (p->x_tap_mode == DFCSA_TAP_3x3) {
+    pick_patch(p->H, p->W, a.w_t, a.h_t);
+    a.tiles_w = (p->W + a.w_t - 1) / a.w_t; a.tiles_h = (p->H + a.h_t - 1) / a.h_t; a.tiles_b = p->B;
+    box[0] = 64; box[1] = a.w_t; box[2] = a.h_t; box[3] = 1; box[4] = 1;
+    dims[0] = p->C; dims[1] = p->W; dims[2] = p->H; dims[3] = p->B; dims[4] = 1;
+    strides[0] = ldx; strides[1] = p->W * ldx; strides[2] = static_cast<uint64_t>(p->H) * p->W * ldx; strides[3] = static_cast<uint64_t>(Mtot) * ldx;
+    int rc = encode_tensor_map(&map_x, p->x_dtype, 5, p->x, dims, strides, box, true);
+    if (rc) return rc;
+    dims[0] = p->N;
+    strides[0] = ldy; strides[1] = p->W * ldy; strides[2] = static_cast<uint64_t>(p->H) * p->W * ldy; strides[3] = static_cast<uint64_t>(Mtot) * ldy;
+    rc = encode_tensor_map(&map_dy, p->dy_dtype, 5, p->dy, dims, strides, box, true);
+    if (rc) return rc;
+  } else if (p->dy_tap_mode == DFCSA_TAP_2x2S2) {
+    const int Hm = p->B * p->H;
+    pick_patch(Hm, p->W, a.w_t, a.h_t);
+    a.tiles_w = (p->W + a.w_t - 1) / a.w_t; a.tiles_h = (Hm + a.h_t - 1) / a.h_t; a.tiles_b = 1;
+    box[0] = 64; box[1] = a.w_t; box[2] = a.h_t; box[3] = 1; box[4] = 1;
+    dims[0] = p->C; dims[1] = p->W; dims[2] = Hm; dims[3] = 1; dims[4] = 1;
+    strides[0] = ldx; strides[1] = p->W * ldx; strides[2] = static_cast<uint64_t>(Mtot) * ldx; strides[3] = strides[2];
+    int rc = encode_tensor_map(&map_x, p->x_dtype, 5, p->x, dims, strides, box, true);
+    if (rc) return rc;
+    // dy on the (B, 2H, 2W) grid: (n, dj, j, di, b*H+i)
+    dims[0] = p->N; dims[1] = 2; dims[2] = p->W; dims[3] = 2; dims[4] = Hm;
+    strides[0] = ldy; strides[1] = 2 * ldy; strides[2] = 2ull * p->W * ldy; strides[3] = 4ull * p->W * ldy;
+    box[0] = 64; box[1] = 1; box[2] = a.w_t; box[3] = 1; box[4] = a.h_t;
+    rc = encode_tensor_map(&map_dy, p->dy_dtype, 5, p->dy, dims, strides, box, true);
+    if (rc) return rc;
+  } else {
+    a.w_t = 64; a.h_t = 1;
+    a.tiles_w = static_cast<int>((Mtot + 63) / 64); a.tiles_h = 1; a.tiles_b = 1;
+    box[0] = 64; box[1] = 64; box[2] = 1; box[3] = 1; box[4] = 1;
+    dims[0] = p->C; dims[1] = Mtot; dims[2] = 1; dims[3] = 1; dims[4] = 1;
+    strides[0] = ldx; strides[1] = static_cast<uint64_t>(Mtot) * ldx; strides[2] = strides[1]; strides[3] = strides[1];
+    int rc = encode_tensor_map(&map_x, p->x_dtype, 5, p->x, dims, strides, box, true);
+    if (rc) return rc;
+    dims[0] = p->N;
+    strides[0] = ldy; strides[1] = static_cast<uint64_t>(Mtot) * ldy; strides[2] = strides[1]; strides[3] = strides[1];
+    rc = encode_tensor_map(&map_dy, p->dy_dtype, 5, p->dy, dims, strides, box, true);
+    if (rc) return rc;
+  }
+  a.box_bytes = a.w_t * a.h_t * 128;
+  a.pix_blocks = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
+
+  const long long items = static_cast<long long>(a.taps) * a.n_tiles * a.c_tiles;
+  long long splits = std::max<long long>(1, (2LL * num_sms() + items - 1) / items);
+  splits = std::min(splits, std::max<long long>(1, a.pix_blocks / 4));
+  a.blocks_per_split = (a.pix_blocks + splits - 1) / splits;
+  a.splits = static_cast<int>((a.pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split);
+  a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
+  a.idesc = umma_idesc_f16(128, a.block_c, umma_fmt(p->dy_dtype), umma_fmt(p->x_dtype), 1, 1);
+  a.tmem_cols = a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256;
+
+  const int smem_bytes = kStages * kStageBytes + 1024;
+  std::call_once(g_attr_once, [smem_bytes] {
+    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  });
+  const long long grid = items * a.splits;
+  DFCSA_CHECK_ARG(grid < (1LL << 31), "conv_wgrad_tc: grid too large");
+  wgrad_tc_kernel<<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, a);
+  DFCSA_LAUNCH_CHECK("wgrad_tc_kernel");
+  return DFCSA_OK;
+}
+
+}  // namespace dfcsa

@@ -1,0 +1,115 @@
+"""ctypes binding of libdfcsa.so (include/dfcsa.h).
+
+The library is the product: there is no CPU or PyTorch fallback here.  If the shared object is missing the
+import of any compute entry point raises, and every non-zero return code becomes a RuntimeError carrying
+dfcsa_last_error().
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libdfcsa.so")
+
+F32, F16, BF16 = 0, 1, 2
+TAP_1x1, TAP_3x3, TAP_2x2S2 = 0, 1, 2
+OUT_DIRECT, OUT_CONVT2x2 = 0, 1
+BACKEND_TC, BACKEND_SIMT = 0, 1
+
+_TORCH2DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+def dt(t):
+    return _TORCH2DT[t.dtype]
+
+
+class Seg(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("channels", C.c_int32), ("tap_mode", C.c_int32)]
+
+
+class ConvParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_seg", C.c_int32),
+        ("seg", Seg * 3),
+        ("src_dtype", C.c_int32), ("w_dtype", C.c_int32),
+        ("w", C.c_void_p), ("N", C.c_int32), ("out_dtype", C.c_int32),
+        ("out", C.c_void_p), ("ld_out", C.c_int64),
+        ("out_mode", C.c_int32), ("accumulate", C.c_int32),
+        ("bias", C.c_void_p), ("stats", C.c_void_p),
+    ]
+
+
+class WgradParams(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+        ("x", C.c_void_p), ("ld_x", C.c_int64), ("C", C.c_int32), ("x_dtype", C.c_int32), ("x_tap_mode", C.c_int32),
+        ("dy", C.c_void_p), ("ld_dy", C.c_int64), ("N", C.c_int32), ("dy_dtype", C.c_int32), ("dy_tap_mode", C.c_int32),
+        ("dw", C.c_void_p), ("ld_dw", C.c_int64),
+        ("alpha", C.c_void_p),
+    ]
+
+
+class SgemmParams(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("A", C.c_void_p), ("a_b", C.c_int64), ("a_m", C.c_int64), ("a_k", C.c_int64),
+        ("B", C.c_void_p), ("b_b", C.c_int64), ("b_k", C.c_int64), ("b_n", C.c_int64),
+        ("C", C.c_void_p), ("c_b", C.c_int64), ("c_m", C.c_int64), ("c_n", C.c_int64),
+        ("bias_n", C.c_void_p), ("bias_m", C.c_void_p),
+        ("alpha", C.c_float), ("beta", C.c_float),
+    ]
+
+
+class ParamDesc(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("n", C.c_int64)]
+
+
+# every symbol include/dfcsa.h declares (the CPU test checks the .so exports exactly these)
+SYMBOLS = [
+    "dfcsa_version", "dfcsa_last_error", "dfcsa_device_ok",
+    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_sgemm",
+    "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd",
+    "dfcsa_bn_finalize", "dfcsa_bn_eval_affine",
+    "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd",
+    "dfcsa_block_out_bwd_reduce", "dfcsa_bn_bwd_apply", "dfcsa_gate_mix_bwd_reduce", "dfcsa_gate_mix_bwd_apply",
+    "dfcsa_branch_bwd_reduce1", "dfcsa_branch_bwd_reduce2", "dfcsa_branch_bwd_apply", "dfcsa_bn_param_grads",
+    "dfcsa_nchw_to_nhwc", "dfcsa_nhwc_to_nchw", "dfcsa_colsum", "dfcsa_cast2d",
+    "dfcsa_bce_dice_sums", "dfcsa_bce_dice_finalize", "dfcsa_bce_dice_bwd",
+    "dfcsa_grad_sumsq", "dfcsa_sgd_step",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libdfcsa.so (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  dfcsa has no CPU or PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        l.dfcsa_last_error.restype = C.c_char_p
+        l.dfcsa_version.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().dfcsa_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libdfcsa {what} failed (code {rc}): {msg}")
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dfcsa kernels take CUDA tensors only (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())

@@ -1,0 +1,272 @@
+/* dfcsa.h — flat C ABI of libdfcsa.so: the B200 (sm_100a) kernels behind the DFC-SA-Res-Block hot path.
+ *
+ * The reference (YukiHataRin/DFC-SA-UNet) is pure PyTorch and has no FFI of its own; every entry point below
+ * replaces a group of ATen call sites on the reference's hot path and cites them (file:line, relative to the
+ * reference root).  A maintainer binds these with ctypes; the Python package
+ * dfc-sa-unet_b200/dfcsa does exactly that.
+ *
+ * Conventions
+ *   - every pointer is a CUDA device pointer owned by the caller (PyTorch's allocator); the library never
+ *     allocates or frees device memory and keeps no pointer past the call;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*) and never synchronises, so
+ *     calls are legal under CUDA-graph capture;
+ *   - return value 0 = success, otherwise a DFCSA_ERR_* code; dfcsa_last_error() gives the message for the
+ *     calling thread.  No exception crosses the boundary and there is no CPU fallback;
+ *   - activations are NHWC "pixel-major" matrices: element (pixel m, channel c) lives at base[m*ld + c] where
+ *     m = (b*H + h)*W + w and ld >= C is the pixel pitch in elements (a channel slice of a wider concat buffer
+ *     is just base+offset with the wide pitch: torch.cat on the reference path becomes zero-copy);
+ *   - 16-bit tensors: DFCSA_F16 for forward activations / forward weights, DFCSA_BF16 for gradients.
+ */
+#ifndef DFCSA_H_
+#define DFCSA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFCSA_VERSION 100
+
+enum { DFCSA_OK = 0, DFCSA_ERR_BAD_ARG = 1, DFCSA_ERR_CUDA = 2, DFCSA_ERR_UNSUPPORTED = 3 };
+enum { DFCSA_F32 = 0, DFCSA_F16 = 1, DFCSA_BF16 = 2 };
+/* how the K axis of one input segment walks the source tensor */
+enum {
+  DFCSA_TAP_1x1 = 0,   /* one tap, same pixel */
+  DFCSA_TAP_3x3 = 1,   /* 9 taps, tap t reads pixel (h + t/3 - 1, w + t%3 - 1), zero outside the image */
+  DFCSA_TAP_2x2S2 = 2  /* 4 taps, tap t reads pixel (2h + t/2, 2w + t%2) of a (2H x 2W) source (ConvT dgrad) */
+};
+enum { DFCSA_OUT_DIRECT = 0, DFCSA_OUT_CONVT2x2 = 1 };
+enum { DFCSA_BACKEND_TC = 0, DFCSA_BACKEND_SIMT = 1 };
+
+int         dfcsa_version(void);
+const char* dfcsa_last_error(void);
+/* 1 if the current device is sm_100 (tcgen05 kernels usable) */
+int         dfcsa_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution:  out[m, n] (+)= sum_seg sum_tap sum_c  src_seg[pix(m, tap), c] * w[n, koff(seg,tap) + c]
+ * Replaces F.conv2d 3x3 / 1x1 forward and their input-gradient (dgrad) on
+ *   models/unet_dfc_sa_res.py:58 (conv_branch), :66 (attn_branch 1x1), :74 (gate), :81 (fusion_conv),
+ *   :88 (residual_conv) and nn.ConvTranspose2d forward/dgrad at :147,150,153,156.
+ * w is "packed": [N, Ktot] with K contiguous, K ordered (segment, tap, channel)  (see dfcsa_pack_weights).
+ * Backend TC: tcgen05.mma (kind::f16, fp32 accumulate in TMEM), operands staged by TMA, persistent over tiles.
+ *             Requires 16-bit src/w, every segment's channel count % 64 == 0, ld % 8 == 0, N % 8 == 0.
+ * Backend SIMT: fp32 FMA tiles; any channel counts / dtypes (the Ci=3 first layer, tiny test networks).
+ * Optional epilogue: + bias[n]; per-channel double-precision sum / sum-of-squares of the fp32 result
+ * (BatchNorm batch statistics, reference :60,67,75,82) accumulated with atomics into stats[0:N], stats[N:2N].
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr;     /* source activation / gradient */
+  int64_t     ld;      /* pixel pitch in elements */
+  int32_t     channels;/* K channels contributed per tap */
+  int32_t     tap_mode;/* DFCSA_TAP_* */
+} dfcsa_seg_t;
+
+typedef struct {
+  int32_t B, H, W;          /* output pixel grid; M = B*H*W */
+  int32_t n_seg;
+  dfcsa_seg_t seg[3];
+  int32_t src_dtype;        /* dtype of all segments */
+  int32_t w_dtype;          /* dtype of w (16-bit for TC; F32 for SIMT) */
+  const void* w;            /* packed weights [N, Ktot] */
+  int32_t N;
+  int32_t out_dtype;
+  void*   out;
+  int64_t ld_out;
+  int32_t out_mode;         /* DFCSA_OUT_DIRECT, or DFCSA_OUT_CONVT2x2: n = q*Co + co goes to pixel (2h+q/2, 2w+q%2), channel co */
+  int32_t accumulate;       /* out += result (read-modify-write) */
+  const float* bias;        /* optional: [N] (DIRECT) or [Co] (CONVT2x2) */
+  double* stats;            /* optional: [2*N] */
+} dfcsa_conv_params_t;
+
+int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Weight gradient:  dw[n, tap*C + c] += alpha * sum_m  dy[pix_dy(m, tap'), n] * x[pix_x(m, tap), c]
+ * Replaces the weight-gradient half of conv2d / conv_transpose2d backward for the call sites above.
+ *   x_tap_mode  = DFCSA_TAP_3x3 : 3x3 conv weight grad (x shifted by the tap), dy at the output pixel
+ *   x_tap_mode  = DFCSA_TAP_1x1 and dy_tap_mode = DFCSA_TAP_1x1 : 1x1 conv
+ *   dy_tap_mode = DFCSA_TAP_2x2S2 : ConvTranspose2d 2x2/s2 (dy on the (2H x 2W) grid, x on the (H x W) grid)
+ * dw is fp32 [N, taps*C] (row pitch ld_dw) and is accumulated with atomics: zero it first.
+ * Backend TC: both operands are MN-major TMA tiles (pixels on the UMMA K axis), split over pixel ranges.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t B, H, W;          /* pixel grid of x */
+  const void* x;  int64_t ld_x;  int32_t C;  int32_t x_dtype;  int32_t x_tap_mode;
+  const void* dy; int64_t ld_dy; int32_t N;  int32_t dy_dtype; int32_t dy_tap_mode;
+  float*  dw; int64_t ld_dw;
+  const float* alpha;       /* optional device scalar multiplier */
+} dfcsa_wgrad_params_t;
+
+int dfcsa_conv_wgrad(const dfcsa_wgrad_params_t* p, int backend, void* stream);
+
+/* dst[(i0*D1 + i1)*D2 + i2] = scale * src[i0*s0 + i1'*s1 + i2*s2], i1' = flip ? D1-1-i1 : i1.
+ * Re-lays fp32 master weights ([Co,Ci,kh,kw], ConvT [Ci,Co,2,2]) into the packed K-major GEMM operands
+ * (forward: [Co,(tap,ci)]; dgrad: [Ci,(flipped tap,co)]) and packed weight gradients back. */
+int dfcsa_permute3(const void* src, int src_dtype, void* dst, int dst_dtype,
+                   int64_t D0, int64_t D1, int64_t D2, int64_t s0, int64_t s1, int64_t s2,
+                   int flip1, const float* scale, void* stream);
+
+/* Strided batched fp32 GEMM  C[b] = alpha * A[b] * B[b] + beta * C[b]  with arbitrary element strides
+ * (transposes are strides).  Used for the pooled attention products, reference
+ * models/unet_dfc_sa_res.py:28-33 (q/k/v 1x1 convs on the pooled map, bmm(Q,K), bmm(V,A^T)) and their backward. */
+typedef struct {
+  int32_t batch, M, N, K;
+  const float* A; int64_t a_b, a_m, a_k;
+  const float* B; int64_t b_b, b_k, b_n;
+  float*       C; int64_t c_b, c_m, c_n;
+  const float* bias_n;      /* optional bias along N */
+  const float* bias_m;      /* optional bias along M */
+  float alpha, beta;
+} dfcsa_sgemm_params_t;
+int dfcsa_sgemm(const dfcsa_sgemm_params_t* p, void* stream);
+
+/* row softmax over the last dim (reference :31) and its backward  dS = A * (dA - rowsum(dA*A)) */
+int dfcsa_softmax_rows(const float* x, float* y, int64_t rows, int32_t cols, void* stream);
+int dfcsa_softmax_rows_bwd(const float* y, const float* dy, float* dx, int64_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d (reference :60,67,75,82; ATen batch_norm semantics: biased variance for normalisation, unbiased
+ * for running_var, momentum 0.1, eps 1e-5).
+ * finalize: from the conv epilogue's double sums -> per-channel scale/shift (y = x*scale + shift), saved
+ *   mean / invstd for backward, running-stat update.  conv_bias (which the conv kernels do not add in front of
+ *   a train-mode BN because it cancels) is folded into the running mean so eval mode stays exact.
+ * eval:     scale/shift from running statistics (+ conv bias).
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfcsa_bn_finalize(const double* stats, int64_t count, int32_t C,
+                      const float* gamma, const float* beta, const float* conv_bias,
+                      float* running_mean, float* running_var, float momentum, float eps,
+                      float* scale, float* shift, float* mean, float* invstd, void* stream);
+int dfcsa_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
+                         const float* running_mean, const float* running_var, float eps,
+                         float* scale, float* shift, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused bandwidth kernels of the DFC-SA block forward (reference models/unet_dfc_sa_res.py:95-116, :20-39).
+ * All activations fp16 NHWC, per-channel BN affine (scale, shift) fp32.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* a = relu(bn2(A0)); pooled = adaptive_avg_pool2d(a, P) (reference :24).  Separable: rows then columns.
+ * tmp is [B, H, P, C] fp32 scratch; pooled is [B, P, P, C] fp32. */
+int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int32_t H, int32_t W, int32_t C,
+                          const float* scale, const float* shift, int32_t P,
+                          float* tmp, float* pooled, void* stream);
+/* L = relu(bn1(L0)) -> z[:, C:2C];  A = gamma*bilinear_up(o) + relu(bn2(A0)) -> z[:, 2C:3C]
+ * (reference :97,:99,:36,:38).  o is [B, P, P, C] fp32. */
+int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a0, int64_t ld_a0,
+                         int32_t B, int32_t H, int32_t W, int32_t C,
+                         const float* scale1, const float* shift1, const float* scale2, const float* shift2,
+                         const float* o, int32_t P, const float* gamma,
+                         void* z, int64_t ld_z, void* stream);
+/* g = sigmoid(bn3(G0)); z[:, 0:C] = g*L + (1-g)*A  (reference :104,:106) */
+int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int32_t C,
+                       const float* scale3, const float* shift3, void* z, int64_t ld_z, void* stream);
+/* y = relu(bn4(F0)) + res_scale*R (reference :110,:114) and optionally yp = maxpool2x2(y) (reference :164) */
+int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r, int64_t ld_r,
+                        int32_t B, int32_t H, int32_t W, int32_t C,
+                        const float* scale4, const float* shift4, const float* res_scale,
+                        void* y, int64_t ld_y, void* yp, int64_t ld_yp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Block backward (autograd of the same lines).  Gradients bf16 NHWC; per-channel reductions in double.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* dy = dskip (optional) + maxpool-backward(dyp) (optional; argmax recomputed from y);
+ * d4 = dy * [bn4(F0) > 0];  red4[0:C] += sum d4, red4[C:2C] += sum d4*xhat4;  *drs += sum dy*R.
+ * dy_out (bf16) receives the combined dy when it has more than one source (may alias dskip). */
+int dfcsa_block_out_bwd_reduce(const void* dskip, int64_t ld_dskip, const void* dyp, int64_t ld_dyp,
+                               const void* y, int64_t ld_y,
+                               const void* f0, int64_t ld_f0, const void* r, int64_t ld_r,
+                               int32_t B, int32_t H, int32_t W, int32_t C,
+                               const float* scale4, const float* shift4, const float* mean4, const float* invstd4,
+                               void* dy_out, int64_t ld_dy, double* red4, double* drs, void* stream);
+/* generic BN(+activation) backward apply:
+ *   d = dy * act'(.)   with act = relu (mode 0: mask from x*scale+shift > 0) or none (mode 2)
+ *   dx = gamma*invstd * (d - red[0:C]/count - xhat * red[C:2C]/count)   (bf16) */
+int dfcsa_bn_bwd_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t M, int32_t C,
+                       const float* scale, const float* shift, const float* mean, const float* invstd,
+                       const float* gamma, const double* red, int32_t act_mode,
+                       void* dx, int64_t ld_dx, void* stream);
+/* gate/mix backward, pass 1: with dz = [df | dL' | dA'] (gradient of the fusion conv input), z = [f | L | A]:
+ *   g = sigmoid(bn3(G0)); dS = df*(L-A)*g*(1-g); red3 += (sum dS, sum dS*xhat3) */
+int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const void* z, int64_t ld_z,
+                              const void* g0, int64_t ld_g0, int64_t M, int32_t C,
+                              const float* scale3, const float* shift3, const float* mean3, const float* invstd3,
+                              double* red3, void* stream);
+/* pass 2: dG0 = gamma3*invstd3*(dS - mean(dS) - xhat3*mean(dS*xhat3)) -> dg0 (bf16);
+ *         dz[:, C:2C] += df*g ; dz[:, 2C:3C] += df*(1-g)   (in place) */
+int dfcsa_gate_mix_bwd_apply(void* dz, int64_t ld_dz, const void* z, int64_t ld_z,
+                             const void* g0, int64_t ld_g0, int64_t M, int32_t C,
+                             const float* scale3, const float* shift3, const float* mean3, const float* invstd3,
+                             const float* gamma3, const double* red3,
+                             void* dg0, int64_t ld_dg0, void* stream);
+/* branch backward, pass 1 (needs the complete dL = dz[:,C:2C], dA = dz[:,2C:3C]):
+ *   red1 += (sum d1, sum d1*xhat1) with d1 = dL*[L>0];
+ *   dgamma += sum dA*U (U = bilinear_up(o));  do = gamma * bilinear_up^T(dA)  ([B,P,P,C] fp32, separable, tmp [B,H,P,C]) */
+int dfcsa_branch_bwd_reduce1(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0,
+                             int32_t B, int32_t H, int32_t W, int32_t C,
+                             const float* scale1, const float* shift1, const float* mean1, const float* invstd1,
+                             const float* o, int32_t P, const float* gamma,
+                             double* red1, double* dgamma, float* tmp, float* d_o, void* stream);
+/* pass 2 (after the pooled-attention backward produced dpooled [B,P,P,C]):
+ *   da = dA + adaptive_avg_pool^T(dpooled);  d2 = da*[a>0];  red2 += (sum d2, sum d2*xhat2) */
+int dfcsa_branch_bwd_reduce2(const void* dz, int64_t ld_dz, const void* a0, int64_t ld_a0,
+                             int32_t B, int32_t H, int32_t W, int32_t C,
+                             const float* scale2, const float* shift2, const float* mean2, const float* invstd2,
+                             const float* dpooled, int32_t P, double* red2, void* stream);
+/* pass 3: dL0, dA0 (bf16) from the two reductions */
+int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0,
+                           const void* a0, int64_t ld_a0, int32_t B, int32_t H, int32_t W, int32_t C,
+                           const float* scale1, const float* shift1, const float* mean1, const float* invstd1,
+                           const float* gamma1, const double* red1,
+                           const float* scale2, const float* shift2, const float* mean2, const float* invstd2,
+                           const float* gamma2, const double* red2,
+                           const float* dpooled, int32_t P,
+                           void* dl0, int64_t ld_dl0, void* da0, int64_t ld_da0, void* stream);
+/* BN affine gradients from a reduction: dgamma = red[C:2C], dbeta = red[0:C] (fp32 out) */
+int dfcsa_bn_param_grads(const double* red, int32_t C, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layout / misc
+ * ---------------------------------------------------------------------------------------------------------- */
+/* NCHW fp32 [B,C,H,W] -> NHWC (dst dtype, pitch ld) and back (reference tensors at the module boundary) */
+int dfcsa_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int64_t ld,
+                       int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+int dfcsa_nhwc_to_nchw(const void* src, int src_dtype, int64_t ld, float* dst,
+                       int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* per-channel column sums of a [M, C] matrix (bias gradients): out[c] += sum_m x[m,c] */
+int dfcsa_colsum(const void* x, int x_dtype, int64_t ld, int64_t M, int32_t C, float* out, void* stream);
+/* y = cast(x) elementwise on [M, C] matrices with pitches */
+int dfcsa_cast2d(const void* x, int x_dtype, int64_t ld_x, void* y, int y_dtype, int64_t ld_y,
+                 int64_t M, int32_t C, void* stream);
+/* dx[m, c] (+)= maxpool2x2 backward of dyp routed to the argmax of y (used when a block is run stand-alone) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * bce_dice loss (reference utils/trainer.py:124 sigmoid; utils/metrics.py:74-78 BCELoss + dice_loss :19-24;
+ * hard metrics :228-236).  sums (double[8]): 0 bce_sum, 1 sum p*t, 2 sum p, 3 sum t, 4 sum [p>.5]*t, 5 sum [p>.5].
+ * from_logits=1: x are logits (p = sigmoid(x)); 0: x are probabilities (the calculate_metrics boundary).
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfcsa_bce_dice_sums(const float* x, const float* t, int64_t n, int from_logits, double* sums, void* stream);
+/* out[0]=loss, out[1]=bce, out[2]=dice_loss, out[3]=hard iou, out[4]=hard dice  (fp32, device) */
+int dfcsa_bce_dice_finalize(const double* sums, int64_t n, float w_bce, float w_dice, float smooth,
+                            float* out, void* stream);
+/* dx = gout * dloss/dx  (wrt logits if from_logits else wrt probabilities); gout optional device scalar */
+int dfcsa_bce_dice_bwd(const float* x, const float* t, int64_t n, int from_logits, const double* sums,
+                       float w_bce, float w_dice, float smooth, const float* gout,
+                       void* dx, int dx_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimizer (reference utils/trainer.py:149 clip_grad_norm_(1.0); train.py:73-78 SGD momentum/weight decay).
+ * Works on a device table of tensor descriptors so one launch covers all 235 parameter tensors.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct { float* w; float* g; float* m; int64_t n; } dfcsa_param_t;
+/* sumsq[0] += sum over all tensors of g^2 (double) */
+int dfcsa_grad_sumsq(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t max_n, double* sumsq, void* stream);
+/* c = min(1, max_norm/(sqrt(sumsq*gscale^2)+1e-6)); g = c*gscale*g + wd*w; m = first ? g : mom*m + g; w -= lr*m */
+int dfcsa_sgd_step(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t max_n, const double* sumsq,
+                   float gscale, float max_norm, float lr, float momentum, float weight_decay, int first_step,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFCSA_H_ */

@@ -1,0 +1,190 @@
+"""Kernel-level parity of the implicit-GEMM convolution, its weight gradient and the weight re-layout.
+
+The tcgen05 path (backend TC) and the fp32 SIMT path are both checked against a plain PyTorch fp32 computation of
+the same op on the same (already 16-bit-rounded) operands, so the only difference left is accumulation order:
+tolerance 2e-3 relative to the output scale for the tensor-core path (fp32 accumulate, 16-bit output rounding).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+
+
+def _pack_fwd(wt):  # [N, C, kh, kw] -> [N, (tap, c)]
+    n, c, kh, kw = wt.shape
+    return wt.permute(0, 2, 3, 1).reshape(n, kh * kw * c).contiguous()
+
+
+def _run_conv(dev, B, H, W, cins, modes, N, backend, src_dt=torch.float16, w_dt=torch.float16, out_dt=torch.float16,
+              bias=False, stats=False, accumulate=False, seed=0):
+    from dfcsa import ops
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    segs, ref = [], 0
+    wparts = []
+    for c, mode in zip(cins, modes):
+        if mode == ops.TAP_2x2S2:
+            x = torch.randn(B, 2 * H, 2 * W, c, generator=g).to(dev).to(src_dt)
+            wt = (torch.randn(N, c, 2, 2, generator=g) / (4 * c) ** 0.5).to(dev).to(w_dt)
+            ref = ref + F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), stride=2)
+            segs.append((x.reshape(-1, c), mode))
+        elif mode == ops.TAP_3x3:
+            x = torch.randn(B, H, W, c, generator=g).to(dev).to(src_dt)
+            wt = (torch.randn(N, c, 3, 3, generator=g) / (9 * c) ** 0.5).to(dev).to(w_dt)
+            ref = ref + F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1)
+            segs.append((x.reshape(-1, c), mode))
+        else:
+            x = torch.randn(B, H, W, c, generator=g).to(dev).to(src_dt)
+            wt = (torch.randn(N, c, 1, 1, generator=g) / c ** 0.5).to(dev).to(w_dt)
+            ref = ref + F.conv2d(x.float().permute(0, 3, 1, 2), wt.float())
+            segs.append((x.reshape(-1, c), mode))
+        wparts.append(_pack_fwd(wt))
+    w = torch.cat(wparts, dim=1).contiguous()
+    if backend == ops.BACKEND_SIMT:
+        w = w.float()
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, N)  # [M, N]
+    bias_t = None
+    if bias:
+        bias_t = torch.randn(N, generator=g).to(dev)
+        ref = ref + bias_t
+    out = torch.zeros(B * H * W, N, device=dev, dtype=out_dt)
+    if accumulate:
+        base = torch.randn(B * H * W, N, generator=g).to(dev).to(out_dt)
+        out.copy_(base)
+        ref = ref + base.float()
+    st = torch.zeros(2 * N, device=dev, dtype=torch.float64) if stats else None
+    ops.conv_gemm(B, H, W, segs, w, N, out, accumulate=accumulate, bias=bias_t, stats=st, backend=backend)
+    torch.cuda.synchronize()
+    err = _rel_err(out, ref)
+    serr = 0.0
+    if stats:
+        s_ref = torch.cat([ref.double().sum(0), (ref.double() ** 2).sum(0)])
+        serr = ((st - s_ref).abs() / (s_ref.abs() + 1e-3 * s_ref.abs().max())).max().item()
+    return err, serr
+
+
+CASES = [
+    # B, H, W, cins, modes(str), N, extras
+    (2, 9, 11, [64], "1", 64, {}),                       # flattened 1x1, M=198 (tail tile)
+    (1, 16, 16, [128], "1", 128, {"stats": True}),
+    (2, 12, 12, [192], "1", 64, {"stats": True}),        # fusion-conv shape at level 1
+    (2, 8, 8, [64], "1", 192, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
+    (2, 8, 8, [64], "1", 384, {}),                       # two n tiles of 192
+    (1, 32, 32, [64], "3", 64, {"stats": True}),         # 3x3, 32x4 spatial tiles
+    (2, 14, 14, [64], "3", 128, {"stats": True}),        # 14x14: partial boxes
+    (1, 28, 28, [128], "3", 64, {}),
+    (1, 56, 56, [64], "3", 64, {"stats": True}),
+    (2, 10, 12, [64, 64, 128], "311", 64, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),  # dgrad: 3 segments
+    (2, 6, 10, [64], "2", 128, {"src_dt": torch.bfloat16, "w_dt": torch.bfloat16, "out_dt": torch.bfloat16}),  # ConvT dgrad gather
+    (1, 16, 16, [128], "1", 64, {"bias": True, "out_dt": torch.float32}),
+    (1, 16, 16, [64], "1", 128, {"accumulate": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
+    (1, 4, 4, [512], "3", 1024, {}),                     # deep K, several n tiles
+]
+_MODE = {"1": 0, "3": 1, "2": 2}
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+@pytest.mark.parametrize("case", CASES, ids=[f"c{i}" for i in range(len(CASES))])
+def test_conv_gemm(cuda, case, backend):
+    B, H, W, cins, modes, N, kw = case
+    err, serr = _run_conv(cuda, B, H, W, cins, [_MODE[m] for m in modes], N, backend, **kw)
+    assert err < 2e-3, f"conv_gemm rel err {err}"
+    assert serr < 2e-3, f"BN statistics rel err {serr}"
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+def test_conv_gemm_mixed_formats(cuda, backend):
+    """fp16 activations x bf16 weights in one kind::f16 MMA (used by the weight-gradient kernel)."""
+    err, _ = _run_conv(cuda, 1, 16, 16, [128], [0], 64, backend, src_dt=torch.float16, w_dt=torch.bfloat16,
+                       out_dt=torch.float32)
+    assert err < 2e-3, f"mixed-format rel err {err}"
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+def test_convt_forward(cuda, backend):
+    """ConvTranspose2d 2x2 stride 2 as one GEMM with a scatter epilogue (reference models/unet_dfc_sa_res.py:147)."""
+    from dfcsa import ops
+    dev = cuda
+    B, H, W, Ci, Co = 2, 7, 9, 128, 64
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, H, W, Ci, generator=g).to(dev).half()
+    wt = (torch.randn(Ci, Co, 2, 2, generator=g) / Ci ** 0.5).to(dev).half()
+    bias = torch.randn(Co, generator=g).to(dev)
+    ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, stride=2).permute(0, 2, 3, 1).reshape(-1, Co)
+    w = wt.permute(2, 3, 1, 0).reshape(4 * Co, Ci).contiguous()  # [(q, co), ci]
+    if backend == 1:
+        w = w.float()
+    out = torch.zeros(B * 2 * H * 2 * W, Co, device=dev, dtype=torch.float16)
+    ops.conv_gemm(B, H, W, [(x.reshape(-1, Ci), 0)], w, 4 * Co, out, out_mode=ops.OUT_CONVT2x2, bias=bias, backend=backend)
+    torch.cuda.synchronize()
+    assert _rel_err(out, ref) < 2e-3
+
+
+WG_CASES = [
+    # B, H, W, C, N, x_mode, dy_mode
+    (2, 9, 11, 64, 64, 0, 0),
+    (1, 16, 16, 128, 128, 0, 0),
+    (2, 8, 8, 192, 64, 0, 0),
+    (1, 8, 8, 64, 256, 0, 0),
+    (1, 32, 32, 64, 64, 1, 0),
+    (2, 14, 14, 64, 128, 1, 0),
+    (1, 28, 28, 128, 64, 1, 0),
+    (2, 6, 10, 128, 64, 0, 2),
+    (1, 4, 4, 512, 128, 1, 0),
+]
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+@pytest.mark.parametrize("case", WG_CASES, ids=[f"w{i}" for i in range(len(WG_CASES))])
+def test_conv_wgrad(cuda, case, backend):
+    from dfcsa import ops
+    dev = cuda
+    B, H, W, Cc, N, xm, dm = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, H, W, Cc, generator=g).to(dev).half()
+    alpha = torch.tensor([0.37], device=dev)
+    if dm == 2:
+        dy = torch.randn(B, 2 * H, 2 * W, N, generator=g).to(dev).bfloat16()
+        # dW[ci, co, q] of conv_transpose2d == weight grad of the stride-2 conv dy -> x
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+        wt = torch.zeros(Cc, N, 2, 2, device=dev, requires_grad=True)
+        y = F.conv_transpose2d(xr, wt, stride=2)
+        (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+        ref = gw.permute(1, 2, 3, 0).reshape(N, 4 * Cc)  # [n, (q, c)]
+        taps = 4
+    else:
+        dy = torch.randn(B, H, W, N, generator=g).to(dev).bfloat16()
+        k = 3 if xm == 1 else 1
+        wt = torch.zeros(N, Cc, k, k, device=dev, requires_grad=True)
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=k // 2)
+        (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+        ref = gw.permute(0, 2, 3, 1).reshape(N, k * k * Cc)
+        taps = k * k
+    ref = ref * 0.37
+    dw = torch.zeros(N, taps * Cc, device=dev)
+    if backend == 0:
+        ops.conv_wgrad(B, H, W, x.reshape(-1, Cc), xm, dy.reshape(-1, N), dm, dw, alpha=alpha, backend=0)
+    else:
+        ops.conv_wgrad(B, H, W, x.reshape(-1, Cc), xm, dy.reshape(-1, N), dm, dw, alpha=alpha, backend=1)
+    torch.cuda.synchronize()
+    assert _rel_err(dw, ref) < 2e-3
+
+
+def test_permute3(cuda):
+    from dfcsa import ops
+    dev = cuda
+    w = torch.randn(24, 40, 3, 3, device=dev)
+    fwd = torch.empty(24, 9 * 40, device=dev, dtype=torch.float16)
+    ops.permute3(w, fwd, (24, 9, 40), (40 * 9, 1, 9))
+    assert torch.equal(fwd, w.permute(0, 2, 3, 1).reshape(24, 360).half())
+    dg = torch.empty(40, 9 * 24, device=dev, dtype=torch.bfloat16)
+    sc = torch.tensor([0.5], device=dev)
+    ops.permute3(w, dg, (40, 9, 24), (9, 1, 40 * 9), flip1=True, scale=sc)
+    ref = (0.5 * w.flip(2, 3)).permute(1, 2, 3, 0).reshape(40, 216).bfloat16()
+    assert torch.equal(dg, ref)
