@@ -23,7 +23,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kMaxStages = 8;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kSmemBudget = 227 * 1024;
+constexpr int kSmemBudget = 227 * 1024 - 4096;   // dynamic part; static barriers / stats live beside it
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                 // TMEM columns between the two accumulators
 
@@ -323,6 +323,8 @@ void pick_spatial_tile(int H, int W, int& w_t, int& h_t) {
 int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->n_seg >= 1 && p->n_seg <= 3, "conv_gemm_tc: n_seg must be 1..3");
   DFCSA_CHECK_ARG(p->src_dtype != DFCSA_F32 && p->w_dtype != DFCSA_F32, "conv_gemm_tc: 16-bit operands required");
+  // measured on B200: a kind::f16 tcgen05.mma with A fp16 and B bf16 (or the reverse) raises an illegal instruction
+  DFCSA_CHECK_ARG(p->src_dtype == p->w_dtype, "conv_gemm_tc: activations and weights must share one 16-bit format");
   DFCSA_CHECK_ARG(p->N % 8 == 0 && p->ld_out % 8 == 0, "conv_gemm_tc: N and ld_out must be multiples of 8");
   DFCSA_CHECK_ARG((reinterpret_cast<uintptr_t>(p->out) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->w) & 15) == 0,
                   "conv_gemm_tc: out / w must be 16-byte aligned");
@@ -379,7 +381,7 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   a.block_n = block_n;
   a.n_tiles_n = (p->N + block_n - 1) / block_n;
   const int stage_bytes = kABytes + block_n * 128;
-  a.stages = std::min(kMaxStages, (kSmemBudget - 2048) / stage_bytes);
+  a.stages = std::min(kMaxStages, (kSmemBudget - 1024) / stage_bytes);
   a.idesc = umma_idesc_f16(kBlockM, block_n, umma_fmt(p->src_dtype), umma_fmt(p->w_dtype), 0, 0);
 
   // ---- tensor maps ----
@@ -423,9 +425,11 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   if (p->out_mode == DFCSA_OUT_CONVT2x2) { a.convt_co = p->N / 4; a.convt_h = p->H; a.convt_w = p->W; }
 
   const int smem_bytes = a.stages * stage_bytes + 1024;
+  static cudaError_t attr_err = cudaSuccess;
   std::call_once(g_attr_once, [] {
-    cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   const long long total_tiles = m_tiles * a.n_tiles_n;
   const int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
   conv_tc_kernel<<<grid, 256, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);

@@ -1,0 +1,978 @@
+// Bandwidth-bound kernels of the DFC-SA block (forward and backward): BatchNorm finalize / apply, ReLU, the
+// adaptive average pool and bilinear up-sample (and their transposes), gating, residual + max-pool, layout moves.
+// Activations fp16, gradients bf16, all arithmetic fp32, per-channel reductions flushed in double.
+// Every kernel walks NHWC so that consecutive threads touch consecutive 16-byte channel vectors of a pixel.
+#include "common.cuh"
+#include <algorithm>
+
+namespace dfcsa {
+namespace {
+
+typedef __half act_t;
+typedef __nv_bfloat16 grad_t;
+
+template <int VEC, typename T> __device__ __forceinline__ void ldv(const T* p, float (&v)[VEC]) {
+  if constexpr (VEC == 8) load8<T>(p, v);
+  else v[0] = Cvt<T>::to_f(p[0]);
+}
+template <int VEC, typename T> __device__ __forceinline__ void stv(T* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 8) store8<T>(p, v);
+  else p[0] = Cvt<T>::from_f(v[0]);
+}
+template <int VEC> __device__ __forceinline__ void ldf(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 8) load8<float>(p, v);
+  else v[0] = p[0];
+}
+
+static inline bool vec8_ok(int C, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
+  if (C % 8) return false;
+  for (long long l : lds) if (l % 8) return false;
+  for (const void* p : ptrs) if (p && (reinterpret_cast<uintptr_t>(p) & 15)) return false;
+  return true;
+}
+
+// adaptive_avg_pool2d window of output index i: [lo, hi)
+__device__ __forceinline__ void pool_win(int i, int s, int P, int& lo, int& hi) {
+  lo = (i * s) / P;
+  hi = ((i + 1) * s + P - 1) / P;
+}
+// windows containing source index y: [ilo, ihi]
+__device__ __forceinline__ void pool_win_of(int y, int s, int P, int& ilo, int& ihi) {
+  ilo = (y * P) / s;
+  ihi = ((y + 1) * P - 1) / s;
+  if (ihi > P - 1) ihi = P - 1;
+}
+// bilinear, align_corners=False: source taps of destination index d (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void bilerp_taps(int d, int P, int s, int& i0, int& i1, float& l1) {
+  const float scale = static_cast<float>(P) / static_cast<float>(s);
+  float src = scale * (static_cast<float>(d) + 0.5f) - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = min(static_cast<int>(src), P - 1);
+  i1 = min(i0 + 1, P - 1);
+  l1 = src - static_cast<float>(i0);
+}
+
+// ---- per-channel block reduction: thread (cl, pl) holds NRED x VEC partials for channel vector cl ----
+template <int VEC, int NRED>
+__device__ __forceinline__ void flush_channel_partials(float (&acc)[NRED][VEC], int cl, int pl, int CL, int PL,
+                                                       int c_base, int C, double* const (&outs)[NRED], float* s_red) {
+  // s_red: [NRED][PL][CL*VEC]
+  const int row = CL * VEC;
+  if (cl < CL && pl < PL) {
+#pragma unroll
+    for (int r = 0; r < NRED; ++r)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s_red[(r * PL + pl) * row + cl * VEC + v] = acc[r][v];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < row; idx += blockDim.x) {
+    const int c = c_base + idx;
+    if (c < C) {
+#pragma unroll
+      for (int r = 0; r < NRED; ++r) {
+        float s = 0.f;
+        for (int p = 0; p < PL; ++p) s += s_red[(r * PL + p) * row + idx];
+        atomicAdd(outs[r] + c, static_cast<double>(s));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void block_scalar_reduce_add(float v, double* out) {
+  __shared__ float s_w[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_w[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < (blockDim.x + 31) / 32 ? s_w[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) atomicAdd(out, static_cast<double>(t));
+  }
+}
+
+struct RedGeom { int CL, PL, chunks; };
+static RedGeom red_geom(int C, int VEC) {
+  RedGeom g;
+  const int cv = (C + VEC - 1) / VEC;
+  g.CL = std::min(cv, VEC == 8 ? 32 : 64);
+  g.PL = 256 / g.CL;
+  g.chunks = (cv + g.CL - 1) / g.CL;
+  return g;
+}
+static int red_blocks(long long items, int PL) {
+  long long b = (items + PL - 1) / PL;
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(b, 148 * 8)));
+}
+
+// =============================================================================================
+// BatchNorm finalize / eval affine / param grads
+// =============================================================================================
+__global__ void bn_finalize_kernel(const double* stats, long long count, int C, const float* gamma, const float* beta,
+                                   const float* conv_bias, float* rmean, float* rvar, float momentum, float eps,
+                                   float* scale, float* shift, float* mean_out, float* invstd_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = static_cast<double>(count);
+  const double mean = stats[c] / n;
+  double var = stats[C + c] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double invstd = rsqrt(var + static_cast<double>(eps));
+  const float sc = static_cast<float>(gamma[c] * invstd);
+  scale[c] = sc;
+  shift[c] = static_cast<float>(beta[c] - mean * gamma[c] * invstd);
+  mean_out[c] = static_cast<float>(mean);
+  invstd_out[c] = static_cast<float>(invstd);
+  if (rmean != nullptr) {
+    const double b = conv_bias ? conv_bias[c] : 0.0;
+    rmean[c] = static_cast<float>((1.0 - momentum) * rmean[c] + momentum * (mean + b));
+    const double unb = count > 1 ? var * n / (n - 1.0) : var;
+    rvar[c] = static_cast<float>((1.0 - momentum) * rvar[c] + momentum * unb);
+  }
+}
+__global__ void bn_eval_affine_kernel(int C, const float* gamma, const float* beta, const float* conv_bias,
+                                      const float* rmean, const float* rvar, float eps, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(rvar[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rmean[c]) * sc;
+}
+__global__ void bn_param_grads_kernel(const double* red, int C, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbeta[c] = static_cast<float>(red[c]);
+  dgamma[c] = static_cast<float>(red[C + c]);
+}
+
+// =============================================================================================
+// forward: bn+relu -> adaptive pool (separable)
+// =============================================================================================
+template <int VEC>
+__global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, int W, int C, const float* scale,
+                                 const float* shift, int P, float* tmp) {
+  const int CV = C / VEC;
+  const long long total = static_cast<long long>(B) * H * P * CV;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    long long r = i / CV;
+    const int j = static_cast<int>(r % P); r /= P;
+    const int y = static_cast<int>(r % H);
+    const long long b = r / H;
+    int lo, hi; pool_win(j, W, P, lo, hi);
+    float sc[VEC], sh[VEC], acc[VEC];
+    ldf<VEC>(scale + cv * VEC, sc); ldf<VEC>(shift + cv * VEC, sh);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    const act_t* row = a0 + ((b * H + y) * W) * ld + cv * VEC;
+    for (int x = lo; x < hi; ++x) {
+      float t[VEC]; ldv<VEC>(row + x * ld, t);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] += fmaxf(fmaf(t[v], sc[v], sh[v]), 0.f);
+    }
+    const float inv = 1.f / static_cast<float>(hi - lo);
+    float* o = tmp + ((b * H + y) * P + j) * C + cv * VEC;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o[v] = acc[v] * inv;
+  }
+}
+// out[b, i, j, c] = scale_out * sum_y wgt(i, y) * tmp[b, y, j, c]; mode 0: pool windows over y, mode 1: bilinear^T
+__global__ void cols_reduce_kernel(const float* tmp, int B, int H, int P, int C, int mode, const float* mul, float* out) {
+  const long long total = static_cast<long long>(B) * P * P * C;
+  const float m = mul ? *mul : 1.f;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % C);
+    long long r = idx / C;
+    const int j = static_cast<int>(r % P); r /= P;
+    const int i = static_cast<int>(r % P);
+    const long long b = r / P;
+    float acc = 0.f;
+    if (mode == 0) {
+      int lo, hi; pool_win(i, H, P, lo, hi);
+      for (int y = lo; y < hi; ++y) acc += tmp[((b * H + y) * P + j) * C + c];
+      acc /= static_cast<float>(hi - lo);
+    } else {
+      const float ratio = static_cast<float>(H) / static_cast<float>(P);
+      int lo = static_cast<int>(floorf((i - 0.5f) * ratio - 0.5f)) - 1;
+      int hi = static_cast<int>(ceilf((i + 1.5f) * ratio - 0.5f)) + 1;
+      lo = max(lo, 0); hi = min(hi, H - 1);
+      for (int y = lo; y <= hi; ++y) {
+        int i0, i1; float l1; bilerp_taps(y, P, H, i0, i1, l1);
+        float wgt = 0.f;
+        if (i0 == i) wgt += 1.f - l1;
+        if (i1 == i) wgt += l1;
+        if (wgt != 0.f) acc += wgt * tmp[((b * H + y) * P + j) * C + c];
+      }
+    }
+    out[idx] = acc * m;
+  }
+}
+
+// =============================================================================================
+// forward: L / A into the concat buffer
+// =============================================================================================
+template <int VEC>
+__device__ __forceinline__ void bilerp_gather(const float* o, long long b, int y, int x, int H, int W, int P, int C,
+                                              int c, float (&u)[VEC]) {
+  int y0, y1, x0, x1; float ly, lx;
+  bilerp_taps(y, P, H, y0, y1, ly);
+  bilerp_taps(x, P, W, x0, x1, lx);
+  const float* base = o + b * P * P * C + c;
+  float a00[VEC], a01[VEC], a10[VEC], a11[VEC];
+  ldf<VEC>(base + (y0 * P + x0) * C, a00); ldf<VEC>(base + (y0 * P + x1) * C, a01);
+  ldf<VEC>(base + (y1 * P + x0) * C, a10); ldf<VEC>(base + (y1 * P + x1) * C, a11);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) u[v] = w00 * a00[v] + w01 * a01[v] + w10 * a10[v] + w11 * a11[v];
+}
+
+template <int VEC>
+__global__ void branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H,
+                                      int W, int C, const float* s1, const float* t1, const float* s2, const float* t2,
+                                      const float* o, int P, const float* gamma, act_t* z, long long ld_z) {
+  const int CV = C / VEC;
+  const long long total = static_cast<long long>(B) * H * W * CV;
+  const float gm = *gamma;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    const long long m = i / CV;
+    const int x = static_cast<int>(m % W);
+    const long long r = m / W;
+    const int y = static_cast<int>(r % H);
+    const long long b = r / H;
+    float v0[VEC], sc[VEC], sh[VEC], outv[VEC];
+    ldv<VEC>(l0 + m * ld_l0 + c, v0); ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) outv[v] = fmaxf(fmaf(v0[v], sc[v], sh[v]), 0.f);
+    stv<VEC>(z + m * ld_z + C + c, outv);
+    float u[VEC];
+    bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
+    ldv<VEC>(a0 + m * ld_a0 + c, v0); ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmaxf(fmaf(v0[v], sc[v], sh[v]), 0.f);
+    stv<VEC>(z + m * ld_z + 2 * C + c, outv);
+  }
+}
+
+template <int VEC>
+__global__ void gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const float* s3,
+                                    const float* t3, act_t* z, long long ld_z) {
+  const int CV = C / VEC;
+  const long long total = M * CV;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    const long long m = i / CV;
+    float g[VEC], sc[VEC], sh[VEC], l[VEC], a[VEC], f[VEC];
+    ldv<VEC>(g0 + m * ld_g0 + c, g); ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh);
+    ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
+      f[v] = gg * l[v] + (1.f - gg) * a[v];
+    }
+    stv<VEC>(z + m * ld_z + c, f);
+  }
+}
+
+// y = relu(bn4(F0)) + rs*R, optional 2x2 max pool; one thread per 2x2 window and channel vector
+template <int VEC>
+__global__ void block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long ld_r, int B, int H,
+                                     int W, int C, const float* s4, const float* t4, const float* res_scale, act_t* y,
+                                     long long ld_y, act_t* yp, long long ld_yp) {
+  const int CV = C / VEC;
+  const int Hw = (H + 1) / 2, Ww = (W + 1) / 2;
+  const int Hp = H / 2, Wp = W / 2;
+  const long long total = static_cast<long long>(B) * Hw * Ww * CV;
+  const float rs = *res_scale;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    long long q = i / CV;
+    const int xo = static_cast<int>(q % Ww); q /= Ww;
+    const int yo = static_cast<int>(q % Hw);
+    const long long b = q / Hw;
+    float sc[VEC], sh[VEC], mx[VEC];
+    ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) mx[v] = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+      if (yy >= H || xx >= W) continue;
+      const long long m = (b * H + yy) * W + xx;
+      float fv[VEC], rv[VEC], ov[VEC];
+      ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        ov[v] = fmaxf(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
+      }
+      stv<VEC>(y + m * ld_y + c, ov);
+      // pool over the values as stored (fp16), so backward can recompute the argmax from y
+      float rd[VEC];
+      ldv<VEC>(y + m * ld_y + c, rd);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) mx[v] = fmaxf(mx[v], rd[v]);
+    }
+    if (yp != nullptr && yo < Hp && xo < Wp) stv<VEC>(yp + ((b * Hp + yo) * Wp + xo) * ld_yp + c, mx);
+  }
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+template <int VEC>
+__global__ void __launch_bounds__(256)
+block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_t* dyp, long long ld_dyp,
+                            const act_t* y, long long ld_y, const act_t* f0, long long ld_f0, const act_t* r,
+                            long long ld_r, int B, int H, int W, int C, const float* s4, const float* t4,
+                            const float* mean4, const float* invstd4, grad_t* dy_out, long long ld_dy, double* red4,
+                            double* drs, int CL, int PL) {
+  __shared__ float s_red[2 * 256 * VEC];
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * VEC;
+  const int c = c_base + cl * VEC;
+  const bool active = pl < PL && c < C;
+  const int Hw = (H + 1) / 2, Ww = (W + 1) / 2;
+  const int Hp = H / 2, Wp = W / 2;
+  const long long nwin = static_cast<long long>(B) * Hw * Ww;
+  float acc[2][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
+  float drs_acc = 0.f;
+  if (active) {
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh); ldf<VEC>(mean4 + c, mu); ldf<VEC>(invstd4 + c, is);
+    for (long long wi = static_cast<long long>(blockIdx.x) * PL + pl; wi < nwin; wi += static_cast<long long>(gridDim.x) * PL) {
+      const int xo = static_cast<int>(wi % Ww);
+      long long q = wi / Ww;
+      const int yo = static_cast<int>(q % Hw);
+      const long long b = q / Hw;
+      // argmax of the stored y over the window (first maximum in scan order, like ATen's max_pool2d)
+      int arg[VEC];
+      float gp[VEC];
+      const bool pooled = dyp != nullptr && yo < Hp && xo < Wp;
+      if (pooled) {
+        float best[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { best[v] = -INFINITY; arg[v] = 0; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const long long m = (b * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1);
+          float yv[VEC]; ldv<VEC>(y + m * ld_y + c, yv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) if (yv[v] > best[v]) { best[v] = yv[v]; arg[v] = k; }
+        }
+        ldv<VEC>(dyp + ((b * Hp + yo) * Wp + xo) * ld_dyp + c, gp);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+        if (yy >= H || xx >= W) continue;
+        const long long m = (b * H + yy) * W + xx;
+        float d[VEC];
+        if (dskip != nullptr) ldv<VEC>(dskip + m * ld_dskip + c, d);
+        else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[v] = 0.f;
+        }
+        if (pooled) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) if (arg[v] == k) d[v] += gp[v];
+        }
+        if (dy_out != nullptr && (dy_out != dskip || pooled)) {
+          stv<VEC>(dy_out + m * ld_dy + c, d);
+          if (pooled || dy_out != dskip) ldv<VEC>(dy_out + m * ld_dy + c, d);   // use the value later passes will read
+        }
+        float fv[VEC], rv[VEC];
+        ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          drs_acc += d[v] * rv[v];
+          const float d4 = fmaf(fv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
+          acc[0][v] += d4;
+          acc[1][v] += d4 * (fv[v] - mu[v]) * is[v];
+        }
+      }
+    }
+  }
+  double* const outs[2] = {red4, red4 + C};
+  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+  block_scalar_reduce_add(drs_acc, drs);
+}
+
+// dx = scale * (d - k1 - xhat*k2), d = dy * [relu mask] (act_mode 0) or dy (act_mode 2)
+template <int VEC>
+__global__ void bn_bwd_apply_kernel(const grad_t* dy, long long ld_dy, const act_t* x, long long ld_x, long long M, int C,
+                                    const float* scale, const float* shift, const float* mean, const float* invstd,
+                                    const double* red, int act_mode, grad_t* dx, long long ld_dx) {
+  const int CV = C / VEC;
+  const long long total = M * CV;
+  const double invn = 1.0 / static_cast<double>(M);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    const long long m = i / CV;
+    float d[VEC], xv[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC], o[VEC];
+    ldv<VEC>(dy + m * ld_dy + c, d); ldv<VEC>(x + m * ld_x + c, xv);
+    ldf<VEC>(scale + c, sc); ldf<VEC>(shift + c, sh); ldf<VEC>(mean + c, mu); ldf<VEC>(invstd + c, is);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float k1 = static_cast<float>(red[c + v] * invn), k2 = static_cast<float>(red[C + c + v] * invn);
+      float dd = d[v];
+      if (act_mode == 0 && !(fmaf(xv[v], sc[v], sh[v]) > 0.f)) dd = 0.f;
+      o[v] = sc[v] * (dd - k1 - (xv[v] - mu[v]) * is[v] * k2);
+    }
+    stv<VEC>(dx + m * ld_dx + c, o);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0,
+                           long long ld_g0, long long M, int C, const float* s3, const float* t3, const float* mean3,
+                           const float* invstd3, double* red3, int CL, int PL) {
+  __shared__ float s_red[2 * 256 * VEC];
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * VEC;
+  const int c = c_base + cl * VEC;
+  float acc[2][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
+  if (pl < PL && c < C) {
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh); ldf<VEC>(mean3 + c, mu); ldf<VEC>(invstd3 + c, is);
+    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+      float df[VEC], l[VEC], a[VEC], g[VEC];
+      ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a);
+      ldv<VEC>(g0 + m * ld_g0 + c, g);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
+        const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
+        acc[0][v] += ds;
+        acc[1][v] += ds * (g[v] - mu[v]) * is[v];
+      }
+    }
+  }
+  double* const outs[2] = {red3, red3 + C};
+  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+}
+
+template <int VEC>
+__global__ void gate_mix_bwd_apply_kernel(grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0,
+                                          long long ld_g0, long long M, int C, const float* s3, const float* t3,
+                                          const float* mean3, const float* invstd3, const double* red3, grad_t* dg0,
+                                          long long ld_dg0) {
+  const int CV = C / VEC;
+  const long long total = M * CV;
+  const double invn = 1.0 / static_cast<double>(M);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    const long long m = i / CV;
+    float df[VEC], dl[VEC], da[VEC], l[VEC], a[VEC], g[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC], o[VEC];
+    ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+    ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a); ldv<VEC>(g0 + m * ld_g0 + c, g);
+    ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh); ldf<VEC>(mean3 + c, mu); ldf<VEC>(invstd3 + c, is);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float k1 = static_cast<float>(red3[c + v] * invn), k2 = static_cast<float>(red3[C + c + v] * invn);
+      const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
+      const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
+      o[v] = sc[v] * (ds - k1 - (g[v] - mu[v]) * is[v] * k2);
+      dl[v] += df[v] * gg;
+      da[v] += df[v] * (1.f - gg);
+    }
+    stv<VEC>(dg0 + m * ld_dg0 + c, o);
+    stv<VEC>(dz + m * ld_dz + C + c, dl);
+    stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+  }
+}
+
+// pass 1 of the branch backward: BN1 reductions and dgamma
+template <int VEC>
+__global__ void __launch_bounds__(256)
+branch_bwd_reduce1_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, int B, int H, int W,
+                          int C, const float* s1, const float* t1, const float* mean1, const float* invstd1,
+                          const float* o, int P, double* red1, double* dgamma, int CL, int PL) {
+  __shared__ float s_red[2 * 256 * VEC];
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * VEC;
+  const int c = c_base + cl * VEC;
+  const long long M = static_cast<long long>(B) * H * W;
+  float acc[2][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
+  float dg = 0.f;
+  if (pl < PL && c < C) {
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(mean1 + c, mu); ldf<VEC>(invstd1 + c, is);
+    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+      const int x = static_cast<int>(m % W);
+      const long long r = m / W;
+      const int y = static_cast<int>(r % H);
+      const long long b = r / H;
+      float dl[VEC], da[VEC], lv[VEC], u[VEC];
+      ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+      ldv<VEC>(l0 + m * ld_l0 + c, lv);
+      bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float d1 = fmaf(lv[v], sc[v], sh[v]) > 0.f ? dl[v] : 0.f;
+        acc[0][v] += d1;
+        acc[1][v] += d1 * (lv[v] - mu[v]) * is[v];
+        dg += da[v] * u[v];
+      }
+    }
+  }
+  double* const outs[2] = {red1, red1 + C};
+  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+  block_scalar_reduce_add(dg, dgamma);
+}
+
+// bilinear^T along x: tmp[b, y, px, c] = sum_x wx(x, px) * dA[b, y, x, c]
+template <int VEC>
+__global__ void bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int C, int P, float* tmp) {
+  const int CV = C / VEC;
+  const long long total = static_cast<long long>(B) * H * P * CV;
+  const float ratio = static_cast<float>(W) / static_cast<float>(P);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    long long r = i / CV;
+    const int px = static_cast<int>(r % P); r /= P;
+    const int y = static_cast<int>(r % H);
+    const long long b = r / H;
+    int lo = static_cast<int>(floorf((px - 0.5f) * ratio - 0.5f)) - 1;
+    int hi = static_cast<int>(ceilf((px + 1.5f) * ratio - 0.5f)) + 1;
+    lo = max(lo, 0); hi = min(hi, W - 1);
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    const grad_t* row = dz + ((b * H + y) * W) * ld_dz + 2 * C + c;
+    for (int x = lo; x <= hi; ++x) {
+      int x0, x1; float lx; bilerp_taps(x, P, W, x0, x1, lx);
+      float wgt = 0.f;
+      if (x0 == px) wgt += 1.f - lx;
+      if (x1 == px) wgt += lx;
+      if (wgt != 0.f) {
+        float d[VEC]; ldv<VEC>(row + x * ld_dz, d);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += wgt * d[v];
+      }
+    }
+    float* o = tmp + ((b * H + y) * P + px) * C + c;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o[v] = acc[v];
+  }
+}
+
+// adaptive_avg_pool^T gather of dpooled at pixel (y, x)
+template <int VEC>
+__device__ __forceinline__ void poolT_gather(const float* dp, long long b, int y, int x, int H, int W, int P, int C, int c,
+                                             float (&g)[VEC]) {
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) g[v] = 0.f;
+  int ilo, ihi, jlo, jhi;
+  pool_win_of(y, H, P, ilo, ihi);
+  pool_win_of(x, W, P, jlo, jhi);
+  for (int i = ilo; i <= ihi; ++i) {
+    int a, e; pool_win(i, H, P, a, e);
+    const float wi = 1.f / static_cast<float>(e - a);
+    for (int j = jlo; j <= jhi; ++j) {
+      int a2, e2; pool_win(j, W, P, a2, e2);
+      const float wgt = wi / static_cast<float>(e2 - a2);
+      float t[VEC]; ldf<VEC>(dp + ((b * P + i) * P + j) * C + c, t);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) g[v] += wgt * t[v];
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256)
+branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, long long ld_a0, int B, int H, int W,
+                          int C, const float* s2, const float* t2, const float* mean2, const float* invstd2,
+                          const float* dpooled, int P, double* red2, int CL, int PL) {
+  __shared__ float s_red[2 * 256 * VEC];
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * VEC;
+  const int c = c_base + cl * VEC;
+  const long long M = static_cast<long long>(B) * H * W;
+  float acc[2][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
+  if (pl < PL && c < C) {
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh); ldf<VEC>(mean2 + c, mu); ldf<VEC>(invstd2 + c, is);
+    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+      const int x = static_cast<int>(m % W);
+      const long long r = m / W;
+      const int y = static_cast<int>(r % H);
+      const long long b = r / H;
+      float da[VEC], av[VEC], gp[VEC];
+      ldv<VEC>(dz + m * ld_dz + 2 * C + c, da); ldv<VEC>(a0 + m * ld_a0 + c, av);
+      poolT_gather<VEC>(dpooled, b, y, x, H, W, P, C, c, gp);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float d2 = fmaf(av[v], sc[v], sh[v]) > 0.f ? da[v] + gp[v] : 0.f;
+        acc[0][v] += d2;
+        acc[1][v] += d2 * (av[v] - mu[v]) * is[v];
+      }
+    }
+  }
+  double* const outs[2] = {red2, red2 + C};
+  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+}
+
+template <int VEC>
+__global__ void branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0,
+                                        const act_t* a0, long long ld_a0, int B, int H, int W, int C, const float* s1,
+                                        const float* t1, const float* mean1, const float* invstd1, const double* red1,
+                                        const float* s2, const float* t2, const float* mean2, const float* invstd2,
+                                        const double* red2, const float* dpooled, int P, grad_t* dl0, long long ld_dl0,
+                                        grad_t* da0, long long ld_da0) {
+  const int CV = C / VEC;
+  const long long M = static_cast<long long>(B) * H * W;
+  const long long total = M * CV;
+  const double invn = 1.0 / static_cast<double>(M);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % CV) * VEC;
+    const long long m = i / CV;
+    const int x = static_cast<int>(m % W);
+    const long long r = m / W;
+    const int y = static_cast<int>(r % H);
+    const long long b = r / H;
+    float d[VEC], xv[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC], o[VEC];
+    // conv branch
+    ldv<VEC>(dz + m * ld_dz + C + c, d); ldv<VEC>(l0 + m * ld_l0 + c, xv);
+    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(mean1 + c, mu); ldf<VEC>(invstd1 + c, is);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float k1 = static_cast<float>(red1[c + v] * invn), k2 = static_cast<float>(red1[C + c + v] * invn);
+      const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
+      o[v] = sc[v] * (dd - k1 - (xv[v] - mu[v]) * is[v] * k2);
+    }
+    stv<VEC>(dl0 + m * ld_dl0 + c, o);
+    // attention branch
+    float gp[VEC];
+    ldv<VEC>(dz + m * ld_dz + 2 * C + c, d); ldv<VEC>(a0 + m * ld_a0 + c, xv);
+    ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh); ldf<VEC>(mean2 + c, mu); ldf<VEC>(invstd2 + c, is);
+    poolT_gather<VEC>(dpooled, b, y, x, H, W, P, C, c, gp);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float k1 = static_cast<float>(red2[c + v] * invn), k2 = static_cast<float>(red2[C + c + v] * invn);
+      const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] + gp[v] : 0.f;
+      o[v] = sc[v] * (dd - k1 - (xv[v] - mu[v]) * is[v] * k2);
+    }
+    stv<VEC>(da0 + m * ld_da0 + c, o);
+  }
+}
+
+// =============================================================================================
+// layout / misc
+// =============================================================================================
+__global__ void nchw_to_nhwc_kernel(const float* src, void* dst, int ddt, long long ld, int B, int C, int H, int W) {
+  const long long total = static_cast<long long>(B) * H * W * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long m = i / C;
+    const long long hw = m % (static_cast<long long>(H) * W);
+    const long long b = m / (static_cast<long long>(H) * W);
+    const float v = src[(b * C + c) * H * W + hw];
+    if (ddt == DFCSA_F32) reinterpret_cast<float*>(dst)[m * ld + c] = v;
+    else if (ddt == DFCSA_F16) reinterpret_cast<__half*>(dst)[m * ld + c] = Cvt<__half>::from_f(v);
+    else reinterpret_cast<__nv_bfloat16*>(dst)[m * ld + c] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void nhwc_to_nchw_kernel(const void* src, int sdt, long long ld, float* dst, int B, int C, int H, int W) {
+  const long long total = static_cast<long long>(B) * H * W * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long hw = i % (static_cast<long long>(H) * W);
+    const long long r = i / (static_cast<long long>(H) * W);
+    const int c = static_cast<int>(r % C);
+    const long long b = r / C;
+    const long long m = b * H * W + hw;
+    float v;
+    if (sdt == DFCSA_F32) v = reinterpret_cast<const float*>(src)[m * ld + c];
+    else if (sdt == DFCSA_F16) v = __half2float(reinterpret_cast<const __half*>(src)[m * ld + c]);
+    else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[m * ld + c]);
+    dst[i] = v;
+  }
+}
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* x, int dt, long long ld, long long M, int C, float* out) {
+  // block: 32 channels x 8 pixel lanes
+  const int cl = threadIdx.x % 32, pl = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + cl;
+  float acc = 0.f;
+  if (c < C) {
+    for (long long m = static_cast<long long>(blockIdx.x) * 8 + pl; m < M; m += static_cast<long long>(gridDim.x) * 8) {
+      if (dt == DFCSA_F32) acc += reinterpret_cast<const float*>(x)[m * ld + c];
+      else if (dt == DFCSA_F16) acc += __half2float(reinterpret_cast<const __half*>(x)[m * ld + c]);
+      else acc += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[m * ld + c]);
+    }
+  }
+  __shared__ float s[8][33];
+  s[pl][cl] = acc;
+  __syncthreads();
+  if (pl == 0 && c < C) {
+    float t = 0.f;
+    for (int p = 0; p < 8; ++p) t += s[p][cl];
+    atomicAdd(out + c, t);
+  }
+}
+__global__ void cast2d_kernel(const void* x, int xdt, long long ld_x, void* y, int ydt, long long ld_y, long long M, int C) {
+  const long long total = M * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const long long m = i / C;
+    float v;
+    if (xdt == DFCSA_F32) v = reinterpret_cast<const float*>(x)[m * ld_x + c];
+    else if (xdt == DFCSA_F16) v = __half2float(reinterpret_cast<const __half*>(x)[m * ld_x + c]);
+    else v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[m * ld_x + c]);
+    if (ydt == DFCSA_F32) reinterpret_cast<float*>(y)[m * ld_y + c] = v;
+    else if (ydt == DFCSA_F16) reinterpret_cast<__half*>(y)[m * ld_y + c] = Cvt<__half>::from_f(v);
+    else reinterpret_cast<__nv_bfloat16*>(y)[m * ld_y + c] = __float2bfloat16_rn(v);
+  }
+}
+
+static int ew_blocks(long long total) {
+  return static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, 148LL * 32)));
+}
+
+}  // namespace
+}  // namespace dfcsa
+
+using namespace dfcsa;
+#define ST static_cast<cudaStream_t>(stream)
+#define A_(p) reinterpret_cast<const act_t*>(p)
+#define AM_(p) reinterpret_cast<act_t*>(p)
+#define G_(p) reinterpret_cast<const grad_t*>(p)
+#define GM_(p) reinterpret_cast<grad_t*>(p)
+// dispatch on the vector width
+#define VEC_DISPATCH(ok, ...)            \
+  do { if (ok) { constexpr int VEC = 8; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; } } while (0)
+
+extern "C" int dfcsa_bn_finalize(const double* stats, int64_t count, int32_t C, const float* gamma, const float* beta,
+                                 const float* conv_bias, float* running_mean, float* running_var, float momentum,
+                                 float eps, float* scale, float* shift, float* mean, float* invstd, void* stream) {
+  DFCSA_CHECK_ARG(stats && gamma && beta && scale && shift && mean && invstd && C > 0 && count > 0, "dfcsa_bn_finalize: bad args");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(stats, count, C, gamma, beta, conv_bias, running_mean, running_var,
+                                                      momentum, eps, scale, shift, mean, invstd);
+  DFCSA_LAUNCH_CHECK("bn_finalize_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const float* conv_bias,
+                                    const float* running_mean, const float* running_var, float eps, float* scale,
+                                    float* shift, void* stream) {
+  DFCSA_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && C > 0, "dfcsa_bn_eval_affine: bad args");
+  bn_eval_affine_kernel<<<(C + 127) / 128, 128, 0, ST>>>(C, gamma, beta, conv_bias, running_mean, running_var, eps, scale, shift);
+  DFCSA_LAUNCH_CHECK("bn_eval_affine_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_bn_param_grads(const double* red, int32_t C, float* dgamma, float* dbeta, void* stream) {
+  DFCSA_CHECK_ARG(red && dgamma && dbeta && C > 0, "dfcsa_bn_param_grads: bad args");
+  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST>>>(red, C, dgamma, dbeta);
+  DFCSA_LAUNCH_CHECK("bn_param_grads_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int32_t H, int32_t W, int32_t C,
+                                     const float* scale, const float* shift, int32_t P, float* tmp, float* pooled,
+                                     void* stream) {
+  DFCSA_CHECK_ARG(a0 && scale && shift && tmp && pooled && B > 0 && H > 0 && W > 0 && C > 0 && P > 0, "dfcsa_bnrelu_pool_fwd: bad args");
+  const bool v8 = vec8_ok(C, {ld}, {a0, scale, shift, tmp});
+  const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (pool_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(a0), ld, B, H, W, C, scale, shift, P, tmp)));
+  DFCSA_LAUNCH_CHECK("pool_rows_kernel");
+  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled);
+  DFCSA_LAUNCH_CHECK("cols_reduce_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a0, int64_t ld_a0, int32_t B, int32_t H,
+                                    int32_t W, int32_t C, const float* scale1, const float* shift1, const float* scale2,
+                                    const float* shift2, const float* o, int32_t P, const float* gamma, void* z,
+                                    int64_t ld_z, void* stream) {
+  DFCSA_CHECK_ARG(l0 && a0 && scale1 && shift1 && scale2 && shift2 && o && gamma && z, "dfcsa_branch_act_fwd: null pointer");
+  const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z}, {l0, a0, z, o, scale1, shift1, scale2, shift2});
+  const long long total = static_cast<long long>(B) * H * W * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
+                                                                                 shift1, scale2, shift2, o, P, gamma, AM_(z), ld_z)));
+  DFCSA_LAUNCH_CHECK("branch_act_fwd_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int32_t C, const float* scale3,
+                                  const float* shift3, void* z, int64_t ld_z, void* stream) {
+  DFCSA_CHECK_ARG(g0 && scale3 && shift3 && z && M > 0 && C > 0, "dfcsa_gate_mix_fwd: bad args");
+  const bool v8 = vec8_ok(C, {ld_g0, ld_z}, {g0, z, scale3, shift3});
+  const long long total = M * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (gate_mix_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(g0), ld_g0, M, C, scale3, shift3, AM_(z), ld_z)));
+  DFCSA_LAUNCH_CHECK("gate_mix_fwd_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r, int64_t ld_r, int32_t B, int32_t H,
+                                   int32_t W, int32_t C, const float* scale4, const float* shift4, const float* res_scale,
+                                   void* y, int64_t ld_y, void* yp, int64_t ld_yp, void* stream) {
+  DFCSA_CHECK_ARG(f0 && r && scale4 && shift4 && res_scale && y, "dfcsa_block_out_fwd: null pointer");
+  const bool v8 = vec8_ok(C, {ld_f0, ld_r, ld_y, yp ? ld_yp : 0}, {f0, r, y, yp, scale4, shift4});
+  const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4,
+                                                                                res_scale, AM_(y), ld_y, AM_(yp), ld_yp)));
+  DFCSA_LAUNCH_CHECK("block_out_fwd_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_block_out_bwd_reduce(const void* dskip, int64_t ld_dskip, const void* dyp, int64_t ld_dyp,
+                                          const void* y, int64_t ld_y, const void* f0, int64_t ld_f0, const void* r,
+                                          int64_t ld_r, int32_t B, int32_t H, int32_t W, int32_t C, const float* scale4,
+                                          const float* shift4, const float* mean4, const float* invstd4, void* dy_out,
+                                          int64_t ld_dy, double* red4, double* drs, void* stream) {
+  DFCSA_CHECK_ARG((dskip || dyp) && y && f0 && r && scale4 && shift4 && mean4 && invstd4 && red4 && drs, "dfcsa_block_out_bwd_reduce: null pointer");
+  DFCSA_CHECK_ARG(dy_out != nullptr || dyp == nullptr, "dfcsa_block_out_bwd_reduce: dy_out required when dyp is given");
+  const bool v8 = vec8_ok(C, {dskip ? ld_dskip : 0, dyp ? ld_dyp : 0, ld_y, ld_f0, ld_r, dy_out ? ld_dy : 0},
+                          {dskip, dyp, y, f0, r, dy_out, scale4, shift4, mean4, invstd4});
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
+  dim3 grid(red_blocks(nwin, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (block_out_bwd_reduce_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dskip), ld_dskip, G_(dyp), ld_dyp, A_(y), ld_y, A_(f0), ld_f0,
+                                                                           A_(r), ld_r, B, H, W, C, scale4, shift4, mean4, invstd4,
+                                                                           GM_(dy_out), ld_dy, red4, drs, g.CL, g.PL)));
+  DFCSA_LAUNCH_CHECK("block_out_bwd_reduce_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_bn_bwd_apply(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t M, int32_t C,
+                                  const float* scale, const float* shift, const float* mean, const float* invstd,
+                                  const float* gamma, const double* red, int32_t act_mode, void* dx, int64_t ld_dx,
+                                  void* stream) {
+  (void)gamma;
+  DFCSA_CHECK_ARG(dy && x && scale && shift && mean && invstd && red && dx && M > 0, "dfcsa_bn_bwd_apply: bad args");
+  const bool v8 = vec8_ok(C, {ld_dy, ld_x, ld_dx}, {dy, x, dx, scale, shift, mean, invstd});
+  const long long total = M * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dy), ld_dy, A_(x), ld_x, M, C, scale, shift, mean, invstd,
+                                                                               red, act_mode, GM_(dx), ld_dx)));
+  DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const void* z, int64_t ld_z, const void* g0,
+                                         int64_t ld_g0, int64_t M, int32_t C, const float* scale3, const float* shift3,
+                                         const float* mean3, const float* invstd3, double* red3, void* stream) {
+  DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && M > 0, "dfcsa_gate_mix_bwd_reduce: bad args");
+  const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0}, {dz, z, g0, scale3, shift3, mean3, invstd3});
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (gate_mix_bwd_reduce_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
+                                                                          mean3, invstd3, red3, g.CL, g.PL)));
+  DFCSA_LAUNCH_CHECK("gate_mix_bwd_reduce_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_gate_mix_bwd_apply(void* dz, int64_t ld_dz, const void* z, int64_t ld_z, const void* g0,
+                                        int64_t ld_g0, int64_t M, int32_t C, const float* scale3, const float* shift3,
+                                        const float* mean3, const float* invstd3, const float* gamma3, const double* red3,
+                                        void* dg0, int64_t ld_dg0, void* stream) {
+  (void)gamma3;
+  DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && dg0 && M > 0, "dfcsa_gate_mix_bwd_apply: bad args");
+  const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0, ld_dg0}, {dz, z, g0, dg0, scale3, shift3, mean3, invstd3});
+  const long long total = M * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(GM_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3,
+                                                                                     shift3, mean3, invstd3, red3, GM_(dg0), ld_dg0)));
+  DFCSA_LAUNCH_CHECK("gate_mix_bwd_apply_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_branch_bwd_reduce1(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, int32_t B, int32_t H,
+                                        int32_t W, int32_t C, const float* scale1, const float* shift1, const float* mean1,
+                                        const float* invstd1, const float* o, int32_t P, const float* gamma, double* red1,
+                                        double* dgamma, float* tmp, float* d_o, void* stream) {
+  DFCSA_CHECK_ARG(dz && l0 && scale1 && shift1 && mean1 && invstd1 && o && gamma && red1 && dgamma && tmp && d_o, "dfcsa_branch_bwd_reduce1: null pointer");
+  const bool v8 = vec8_ok(C, {ld_dz, ld_l0}, {dz, l0, o, tmp, scale1, shift1, mean1, invstd1});
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  const long long M = static_cast<long long>(B) * H * W;
+  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, B, H, W, C, scale1, shift1, mean1,
+                                                                         invstd1, o, P, red1, dgamma, g.CL, g.PL)));
+  DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
+  const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));
+  DFCSA_LAUNCH_CHECK("bilerpT_rows_kernel");
+  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o);
+  DFCSA_LAUNCH_CHECK("cols_reduce_kernel(bilerpT)");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_branch_bwd_reduce2(const void* dz, int64_t ld_dz, const void* a0, int64_t ld_a0, int32_t B, int32_t H,
+                                        int32_t W, int32_t C, const float* scale2, const float* shift2, const float* mean2,
+                                        const float* invstd2, const float* dpooled, int32_t P, double* red2, void* stream) {
+  DFCSA_CHECK_ARG(dz && a0 && scale2 && shift2 && mean2 && invstd2 && dpooled && red2, "dfcsa_branch_bwd_reduce2: null pointer");
+  const bool v8 = vec8_ok(C, {ld_dz, ld_a0}, {dz, a0, dpooled, scale2, shift2, mean2, invstd2});
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  const long long M = static_cast<long long>(B) * H * W;
+  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (branch_bwd_reduce2_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2,
+                                                                         invstd2, dpooled, P, red2, g.CL, g.PL)));
+  DFCSA_LAUNCH_CHECK("branch_bwd_reduce2_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, const void* a0,
+                                      int64_t ld_a0, int32_t B, int32_t H, int32_t W, int32_t C, const float* scale1,
+                                      const float* shift1, const float* mean1, const float* invstd1, const float* gamma1,
+                                      const double* red1, const float* scale2, const float* shift2, const float* mean2,
+                                      const float* invstd2, const float* gamma2, const double* red2, const float* dpooled,
+                                      int32_t P, void* dl0, int64_t ld_dl0, void* da0, int64_t ld_da0, void* stream) {
+  (void)gamma1; (void)gamma2;
+  DFCSA_CHECK_ARG(dz && l0 && a0 && red1 && red2 && dpooled && dl0 && da0, "dfcsa_branch_bwd_apply: null pointer");
+  const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_a0, ld_dl0, ld_da0},
+                          {dz, l0, a0, dl0, da0, dpooled, scale1, shift1, mean1, invstd1, scale2, shift2, mean2, invstd2});
+  const long long total = static_cast<long long>(B) * H * W * (v8 ? C / 8 : C);
+  VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C,
+                                                                                   scale1, shift1, mean1, invstd1, red1, scale2, shift2,
+                                                                                   mean2, invstd2, red2, dpooled, P, GM_(dl0), ld_dl0,
+                                                                                   GM_(da0), ld_da0)));
+  DFCSA_LAUNCH_CHECK("branch_bwd_apply_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_nchw_to_nhwc(const float* src, void* dst, int dst_dtype, int64_t ld, int32_t B, int32_t C, int32_t H,
+                                  int32_t W, void* stream) {
+  DFCSA_CHECK_ARG(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "dfcsa_nchw_to_nhwc: bad args");
+  nchw_to_nhwc_kernel<<<ew_blocks(static_cast<long long>(B) * C * H * W), 256, 0, ST>>>(src, dst, dst_dtype, ld, B, C, H, W);
+  DFCSA_LAUNCH_CHECK("nchw_to_nhwc_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_nhwc_to_nchw(const void* src, int src_dtype, int64_t ld, float* dst, int32_t B, int32_t C, int32_t H,
+                                  int32_t W, void* stream) {
+  DFCSA_CHECK_ARG(src && dst && B > 0 && C > 0 && H > 0 && W > 0, "dfcsa_nhwc_to_nchw: bad args");
+  nhwc_to_nchw_kernel<<<ew_blocks(static_cast<long long>(B) * C * H * W), 256, 0, ST>>>(src, src_dtype, ld, dst, B, C, H, W);
+  DFCSA_LAUNCH_CHECK("nhwc_to_nchw_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_colsum(const void* x, int x_dtype, int64_t ld, int64_t M, int32_t C, float* out, void* stream) {
+  DFCSA_CHECK_ARG(x && out && M > 0 && C > 0, "dfcsa_colsum: bad args");
+  dim3 grid(static_cast<unsigned>(std::max<long long>(1, std::min<long long>((M + 63) / 64, 148 * 4))), (C + 31) / 32);
+  colsum_kernel<<<grid, 256, 0, ST>>>(x, x_dtype, ld, M, C, out);
+  DFCSA_LAUNCH_CHECK("colsum_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_cast2d(const void* x, int x_dtype, int64_t ld_x, void* y, int y_dtype, int64_t ld_y, int64_t M,
+                            int32_t C, void* stream) {
+  DFCSA_CHECK_ARG(x && y && M > 0 && C > 0, "dfcsa_cast2d: bad args");
+  cast2d_kernel<<<ew_blocks(M * C), 256, 0, ST>>>(x, x_dtype, ld_x, y, y_dtype, ld_y, M, C);
+  DFCSA_LAUNCH_CHECK("cast2d_kernel");
+  return DFCSA_OK;
+}

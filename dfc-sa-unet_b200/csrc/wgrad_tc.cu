@@ -181,6 +181,7 @@ void pick_patch(int H, int W, int& w_t, int& h_t) {
 
 int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->x_dtype != DFCSA_F32 && p->dy_dtype != DFCSA_F32, "conv_wgrad_tc: 16-bit operands required");
+  DFCSA_CHECK_ARG(p->x_dtype == p->dy_dtype, "conv_wgrad_tc: x and dy must share one 16-bit format (kind::f16 cannot mix fp16 and bf16)");
   DFCSA_CHECK_ARG(p->C % 64 == 0 && p->N % 8 == 0, "conv_wgrad_tc: C must be a multiple of 64 and N of 8 (C=%d N=%d)", p->C, p->N);
   DFCSA_CHECK_ARG(p->ld_x % 8 == 0 && p->ld_dy % 8 == 0, "conv_wgrad_tc: pitches must be multiples of 8");
   DFCSA_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->dy) & 15) == 0,
@@ -261,9 +262,11 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.tmem_cols = a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256;
 
   const int smem_bytes = kStages * kStageBytes + 1024;
+  static cudaError_t attr_err = cudaSuccess;
   std::call_once(g_attr_once, [smem_bytes] {
-    cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   });
+  if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
   const long long grid = items * a.splits;
   DFCSA_CHECK_ARG(grid < (1LL << 31), "conv_wgrad_tc: grid too large");
   wgrad_tc_kernel<<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, a);

@@ -94,16 +94,18 @@ _MODE = {"1": 0, "3": 1, "2": 2}
 def test_conv_gemm(cuda, case, backend):
     B, H, W, cins, modes, N, kw = case
     err, serr = _run_conv(cuda, B, H, W, cins, [_MODE[m] for m in modes], N, backend, **kw)
-    assert err < 2e-3, f"conv_gemm rel err {err}"
+    tol = 6e-3 if kw.get("out_dt") == torch.bfloat16 else 2e-3   # bf16 output rounding is 2^-9 relative
+    assert err < tol, f"conv_gemm rel err {err}"
     assert serr < 2e-3, f"BN statistics rel err {serr}"
 
 
-@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
-def test_conv_gemm_mixed_formats(cuda, backend):
-    """fp16 activations x bf16 weights in one kind::f16 MMA (used by the weight-gradient kernel)."""
-    err, _ = _run_conv(cuda, 1, 16, 16, [128], [0], 64, backend, src_dt=torch.float16, w_dt=torch.bfloat16,
-                       out_dt=torch.float32)
-    assert err < 2e-3, f"mixed-format rel err {err}"
+def test_conv_gemm_mixed_formats_rejected(cuda):
+    """kind::f16 cannot mix fp16 and bf16 operands (measured: illegal instruction on B200), so the C ABI refuses the
+    call instead of faulting; the SIMT path takes any mix."""
+    with pytest.raises(RuntimeError, match="share one 16-bit format"):
+        _run_conv(cuda, 1, 16, 16, [128], [0], 64, 0, src_dt=torch.float16, w_dt=torch.bfloat16, out_dt=torch.float32)
+    err, _ = _run_conv(cuda, 1, 16, 16, [128], [0], 64, 1, src_dt=torch.float16, w_dt=torch.bfloat16, out_dt=torch.float32)
+    assert err < 2e-3
 
 
 @pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
@@ -147,7 +149,7 @@ def test_conv_wgrad(cuda, case, backend):
     dev = cuda
     B, H, W, Cc, N, xm, dm = case
     g = torch.Generator().manual_seed(5)
-    x = torch.randn(B, H, W, Cc, generator=g).to(dev).half()
+    x = torch.randn(B, H, W, Cc, generator=g).to(dev).bfloat16()
     alpha = torch.tensor([0.37], device=dev)
     if dm == 2:
         dy = torch.randn(B, 2 * H, 2 * W, N, generator=g).to(dev).bfloat16()
