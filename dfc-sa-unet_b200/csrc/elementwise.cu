@@ -109,14 +109,14 @@ static int red_blocks(long long items, int PL) {
 // =============================================================================================
 // BatchNorm finalize / eval affine / param grads
 // =============================================================================================
-__global__ void bn_finalize_kernel(const double* stats, long long count, int C, const float* gamma, const float* beta,
+__global__ void bn_finalize_kernel(const double* sum, const double* sumsq, long long count, int C, const float* gamma, const float* beta,
                                    const float* conv_bias, float* rmean, float* rvar, float momentum, float eps,
                                    float* scale, float* shift, float* mean_out, float* invstd_out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double n = static_cast<double>(count);
-  const double mean = stats[c] / n;
-  double var = stats[C + c] / n - mean * mean;
+  const double mean = sum[c] / n;
+  double var = sumsq[c] / n - mean * mean;
   if (var < 0.0) var = 0.0;
   const double invstd = rsqrt(var + static_cast<double>(eps));
   const float sc = static_cast<float>(gamma[c] * invstd);
@@ -763,11 +763,11 @@ using namespace dfcsa;
 #define VEC_DISPATCH(ok, ...)            \
   do { if (ok) { constexpr int VEC = 8; __VA_ARGS__; } else { constexpr int VEC = 1; __VA_ARGS__; } } while (0)
 
-extern "C" int dfcsa_bn_finalize(const double* stats, int64_t count, int32_t C, const float* gamma, const float* beta,
+extern "C" int dfcsa_bn_finalize(const double* sum, const double* sumsq, int64_t count, int32_t C, const float* gamma, const float* beta,
                                  const float* conv_bias, float* running_mean, float* running_var, float momentum,
                                  float eps, float* scale, float* shift, float* mean, float* invstd, void* stream) {
-  DFCSA_CHECK_ARG(stats && gamma && beta && scale && shift && mean && invstd && C > 0 && count > 0, "dfcsa_bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(stats, count, C, gamma, beta, conv_bias, running_mean, running_var,
+  DFCSA_CHECK_ARG(sum && sumsq && gamma && beta && scale && shift && mean && invstd && C > 0 && count > 0, "dfcsa_bn_finalize: bad args");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(sum, sumsq, count, C, gamma, beta, conv_bias, running_mean, running_var,
                                                       momentum, eps, scale, shift, mean, invstd);
   DFCSA_LAUNCH_CHECK("bn_finalize_kernel");
   return DFCSA_OK;

@@ -83,7 +83,7 @@ grad_sumsq_kernel(const dfcsa_param_t* table, int n_tensors, long long max_n, do
   const dfcsa_param_t d = table[blockIdx.y];
   const long long beg = static_cast<long long>(blockIdx.x) * kChunk;
   if (beg >= d.n) return;
-  const long long end = min(d.n, beg + kChunk);
+  const long long end = min(static_cast<long long>(d.n), beg + kChunk);
   float acc = 0.f;
   for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) { const float g = d.g[i]; acc += g * g; }
   __shared__ float s[8];
@@ -103,7 +103,7 @@ sgd_step_kernel(const dfcsa_param_t* table, int n_tensors, long long max_n, cons
   const dfcsa_param_t d = table[blockIdx.y];
   const long long beg = static_cast<long long>(blockIdx.x) * kChunk;
   if (beg >= d.n) return;
-  const long long end = min(d.n, beg + kChunk);
+  const long long end = min(static_cast<long long>(d.n), beg + kChunk);
   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (total_norm + 1e-6), max=1)
   const float total = sqrtf(static_cast<float>(*sumsq)) * fabsf(gscale);
   const float coef = max_norm > 0.f ? fminf(max_norm / (total + 1e-6f), 1.f) * gscale : gscale;

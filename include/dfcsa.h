@@ -134,7 +134,7 @@ int dfcsa_softmax_rows_bwd(const float* y, const float* dy, float* dx, int64_t r
  *   a train-mode BN because it cancels) is folded into the running mean so eval mode stays exact.
  * eval:     scale/shift from running statistics (+ conv bias).
  * ---------------------------------------------------------------------------------------------------------- */
-int dfcsa_bn_finalize(const double* stats, int64_t count, int32_t C,
+int dfcsa_bn_finalize(const double* sum, const double* sumsq, int64_t count, int32_t C,
                       const float* gamma, const float* beta, const float* conv_bias,
                       float* running_mean, float* running_var, float momentum, float eps,
                       float* scale, float* shift, float* mean, float* invstd, void* stream);
