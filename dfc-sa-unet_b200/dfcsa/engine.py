@@ -1,0 +1,421 @@
+"""Host-side orchestration of the DFC-SA hot path: which libdfcsa kernel runs on which buffer, in which order.
+
+Mirrors, kernel launch by kernel launch, the reference forward (models/unet_dfc_sa_res.py:95-116 block, :161-204 net)
+and the hand-derived backward of the same graph.  PyTorch is used only for device memory
+(torch.empty / zeros), streams and a few scalar copies; all arithmetic is in the CUDA library.
+
+Layout: activations NHWC fp16 [M, C] views (M = B*H*W), gradients NHWC bf16.  Every tensor that is also the operand
+of a weight-gradient GEMM has a bf16 "shadow" (kind::f16 tcgen05.mma cannot mix fp16 with bf16 operands - measured,
+see tools/tc_probe.cu probe 7).  torch.cat of the reference is zero-copy: producers write channel slices of one
+buffer ([f | L | A] inside a block, [up | skip] in the decoder).
+"""
+import torch
+
+from . import ops
+from .ops import BACKEND_SIMT, BACKEND_TC, OUT_CONVT2x2, TAP_1x1, TAP_2x2S2, TAP_3x3
+
+F16, BF16, F32, F64 = torch.float16, torch.bfloat16, torch.float32, torch.float64
+BN_MOMENTUM, BN_EPS = 0.1, 1e-5
+
+
+def _e(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _z(shape, dtype, dev):
+    return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+def _backend(segs, w, N, out):
+    if ops.tc_eligible(segs, N, out) and w.dtype == segs[0][0].dtype:
+        return BACKEND_TC
+    return BACKEND_SIMT
+
+
+class BlockParams:
+    """Views of one DynamicFusionConvAttnBlock's parameters / buffers (reference names)."""
+
+    def __init__(self, mod):
+        cb, ab, g, fu = mod.conv_branch, mod.attn_branch, mod.gate, mod.fusion_conv
+        self.mod = mod
+        self.W1, self.b1, self.bn1 = cb[0].weight, cb[0].bias, cb[1]
+        self.W2, self.b2, self.bn2 = ab[0].weight, ab[0].bias, ab[1]
+        att = ab[3]
+        self.att = att
+        self.gamma = att.gamma
+        self.Wq, self.bq = att.query_conv.weight, att.query_conv.bias
+        self.Wk, self.bk = att.key_conv.weight, att.key_conv.bias
+        self.Wv, self.bv = att.value_conv.weight, att.value_conv.bias
+        self.W3, self.b3, self.bn3 = g[0].weight, g[0].bias, g[1]
+        self.W4, self.b4, self.bn4 = fu[0].weight, fu[0].bias, fu[1]
+        if not hasattr(mod.residual_conv, "weight"):
+            raise NotImplementedError("dfcsa: identity residual (in_channels == out_channels) is not on the DFC-SA-Res-Block "
+                                      "path (reference models/unet_dfc_sa_res.py:87-90 always projects in this network)")
+        self.W5 = mod.residual_conv.weight
+        self.res_scale = mod.res_scale
+        self.Ci, self.C = self.W1.shape[1], self.W1.shape[0]
+        self.Cq = self.Wq.shape[0]
+        self.P = att.pool_size
+        self.tc = (self.Ci % 64 == 0) and (self.C % 64 == 0)
+
+
+def pack_block_weights(bp, training, need_dx=True):
+    """fp32 master weights -> packed K-major GEMM operands (forward: fp16 / fp32; dgrad: bf16 / fp32)."""
+    dev = bp.W1.device
+    Ci, C = bp.Ci, bp.C
+    fdt = F16 if bp.tc else F32
+    pk = {}
+    pk["w1"] = _e((C, 9 * Ci), fdt, dev)
+    ops.permute3(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
+    pk["w25"] = _e((2 * C, Ci), fdt, dev)
+    ops.permute3(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1))
+    ops.permute3(bp.W5.detach(), pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
+    gdt = F16 if C % 64 == 0 else F32
+    pk["w3"] = _e((C, 2 * C), gdt, dev)
+    ops.permute3(bp.W3.detach(), pk["w3"], (C, 1, 2 * C), (2 * C, 0, 1))
+    pk["w4"] = _e((C, 3 * C), gdt, dev)
+    ops.permute3(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1))
+    if training:
+        bdt = BF16 if C % 64 == 0 else F32
+        pk["wd4"] = _e((3 * C, C), bdt, dev)       # [k_in, co] = W4^T
+        ops.permute3(bp.W4.detach(), pk["wd4"], (3 * C, 1, C), (1, 0, 3 * C))
+        pk["wd3"] = _e((2 * C, C), bdt, dev)
+        ops.permute3(bp.W3.detach(), pk["wd3"], (2 * C, 1, C), (1, 0, 2 * C))
+        if need_dx:   # the first block never needs the gradient w.r.t. the image
+            xdt = BF16 if bp.tc else F32
+            wd = _e((Ci, 11 * C), xdt, dev)            # [ci, (flipped tap, co) | co (W2) | co (res_scale*W5)]
+            tmp = _e((Ci, 9, C), xdt, dev)
+            ops.permute3(bp.W1.detach(), tmp, (Ci, 9, C), (9, 1, Ci * 9), flip1=True)
+            wd[:, :9 * C].copy_(tmp.view(Ci, 9 * C))
+            tmp2 = _e((Ci, C), xdt, dev)
+            ops.permute3(bp.W2.detach(), tmp2, (Ci, 1, C), (1, 0, Ci))
+            wd[:, 9 * C:10 * C].copy_(tmp2)
+            ops.permute3(bp.W5.detach(), tmp2, (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1))
+            wd[:, 10 * C:].copy_(tmp2)
+            pk["wd125"] = wd
+    return pk
+
+
+class BlockCtx:
+    pass
+
+
+def _bn_affine(bn, conv_bias, s_sum, s_sq, count, training, dev):
+    Cn = bn.weight.numel()
+    aff = _e((4, Cn), F32, dev)   # scale, shift, mean, invstd
+    if training:
+        ops.bn_finalize(s_sum, s_sq, count, bn.weight.detach(), bn.bias.detach(), conv_bias.detach() if conv_bias is not None else None,
+                        bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, aff[0], aff[1], aff[2], aff[3])
+    else:
+        ops.bn_eval_affine(bn.weight.detach(), bn.bias.detach(), conv_bias.detach() if conv_bias is not None else None,
+                           bn.running_mean, bn.running_var, BN_EPS, aff[0], aff[1])
+    return aff
+
+
+def attention_forward(bp, pooled, B, ctx=None):
+    """q/k/v 1x1 convs, softmax(q k^T), attn v on the pooled map [B, N, C] fp32 (reference :28-34)."""
+    dev = pooled.device
+    C, Cq, N = bp.C, bp.Cq, bp.P * bp.P
+    BN = B * N
+    q, k, v = _e((BN, Cq), F32, dev), _e((BN, Cq), F32, dev), _e((BN, C), F32, dev)
+    ops.sgemm(1, BN, Cq, C, pooled, (0, C, 1), bp.Wq.detach(), (0, 1, C), q, (0, Cq, 1), bias_n=bp.bq.detach())
+    ops.sgemm(1, BN, Cq, C, pooled, (0, C, 1), bp.Wk.detach(), (0, 1, C), k, (0, Cq, 1), bias_n=bp.bk.detach())
+    ops.sgemm(1, BN, C, C, pooled, (0, C, 1), bp.Wv.detach(), (0, 1, C), v, (0, C, 1), bias_n=bp.bv.detach())
+    S = _e((B, N, N), F32, dev)
+    ops.sgemm(B, N, N, Cq, q, (N * Cq, Cq, 1), k, (N * Cq, 1, Cq), S, (N * N, N, 1))       # S[i,j] = q_i . k_j
+    attn = _e((B, N, N), F32, dev)
+    ops.softmax_rows(S, attn)
+    o = _e((B, N, C), F32, dev)
+    ops.sgemm(B, N, C, N, attn, (N * N, N, 1), v, (N * C, C, 1), o, (N * C, C, 1))         # o[i,c] = sum_j attn[i,j] v[j,c]
+    if ctx is not None:
+        ctx.q, ctx.k, ctx.v, ctx.attn, ctx.pooled = q, k, v, attn, pooled
+    return o
+
+
+def attention_backward(bp, ctx, d_o, B, grads):
+    """Backward of attention_forward; returns dpooled [B, N, C] and fills the q/k/v weight and bias gradients."""
+    dev = d_o.device
+    C, Cq, N = bp.C, bp.Cq, bp.P * bp.P
+    BN = B * N
+    q, k, v, attn, pooled = ctx.q, ctx.k, ctx.v, ctx.attn, ctx.pooled
+    dv = _e((BN, C), F32, dev)
+    ops.sgemm(B, N, C, N, attn, (N * N, 1, N), d_o, (N * C, C, 1), dv, (N * C, C, 1))      # dv[j,c] = sum_i attn[i,j] do[i,c]
+    dattn = _e((B, N, N), F32, dev)
+    ops.sgemm(B, N, N, C, d_o, (N * C, C, 1), v, (N * C, 1, C), dattn, (N * N, N, 1))      # dattn[i,j] = sum_c do[i,c] v[j,c]
+    dS = _e((B, N, N), F32, dev)
+    ops.softmax_rows_bwd(attn, dattn, dS)
+    dq, dk = _e((BN, Cq), F32, dev), _e((BN, Cq), F32, dev)
+    ops.sgemm(B, N, Cq, N, dS, (N * N, N, 1), k, (N * Cq, Cq, 1), dq, (N * Cq, Cq, 1))     # dq[i,c] = sum_j dS[i,j] k[j,c]
+    ops.sgemm(B, N, Cq, N, dS, (N * N, 1, N), q, (N * Cq, Cq, 1), dk, (N * Cq, Cq, 1))     # dk[j,c] = sum_i dS[i,j] q[i,c]
+    dp = _e((BN, C), F32, dev)
+    ops.sgemm(1, BN, C, Cq, dq, (0, Cq, 1), bp.Wq.detach(), (0, C, 1), dp, (0, C, 1))
+    ops.sgemm(1, BN, C, Cq, dk, (0, Cq, 1), bp.Wk.detach(), (0, C, 1), dp, (0, C, 1), beta=1.0)
+    ops.sgemm(1, BN, C, C, dv, (0, C, 1), bp.Wv.detach(), (0, C, 1), dp, (0, C, 1), beta=1.0)
+    for W, b, d, n_out in ((bp.Wq, bp.bq, dq, Cq), (bp.Wk, bp.bk, dk, Cq), (bp.Wv, bp.bv, dv, C)):
+        gW = grads[W]
+        ops.sgemm(1, n_out, C, BN, d, (0, 1, n_out), pooled, (0, C, 1), gW, (0, C, 1))     # dW[o,c] = sum_m d[m,o] p[m,c]
+        ops.colsum(d, grads[b])
+    return dp
+
+
+def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=True, save=True):
+    """One DynamicFusionConvAttnBlock.  x: [M, Ci] (fp16, or fp32 for the image); y / yp: fp16 output views (full
+    resolution / 2x2 max-pooled); yb / ypb: their bf16 shadows.  Returns the context the backward needs."""
+    dev = x.device
+    C, Ci, P = bp.C, bp.Ci, bp.P
+    M = B * H * W
+    ctx = BlockCtx() if (training and save) else None
+    st = _z((10 * C,), F64, dev) if training else None
+    L0, AR = _e((M, C), F16, dev), _e((M, 2 * C), F16, dev)
+    segs3, segs1 = [(x, TAP_3x3)], [(x, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs3, pk["w1"], C, L0, stats=st[0:2 * C] if training else None,
+                  backend=_backend(segs3, pk["w1"], C, L0))
+    ops.conv_gemm(B, H, W, segs1, pk["w25"], 2 * C, AR, stats=st[2 * C:6 * C] if training else None,
+                  backend=_backend(segs1, pk["w25"], 2 * C, AR))
+    A0, R = AR[:, :C], AR[:, C:]
+    bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
+    bn2 = _bn_affine(bp.bn2, bp.b2, st[2 * C:3 * C] if training else None, st[4 * C:5 * C] if training else None, M, training, dev)
+    # pooled self-attention
+    tmp = _e((B, H, P, C), F32, dev)
+    pooled = _e((B * P * P, C), F32, dev)
+    ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled)
+    o = attention_forward(bp, pooled, B, ctx)
+    z = _e((M, 3 * C), F16, dev)
+    ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z)
+    # gate
+    G0 = _e((M, C), F16, dev)
+    zLA = z[:, C:]
+    segs = [(zLA, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["w3"], C, G0, stats=st[6 * C:8 * C] if training else None, backend=_backend(segs, pk["w3"], C, G0))
+    bn3 = _bn_affine(bp.bn3, bp.b3, st[6 * C:7 * C] if training else None, st[7 * C:8 * C] if training else None, M, training, dev)
+    ops.gate_mix_fwd(G0, bn3[0], bn3[1], z)
+    # fusion
+    F0 = _e((M, C), F16, dev)
+    segs = [(z, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["w4"], C, F0, stats=st[8 * C:10 * C] if training else None, backend=_backend(segs, pk["w4"], C, F0))
+    bn4 = _bn_affine(bp.bn4, bp.b4, st[8 * C:9 * C] if training else None, st[9 * C:10 * C] if training else None, M, training, dev)
+    ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp)
+    if yb is not None:
+        ops.cast2d(y, yb)
+    if ypb is not None and yp is not None:
+        ops.cast2d(yp, ypb)
+    if ctx is not None:
+        zb = _e((M, 3 * C), BF16, dev)
+        ops.cast2d(z, zb)
+        ctx.B, ctx.H, ctx.W = B, H, W
+        ctx.L0, ctx.A0, ctx.R, ctx.G0, ctx.F0, ctx.z, ctx.zb, ctx.y, ctx.o = L0, A0, R, G0, F0, z, zb, y, o
+        ctx.bn1, ctx.bn2, ctx.bn3, ctx.bn4 = bn1, bn2, bn3, bn4
+    return ctx
+
+
+def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None):
+    tc = ops.wgrad_tc_eligible(x, dy) and x.dtype == dy.dtype
+    ops.conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=alpha, backend=BACKEND_TC if tc else BACKEND_SIMT)
+
+
+def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
+    """Backward of block_forward.  xw: the block input as the weight-gradient operand (bf16 shadow, or the fp32 image).
+    dskip: bf16 gradient w.r.t. y ([M, C] view, updated in place when dyp is given); dyp: bf16 gradient w.r.t. the
+    max-pooled output or None; dx_out: bf16 [M, Ci] view that receives the input gradient, or None.
+    grads: dict parameter -> fp32 gradient tensor (zero-initialised where the kernels accumulate)."""
+    dev = dskip.device if dskip is not None else dyp.device
+    B, H, W = ctx.B, ctx.H, ctx.W
+    C, Ci, P = bp.C, bp.Ci, bp.P
+    M = B * H * W
+    red = _z((8 * C + 2,), F64, dev)
+    red1, red2, red3, red4 = red[0:2 * C], red[2 * C:4 * C], red[4 * C:6 * C], red[6 * C:8 * C]
+    drs, dgam = red[8 * C:8 * C + 1], red[8 * C + 1:8 * C + 2]
+    bn1, bn2, bn3, bn4 = ctx.bn1, ctx.bn2, ctx.bn3, ctx.bn4
+    if dskip is None:
+        dskip_buf = _e((M, C), BF16, dev)
+        dy = dskip_buf
+    else:
+        dy = dskip
+    # out = relu(bn4(F0)) + res_scale * R
+    ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.F0, ctx.R, B, H, W, bn4[0], bn4[1], bn4[2], bn4[3], dy, red4, drs)
+    dF0 = _e((M, C), BF16, dev)
+    ops.bn_bwd_apply(dy, ctx.F0, bn4[0], bn4[1], bn4[2], bn4[3], red4, 0, dF0)
+    ops.bn_param_grads(red4, C, grads[bp.bn4.weight], grads[bp.bn4.bias])
+    # fusion conv
+    dz = _e((M, 3 * C), BF16, dev)
+    segs = [(dF0, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["wd4"], 3 * C, dz, backend=_backend(segs, pk["wd4"], 3 * C, dz))
+    _wgrad(B, H, W, ctx.zb, TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 3 * C))
+    # gate / mix
+    ops.gate_mix_bwd_reduce(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3)
+    dG0 = dF0   # dF0 is dead after the fusion wgrad: reuse its storage
+    ops.gate_mix_bwd_apply(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3, dG0)
+    ops.bn_param_grads(red3, C, grads[bp.bn3.weight], grads[bp.bn3.bias])
+    dLA = dz[:, C:]
+    segs = [(dG0, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["wd3"], 2 * C, dLA, accumulate=True, backend=_backend(segs, pk["wd3"], 2 * C, dLA))
+    _wgrad(B, H, W, ctx.zb[:, C:], TAP_1x1, dG0, TAP_1x1, grads[bp.W3].view(C, 2 * C))
+    # branches
+    tmp = _e((B, H, P, C), F32, dev)
+    d_o = _e((B * P * P, C), F32, dev)
+    ops.branch_bwd_reduce1(dz, ctx.L0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], ctx.o, P, bp.gamma.detach(), red1, dgam, tmp, d_o)
+    dpooled = attention_backward(bp, ctx, d_o, B, grads)
+    ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
+    dL0, dA0 = _e((M, C), BF16, dev), dG0
+    ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
+    ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
+    ops.bn_param_grads(red2, C, grads[bp.bn2.weight], grads[bp.bn2.bias])
+    grads[bp.gamma].copy_(dgam)
+    grads[bp.res_scale].copy_(drs[0])
+    # the three convs that read x
+    if dx_out is not None:
+        segs = [(dL0, TAP_3x3), (dA0, TAP_1x1), (dy, TAP_1x1)]
+        ops.conv_gemm(B, H, W, segs, pk["wd125"], Ci, dx_out, backend=_backend(segs, pk["wd125"], Ci, dx_out))
+    dW1p = _z((C, 9 * Ci), F32, dev)
+    _wgrad(B, H, W, xw, TAP_3x3, dL0, TAP_1x1, dW1p)
+    ops.permute3(dW1p, grads[bp.W1], (C, Ci, 9), (9 * Ci, 1, Ci))
+    _wgrad(B, H, W, xw, TAP_1x1, dA0, TAP_1x1, grads[bp.W2].view(C, Ci))
+    _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1))
+    # conv biases in front of a train-mode BatchNorm have exactly zero gradient: grads[...] stay zero
+
+
+class NetCtx:
+    pass
+
+
+def _blocks(net):
+    return [net.down1, net.down2, net.down3, net.down4, net.bottleneck, net.up_conv4, net.up_conv3, net.up_conv2, net.up_conv1]
+
+
+def net_forward(net, x_nchw, training, save=True):
+    """UNetDFCSA.forward (reference :161-204).  Returns (logits NCHW fp32, ctx).  training selects batch-statistics
+    BatchNorm; save keeps what the backward needs (and writes the bf16 shadows)."""
+    keep = training and save
+    dev = x_nchw.device
+    if not x_nchw.is_cuda:
+        raise RuntimeError("dfcsa: the model runs on CUDA tensors only (no CPU fallback)")
+    B, Cin, H, W = x_nchw.shape
+    if H % 16 or W % 16:
+        raise NotImplementedError("dfcsa: H and W must be multiples of 16 (the reference's bilinear re-size fallback at "
+                                  "models/unet_dfc_sa_res.py:180-181 is not on the 224/512/1024 hot path)")
+    x_nchw = x_nchw.contiguous().float()
+    bps = [BlockParams(b) for b in _blocks(net)]
+    pks = [pack_block_weights(bp, keep, need_dx=(i > 0)) for i, bp in enumerate(bps)]
+    f = [bps[i].C for i in range(4)]
+    ctx = NetCtx() if keep else None
+    Hs = [H >> i for i in range(5)]
+    Ws = [W >> i for i in range(5)]
+    Ms = [B * Hs[i] * Ws[i] for i in range(5)]
+    x0 = _e((Ms[0], Cin), F32, dev)
+    ops.nchw_to_nhwc(x_nchw, x0, B, Cin, H, W)
+    cat = [_e((Ms[i], 2 * f[i]), F16, dev) for i in range(4)]      # [up | skip] per level
+    catb = [_e((Ms[i], 2 * f[i]), BF16, dev) for i in range(4)] if keep else [None] * 4
+    bctx = [None] * 9
+    xin, xinb = x0, x0
+    xs = []
+    for i in range(4):   # encoder
+        yp = _e((Ms[i + 1], f[i]), F16, dev)
+        ypb = _e((Ms[i + 1], f[i]), BF16, dev) if keep else None
+        xs.append(xinb)
+        bctx[i] = block_forward(bps[i], pks[i], xin, B, Hs[i], Ws[i], cat[i][:, f[i]:], yp,
+                                catb[i][:, f[i]:] if keep else None, ypb, training, keep)
+        xin, xinb = yp, ypb
+    u = _e((Ms[4], 2 * f[3]), F16, dev)
+    ub = _e((Ms[4], 2 * f[3]), BF16, dev) if keep else None
+    xs.append(xinb)
+    bctx[4] = block_forward(bps[4], pks[4], xin, B, Hs[4], Ws[4], u, None, ub, None, training, keep)
+    ups = [net.up4, net.up3, net.up2, net.up1]
+    upk, uin = [], []
+    for j, lvl in enumerate((3, 2, 1, 0)):   # decoder
+        up = ups[j]
+        Ci_t, Co_t = up.weight.shape[0], up.weight.shape[1]
+        tc = Ci_t % 64 == 0 and Co_t % 64 == 0
+        wt = _e((4 * Co_t, Ci_t), F16 if tc else F32, dev)         # [(q, co), ci]
+        ops.permute3(up.weight.detach(), wt, (4, Co_t, Ci_t), (1, 4, Co_t * 4))
+        segs = [(u, TAP_1x1)]
+        dst = cat[lvl][:, :f[lvl]]
+        ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, wt, 4 * Co_t, dst, out_mode=OUT_CONVT2x2, bias=up.bias.detach(),
+                      backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT)
+        if keep:
+            ops.cast2d(dst, catb[lvl][:, :f[lvl]])
+            wdt = _e((Ci_t, 4 * Co_t), BF16 if tc else F32, dev)   # [ci, (q, co)]
+            ops.permute3(up.weight.detach(), wdt, (Ci_t, 4, Co_t), (Co_t * 4, 1, 4))
+            upk.append(wdt)
+            uin.append(ub)
+        un = _e((Ms[lvl], f[lvl]), F16, dev)
+        unb = _e((Ms[lvl], f[lvl]), BF16, dev) if keep else None
+        xs.append(catb[lvl])
+        bctx[5 + j] = block_forward(bps[5 + j], pks[5 + j], cat[lvl], B, Hs[lvl], Ws[lvl], un, None, unb, None, training, keep)
+        u, ub = un, unb
+    # final 1x1 conv (Co = out_channels is tiny: fp32 SIMT path, logits in fp32)
+    fc = net.final_conv
+    Cout = fc.weight.shape[0]
+    logits_nhwc = _e((Ms[0], Cout), F32, dev)
+    ops.conv_gemm(B, H, W, [(u, TAP_1x1)], fc.weight.detach().view(Cout, -1), Cout, logits_nhwc, bias=fc.bias.detach(), backend=BACKEND_SIMT)
+    if Cout == 1:
+        logits = logits_nhwc.view(B, 1, H, W)
+    else:
+        logits = _e((B, Cout, H, W), F32, dev)
+        ops.nhwc_to_nchw(logits_nhwc, logits, B, Cout, H, W)
+    if training:
+        bns = [m for blk in _blocks(net) for m in (blk.conv_branch[1], blk.attn_branch[1], blk.gate[1], blk.fusion_conv[1])]
+        torch._foreach_add_([m.num_batches_tracked for m in bns], 1)
+    if keep:
+        ctx.bps, ctx.pks, ctx.bctx, ctx.xs = bps, pks, bctx, xs
+        ctx.upk, ctx.uin, ctx.u_last, ctx.u_lastb = upk, uin, u, ub
+        ctx.dims = (B, Cin, H, W, f, Hs, Ws, Ms)
+    return logits, ctx
+
+
+def net_param_list(net):
+    return [p for p in net.parameters()]
+
+
+def net_backward(net, ctx, dlogits_nchw, grads, after_stage=None):
+    """Backward of net_forward: fills grads[param] (fp32, must be zero-initialised) for every parameter.
+    after_stage(k), if given, is called when the k-th gradient bucket of trainer.reduce_buckets() is complete."""
+    stage = [0]
+
+    def done():
+        if after_stage is not None:
+            after_stage(stage[0])
+        stage[0] += 1
+    dev = dlogits_nchw.device
+    B, Cin, H, W, f, Hs, Ws, Ms = ctx.dims
+    bps, pks, bctx = ctx.bps, ctx.pks, ctx.bctx
+    fc = net.final_conv
+    Cout = fc.weight.shape[0]
+    dl = _e((Ms[0], Cout), BF16, dev)
+    ops.nchw_to_nhwc(dlogits_nchw.contiguous().float(), dl, B, Cout, H, W)
+    # final conv backward (K = Cout is tiny: SIMT)
+    du = _e((Ms[0], f[0]), BF16, dev)
+    wdf = fc.weight.detach().view(Cout, f[0]).t().contiguous()        # [f0, Cout]
+    ops.conv_gemm(B, H, W, [(dl, TAP_1x1)], wdf, f[0], du, backend=BACKEND_SIMT)
+    ops.conv_wgrad(B, H, W, ctx.u_lastb, TAP_1x1, dl, TAP_1x1, grads[fc.weight].view(Cout, f[0]), backend=BACKEND_SIMT)
+    ops.colsum(dl, grads[fc.bias])
+    ups = [net.up4, net.up3, net.up2, net.up1]
+    dcat = [None] * 4
+    for j, lvl in reversed(list(enumerate((3, 2, 1, 0)))):   # up_conv1 first
+        dcat[lvl] = _e((Ms[lvl], 2 * f[lvl]), BF16, dev)
+        block_backward(bps[5 + j], pks[5 + j], bctx[5 + j], ctx.xs[5 + j], du, None, dcat[lvl], grads)
+        if lvl == 3:
+            done()          # {up_conv4}
+        # ConvTranspose2d backward
+        up = ups[j]
+        Ci_t, Co_t = up.weight.shape[0], up.weight.shape[1]
+        dup = dcat[lvl][:, :f[lvl]]
+        du = _e((Ms[lvl + 1], Ci_t), BF16, dev)
+        segs = [(dup, TAP_2x2S2)]
+        ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, ctx.upk[j], Ci_t, du, backend=_backend(segs, ctx.upk[j], Ci_t, du))
+        dWp = _z((Co_t, 4 * Ci_t), F32, dev)
+        _wgrad(B, Hs[lvl + 1], Ws[lvl + 1], ctx.uin[j], TAP_1x1, dup, TAP_2x2S2, dWp)
+        ops.permute3(dWp, grads[up.weight], (Ci_t, Co_t, 4), (1, 4 * Ci_t, Ci_t))
+        ops.colsum(dup, grads[up.bias])
+        if lvl != 3:
+            done()          # buckets: {final, up_conv1, up1}, {up_conv2, up2}, {up_conv3, up3}
+    # bottleneck
+    dyp = _e((Ms[4], f[3]), BF16, dev)
+    done()                  # {up4}
+    block_backward(bps[4], pks[4], bctx[4], ctx.xs[4], du, None, dyp, grads)
+    done()                  # {bottleneck}
+    for i in (3, 2, 1, 0):   # encoder
+        dx = _e((Ms[i], bps[i].Ci), BF16, dev) if i > 0 else None
+        block_backward(bps[i], pks[i], bctx[i], ctx.xs[i], dcat[i][:, f[i]:], dyp, dx, grads)
+        dyp = dx
+        if i != 1:
+            done()          # {down4}, {down3}, {down2, down1}

@@ -1,0 +1,153 @@
+"""nn.Module mirror of the reference model classes (models/unet_dfc_sa_res.py:5-220).
+
+Same class names, constructor arguments, sub-module names and therefore the same 343-entry state_dict (SURVEY.md
+App. D) and the same random initialisation for a given torch seed: the standard torch.nn layers are used purely as
+parameter containers (their forward is never called).  forward() goes through libdfcsa via dfcsa.engine; gradients
+come back through one torch.autograd.Function per network (or per stand-alone block), so torch.optim.SGD and
+clip_grad_norm_ of the reference Trainer keep working on ordinary fp32 nn.Parameters.
+"""
+import torch
+import torch.nn as nn
+
+from . import engine, ops
+
+
+class LightSelfAttention(nn.Module):
+    """reference models/unet_dfc_sa_res.py:5-39 (parameter container; the math runs inside the block kernels)."""
+
+    def __init__(self, channels, pool_size=8, ablation_on_qk_channels=8):
+        super().__init__()
+        self.pool_size = pool_size
+        self.query_conv = nn.Conv2d(channels, channels // ablation_on_qk_channels, kernel_size=1)
+        self.key_conv = nn.Conv2d(channels, channels // ablation_on_qk_channels, kernel_size=1)
+        self.value_conv = nn.Conv2d(channels, channels, kernel_size=1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        raise RuntimeError("dfcsa.LightSelfAttention is fused into DynamicFusionConvAttnBlock's kernels; call the block")
+
+
+class _BlockFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, block, need_grad, *params):
+        B, Ci, H, W = x.shape
+        dev = x.device
+        if not x.is_cuda:
+            raise RuntimeError("dfcsa: the block runs on CUDA tensors only (no CPU fallback)")
+        training = block.training
+        keep = training and need_grad
+        bp = engine.BlockParams(block)
+        pk = engine.pack_block_weights(bp, keep, need_dx=True)
+        M = B * H * W
+        xin = engine._e((M, Ci), torch.float16 if bp.tc else torch.float32, dev)
+        ops.nchw_to_nhwc(x.contiguous().float(), xin, B, Ci, H, W)
+        xb = None
+        if keep:
+            xb = engine._e((M, Ci), torch.bfloat16, dev) if bp.tc else xin
+            if bp.tc:
+                ops.cast2d(xin, xb)
+        y = engine._e((M, bp.C), torch.float16, dev)
+        bctx = engine.block_forward(bp, pk, xin, B, H, W, y, training=training, save=keep)
+        out = engine._e((B, bp.C, H, W), torch.float32, dev)
+        ops.nhwc_to_nchw(y, out, B, bp.C, H, W)
+        ctx.block, ctx.bp, ctx.pk, ctx.bctx, ctx.xb, ctx.dims = block, bp, pk, bctx, xb, (B, Ci, H, W)
+        ctx.params = params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Ci, H, W = ctx.dims
+        bp = ctx.bp
+        dev = dout.device
+        if ctx.bctx is None:
+            raise RuntimeError("dfcsa: backward through a block that ran in eval / no-grad mode")
+        M = B * H * W
+        dy = engine._e((M, bp.C), torch.bfloat16, dev)
+        ops.nchw_to_nhwc(dout.contiguous().float(), dy, B, bp.C, H, W)
+        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        dx = engine._e((M, Ci), torch.bfloat16, dev)
+        engine.block_backward(bp, ctx.pk, ctx.bctx, ctx.xb, dy, None, dx, grads)
+        dxo = engine._e((B, Ci, H, W), torch.float32, dev)
+        ops.nhwc_to_nchw(dx, dxo, B, Ci, H, W)
+        return (dxo, None, None) + tuple(grads[p] for p in ctx.params)
+
+
+class DynamicFusionConvAttnBlock(nn.Module):
+    """reference models/unet_dfc_sa_res.py:41-116."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, pool_size=8, ablation_on_qk_channels=8):
+        super().__init__()
+        if (kernel_size, stride, padding) != (3, 1, 1):
+            raise NotImplementedError("dfcsa: the DFC-SA block kernels implement the 3x3 / stride 1 / pad 1 conv branch the "
+                                      "reference network uses (models/unet_dfc_sa_res.py:132-156)")
+        self.conv_branch = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding),
+            nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
+        self.attn_branch = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True),
+            LightSelfAttention(out_channels, pool_size=pool_size, ablation_on_qk_channels=ablation_on_qk_channels))
+        self.gate = nn.Sequential(nn.Conv2d(out_channels * 2, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels), nn.Sigmoid())
+        self.fusion_conv = nn.Sequential(nn.Conv2d(out_channels * 3, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels),
+                                         nn.ReLU(inplace=True))
+        if in_channels != out_channels:
+            self.residual_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, bias=False)
+        else:
+            self.residual_conv = nn.Identity()
+        self.res_scale = nn.Parameter(torch.tensor(0.1))
+
+    def forward(self, x):
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        return _BlockFunction.apply(x, self, need_grad, *params)
+
+
+class _NetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, net, need_grad, *params):
+        logits, nctx = engine.net_forward(net, x, net.training, save=need_grad)
+        ctx.net, ctx.nctx, ctx.params = net, nctx, params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if ctx.nctx is None:
+            raise RuntimeError("dfcsa: backward through a network that ran in eval / no-grad mode")
+        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        engine.net_backward(ctx.net, ctx.nctx, dlogits, grads)
+        ctx.nctx = None
+        return (None, None, None) + tuple(grads[p] for p in ctx.params)
+
+
+class UNetDFCSA(nn.Module):
+    """reference models/unet_dfc_sa_res.py:118-204."""
+
+    def __init__(self, in_channels=3, out_channels=1, features=[64, 128, 256, 512], pool_size=8, ablation_on_qk_channels=8):
+        super().__init__()
+        kw = dict(kernel_size=3, stride=1, padding=1, pool_size=pool_size, ablation_on_qk_channels=ablation_on_qk_channels)
+        self.down1 = DynamicFusionConvAttnBlock(in_channels, features[0], **kw)
+        self.pool1 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.down2 = DynamicFusionConvAttnBlock(features[0], features[1], **kw)
+        self.pool2 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.down3 = DynamicFusionConvAttnBlock(features[1], features[2], **kw)
+        self.pool3 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.down4 = DynamicFusionConvAttnBlock(features[2], features[3], **kw)
+        self.pool4 = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.bottleneck = DynamicFusionConvAttnBlock(features[3], features[3] * 2, **kw)
+        self.up4 = nn.ConvTranspose2d(features[3] * 2, features[3], kernel_size=2, stride=2)
+        self.up_conv4 = DynamicFusionConvAttnBlock(features[3] * 2, features[3], **kw)
+        self.up3 = nn.ConvTranspose2d(features[3], features[2], kernel_size=2, stride=2)
+        self.up_conv3 = DynamicFusionConvAttnBlock(features[2] * 2, features[2], **kw)
+        self.up2 = nn.ConvTranspose2d(features[2], features[1], kernel_size=2, stride=2)
+        self.up_conv2 = DynamicFusionConvAttnBlock(features[1] * 2, features[1], **kw)
+        self.up1 = nn.ConvTranspose2d(features[1], features[0], kernel_size=2, stride=2)
+        self.up_conv1 = DynamicFusionConvAttnBlock(features[0] * 2, features[0], **kw)
+        self.final_conv = nn.Conv2d(features[0], out_channels, kernel_size=1)
+
+    def forward(self, x):
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _NetFunction.apply(x, self, need_grad, *params)
+
+
+class UNetDFCSARes(UNetDFCSA):
+    """reference models/unet_dfc_sa_res.py:207-220 (adds nothing to UNetDFCSA)."""

@@ -1,0 +1,192 @@
+"""Trainer mirror (reference utils/trainer.py:20-460) for the hot loop, plus the data-parallel step.
+
+train_step() is one iteration of Trainer.train_epoch (:115-157): forward, sigmoid + bce_dice, backward,
+clip_grad_norm_(1.0), SGD step - all on libdfcsa kernels, with no device->host sync inside (the reference does >= 7
+.item() syncs per step; here the five step scalars stay on the device and are read back once per `log_every`).
+
+Data parallel (new; the reference is single-device): one process per GPU, batch sharded by rank, per-replica
+BatchNorm statistics (standard DDP semantics), gradients summed with NCCL all-reduce on the flat gradient buffer of
+FusedSGD - issued per bucket on a side stream as soon as that bucket's last weight gradient has been enqueued, so the
+reduction of the decoder / bottleneck buckets overlaps the encoder's backward - then divided by world size inside
+the fused clip + SGD kernel (clip uses the norm of the averaged gradient, exactly as a single-process run would).
+"""
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+from . import engine, ops
+from .metrics import bce_dice_with_logits, calculate_metrics
+from .optim import FusedSGD
+
+
+class StepResult:
+    __slots__ = ("stats",)
+
+    def __init__(self, stats):
+        self.stats = stats      # device tensor [loss, bce, dice_loss, hard_iou, hard_dice]
+
+    def host(self):
+        v = self.stats.tolist()
+        return {"loss": v[0], "bce": v[1], "dice_loss": v[2], "iou": v[3], "dice": v[4]}
+
+
+def reduce_buckets(net):
+    """Parameter buckets in reverse execution order: each is reduced as soon as its backward is done."""
+    order = [[net.final_conv, net.up_conv1, net.up1], [net.up_conv2, net.up2], [net.up_conv3, net.up3], [net.up_conv4],
+             [net.up4], [net.bottleneck], [net.down4], [net.down3], [net.down2, net.down1]]
+    return [[p for m in mods for p in m.parameters()] for mods in order]
+
+
+class Trainer:
+    def __init__(self, model, train_loader, val_loader, optimizer, device, config, log_every=10):
+        self.config = config
+        self.device = torch.device(device)
+        self.model = model.to(self.device)
+        self.train_loader, self.val_loader = train_loader, val_loader
+        tr = config["training"]
+        self.loss_type = tr.get("loss", {}).get("type", "dice")
+        self.loss_params = tr.get("loss", {}).get("params", {})
+        if self.loss_type != "bce_dice":
+            raise NotImplementedError("dfcsa.Trainer runs the bce_dice loss of the DFC-SA configs")
+        # reference quirk kept: calculate_metrics reads weight_bce / weight_dice (utils/metrics.py:246-247)
+        self.w_bce = float(self.loss_params.get("weight_bce", 1.0))
+        self.w_dice = float(self.loss_params.get("weight_dice", 1.0))
+        if optimizer is None or not isinstance(optimizer, FusedSGD):
+            base = optimizer.param_groups[0] if optimizer is not None else {}
+            optimizer = FusedSGD(self.model.parameters(), lr=float(base.get("lr", tr.get("learning_rate", 0.01))),
+                                 momentum=float(base.get("momentum", tr.get("momentum", 0.9))),
+                                 weight_decay=float(base.get("weight_decay", tr.get("weight_decay", 1e-4))), max_norm=1.0)
+        self.optimizer = optimizer
+        self.num_epochs = tr.get("num_epochs", 1)
+        self.log_every = log_every
+        self.train_losses, self.val_losses = [], []
+        self.train_dice_scores, self.val_dice_scores = [], []
+        self.train_iou_scores, self.val_iou_scores = [], []
+        self.best_val_loss = float("inf")
+        log = config.get("logging", {})
+        self.log_dir = str(log.get("log_dir", "runs/dfcsa")).replace("\\", "/")
+        self.checkpoint_dir = os.path.join(self.log_dir, "checkpoints")
+        self.best_model_path = os.path.join(self.log_dir, "best_model.pth")
+        self.start_time = time.time()
+        # data parallel
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self._comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self._buckets = None
+        if self.world > 1:
+            self._buckets = []
+            for ps in reduce_buckets(self.model):
+                ptrs = sorted((self.optimizer.grads[p].data_ptr(), self.optimizer.grads[p].numel()) for p in ps)
+                lo = min(a for a, _ in ptrs)
+                hi = max(a + 4 * n for a, n in ptrs)
+                base = self.optimizer.flat_grad.data_ptr()
+                self._buckets.append(self.optimizer.flat_grad[(lo - base) // 4:(hi - base) // 4])
+
+    # ------------------------------------------------------------------------------------------------------------
+    def train_step(self, images, masks):
+        """reference utils/trainer.py:116-151 for one batch already on the device.  Returns StepResult (device scalars)."""
+        net, opt = self.model, self.optimizer
+        net.train()
+        opt.zero_grad()
+        logits, ctx = engine.net_forward(net, images, True, save=True)
+        dev = logits.device
+        n = logits.numel()
+        sums = torch.zeros(8, dtype=torch.float64, device=dev)
+        stats = torch.empty(5, dtype=torch.float32, device=dev)
+        t = masks.contiguous().float()
+        ops.bce_dice_sums(logits, t, True, sums)
+        if self.world > 1 and self.config.get("training", {}).get("global_batch_dice", False):
+            dist.all_reduce(sums)           # exact global-batch Dice / BCE; n scales with world
+            n = n * self.world
+        ops.bce_dice_finalize(sums, n, self.w_bce, self.w_dice, 1.0, stats)
+        dlogits = torch.empty_like(logits)
+        ops.bce_dice_bwd(logits, t, True, sums, self.w_bce, self.w_dice, 1.0, None, dlogits)
+        if self.world == 1:
+            engine.net_backward(net, ctx, dlogits, opt.grads)
+            opt.step()
+        else:
+            hooks = self._make_bucket_hooks()
+            engine.net_backward(net, ctx, dlogits, opt.grads, after_stage=hooks)
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            opt.step(grad_scale=1.0 / self.world)
+        return StepResult(stats)
+
+    def _make_bucket_hooks(self):
+        """after_stage(k): stage k of net_backward (k-th entry of reduce_buckets) has been enqueued -> all-reduce it."""
+        cs = self._comm_stream
+
+        def hook(k):
+            ev = torch.cuda.Event()
+            ev.record()
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                dist.all_reduce(self._buckets[k])
+        return hook
+
+    # ------------------------------------------------------------------------------------------------------------
+    def train_epoch(self, epoch):
+        running = torch.zeros(5, dtype=torch.float32, device=self.device)
+        nb = 0
+        for batch in self.train_loader:
+            images = batch["image"].to(self.device, non_blocking=True)
+            masks = batch["mask"].to(self.device, non_blocking=True)
+            r = self.train_step(images, masks)
+            running += r.stats
+            nb += 1
+        v = (running / max(nb, 1)).tolist()
+        return v[0], v[3], v[4]
+
+    @torch.no_grad()
+    def validate_epoch(self, dataloader):
+        """reference utils/trainer.py:172-265 reduced to the aggregate numbers (no per-sample CPU copies)."""
+        self.model.eval()
+        tot, nb = [0.0, 0.0, 0.0], 0
+        for batch in dataloader:
+            images = batch["image"].to(self.device)
+            masks = batch["mask"].to(self.device)
+            m = calculate_metrics(torch.sigmoid(self.model(images)), masks, self.loss_type, self.loss_params)
+            tot[0] += float(m["loss"]); tot[1] += m["iou"]; tot[2] += m["dice"]
+            nb += 1
+        nb = max(nb, 1)
+        return tot[0] / nb, tot[1] / nb, tot[2] / nb, {}
+
+    def save_checkpoint(self, epoch, metrics, is_best=False):
+        """reference utils/trainer.py:267-298 (same dict keys / file names); rank 0 only under data parallel."""
+        if self.rank != 0:
+            return
+        os.makedirs(self.checkpoint_dir, exist_ok=True)
+        ckpt = {"epoch": epoch, "model_state_dict": self.model.state_dict(), "optimizer_state_dict": self.optimizer.state_dict(),
+                "train_losses": self.train_losses, "val_losses": self.val_losses,
+                "train_dice_scores": self.train_dice_scores, "val_dice_scores": self.val_dice_scores,
+                "train_iou_scores": self.train_iou_scores, "val_iou_scores": self.val_iou_scores,
+                "best_val_loss": self.best_val_loss, "metrics": metrics}
+        torch.save(ckpt, os.path.join(self.checkpoint_dir, f"checkpoint_epoch_{epoch + 1}.pth"))
+        if is_best:
+            torch.save(self.model.state_dict(), self.best_model_path)
+            torch.save(ckpt, os.path.join(self.checkpoint_dir, "best_checkpoint.pth"))
+
+    def load_checkpoint(self, checkpoint_path):
+        """reference utils/trainer.py:300-324."""
+        ckpt = torch.load(checkpoint_path.replace("\\", "/"), map_location=self.device, weights_only=False)
+        self.model.load_state_dict(ckpt["model_state_dict"])
+        self.optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+        for k in ("train_losses", "val_losses", "train_dice_scores", "val_dice_scores", "train_iou_scores", "val_iou_scores",
+                  "best_val_loss"):
+            setattr(self, k, ckpt[k])
+        return ckpt["epoch"]
+
+    def train(self):
+        best = -1.0
+        for epoch in range(self.num_epochs):
+            tl, ti, td = self.train_epoch(epoch)
+            self.train_losses.append(tl); self.train_iou_scores.append(ti); self.train_dice_scores.append(td)
+            if self.val_loader is not None:
+                vl, vi, vd, metrics = self.validate_epoch(self.val_loader)
+                self.val_losses.append(vl); self.val_iou_scores.append(vi); self.val_dice_scores.append(vd)
+                is_best = vd > best
+                best = max(best, vd)
+                freq = self.config["training"].get("save_checkpoint_freq", 100)
+                if (epoch + 1) % freq == 0 or is_best:
+                    self.save_checkpoint(epoch, metrics, is_best)

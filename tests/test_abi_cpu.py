@@ -1,0 +1,76 @@
+"""CPU-only checks of the boundary: the C-ABI library loads without a GPU and exports exactly the symbols
+include/dfcsa.h declares; the Python mirror keeps the reference's state_dict layout; the product path refuses CPU
+tensors instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "dfcsa.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfcsa_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from dfcsa import _lib
+    lib = _lib.lib()
+    assert lib.dfcsa_version() == 100
+    declared = _declared()
+    assert declared == sorted(_lib.SYMBOLS), set(declared) ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert isinstance(lib.dfcsa_last_error(), bytes)
+
+
+def test_bad_arguments_return_error_codes_not_crashes():
+    from dfcsa import _lib
+    lib = _lib.lib()
+    assert lib.dfcsa_conv_gemm(None, 0, None) == 1
+    assert b"null params" in lib.dfcsa_last_error()
+    assert lib.dfcsa_sgemm(None, None) == 1
+
+
+def test_struct_layouts_match_header():
+    from dfcsa import _lib
+    assert ctypes.sizeof(_lib.Seg) == 24
+    assert ctypes.sizeof(_lib.ConvParams) == 16 + 3 * 24 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(_lib.WgradParams) == 16 + 32 + 32 + 16 + 8
+    assert ctypes.sizeof(_lib.ParamDesc) == 32
+
+
+def test_module_mirror_has_reference_state_dict_layout():
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    m = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)
+    sd, ref = m.state_dict(), O.init_state_dict()
+    assert list(sd.keys()) == list(ref.keys()) and len(sd) == 343
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) for k in sd)
+    assert sum(p.numel() for p in m.parameters()) == 29052083
+    assert float(m.down1.res_scale) == pytest.approx(0.1) and float(m.down1.attn_branch[3].gamma) == 0.0
+
+
+def test_factory_names_and_errors():
+    from dfcsa.model_factory import ModelFactory
+    cfg = {"model": {"name": "DFC-SA-Res-Block", "features": [8, 16, 32, 64], "pool_size": 4, "ablation_on_qk_channels": 8}}
+    m = ModelFactory.get_model(cfg)
+    assert type(m).__name__ == "UNetDFCSARes" and m.down1.attn_branch[3].pool_size == 4
+    with pytest.raises(ValueError):
+        ModelFactory.get_model({"model": {"name": "nope"}})
+    with pytest.raises(NotImplementedError):
+        ModelFactory.get_model({"model": {"name": "UNet"}})
+
+
+def test_no_cpu_fallback():
+    from dfcsa.metrics import calculate_metrics
+    from dfcsa.modules import UNetDFCSARes
+    m = UNetDFCSARes(3, 1, [8, 16, 32, 64], pool_size=4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        calculate_metrics(torch.rand(1, 1, 8, 8), torch.zeros(1, 1, 8, 8), "bce_dice", {})

@@ -1,0 +1,151 @@
+"""Parity of the CUDA path against the oracle / the reference-generated golden fixtures (GPU).
+
+Tolerances are BASELINE.json's: logits max-abs <= 2e-2, gradients relative L2 <= 3e-2 (all parameters concatenated),
+hard Dice within 1e-3 after a fixed 12-step run.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name))
+    return {k: torch.from_numpy(np.asarray(z[k])) for k in z.files}
+
+
+def test_loss_kernel_matches_reference_fixture(cuda):
+    from dfcsa.metrics import calculate_metrics
+    d = _load("metrics.npz")
+    p = d["p"].cuda().requires_grad_(True)
+    m = calculate_metrics(p, d["t"].cuda(), "bce_dice", {})
+    assert abs(float(m["loss"]) - d["loss"].item()) < 1e-5
+    assert abs(m["iou"] - d["iou"].item()) < 1e-6 and abs(m["dice"] - d["dice"].item()) < 1e-6
+    m["loss"].backward()
+    # includes p == 0 and p == 1 exactly: ATen clamps the BCE backward denominator at 1e-12
+    assert torch.allclose(p.grad.cpu(), d["dp"], rtol=1e-4, atol=1e-6 * d["dp"].abs().max().item())
+
+
+def test_loss_from_logits_matches_oracle(cuda):
+    from oracle import dfcsa_oracle as O
+    from dfcsa.metrics import bce_dice_with_logits
+    g = torch.Generator().manual_seed(3)
+    z = (torch.randn(2, 1, 40, 40, generator=g) * 6).requires_grad_(True)   # includes saturated sigmoids
+    t = (torch.rand(2, 1, 40, 40, generator=g) > 0.7).float()
+    ref = O.calculate_metrics(torch.sigmoid(z), t, "bce_dice", {})
+    (gref,) = torch.autograd.grad(ref["loss"], z)
+    zc = z.detach().cuda().requires_grad_(True)
+    loss, stats = bce_dice_with_logits(zc, t.cuda())
+    loss.backward()
+    assert abs(float(loss) - float(ref["loss"])) < 1e-5
+    s = stats.tolist()
+    assert abs(s[3] - ref["iou"]) < 1e-6 and abs(s[4] - ref["dice"]) < 1e-6
+    assert torch.allclose(zc.grad.cpu(), gref, rtol=1e-4, atol=1e-8)
+
+
+def test_small_net_matches_reference_golden(cuda):
+    """features [4,8,16,32] (fp32 SIMT kernels everywhere) against logits / loss / gradients produced by the
+    unmodified reference (tests/golden/net_p4.npz)."""
+    from dfcsa.metrics import calculate_metrics
+    from dfcsa.modules import UNetDFCSARes
+    d = _load("net_p4.npz")
+    model = UNetDFCSARes(3, 1, [4, 8, 16, 32], pool_size=4, ablation_on_qk_channels=4)
+    model.load_state_dict({k[2:]: v for k, v in d.items() if k.startswith("w:")})
+    model = model.cuda().train()
+    logits = model(d["image"].cuda())
+    assert (logits.cpu() - d["logits"]).abs().max().item() <= 2e-2
+    m = calculate_metrics(torch.sigmoid(logits), d["mask"].cuda(), "bce_dice", {"bce_weight": 0.5, "dice_weight": 0.5})
+    assert abs(float(m["loss"]) - d["loss"].item()) < 5e-3
+    m["loss"].backward()
+    num = sum(((p.grad.cpu() - d["g:" + n]) ** 2).sum() for n, p in model.named_parameters()).sqrt()
+    den = sum((d["g:" + n] ** 2).sum() for n, _ in model.named_parameters()).sqrt()
+    assert (num / den).item() <= 3e-2, (num / den).item()
+    # BatchNorm running statistics after the step
+    sd = model.state_dict()
+    for k, v in d.items():
+        if k.startswith("after:") and "running" in k:
+            assert torch.allclose(sd[k[6:]].cpu(), v, atol=3e-3, rtol=2e-2), k
+    assert int(sd["down1.conv_branch.1.num_batches_tracked"]) == 1
+
+
+def test_small_net_eval_matches_reference_golden(cuda):
+    from dfcsa.modules import UNetDFCSARes
+    d, e = _load("net_p4.npz"), _load("net_eval.npz")
+    sd = {k[2:]: v for k, v in d.items() if k.startswith("w:")}
+    for k, v in d.items():
+        if k.startswith("after:") and "running" in k:
+            sd[k[6:]] = v
+    model = UNetDFCSARes(3, 1, [4, 8, 16, 32], pool_size=4, ablation_on_qk_channels=4)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    with torch.no_grad():
+        logits = model(e["image"].cuda())
+    assert (logits.cpu() - e["logits"]).abs().max().item() <= 2e-2
+
+
+def test_block_matches_reference_golden(cuda):
+    from dfcsa.modules import DynamicFusionConvAttnBlock
+    d = _load("block_p4.npz")
+    blk = DynamicFusionConvAttnBlock(3, 16, pool_size=4, ablation_on_qk_channels=8)
+    blk.load_state_dict({k[2:]: v for k, v in d.items() if k.startswith("w:")})
+    blk = blk.cuda().train()
+    out = blk(d["x"].cuda())
+    assert (out.cpu() - d["out"]).abs().max().item() <= 2e-2
+    (out * d["r"].cuda()).sum().backward()
+    num = sum(((p.grad.cpu() - d["g:" + n]) ** 2).sum() for n, p in blk.named_parameters()).sqrt()
+    den = sum((d["g:" + n] ** 2).sum() for n, _ in blk.named_parameters()).sqrt()
+    assert (num / den).item() <= 3e-2, (num / den).item()
+
+
+@pytest.mark.parametrize("gamma", [0.0, 0.5])
+@pytest.mark.parametrize("hw,B,P", [(64, 2, 4), (224, 2, 4), (96, 2, 8)])
+def test_full_width_net_matches_oracle(cuda, hw, B, P, gamma):
+    """features [64,128,256,512]: every conv except the Ci=3 layer and the final conv runs on tcgen05."""
+    from dfcsa.selftest import forward_backward_parity
+    r = forward_backward_parity(pool_size=P, B=B, H=hw, W=hw, gamma=gamma)
+    print(r)
+    assert r["logit_maxabs"] <= 2e-2, r
+    assert r["grad_rel_l2"] <= 3e-2, r
+    assert abs(r["loss"] - r["loss_ref"]) <= 2e-3, r
+
+
+def test_state_dict_layout_and_roundtrip(cuda):
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    m = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)
+    sd = m.state_dict()
+    ref = O.init_state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(tuple(sd[k].shape) == tuple(ref[k].shape) and sd[k].dtype == ref[k].dtype for k in sd)
+    m2 = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)
+    m2.load_state_dict(ref)
+    assert sum(p.numel() for p in m2.parameters()) == 29052083
+
+
+def test_twelve_step_dice_trajectory(cuda):
+    """BASELINE.json: Dice within 1e-3 after a fixed short run (12 SGD steps, two alternating batches of 4, lr .01,
+    momentum .9, wd 1e-4, clip 1.0) - fused trainer path vs the oracle's train_step."""
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    from dfcsa.selftest import oracle_state, set_gamma
+    from dfcsa.trainer import Trainer
+    torch.manual_seed(0)
+    model = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)
+    set_gamma(model, 0.5)
+    sd = oracle_state(model)
+    batches = [O.synthetic_batch(4, 64, 64, seed=s) for s in (1, 2)]
+    cfg = {"training": {"loss": {"type": "bce_dice", "params": {"bce_weight": 0.5, "dice_weight": 0.5}}, "num_epochs": 1},
+           "logging": {"log_dir": "/tmp/dfcsa_test"}}
+    tr = Trainer(model, None, None, None, "cuda", cfg)
+    bufs = None
+    for step in range(12):
+        img, mask = batches[step % 2]
+        ref = O.train_step(sd, bufs, img, mask, pool_size=4)
+        bufs = ref["bufs"]
+        got = tr.train_step(img.cuda(), mask.cuda()).host()
+        assert abs(got["dice"] - ref["dice"]) <= 1e-3, (step, got, ref["dice"])
+        assert abs(got["loss"] - ref["loss"]) <= 5e-3, (step, got, ref["loss"])
