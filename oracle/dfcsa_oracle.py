@@ -167,10 +167,10 @@ def dice_loss(pred, target, smooth=1.0):
 
 
 def bce_loss(pred, target):
-    """nn.BCELoss (mean) with ATen's log clamp at -100 (reference utils/metrics.py:60,74)."""
-    lp = torch.clamp(torch.log(pred), min=-100.0)
-    l1p = torch.clamp(torch.log(1 - pred), min=-100.0)
-    return -(target * lp + (1 - target) * l1p).mean()
+    """nn.BCELoss() as constructed at reference utils/metrics.py:60 and called at :74: mean reduction; ATen clamps the
+    log terms at -100 in the forward and the denominator p*(1-p) at 1e-12 in the backward, so saturated probabilities
+    give finite (zero-ish) gradients - restating it with torch.clamp(torch.log(p)) would give NaN gradients there."""
+    return F.binary_cross_entropy(pred, target)
 
 
 def calculate_metrics(pred, target, loss_type="bce_dice", loss_params=None):
