@@ -103,6 +103,45 @@ def check(rc, what=""):
         raise RuntimeError(f"libdfcsa {what} failed (code {rc}): {msg}")
 
 
+class Profiler:
+    """Optional per-entry-point timing with CUDA events on the launching stream (bench.py's roofline numbers)."""
+
+    def __init__(self):
+        self.records = []       # (tag, flops, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for tag, flops, e0, e1 in self.records:
+            a = agg.setdefault(tag, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["launches"] += 1
+        return agg
+
+
+PROF = None          # set to a Profiler() to time every ABI call
+LAUNCHES = 0         # kernels enqueued through the ABI (bench.py's gpu_launches)
+# entry points that enqueue more than one kernel
+_KERNELS = {"dfcsa_bnrelu_pool_fwd": 2, "dfcsa_branch_bwd_reduce1": 3}
+
+
+def call(name, *args, tag=None, flops=0.0):
+    """Invoke one ABI entry point on the current stream; raise on a non-zero return code."""
+    global LAUNCHES
+    fn = getattr(lib(), name)
+    if PROF is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROF.records.append((tag or name[6:], flops, e0, e1))
+    else:
+        rc = fn(*args)
+    LAUNCHES += _KERNELS.get(name, 1)
+    check(rc, name)
+
+
 def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -46,7 +46,9 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.accumulate = 1 if accumulate else 0
     p.bias = bias.data_ptr() if bias is not None else None
     p.stats = stats.data_ptr() if stats is not None else None
-    L.check(L.lib().dfcsa_conv_gemm(C.byref(p), backend, L.stream()), "dfcsa_conv_gemm")
+    ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
+    L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
+           flops=2.0 * B * H * W * N * ktot)
 
 
 def conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw, alpha=None, backend=BACKEND_TC):
@@ -57,7 +59,9 @@ def conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw, alpha=None, backend=BACKEND_
     p.dy, p.ld_dy, p.N, p.dy_dtype, p.dy_tap_mode = dy.data_ptr(), _mat(dy), dy.shape[1], L.dt(dy), dy_mode
     p.dw, p.ld_dw = dw.data_ptr(), dw.stride(0)
     p.alpha = alpha.data_ptr() if alpha is not None else None
-    L.check(L.lib().dfcsa_conv_wgrad(C.byref(p), backend, L.stream()), "dfcsa_conv_wgrad")
+    taps = 9 if x_mode == TAP_3x3 else (4 if dy_mode == TAP_2x2S2 else 1)
+    L.call("dfcsa_conv_wgrad", C.byref(p), backend, L.stream(), tag="wgrad_tc" if backend == BACKEND_TC else "wgrad_simt",
+           flops=2.0 * B * H * W * taps * x.shape[1] * dy.shape[1])
 
 
 def wgrad_tc_eligible(x, dy):
@@ -67,10 +71,10 @@ def wgrad_tc_eligible(x, dy):
 
 def permute3(src, dst, D, s, flip1=False, scale=None):
     """dst[(i0*D1+i1)*D2+i2] = scale*src[i0*s0 + i1'*s1 + i2*s2]   (dfcsa_permute3)."""
-    L.check(L.lib().dfcsa_permute3(L.ptr(src), L.dt(src), L.ptr(dst), L.dt(dst),
+    L.call("dfcsa_permute3", L.ptr(src), L.dt(src), L.ptr(dst), L.dt(dst),
                                    C.c_int64(D[0]), C.c_int64(D[1]), C.c_int64(D[2]),
                                    C.c_int64(s[0]), C.c_int64(s[1]), C.c_int64(s[2]),
-                                   1 if flip1 else 0, L.ptr(scale), L.stream()), "dfcsa_permute3")
+                                   1 if flip1 else 0, L.ptr(scale), L.stream())
 
 
 def sgemm(batch, M, N, K, A, a_str, Bm, b_str, Cm, c_str, alpha=1.0, beta=0.0, bias_n=None, bias_m=None):
@@ -83,18 +87,17 @@ def sgemm(batch, M, N, K, A, a_str, Bm, b_str, Cm, c_str, alpha=1.0, beta=0.0, b
     p.bias_n = bias_n.data_ptr() if bias_n is not None else None
     p.bias_m = bias_m.data_ptr() if bias_m is not None else None
     p.alpha, p.beta = alpha, beta
-    L.check(L.lib().dfcsa_sgemm(C.byref(p), L.stream()), "dfcsa_sgemm")
+    L.call("dfcsa_sgemm", C.byref(p), L.stream())
 
 
 def softmax_rows(x, y):
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
-    L.check(L.lib().dfcsa_softmax_rows(L.ptr(x), L.ptr(y), C.c_int64(rows), cols, L.stream()), "dfcsa_softmax_rows")
+    L.call("dfcsa_softmax_rows", L.ptr(x), L.ptr(y), C.c_int64(rows), cols, L.stream())
 
 
 def softmax_rows_bwd(y, dy, dx):
     rows, cols = y.numel() // y.shape[-1], y.shape[-1]
-    L.check(L.lib().dfcsa_softmax_rows_bwd(L.ptr(y), L.ptr(dy), L.ptr(dx), C.c_int64(rows), cols, L.stream()),
-            "dfcsa_softmax_rows_bwd")
+    L.call("dfcsa_softmax_rows_bwd", L.ptr(y), L.ptr(dy), L.ptr(dx), C.c_int64(rows), cols, L.stream())
 
 
 def _i64(v):
@@ -103,143 +106,139 @@ def _i64(v):
 
 def bn_finalize(s_sum, s_sq, count, gamma, beta, conv_bias, rmean, rvar, momentum, eps, scale, shift, mean, invstd):
     Cn = gamma.numel()
-    L.check(L.lib().dfcsa_bn_finalize(L.ptr(s_sum), L.ptr(s_sq), _i64(count), Cn, L.ptr(gamma), L.ptr(beta),
+    L.call("dfcsa_bn_finalize", L.ptr(s_sum), L.ptr(s_sq), _i64(count), Cn, L.ptr(gamma), L.ptr(beta),
                                       L.ptr(conv_bias), L.ptr(rmean), L.ptr(rvar), C.c_float(momentum), C.c_float(eps),
-                                      L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.stream()), "dfcsa_bn_finalize")
+                                      L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.stream())
 
 
 def bn_eval_affine(gamma, beta, conv_bias, rmean, rvar, eps, scale, shift):
-    L.check(L.lib().dfcsa_bn_eval_affine(gamma.numel(), L.ptr(gamma), L.ptr(beta), L.ptr(conv_bias), L.ptr(rmean),
-                                         L.ptr(rvar), C.c_float(eps), L.ptr(scale), L.ptr(shift), L.stream()),
-            "dfcsa_bn_eval_affine")
+    L.call("dfcsa_bn_eval_affine", gamma.numel(), L.ptr(gamma), L.ptr(beta), L.ptr(conv_bias), L.ptr(rmean),
+                                         L.ptr(rvar), C.c_float(eps), L.ptr(scale), L.ptr(shift), L.stream())
 
 
 def bn_param_grads(red, Cn, dgamma, dbeta):
-    L.check(L.lib().dfcsa_bn_param_grads(L.ptr(red), Cn, L.ptr(dgamma), L.ptr(dbeta), L.stream()), "dfcsa_bn_param_grads")
+    L.call("dfcsa_bn_param_grads", L.ptr(red), Cn, L.ptr(dgamma), L.ptr(dbeta), L.stream())
 
 
 def bnrelu_pool_fwd(a0, B, H, W, scale, shift, P, tmp, pooled):
-    L.check(L.lib().dfcsa_bnrelu_pool_fwd(L.ptr(a0), _i64(_mat(a0)), B, H, W, a0.shape[1], L.ptr(scale), L.ptr(shift), P,
-                                          L.ptr(tmp), L.ptr(pooled), L.stream()), "dfcsa_bnrelu_pool_fwd")
+    L.call("dfcsa_bnrelu_pool_fwd", L.ptr(a0), _i64(_mat(a0)), B, H, W, a0.shape[1], L.ptr(scale), L.ptr(shift), P,
+                                          L.ptr(tmp), L.ptr(pooled), L.stream())
 
 
 def branch_act_fwd(l0, a0, B, H, W, s1, t1, s2, t2, o, P, gamma, z):
     Cn = l0.shape[1]
-    L.check(L.lib().dfcsa_branch_act_fwd(L.ptr(l0), _i64(_mat(l0)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s1),
+    L.call("dfcsa_branch_act_fwd", L.ptr(l0), _i64(_mat(l0)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s1),
                                          L.ptr(t1), L.ptr(s2), L.ptr(t2), L.ptr(o), P, L.ptr(gamma), L.ptr(z),
-                                         _i64(_mat(z)), L.stream()), "dfcsa_branch_act_fwd")
+                                         _i64(_mat(z)), L.stream())
 
 
 def gate_mix_fwd(g0, s3, t3, z):
     M, Cn = g0.shape
-    L.check(L.lib().dfcsa_gate_mix_fwd(L.ptr(g0), _i64(_mat(g0)), _i64(M), Cn, L.ptr(s3), L.ptr(t3), L.ptr(z),
-                                       _i64(_mat(z)), L.stream()), "dfcsa_gate_mix_fwd")
+    L.call("dfcsa_gate_mix_fwd", L.ptr(g0), _i64(_mat(g0)), _i64(M), Cn, L.ptr(s3), L.ptr(t3), L.ptr(z),
+                                       _i64(_mat(z)), L.stream())
 
 
 def block_out_fwd(f0, r, B, H, W, s4, t4, res_scale, y, yp=None):
     Cn = f0.shape[1]
-    L.check(L.lib().dfcsa_block_out_fwd(L.ptr(f0), _i64(_mat(f0)), L.ptr(r), _i64(_mat(r)), B, H, W, Cn, L.ptr(s4),
+    L.call("dfcsa_block_out_fwd", L.ptr(f0), _i64(_mat(f0)), L.ptr(r), _i64(_mat(r)), B, H, W, Cn, L.ptr(s4),
                                         L.ptr(t4), L.ptr(res_scale), L.ptr(y), _i64(_mat(y)), L.ptr(yp),
-                                        _i64(_mat(yp) if yp is not None else 0), L.stream()), "dfcsa_block_out_fwd")
+                                        _i64(_mat(yp) if yp is not None else 0), L.stream())
 
 
 def block_out_bwd_reduce(dskip, dyp, y, f0, r, B, H, W, s4, t4, mean4, invstd4, dy_out, red4, drs):
     Cn = f0.shape[1]
-    L.check(L.lib().dfcsa_block_out_bwd_reduce(
+    L.call("dfcsa_block_out_bwd_reduce", 
         L.ptr(dskip), _i64(_mat(dskip) if dskip is not None else 0), L.ptr(dyp), _i64(_mat(dyp) if dyp is not None else 0),
         L.ptr(y), _i64(_mat(y)), L.ptr(f0), _i64(_mat(f0)), L.ptr(r), _i64(_mat(r)), B, H, W, Cn,
         L.ptr(s4), L.ptr(t4), L.ptr(mean4), L.ptr(invstd4), L.ptr(dy_out), _i64(_mat(dy_out) if dy_out is not None else 0),
-        L.ptr(red4), L.ptr(drs), L.stream()), "dfcsa_block_out_bwd_reduce")
+        L.ptr(red4), L.ptr(drs), L.stream())
 
 
 def bn_bwd_apply(dy, x, scale, shift, mean, invstd, red, act_mode, dx):
     M, Cn = x.shape
-    L.check(L.lib().dfcsa_bn_bwd_apply(L.ptr(dy), _i64(_mat(dy)), L.ptr(x), _i64(_mat(x)), _i64(M), Cn, L.ptr(scale),
+    L.call("dfcsa_bn_bwd_apply", L.ptr(dy), _i64(_mat(dy)), L.ptr(x), _i64(_mat(x)), _i64(M), Cn, L.ptr(scale),
                                        L.ptr(shift), L.ptr(mean), L.ptr(invstd), None, L.ptr(red), act_mode, L.ptr(dx),
-                                       _i64(_mat(dx)), L.stream()), "dfcsa_bn_bwd_apply")
+                                       _i64(_mat(dx)), L.stream())
 
 
 def gate_mix_bwd_reduce(dz, z, g0, s3, t3, mean3, invstd3, red3):
     M, Cn = g0.shape
-    L.check(L.lib().dfcsa_gate_mix_bwd_reduce(L.ptr(dz), _i64(_mat(dz)), L.ptr(z), _i64(_mat(z)), L.ptr(g0), _i64(_mat(g0)),
+    L.call("dfcsa_gate_mix_bwd_reduce", L.ptr(dz), _i64(_mat(dz)), L.ptr(z), _i64(_mat(z)), L.ptr(g0), _i64(_mat(g0)),
                                               _i64(M), Cn, L.ptr(s3), L.ptr(t3), L.ptr(mean3), L.ptr(invstd3), L.ptr(red3),
-                                              L.stream()), "dfcsa_gate_mix_bwd_reduce")
+                                              L.stream())
 
 
 def gate_mix_bwd_apply(dz, z, g0, s3, t3, mean3, invstd3, red3, dg0):
     M, Cn = g0.shape
-    L.check(L.lib().dfcsa_gate_mix_bwd_apply(L.ptr(dz), _i64(_mat(dz)), L.ptr(z), _i64(_mat(z)), L.ptr(g0), _i64(_mat(g0)),
+    L.call("dfcsa_gate_mix_bwd_apply", L.ptr(dz), _i64(_mat(dz)), L.ptr(z), _i64(_mat(z)), L.ptr(g0), _i64(_mat(g0)),
                                              _i64(M), Cn, L.ptr(s3), L.ptr(t3), L.ptr(mean3), L.ptr(invstd3), None,
-                                             L.ptr(red3), L.ptr(dg0), _i64(_mat(dg0)), L.stream()), "dfcsa_gate_mix_bwd_apply")
+                                             L.ptr(red3), L.ptr(dg0), _i64(_mat(dg0)), L.stream())
 
 
 def branch_bwd_reduce1(dz, l0, B, H, W, s1, t1, mean1, invstd1, o, P, gamma, red1, dgamma, tmp, d_o):
     Cn = l0.shape[1]
-    L.check(L.lib().dfcsa_branch_bwd_reduce1(L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), B, H, W, Cn, L.ptr(s1),
+    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), B, H, W, Cn, L.ptr(s1),
                                              L.ptr(t1), L.ptr(mean1), L.ptr(invstd1), L.ptr(o), P, L.ptr(gamma), L.ptr(red1),
-                                             L.ptr(dgamma), L.ptr(tmp), L.ptr(d_o), L.stream()), "dfcsa_branch_bwd_reduce1")
+                                             L.ptr(dgamma), L.ptr(tmp), L.ptr(d_o), L.stream())
 
 
 def branch_bwd_reduce2(dz, a0, B, H, W, s2, t2, mean2, invstd2, dpooled, P, red2):
     Cn = a0.shape[1]
-    L.check(L.lib().dfcsa_branch_bwd_reduce2(L.ptr(dz), _i64(_mat(dz)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s2),
+    L.call("dfcsa_branch_bwd_reduce2", L.ptr(dz), _i64(_mat(dz)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s2),
                                              L.ptr(t2), L.ptr(mean2), L.ptr(invstd2), L.ptr(dpooled), P, L.ptr(red2),
-                                             L.stream()), "dfcsa_branch_bwd_reduce2")
+                                             L.stream())
 
 
 def branch_bwd_apply(dz, l0, a0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dl0, da0):
     Cn = l0.shape[1]
     s1, t1, m1, i1 = bn1
     s2, t2, m2, i2 = bn2
-    L.check(L.lib().dfcsa_branch_bwd_apply(
+    L.call("dfcsa_branch_bwd_apply", 
         L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn,
         L.ptr(s1), L.ptr(t1), L.ptr(m1), L.ptr(i1), None, L.ptr(red1),
         L.ptr(s2), L.ptr(t2), L.ptr(m2), L.ptr(i2), None, L.ptr(red2),
-        L.ptr(dpooled), P, L.ptr(dl0), _i64(_mat(dl0)), L.ptr(da0), _i64(_mat(da0)), L.stream()), "dfcsa_branch_bwd_apply")
+        L.ptr(dpooled), P, L.ptr(dl0), _i64(_mat(dl0)), L.ptr(da0), _i64(_mat(da0)), L.stream())
 
 
 def nchw_to_nhwc(src, dst2d, B, Cn, H, W):
-    L.check(L.lib().dfcsa_nchw_to_nhwc(L.ptr(src), L.ptr(dst2d), L.dt(dst2d), _i64(_mat(dst2d)), B, Cn, H, W, L.stream()),
-            "dfcsa_nchw_to_nhwc")
+    L.call("dfcsa_nchw_to_nhwc", L.ptr(src), L.ptr(dst2d), L.dt(dst2d), _i64(_mat(dst2d)), B, Cn, H, W, L.stream())
 
 
 def nhwc_to_nchw(src2d, dst, B, Cn, H, W):
-    L.check(L.lib().dfcsa_nhwc_to_nchw(L.ptr(src2d), L.dt(src2d), _i64(_mat(src2d)), L.ptr(dst), B, Cn, H, W, L.stream()),
-            "dfcsa_nhwc_to_nchw")
+    L.call("dfcsa_nhwc_to_nchw", L.ptr(src2d), L.dt(src2d), _i64(_mat(src2d)), L.ptr(dst), B, Cn, H, W, L.stream())
 
 
 def colsum(x2d, out):
     M, Cn = x2d.shape
-    L.check(L.lib().dfcsa_colsum(L.ptr(x2d), L.dt(x2d), _i64(_mat(x2d)), _i64(M), Cn, L.ptr(out), L.stream()), "dfcsa_colsum")
+    L.call("dfcsa_colsum", L.ptr(x2d), L.dt(x2d), _i64(_mat(x2d)), _i64(M), Cn, L.ptr(out), L.stream())
 
 
 def cast2d(x2d, y2d):
     M, Cn = x2d.shape
-    L.check(L.lib().dfcsa_cast2d(L.ptr(x2d), L.dt(x2d), _i64(_mat(x2d)), L.ptr(y2d), L.dt(y2d), _i64(_mat(y2d)), _i64(M), Cn,
-                                 L.stream()), "dfcsa_cast2d")
+    L.call("dfcsa_cast2d", L.ptr(x2d), L.dt(x2d), _i64(_mat(x2d)), L.ptr(y2d), L.dt(y2d), _i64(_mat(y2d)), _i64(M), Cn,
+                                 L.stream())
 
 
 def bce_dice_sums(x, t, from_logits, sums):
-    L.check(L.lib().dfcsa_bce_dice_sums(L.ptr(x), L.ptr(t), _i64(x.numel()), 1 if from_logits else 0, L.ptr(sums), L.stream()),
-            "dfcsa_bce_dice_sums")
+    L.call("dfcsa_bce_dice_sums", L.ptr(x), L.ptr(t), _i64(x.numel()), 1 if from_logits else 0, L.ptr(sums), L.stream())
 
 
 def bce_dice_finalize(sums, n, w_bce, w_dice, smooth, out):
-    L.check(L.lib().dfcsa_bce_dice_finalize(L.ptr(sums), _i64(n), C.c_float(w_bce), C.c_float(w_dice), C.c_float(smooth),
-                                            L.ptr(out), L.stream()), "dfcsa_bce_dice_finalize")
+    L.call("dfcsa_bce_dice_finalize", L.ptr(sums), _i64(n), C.c_float(w_bce), C.c_float(w_dice), C.c_float(smooth),
+                                            L.ptr(out), L.stream())
 
 
 def bce_dice_bwd(x, t, from_logits, sums, w_bce, w_dice, smooth, gout, dx):
-    L.check(L.lib().dfcsa_bce_dice_bwd(L.ptr(x), L.ptr(t), _i64(x.numel()), 1 if from_logits else 0, L.ptr(sums),
+    L.call("dfcsa_bce_dice_bwd", L.ptr(x), L.ptr(t), _i64(x.numel()), 1 if from_logits else 0, L.ptr(sums),
                                        C.c_float(w_bce), C.c_float(w_dice), C.c_float(smooth), L.ptr(gout), L.ptr(dx),
-                                       L.dt(dx), L.stream()), "dfcsa_bce_dice_bwd")
+                                       L.dt(dx), L.stream())
 
 
 def grad_sumsq(table, n_tensors, max_n, sumsq):
-    L.check(L.lib().dfcsa_grad_sumsq(L.ptr(table), n_tensors, _i64(max_n), L.ptr(sumsq), L.stream()), "dfcsa_grad_sumsq")
+    L.call("dfcsa_grad_sumsq", L.ptr(table), n_tensors, _i64(max_n), L.ptr(sumsq), L.stream())
 
 
 def sgd_step(table, n_tensors, max_n, sumsq, gscale, max_norm, lr, momentum, weight_decay, first_step):
-    L.check(L.lib().dfcsa_sgd_step(L.ptr(table), n_tensors, _i64(max_n), L.ptr(sumsq), C.c_float(gscale), C.c_float(max_norm),
+    L.call("dfcsa_sgd_step", L.ptr(table), n_tensors, _i64(max_n), L.ptr(sumsq), C.c_float(gscale), C.c_float(max_norm),
                                    C.c_float(lr), C.c_float(momentum), C.c_float(weight_decay), 1 if first_step else 0,
-                                   L.stream()), "dfcsa_sgd_step")
+                                   L.stream())

@@ -18,6 +18,10 @@ import math
 import torch
 import torch.nn.functional as F
 
+# bench.py's CPU-baseline leg sets this so the timed port issues the same ATen calls the reference issues
+# (F.batch_norm, F.adaptive_avg_pool2d, F.interpolate) instead of the explicit restatements; tests check both agree.
+USE_ATEN_OPS = False
+
 # --------------------------------------------------------------------------------------------------------------
 # index rules
 # --------------------------------------------------------------------------------------------------------------
@@ -50,6 +54,8 @@ def bilinear_matrix(P, s, dtype=torch.float32):
 
 
 def adaptive_avg_pool(x, P):
+    if USE_ATEN_OPS:
+        return F.adaptive_avg_pool2d(x, (P, P))
     B, C, H, W = x.shape
     my = adaptive_pool_matrix(H, P, x.dtype)
     mx = adaptive_pool_matrix(W, P, x.dtype)
@@ -57,6 +63,8 @@ def adaptive_avg_pool(x, P):
 
 
 def bilinear_upsample(o, H, W):
+    if USE_ATEN_OPS:
+        return F.interpolate(o, size=(H, W), mode="bilinear", align_corners=False)
     B, C, P, Q = o.shape
     my = bilinear_matrix(P, H, o.dtype)
     mx = bilinear_matrix(Q, W, o.dtype)
@@ -72,6 +80,10 @@ def batch_norm(x, sd, prefix, training, momentum=0.1, eps=1e-5, update_running=T
     """nn.BatchNorm2d (reference models/unet_dfc_sa_res.py:60,67,75,82): batch statistics with biased variance for
     normalisation; running_var gets the unbiased variance; num_batches_tracked += 1."""
     w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    if USE_ATEN_OPS and (update_running or not training):
+        if training:
+            sd[prefix + ".num_batches_tracked"] += 1
+        return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"], w, b, training, momentum, eps)
     if training:
         mean = x.mean(dim=(0, 2, 3))
         var = x.var(dim=(0, 2, 3), unbiased=False)
