@@ -75,6 +75,8 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream);
 int conv_gemm_simt(const dfcsa_conv_params_t* p, cudaStream_t stream);
 int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream);
 int conv_wgrad_simt(const dfcsa_wgrad_params_t* p, cudaStream_t stream);
+int conv_gemm_small(const dfcsa_conv_params_t* p, cudaStream_t stream, int* rc_out);
+int conv_wgrad_small(const dfcsa_wgrad_params_t* p, cudaStream_t stream, int* rc_out);
 
 }  // namespace dfcsa
 
@@ -96,7 +98,11 @@ extern "C" int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* 
   for (int s = 0; s < p->n_seg && s < 3; ++s)
     DFCSA_CHECK_ARG(p->seg[s].ptr != nullptr, "dfcsa_conv_gemm: null segment %d", s);
   if (backend == DFCSA_BACKEND_TC) return conv_gemm_tc(p, static_cast<cudaStream_t>(stream));
-  if (backend == DFCSA_BACKEND_SIMT) return conv_gemm_simt(p, static_cast<cudaStream_t>(stream));
+  if (backend == DFCSA_BACKEND_SIMT) {
+    int rc = DFCSA_OK;   // the tiny-K / tiny-N layers (first conv, final conv) have bandwidth-shaped kernels of their own
+    if (conv_gemm_small(p, static_cast<cudaStream_t>(stream), &rc)) return rc;
+    return conv_gemm_simt(p, static_cast<cudaStream_t>(stream));
+  }
   set_error("dfcsa_conv_gemm: unknown backend %d", backend);
   return DFCSA_ERR_BAD_ARG;
 }
@@ -107,7 +113,11 @@ extern "C" int dfcsa_conv_wgrad(const dfcsa_wgrad_params_t* p, int backend, void
   DFCSA_CHECK_ARG(!(p->x_tap_mode == DFCSA_TAP_3x3 && p->dy_tap_mode != DFCSA_TAP_1x1) && p->x_tap_mode != DFCSA_TAP_2x2S2 &&
                   p->dy_tap_mode != DFCSA_TAP_3x3, "dfcsa_conv_wgrad: unsupported tap mode combination");
   if (backend == DFCSA_BACKEND_TC) return conv_wgrad_tc(p, static_cast<cudaStream_t>(stream));
-  if (backend == DFCSA_BACKEND_SIMT) return conv_wgrad_simt(p, static_cast<cudaStream_t>(stream));
+  if (backend == DFCSA_BACKEND_SIMT) {
+    int rc = DFCSA_OK;
+    if (conv_wgrad_small(p, static_cast<cudaStream_t>(stream), &rc)) return rc;
+    return conv_wgrad_simt(p, static_cast<cudaStream_t>(stream));
+  }
   set_error("dfcsa_conv_wgrad: unknown backend %d", backend);
   return DFCSA_ERR_BAD_ARG;
 }

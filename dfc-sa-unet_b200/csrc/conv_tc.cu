@@ -44,6 +44,8 @@ struct ConvTcArgs {
   double* stats;
   int convt_co, convt_h, convt_w;
   uint32_t idesc;
+  __nv_bfloat16* shadow;
+  long long ld_shadow;
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -255,6 +257,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
           else
             store_chunk<float>(reinterpret_cast<float*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
+          if (a.shadow != nullptr) store_chunk<__nv_bfloat16>(a.shadow + pix * a.ld_shadow + cn, v, ncols, false);
         }
         if (a.stats != nullptr) {
           float sq[32];
@@ -422,6 +425,9 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
 
   a.out = p->out; a.ld_out = p->ld_out; a.out_dtype = p->out_dtype; a.out_mode = p->out_mode;
   a.accumulate = p->accumulate; a.bias = p->bias; a.stats = p->stats;
+  a.shadow = reinterpret_cast<__nv_bfloat16*>(p->shadow); a.ld_shadow = p->ld_shadow;
+  DFCSA_CHECK_ARG(p->shadow == nullptr || (!p->accumulate && p->ld_shadow % 8 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 15) == 0),
+                  "conv_gemm_tc: bad shadow output");
   if (p->out_mode == DFCSA_OUT_CONVT2x2) { a.convt_co = p->N / 4; a.convt_h = p->H; a.convt_w = p->W; }
 
   const int smem_bytes = a.stages * stage_bytes + 1024;

@@ -232,7 +232,8 @@ __device__ __forceinline__ void bilerp_gather(const float* o, long long b, int y
 template <int VEC>
 __global__ void branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H,
                                       int W, int C, const float* s1, const float* t1, const float* s2, const float* t2,
-                                      const float* o, int P, const float* gamma, act_t* z, long long ld_z) {
+                                      const float* o, int P, const float* gamma, act_t* z, long long ld_z, grad_t* zb,
+                                      long long ld_zb) {
   const int CV = C / VEC;
   const long long total = static_cast<long long>(B) * H * W * CV;
   const float gm = *gamma;
@@ -249,18 +250,20 @@ __global__ void branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const ac
 #pragma unroll
     for (int v = 0; v < VEC; ++v) outv[v] = fmaxf(fmaf(v0[v], sc[v], sh[v]), 0.f);
     stv<VEC>(z + m * ld_z + C + c, outv);
+    if (zb != nullptr) stv<VEC>(zb + m * ld_zb + C + c, outv);
     float u[VEC];
     bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
     ldv<VEC>(a0 + m * ld_a0 + c, v0); ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmaxf(fmaf(v0[v], sc[v], sh[v]), 0.f);
     stv<VEC>(z + m * ld_z + 2 * C + c, outv);
+    if (zb != nullptr) stv<VEC>(zb + m * ld_zb + 2 * C + c, outv);
   }
 }
 
 template <int VEC>
 __global__ void gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const float* s3,
-                                    const float* t3, act_t* z, long long ld_z) {
+                                    const float* t3, act_t* z, long long ld_z, grad_t* zb, long long ld_zb) {
   const int CV = C / VEC;
   const long long total = M * CV;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -276,6 +279,7 @@ __global__ void gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long 
       f[v] = gg * l[v] + (1.f - gg) * a[v];
     }
     stv<VEC>(z + m * ld_z + c, f);
+    if (zb != nullptr) stv<VEC>(zb + m * ld_zb + c, f);
   }
 }
 
@@ -283,7 +287,8 @@ __global__ void gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long 
 template <int VEC>
 __global__ void block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long ld_r, int B, int H,
                                      int W, int C, const float* s4, const float* t4, const float* res_scale, act_t* y,
-                                     long long ld_y, act_t* yp, long long ld_yp) {
+                                     long long ld_y, act_t* yp, long long ld_yp, grad_t* yb, long long ld_yb, grad_t* ypb,
+                                     long long ld_ypb) {
   const int CV = C / VEC;
   const int Hw = (H + 1) / 2, Ww = (W + 1) / 2;
   const int Hp = H / 2, Wp = W / 2;
@@ -312,13 +317,17 @@ __global__ void block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act
         ov[v] = fmaxf(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
       }
       stv<VEC>(y + m * ld_y + c, ov);
+      if (yb != nullptr) stv<VEC>(yb + m * ld_yb + c, ov);
       // pool over the values as stored (fp16), so backward can recompute the argmax from y
       float rd[VEC];
       ldv<VEC>(y + m * ld_y + c, rd);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) mx[v] = fmaxf(mx[v], rd[v]);
     }
-    if (yp != nullptr && yo < Hp && xo < Wp) stv<VEC>(yp + ((b * Hp + yo) * Wp + xo) * ld_yp + c, mx);
+    if (yp != nullptr && yo < Hp && xo < Wp) {
+      stv<VEC>(yp + ((b * Hp + yo) * Wp + xo) * ld_yp + c, mx);
+      if (ypb != nullptr) stv<VEC>(ypb + ((b * Hp + yo) * Wp + xo) * ld_ypb + c, mx);
+    }
   }
 }
 
@@ -803,34 +812,37 @@ extern "C" int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int3
 extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a0, int64_t ld_a0, int32_t B, int32_t H,
                                     int32_t W, int32_t C, const float* scale1, const float* shift1, const float* scale2,
                                     const float* shift2, const float* o, int32_t P, const float* gamma, void* z,
-                                    int64_t ld_z, void* stream) {
+                                    int64_t ld_z, void* zb, int64_t ld_zb, void* stream) {
   DFCSA_CHECK_ARG(l0 && a0 && scale1 && shift1 && scale2 && shift2 && o && gamma && z, "dfcsa_branch_act_fwd: null pointer");
-  const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z}, {l0, a0, z, o, scale1, shift1, scale2, shift2});
+  const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
   const long long total = static_cast<long long>(B) * H * W * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
-                                                                                 shift1, scale2, shift2, o, P, gamma, AM_(z), ld_z)));
+                                                                                 shift1, scale2, shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb)));
   DFCSA_LAUNCH_CHECK("branch_act_fwd_kernel");
   return DFCSA_OK;
 }
 
 extern "C" int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int32_t C, const float* scale3,
-                                  const float* shift3, void* z, int64_t ld_z, void* stream) {
+                                  const float* shift3, void* z, int64_t ld_z, void* zb, int64_t ld_zb, void* stream) {
   DFCSA_CHECK_ARG(g0 && scale3 && shift3 && z && M > 0 && C > 0, "dfcsa_gate_mix_fwd: bad args");
-  const bool v8 = vec8_ok(C, {ld_g0, ld_z}, {g0, z, scale3, shift3});
+  const bool v8 = vec8_ok(C, {ld_g0, ld_z, zb ? ld_zb : 0}, {g0, z, zb, scale3, shift3});
   const long long total = M * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (gate_mix_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(g0), ld_g0, M, C, scale3, shift3, AM_(z), ld_z)));
+  VEC_DISPATCH(v8, (gate_mix_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(g0), ld_g0, M, C, scale3, shift3, AM_(z), ld_z, GM_(zb), ld_zb)));
   DFCSA_LAUNCH_CHECK("gate_mix_fwd_kernel");
   return DFCSA_OK;
 }
 
 extern "C" int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r, int64_t ld_r, int32_t B, int32_t H,
                                    int32_t W, int32_t C, const float* scale4, const float* shift4, const float* res_scale,
-                                   void* y, int64_t ld_y, void* yp, int64_t ld_yp, void* stream) {
+                                   void* y, int64_t ld_y, void* yp, int64_t ld_yp, void* yb, int64_t ld_yb, void* ypb,
+                                   int64_t ld_ypb, void* stream) {
   DFCSA_CHECK_ARG(f0 && r && scale4 && shift4 && res_scale && y, "dfcsa_block_out_fwd: null pointer");
-  const bool v8 = vec8_ok(C, {ld_f0, ld_r, ld_y, yp ? ld_yp : 0}, {f0, r, y, yp, scale4, shift4});
+  const bool v8 = vec8_ok(C, {ld_f0, ld_r, ld_y, yp ? ld_yp : 0, yb ? ld_yb : 0, ypb ? ld_ypb : 0},
+                          {f0, r, y, yp, yb, ypb, scale4, shift4});
   const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4,
-                                                                                res_scale, AM_(y), ld_y, AM_(yp), ld_yp)));
+                                                                                res_scale, AM_(y), ld_y, AM_(yp), ld_yp, GM_(yb), ld_yb,
+                                                                                GM_(ypb), ld_ypb)));
   DFCSA_LAUNCH_CHECK("block_out_fwd_kernel");
   return DFCSA_OK;
 }

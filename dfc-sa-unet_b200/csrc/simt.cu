@@ -142,6 +142,7 @@ conv_simt_kernel(const SimtConvArgs a) {
       const long long o = pix * p.ld_out + cn;
       if (p.accumulate) v += ld_any(p.out, o, p.out_dtype);
       st_any(p.out, o, p.out_dtype, v);
+      if (p.shadow != nullptr) reinterpret_cast<__nv_bfloat16*>(p.shadow)[pix * p.ld_shadow + cn] = __float2bfloat16_rn(v);
       cs[j] += v; cq[j] += v * v;
     }
   }

@@ -37,6 +37,7 @@ class ConvParams(C.Structure):
         ("out", C.c_void_p), ("ld_out", C.c_int64),
         ("out_mode", C.c_int32), ("accumulate", C.c_int32),
         ("bias", C.c_void_p), ("stats", C.c_void_p),
+        ("shadow", C.c_void_p), ("ld_shadow", C.c_int64),
     ]
 
 

@@ -181,27 +181,22 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=Tr
     ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled)
     o = attention_forward(bp, pooled, B, ctx)
     z = _e((M, 3 * C), F16, dev)
-    ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z)
+    zb = _e((M, 3 * C), BF16, dev) if ctx is not None else None
+    ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z, zb)
     # gate
     G0 = _e((M, C), F16, dev)
     zLA = z[:, C:]
     segs = [(zLA, TAP_1x1)]
     ops.conv_gemm(B, H, W, segs, pk["w3"], C, G0, stats=st[6 * C:8 * C] if training else None, backend=_backend(segs, pk["w3"], C, G0))
     bn3 = _bn_affine(bp.bn3, bp.b3, st[6 * C:7 * C] if training else None, st[7 * C:8 * C] if training else None, M, training, dev)
-    ops.gate_mix_fwd(G0, bn3[0], bn3[1], z)
+    ops.gate_mix_fwd(G0, bn3[0], bn3[1], z, zb)
     # fusion
     F0 = _e((M, C), F16, dev)
     segs = [(z, TAP_1x1)]
     ops.conv_gemm(B, H, W, segs, pk["w4"], C, F0, stats=st[8 * C:10 * C] if training else None, backend=_backend(segs, pk["w4"], C, F0))
     bn4 = _bn_affine(bp.bn4, bp.b4, st[8 * C:9 * C] if training else None, st[9 * C:10 * C] if training else None, M, training, dev)
-    ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp)
-    if yb is not None:
-        ops.cast2d(y, yb)
-    if ypb is not None and yp is not None:
-        ops.cast2d(yp, ypb)
+    ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp, yb, ypb if yp is not None else None)
     if ctx is not None:
-        zb = _e((M, 3 * C), BF16, dev)
-        ops.cast2d(z, zb)
         ctx.B, ctx.H, ctx.W = B, H, W
         ctx.L0, ctx.A0, ctx.R, ctx.G0, ctx.F0, ctx.z, ctx.zb, ctx.y, ctx.o = L0, A0, R, G0, F0, z, zb, y, o
         ctx.bn1, ctx.bn2, ctx.bn3, ctx.bn4 = bn1, bn2, bn3, bn4
@@ -330,9 +325,9 @@ def net_forward(net, x_nchw, training, save=True):
         segs = [(u, TAP_1x1)]
         dst = cat[lvl][:, :f[lvl]]
         ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, wt, 4 * Co_t, dst, out_mode=OUT_CONVT2x2, bias=up.bias.detach(),
-                      backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT)
+                      backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT,
+                      shadow=catb[lvl][:, :f[lvl]] if keep else None)
         if keep:
-            ops.cast2d(dst, catb[lvl][:, :f[lvl]])
             wdt = _e((Ci_t, 4 * Co_t), BF16 if tc else F32, dev)   # [ci, (q, co)]
             ops.permute3(up.weight.detach(), wdt, (Ci_t, 4, Co_t), (Co_t * 4, 1, 4))
             upk.append(wdt)

@@ -26,7 +26,7 @@ def tc_eligible(segs, N, out):
 
 
 def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, bias=None, stats=None,
-              backend=BACKEND_TC):
+              backend=BACKEND_TC, shadow=None):
     """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm)."""
     p = L.ConvParams()
     p.B, p.H, p.W, p.n_seg = B, H, W, len(segs)
@@ -46,6 +46,8 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.accumulate = 1 if accumulate else 0
     p.bias = bias.data_ptr() if bias is not None else None
     p.stats = stats.data_ptr() if stats is not None else None
+    p.shadow = shadow.data_ptr() if shadow is not None else None
+    p.ld_shadow = _mat(shadow) if shadow is not None else 0
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
            flops=2.0 * B * H * W * N * ktot)
@@ -125,24 +127,25 @@ def bnrelu_pool_fwd(a0, B, H, W, scale, shift, P, tmp, pooled):
                                           L.ptr(tmp), L.ptr(pooled), L.stream())
 
 
-def branch_act_fwd(l0, a0, B, H, W, s1, t1, s2, t2, o, P, gamma, z):
+def branch_act_fwd(l0, a0, B, H, W, s1, t1, s2, t2, o, P, gamma, z, zb=None):
     Cn = l0.shape[1]
     L.call("dfcsa_branch_act_fwd", L.ptr(l0), _i64(_mat(l0)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s1),
                                          L.ptr(t1), L.ptr(s2), L.ptr(t2), L.ptr(o), P, L.ptr(gamma), L.ptr(z),
-                                         _i64(_mat(z)), L.stream())
+                                         _i64(_mat(z)), L.ptr(zb), _i64(_mat(zb) if zb is not None else 0), L.stream())
 
 
-def gate_mix_fwd(g0, s3, t3, z):
+def gate_mix_fwd(g0, s3, t3, z, zb=None):
     M, Cn = g0.shape
     L.call("dfcsa_gate_mix_fwd", L.ptr(g0), _i64(_mat(g0)), _i64(M), Cn, L.ptr(s3), L.ptr(t3), L.ptr(z),
-                                       _i64(_mat(z)), L.stream())
+                                       _i64(_mat(z)), L.ptr(zb), _i64(_mat(zb) if zb is not None else 0), L.stream())
 
 
-def block_out_fwd(f0, r, B, H, W, s4, t4, res_scale, y, yp=None):
+def block_out_fwd(f0, r, B, H, W, s4, t4, res_scale, y, yp=None, yb=None, ypb=None):
     Cn = f0.shape[1]
     L.call("dfcsa_block_out_fwd", L.ptr(f0), _i64(_mat(f0)), L.ptr(r), _i64(_mat(r)), B, H, W, Cn, L.ptr(s4),
                                         L.ptr(t4), L.ptr(res_scale), L.ptr(y), _i64(_mat(y)), L.ptr(yp),
-                                        _i64(_mat(yp) if yp is not None else 0), L.stream())
+                                        _i64(_mat(yp) if yp is not None else 0), L.ptr(yb), _i64(_mat(yb) if yb is not None else 0),
+                                        L.ptr(ypb), _i64(_mat(ypb) if ypb is not None else 0), L.stream())
 
 
 def block_out_bwd_reduce(dskip, dyp, y, f0, r, B, H, W, s4, t4, mean4, invstd4, dy_out, red4, drs):

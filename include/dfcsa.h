@@ -78,6 +78,9 @@ typedef struct {
   int32_t accumulate;       /* out += result (read-modify-write) */
   const float* bias;        /* optional: [N] (DIRECT) or [Co] (CONVT2x2) */
   double* stats;            /* optional: [2*N] */
+  void*   shadow;           /* optional bf16 copy of the result at the same coordinates (pitch ld_shadow): the operand
+                               the weight-gradient GEMM reads later (kind::f16 cannot mix fp16 and bf16) */
+  int64_t ld_shadow;
 } dfcsa_conv_params_t;
 
 int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);
@@ -152,20 +155,23 @@ int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int32_t H, int3
                           const float* scale, const float* shift, int32_t P,
                           float* tmp, float* pooled, void* stream);
 /* L = relu(bn1(L0)) -> z[:, C:2C];  A = gamma*bilinear_up(o) + relu(bn2(A0)) -> z[:, 2C:3C]
- * (reference :97,:99,:36,:38).  o is [B, P, P, C] fp32. */
+ * (reference :97,:99,:36,:38).  o is [B, P, P, C] fp32.  zb: optional bf16 shadow of z (same channel offsets). */
 int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a0, int64_t ld_a0,
                          int32_t B, int32_t H, int32_t W, int32_t C,
                          const float* scale1, const float* shift1, const float* scale2, const float* shift2,
                          const float* o, int32_t P, const float* gamma,
-                         void* z, int64_t ld_z, void* stream);
-/* g = sigmoid(bn3(G0)); z[:, 0:C] = g*L + (1-g)*A  (reference :104,:106) */
+                         void* z, int64_t ld_z, void* zb, int64_t ld_zb, void* stream);
+/* g = sigmoid(bn3(G0)); z[:, 0:C] = g*L + (1-g)*A  (reference :104,:106); zb: optional bf16 shadow of z */
 int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int32_t C,
-                       const float* scale3, const float* shift3, void* z, int64_t ld_z, void* stream);
-/* y = relu(bn4(F0)) + res_scale*R (reference :110,:114) and optionally yp = maxpool2x2(y) (reference :164) */
+                       const float* scale3, const float* shift3, void* z, int64_t ld_z, void* zb, int64_t ld_zb,
+                       void* stream);
+/* y = relu(bn4(F0)) + res_scale*R (reference :110,:114) and optionally yp = maxpool2x2(y) (reference :164);
+ * yb / ypb: optional bf16 shadows */
 int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r, int64_t ld_r,
                         int32_t B, int32_t H, int32_t W, int32_t C,
                         const float* scale4, const float* shift4, const float* res_scale,
-                        void* y, int64_t ld_y, void* yp, int64_t ld_yp, void* stream);
+                        void* y, int64_t ld_y, void* yp, int64_t ld_yp,
+                        void* yb, int64_t ld_yb, void* ypb, int64_t ld_ypb, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Block backward (autograd of the same lines).  Gradients bf16 NHWC; per-channel reductions in double.

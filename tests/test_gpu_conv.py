@@ -190,3 +190,42 @@ def test_permute3(cuda):
     ops.permute3(w, dg, (40, 9, 24), (9, 1, 40 * 9), flip1=True, scale=sc)
     ref = (0.5 * w.flip(2, 3)).permute(1, 2, 3, 0).reshape(40, 216).bfloat16()
     assert torch.equal(dg, ref)
+
+
+SMALL_CASES = [
+    # the bandwidth-shaped kernels behind the SIMT backend (csrc/small.cu): first layer (Ci=3) and final conv (Co=1)
+    (2, 9, 11, [3], "3", 64, {"src_dt": torch.float32, "stats": True}),
+    (1, 20, 33, [3], "1", 128, {"src_dt": torch.float32, "stats": True}),
+    (2, 7, 9, [64], "1", 1, {"out_dt": torch.float32, "bias": True}),
+    (2, 7, 9, [128], "1", 2, {"out_dt": torch.float32, "bias": True, "src_dt": torch.bfloat16}),
+    (2, 7, 9, [1], "1", 64, {"src_dt": torch.bfloat16, "out_dt": torch.bfloat16}),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[f"s{i}" for i in range(len(SMALL_CASES))])
+def test_conv_small_channel_kernels(cuda, case):
+    B, H, W, cins, modes, N, kw = case
+    err, serr = _run_conv(cuda, B, H, W, cins, [_MODE[m] for m in modes], N, 1, **kw)
+    tol = 6e-3 if kw.get("out_dt") == torch.bfloat16 else 2e-3
+    assert err < tol, f"conv small rel err {err}"
+    assert serr < 2e-3, f"BN statistics rel err {serr}"
+
+
+@pytest.mark.parametrize("case", [(2, 9, 11, 3, 64, 1), (1, 20, 33, 3, 128, 0), (2, 7, 9, 64, 1, 0)], ids=["x3_3x3", "x3_1x1", "dy1"])
+def test_wgrad_small_channel_kernels(cuda, case):
+    from dfcsa import ops
+    dev = cuda
+    B, H, W, Cc, N, xm = case
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, H, W, Cc, generator=g).to(dev)
+    x = x if Cc == 3 else x.bfloat16()
+    dy = torch.randn(B, H, W, N, generator=g).to(dev).bfloat16()
+    k = 3 if xm == 1 else 1
+    wt = torch.zeros(N, Cc, k, k, device=dev, requires_grad=True)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, padding=k // 2)
+    (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+    ref = gw.permute(0, 2, 3, 1).reshape(N, k * k * Cc) * 0.5
+    dw = torch.zeros(N, k * k * Cc, device=dev)
+    ops.conv_wgrad(B, H, W, x.reshape(-1, Cc), xm, dy.reshape(-1, N), 0, dw, alpha=torch.tensor([0.5], device=dev), backend=1)
+    torch.cuda.synchronize()
+    assert _rel_err(dw, ref) < 2e-3
