@@ -184,6 +184,12 @@ def run_dfcsa(args):
     launches = _lib.LAUNCHES - launches0
     _lib.PROF = None
     kern = prof.summary() if prof else {}
+    if prof and args.detail:
+        det = prof.detail()
+        rows = sorted(({"shape": k, "ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                        "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} for k, v in det.items()), key=lambda r: -r["ms_per_step"])
+        os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)
+        json.dump(rows, open(args.detail, "w"), indent=1)
 
     # ---------------- timed: end to end from pinned host memory ----------------
     barrier()
@@ -255,6 +261,7 @@ def main():
     ap.add_argument("--impl", default="dfcsa", choices=["dfcsa", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (default: the BASELINE config, 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--detail", default=None, help="write per-shape GEMM timings (JSON) to this path")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -8,8 +8,9 @@
 //   warp 1   : MMA issuer    - lane 0 issues tcgen05.mma (M=128, N=block_n, K=16) into a double-buffered TMEM
 //              accumulator; tcgen05.commit releases smem stages / publishes the accumulator
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      - tcgen05.ld (one pixel row per thread), optional bias / accumulate, per-channel
-//              sum / sum^2 (BatchNorm batch statistics) by a shuffle transpose-reduce, 16-byte stores
+//   warps 4-11: epilogue     - tcgen05.ld (one pixel row per thread; two warps per TMEM lane quarter split the
+//              columns), optional bias / accumulate, per-channel sum / sum^2 (BatchNorm batch statistics) by a
+//              shuffle transpose-reduce, 16-byte stores
 // Both operands are K-major, 128-byte swizzled: a pixel's 64 channels (128 B) form one swizzle row.
 #include "common.cuh"
 #include <algorithm>
@@ -23,7 +24,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kMaxStages = 8;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KiB
-constexpr int kSmemBudget = 227 * 1024 - 4096;   // dynamic part; static barriers / stats live beside it
+constexpr int kSmemBudget = 227 * 1024 - 12288;  // dynamic part; ~8 KB of static barriers / stats live beside it
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                 // TMEM columns between the two accumulators
 
@@ -36,6 +37,7 @@ struct ConvTcArgs {
   int H, W;         // output grid as seen by the tile walker (B merged into H when there is no halo)
   int n_tiles_n, block_n, N;
   int stages;
+  int kbs;          // K blocks (of 64) per pipeline stage: 2 for narrow tiles so one barrier round-trip feeds 8 MMAs
   int a_box_bytes;  // bytes one activation TMA delivers
   void* out;
   long long ld_out;
@@ -96,7 +98,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ ConvTcArgs a) {
@@ -106,12 +108,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_stats[2][256];
+  __shared__ float s_stats[4][2][256];   // [TMEM lane quarter][sum | sumsq][column]: one writer warp per entry
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int stage_bytes = kABytes + a.block_n * 128;
+  const int kb_bytes = kABytes + a.block_n * 128;
+  const int stage_bytes = a.kbs * kb_bytes;
   const int total_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.n_tiles_n;
 
   // Rows a partial activation box never writes must read as zero for the MMA.
@@ -120,8 +123,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     uint4* p = reinterpret_cast<uint4*>(smem);
     const int n16 = a.stages * stage_bytes / 16;
     for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = z;
-    s_stats[0][threadIdx.x] = 0.f;
-    s_stats[1][threadIdx.x] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
     fence_proxy_async();
   }
   if (warp == 0 && lane == 0) {
@@ -132,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -144,10 +146,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(a.a_box_bytes + a.block_n * 128);
+    const uint32_t kb_tx = static_cast<uint32_t>(a.a_box_bytes + a.block_n * 128);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(a, tile);
-      int kb_global = 0;
+      int kb_global = 0, sub = 0;
       for (int s = 0; s < a.n_seg; ++s) {
         const CUtensorMap* ma = (s == 0) ? &map_a0 : (s == 1) ? &map_a1 : &map_a2;
         const int mode = a.seg_mode[s];
@@ -159,15 +161,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           else { c1 = tc.w0; c2 = tc.h0; c3 = tc.tb; c4 = 0; }
           for (int kb = 0; kb < a.seg_kb[s]; ++kb) {
             if (lane == 0) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              uint8_t* sa = smem + stage * stage_bytes;
+              if (sub == 0) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[stage], kb_tx * static_cast<uint32_t>(min(a.kbs, a.total_kb - kb_global)));
+              }
+              uint8_t* sa = smem + stage * stage_bytes + sub * kABytes;
+              uint8_t* sb = smem + stage * stage_bytes + a.kbs * kABytes + sub * (a.block_n * 128);
               tma_load_5d(sa, ma, &full_bar[stage], kb * kBlockK, c1, c2, c3, c4);
-              tma_load_2d(sa + kABytes, &map_b, &full_bar[stage], kb_global * kBlockK, tc.nt * a.block_n);
+              tma_load_2d(sb, &map_b, &full_bar[stage], kb_global * kBlockK, tc.nt * a.block_n);
             }
             __syncwarp();
             ++kb_global;
-            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            if (++sub == a.kbs || kb_global == a.total_kb) {
+              sub = 0;
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
           }
         }
       }
@@ -180,20 +188,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
-      for (int kb = 0; kb < a.total_kb; ++kb) {
+      for (int kb = 0; kb < a.total_kb; kb += a.kbs) {
+        const int nsub = min(a.kbs, a.total_kb - kb);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t b_addr = a_addr + a.kbs * kABytes;
+          for (int sub = 0; sub < nsub; ++sub) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_f16(d_tmem, da, db, a.idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t da = umma_smem_desc(a_addr + sub * kABytes + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + sub * (a.block_n * 128) + k * 32, 16, 1024);
+              umma_f16(d_tmem, da, db, a.idesc, (kb | sub | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
-          if (kb == a.total_kb - 1) umma_commit(&tmem_full_bar[as]);
+          if (kb + nsub >= a.total_kb) umma_commit(&tmem_full_bar[as]);
         }
         __syncwarp();
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -202,7 +213,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;              // == warp % 4: the TMEM lane quarter this warp may read
+    const int ew = (warp - 4) & 3;        // == warp % 4: the TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;     // which half of the column chunks this warp takes
     const int r = ew * 32 + lane;         // tile row == TMEM lane
     const int et = threadIdx.x - 128;
     const bool flush_each = a.n_tiles_n > 1;
@@ -229,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
       const int nchunks = a.block_n / 32;
-      for (int ch = 0; ch < nchunks; ++ch) {
+      for (int ch = half; ch < nchunks; ch += 2) {
         const int n0 = tc.nt * a.block_n + ch * 32;
         if (n0 >= a.N) break;
         const int ncols = min(32, a.N - n0);
@@ -265,8 +277,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
           const float s1 = transpose_reduce32(v, lane);
           const float s2 = transpose_reduce32(sq, lane);
-          atomicAdd(&s_stats[0][ch * 32 + lane], s1);
-          atomicAdd(&s_stats[1][ch * 32 + lane], s2);
+          s_stats[ew][0][ch * 32 + lane] += s1;     // this warp is the only writer of (ew, column)
+          s_stats[ew][1][ch * 32 + lane] += s2;
           have_stats = true;
         }
       }
@@ -276,16 +288,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       as ^= 1; if (as == 0) aphase ^= 1;
       last_nt = tc.nt;
       if (a.stats != nullptr && flush_each) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int c = et; c < a.block_n; c += 128) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        for (int c = et; c < a.block_n; c += 256) {
           const int n = last_nt * a.block_n + c;
           if (n < a.N) {
-            atomicAdd(a.stats + n, static_cast<double>(s_stats[0][c]));
-            atomicAdd(a.stats + a.N + n, static_cast<double>(s_stats[1][c]));
+            atomicAdd(a.stats + n, static_cast<double>(s_stats[0][0][c] + s_stats[1][0][c] + s_stats[2][0][c] + s_stats[3][0][c]));
+            atomicAdd(a.stats + a.N + n, static_cast<double>(s_stats[0][1][c] + s_stats[1][1][c] + s_stats[2][1][c] + s_stats[3][1][c]));
           }
-          s_stats[0][c] = 0.f; s_stats[1][c] = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { s_stats[q][0][c] = 0.f; s_stats[q][1][c] = 0.f; }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
     }
     (void)have_stats;
@@ -296,8 +309,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (a.stats != nullptr && a.n_tiles_n == 1 && blockIdx.x < total_tiles) {
     for (int c = threadIdx.x; c < a.block_n; c += blockDim.x) {
       if (c < a.N) {
-        atomicAdd(a.stats + c, static_cast<double>(s_stats[0][c]));
-        atomicAdd(a.stats + a.N + c, static_cast<double>(s_stats[1][c]));
+        atomicAdd(a.stats + c, static_cast<double>(s_stats[0][0][c] + s_stats[1][0][c] + s_stats[2][0][c] + s_stats[3][0][c]));
+        atomicAdd(a.stats + a.N + c, static_cast<double>(s_stats[0][1][c] + s_stats[1][1][c] + s_stats[2][1][c] + s_stats[3][1][c]));
       }
     }
   }
@@ -383,7 +396,8 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   while (block_n > 64 && block_n % 64 == 0 && m_tiles * ((p->N + block_n - 1) / block_n) < sms) block_n /= 2;
   a.block_n = block_n;
   a.n_tiles_n = (p->N + block_n - 1) / block_n;
-  const int stage_bytes = kABytes + block_n * 128;
+  a.kbs = (block_n <= 128 && a.total_kb >= 2) ? 2 : 1;
+  const int stage_bytes = a.kbs * (kABytes + block_n * 128);
   a.stages = std::min(kMaxStages, (kSmemBudget - 1024) / stage_bytes);
   a.idesc = umma_idesc_f16(kBlockM, block_n, umma_fmt(p->src_dtype), umma_fmt(p->w_dtype), 0, 0);
 
@@ -438,7 +452,7 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   const long long total_tiles = m_tiles * a.n_tiles_n;
   const int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
-  conv_tc_kernel<<<grid, 256, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
+  conv_tc_kernel<<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
   DFCSA_LAUNCH_CHECK("conv_tc_kernel");
   return DFCSA_OK;
 }

@@ -230,48 +230,47 @@ __device__ __forceinline__ void bilerp_gather(const float* o, long long b, int y
 }
 
 template <int VEC>
-__global__ void branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H,
-                                      int W, int C, const float* s1, const float* t1, const float* s2, const float* t2,
-                                      const float* o, int P, const float* gamma, act_t* z, long long ld_z, grad_t* zb,
-                                      long long ld_zb) {
-  const int CV = C / VEC;
-  const long long total = static_cast<long long>(B) * H * W * CV;
+__global__ void __launch_bounds__(256)
+branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H, int W, int C,
+                      const float* s1, const float* t1, const float* s2, const float* t2, const float* o, int P,
+                      const float* gamma, act_t* z, long long ld_z, grad_t* zb, long long ld_zb, int CL, int PL) {
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c = (blockIdx.y * CL + cl) * VEC;
+  if (pl >= PL || c >= C) return;
+  const unsigned M = static_cast<unsigned>(B) * H * W;
   const float gm = *gamma;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    const long long m = i / CV;
-    const int x = static_cast<int>(m % W);
-    const long long r = m / W;
-    const int y = static_cast<int>(r % H);
-    const long long b = r / H;
-    float v0[VEC], sc[VEC], sh[VEC], outv[VEC];
-    ldv<VEC>(l0 + m * ld_l0 + c, v0); ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh);
+  float sc1[VEC], sh1[VEC], sc2[VEC], sh2[VEC];
+  ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2);
+  for (unsigned m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL) {
+    const unsigned x = m % W, r = m / W, y = r % H, b = r / H;
+    float v0[VEC], outv[VEC];
+    ldv<VEC>(l0 + static_cast<long long>(m) * ld_l0 + c, v0);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) outv[v] = fmaxf(fmaf(v0[v], sc[v], sh[v]), 0.f);
-    stv<VEC>(z + m * ld_z + C + c, outv);
-    if (zb != nullptr) stv<VEC>(zb + m * ld_zb + C + c, outv);
+    for (int v = 0; v < VEC; ++v) outv[v] = fmaxf(fmaf(v0[v], sc1[v], sh1[v]), 0.f);
+    stv<VEC>(z + static_cast<long long>(m) * ld_z + C + c, outv);
+    if (zb != nullptr) stv<VEC>(zb + static_cast<long long>(m) * ld_zb + C + c, outv);
     float u[VEC];
     bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
-    ldv<VEC>(a0 + m * ld_a0 + c, v0); ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh);
+    ldv<VEC>(a0 + static_cast<long long>(m) * ld_a0 + c, v0);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmaxf(fmaf(v0[v], sc[v], sh[v]), 0.f);
-    stv<VEC>(z + m * ld_z + 2 * C + c, outv);
-    if (zb != nullptr) stv<VEC>(zb + m * ld_zb + 2 * C + c, outv);
+    for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmaxf(fmaf(v0[v], sc2[v], sh2[v]), 0.f);
+    stv<VEC>(z + static_cast<long long>(m) * ld_z + 2 * C + c, outv);
+    if (zb != nullptr) stv<VEC>(zb + static_cast<long long>(m) * ld_zb + 2 * C + c, outv);
   }
 }
 
 template <int VEC>
-__global__ void gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const float* s3,
-                                    const float* t3, act_t* z, long long ld_z, grad_t* zb, long long ld_zb) {
-  const int CV = C / VEC;
-  const long long total = M * CV;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    const long long m = i / CV;
-    float g[VEC], sc[VEC], sh[VEC], l[VEC], a[VEC], f[VEC];
-    ldv<VEC>(g0 + m * ld_g0 + c, g); ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh);
+__global__ void __launch_bounds__(256)
+gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const float* s3, const float* t3, act_t* z,
+                    long long ld_z, grad_t* zb, long long ld_zb, int CL, int PL) {
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c = (blockIdx.y * CL + cl) * VEC;
+  if (pl >= PL || c >= C) return;
+  float sc[VEC], sh[VEC];
+  ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh);
+  for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+    float g[VEC], l[VEC], a[VEC], f[VEC];
+    ldv<VEC>(g0 + m * ld_g0 + c, g);
     ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -285,48 +284,43 @@ __global__ void gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long 
 
 // y = relu(bn4(F0)) + rs*R, optional 2x2 max pool; one thread per 2x2 window and channel vector
 template <int VEC>
-__global__ void block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long ld_r, int B, int H,
-                                     int W, int C, const float* s4, const float* t4, const float* res_scale, act_t* y,
-                                     long long ld_y, act_t* yp, long long ld_yp, grad_t* yb, long long ld_yb, grad_t* ypb,
-                                     long long ld_ypb) {
-  const int CV = C / VEC;
-  const int Hw = (H + 1) / 2, Ww = (W + 1) / 2;
-  const int Hp = H / 2, Wp = W / 2;
-  const long long total = static_cast<long long>(B) * Hw * Ww * CV;
+__global__ void __launch_bounds__(256)
+block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long ld_r, int B, int H, int W, int C,
+                     const float* s4, const float* t4, const float* res_scale, act_t* y, long long ld_y, act_t* yp,
+                     long long ld_yp, grad_t* yb, long long ld_yb, grad_t* ypb, long long ld_ypb, int CL, int PL) {
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c = (blockIdx.y * CL + cl) * VEC;
+  if (pl >= PL || c >= C) return;
+  const unsigned Hw = (H + 1) / 2, Ww = (W + 1) / 2;
+  const unsigned Hp = H / 2, Wp = W / 2;
+  const unsigned nwin = static_cast<unsigned>(B) * Hw * Ww;
   const float rs = *res_scale;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    long long q = i / CV;
-    const int xo = static_cast<int>(q % Ww); q /= Ww;
-    const int yo = static_cast<int>(q % Hw);
-    const long long b = q / Hw;
-    float sc[VEC], sh[VEC], mx[VEC];
-    ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh);
+  float sc[VEC], sh[VEC];
+  ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh);
+  for (unsigned wi = blockIdx.x * PL + pl; wi < nwin; wi += gridDim.x * PL) {
+    const unsigned xo = wi % Ww, q = wi / Ww, yo = q % Hw, b = q / Hw;
+    float mx[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) mx[v] = -INFINITY;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
-      if (yy >= H || xx >= W) continue;
-      const long long m = (b * H + yy) * W + xx;
+      const unsigned yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+      if (yy >= static_cast<unsigned>(H) || xx >= static_cast<unsigned>(W)) continue;
+      const long long m = (static_cast<long long>(b) * H + yy) * W + xx;
       float fv[VEC], rv[VEC], ov[VEC];
       ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        ov[v] = fmaxf(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
-      }
+      for (int v = 0; v < VEC; ++v) ov[v] = fmaxf(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
       stv<VEC>(y + m * ld_y + c, ov);
       if (yb != nullptr) stv<VEC>(yb + m * ld_yb + c, ov);
       // pool over the values as stored (fp16), so backward can recompute the argmax from y
-      float rd[VEC];
-      ldv<VEC>(y + m * ld_y + c, rd);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) mx[v] = fmaxf(mx[v], rd[v]);
+      for (int v = 0; v < VEC; ++v) mx[v] = fmaxf(mx[v], Cvt<act_t>::to_f(Cvt<act_t>::from_f(ov[v])));
     }
     if (yp != nullptr && yo < Hp && xo < Wp) {
-      stv<VEC>(yp + ((b * Hp + yo) * Wp + xo) * ld_yp + c, mx);
-      if (ypb != nullptr) stv<VEC>(ypb + ((b * Hp + yo) * Wp + xo) * ld_ypb + c, mx);
+      const long long mp = (static_cast<long long>(b) * Hp + yo) * Wp + xo;
+      stv<VEC>(yp + mp * ld_yp + c, mx);
+      if (ypb != nullptr) stv<VEC>(ypb + mp * ld_ypb + c, mx);
     }
   }
 }
@@ -416,25 +410,26 @@ block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_
 
 // dx = scale * (d - k1 - xhat*k2), d = dy * [relu mask] (act_mode 0) or dy (act_mode 2)
 template <int VEC>
-__global__ void bn_bwd_apply_kernel(const grad_t* dy, long long ld_dy, const act_t* x, long long ld_x, long long M, int C,
-                                    const float* scale, const float* shift, const float* mean, const float* invstd,
-                                    const double* red, int act_mode, grad_t* dx, long long ld_dx) {
-  const int CV = C / VEC;
-  const long long total = M * CV;
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const grad_t* dy, long long ld_dy, const act_t* x, long long ld_x, long long M, int C,
+                    const float* scale, const float* shift, const float* mean, const float* invstd, const double* red,
+                    int act_mode, grad_t* dx, long long ld_dx, int CL, int PL) {
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c = (blockIdx.y * CL + cl) * VEC;
+  if (pl >= PL || c >= C) return;
   const double invn = 1.0 / static_cast<double>(M);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    const long long m = i / CV;
-    float d[VEC], xv[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC], o[VEC];
+  float sc[VEC], sh[VEC], mu[VEC], is[VEC], k1[VEC], k2[VEC];
+  ldf<VEC>(scale + c, sc); ldf<VEC>(shift + c, sh); ldf<VEC>(mean + c, mu); ldf<VEC>(invstd + c, is);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { k1[v] = static_cast<float>(red[c + v] * invn); k2[v] = static_cast<float>(red[C + c + v] * invn) * is[v]; }
+  for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+    float d[VEC], xv[VEC], o[VEC];
     ldv<VEC>(dy + m * ld_dy + c, d); ldv<VEC>(x + m * ld_x + c, xv);
-    ldf<VEC>(scale + c, sc); ldf<VEC>(shift + c, sh); ldf<VEC>(mean + c, mu); ldf<VEC>(invstd + c, is);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const float k1 = static_cast<float>(red[c + v] * invn), k2 = static_cast<float>(red[C + c + v] * invn);
       float dd = d[v];
       if (act_mode == 0 && !(fmaf(xv[v], sc[v], sh[v]) > 0.f)) dd = 0.f;
-      o[v] = sc[v] * (dd - k1 - (xv[v] - mu[v]) * is[v] * k2);
+      o[v] = sc[v] * (dd - k1[v] - (xv[v] - mu[v]) * k2[v]);
     }
     stv<VEC>(dx + m * ld_dx + c, o);
   }
@@ -473,27 +468,30 @@ gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lo
 }
 
 template <int VEC>
-__global__ void gate_mix_bwd_apply_kernel(grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0,
-                                          long long ld_g0, long long M, int C, const float* s3, const float* t3,
-                                          const float* mean3, const float* invstd3, const double* red3, grad_t* dg0,
-                                          long long ld_dg0) {
-  const int CV = C / VEC;
-  const long long total = M * CV;
+__global__ void __launch_bounds__(256)
+gate_mix_bwd_apply_kernel(grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0, long long ld_g0,
+                          long long M, int C, const float* s3, const float* t3, const float* mean3, const float* invstd3,
+                          const double* red3, grad_t* dg0, long long ld_dg0, int CL, int PL) {
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c = (blockIdx.y * CL + cl) * VEC;
+  if (pl >= PL || c >= C) return;
   const double invn = 1.0 / static_cast<double>(M);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    const long long m = i / CV;
-    float df[VEC], dl[VEC], da[VEC], l[VEC], a[VEC], g[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC], o[VEC];
+  float sc[VEC], sh[VEC], mu[VEC], k1[VEC], k2[VEC];
+  ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh); ldf<VEC>(mean3 + c, mu);
+  {
+    float is[VEC]; ldf<VEC>(invstd3 + c, is);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { k1[v] = static_cast<float>(red3[c + v] * invn); k2[v] = static_cast<float>(red3[C + c + v] * invn) * is[v]; }
+  }
+  for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+    float df[VEC], dl[VEC], da[VEC], l[VEC], a[VEC], g[VEC], o[VEC];
     ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
     ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a); ldv<VEC>(g0 + m * ld_g0 + c, g);
-    ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh); ldf<VEC>(mean3 + c, mu); ldf<VEC>(invstd3 + c, is);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const float k1 = static_cast<float>(red3[c + v] * invn), k2 = static_cast<float>(red3[C + c + v] * invn);
       const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
       const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
-      o[v] = sc[v] * (ds - k1 - (g[v] - mu[v]) * is[v] * k2);
+      o[v] = sc[v] * (ds - k1[v] - (g[v] - mu[v]) * k2[v]);
       dl[v] += df[v] * gg;
       da[v] += df[v] * (1.f - gg);
     }
@@ -522,10 +520,11 @@ branch_bwd_reduce1_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, lo
     float sc[VEC], sh[VEC], mu[VEC], is[VEC];
     ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(mean1 + c, mu); ldf<VEC>(invstd1 + c, is);
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      const int x = static_cast<int>(m % W);
-      const long long r = m / W;
-      const int y = static_cast<int>(r % H);
-      const long long b = r / H;
+      const unsigned mu32 = static_cast<unsigned>(m);
+      const int x = static_cast<int>(mu32 % static_cast<unsigned>(W));
+      const unsigned r = mu32 / static_cast<unsigned>(W);
+      const int y = static_cast<int>(r % static_cast<unsigned>(H));
+      const long long b = r / static_cast<unsigned>(H);
       float dl[VEC], da[VEC], lv[VEC], u[VEC];
       ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
       ldv<VEC>(l0 + m * ld_l0 + c, lv);
@@ -620,10 +619,11 @@ branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, lo
     float sc[VEC], sh[VEC], mu[VEC], is[VEC];
     ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh); ldf<VEC>(mean2 + c, mu); ldf<VEC>(invstd2 + c, is);
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      const int x = static_cast<int>(m % W);
-      const long long r = m / W;
-      const int y = static_cast<int>(r % H);
-      const long long b = r / H;
+      const unsigned mu32 = static_cast<unsigned>(m);
+      const int x = static_cast<int>(mu32 % static_cast<unsigned>(W));
+      const unsigned r = mu32 / static_cast<unsigned>(W);
+      const int y = static_cast<int>(r % static_cast<unsigned>(H));
+      const long long b = r / static_cast<unsigned>(H);
       float da[VEC], av[VEC], gp[VEC];
       ldv<VEC>(dz + m * ld_dz + 2 * C + c, da); ldv<VEC>(a0 + m * ld_a0 + c, av);
       poolT_gather<VEC>(dpooled, b, y, x, H, W, P, C, c, gp);
@@ -640,47 +640,48 @@ branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, lo
 }
 
 template <int VEC>
-__global__ void branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0,
-                                        const act_t* a0, long long ld_a0, int B, int H, int W, int C, const float* s1,
-                                        const float* t1, const float* mean1, const float* invstd1, const double* red1,
-                                        const float* s2, const float* t2, const float* mean2, const float* invstd2,
-                                        const double* red2, const float* dpooled, int P, grad_t* dl0, long long ld_dl0,
-                                        grad_t* da0, long long ld_da0) {
-  const int CV = C / VEC;
-  const long long M = static_cast<long long>(B) * H * W;
-  const long long total = M * CV;
+__global__ void __launch_bounds__(256)
+branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* a0,
+                        long long ld_a0, int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
+                        const float* invstd1, const double* red1, const float* s2, const float* t2, const float* mean2,
+                        const float* invstd2, const double* red2, const float* dpooled, int P, grad_t* dl0,
+                        long long ld_dl0, grad_t* da0, long long ld_da0, int CL, int PL) {
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c = (blockIdx.y * CL + cl) * VEC;
+  if (pl >= PL || c >= C) return;
+  const unsigned M = static_cast<unsigned>(B) * H * W;
   const double invn = 1.0 / static_cast<double>(M);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    const long long m = i / CV;
-    const int x = static_cast<int>(m % W);
-    const long long r = m / W;
-    const int y = static_cast<int>(r % H);
-    const long long b = r / H;
-    float d[VEC], xv[VEC], sc[VEC], sh[VEC], mu[VEC], is[VEC], o[VEC];
-    // conv branch
-    ldv<VEC>(dz + m * ld_dz + C + c, d); ldv<VEC>(l0 + m * ld_l0 + c, xv);
-    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(mean1 + c, mu); ldf<VEC>(invstd1 + c, is);
+  float sc1[VEC], sh1[VEC], mu1[VEC], ka1[VEC], kb1[VEC], sc2[VEC], sh2[VEC], mu2[VEC], ka2[VEC], kb2[VEC];
+  ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); ldf<VEC>(mean1 + c, mu1);
+  ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2); ldf<VEC>(mean2 + c, mu2);
+  {
+    float i1[VEC], i2[VEC]; ldf<VEC>(invstd1 + c, i1); ldf<VEC>(invstd2 + c, i2);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const float k1 = static_cast<float>(red1[c + v] * invn), k2 = static_cast<float>(red1[C + c + v] * invn);
-      const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
-      o[v] = sc[v] * (dd - k1 - (xv[v] - mu[v]) * is[v] * k2);
+      ka1[v] = static_cast<float>(red1[c + v] * invn); kb1[v] = static_cast<float>(red1[C + c + v] * invn) * i1[v];
+      ka2[v] = static_cast<float>(red2[c + v] * invn); kb2[v] = static_cast<float>(red2[C + c + v] * invn) * i2[v];
     }
-    stv<VEC>(dl0 + m * ld_dl0 + c, o);
-    // attention branch
+  }
+  for (unsigned m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL) {
+    const unsigned x = m % W, r = m / W, y = r % H, b = r / H;
+    const long long mm = m;
+    float d[VEC], xv[VEC], o[VEC];
+    ldv<VEC>(dz + mm * ld_dz + C + c, d); ldv<VEC>(l0 + mm * ld_l0 + c, xv);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float dd = fmaf(xv[v], sc1[v], sh1[v]) > 0.f ? d[v] : 0.f;
+      o[v] = sc1[v] * (dd - ka1[v] - (xv[v] - mu1[v]) * kb1[v]);
+    }
+    stv<VEC>(dl0 + mm * ld_dl0 + c, o);
     float gp[VEC];
-    ldv<VEC>(dz + m * ld_dz + 2 * C + c, d); ldv<VEC>(a0 + m * ld_a0 + c, xv);
-    ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh); ldf<VEC>(mean2 + c, mu); ldf<VEC>(invstd2 + c, is);
+    ldv<VEC>(dz + mm * ld_dz + 2 * C + c, d); ldv<VEC>(a0 + mm * ld_a0 + c, xv);
     poolT_gather<VEC>(dpooled, b, y, x, H, W, P, C, c, gp);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const float k1 = static_cast<float>(red2[c + v] * invn), k2 = static_cast<float>(red2[C + c + v] * invn);
-      const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] + gp[v] : 0.f;
-      o[v] = sc[v] * (dd - k1 - (xv[v] - mu[v]) * is[v] * k2);
+      const float dd = fmaf(xv[v], sc2[v], sh2[v]) > 0.f ? d[v] + gp[v] : 0.f;
+      o[v] = sc2[v] * (dd - ka2[v] - (xv[v] - mu2[v]) * kb2[v]);
     }
-    stv<VEC>(da0 + m * ld_da0 + c, o);
+    stv<VEC>(da0 + mm * ld_da0 + c, o);
   }
 }
 
@@ -815,9 +816,11 @@ extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a
                                     int64_t ld_z, void* zb, int64_t ld_zb, void* stream) {
   DFCSA_CHECK_ARG(l0 && a0 && scale1 && shift1 && scale2 && shift2 && o && gamma && z, "dfcsa_branch_act_fwd: null pointer");
   const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
-  const long long total = static_cast<long long>(B) * H * W * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
-                                                                                 shift1, scale2, shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb)));
+  DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_act_fwd: too many pixels");
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
+                                                                     shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_act_fwd_kernel");
   return DFCSA_OK;
 }
@@ -826,8 +829,10 @@ extern "C" int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int3
                                   const float* shift3, void* z, int64_t ld_z, void* zb, int64_t ld_zb, void* stream) {
   DFCSA_CHECK_ARG(g0 && scale3 && shift3 && z && M > 0 && C > 0, "dfcsa_gate_mix_fwd: bad args");
   const bool v8 = vec8_ok(C, {ld_g0, ld_z, zb ? ld_zb : 0}, {g0, z, zb, scale3, shift3});
-  const long long total = M * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (gate_mix_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(g0), ld_g0, M, C, scale3, shift3, AM_(z), ld_z, GM_(zb), ld_zb)));
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (gate_mix_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(g0), ld_g0, M, C, scale3, shift3, AM_(z), ld_z, GM_(zb), ld_zb,
+                                                                   g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("gate_mix_fwd_kernel");
   return DFCSA_OK;
 }
@@ -839,10 +844,13 @@ extern "C" int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r,
   DFCSA_CHECK_ARG(f0 && r && scale4 && shift4 && res_scale && y, "dfcsa_block_out_fwd: null pointer");
   const bool v8 = vec8_ok(C, {ld_f0, ld_r, ld_y, yp ? ld_yp : 0, yb ? ld_yb : 0, ypb ? ld_ypb : 0},
                           {f0, r, y, yp, yb, ypb, scale4, shift4});
-  const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4,
-                                                                                res_scale, AM_(y), ld_y, AM_(yp), ld_yp, GM_(yb), ld_yb,
-                                                                                GM_(ypb), ld_ypb)));
+  const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
+  DFCSA_CHECK_ARG(nwin < (1LL << 31), "dfcsa_block_out_fwd: too many pixels");
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(nwin, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4, res_scale,
+                                                                    AM_(y), ld_y, AM_(yp), ld_yp, GM_(yb), ld_yb, GM_(ypb), ld_ypb,
+                                                                    g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("block_out_fwd_kernel");
   return DFCSA_OK;
 }
@@ -873,9 +881,10 @@ extern "C" int dfcsa_bn_bwd_apply(const void* dy, int64_t ld_dy, const void* x, 
   (void)gamma;
   DFCSA_CHECK_ARG(dy && x && scale && shift && mean && invstd && red && dx && M > 0, "dfcsa_bn_bwd_apply: bad args");
   const bool v8 = vec8_ok(C, {ld_dy, ld_x, ld_dx}, {dy, x, dx, scale, shift, mean, invstd});
-  const long long total = M * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dy), ld_dy, A_(x), ld_x, M, C, scale, shift, mean, invstd,
-                                                                               red, act_mode, GM_(dx), ld_dx)));
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dy), ld_dy, A_(x), ld_x, M, C, scale, shift, mean, invstd, red,
+                                                                   act_mode, GM_(dx), ld_dx, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return DFCSA_OK;
 }
@@ -900,9 +909,10 @@ extern "C" int dfcsa_gate_mix_bwd_apply(void* dz, int64_t ld_dz, const void* z, 
   (void)gamma3;
   DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && dg0 && M > 0, "dfcsa_gate_mix_bwd_apply: bad args");
   const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0, ld_dg0}, {dz, z, g0, dg0, scale3, shift3, mean3, invstd3});
-  const long long total = M * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(GM_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3,
-                                                                                     shift3, mean3, invstd3, red3, GM_(dg0), ld_dg0)));
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
+                                                                         mean3, invstd3, red3, GM_(dg0), ld_dg0, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("gate_mix_bwd_apply_kernel");
   return DFCSA_OK;
 }
@@ -951,11 +961,12 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
   DFCSA_CHECK_ARG(dz && l0 && a0 && red1 && red2 && dpooled && dl0 && da0, "dfcsa_branch_bwd_apply: null pointer");
   const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_a0, ld_dl0, ld_da0},
                           {dz, l0, a0, dl0, da0, dpooled, scale1, shift1, mean1, invstd1, scale2, shift2, mean2, invstd2});
-  const long long total = static_cast<long long>(B) * H * W * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C,
-                                                                                   scale1, shift1, mean1, invstd1, red1, scale2, shift2,
-                                                                                   mean2, invstd2, red2, dpooled, P, GM_(dl0), ld_dl0,
-                                                                                   GM_(da0), ld_da0)));
+  DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_bwd_apply: too many pixels");
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL), g.chunks);
+  VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
+                                                                       shift1, mean1, invstd1, red1, scale2, shift2, mean2, invstd2,
+                                                                       red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_apply_kernel");
   return DFCSA_OK;
 }

@@ -108,17 +108,27 @@ class Profiler:
     """Optional per-entry-point timing with CUDA events on the launching stream (bench.py's roofline numbers)."""
 
     def __init__(self):
-        self.records = []       # (tag, flops, start_event, end_event)
+        self.records = []       # (tag, flops, start_event, end_event, desc)
 
     def summary(self):
         torch.cuda.synchronize()
         agg = {}
-        for tag, flops, e0, e1 in self.records:
+        for tag, flops, e0, e1, _ in self.records:
             a = agg.setdefault(tag, {"ms": 0.0, "flops": 0.0, "launches": 0})
             a["ms"] += e0.elapsed_time(e1)
             a["flops"] += flops
             a["launches"] += 1
         return agg
+
+    def detail(self, tags=("conv_tc", "wgrad_tc")):
+        """per-shape totals for the GEMM kernels: {desc: {ms, flops, launches}}"""
+        torch.cuda.synchronize()
+        out = {}
+        for tag, flops, e0, e1, desc in self.records:
+            if tag in tags:
+                a = out.setdefault(f"{tag} {desc}", {"ms": 0.0, "flops": 0.0, "launches": 0})
+                a["ms"] += e0.elapsed_time(e1); a["flops"] += flops; a["launches"] += 1
+        return out
 
 
 PROF = None          # set to a Profiler() to time every ABI call
@@ -127,7 +137,7 @@ LAUNCHES = 0         # kernels enqueued through the ABI (bench.py's gpu_launches
 _KERNELS = {"dfcsa_bnrelu_pool_fwd": 2, "dfcsa_branch_bwd_reduce1": 3}
 
 
-def call(name, *args, tag=None, flops=0.0):
+def call(name, *args, tag=None, flops=0.0, desc=""):
     """Invoke one ABI entry point on the current stream; raise on a non-zero return code."""
     global LAUNCHES
     fn = getattr(lib(), name)
@@ -136,7 +146,7 @@ def call(name, *args, tag=None, flops=0.0):
         e0.record()
         rc = fn(*args)
         e1.record()
-        PROF.records.append((tag or name[6:], flops, e0, e1))
+        PROF.records.append((tag or name[6:], flops, e0, e1, desc))
     else:
         rc = fn(*args)
     LAUNCHES += _KERNELS.get(name, 1)

@@ -50,7 +50,9 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.ld_shadow = _mat(shadow) if shadow is not None else 0
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
-           flops=2.0 * B * H * W * N * ktot)
+           flops=2.0 * B * H * W * N * ktot,
+           desc=f"M={B * H * W} {H}x{W} N={N} K={ktot} segs={[(m.shape[1], mode) for m, mode in segs]} acc={int(bool(accumulate))} "
+                f"stats={int(stats is not None)} out={str(out.dtype)[6:]} mode={out_mode}")
 
 
 def conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw, alpha=None, backend=BACKEND_TC):
@@ -63,7 +65,8 @@ def conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw, alpha=None, backend=BACKEND_
     p.alpha = alpha.data_ptr() if alpha is not None else None
     taps = 9 if x_mode == TAP_3x3 else (4 if dy_mode == TAP_2x2S2 else 1)
     L.call("dfcsa_conv_wgrad", C.byref(p), backend, L.stream(), tag="wgrad_tc" if backend == BACKEND_TC else "wgrad_simt",
-           flops=2.0 * B * H * W * taps * x.shape[1] * dy.shape[1])
+           flops=2.0 * B * H * W * taps * x.shape[1] * dy.shape[1],
+           desc=f"M={B * H * W} {H}x{W} N={dy.shape[1]} C={x.shape[1]} taps={taps}")
 
 
 def wgrad_tc_eligible(x, dy):
