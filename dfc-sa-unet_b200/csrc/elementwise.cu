@@ -469,7 +469,7 @@ gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lo
 
 template <int VEC>
 __global__ void __launch_bounds__(256)
-gate_mix_bwd_apply_kernel(grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0, long long ld_g0,
+gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0, long long ld_g0,
                           long long M, int C, const float* s3, const float* t3, const float* mean3, const float* invstd3,
                           const double* red3, grad_t* dg0, long long ld_dg0, int CL, int PL) {
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
@@ -484,29 +484,26 @@ gate_mix_bwd_apply_kernel(grad_t* dz, long long ld_dz, const act_t* z, long long
     for (int v = 0; v < VEC; ++v) { k1[v] = static_cast<float>(red3[c + v] * invn); k2[v] = static_cast<float>(red3[C + c + v] * invn) * is[v]; }
   }
   for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-    float df[VEC], dl[VEC], da[VEC], l[VEC], a[VEC], g[VEC], o[VEC];
-    ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+    float df[VEC], l[VEC], a[VEC], g[VEC], o[VEC];
+    ldv<VEC>(dz + m * ld_dz + c, df);
     ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a); ldv<VEC>(g0 + m * ld_g0 + c, g);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
       const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
       const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
       o[v] = sc[v] * (ds - k1[v] - (g[v] - mu[v]) * k2[v]);
-      dl[v] += df[v] * gg;
-      da[v] += df[v] * (1.f - gg);
     }
     stv<VEC>(dg0 + m * ld_dg0 + c, o);
-    stv<VEC>(dz + m * ld_dz + C + c, dl);
-    stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
   }
 }
 
 // pass 1 of the branch backward: BN1 reductions and dgamma
 template <int VEC>
 __global__ void __launch_bounds__(256)
-branch_bwd_reduce1_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, int B, int H, int W,
-                          int C, const float* s1, const float* t1, const float* mean1, const float* invstd1,
-                          const float* o, int P, double* red1, double* dgamma, int CL, int PL) {
+branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* g0, long long ld_g0,
+                          int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
+                          const float* invstd1, const float* s3, const float* t3, const float* o, int P, double* red1,
+                          double* dgamma, int CL, int PL) {
   __shared__ float s_red[2 * 256 * VEC];
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c_base = blockIdx.y * CL * VEC;
@@ -517,16 +514,27 @@ branch_bwd_reduce1_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, lo
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
   float dg = 0.f;
   if (pl < PL && c < C) {
-    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC], sc3[VEC], sh3[VEC];
     ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(mean1 + c, mu); ldf<VEC>(invstd1 + c, is);
+    ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3);
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
       const unsigned mu32 = static_cast<unsigned>(m);
       const int x = static_cast<int>(mu32 % static_cast<unsigned>(W));
       const unsigned r = mu32 / static_cast<unsigned>(W);
       const int y = static_cast<int>(r % static_cast<unsigned>(H));
       const long long b = r / static_cast<unsigned>(H);
-      float dl[VEC], da[VEC], lv[VEC], u[VEC];
+      float dl[VEC], da[VEC], lv[VEC], u[VEC], df[VEC], gv[VEC];
       ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+      ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(g0 + m * ld_g0 + c, gv);
+      // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); stored back so the later passes read the totals
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float gg = 1.f / (1.f + __expf(-fmaf(gv[v], sc3[v], sh3[v])));
+        dl[v] += df[v] * gg;
+        da[v] += df[v] * (1.f - gg);
+      }
+      stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+      ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);   // bf16-rounded, as later passes see them
       ldv<VEC>(l0 + m * ld_l0 + c, lv);
       bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
 #pragma unroll
@@ -902,7 +910,7 @@ extern "C" int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const vo
   return DFCSA_OK;
 }
 
-extern "C" int dfcsa_gate_mix_bwd_apply(void* dz, int64_t ld_dz, const void* z, int64_t ld_z, const void* g0,
+extern "C" int dfcsa_gate_mix_bwd_apply(const void* dz, int64_t ld_dz, const void* z, int64_t ld_z, const void* g0,
                                         int64_t ld_g0, int64_t M, int32_t C, const float* scale3, const float* shift3,
                                         const float* mean3, const float* invstd3, const float* gamma3, const double* red3,
                                         void* dg0, int64_t ld_dg0, void* stream) {
@@ -911,23 +919,26 @@ extern "C" int dfcsa_gate_mix_bwd_apply(void* dz, int64_t ld_dz, const void* z, 
   const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0, ld_dg0}, {dz, z, g0, dg0, scale3, shift3, mean3, invstd3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   dim3 grid(red_blocks(M, g.PL), g.chunks);
-  VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
+  VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
                                                                          mean3, invstd3, red3, GM_(dg0), ld_dg0, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("gate_mix_bwd_apply_kernel");
   return DFCSA_OK;
 }
 
-extern "C" int dfcsa_branch_bwd_reduce1(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, int32_t B, int32_t H,
-                                        int32_t W, int32_t C, const float* scale1, const float* shift1, const float* mean1,
-                                        const float* invstd1, const float* o, int32_t P, const float* gamma, double* red1,
-                                        double* dgamma, float* tmp, float* d_o, void* stream) {
-  DFCSA_CHECK_ARG(dz && l0 && scale1 && shift1 && mean1 && invstd1 && o && gamma && red1 && dgamma && tmp && d_o, "dfcsa_branch_bwd_reduce1: null pointer");
-  const bool v8 = vec8_ok(C, {ld_dz, ld_l0}, {dz, l0, o, tmp, scale1, shift1, mean1, invstd1});
+extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, const void* g0, int64_t ld_g0,
+                                        int32_t B, int32_t H, int32_t W, int32_t C, const float* scale1, const float* shift1,
+                                        const float* mean1, const float* invstd1, const float* scale3, const float* shift3,
+                                        const float* o, int32_t P, const float* gamma, double* red1, double* dgamma, float* tmp,
+                                        float* d_o, void* stream) {
+  DFCSA_CHECK_ARG(dz && l0 && g0 && scale1 && shift1 && mean1 && invstd1 && scale3 && shift3 && o && gamma && red1 && dgamma && tmp && d_o,
+                  "dfcsa_branch_bwd_reduce1: null pointer");
+  const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_g0}, {dz, l0, g0, o, tmp, scale1, shift1, mean1, invstd1, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
   dim3 grid(red_blocks(M, g.PL), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, B, H, W, C, scale1, shift1, mean1,
-                                                                         invstd1, o, P, red1, dgamma, g.CL, g.PL)));
+  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, B, H, W, C, scale1,
+                                                                         shift1, mean1, invstd1, scale3, shift3, o, P, red1, dgamma,
+                                                                         g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));

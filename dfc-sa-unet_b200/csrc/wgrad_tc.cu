@@ -48,11 +48,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   // work item
+  // tap fastest: the CTAs resident together are the taps / tiles of the SAME pixel range, so the shifted re-reads of
+  // x and the repeated reads of dy hit L2 instead of HBM (x alone is 822 MB at level 1, far beyond the 126 MB L2)
   int id = blockIdx.x;
-  const int split = id % a.splits; id /= a.splits;
-  const int ct = id % a.c_tiles;   id /= a.c_tiles;
+  const int tap = id % a.taps;     id /= a.taps;
   const int nt = id % a.n_tiles;   id /= a.n_tiles;
-  const int tap = id;
+  const int ct = id % a.c_tiles;   id /= a.c_tiles;
+  const int split = id;
   const int n0 = nt * 128;
   const int c0 = ct * a.block_c;
   const long long pb_beg = split * a.blocks_per_split;

@@ -77,10 +77,12 @@ def pack_block_weights(bp, training, need_dx=True):
     ops.permute3(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1))
     if training:
         bdt = BF16 if C % 64 == 0 else F32
-        pk["wd4"] = _e((3 * C, C), bdt, dev)       # [k_in, co] = W4^T
-        ops.permute3(bp.W4.detach(), pk["wd4"], (3 * C, 1, C), (1, 0, 3 * C))
-        pk["wd3"] = _e((2 * C, C), bdt, dev)
-        ops.permute3(bp.W3.detach(), pk["wd3"], (2 * C, 1, C), (1, 0, 2 * C))
+        wd4 = _e((3 * C, C), bdt, dev)             # [k_in, co] = W4^T
+        ops.permute3(bp.W4.detach(), wd4, (3 * C, 1, C), (1, 0, 3 * C))
+        wd3 = _e((2 * C, C), bdt, dev)
+        ops.permute3(bp.W3.detach(), wd3, (2 * C, 1, C), (1, 0, 2 * C))
+        pk["wd4f"] = wd4[:C]                       # df  = dF0 . W4^T[:, 0:C]
+        pk["wd43"] = torch.cat([wd4[C:], wd3], dim=1).contiguous()   # [dL|dA] = [dF0 | dG0] . [W4^T[:, C:3C] ; W3^T]
         if need_dx:   # the first block never needs the gradient w.r.t. the image
             xdt = BF16 if bp.tc else F32
             wd = _e((Ci, 11 * C), xdt, dev)            # [ci, (flipped tap, co) | co (W2) | co (res_scale*W5)]
@@ -231,27 +233,30 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     dF0 = _e((M, C), BF16, dev)
     ops.bn_bwd_apply(dy, ctx.F0, bn4[0], bn4[1], bn4[2], bn4[3], red4, 0, dF0)
     ops.bn_param_grads(red4, C, grads[bp.bn4.weight], grads[bp.bn4.bias])
-    # fusion conv
+    # fusion conv, part 1: df = dF0 . W4^T[:, 0:C]  (the gate-mix backward only needs df)
     dz = _e((M, 3 * C), BF16, dev)
     segs = [(dF0, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["wd4"], 3 * C, dz, backend=_backend(segs, pk["wd4"], 3 * C, dz))
+    df = dz[:, :C]
+    ops.conv_gemm(B, H, W, segs, pk["wd4f"], C, df, backend=_backend(segs, pk["wd4f"], C, df))
     _wgrad(B, H, W, ctx.zb, TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 3 * C))
     # gate / mix
     ops.gate_mix_bwd_reduce(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3)
-    dG0 = dF0   # dF0 is dead after the fusion wgrad: reuse its storage
+    dG0 = _e((M, C), BF16, dev)
     ops.gate_mix_bwd_apply(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3, dG0)
     ops.bn_param_grads(red3, C, grads[bp.bn3.weight], grads[bp.bn3.bias])
+    # fusion conv part 2 + gate conv in ONE dgrad GEMM: [dL' | dA'] = [dF0 | dG0] . [W4^T[:, C:3C] ; W3^T]
     dLA = dz[:, C:]
-    segs = [(dG0, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["wd3"], 2 * C, dLA, accumulate=True, backend=_backend(segs, pk["wd3"], 2 * C, dLA))
+    segs = [(dF0, TAP_1x1), (dG0, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["wd43"], 2 * C, dLA, backend=_backend(segs, pk["wd43"], 2 * C, dLA))
     _wgrad(B, H, W, ctx.zb[:, C:], TAP_1x1, dG0, TAP_1x1, grads[bp.W3].view(C, 2 * C))
-    # branches
+    # branches (reduce1 first adds the gate-mix terms df*g / df*(1-g) into dL / dA in place)
     tmp = _e((B, H, P, C), F32, dev)
     d_o = _e((B * P * P, C), F32, dev)
-    ops.branch_bwd_reduce1(dz, ctx.L0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], ctx.o, P, bp.gamma.detach(), red1, dgam, tmp, d_o)
+    ops.branch_bwd_reduce1(dz, ctx.L0, ctx.G0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], bn3[0], bn3[1], ctx.o, P,
+                           bp.gamma.detach(), red1, dgam, tmp, d_o)
     dpooled = attention_backward(bp, ctx, d_o, B, grads)
     ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
-    dL0, dA0 = _e((M, C), BF16, dev), dG0
+    dL0, dA0 = dF0, dG0     # both dead after the GEMMs above: reuse their storage
     ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
     ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
     ops.bn_param_grads(red2, C, grads[bp.bn2.weight], grads[bp.bn2.bias])

@@ -181,10 +181,11 @@ def gate_mix_bwd_apply(dz, z, g0, s3, t3, mean3, invstd3, red3, dg0):
                                              L.ptr(red3), L.ptr(dg0), _i64(_mat(dg0)), L.stream())
 
 
-def branch_bwd_reduce1(dz, l0, B, H, W, s1, t1, mean1, invstd1, o, P, gamma, red1, dgamma, tmp, d_o):
+def branch_bwd_reduce1(dz, l0, g0, B, H, W, s1, t1, mean1, invstd1, s3, t3, o, P, gamma, red1, dgamma, tmp, d_o):
     Cn = l0.shape[1]
-    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), B, H, W, Cn, L.ptr(s1),
-                                             L.ptr(t1), L.ptr(mean1), L.ptr(invstd1), L.ptr(o), P, L.ptr(gamma), L.ptr(red1),
+    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), L.ptr(g0), _i64(_mat(g0)),
+                                             B, H, W, Cn, L.ptr(s1),
+                                             L.ptr(t1), L.ptr(mean1), L.ptr(invstd1), L.ptr(s3), L.ptr(t3), L.ptr(o), P, L.ptr(gamma), L.ptr(red1),
                                              L.ptr(dgamma), L.ptr(tmp), L.ptr(d_o), L.stream())
 
 

@@ -198,19 +198,21 @@ int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const void* z, int6
                               const void* g0, int64_t ld_g0, int64_t M, int32_t C,
                               const float* scale3, const float* shift3, const float* mean3, const float* invstd3,
                               double* red3, void* stream);
-/* pass 2: dG0 = gamma3*invstd3*(dS - mean(dS) - xhat3*mean(dS*xhat3)) -> dg0 (bf16);
- *         dz[:, C:2C] += df*g ; dz[:, 2C:3C] += df*(1-g)   (in place) */
-int dfcsa_gate_mix_bwd_apply(void* dz, int64_t ld_dz, const void* z, int64_t ld_z,
+/* pass 2: dG0 = gamma3*invstd3*(dS - mean(dS) - xhat3*mean(dS*xhat3)) -> dg0 (bf16).  Only df = dz[:, 0:C] is read: the
+ * dL / dA columns of dz are produced afterwards by one two-segment dgrad GEMM over [dF0 | dG0] (no read-modify-write). */
+int dfcsa_gate_mix_bwd_apply(const void* dz, int64_t ld_dz, const void* z, int64_t ld_z,
                              const void* g0, int64_t ld_g0, int64_t M, int32_t C,
                              const float* scale3, const float* shift3, const float* mean3, const float* invstd3,
                              const float* gamma3, const double* red3,
                              void* dg0, int64_t ld_dg0, void* stream);
-/* branch backward, pass 1 (needs the complete dL = dz[:,C:2C], dA = dz[:,2C:3C]):
+/* branch backward, pass 1.  First completes the gradients of the two branches in place with the gate-mix terms:
+ *   dL = dz[:,C:2C] += df*g,  dA = dz[:,2C:3C] += df*(1-g),  g = sigmoid(bn3(G0)), df = dz[:,0:C];  then
  *   red1 += (sum d1, sum d1*xhat1) with d1 = dL*[L>0];
  *   dgamma += sum dA*U (U = bilinear_up(o));  do = gamma * bilinear_up^T(dA)  ([B,P,P,C] fp32, separable, tmp [B,H,P,C]) */
-int dfcsa_branch_bwd_reduce1(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0,
+int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, const void* g0, int64_t ld_g0,
                              int32_t B, int32_t H, int32_t W, int32_t C,
                              const float* scale1, const float* shift1, const float* mean1, const float* invstd1,
+                             const float* scale3, const float* shift3,
                              const float* o, int32_t P, const float* gamma,
                              double* red1, double* dgamma, float* tmp, float* d_o, void* stream);
 /* pass 2 (after the pooled-attention backward produced dpooled [B,P,P,C]):
