@@ -52,6 +52,40 @@ __device__ __forceinline__ void bilerp_taps(int d, int P, int s, int& i0, int& i
   l1 = src - static_cast<float>(i0);
 }
 
+// (b, y, x) of pixel m for a grid-stride walk, advanced without divisions
+struct PixIter {
+  unsigned x, y, b, sx, sy, sb;
+  __device__ __forceinline__ void init(unsigned m0, unsigned stride, unsigned H, unsigned W) {
+    x = m0 % W; unsigned r = m0 / W; y = r % H; b = r / H;
+    sx = stride % W; r = stride / W; sy = r % H; sb = r / H;
+  }
+  __device__ __forceinline__ void next(unsigned H, unsigned W) {
+    x += sx; if (x >= W) { x -= W; ++y; }
+    y += sy; if (y >= H) { y -= H; ++b; }
+    b += sb;
+  }
+};
+
+// adaptive_avg_pool^T lookup tables in shared memory: for every source row / column the range of windows that contain
+// it, and 1/|window| per window (integer divisions done once per block instead of ~10 per 16-byte vector)
+struct PoolTabs { const int* yt; const int* xt; const float* wy; const float* wx; };
+__device__ __forceinline__ PoolTabs build_pool_tabs(unsigned char* smem, int H, int W, int P) {
+  int* yt = reinterpret_cast<int*>(smem);
+  int* xt = yt + H;
+  float* wy = reinterpret_cast<float*>(xt + W);
+  float* wx = wy + P;
+  for (int t = threadIdx.x; t < H; t += blockDim.x) { int lo, hi; pool_win_of(t, H, P, lo, hi); yt[t] = lo | (hi << 16); }
+  for (int t = threadIdx.x; t < W; t += blockDim.x) { int lo, hi; pool_win_of(t, W, P, lo, hi); xt[t] = lo | (hi << 16); }
+  for (int t = threadIdx.x; t < P; t += blockDim.x) {
+    int a, e; pool_win(t, H, P, a, e); wy[t] = 1.f / static_cast<float>(e - a);
+    pool_win(t, W, P, a, e); wx[t] = 1.f / static_cast<float>(e - a);
+  }
+  __syncthreads();
+  PoolTabs t; t.yt = yt; t.xt = xt; t.wy = wy; t.wx = wx;
+  return t;
+}
+static inline size_t pool_tabs_bytes(int H, int W, int P) { return static_cast<size_t>(H + W + 2 * P) * 4; }
+
 // ---- per-channel block reduction: thread (cl, pl) holds NRED x VEC partials for channel vector cl ----
 template <int VEC, int NRED>
 __device__ __forceinline__ void flush_channel_partials(float (&acc)[NRED][VEC], int cl, int pl, int CL, int PL,
@@ -179,9 +213,12 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
   }
 }
 // out[b, i, j, c] = scale_out * sum_y wgt(i, y) * tmp[b, y, j, c]; mode 0: pool windows over y, mode 1: bilinear^T
-__global__ void cols_reduce_kernel(const float* tmp, int B, int H, int P, int C, int mode, const float* mul, float* out) {
+__global__ void __launch_bounds__(256)
+cols_reduce_kernel(const float* tmp, int B, int H, int P, int C, int mode, const float* mul, float* out,
+                   const float* dot_with, double* dot_out) {
   const long long total = static_cast<long long>(B) * P * P * C;
   const float m = mul ? *mul : 1.f;
+  float dot = 0.f;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(idx % C);
@@ -208,7 +245,9 @@ __global__ void cols_reduce_kernel(const float* tmp, int B, int H, int P, int C,
       }
     }
     out[idx] = acc * m;
+    if (dot_with != nullptr) dot = fmaf(acc, dot_with[idx], dot);
   }
+  if (dot_out != nullptr) block_scalar_reduce_add(dot, dot_out);   // <unscaled result, dot_with>
 }
 
 // =============================================================================================
@@ -230,7 +269,7 @@ __device__ __forceinline__ void bilerp_gather(const float* o, long long b, int y
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H, int W, int C,
                       const float* s1, const float* t1, const float* s2, const float* t2, const float* o, int P,
                       const float* gamma, act_t* z, long long ld_z, grad_t* zb, long long ld_zb, int CL, int PL) {
@@ -241,8 +280,9 @@ branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long lo
   const float gm = *gamma;
   float sc1[VEC], sh1[VEC], sc2[VEC], sh2[VEC];
   ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2);
-  for (unsigned m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL) {
-    const unsigned x = m % W, r = m / W, y = r % H, b = r / H;
+  PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, H, W);
+  for (unsigned m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL, it.next(H, W)) {
+    const unsigned x = it.x, y = it.y, b = it.b;
     float v0[VEC], outv[VEC];
     ldv<VEC>(l0 + static_cast<long long>(m) * ld_l0 + c, v0);
 #pragma unroll
@@ -327,9 +367,52 @@ block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long
 
 // =============================================================================================
 // backward
+// Register budget: these kernels are pure streaming, so what matters is resident threads per SM.  Per-channel
+// constants are kept to (scale, shift) for the activation mask plus two folded BN-backward coefficients
+//   dx = scale*(d - k1 - (x - mean)*k2)  =  scale*d + p*x + q,   p = -scale*k2,  q = scale*(k2*mean - k1)
+// and the second BatchNorm reduction is accumulated as sum(d*x) and turned into sum(d*xhat) = invstd*(sum(d*x) -
+// mean*sum(d)) in double when a block flushes, so mean / invstd never live in registers.
 // =============================================================================================
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void flush_bn_partials(float (&acc)[2][VEC], int cl, int pl, int CL, int PL, int c_base, int C,
+                                                  const float* mean, const float* invstd, double* red, float* s_red) {
+  // s_red: [2][PL][CL*VEC]
+  const int row = CL * VEC;
+  if (cl < CL && pl < PL) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s_red[(r * PL + pl) * row + cl * VEC + v] = acc[r][v];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < row; idx += blockDim.x) {
+    const int c = c_base + idx;
+    if (c < C) {
+      float s1 = 0.f, s2 = 0.f;
+      for (int p = 0; p < PL; ++p) { s1 += s_red[p * row + idx]; s2 += s_red[(PL + p) * row + idx]; }
+      atomicAdd(red + c, static_cast<double>(s1));
+      atomicAdd(red + C + c, static_cast<double>(invstd[c]) * (static_cast<double>(s2) - static_cast<double>(mean[c]) * static_cast<double>(s1)));
+    }
+  }
+}
+
+// folded BN-backward coefficients of channel vector c (see the section comment)
+template <int VEC>
+__device__ __forceinline__ void bn_bwd_coeffs(const float* scale, const float* mean, const float* invstd, const double* red,
+                                              int C, int c, double invn, float (&sc)[VEC], float (&p)[VEC], float (&q)[VEC]) {
+  float mu[VEC], is[VEC];
+  ldf<VEC>(scale + c, sc); ldf<VEC>(mean + c, mu); ldf<VEC>(invstd + c, is);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const float k1 = static_cast<float>(red[c + v] * invn);
+    const float k2 = static_cast<float>(red[C + c + v] * invn) * is[v];
+    p[v] = -sc[v] * k2;
+    q[v] = sc[v] * (k2 * mu[v] - k1);
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256, 3)
 block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_t* dyp, long long ld_dyp,
                             const act_t* y, long long ld_y, const act_t* f0, long long ld_f0, const act_t* r,
                             long long ld_r, int B, int H, int W, int C, const float* s4, const float* t4,
@@ -342,19 +425,18 @@ block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_
   const bool active = pl < PL && c < C;
   const int Hw = (H + 1) / 2, Ww = (W + 1) / 2;
   const int Hp = H / 2, Wp = W / 2;
-  const long long nwin = static_cast<long long>(B) * Hw * Ww;
+  const unsigned nwin = static_cast<unsigned>(B) * Hw * Ww;
   float acc[2][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
   float drs_acc = 0.f;
   if (active) {
-    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
-    ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh); ldf<VEC>(mean4 + c, mu); ldf<VEC>(invstd4 + c, is);
-    for (long long wi = static_cast<long long>(blockIdx.x) * PL + pl; wi < nwin; wi += static_cast<long long>(gridDim.x) * PL) {
-      const int xo = static_cast<int>(wi % Ww);
-      long long q = wi / Ww;
-      const int yo = static_cast<int>(q % Hw);
-      const long long b = q / Hw;
+    float sc[VEC], sh[VEC];
+    ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh);
+    PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, Hw, Ww);
+    for (unsigned wi = blockIdx.x * PL + pl; wi < nwin; wi += gridDim.x * PL, it.next(Hw, Ww)) {
+      const int xo = it.x, yo = it.y;
+      const long long b = it.b;
       // argmax of the stored y over the window (first maximum in scan order, like ATen's max_pool2d)
       int arg[VEC];
       float gp[VEC];
@@ -388,40 +470,39 @@ block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_
           for (int v = 0; v < VEC; ++v) if (arg[v] == k) d[v] += gp[v];
         }
         if (dy_out != nullptr && (dy_out != dskip || pooled)) {
+          // round to the stored precision first, so the sums see exactly what the later passes read
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(d[v]));
           stv<VEC>(dy_out + m * ld_dy + c, d);
-          if (pooled || dy_out != dskip) ldv<VEC>(dy_out + m * ld_dy + c, d);   // use the value later passes will read
         }
         float fv[VEC], rv[VEC];
         ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          drs_acc += d[v] * rv[v];
+          drs_acc = fmaf(d[v], rv[v], drs_acc);
           const float d4 = fmaf(fv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
           acc[0][v] += d4;
-          acc[1][v] += d4 * (fv[v] - mu[v]) * is[v];
+          acc[1][v] = fmaf(d4, fv[v], acc[1][v]);
         }
       }
     }
   }
-  double* const outs[2] = {red4, red4 + C};
-  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+  flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean4, invstd4, red4, s_red);
   block_scalar_reduce_add(drs_acc, drs);
 }
 
 // dx = scale * (d - k1 - xhat*k2), d = dy * [relu mask] (act_mode 0) or dy (act_mode 2)
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_bwd_apply_kernel(const grad_t* dy, long long ld_dy, const act_t* x, long long ld_x, long long M, int C,
                     const float* scale, const float* shift, const float* mean, const float* invstd, const double* red,
                     int act_mode, grad_t* dx, long long ld_dx, int CL, int PL) {
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c = (blockIdx.y * CL + cl) * VEC;
   if (pl >= PL || c >= C) return;
-  const double invn = 1.0 / static_cast<double>(M);
-  float sc[VEC], sh[VEC], mu[VEC], is[VEC], k1[VEC], k2[VEC];
-  ldf<VEC>(scale + c, sc); ldf<VEC>(shift + c, sh); ldf<VEC>(mean + c, mu); ldf<VEC>(invstd + c, is);
-#pragma unroll
-  for (int v = 0; v < VEC; ++v) { k1[v] = static_cast<float>(red[c + v] * invn); k2[v] = static_cast<float>(red[C + c + v] * invn) * is[v]; }
+  float sc[VEC], sh[VEC], p[VEC], q[VEC];
+  bn_bwd_coeffs<VEC>(scale, mean, invstd, red, C, c, 1.0 / static_cast<double>(M), sc, p, q);
+  ldf<VEC>(shift + c, sh);
   for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
     float d[VEC], xv[VEC], o[VEC];
     ldv<VEC>(dy + m * ld_dy + c, d); ldv<VEC>(x + m * ld_x + c, xv);
@@ -429,14 +510,14 @@ bn_bwd_apply_kernel(const grad_t* dy, long long ld_dy, const act_t* x, long long
     for (int v = 0; v < VEC; ++v) {
       float dd = d[v];
       if (act_mode == 0 && !(fmaf(xv[v], sc[v], sh[v]) > 0.f)) dd = 0.f;
-      o[v] = sc[v] * (dd - k1[v] - (xv[v] - mu[v]) * k2[v]);
+      o[v] = fmaf(sc[v], dd, fmaf(p[v], xv[v], q[v]));
     }
     stv<VEC>(dx + m * ld_dx + c, o);
   }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0,
                            long long ld_g0, long long M, int C, const float* s3, const float* t3, const float* mean3,
                            const float* invstd3, double* red3, int CL, int PL) {
@@ -448,8 +529,8 @@ gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lo
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
   if (pl < PL && c < C) {
-    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
-    ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh); ldf<VEC>(mean3 + c, mu); ldf<VEC>(invstd3 + c, is);
+    float sc[VEC], sh[VEC];
+    ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh);
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
       float df[VEC], l[VEC], a[VEC], g[VEC];
       ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a);
@@ -459,30 +540,24 @@ gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lo
         const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
         const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
         acc[0][v] += ds;
-        acc[1][v] += ds * (g[v] - mu[v]) * is[v];
+        acc[1][v] = fmaf(ds, g[v], acc[1][v]);
       }
     }
   }
-  double* const outs[2] = {red3, red3 + C};
-  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+  flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean3, invstd3, red3, s_red);
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0, long long ld_g0,
                           long long M, int C, const float* s3, const float* t3, const float* mean3, const float* invstd3,
                           const double* red3, grad_t* dg0, long long ld_dg0, int CL, int PL) {
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c = (blockIdx.y * CL + cl) * VEC;
   if (pl >= PL || c >= C) return;
-  const double invn = 1.0 / static_cast<double>(M);
-  float sc[VEC], sh[VEC], mu[VEC], k1[VEC], k2[VEC];
-  ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh); ldf<VEC>(mean3 + c, mu);
-  {
-    float is[VEC]; ldf<VEC>(invstd3 + c, is);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) { k1[v] = static_cast<float>(red3[c + v] * invn); k2[v] = static_cast<float>(red3[C + c + v] * invn) * is[v]; }
-  }
+  float sc[VEC], sh[VEC], p[VEC], q[VEC];
+  bn_bwd_coeffs<VEC>(s3, mean3, invstd3, red3, C, c, 1.0 / static_cast<double>(M), sc, p, q);
+  ldf<VEC>(t3 + c, sh);
   for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
     float df[VEC], l[VEC], a[VEC], g[VEC], o[VEC];
     ldv<VEC>(dz + m * ld_dz + c, df);
@@ -491,64 +566,51 @@ gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lon
     for (int v = 0; v < VEC; ++v) {
       const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
       const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
-      o[v] = sc[v] * (ds - k1[v] - (g[v] - mu[v]) * k2[v]);
+      o[v] = fmaf(sc[v], ds, fmaf(p[v], g[v], q[v]));
     }
     stv<VEC>(dg0 + m * ld_dg0 + c, o);
   }
 }
 
-// pass 1 of the branch backward: BN1 reductions and dgamma
+// pass 1 of the branch backward: gate-mix terms into dL / dA (in place) and the BN1 reductions
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* g0, long long ld_g0,
-                          int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
-                          const float* invstd1, const float* s3, const float* t3, const float* o, int P, double* red1,
-                          double* dgamma, int CL, int PL) {
+                          long long M, int C, const float* s1, const float* t1, const float* mean1,
+                          const float* invstd1, const float* s3, const float* t3, double* red1, int CL, int PL) {
   __shared__ float s_red[2 * 256 * VEC];
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c_base = blockIdx.y * CL * VEC;
   const int c = c_base + cl * VEC;
-  const long long M = static_cast<long long>(B) * H * W;
   float acc[2][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
-  float dg = 0.f;
   if (pl < PL && c < C) {
-    float sc[VEC], sh[VEC], mu[VEC], is[VEC], sc3[VEC], sh3[VEC];
-    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(mean1 + c, mu); ldf<VEC>(invstd1 + c, is);
-    ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3);
+    float sc[VEC], sh[VEC], sc3[VEC], sh3[VEC];
+    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3);
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      const unsigned mu32 = static_cast<unsigned>(m);
-      const int x = static_cast<int>(mu32 % static_cast<unsigned>(W));
-      const unsigned r = mu32 / static_cast<unsigned>(W);
-      const int y = static_cast<int>(r % static_cast<unsigned>(H));
-      const long long b = r / static_cast<unsigned>(H);
-      float dl[VEC], da[VEC], lv[VEC], u[VEC], df[VEC], gv[VEC];
+      float dl[VEC], da[VEC], df[VEC], gv[VEC], lv[VEC];
       ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
       ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(g0 + m * ld_g0 + c, gv);
-      // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); stored back so the later passes read the totals
+      ldv<VEC>(l0 + m * ld_l0 + c, lv);
+      // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); rounded to the stored precision so that the sums see
+      // exactly what the later passes read back
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float gg = 1.f / (1.f + __expf(-fmaf(gv[v], sc3[v], sh3[v])));
-        dl[v] += df[v] * gg;
-        da[v] += df[v] * (1.f - gg);
+        dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
+        da[v] = fmaf(df[v], 1.f - gg, da[v]);
       }
       stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
-      ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);   // bf16-rounded, as later passes see them
-      ldv<VEC>(l0 + m * ld_l0 + c, lv);
-      bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float d1 = fmaf(lv[v], sc[v], sh[v]) > 0.f ? dl[v] : 0.f;
         acc[0][v] += d1;
-        acc[1][v] += d1 * (lv[v] - mu[v]) * is[v];
-        dg += da[v] * u[v];
+        acc[1][v] = fmaf(d1, lv[v], acc[1][v]);
       }
     }
   }
-  double* const outs[2] = {red1, red1 + C};
-  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
-  block_scalar_reduce_add(dg, dgamma);
+  flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean1, invstd1, red1, s_red);
 }
 
 // bilinear^T along x: tmp[b, y, px, c] = sum_x wx(x, px) * dA[b, y, x, c]
@@ -590,106 +652,101 @@ __global__ void bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, in
 
 // adaptive_avg_pool^T gather of dpooled at pixel (y, x)
 template <int VEC>
-__device__ __forceinline__ void poolT_gather(const float* dp, long long b, int y, int x, int H, int W, int P, int C, int c,
-                                             float (&g)[VEC]) {
+__device__ __forceinline__ void poolT_gather(const float* dp, unsigned b, int y, int x, int P, int C, int c,
+                                             const PoolTabs& tb, float (&g)[VEC]) {
 #pragma unroll
   for (int v = 0; v < VEC; ++v) g[v] = 0.f;
-  int ilo, ihi, jlo, jhi;
-  pool_win_of(y, H, P, ilo, ihi);
-  pool_win_of(x, W, P, jlo, jhi);
+  const int ty = tb.yt[y], tx = tb.xt[x];
+  const int ilo = ty & 0xffff, ihi = ty >> 16, jlo = tx & 0xffff, jhi = tx >> 16;
+  const float* base = dp + static_cast<long long>(b) * P * P * C + c;
   for (int i = ilo; i <= ihi; ++i) {
-    int a, e; pool_win(i, H, P, a, e);
-    const float wi = 1.f / static_cast<float>(e - a);
+    const float wi = tb.wy[i];
     for (int j = jlo; j <= jhi; ++j) {
-      int a2, e2; pool_win(j, W, P, a2, e2);
-      const float wgt = wi / static_cast<float>(e2 - a2);
-      float t[VEC]; ldf<VEC>(dp + ((b * P + i) * P + j) * C + c, t);
+      const float wgt = wi * tb.wx[j];
+      float t[VEC]; ldf<VEC>(base + (i * P + j) * C, t);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) g[v] += wgt * t[v];
+      for (int v = 0; v < VEC; ++v) g[v] = fmaf(wgt, t[v], g[v]);
     }
   }
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, long long ld_a0, int B, int H, int W,
                           int C, const float* s2, const float* t2, const float* mean2, const float* invstd2,
                           const float* dpooled, int P, double* red2, int CL, int PL) {
   __shared__ float s_red[2 * 256 * VEC];
+  extern __shared__ unsigned char s_dyn[];
+  const PoolTabs tabs = build_pool_tabs(s_dyn, H, W, P);
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c_base = blockIdx.y * CL * VEC;
   const int c = c_base + cl * VEC;
-  const long long M = static_cast<long long>(B) * H * W;
+  const unsigned M = static_cast<unsigned>(B) * H * W;
   float acc[2][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
   if (pl < PL && c < C) {
-    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
-    ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh); ldf<VEC>(mean2 + c, mu); ldf<VEC>(invstd2 + c, is);
-    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      const unsigned mu32 = static_cast<unsigned>(m);
-      const int x = static_cast<int>(mu32 % static_cast<unsigned>(W));
-      const unsigned r = mu32 / static_cast<unsigned>(W);
-      const int y = static_cast<int>(r % static_cast<unsigned>(H));
-      const long long b = r / static_cast<unsigned>(H);
+    float sc[VEC], sh[VEC];
+    ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh);
+    PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, H, W);
+    for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += gridDim.x * PL, it.next(H, W)) {
+      const long long m = m32;
       float da[VEC], av[VEC], gp[VEC];
       ldv<VEC>(dz + m * ld_dz + 2 * C + c, da); ldv<VEC>(a0 + m * ld_a0 + c, av);
-      poolT_gather<VEC>(dpooled, b, y, x, H, W, P, C, c, gp);
+      poolT_gather<VEC>(dpooled, it.b, it.y, it.x, P, C, c, tabs, gp);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float d2 = fmaf(av[v], sc[v], sh[v]) > 0.f ? da[v] + gp[v] : 0.f;
         acc[0][v] += d2;
-        acc[1][v] += d2 * (av[v] - mu[v]) * is[v];
+        acc[1][v] = fmaf(d2, av[v], acc[1][v]);
       }
     }
   }
-  double* const outs[2] = {red2, red2 + C};
-  flush_channel_partials<VEC, 2>(acc, cl, pl, CL, PL, c_base, C, outs, s_red);
+  flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean2, invstd2, red2, s_red);
 }
 
+// pass 3: blockIdx.z = 0 -> dL0 from (dL, L0, BN1);  blockIdx.z = 1 -> dA0 from (dA + pool^T(dpooled), A0, BN2)
 template <int VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* a0,
                         long long ld_a0, int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
                         const float* invstd1, const double* red1, const float* s2, const float* t2, const float* mean2,
                         const float* invstd2, const double* red2, const float* dpooled, int P, grad_t* dl0,
                         long long ld_dl0, grad_t* da0, long long ld_da0, int CL, int PL) {
+  extern __shared__ unsigned char s_dyn[];
+  const bool abranch = blockIdx.z == 1;
+  PoolTabs tabs{};
+  if (abranch) tabs = build_pool_tabs(s_dyn, H, W, P);
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c = (blockIdx.y * CL + cl) * VEC;
   if (pl >= PL || c >= C) return;
   const unsigned M = static_cast<unsigned>(B) * H * W;
   const double invn = 1.0 / static_cast<double>(M);
-  float sc1[VEC], sh1[VEC], mu1[VEC], ka1[VEC], kb1[VEC], sc2[VEC], sh2[VEC], mu2[VEC], ka2[VEC], kb2[VEC];
-  ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); ldf<VEC>(mean1 + c, mu1);
-  ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2); ldf<VEC>(mean2 + c, mu2);
-  {
-    float i1[VEC], i2[VEC]; ldf<VEC>(invstd1 + c, i1); ldf<VEC>(invstd2 + c, i2);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      ka1[v] = static_cast<float>(red1[c + v] * invn); kb1[v] = static_cast<float>(red1[C + c + v] * invn) * i1[v];
-      ka2[v] = static_cast<float>(red2[c + v] * invn); kb2[v] = static_cast<float>(red2[C + c + v] * invn) * i2[v];
-    }
-  }
-  for (unsigned m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL) {
-    const unsigned x = m % W, r = m / W, y = r % H, b = r / H;
-    const long long mm = m;
+  float sc[VEC], sh[VEC], p[VEC], q[VEC];
+  if (abranch) { bn_bwd_coeffs<VEC>(s2, mean2, invstd2, red2, C, c, invn, sc, p, q); ldf<VEC>(t2 + c, sh); }
+  else         { bn_bwd_coeffs<VEC>(s1, mean1, invstd1, red1, C, c, invn, sc, p, q); ldf<VEC>(t1 + c, sh); }
+  const grad_t* dsrc = dz + (abranch ? 2 * C : C) + c;
+  const act_t* xsrc = abranch ? a0 + c : l0 + c;
+  const long long ld_xs = abranch ? ld_a0 : ld_l0;
+  grad_t* dst = abranch ? da0 + c : dl0 + c;
+  const long long ld_dst = abranch ? ld_da0 : ld_dl0;
+  PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, H, W);
+  for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += gridDim.x * PL, it.next(H, W)) {
+    const long long m = m32;
     float d[VEC], xv[VEC], o[VEC];
-    ldv<VEC>(dz + mm * ld_dz + C + c, d); ldv<VEC>(l0 + mm * ld_l0 + c, xv);
+    ldv<VEC>(dsrc + m * ld_dz, d); ldv<VEC>(xsrc + m * ld_xs, xv);
+    if (abranch) {
+      float gp[VEC];
+      poolT_gather<VEC>(dpooled, it.b, it.y, it.x, P, C, c, tabs, gp);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) d[v] += gp[v];
+    }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
-      const float dd = fmaf(xv[v], sc1[v], sh1[v]) > 0.f ? d[v] : 0.f;
-      o[v] = sc1[v] * (dd - ka1[v] - (xv[v] - mu1[v]) * kb1[v]);
+      const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
+      o[v] = fmaf(sc[v], dd, fmaf(p[v], xv[v], q[v]));
     }
-    stv<VEC>(dl0 + mm * ld_dl0 + c, o);
-    float gp[VEC];
-    ldv<VEC>(dz + mm * ld_dz + 2 * C + c, d); ldv<VEC>(a0 + mm * ld_a0 + c, xv);
-    poolT_gather<VEC>(dpooled, b, y, x, H, W, P, C, c, gp);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float dd = fmaf(xv[v], sc2[v], sh2[v]) > 0.f ? d[v] + gp[v] : 0.f;
-      o[v] = sc2[v] * (dd - ka2[v] - (xv[v] - mu2[v]) * kb2[v]);
-    }
-    stv<VEC>(da0 + mm * ld_da0 + c, o);
+    stv<VEC>(dst + m * ld_dst, o);
   }
 }
 
@@ -813,7 +870,7 @@ extern "C" int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int3
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (pool_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(a0), ld, B, H, W, C, scale, shift, P, tmp)));
   DFCSA_LAUNCH_CHECK("pool_rows_kernel");
-  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled);
+  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
   DFCSA_LAUNCH_CHECK("cols_reduce_kernel");
   return DFCSA_OK;
 }
@@ -932,18 +989,19 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
                                         float* d_o, void* stream) {
   DFCSA_CHECK_ARG(dz && l0 && g0 && scale1 && shift1 && mean1 && invstd1 && scale3 && shift3 && o && gamma && red1 && dgamma && tmp && d_o,
                   "dfcsa_branch_bwd_reduce1: null pointer");
+  DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_bwd_reduce1: too many pixels");
   const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_g0}, {dz, l0, g0, o, tmp, scale1, shift1, mean1, invstd1, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
   dim3 grid(red_blocks(M, g.PL), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, B, H, W, C, scale1,
-                                                                         shift1, mean1, invstd1, scale3, shift3, o, P, red1, dgamma,
-                                                                         g.CL, g.PL)));
+  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
+                                                                         shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));
   DFCSA_LAUNCH_CHECK("bilerpT_rows_kernel");
-  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o);
+  // dgamma = sum dA*U = <bilinear_up^T(dA), o>: a dot product over the small pooled map instead of a gather per pixel
+  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);
   DFCSA_LAUNCH_CHECK("cols_reduce_kernel(bilerpT)");
   return DFCSA_OK;
 }
@@ -952,11 +1010,12 @@ extern "C" int dfcsa_branch_bwd_reduce2(const void* dz, int64_t ld_dz, const voi
                                         int32_t W, int32_t C, const float* scale2, const float* shift2, const float* mean2,
                                         const float* invstd2, const float* dpooled, int32_t P, double* red2, void* stream) {
   DFCSA_CHECK_ARG(dz && a0 && scale2 && shift2 && mean2 && invstd2 && dpooled && red2, "dfcsa_branch_bwd_reduce2: null pointer");
+  DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31) && H < 32768 && W < 32768, "dfcsa_branch_bwd_reduce2: too many pixels");
   const bool v8 = vec8_ok(C, {ld_dz, ld_a0}, {dz, a0, dpooled, scale2, shift2, mean2, invstd2});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
   dim3 grid(red_blocks(M, g.PL), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_reduce2_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2,
+  VEC_DISPATCH(v8, (branch_bwd_reduce2_kernel<VEC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2,
                                                                          invstd2, dpooled, P, red2, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce2_kernel");
   return DFCSA_OK;
@@ -972,10 +1031,10 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
   DFCSA_CHECK_ARG(dz && l0 && a0 && red1 && red2 && dpooled && dl0 && da0, "dfcsa_branch_bwd_apply: null pointer");
   const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_a0, ld_dl0, ld_da0},
                           {dz, l0, a0, dl0, da0, dpooled, scale1, shift1, mean1, invstd1, scale2, shift2, mean2, invstd2});
-  DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_bwd_apply: too many pixels");
+  DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31) && H < 32768 && W < 32768, "dfcsa_branch_bwd_apply: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL), g.chunks, 2);
+  VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
                                                                        shift1, mean1, invstd1, red1, scale2, shift2, mean2, invstd2,
                                                                        red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_apply_kernel");

@@ -349,7 +349,7 @@ __global__ void softmax_rows_bwd_kernel(const float* __restrict__ y, const float
 // permute3 (weight re-layout with cast)
 // ---------------------------------------------------------------------------------------------
 __global__ void permute3_kernel(const void* src, int sdt, void* dst, int ddt, long long D0, long long D1, long long D2,
-                                long long s0, long long s1, long long s2, int flip1, const float* scale) {
+                                long long s0, long long s1, long long s2, int flip1, const float* scale, long long ld_dst) {
   const long long total = D0 * D1 * D2;
   const float sc = scale ? *scale : 1.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -359,7 +359,8 @@ __global__ void permute3_kernel(const void* src, int sdt, void* dst, int ddt, lo
     long long i1 = r % D1;
     const long long i0 = r / D1;
     if (flip1) i1 = D1 - 1 - i1;
-    st_any(dst, i, ddt, sc * ld_any(src, i0 * s0 + i1 * s1 + i2 * s2, sdt));
+    const long long o = i0 * ld_dst + (r % D1) * D2 + i2;
+    st_any(dst, o, ddt, sc * ld_any(src, i0 * s0 + i1 * s1 + i2 * s2, sdt));
   }
 }
 
@@ -431,11 +432,13 @@ extern "C" int dfcsa_softmax_rows_bwd(const float* y, const float* dy, float* dx
 
 extern "C" int dfcsa_permute3(const void* src, int src_dtype, void* dst, int dst_dtype,
                               int64_t D0, int64_t D1, int64_t D2, int64_t s0, int64_t s1, int64_t s2,
-                              int flip1, const float* scale, void* stream) {
+                              int flip1, const float* scale, int64_t ld_dst, void* stream) {
   const long long total = D0 * D1 * D2;
   DFCSA_CHECK_ARG(total > 0, "dfcsa_permute3: empty");
+  if (ld_dst <= 0) ld_dst = D1 * D2;
+  DFCSA_CHECK_ARG(ld_dst >= D1 * D2, "dfcsa_permute3: ld_dst smaller than a destination row");
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 16));
-  permute3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_dtype, dst, dst_dtype, D0, D1, D2, s0, s1, s2, flip1, scale);
+  permute3_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, src_dtype, dst, dst_dtype, D0, D1, D2, s0, s1, s2, flip1, scale, ld_dst);
   DFCSA_LAUNCH_CHECK("permute3_kernel");
   return DFCSA_OK;
 }

@@ -5,7 +5,8 @@
 // The reduction runs over pixels, which are the *rows* of the NHWC tensors, so both operands are MN-major:
 // a TMA box of (64 channels x <=64 pixels) lands as <=64 swizzled 128-byte rows (row = pixel = UMMA K index,
 // 64 contiguous channels = UMMA M/N index).  The 3x3 taps shift the x box by (dh, dw); TMA zero-fills the halo.
-// One CTA per (tap, 128-wide n tile, c tile, pixel split); fp32 partials leave through atomics.
+// One CTA per (tap, n tile, c tile, pixel split); fp32 partials leave through atomics.  The n tile is 256 wide (two
+// M=128 accumulators that share every x box: 128 FLOP per byte staged from L2 instead of 85) when N >= 256, else 128.
 //   warps 0-3: epilogue (TMEM -> atomicAdd),  warp 4: TMA producer,  warp 5: TMEM alloc + MMA issuer
 #include "common.cuh"
 #include <algorithm>
@@ -14,14 +15,14 @@
 namespace dfcsa {
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kBoxBytes = 64 * 128;          // one (64 ch x 64 px) box
-constexpr int kABytes = 2 * kBoxBytes;       // 128 n
 constexpr int kBMaxBytes = 4 * kBoxBytes;    // up to 256 c
-constexpr int kStageBytes = kABytes + kBMaxBytes;
 
 struct WgradTcArgs {
   int taps, n_tiles, c_tiles, splits;
+  int block_n;             // 128 or 256 (two accumulators)
+  int stages, a_bytes, stage_bytes;
   int block_c;             // multiple of 64, <= 256
   int N, C;
   int tiles_w, tiles_h, tiles_b, w_t, h_t;   // pixel-block geometry
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ WgradTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -55,23 +56,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const int nt = id % a.n_tiles;   id /= a.n_tiles;
   const int ct = id % a.c_tiles;   id /= a.c_tiles;
   const int split = id;
-  const int n0 = nt * 128;
+  const int n0 = nt * a.block_n;
   const int c0 = ct * a.block_c;
+  const int kStages = a.stages, kStageBytes = a.stage_bytes, kABytes = a.a_bytes;
   const long long pb_beg = split * a.blocks_per_split;
   const long long pb_end = min(a.pix_blocks, pb_beg + a.blocks_per_split);
-  const int n_boxes_a = (a.N - n0 > 64) ? 2 : 1;
+  const int n_boxes_a = min((a.N - n0 + 63) / 64, a.block_n / 64);
+  const int n_halves = (n_boxes_a + 1) / 2;
   const int n_boxes_b = min(a.block_c, a.C - c0) / 64;
 
   {
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* p = reinterpret_cast<uint4*>(smem);
-    for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += blockDim.x) p[i] = z;
+    for (int i = threadIdx.x; i < a.stages * a.stage_bytes / 16; i += blockDim.x) p[i] = z;
     fence_proxy_async();
   }
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_dy);
     tma_prefetch_desc(&map_x);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
@@ -122,11 +125,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
         const uint32_t b_addr = a_addr + kABytes;
+        for (int h = 0; h < n_halves; ++h) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {   // 16 pixels (rows) per instruction = 2 KiB
-          const uint64_t da = umma_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
-          const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
-          umma_f16(tmem_base, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
+          for (int k = 0; k < 4; ++k) {   // 16 pixels (rows) per instruction = 2 KiB
+            const uint64_t da = umma_smem_desc(a_addr + h * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+            const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
+            umma_f16(tmem_base + h * 256, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
+          }
         }
         umma_commit(&empty_bar[stage]);
       }
@@ -141,18 +146,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (pb_end > pb_beg) {
       mbar_wait(&done_bar, 0);
       tc_fence_after();
-      const int n = n0 + warp * 32 + lane;
       const float alpha = a.alpha ? __ldg(a.alpha) : 1.f;
       const int ccols = min(a.block_c, a.C - c0);
-      for (int ch = 0; ch * 32 < ccols; ++ch) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + ch * 32 + (static_cast<uint32_t>(warp * 32) << 16), raw);
-        tmem_ld_wait();
-        if (n < a.N) {
-          float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap) * a.C + c0 + ch * 32;
+      for (int h = 0; h < n_halves; ++h) {
+        const int n = n0 + h * 128 + warp * 32 + lane;
+        for (int ch = 0; ch * 32 < ccols; ++ch) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + h * 256 + ch * 32 + (static_cast<uint32_t>(warp * 32) << 16), raw);
+          tmem_ld_wait();
+          if (n < a.N) {
+            float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap) * a.C + c0 + ch * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (ch * 32 + i < ccols) atomicAdd(dst + i, alpha * __uint_as_float(raw[i]));
+            for (int i = 0; i < 32; ++i)
+              if (ch * 32 + i < ccols) atomicAdd(dst + i, alpha * __uint_as_float(raw[i]));
+          }
         }
       }
     }
@@ -195,7 +202,11 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.N = p->N; a.C = p->C;
   a.x_mode = p->x_tap_mode; a.dy_mode = p->dy_tap_mode;
   a.taps = p->x_tap_mode == DFCSA_TAP_3x3 ? 9 : (p->dy_tap_mode == DFCSA_TAP_2x2S2 ? 4 : 1);
-  a.n_tiles = (p->N + 127) / 128;
+  a.block_n = p->N >= 256 ? 256 : 128;
+  a.n_tiles = (p->N + a.block_n - 1) / a.block_n;
+  a.a_bytes = (a.block_n / 64) * kBoxBytes;
+  a.stage_bytes = a.a_bytes + kBMaxBytes;
+  a.stages = a.block_n == 256 ? 3 : 4;
   if (p->C <= 256) a.block_c = p->C;
   else {
     int best_pad = 1 << 30; a.block_c = 256;
@@ -261,12 +272,12 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.splits = static_cast<int>((a.pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split);
   a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
   a.idesc = umma_idesc_f16(128, a.block_c, umma_fmt(p->dy_dtype), umma_fmt(p->x_dtype), 1, 1);
-  a.tmem_cols = a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256;
+  a.tmem_cols = a.block_n == 256 ? 512 : (a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256);
 
-  const int smem_bytes = kStages * kStageBytes + 1024;
+  const int smem_bytes = a.stages * a.stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(g_attr_once, [smem_bytes] {
-    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  std::call_once(g_attr_once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (4 * kBoxBytes + kBMaxBytes) + 1024);  // == 4 stages of the 128-wide tile
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
   const long long grid = items * a.splits;

@@ -48,10 +48,9 @@ class BlockParams:
         self.Wv, self.bv = att.value_conv.weight, att.value_conv.bias
         self.W3, self.b3, self.bn3 = g[0].weight, g[0].bias, g[1]
         self.W4, self.b4, self.bn4 = fu[0].weight, fu[0].bias, fu[1]
-        if not hasattr(mod.residual_conv, "weight"):
-            raise NotImplementedError("dfcsa: identity residual (in_channels == out_channels) is not on the DFC-SA-Res-Block "
-                                      "path (reference models/unet_dfc_sa_res.py:87-90 always projects in this network)")
-        self.W5 = mod.residual_conv.weight
+        # in_channels == out_channels: the reference uses nn.Identity (models/unet_dfc_sa_res.py:87-90); here the residual
+        # GEMM then multiplies by an identity matrix (never the case in the DFC-SA-Res-Block network itself)
+        self.W5 = getattr(mod.residual_conv, "weight", None)
         self.res_scale = mod.res_scale
         self.Ci, self.C = self.W1.shape[1], self.W1.shape[0]
         self.Cq = self.Wq.shape[0]
@@ -65,18 +64,33 @@ def pack_block_weights(bp, training, need_dx=True):
     Ci, C = bp.Ci, bp.C
     fdt = F16 if bp.tc else F32
     pk = {}
+    W5 = bp.W5.detach() if bp.W5 is not None else torch.eye(C, dtype=F32, device=dev).view(C, C, 1, 1)
     pk["w1"] = _e((C, 9 * Ci), fdt, dev)
     ops.permute3(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
     pk["w25"] = _e((2 * C, Ci), fdt, dev)
     ops.permute3(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1))
-    ops.permute3(bp.W5.detach(), pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
+    ops.permute3(W5, pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
     gdt = F16 if C % 64 == 0 else F32
     pk["w3"] = _e((C, 2 * C), gdt, dev)
     ops.permute3(bp.W3.detach(), pk["w3"], (C, 1, 2 * C), (2 * C, 0, 1))
     pk["w4"] = _e((C, 3 * C), gdt, dev)
     ops.permute3(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1))
+    # q/k/v 1x1 convs on the pooled map as ONE GEMM: rows [Wq ; Wk ; Wv], bias [bq | bk | bv]
+    Cq = bp.Cq
+    nq = 2 * Cq + C
+    pk["wqkv"] = _e((nq, C), gdt, dev)
+    ops.permute3(bp.Wq.detach(), pk["wqkv"][:Cq], (Cq, 1, C), (C, 0, 1))
+    ops.permute3(bp.Wk.detach(), pk["wqkv"][Cq:2 * Cq], (Cq, 1, C), (C, 0, 1))
+    ops.permute3(bp.Wv.detach(), pk["wqkv"][2 * Cq:], (C, 1, C), (C, 0, 1))
+    pk["bqkv"] = torch.cat([bp.bq.detach(), bp.bk.detach(), bp.bv.detach()])
     if training:
         bdt = BF16 if C % 64 == 0 else F32
+        kp = (nq + 63) // 64 * 64 if C % 64 == 0 else nq      # K of the dgrad GEMM, zero-padded to the UMMA K block
+        wdq = _z((C, kp), bdt, dev)                 # [c, (q | k | v | pad)] = [Wq ; Wk ; Wv]^T
+        ops.permute3(bp.Wq.detach(), wdq[:, :Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
+        ops.permute3(bp.Wk.detach(), wdq[:, Cq:2 * Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
+        ops.permute3(bp.Wv.detach(), wdq[:, 2 * Cq:nq], (C, 1, C), (1, 0, C), ld_dst=kp)
+        pk["wdqkv"] = wdq
         wd4 = _e((3 * C, C), bdt, dev)             # [k_in, co] = W4^T
         ops.permute3(bp.W4.detach(), wd4, (3 * C, 1, C), (1, 0, 3 * C))
         wd3 = _e((2 * C, C), bdt, dev)
@@ -86,20 +100,28 @@ def pack_block_weights(bp, training, need_dx=True):
         if need_dx:   # the first block never needs the gradient w.r.t. the image
             xdt = BF16 if bp.tc else F32
             wd = _e((Ci, 11 * C), xdt, dev)            # [ci, (flipped tap, co) | co (W2) | co (res_scale*W5)]
-            tmp = _e((Ci, 9, C), xdt, dev)
-            ops.permute3(bp.W1.detach(), tmp, (Ci, 9, C), (9, 1, Ci * 9), flip1=True)
-            wd[:, :9 * C].copy_(tmp.view(Ci, 9 * C))
-            tmp2 = _e((Ci, C), xdt, dev)
-            ops.permute3(bp.W2.detach(), tmp2, (Ci, 1, C), (1, 0, Ci))
-            wd[:, 9 * C:10 * C].copy_(tmp2)
-            ops.permute3(bp.W5.detach(), tmp2, (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1))
-            wd[:, 10 * C:].copy_(tmp2)
+            ops.permute3(bp.W1.detach(), wd, (Ci, 9, C), (9, 1, Ci * 9), flip1=True, ld_dst=11 * C)
+            ops.permute3(bp.W2.detach(), wd[:, 9 * C:], (Ci, 1, C), (1, 0, Ci), ld_dst=11 * C)
+            ops.permute3(W5, wd[:, 10 * C:], (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1), ld_dst=11 * C)
             pk["wd125"] = wd
     return pk
 
 
 class BlockCtx:
     pass
+
+
+def _pool_side(bp, H, W):
+    """Side of the pooled attention map.  pool_size=None is the full-resolution attention of ablation 3 (reference
+    models/unet_dfc_sa_ablation_attention.py:15-26): attention over all H*W positions, which is exactly the pooled
+    block with pool_size = H (adaptive_avg_pool2d to the input size and bilinear re-sizing to the same size are both
+    the identity), so the same kernels run it."""
+    if bp.P is not None:
+        return bp.P
+    if H != W:
+        raise NotImplementedError("dfcsa: full-resolution attention is implemented for square feature maps (the 224/512/1024 "
+                                  "hot-path shapes)")
+    return H
 
 
 def _bn_affine(bn, conv_bias, s_sum, s_sq, count, training, dev):
@@ -114,49 +136,101 @@ def _bn_affine(bn, conv_bias, s_sum, s_sq, count, training, dev):
     return aff
 
 
-def attention_forward(bp, pooled, B, ctx=None):
-    """q/k/v 1x1 convs, softmax(q k^T), attn v on the pooled map [B, N, C] fp32 (reference :28-34)."""
+_ATTN_SAVE_BYTES = 4 << 30     # keep softmax(q k^T) for backward only below this size; above it backward recomputes it
+_ATTN_CHUNK_BYTES = 12 << 30   # images are processed in chunks so that one [chunk, N, N] fp32 buffer stays below this
+
+
+def _attn_chunk(B, N):
+    return max(1, min(B, _ATTN_CHUNK_BYTES // (N * N * 4)))
+
+
+def _attn_probs(qkv, nb, N, Cq, nq, out):
+    """out[b] = softmax_j(q_i . k_j) for nb images; qkv: [nb*N, nq] fp32 rows (q | k | v)."""
+    S = _e((nb, N, N), F32, qkv.device)
+    ops.sgemm(nb, N, N, Cq, qkv[:, :Cq], (N * nq, nq, 1), qkv[:, Cq:2 * Cq], (N * nq, 1, nq), S, (N * N, N, 1))
+    ops.softmax_rows(S, out)
+
+
+def attention_forward(bp, pk, pooled, B, N, ctx=None):
+    """q/k/v 1x1 convs (ONE tensor-core GEMM over [Wq ; Wk ; Wv]), softmax(q k^T), attn v on the pooled map
+    [B*N, C] (reference :28-34).  pooled is fp32; the GEMM reads an fp16 copy."""
     dev = pooled.device
-    C, Cq, N = bp.C, bp.Cq, bp.P * bp.P
+    C, Cq = bp.C, bp.Cq
     BN = B * N
-    q, k, v = _e((BN, Cq), F32, dev), _e((BN, Cq), F32, dev), _e((BN, C), F32, dev)
-    ops.sgemm(1, BN, Cq, C, pooled, (0, C, 1), bp.Wq.detach(), (0, 1, C), q, (0, Cq, 1), bias_n=bp.bq.detach())
-    ops.sgemm(1, BN, Cq, C, pooled, (0, C, 1), bp.Wk.detach(), (0, 1, C), k, (0, Cq, 1), bias_n=bp.bk.detach())
-    ops.sgemm(1, BN, C, C, pooled, (0, C, 1), bp.Wv.detach(), (0, 1, C), v, (0, C, 1), bias_n=bp.bv.detach())
-    S = _e((B, N, N), F32, dev)
-    ops.sgemm(B, N, N, Cq, q, (N * Cq, Cq, 1), k, (N * Cq, 1, Cq), S, (N * N, N, 1))       # S[i,j] = q_i . k_j
-    attn = _e((B, N, N), F32, dev)
-    ops.softmax_rows(S, attn)
+    nq = 2 * Cq + C
+    tc = C % 64 == 0
+    p16 = pooled
+    if tc:
+        p16 = _e((BN, C), F16, dev)
+        ops.cast2d(pooled, p16)
+    qkv = _e((BN, nq), F32, dev)
+    segs = [(p16, TAP_1x1)]
+    ops.conv_gemm(1, 1, BN, segs, pk["wqkv"], nq, qkv, bias=pk["bqkv"], backend=_backend(segs, pk["wqkv"], nq, qkv))
+    # softmax(q k^T) v, a few images at a time when [N, N] is large (full-resolution attention: N = H*W)
+    keep_attn = ctx is not None and B * N * N * 4 <= _ATTN_SAVE_BYTES
+    attn = _e((B, N, N), F32, dev) if keep_attn else None
     o = _e((B, N, C), F32, dev)
-    ops.sgemm(B, N, C, N, attn, (N * N, N, 1), v, (N * C, C, 1), o, (N * C, C, 1))         # o[i,c] = sum_j attn[i,j] v[j,c]
+    ch = _attn_chunk(B, N)
+    for b0 in range(0, B, ch):
+        nb = min(ch, B - b0)
+        A = attn[b0:b0 + nb] if keep_attn else _e((nb, N, N), F32, dev)
+        _attn_probs(qkv[b0 * N:(b0 + nb) * N], nb, N, Cq, nq, A)
+        v = qkv[b0 * N:(b0 + nb) * N, 2 * Cq:]
+        ops.sgemm(nb, N, C, N, A, (N * N, N, 1), v, (N * nq, nq, 1), o[b0:b0 + nb], (N * C, C, 1))   # o[i,c] = sum_j attn[i,j] v[j,c]
     if ctx is not None:
-        ctx.q, ctx.k, ctx.v, ctx.attn, ctx.pooled = q, k, v, attn, pooled
+        ctx.qkv, ctx.attn = qkv, attn
+        ctx.pooled_w = pooled
+        if tc:
+            ctx.pooled_w = _e((BN, C), BF16, dev)      # weight-gradient operand
+            ops.cast2d(pooled, ctx.pooled_w)
     return o
 
 
-def attention_backward(bp, ctx, d_o, B, grads):
-    """Backward of attention_forward; returns dpooled [B, N, C] and fills the q/k/v weight and bias gradients."""
+def attention_backward(bp, pk, ctx, d_o, B, N, grads):
+    """Backward of attention_forward; returns dpooled [B*N, C] fp32 and fills the q/k/v weight and bias gradients."""
     dev = d_o.device
-    C, Cq, N = bp.C, bp.Cq, bp.P * bp.P
+    C, Cq = bp.C, bp.Cq
     BN = B * N
-    q, k, v, attn, pooled = ctx.q, ctx.k, ctx.v, ctx.attn, ctx.pooled
-    dv = _e((BN, C), F32, dev)
-    ops.sgemm(B, N, C, N, attn, (N * N, 1, N), d_o, (N * C, C, 1), dv, (N * C, C, 1))      # dv[j,c] = sum_i attn[i,j] do[i,c]
-    dattn = _e((B, N, N), F32, dev)
-    ops.sgemm(B, N, N, C, d_o, (N * C, C, 1), v, (N * C, 1, C), dattn, (N * N, N, 1))      # dattn[i,j] = sum_c do[i,c] v[j,c]
-    dS = _e((B, N, N), F32, dev)
-    ops.softmax_rows_bwd(attn, dattn, dS)
-    dq, dk = _e((BN, Cq), F32, dev), _e((BN, Cq), F32, dev)
-    ops.sgemm(B, N, Cq, N, dS, (N * N, N, 1), k, (N * Cq, Cq, 1), dq, (N * Cq, Cq, 1))     # dq[i,c] = sum_j dS[i,j] k[j,c]
-    ops.sgemm(B, N, Cq, N, dS, (N * N, 1, N), q, (N * Cq, Cq, 1), dk, (N * Cq, Cq, 1))     # dk[j,c] = sum_i dS[i,j] q[i,c]
-    dp = _e((BN, C), F32, dev)
-    ops.sgemm(1, BN, C, Cq, dq, (0, Cq, 1), bp.Wq.detach(), (0, C, 1), dp, (0, C, 1))
-    ops.sgemm(1, BN, C, Cq, dk, (0, Cq, 1), bp.Wk.detach(), (0, C, 1), dp, (0, C, 1), beta=1.0)
-    ops.sgemm(1, BN, C, C, dv, (0, C, 1), bp.Wv.detach(), (0, C, 1), dp, (0, C, 1), beta=1.0)
-    for W, b, d, n_out in ((bp.Wq, bp.bq, dq, Cq), (bp.Wk, bp.bk, dk, Cq), (bp.Wv, bp.bv, dv, C)):
-        gW = grads[W]
-        ops.sgemm(1, n_out, C, BN, d, (0, 1, n_out), pooled, (0, C, 1), gW, (0, C, 1))     # dW[o,c] = sum_m d[m,o] p[m,c]
+    nq = 2 * Cq + C
+    qkv, attn = ctx.qkv, ctx.attn
+    dqkv = _e((BN, nq), F32, dev)
+    ch = _attn_chunk(B, N)
+    for b0 in range(0, B, ch):
+        nb = min(ch, B - b0)
+        rows = slice(b0 * N, (b0 + nb) * N)
+        q, k, v = qkv[rows, :Cq], qkv[rows, Cq:2 * Cq], qkv[rows, 2 * Cq:]
+        dq, dk, dv = dqkv[rows, :Cq], dqkv[rows, Cq:2 * Cq], dqkv[rows, 2 * Cq:]
+        if attn is not None:
+            A = attn[b0:b0 + nb]
+        else:                                  # not saved (too large): recompute the probabilities
+            A = _e((nb, N, N), F32, dev)
+            _attn_probs(qkv[rows], nb, N, Cq, nq, A)
+        do = d_o[rows]
+        ops.sgemm(nb, N, C, N, A, (N * N, 1, N), do, (N * C, C, 1), dv, (N * nq, nq, 1))       # dv[j,c] = sum_i attn[i,j] do[i,c]
+        dattn = _e((nb, N, N), F32, dev)
+        ops.sgemm(nb, N, N, C, do, (N * C, C, 1), v, (N * nq, 1, nq), dattn, (N * N, N, 1))     # dattn[i,j] = sum_c do[i,c] v[j,c]
+        dS = _e((nb, N, N), F32, dev)
+        ops.softmax_rows_bwd(A, dattn, dS)
+        del dattn
+        ops.sgemm(nb, N, Cq, N, dS, (N * N, N, 1), k, (N * nq, nq, 1), dq, (N * nq, nq, 1))    # dq[i,c] = sum_j dS[i,j] k[j,c]
+        ops.sgemm(nb, N, Cq, N, dS, (N * N, 1, N), q, (N * nq, nq, 1), dk, (N * nq, nq, 1))    # dk[j,c] = sum_i dS[i,j] q[i,c]
+        del dS, A
+    dq, dk, dv = dqkv[:, :Cq], dqkv[:, Cq:2 * Cq], dqkv[:, 2 * Cq:]
+    for b, d in ((bp.bq, dq), (bp.bk, dk), (bp.bv, dv)):
         ops.colsum(d, grads[b])
+    # dpooled = dqkv . [Wq ; Wk ; Wv]  and the three weight gradients, on the tensor cores when C allows
+    wdq = pk["wdqkv"]
+    kp = wdq.shape[1]
+    dp = _e((BN, C), F32, dev)
+    if wdq.dtype == BF16:
+        d16 = _z((BN, kp), BF16, dev) if kp != nq else _e((BN, kp), BF16, dev)
+        ops.cast2d(dqkv, d16[:, :nq])
+    else:
+        d16 = dqkv
+    segs = [(d16, TAP_1x1)]
+    ops.conv_gemm(1, 1, BN, segs, wdq, C, dp, backend=_backend(segs, wdq, C, dp))
+    for W, lo, hi in ((bp.Wq, 0, Cq), (bp.Wk, Cq, 2 * Cq), (bp.Wv, 2 * Cq, nq)):
+        _wgrad(1, 1, BN, ctx.pooled_w, TAP_1x1, d16[:, lo:hi], TAP_1x1, grads[W].view(hi - lo, C))
     return dp
 
 
@@ -164,7 +238,7 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=Tr
     """One DynamicFusionConvAttnBlock.  x: [M, Ci] (fp16, or fp32 for the image); y / yp: fp16 output views (full
     resolution / 2x2 max-pooled); yb / ypb: their bf16 shadows.  Returns the context the backward needs."""
     dev = x.device
-    C, Ci, P = bp.C, bp.Ci, bp.P
+    C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
     M = B * H * W
     ctx = BlockCtx() if (training and save) else None
     st = _z((10 * C,), F64, dev) if training else None
@@ -181,7 +255,7 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=Tr
     tmp = _e((B, H, P, C), F32, dev)
     pooled = _e((B * P * P, C), F32, dev)
     ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled)
-    o = attention_forward(bp, pooled, B, ctx)
+    o = attention_forward(bp, pk, pooled, B, P * P, ctx)
     z = _e((M, 3 * C), F16, dev)
     zb = _e((M, 3 * C), BF16, dev) if ctx is not None else None
     ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z, zb)
@@ -217,7 +291,7 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     grads: dict parameter -> fp32 gradient tensor (zero-initialised where the kernels accumulate)."""
     dev = dskip.device if dskip is not None else dyp.device
     B, H, W = ctx.B, ctx.H, ctx.W
-    C, Ci, P = bp.C, bp.Ci, bp.P
+    C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
     M = B * H * W
     red = _z((8 * C + 2,), F64, dev)
     red1, red2, red3, red4 = red[0:2 * C], red[2 * C:4 * C], red[4 * C:6 * C], red[6 * C:8 * C]
@@ -254,7 +328,7 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     d_o = _e((B * P * P, C), F32, dev)
     ops.branch_bwd_reduce1(dz, ctx.L0, ctx.G0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], bn3[0], bn3[1], ctx.o, P,
                            bp.gamma.detach(), red1, dgam, tmp, d_o)
-    dpooled = attention_backward(bp, ctx, d_o, B, grads)
+    dpooled = attention_backward(bp, pk, ctx, d_o, B, P * P, grads)
     ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
     dL0, dA0 = dF0, dG0     # both dead after the GEMMs above: reuse their storage
     ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
@@ -270,7 +344,8 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     _wgrad(B, H, W, xw, TAP_3x3, dL0, TAP_1x1, dW1p)
     ops.permute3(dW1p, grads[bp.W1], (C, Ci, 9), (9 * Ci, 1, Ci))
     _wgrad(B, H, W, xw, TAP_1x1, dA0, TAP_1x1, grads[bp.W2].view(C, Ci))
-    _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1))
+    if bp.W5 is not None:
+        _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1))
     # conv biases in front of a train-mode BatchNorm have exactly zero gradient: grads[...] stay zero
 
 

@@ -1,7 +1,7 @@
 """ModelFactory mirror (reference models/model_factory.py:14-186): the name -> class boundary of the hot path."""
 import torch
 
-from .modules import UNetDFCSARes
+from .modules import UNet_FullResAttention, UNetDFCSARes
 
 # names the reference factory knows (models/model_factory.py:94-183) that are outside the B200 hot path
 _OUT_OF_SCOPE = {
@@ -47,8 +47,7 @@ class ModelFactory:
             return UNetDFCSARes(in_channels=in_channels, out_channels=out_channels, features=features,
                                 pool_size=pool_size, ablation_on_qk_channels=qk)
         if name == "UNet_FullResAttention":                  # reference :174-175 (ablation 3)
-            raise NotImplementedError("dfcsa: UNet_FullResAttention needs the flash-style full-resolution attention kernel, "
-                                      "which is scheduled after the pooled DFC-SA path (DESIGN.md, scope row a4)")
+            return UNet_FullResAttention(in_channels=in_channels, out_channels=out_channels, features=features)
         if name in _OUT_OF_SCOPE:
             raise NotImplementedError(f"dfcsa: model '{name}' is outside the DFC-SA-Res-Block hot path this library accelerates")
         raise ValueError(f"不支援的模型類型: {name}")   # reference models/model_factory.py:186

@@ -27,6 +27,22 @@ class LightSelfAttention(nn.Module):
         raise RuntimeError("dfcsa.LightSelfAttention is fused into DynamicFusionConvAttnBlock's kernels; call the block")
 
 
+class FullResolutionAttention(nn.Module):
+    """reference models/unet_dfc_sa_ablation_attention.py:7-26 (ablation 3): same parameters as LightSelfAttention with
+    channels // 8 query/key channels and no pooling; pool_size=None tells the engine to attend over all H*W positions."""
+
+    def __init__(self, channels, **kwargs):
+        super().__init__()
+        self.pool_size = None
+        self.query_conv = nn.Conv2d(channels, channels // 8, kernel_size=1)
+        self.key_conv = nn.Conv2d(channels, channels // 8, kernel_size=1)
+        self.value_conv = nn.Conv2d(channels, channels, kernel_size=1)
+        self.gamma = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        raise RuntimeError("dfcsa.FullResolutionAttention is fused into FullResAttnDFCBlock's kernels; call the block")
+
+
 class _BlockFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, block, need_grad, *params):
@@ -75,7 +91,8 @@ class _BlockFunction(torch.autograd.Function):
 class DynamicFusionConvAttnBlock(nn.Module):
     """reference models/unet_dfc_sa_res.py:41-116."""
 
-    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, pool_size=8, ablation_on_qk_channels=8):
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, pool_size=8, ablation_on_qk_channels=8,
+                 full_res_attention=False):
         super().__init__()
         if (kernel_size, stride, padding) != (3, 1, 1):
             raise NotImplementedError("dfcsa: the DFC-SA block kernels implement the 3x3 / stride 1 / pad 1 conv branch the "
@@ -85,6 +102,7 @@ class DynamicFusionConvAttnBlock(nn.Module):
             nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
         self.attn_branch = nn.Sequential(
             nn.Conv2d(in_channels, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True),
+            FullResolutionAttention(out_channels) if full_res_attention else
             LightSelfAttention(out_channels, pool_size=pool_size, ablation_on_qk_channels=ablation_on_qk_channels))
         self.gate = nn.Sequential(nn.Conv2d(out_channels * 2, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels), nn.Sigmoid())
         self.fusion_conv = nn.Sequential(nn.Conv2d(out_channels * 3, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels),
@@ -121,9 +139,11 @@ class _NetFunction(torch.autograd.Function):
 class UNetDFCSA(nn.Module):
     """reference models/unet_dfc_sa_res.py:118-204."""
 
-    def __init__(self, in_channels=3, out_channels=1, features=[64, 128, 256, 512], pool_size=8, ablation_on_qk_channels=8):
+    def __init__(self, in_channels=3, out_channels=1, features=[64, 128, 256, 512], pool_size=8, ablation_on_qk_channels=8,
+                 full_res_attention=False):
         super().__init__()
-        kw = dict(kernel_size=3, stride=1, padding=1, pool_size=pool_size, ablation_on_qk_channels=ablation_on_qk_channels)
+        kw = dict(kernel_size=3, stride=1, padding=1, pool_size=pool_size, ablation_on_qk_channels=ablation_on_qk_channels,
+                  full_res_attention=full_res_attention)
         self.down1 = DynamicFusionConvAttnBlock(in_channels, features[0], **kw)
         self.pool1 = nn.MaxPool2d(kernel_size=2, stride=2)
         self.down2 = DynamicFusionConvAttnBlock(features[0], features[1], **kw)
@@ -151,3 +171,18 @@ class UNetDFCSA(nn.Module):
 
 class UNetDFCSARes(UNetDFCSA):
     """reference models/unet_dfc_sa_res.py:207-220 (adds nothing to UNetDFCSA)."""
+
+
+class FullResAttnDFCBlock(DynamicFusionConvAttnBlock):
+    """reference models/unet_dfc_sa_ablation_attention.py:29-93: the DFC-SA block with full-resolution attention."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, **kwargs):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, full_res_attention=True)
+
+
+class UNet_FullResAttention(UNetDFCSA):
+    """reference models/unet_dfc_sa_ablation_attention.py:96-98 over AblationUNetBase
+    (models/unet_dfc_sa_ablation_branches.py:104-164): same wiring and the same state_dict keys as UNetDFCSARes."""
+
+    def __init__(self, in_channels, out_channels, features, **kwargs):
+        super().__init__(in_channels, out_channels, features, full_res_attention=True)

@@ -74,12 +74,12 @@ def wgrad_tc_eligible(x, dy):
             and x.stride(0) % 8 == 0 and dy.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0 and dy.data_ptr() % 16 == 0)
 
 
-def permute3(src, dst, D, s, flip1=False, scale=None):
-    """dst[(i0*D1+i1)*D2+i2] = scale*src[i0*s0 + i1'*s1 + i2*s2]   (dfcsa_permute3)."""
+def permute3(src, dst, D, s, flip1=False, scale=None, ld_dst=0):
+    """dst[i0*ld_dst + i1*D2 + i2] = scale*src[i0*s0 + i1'*s1 + i2*s2]   (dfcsa_permute3); ld_dst=0: dense."""
     L.call("dfcsa_permute3", L.ptr(src), L.dt(src), L.ptr(dst), L.dt(dst),
                                    C.c_int64(D[0]), C.c_int64(D[1]), C.c_int64(D[2]),
                                    C.c_int64(s[0]), C.c_int64(s[1]), C.c_int64(s[2]),
-                                   1 if flip1 else 0, L.ptr(scale), L.stream())
+                                   1 if flip1 else 0, L.ptr(scale), C.c_int64(ld_dst), L.stream())
 
 
 def sgemm(batch, M, N, K, A, a_str, Bm, b_str, Cm, c_str, alpha=1.0, beta=0.0, bias_n=None, bias_m=None):

@@ -36,13 +36,18 @@ def grad_rel_l2(model, ref_grads):
     return (num / max(den, 1e-300)) ** 0.5
 
 
-def forward_backward_parity(features=(64, 128, 256, 512), pool_size=4, qk=8, B=2, H=64, W=64, gamma=0.5, seed=0):
-    """Returns dict(logit_maxabs, grad_rel_l2, loss, loss_ref) of dfcsa vs the oracle on identical weights/inputs."""
+def forward_backward_parity(features=(64, 128, 256, 512), pool_size=4, qk=8, B=2, H=64, W=64, gamma=0.5, seed=0,
+                            full_res_attention=False):
+    """Returns dict(logit_maxabs, grad_rel_l2, loss, loss_ref) of dfcsa vs the oracle on identical weights/inputs.
+    full_res_attention: the ablation-3 network (UNet_FullResAttention) instead of DFC-SA-Res-Block."""
     O = _oracle()
     from .metrics import calculate_metrics
-    from .modules import UNetDFCSARes
+    from .modules import UNet_FullResAttention, UNetDFCSARes
     torch.manual_seed(seed)
-    model = UNetDFCSARes(3, 1, list(features), pool_size=pool_size, ablation_on_qk_channels=qk)
+    if full_res_attention:
+        model = UNet_FullResAttention(3, 1, list(features))
+    else:
+        model = UNetDFCSARes(3, 1, list(features), pool_size=pool_size, ablation_on_qk_channels=qk)
     set_gamma(model, gamma)
     sd = oracle_state(model)
     img, mask = O.synthetic_batch(B, H, W, seed=1)
@@ -50,7 +55,7 @@ def forward_backward_parity(features=(64, 128, 256, 512), pool_size=4, qk=8, B=2
     names = O.param_names(sd)
     for k in names:
         sd[k].requires_grad_(True)
-    ref_logits = O.unet_forward(img, sd, pool_size, training=True)
+    ref_logits = O.unet_forward(img, sd, pool_size, training=True, full_res_attention=full_res_attention)
     ref_m = O.calculate_metrics(torch.sigmoid(ref_logits), mask, "bce_dice", {})
     ref_grads = dict(zip(names, torch.autograd.grad(ref_m["loss"], [sd[k] for k in names])))
     # dfcsa (CUDA)

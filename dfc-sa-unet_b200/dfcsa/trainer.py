@@ -17,6 +17,7 @@ import torch
 import torch.distributed as dist
 
 from . import engine, ops
+from .ddp import BucketReducer, bucket_modules, bucket_ranges
 from .metrics import bce_dice_with_logits, calculate_metrics
 from .optim import FusedSGD
 
@@ -34,9 +35,7 @@ class StepResult:
 
 def reduce_buckets(net):
     """Parameter buckets in reverse execution order: each is reduced as soon as its backward is done."""
-    order = [[net.final_conv, net.up_conv1, net.up1], [net.up_conv2, net.up2], [net.up_conv3, net.up3], [net.up_conv4],
-             [net.up4], [net.bottleneck], [net.down4], [net.down3], [net.down2, net.down1]]
-    return [[p for m in mods for p in m.parameters()] for mods in order]
+    return [[p for m in mods for p in m.parameters()] for mods in bucket_modules(net)]
 
 
 class Trainer:
@@ -73,16 +72,7 @@ class Trainer:
         # data parallel
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
-        self._comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
-        self._buckets = None
-        if self.world > 1:
-            self._buckets = []
-            for ps in reduce_buckets(self.model):
-                ptrs = sorted((self.optimizer.grads[p].data_ptr(), self.optimizer.grads[p].numel()) for p in ps)
-                lo = min(a for a, _ in ptrs)
-                hi = max(a + 4 * n for a, n in ptrs)
-                base = self.optimizer.flat_grad.data_ptr()
-                self._buckets.append(self.optimizer.flat_grad[(lo - base) // 4:(hi - base) // 4])
+        self._reducer = BucketReducer(self.optimizer.flat_grad, bucket_ranges(self.model)) if self.world > 1 else None
 
     # ------------------------------------------------------------------------------------------------------------
     def train_step(self, images, masks):
@@ -107,23 +97,10 @@ class Trainer:
             engine.net_backward(net, ctx, dlogits, opt.grads)
             opt.step()
         else:
-            hooks = self._make_bucket_hooks()
-            engine.net_backward(net, ctx, dlogits, opt.grads, after_stage=hooks)
-            torch.cuda.current_stream().wait_stream(self._comm_stream)
+            engine.net_backward(net, ctx, dlogits, opt.grads, after_stage=self._reducer.reduce)
+            self._reducer.finish()
             opt.step(grad_scale=1.0 / self.world)
         return StepResult(stats)
-
-    def _make_bucket_hooks(self):
-        """after_stage(k): stage k of net_backward (k-th entry of reduce_buckets) has been enqueued -> all-reduce it."""
-        cs = self._comm_stream
-
-        def hook(k):
-            ev = torch.cuda.Event()
-            ev.record()
-            cs.wait_event(ev)
-            with torch.cuda.stream(cs):
-                dist.all_reduce(self._buckets[k])
-        return hook
 
     # ------------------------------------------------------------------------------------------------------------
     def train_epoch(self, epoch):

@@ -104,12 +104,13 @@ typedef struct {
 
 int dfcsa_conv_wgrad(const dfcsa_wgrad_params_t* p, int backend, void* stream);
 
-/* dst[(i0*D1 + i1)*D2 + i2] = scale * src[i0*s0 + i1'*s1 + i2*s2], i1' = flip ? D1-1-i1 : i1.
+/* dst[i0*ld_dst + i1*D2 + i2] = scale * src[i0*s0 + i1'*s1 + i2*s2], i1' = flip ? D1-1-i1 : i1
+ * (ld_dst = 0 means a dense destination, ld_dst = D1*D2).
  * Re-lays fp32 master weights ([Co,Ci,kh,kw], ConvT [Ci,Co,2,2]) into the packed K-major GEMM operands
  * (forward: [Co,(tap,ci)]; dgrad: [Ci,(flipped tap,co)]) and packed weight gradients back. */
 int dfcsa_permute3(const void* src, int src_dtype, void* dst, int dst_dtype,
                    int64_t D0, int64_t D1, int64_t D2, int64_t s0, int64_t s1, int64_t s2,
-                   int flip1, const float* scale, void* stream);
+                   int flip1, const float* scale, int64_t ld_dst, void* stream);
 
 /* Strided batched fp32 GEMM  C[b] = alpha * A[b] * B[b] + beta * C[b]  with arbitrary element strides
  * (transposes are strides).  Used for the pooled attention products, reference

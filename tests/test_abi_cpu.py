@@ -74,3 +74,17 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError, match="CUDA"):
         calculate_metrics(torch.rand(1, 1, 8, 8), torch.zeros(1, 1, 8, 8), "bce_dice", {})
+
+
+def test_full_res_attention_model_has_the_reference_state_dict_layout():
+    """UNet_FullResAttention shares the key list / shapes of DFC-SA-Res-Block and is reachable
+    through the factory name the reference uses (models/model_factory.py:174)."""
+    import numpy as np
+    from dfcsa.model_factory import ModelFactory
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fullres.npz"))
+    want = {k[2:]: z[k].shape for k in z.files if k.startswith("w:")}
+    m = ModelFactory.get_model({"model": {"name": "UNet_FullResAttention", "features": [8, 8, 16, 16]}})
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(want.keys())
+    assert all(tuple(sd[k].shape) == tuple(want[k]) for k in sd)
+    assert m.down1.attn_branch[3].pool_size is None

@@ -1,0 +1,93 @@
+"""Host-side data-parallel logic on CPU: gradient buckets partition the flat gradient buffer in backward-completion
+order, and a world_size-2 `gloo` run of the bucketed all-reduce reproduces the gradient of the global batch
+(per-replica BatchNorm statistics, as in the GPU path).  The oracle is used here only as the per-rank gradient
+producer / checker."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _small_net():
+    from dfcsa.modules import UNetDFCSARes
+    torch.manual_seed(0)
+    return UNetDFCSARes(3, 1, [4, 8, 16, 32], pool_size=4, ablation_on_qk_channels=4)
+
+
+def test_buckets_partition_the_flat_gradient_buffer_in_backward_order():
+    from dfcsa.ddp import bucket_modules, bucket_ranges
+    net = _small_net()
+    ranges = bucket_ranges(net)            # asserts: every parameter in exactly one bucket
+    assert len(ranges) == 9 and all(len(r) == 1 for r in ranges)
+    total = sum(p.numel() for p in net.parameters())
+    assert sum(hi - lo for runs in ranges for lo, hi in runs) == total
+    # reverse execution order: the first bucket ends at the end of the buffer (final_conv), the last one starts at 0
+    assert ranges[0][0][1] == total and ranges[-1][0][0] == 0
+    assert [type(m).__name__ for m in bucket_modules(net)[4]] == ["ConvTranspose2d"]      # {up4} precedes the bottleneck
+    # the bottleneck bucket is the largest one (42 % of the bytes at full width)
+    sizes = [sum(hi - lo for lo, hi in runs) for runs in ranges]
+    assert sizes.index(max(sizes)) == 5
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard_grads(sd, names, img, mask):
+    from oracle import dfcsa_oracle as O
+    ps = {k: (v.clone().requires_grad_(True) if k in names else v.clone()) for k, v in sd.items()}
+    logits = O.unet_forward(img, ps, 4, training=True)
+    loss = O.calculate_metrics(torch.sigmoid(logits), mask, "bce_dice", {})["loss"]
+    return torch.autograd.grad(loss, [ps[k] for k in names])
+
+
+def _worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "dfc-sa-unet_b200")]
+    from dfcsa.ddp import BucketReducer, bucket_ranges
+    from oracle import dfcsa_oracle as O
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    net = _small_net()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    names = [n for n, _ in net.named_parameters()]
+    img, mask = O.synthetic_batch(2 * world, 32, 32, seed=5)
+    g = _shard_grads(sd, names, img[2 * rank:2 * rank + 2], mask[2 * rank:2 * rank + 2])
+    flat = torch.cat([t.reshape(-1) for t in g]).contiguous()
+    red = BucketReducer(flat, bucket_ranges(net))
+    calls = []
+    for k in range(len(red.ranges)):        # the order net_backward's after_stage(k) fires in
+        red.reduce(k)
+        calls.append(k)
+    red.finish()
+    flat *= 1.0 / world                     # what the fused SGD kernel's grad_scale does
+    torch.save({"flat": flat, "calls": calls}, os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_bucketed_allreduce_matches_mean_of_shard_gradients(tmp_path):
+    from oracle import dfcsa_oracle as O
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
+    assert torch.equal(outs[0]["flat"], outs[1]["flat"])            # every rank ends with the same gradient
+    net = _small_net()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    names = [n for n, _ in net.named_parameters()]
+    img, mask = O.synthetic_batch(2 * world, 32, 32, seed=5)
+    ref = None
+    for r in range(world):
+        g = torch.cat([t.reshape(-1) for t in _shard_grads(sd, names, img[2 * r:2 * r + 2], mask[2 * r:2 * r + 2])])
+        ref = g if ref is None else ref + g
+    ref /= world
+    assert torch.allclose(outs[0]["flat"], ref, rtol=1e-5, atol=1e-7)

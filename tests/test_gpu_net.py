@@ -116,6 +116,32 @@ def test_full_width_net_matches_oracle(cuda, hw, B, P, gamma):
     assert abs(r["loss"] - r["loss_ref"]) <= 2e-3, r
 
 
+def test_full_resolution_attention_matches_reference_golden(cuda):
+    """ablation 3 (UNet_FullResAttention): logits produced by the unmodified reference (tests/golden/fullres.npz)."""
+    from dfcsa.model_factory import ModelFactory
+    d = _load("fullres.npz")
+    model = ModelFactory.get_model({"model": {"name": "UNet_FullResAttention", "in_channels": 3, "out_channels": 1,
+                                              "features": [8, 8, 16, 16]}})   # incl. identity-residual blocks
+    model.load_state_dict({k[2:]: v for k, v in d.items() if k.startswith("w:")})
+    model = model.cuda().train()
+    logits = model(d["image"].cuda())
+    assert (logits.cpu() - d["logits"]).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("gamma", [0.0, 0.5])
+@pytest.mark.parametrize("hw,B", [(64, 2), (96, 1)])
+def test_full_resolution_attention_net_matches_oracle(cuda, hw, B, gamma):
+    """ablation 3 at full width: attention over all H*W positions of every level (N = 9216 at level 1 for 96x96, the
+    largest size the CPU oracle can materialise).  Smaller inputs leave < 32 samples per channel in
+    the bottleneck BatchNorms and are ill-conditioned for any reduced-precision path."""
+    from dfcsa.selftest import forward_backward_parity
+    r = forward_backward_parity(B=B, H=hw, W=hw, gamma=gamma, full_res_attention=True)
+    print(r)
+    assert r["logit_maxabs"] <= 2e-2, r
+    assert r["grad_rel_l2"] <= 3e-2, r
+    assert abs(r["loss"] - r["loss_ref"]) <= 2e-3, r
+
+
 def test_state_dict_layout_and_roundtrip(cuda):
     from oracle import dfcsa_oracle as O
     from dfcsa.modules import UNetDFCSARes

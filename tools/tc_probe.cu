@@ -107,6 +107,103 @@ __global__ void k_mma_manual(const __half* A, const __half* B, float* out, int N
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tb, 256); }
 }
 
+// descriptor with an explicit matrix base offset (bits [49,52)): needed (or not) when the start address is not
+// aligned to the 1024-byte swizzle repeat - probes 9 / 10 measure which
+__device__ __forceinline__ uint64_t desc_bo(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t bo) {
+  return umma_smem_desc(addr, lbo, sbo) | (static_cast<uint64_t>(bo & 7) << 49);
+}
+// probe 9: K-major A tile of 144 rows in the TMA SW128 layout; the MMA reads rows [s, s+128) through a descriptor
+// whose start address is shifted by s*128 bytes (a 3x3 tap shift inside one halo tile).  out[m,n] = A[m+s,:].B[n,:]
+__global__ void k_mma_kshift(const __half* A, const __half* B, float* out, int N, uint32_t idesc, int s, int bo_mode) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tbase;
+  uint8_t* sa = sm; uint8_t* sb = sm + 144 * 128;
+  for (int i = threadIdx.x; i < 144 * 64; i += blockDim.x) {
+    int r = i / 64, k = i % 64;
+    int off = r * 128 + ((((k * 2) / 16) ^ (r % 8)) * 16) + (k * 2) % 16;
+    *reinterpret_cast<__half*>(sa + off) = A[i];
+  }
+  for (int i = threadIdx.x; i < N * 64; i += blockDim.x) {
+    int r = i / 64, k = i % 64;
+    int off = r * 128 + ((((k * 2) / 16) ^ (r % 8)) * 16) + (k * 2) % 16;
+    *reinterpret_cast<__half*>(sb + off) = B[i];
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(&tbase, 256);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tb = tbase;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a_addr = smem_u32(sa) + s * 128 + k * 32;
+      uint64_t da = desc_bo(a_addr, 16, 1024, bo_mode ? (a_addr >> 7) & 7 : 0);
+      uint64_t db = umma_smem_desc(smem_u32(sb) + k * 32, 16, 1024);
+      umma_f16(tb, da, db, idesc, k != 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int ch = 0; ch < N / 32; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(tb + ch * 32 + (uint32_t(w * 32) << 16), v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(w * 32 + lane) * N + ch * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tb, 256); }
+}
+// probe 10: MN-major operands (rows = K index = pixel, 64 contiguous M/N elements per 128-byte row, SW128).
+// A: 80 K-rows x 128 M (two 64-wide blocks LBO apart), read from K-row s on;  B: 64 K-rows x 64 N unshifted.
+// out[m,n] = sum_{k<64} A[k+s, m] * B[k, n]
+__global__ void k_mma_mnshift(const __half* A, const __half* B, float* out, uint32_t idesc, int s, int bo_mode) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tbase;
+  const int RA = 80;
+  uint8_t* sa = sm; uint8_t* sb = sm + 2 * RA * 128;
+  for (int i = threadIdx.x; i < RA * 128; i += blockDim.x) {       // A[k][m]
+    int k = i / 128, m = i % 128;
+    int blk = m / 64, mm = m % 64;
+    int off = blk * RA * 128 + k * 128 + ((((mm * 2) / 16) ^ (k % 8)) * 16) + (mm * 2) % 16;
+    *reinterpret_cast<__half*>(sa + off) = A[i];
+  }
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {        // B[k][n]
+    int k = i / 64, n = i % 64;
+    int off = k * 128 + ((((n * 2) / 16) ^ (k % 8)) * 16) + (n * 2) % 16;
+    *reinterpret_cast<__half*>(sb + off) = B[i];
+  }
+  fence_proxy_async();
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (threadIdx.x < 32) tmem_alloc(&tbase, 64);
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tb = tbase;
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t a_addr = smem_u32(sa) + s * 128 + k * 2048;
+      uint64_t da = desc_bo(a_addr, RA * 128, 1024, bo_mode ? (a_addr >> 7) & 7 : 0);
+      uint64_t db = umma_smem_desc(smem_u32(sb) + k * 2048, 64 * 128, 1024);
+      umma_f16(tb, da, db, idesc, k != 0);
+    }
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  const int w = threadIdx.x / 32, lane = threadIdx.x % 32;
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t v[32];
+    tmem_ld_32x32(tb + ch * 32 + (uint32_t(w * 32) << 16), v);
+    tmem_ld_wait();
+    for (int j = 0; j < 32; ++j) out[(w * 32 + lane) * 64 + ch * 32 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before(); __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tb, 64); }
+}
+
 static void report(const char* name) {
   cudaError_t e = cudaDeviceSynchronize();
   printf("%s: %s\n", name, e == cudaSuccess ? "ran OK" : cudaGetErrorString(e));
@@ -186,6 +283,49 @@ int main(int argc, char** argv) {
       double e = fabs(ref - O[m * N + n]); if (e > maxerr) maxerr = e; if (e > 1e-3) ++bad;
     }
     printf("  mismatches %d maxerr %g\n", bad, maxerr);
+    return 0;
+  }
+  if (id == 9 || id == 10) {
+    const int sft = argc > 2 ? atoi(argv[2]) : 1, bo = argc > 3 ? atoi(argv[3]) : 0;
+    srand(3);
+    if (id == 9) {
+      const int N = 64;
+      std::vector<__half> A(144 * 64), B(N * 64); std::vector<float> Af(A.size()), Bf(B.size());
+      for (size_t i = 0; i < A.size(); ++i) { float v = (rand() % 17 - 8) / 8.f; A[i] = __float2half(v); Af[i] = v; }
+      for (size_t i = 0; i < B.size(); ++i) { float v = (rand() % 13 - 6) / 4.f; B[i] = __float2half(v); Bf[i] = v; }
+      __half *dA, *dB; float* dO;
+      cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dO, 128 * N * 4);
+      cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
+      cudaMemset(dO, 0, 128 * N * 4);
+      cudaFuncSetAttribute(k_mma_kshift, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
+      k_mma_kshift<<<1, 128, 60000>>>(dA, dB, dO, N, umma_idesc_f16(128, N, 0, 0, 0, 0), sft, bo);
+      report("mma K-major row shift");
+      std::vector<float> O(128 * N); cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
+      int bad = 0;
+      for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
+        float ref = 0; for (int k = 0; k < 64; ++k) ref += Af[(m + sft) * 64 + k] * Bf[n * 64 + k];
+        if (fabs(ref - O[m * N + n]) > 1e-3) ++bad;
+      }
+      printf("  K-major shift %d base_offset_mode %d: mismatches %d of %d\n", sft, bo, bad, 128 * N);
+    } else {
+      std::vector<__half> A(80 * 128), B(64 * 64); std::vector<float> Af(A.size()), Bf(B.size());
+      for (size_t i = 0; i < A.size(); ++i) { float v = (rand() % 17 - 8) / 8.f; A[i] = __float2half(v); Af[i] = v; }
+      for (size_t i = 0; i < B.size(); ++i) { float v = (rand() % 13 - 6) / 4.f; B[i] = __float2half(v); Bf[i] = v; }
+      __half *dA, *dB; float* dO;
+      cudaMalloc(&dA, A.size() * 2); cudaMalloc(&dB, B.size() * 2); cudaMalloc(&dO, 128 * 64 * 4);
+      cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
+      cudaMemset(dO, 0, 128 * 64 * 4);
+      cudaFuncSetAttribute(k_mma_mnshift, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
+      k_mma_mnshift<<<1, 128, 60000>>>(dA, dB, dO, umma_idesc_f16(128, 64, 0, 0, 1, 1), sft, bo);
+      report("mma MN-major K-row shift");
+      std::vector<float> O(128 * 64); cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
+      int bad = 0;
+      for (int m = 0; m < 128; ++m) for (int n = 0; n < 64; ++n) {
+        float ref = 0; for (int k = 0; k < 64; ++k) ref += Af[(k + sft) * 128 + m] * Bf[k * 64 + n];
+        if (fabs(ref - O[m * 64 + n]) > 1e-3) ++bad;
+      }
+      printf("  MN-major shift %d base_offset_mode %d: mismatches %d of %d\n", sft, bo, bad, 128 * 64);
+    }
     return 0;
   }
   return 0;
