@@ -5,7 +5,11 @@
 // The reduction runs over pixels, which are the *rows* of the NHWC tensors, so both operands are MN-major:
 // a TMA box of (64 channels x <=64 pixels) lands as <=64 swizzled 128-byte rows (row = pixel = UMMA K index,
 // 64 contiguous channels = UMMA M/N index).  The 3x3 taps shift the x box by (dh, dw); TMA zero-fills the halo.
-// One CTA per (tap, n tile, c tile, pixel split); fp32 partials leave through atomics.  The n tile is 256 wide (two
+// 3x3: a CTA owns one kernel ROW (dh) and computes its three taps (dw = -1, 0, +1) from ONE x box loaded with a
+// one-pixel halo in W: the tap shift is a 128-byte shift of the UMMA descriptor start address inside that box (the
+// hardware applies the 128-byte swizzle to absolute shared-memory addresses, so any row offset is legal - measured,
+// tools/tc_probe.cu probe 10).  dy is loaded once for the three taps: ~3x less L2->SMEM traffic than a box per tap.
+// One CTA per (tap row, n tile, c tile, pixel split); fp32 partials leave through atomics.  The n tile is 256 wide (two
 // M=128 accumulators that share every x box: 128 FLOP per byte staged from L2 instead of 85) when N >= 256, else 128.
 //   warps 0-3: epilogue (TMEM -> atomicAdd),  warp 4: TMA producer,  warp 5: TMEM alloc + MMA issuer
 #include "common.cuh"
@@ -15,7 +19,7 @@
 namespace dfcsa {
 namespace {
 
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kBoxBytes = 64 * 128;          // one (64 ch x 64 px) box
 constexpr int kBMaxBytes = 4 * kBoxBytes;    // up to 256 c
 
@@ -28,7 +32,10 @@ struct WgradTcArgs {
   int tiles_w, tiles_h, tiles_b, w_t, h_t;   // pixel-block geometry
   long long pix_blocks, blocks_per_split;
   int x_mode, dy_mode;
-  int box_bytes;           // bytes one TMA box delivers (w_t*h_t*128)
+  int dw3;                 // 3x3 mode: three dw taps per CTA from one halo box (patch 16 x 4 pixels, x box 18 x 4)
+  int x_box_bytes;         // shared-memory pitch of one x box (also the LBO between its 64-channel blocks)
+  int x_tx_bytes;          // bytes one x TMA box delivers
+  int box_bytes;           // bytes one dy TMA box delivers (w_t*h_t*128)
   float* dw; long long ld_dw;
   const float* alpha;
   uint32_t idesc;
@@ -87,7 +94,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   if (warp == 4) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>((n_boxes_a + n_boxes_b) * a.box_bytes);
+    const uint32_t tx_bytes = static_cast<uint32_t>(n_boxes_a * a.box_bytes + n_boxes_b * a.x_tx_bytes);
     for (long long pb = pb_beg; pb < pb_end; ++pb) {
       const int tw = static_cast<int>(pb % a.tiles_w);
       const long long r = pb / a.tiles_w;
@@ -106,8 +113,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             tma_load_5d(sa + j * kBoxBytes, &map_dy, &full_bar[stage], n0 + j * 64, w0, h0, tb, 0);
         }
         for (int j = 0; j < n_boxes_b; ++j) {
-          if (a.x_mode == DFCSA_TAP_3x3)
-            tma_load_5d(sb + j * kBoxBytes, &map_x, &full_bar[stage], c0 + j * 64, w0 + tap % 3 - 1, h0 + tap / 3 - 1, tb, 0);
+          if (a.dw3)   // tap == dh: rows h0+dh-1 .., columns w0-1 .. w0+16 (halo of one pixel on each side)
+            tma_load_5d(sb + j * a.x_box_bytes, &map_x, &full_bar[stage], c0 + j * 64, w0 - 1, h0 + tap - 1, tb, 0);
           else
             tma_load_5d(sb + j * kBoxBytes, &map_x, &full_bar[stage], c0 + j * 64, w0, h0, tb, 0);
         }
@@ -125,12 +132,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
         const uint32_t b_addr = a_addr + kABytes;
-        for (int h = 0; h < n_halves; ++h) {
+        if (a.dw3) {
+          for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {   // 16 pixels (rows) per instruction = 2 KiB
-            const uint64_t da = umma_smem_desc(a_addr + h * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-            const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
-            umma_f16(tmem_base + h * 256, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 4; ++k) {   // patch row k: 16 dy pixels against x pixels shifted by dw inside the 18-wide row
+              const uint64_t da = umma_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + (k * 18 + dw) * 128, a.x_box_bytes, 1024);
+              umma_f16(tmem_base + dw * 128, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
+            }
+          }
+        } else {
+          for (int h = 0; h < n_halves; ++h) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {   // 16 pixels (rows) per instruction = 2 KiB
+              const uint64_t da = umma_smem_desc(a_addr + h * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
+              umma_f16(tmem_base + h * 256, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -148,14 +166,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       tc_fence_after();
       const float alpha = a.alpha ? __ldg(a.alpha) : 1.f;
       const int ccols = min(a.block_c, a.C - c0);
-      for (int h = 0; h < n_halves; ++h) {
-        const int n = n0 + h * 128 + warp * 32 + lane;
+      const int n_acc = a.dw3 ? 3 : n_halves;           // accumulators: the three dw taps, or the two 128-row halves
+      for (int h = 0; h < n_acc; ++h) {
+        const int n = n0 + (a.dw3 ? 0 : h * 128) + warp * 32 + lane;
+        const int tap_out = a.dw3 ? tap * 3 + h : tap;
+        const uint32_t acc_col = a.dw3 ? h * 128 : h * 256;
         for (int ch = 0; ch * 32 < ccols; ++ch) {
           uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + h * 256 + ch * 32 + (static_cast<uint32_t>(warp * 32) << 16), raw);
+          tmem_ld_32x32(tmem_base + acc_col + ch * 32 + (static_cast<uint32_t>(warp * 32) << 16), raw);
           tmem_ld_wait();
           if (n < a.N) {
-            float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap) * a.C + c0 + ch * 32;
+            float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap_out) * a.C + c0 + ch * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (ch * 32 + i < ccols) atomicAdd(dst + i, alpha * __uint_as_float(raw[i]));
@@ -222,14 +243,25 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   const uint64_t ldx = static_cast<uint64_t>(p->ld_x) * 2, ldy = static_cast<uint64_t>(p->ld_dy) * 2;
   uint64_t dims[5], strides[4];
   uint32_t box[5];
+  a.x_box_bytes = kBoxBytes;
   if (p->x_tap_mode == DFCSA_TAP_3x3) {
-    pick_patch(p->H, p->W, a.w_t, a.h_t);
+    // one kernel row per CTA; pixel patch 16 wide x 4 high so that every UMMA K step (16 pixels) is one patch row and
+    // the dw shift never crosses a row boundary; the x box carries one halo pixel on each side: 18 x 4 pixels
+    a.dw3 = 1; a.taps = 3;
+    a.w_t = 16; a.h_t = 4;
+    a.block_n = 128; a.n_tiles = (p->N + 127) / 128;
+    a.block_c = std::min(p->C, 128); a.c_tiles = (p->C + a.block_c - 1) / a.block_c;
+    a.x_box_bytes = 18 * 4 * 128;                       // 9216
+    a.a_bytes = 2 * kBoxBytes;
+    a.stage_bytes = a.a_bytes + 2 * a.x_box_bytes;      // 34816
+    a.stages = 5;
     a.tiles_w = (p->W + a.w_t - 1) / a.w_t; a.tiles_h = (p->H + a.h_t - 1) / a.h_t; a.tiles_b = p->B;
-    box[0] = 64; box[1] = a.w_t; box[2] = a.h_t; box[3] = 1; box[4] = 1;
+    box[0] = 64; box[1] = 18; box[2] = 4; box[3] = 1; box[4] = 1;
     dims[0] = p->C; dims[1] = p->W; dims[2] = p->H; dims[3] = p->B; dims[4] = 1;
     strides[0] = ldx; strides[1] = p->W * ldx; strides[2] = static_cast<uint64_t>(p->H) * p->W * ldx; strides[3] = static_cast<uint64_t>(Mtot) * ldx;
     int rc = encode_tensor_map(&map_x, p->x_dtype, 5, p->x, dims, strides, box, true);
     if (rc) return rc;
+    box[1] = 16;
     dims[0] = p->N;
     strides[0] = ldy; strides[1] = p->W * ldy; strides[2] = static_cast<uint64_t>(p->H) * p->W * ldy; strides[3] = static_cast<uint64_t>(Mtot) * ldy;
     rc = encode_tensor_map(&map_dy, p->dy_dtype, 5, p->dy, dims, strides, box, true);
@@ -263,6 +295,7 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
     if (rc) return rc;
   }
   a.box_bytes = a.w_t * a.h_t * 128;
+  a.x_tx_bytes = a.dw3 ? a.x_box_bytes : a.box_bytes;
   a.pix_blocks = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
 
   const long long items = static_cast<long long>(a.taps) * a.n_tiles * a.c_tiles;
@@ -272,7 +305,7 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.splits = static_cast<int>((a.pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split);
   a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
   a.idesc = umma_idesc_f16(128, a.block_c, umma_fmt(p->dy_dtype), umma_fmt(p->x_dtype), 1, 1);
-  a.tmem_cols = a.block_n == 256 ? 512 : (a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256);
+  a.tmem_cols = (a.block_n == 256 || a.dw3) ? 512 : (a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256);
 
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;

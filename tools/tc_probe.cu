@@ -114,13 +114,13 @@ __device__ __forceinline__ uint64_t desc_bo(uint32_t addr, uint32_t lbo, uint32_
 }
 // probe 9: K-major A tile of 144 rows in the TMA SW128 layout; the MMA reads rows [s, s+128) through a descriptor
 // whose start address is shifted by s*128 bytes (a 3x3 tap shift inside one halo tile).  out[m,n] = A[m+s,:].B[n,:]
-__global__ void k_mma_kshift(const __half* A, const __half* B, float* out, int N, uint32_t idesc, int s, int bo_mode) {
+__global__ void k_mma_kshift(const __half* A, const __half* B, float* out, int N, uint32_t idesc, int s, int bo_mode, int sbo = 1024) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tbase;
-  uint8_t* sa = sm; uint8_t* sb = sm + 144 * 128;
-  for (int i = threadIdx.x; i < 144 * 64; i += blockDim.x) {
+  uint8_t* sa = sm; uint8_t* sb = sm + 176 * 128;
+  for (int i = threadIdx.x; i < 176 * 64; i += blockDim.x) {
     int r = i / 64, k = i % 64;
     int off = r * 128 + ((((k * 2) / 16) ^ (r % 8)) * 16) + (k * 2) % 16;
     *reinterpret_cast<__half*>(sa + off) = A[i];
@@ -138,7 +138,7 @@ __global__ void k_mma_kshift(const __half* A, const __half* B, float* out, int N
   if (threadIdx.x == 0) {
     for (int k = 0; k < 4; ++k) {
       const uint32_t a_addr = smem_u32(sa) + s * 128 + k * 32;
-      uint64_t da = desc_bo(a_addr, 16, 1024, bo_mode ? (a_addr >> 7) & 7 : 0);
+      uint64_t da = desc_bo(a_addr, 16, sbo, bo_mode ? (a_addr >> 7) & 7 : 0);
       uint64_t db = umma_smem_desc(smem_u32(sb) + k * 32, 16, 1024);
       umma_f16(tb, da, db, idesc, k != 0);
     }
@@ -290,7 +290,8 @@ int main(int argc, char** argv) {
     srand(3);
     if (id == 9) {
       const int N = 64;
-      std::vector<__half> A(144 * 64), B(N * 64); std::vector<float> Af(A.size()), Bf(B.size());
+      std::vector<__half> A(176 * 64), B(N * 64); std::vector<float> Af(A.size()), Bf(B.size());
+      const int sbo = argc > 4 ? atoi(argv[4]) : 1024;      // 1280: 8-row groups 10 rows apart (8-wide patch rows with a halo)
       for (size_t i = 0; i < A.size(); ++i) { float v = (rand() % 17 - 8) / 8.f; A[i] = __float2half(v); Af[i] = v; }
       for (size_t i = 0; i < B.size(); ++i) { float v = (rand() % 13 - 6) / 4.f; B[i] = __float2half(v); Bf[i] = v; }
       __half *dA, *dB; float* dO;
@@ -298,15 +299,16 @@ int main(int argc, char** argv) {
       cudaMemcpy(dA, A.data(), A.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, B.data(), B.size() * 2, cudaMemcpyHostToDevice);
       cudaMemset(dO, 0, 128 * N * 4);
       cudaFuncSetAttribute(k_mma_kshift, cudaFuncAttributeMaxDynamicSharedMemorySize, 60000);
-      k_mma_kshift<<<1, 128, 60000>>>(dA, dB, dO, N, umma_idesc_f16(128, N, 0, 0, 0, 0), sft, bo);
+      k_mma_kshift<<<1, 128, 60000>>>(dA, dB, dO, N, umma_idesc_f16(128, N, 0, 0, 0, 0), sft, bo, sbo);
       report("mma K-major row shift");
       std::vector<float> O(128 * N); cudaMemcpy(O.data(), dO, O.size() * 4, cudaMemcpyDeviceToHost);
       int bad = 0;
       for (int m = 0; m < 128; ++m) for (int n = 0; n < N; ++n) {
-        float ref = 0; for (int k = 0; k < 64; ++k) ref += Af[(m + sft) * 64 + k] * Bf[n * 64 + k];
+        const int row = (m / 8) * (sbo / 128) + m % 8 + sft;
+        float ref = 0; for (int k = 0; k < 64; ++k) ref += Af[row * 64 + k] * Bf[n * 64 + k];
         if (fabs(ref - O[m * N + n]) > 1e-3) ++bad;
       }
-      printf("  K-major shift %d base_offset_mode %d: mismatches %d of %d\n", sft, bo, bad, 128 * N);
+      printf("  K-major shift %d base_offset_mode %d sbo %d: mismatches %d of %d\n", sft, bo, sbo, bad, 128 * N);
     } else {
       std::vector<__half> A(80 * 128), B(64 * 64); std::vector<float> Af(A.size()), Bf(B.size());
       for (size_t i = 0; i < A.size(); ++i) { float v = (rand() % 17 - 8) / 8.f; A[i] = __float2half(v); Af[i] = v; }
