@@ -364,6 +364,34 @@ __global__ void permute3_kernel(const void* src, int sdt, void* dst, int ddt, lo
   }
 }
 
+// many permute3 jobs in one launch: chunk_prefix[j] = first 1024-element chunk of job j (n_jobs + 1 entries)
+__global__ void __launch_bounds__(256)
+pack_jobs_kernel(const dfcsa_pack_job_t* jobs, int n_jobs, const long long* chunk_prefix, long long total_chunks) {
+  for (long long ch = blockIdx.x; ch < total_chunks; ch += gridDim.x) {
+    int lo = 0, hi = n_jobs - 1;               // last job whose first chunk is <= ch
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (chunk_prefix[mid] <= ch) lo = mid; else hi = mid - 1;
+    }
+    const dfcsa_pack_job_t j = jobs[lo];
+    const long long total = j.D0 * j.D1 * j.D2;
+    const long long base = (ch - chunk_prefix[lo]) * 1024;
+    const float sc = j.scale ? *j.scale : 1.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = base + u * 256 + threadIdx.x;
+      if (i < total) {
+        const long long i2 = i % j.D2;
+        const long long r = i / j.D2;
+        const long long i1 = r % j.D1;
+        const long long i0 = r / j.D1;
+        const long long i1s = j.flip1 ? j.D1 - 1 - i1 : i1;
+        st_any(j.dst, i0 * j.ld_dst + i1 * j.D2 + i2, j.dst_dtype, sc * ld_any(j.src, i0 * j.s0 + i1s * j.s1 + i2 * j.s2, j.src_dtype));
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int conv_gemm_simt(const dfcsa_conv_params_t* p, cudaStream_t stream) {
@@ -427,6 +455,16 @@ extern "C" int dfcsa_softmax_rows_bwd(const float* y, const float* dy, float* dx
   const int wpb = 8;
   softmax_rows_bwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(y, dy, dx, rows, cols);
   DFCSA_LAUNCH_CHECK("softmax_rows_bwd_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_pack_jobs(const dfcsa_pack_job_t* jobs_dev, int32_t n_jobs, const int64_t* chunk_prefix_dev,
+                               int64_t total_chunks, void* stream) {
+  DFCSA_CHECK_ARG(jobs_dev && chunk_prefix_dev && n_jobs > 0 && total_chunks > 0, "dfcsa_pack_jobs: bad args");
+  const int blocks = static_cast<int>(std::min<long long>(total_chunks, 148 * 16));
+  pack_jobs_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, n_jobs, reinterpret_cast<const long long*>(chunk_prefix_dev),
+                                                                          total_chunks);
+  DFCSA_LAUNCH_CHECK("pack_jobs_kernel");
   return DFCSA_OK;
 }
 

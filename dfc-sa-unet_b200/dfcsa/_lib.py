@@ -62,6 +62,13 @@ class SgemmParams(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("scale", C.c_void_p),
+                ("D0", C.c_int64), ("D1", C.c_int64), ("D2", C.c_int64),
+                ("s0", C.c_int64), ("s1", C.c_int64), ("s2", C.c_int64), ("ld_dst", C.c_int64),
+                ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32), ("flip1", C.c_int32), ("pad_", C.c_int32)]
+
+
 class ParamDesc(C.Structure):
     _fields_ = [("w", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("n", C.c_int64)]
 
@@ -69,7 +76,7 @@ class ParamDesc(C.Structure):
 # every symbol include/dfcsa.h declares (the CPU test checks the .so exports exactly these)
 SYMBOLS = [
     "dfcsa_version", "dfcsa_last_error", "dfcsa_device_ok",
-    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_sgemm",
+    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm",
     "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd",
     "dfcsa_bn_finalize", "dfcsa_bn_eval_affine",
     "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd",

@@ -58,53 +58,137 @@ class BlockParams:
         self.tc = (self.Ci % 64 == 0) and (self.C % 64 == 0)
 
 
-def pack_block_weights(bp, training, need_dx=True):
-    """fp32 master weights -> packed K-major GEMM operands (forward: fp16 / fp32; dgrad: bf16 / fp32)."""
+class PackPlan:
+    """Every weight re-layout of a network (fp32 masters -> packed 16-bit GEMM operands) as a device table of jobs that
+    ONE dfcsa_pack_jobs launch executes per step.  Destination buffers are persistent, so the plan is built once per
+    (network, mode) and only re-run after the optimizer has changed the masters."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.jobs = []
+        self.keep = []          # tensors whose storage the table points into
+        self._table = None
+
+    def add(self, src, dst, D, s, flip1=False, scale=None, ld_dst=0):
+        self.jobs.append((src, dst, tuple(D), tuple(s), flip1, scale, ld_dst or D[1] * D[2]))
+        self.keep += [src, dst, scale]
+
+    def run(self):
+        if not self.jobs:
+            return
+        if self._table is None:
+            from . import _lib as L
+            tab = (L.PackJob * len(self.jobs))()
+            prefix, tot = [0], 0
+            for i, (src, dst, D, st, flip1, scale, ld) in enumerate(self.jobs):
+                j = tab[i]
+                j.src, j.dst = src.data_ptr(), dst.data_ptr()
+                j.scale = scale.data_ptr() if scale is not None else None
+                j.D0, j.D1, j.D2 = D
+                j.s0, j.s1, j.s2 = st
+                j.ld_dst = ld
+                j.src_dtype, j.dst_dtype, j.flip1 = L.dt(src), L.dt(dst), 1 if flip1 else 0
+                tot += (D[0] * D[1] * D[2] + 1023) // 1024
+                prefix.append(tot)
+            self._table = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(self.dev)
+            self._prefix = torch.tensor(prefix, dtype=torch.int64, device=self.dev)
+            self._chunks = tot
+        ops.pack_jobs(self._table, len(self.jobs), self._prefix, self._chunks)
+
+
+def pack_block_weights(bp, training, need_dx, plan):
+    """fp32 master weights -> packed K-major GEMM operands (forward: fp16 / fp32; dgrad: bf16 / fp32): allocates the
+    persistent destination buffers and records the re-layout jobs in `plan`."""
     dev = bp.W1.device
     Ci, C = bp.Ci, bp.C
     fdt = F16 if bp.tc else F32
     pk = {}
     W5 = bp.W5.detach() if bp.W5 is not None else torch.eye(C, dtype=F32, device=dev).view(C, C, 1, 1)
     pk["w1"] = _e((C, 9 * Ci), fdt, dev)
-    ops.permute3(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
+    plan.add(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
     pk["w25"] = _e((2 * C, Ci), fdt, dev)
-    ops.permute3(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1))
-    ops.permute3(W5, pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
+    plan.add(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1))
+    plan.add(W5, pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
     gdt = F16 if C % 64 == 0 else F32
     pk["w3"] = _e((C, 2 * C), gdt, dev)
-    ops.permute3(bp.W3.detach(), pk["w3"], (C, 1, 2 * C), (2 * C, 0, 1))
+    plan.add(bp.W3.detach(), pk["w3"], (C, 1, 2 * C), (2 * C, 0, 1))
     pk["w4"] = _e((C, 3 * C), gdt, dev)
-    ops.permute3(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1))
+    plan.add(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1))
     # q/k/v 1x1 convs on the pooled map as ONE GEMM: rows [Wq ; Wk ; Wv], bias [bq | bk | bv]
     Cq = bp.Cq
     nq = 2 * Cq + C
     pk["wqkv"] = _e((nq, C), gdt, dev)
-    ops.permute3(bp.Wq.detach(), pk["wqkv"][:Cq], (Cq, 1, C), (C, 0, 1))
-    ops.permute3(bp.Wk.detach(), pk["wqkv"][Cq:2 * Cq], (Cq, 1, C), (C, 0, 1))
-    ops.permute3(bp.Wv.detach(), pk["wqkv"][2 * Cq:], (C, 1, C), (C, 0, 1))
-    pk["bqkv"] = torch.cat([bp.bq.detach(), bp.bk.detach(), bp.bv.detach()])
+    plan.add(bp.Wq.detach(), pk["wqkv"][:Cq], (Cq, 1, C), (C, 0, 1))
+    plan.add(bp.Wk.detach(), pk["wqkv"][Cq:2 * Cq], (Cq, 1, C), (C, 0, 1))
+    plan.add(bp.Wv.detach(), pk["wqkv"][2 * Cq:], (C, 1, C), (C, 0, 1))
+    pk["bqkv"] = _e((nq,), F32, dev)
+    plan.add(bp.bq.detach(), pk["bqkv"][:Cq], (1, 1, Cq), (0, 0, 1))
+    plan.add(bp.bk.detach(), pk["bqkv"][Cq:2 * Cq], (1, 1, Cq), (0, 0, 1))
+    plan.add(bp.bv.detach(), pk["bqkv"][2 * Cq:], (1, 1, C), (0, 0, 1))
     if training:
         bdt = BF16 if C % 64 == 0 else F32
         kp = (nq + 63) // 64 * 64 if C % 64 == 0 else nq      # K of the dgrad GEMM, zero-padded to the UMMA K block
         wdq = _z((C, kp), bdt, dev)                 # [c, (q | k | v | pad)] = [Wq ; Wk ; Wv]^T
-        ops.permute3(bp.Wq.detach(), wdq[:, :Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
-        ops.permute3(bp.Wk.detach(), wdq[:, Cq:2 * Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
-        ops.permute3(bp.Wv.detach(), wdq[:, 2 * Cq:nq], (C, 1, C), (1, 0, C), ld_dst=kp)
+        plan.add(bp.Wq.detach(), wdq[:, :Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
+        plan.add(bp.Wk.detach(), wdq[:, Cq:2 * Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
+        plan.add(bp.Wv.detach(), wdq[:, 2 * Cq:nq], (C, 1, C), (1, 0, C), ld_dst=kp)
         pk["wdqkv"] = wdq
-        wd4 = _e((3 * C, C), bdt, dev)             # [k_in, co] = W4^T
-        ops.permute3(bp.W4.detach(), wd4, (3 * C, 1, C), (1, 0, 3 * C))
-        wd3 = _e((2 * C, C), bdt, dev)
-        ops.permute3(bp.W3.detach(), wd3, (2 * C, 1, C), (1, 0, 2 * C))
-        pk["wd4f"] = wd4[:C]                       # df  = dF0 . W4^T[:, 0:C]
-        pk["wd43"] = torch.cat([wd4[C:], wd3], dim=1).contiguous()   # [dL|dA] = [dF0 | dG0] . [W4^T[:, C:3C] ; W3^T]
+        W4m, W3m = bp.W4.detach().view(C, 3 * C), bp.W3.detach().view(C, 2 * C)
+        pk["wd4f"] = _e((C, C), bdt, dev)           # df = dF0 . W4^T[0:C, :]:  wd4f[k, co] = W4[co, k]
+        plan.add(W4m, pk["wd4f"], (C, 1, C), (1, 0, 3 * C))
+        # [dL | dA] = [dF0 | dG0] . wd43^T with wd43[n, (co of W4 | co of W3)] = (W4[co, C + n] | W3[co, n])
+        pk["wd43"] = _e((2 * C, 2 * C), bdt, dev)
+        plan.add(W4m[:, C:], pk["wd43"], (2 * C, 1, C), (1, 0, 3 * C), ld_dst=2 * C)
+        plan.add(W3m, pk["wd43"][:, C:], (2 * C, 1, C), (1, 0, 2 * C), ld_dst=2 * C)
         if need_dx:   # the first block never needs the gradient w.r.t. the image
             xdt = BF16 if bp.tc else F32
             wd = _e((Ci, 11 * C), xdt, dev)            # [ci, (flipped tap, co) | co (W2) | co (res_scale*W5)]
-            ops.permute3(bp.W1.detach(), wd, (Ci, 9, C), (9, 1, Ci * 9), flip1=True, ld_dst=11 * C)
-            ops.permute3(bp.W2.detach(), wd[:, 9 * C:], (Ci, 1, C), (1, 0, Ci), ld_dst=11 * C)
-            ops.permute3(W5, wd[:, 10 * C:], (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1), ld_dst=11 * C)
+            plan.add(bp.W1.detach(), wd, (Ci, 9, C), (9, 1, Ci * 9), flip1=True, ld_dst=11 * C)
+            plan.add(bp.W2.detach(), wd[:, 9 * C:], (Ci, 1, C), (1, 0, Ci), ld_dst=11 * C)
+            plan.add(W5, wd[:, 10 * C:], (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1), ld_dst=11 * C)
             pk["wd125"] = wd
     return pk
+
+
+class NetPacks:
+    """Persistent packed operands of a whole UNetDFCSA + the plan that refreshes them (cached on the module)."""
+
+    def __init__(self, net, keep):
+        dev = next(net.parameters()).device
+        self.sig = NetPacks.signature(net)
+        self.plan = PackPlan(dev)
+        self.bps = [BlockParams(b) for b in _blocks(net)]
+        self.pks = [pack_block_weights(bp, keep, i > 0, self.plan) for i, bp in enumerate(self.bps)]
+        self.up_fwd, self.up_bwd = [], []
+        for up in (net.up4, net.up3, net.up2, net.up1):
+            Ci_t, Co_t = up.weight.shape[0], up.weight.shape[1]
+            tc = Ci_t % 64 == 0 and Co_t % 64 == 0
+            wt = _e((4 * Co_t, Ci_t), F16 if tc else F32, dev)         # [(q, co), ci]
+            self.plan.add(up.weight.detach(), wt, (4, Co_t, Ci_t), (1, 4, Co_t * 4))
+            self.up_fwd.append(wt)
+            if keep:
+                wdt = _e((Ci_t, 4 * Co_t), BF16 if tc else F32, dev)   # [ci, (q, co)]
+                self.plan.add(up.weight.detach(), wdt, (Ci_t, 4, Co_t), (Co_t * 4, 1, 4))
+                self.up_bwd.append(wdt)
+        fc = net.final_conv
+        Cout, f0 = fc.weight.shape[0], fc.weight.shape[1]
+        self.wdf = None
+        if keep:
+            self.wdf = _e((f0, Cout), F32, dev)                         # final conv dgrad operand [f0, Cout]
+            self.plan.add(fc.weight.detach(), self.wdf, (f0, 1, Cout), (1, 0, f0))
+
+    @staticmethod
+    def signature(net):
+        return tuple(p.data_ptr() for p in net.parameters())
+
+    @staticmethod
+    def get(net, keep):
+        cache = net.__dict__.setdefault("_dfcsa_packs", {})
+        pk = cache.get(keep)
+        if pk is None or pk.sig != NetPacks.signature(net):
+            pk = cache[keep] = NetPacks(net, keep)
+        pk.plan.run()
+        return pk
 
 
 class BlockCtx:
@@ -369,8 +453,8 @@ def net_forward(net, x_nchw, training, save=True):
         raise NotImplementedError("dfcsa: H and W must be multiples of 16 (the reference's bilinear re-size fallback at "
                                   "models/unet_dfc_sa_res.py:180-181 is not on the 224/512/1024 hot path)")
     x_nchw = x_nchw.contiguous().float()
-    bps = [BlockParams(b) for b in _blocks(net)]
-    pks = [pack_block_weights(bp, keep, need_dx=(i > 0)) for i, bp in enumerate(bps)]
+    packs = NetPacks.get(net, keep)
+    bps, pks = packs.bps, packs.pks
     f = [bps[i].C for i in range(4)]
     ctx = NetCtx() if keep else None
     Hs = [H >> i for i in range(5)]
@@ -400,17 +484,14 @@ def net_forward(net, x_nchw, training, save=True):
         up = ups[j]
         Ci_t, Co_t = up.weight.shape[0], up.weight.shape[1]
         tc = Ci_t % 64 == 0 and Co_t % 64 == 0
-        wt = _e((4 * Co_t, Ci_t), F16 if tc else F32, dev)         # [(q, co), ci]
-        ops.permute3(up.weight.detach(), wt, (4, Co_t, Ci_t), (1, 4, Co_t * 4))
+        wt = packs.up_fwd[j]
         segs = [(u, TAP_1x1)]
         dst = cat[lvl][:, :f[lvl]]
         ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, wt, 4 * Co_t, dst, out_mode=OUT_CONVT2x2, bias=up.bias.detach(),
                       backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT,
                       shadow=catb[lvl][:, :f[lvl]] if keep else None)
         if keep:
-            wdt = _e((Ci_t, 4 * Co_t), BF16 if tc else F32, dev)   # [ci, (q, co)]
-            ops.permute3(up.weight.detach(), wdt, (Ci_t, 4, Co_t), (Co_t * 4, 1, 4))
-            upk.append(wdt)
+            upk.append(packs.up_bwd[j])
             uin.append(ub)
         un = _e((Ms[lvl], f[lvl]), F16, dev)
         unb = _e((Ms[lvl], f[lvl]), BF16, dev) if keep else None
@@ -434,6 +515,7 @@ def net_forward(net, x_nchw, training, save=True):
         ctx.bps, ctx.pks, ctx.bctx, ctx.xs = bps, pks, bctx, xs
         ctx.upk, ctx.uin, ctx.u_last, ctx.u_lastb = upk, uin, u, ub
         ctx.dims = (B, Cin, H, W, f, Hs, Ws, Ms)
+        ctx.wdf = packs.wdf
     return logits, ctx
 
 
@@ -459,8 +541,7 @@ def net_backward(net, ctx, dlogits_nchw, grads, after_stage=None):
     ops.nchw_to_nhwc(dlogits_nchw.contiguous().float(), dl, B, Cout, H, W)
     # final conv backward (K = Cout is tiny: SIMT)
     du = _e((Ms[0], f[0]), BF16, dev)
-    wdf = fc.weight.detach().view(Cout, f[0]).t().contiguous()        # [f0, Cout]
-    ops.conv_gemm(B, H, W, [(dl, TAP_1x1)], wdf, f[0], du, backend=BACKEND_SIMT)
+    ops.conv_gemm(B, H, W, [(dl, TAP_1x1)], ctx.wdf, f[0], du, backend=BACKEND_SIMT)
     ops.conv_wgrad(B, H, W, ctx.u_lastb, TAP_1x1, dl, TAP_1x1, grads[fc.weight].view(Cout, f[0]), backend=BACKEND_SIMT)
     ops.colsum(dl, grads[fc.bias])
     ups = [net.up4, net.up3, net.up2, net.up1]

@@ -53,7 +53,9 @@ class _BlockFunction(torch.autograd.Function):
         training = block.training
         keep = training and need_grad
         bp = engine.BlockParams(block)
-        pk = engine.pack_block_weights(bp, keep, need_dx=True)
+        plan = engine.PackPlan(dev)
+        pk = engine.pack_block_weights(bp, keep, True, plan)
+        plan.run()
         M = B * H * W
         xin = engine._e((M, Ci), torch.float16 if bp.tc else torch.float32, dev)
         ops.nchw_to_nhwc(x.contiguous().float(), xin, B, Ci, H, W)

@@ -82,6 +82,11 @@ def permute3(src, dst, D, s, flip1=False, scale=None, ld_dst=0):
                                    1 if flip1 else 0, L.ptr(scale), C.c_int64(ld_dst), L.stream())
 
 
+def pack_jobs(table, n_jobs, prefix, total_chunks):
+    """run a PackPlan's device job table (dfcsa_pack_jobs): every weight re-layout of the network in one launch."""
+    L.call("dfcsa_pack_jobs", L.ptr(table), n_jobs, L.ptr(prefix), C.c_int64(total_chunks), L.stream())
+
+
 def sgemm(batch, M, N, K, A, a_str, Bm, b_str, Cm, c_str, alpha=1.0, beta=0.0, bias_n=None, bias_m=None):
     """C[b] = alpha*A[b]@B[b] + beta*C[b] with element strides (batch, row, col)   (dfcsa_sgemm)."""
     p = L.SgemmParams()

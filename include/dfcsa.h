@@ -112,6 +112,16 @@ int dfcsa_permute3(const void* src, int src_dtype, void* dst, int dst_dtype,
                    int64_t D0, int64_t D1, int64_t D2, int64_t s0, int64_t s1, int64_t s2,
                    int flip1, const float* scale, int64_t ld_dst, void* stream);
 
+/* The same re-layout for a whole network in ONE launch: a device table of jobs (all weight tensors of the model,
+ * built once by the host) and the prefix sum of their sizes in 1024-element chunks (n_jobs + 1 entries). */
+typedef struct {
+  const void* src; void* dst; const float* scale;
+  int64_t D0, D1, D2, s0, s1, s2, ld_dst;
+  int32_t src_dtype, dst_dtype, flip1, pad_;
+} dfcsa_pack_job_t;
+int dfcsa_pack_jobs(const dfcsa_pack_job_t* jobs_dev, int32_t n_jobs, const int64_t* chunk_prefix_dev,
+                    int64_t total_chunks, void* stream);
+
 /* Strided batched fp32 GEMM  C[b] = alpha * A[b] * B[b] + beta * C[b]  with arbitrary element strides
  * (transposes are strides).  Used for the pooled attention products, reference
  * models/unet_dfc_sa_res.py:28-33 (q/k/v 1x1 convs on the pooled map, bmm(Q,K), bmm(V,A^T)) and their backward. */
