@@ -48,10 +48,6 @@ struct ConvTcArgs {
   uint32_t idesc;
   __nv_bfloat16* shadow;
   long long ld_shadow;
-  int epi_mode, epi_C;
-  const __nv_bfloat16* epi_df; long long ld_epi_df;
-  const __half* epi_g0; long long ld_epi_g0;
-  const float* epi_scale; const float* epi_shift;
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -266,24 +262,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(a.bias + cn + i);
         }
-        if (a.epi_mode == DFCSA_EPI_GATE_MIX && valid) {
-          // backward of fused = g*L + (1-g)*A: this 32-column chunk lies in the dL half (n0 < C) or the dA half
-          const int hi = n0 >= a.epi_C ? 1 : 0;
-          const int c = n0 - hi * a.epi_C;
-          const __nv_bfloat16* dfp = a.epi_df + row_off * a.ld_epi_df + c;
-          const __half* gp = a.epi_g0 + row_off * a.ld_epi_g0 + c;
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float d[8], g[8], sc[8], sh[8];
-            load8<__nv_bfloat16>(dfp + g8 * 8, d); load8<__half>(gp + g8 * 8, g);
-            load8<float>(a.epi_scale + c + g8 * 8, sc); load8<float>(a.epi_shift + c + g8 * 8, sh);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float gg = 1.f / (1.f + __expf(-fmaf(g[i], sc[i], sh[i])));
-              v[g8 * 8 + i] = fmaf(d[i], hi ? 1.f - gg : gg, v[g8 * 8 + i]);
-            }
-          }
-        }
         if (valid) {
           if (a.out_dtype == DFCSA_F16)
             store_chunk<__half>(reinterpret_cast<__half*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
@@ -465,20 +443,6 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->shadow == nullptr || (!p->accumulate && p->ld_shadow % 8 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 15) == 0),
                   "conv_gemm_tc: bad shadow output");
   if (p->out_mode == DFCSA_OUT_CONVT2x2) { a.convt_co = p->N / 4; a.convt_h = p->H; a.convt_w = p->W; }
-  a.epi_mode = p->epi_mode;
-  if (p->epi_mode == DFCSA_EPI_GATE_MIX) {
-    DFCSA_CHECK_ARG(p->out_mode == DFCSA_OUT_DIRECT && !p->accumulate && p->N == 2 * p->epi_C && p->epi_C % 32 == 0 &&
-                    p->epi_df && p->epi_g0 && p->epi_scale && p->epi_shift && p->ld_epi_df % 8 == 0 && p->ld_epi_g0 % 8 == 0 &&
-                    (reinterpret_cast<uintptr_t>(p->epi_df) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->epi_g0) & 15) == 0 &&
-                    (reinterpret_cast<uintptr_t>(p->epi_scale) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->epi_shift) & 15) == 0,
-                    "conv_gemm_tc: bad gate-mix epilogue arguments");
-    a.epi_C = p->epi_C;
-    a.epi_df = reinterpret_cast<const __nv_bfloat16*>(p->epi_df); a.ld_epi_df = p->ld_epi_df;
-    a.epi_g0 = reinterpret_cast<const __half*>(p->epi_g0); a.ld_epi_g0 = p->ld_epi_g0;
-    a.epi_scale = p->epi_scale; a.epi_shift = p->epi_shift;
-  } else {
-    DFCSA_CHECK_ARG(p->epi_mode == DFCSA_EPI_NONE, "conv_gemm_tc: unknown epilogue mode %d", p->epi_mode);
-  }
 
   const int smem_bytes = a.stages * stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;

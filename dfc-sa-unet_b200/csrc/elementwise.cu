@@ -572,12 +572,12 @@ gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lon
   }
 }
 
-// pass 1 of the branch backward: the BN1 reductions over d1 = dL * [L > 0]
+// pass 1 of the branch backward: gate-mix terms into dL / dA (in place) and the BN1 reductions
 template <int VEC>
-__global__ void __launch_bounds__(256, 4)
-branch_bwd_reduce1_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, long long M, int C,
-                          const float* s1, const float* t1, const float* mean1, const float* invstd1, double* red1,
-                          int CL, int PL) {
+__global__ void __launch_bounds__(256, 3)
+branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* g0, long long ld_g0,
+                          long long M, int C, const float* s1, const float* t1, const float* mean1,
+                          const float* invstd1, const float* s3, const float* t3, double* red1, int CL, int PL) {
   __shared__ float s_red[2 * 256 * VEC];
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c_base = blockIdx.y * CL * VEC;
@@ -586,11 +586,22 @@ branch_bwd_reduce1_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, lo
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
   if (pl < PL && c < C) {
-    float sc[VEC], sh[VEC];
-    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh);
+    float sc[VEC], sh[VEC], sc3[VEC], sh3[VEC];
+    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3);
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      float dl[VEC], lv[VEC];
-      ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(l0 + m * ld_l0 + c, lv);
+      float dl[VEC], da[VEC], df[VEC], gv[VEC], lv[VEC];
+      ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+      ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(g0 + m * ld_g0 + c, gv);
+      ldv<VEC>(l0 + m * ld_l0 + c, lv);
+      // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); rounded to the stored precision so that the sums see
+      // exactly what the later passes read back
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float gg = 1.f / (1.f + __expf(-fmaf(gv[v], sc3[v], sh3[v])));
+        dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
+        da[v] = fmaf(df[v], 1.f - gg, da[v]);
+      }
+      stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float d1 = fmaf(lv[v], sc[v], sh[v]) > 0.f ? dl[v] : 0.f;
@@ -971,20 +982,20 @@ extern "C" int dfcsa_gate_mix_bwd_apply(const void* dz, int64_t ld_dz, const voi
   return DFCSA_OK;
 }
 
-extern "C" int dfcsa_branch_bwd_reduce1(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0,
+extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, const void* g0, int64_t ld_g0,
                                         int32_t B, int32_t H, int32_t W, int32_t C, const float* scale1, const float* shift1,
-                                        const float* mean1, const float* invstd1,
+                                        const float* mean1, const float* invstd1, const float* scale3, const float* shift3,
                                         const float* o, int32_t P, const float* gamma, double* red1, double* dgamma, float* tmp,
                                         float* d_o, void* stream) {
-  DFCSA_CHECK_ARG(dz && l0 && scale1 && shift1 && mean1 && invstd1 && o && gamma && red1 && dgamma && tmp && d_o,
+  DFCSA_CHECK_ARG(dz && l0 && g0 && scale1 && shift1 && mean1 && invstd1 && scale3 && shift3 && o && gamma && red1 && dgamma && tmp && d_o,
                   "dfcsa_branch_bwd_reduce1: null pointer");
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_bwd_reduce1: too many pixels");
-  const bool v8 = vec8_ok(C, {ld_dz, ld_l0}, {dz, l0, o, tmp, scale1, shift1, mean1, invstd1});
+  const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_g0}, {dz, l0, g0, o, tmp, scale1, shift1, mean1, invstd1, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
   dim3 grid(red_blocks(M, g.PL), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, M, C, scale1, shift1, mean1,
-                                                                         invstd1, red1, g.CL, g.PL)));
+  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
+                                                                         shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));

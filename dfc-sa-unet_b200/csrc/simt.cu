@@ -139,12 +139,6 @@ conv_simt_kernel(const SimtConvArgs a) {
         pix = (b * 2 * p.H + 2 * h + (q >> 1)) * (2LL * p.W) + 2 * w + (q & 1);
       }
       if (p.bias != nullptr) v += p.bias[cn];
-      if (p.epi_mode == DFCSA_EPI_GATE_MIX) {
-        const int hi = n >= p.epi_C ? 1 : 0;
-        const int c = n - hi * p.epi_C;
-        const float gg = 1.f / (1.f + __expf(-fmaf(ld_any(p.epi_g0, m * p.ld_epi_g0 + c, DFCSA_F16), p.epi_scale[c], p.epi_shift[c])));
-        v = fmaf(ld_any(p.epi_df, m * p.ld_epi_df + c, DFCSA_BF16), hi ? 1.f - gg : gg, v);
-      }
       const long long o = pix * p.ld_out + cn;
       if (p.accumulate) v += ld_any(p.out, o, p.out_dtype);
       st_any(p.out, o, p.out_dtype, v);
@@ -406,9 +400,6 @@ int conv_gemm_simt(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   a.p = *p;
   a.M = static_cast<long long>(p->B) * p->H * p->W;
   DFCSA_CHECK_ARG(a.M > 0 && p->N > 0, "conv_gemm_simt: empty problem");
-  DFCSA_CHECK_ARG(p->epi_mode == DFCSA_EPI_NONE ||
-                  (p->epi_mode == DFCSA_EPI_GATE_MIX && p->out_mode == DFCSA_OUT_DIRECT && !p->accumulate && p->N == 2 * p->epi_C &&
-                   p->epi_df && p->epi_g0 && p->epi_scale && p->epi_shift), "conv_gemm_simt: bad epilogue arguments");
   a.ktot = 0;
   for (int s = 0; s < p->n_seg; ++s)
     a.ktot += p->seg[s].channels * (p->seg[s].tap_mode == DFCSA_TAP_1x1 ? 1 : p->seg[s].tap_mode == DFCSA_TAP_3x3 ? 9 : 4);

@@ -194,7 +194,7 @@ int small_blocks(long long M) {
 // returns 1 if handled, 0 if the shape is not one of the specialised ones, < 0 on error
 int conv_gemm_small(const dfcsa_conv_params_t* p, cudaStream_t stream, int* rc_out) {
   *rc_out = DFCSA_OK;
-  if (p->n_seg != 1 || p->out_mode != DFCSA_OUT_DIRECT || p->accumulate || p->shadow != nullptr || p->epi_mode != DFCSA_EPI_NONE) return 0;
+  if (p->n_seg != 1 || p->out_mode != DFCSA_OUT_DIRECT || p->accumulate || p->shadow != nullptr) return 0;
   const dfcsa_seg_t& sg = p->seg[0];
   const long long M = static_cast<long long>(p->B) * p->H * p->W;
   // ---- tiny N (final 1x1 conv) ----

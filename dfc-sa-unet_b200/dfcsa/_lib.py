@@ -16,7 +16,6 @@ F32, F16, BF16 = 0, 1, 2
 TAP_1x1, TAP_3x3, TAP_2x2S2 = 0, 1, 2
 OUT_DIRECT, OUT_CONVT2x2 = 0, 1
 BACKEND_TC, BACKEND_SIMT = 0, 1
-EPI_NONE, EPI_GATE_MIX = 0, 1
 
 _TORCH2DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
 
@@ -39,9 +38,6 @@ class ConvParams(C.Structure):
         ("out_mode", C.c_int32), ("accumulate", C.c_int32),
         ("bias", C.c_void_p), ("stats", C.c_void_p),
         ("shadow", C.c_void_p), ("ld_shadow", C.c_int64),
-        ("epi_mode", C.c_int32), ("epi_C", C.c_int32),
-        ("epi_df", C.c_void_p), ("ld_epi_df", C.c_int64), ("epi_g0", C.c_void_p), ("ld_epi_g0", C.c_int64),
-        ("epi_scale", C.c_void_p), ("epi_shift", C.c_void_p),
     ]
 
 

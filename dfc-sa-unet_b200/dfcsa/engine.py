@@ -402,17 +402,16 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     dG0 = _e((M, C), BF16, dev)
     ops.gate_mix_bwd_apply(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3, dG0)
     ops.bn_param_grads(red3, C, grads[bp.bn3.weight], grads[bp.bn3.bias])
-    # fusion conv part 2 + gate conv in ONE dgrad GEMM: [dL | dA] = [dF0 | dG0] . [W4^T[:, C:3C] ; W3^T], whose epilogue
-    # also adds the gate-mix terms df*g / df*(1-g): dz[:, C:3C] leaves the GEMM complete
+    # fusion conv part 2 + gate conv in ONE dgrad GEMM: [dL' | dA'] = [dF0 | dG0] . [W4^T[:, C:3C] ; W3^T]
     dLA = dz[:, C:]
     segs = [(dF0, TAP_1x1), (dG0, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["wd43"], 2 * C, dLA, backend=_backend(segs, pk["wd43"], 2 * C, dLA),
-                  gate_mix=(df, ctx.G0, bn3[0], bn3[1]))
+    ops.conv_gemm(B, H, W, segs, pk["wd43"], 2 * C, dLA, backend=_backend(segs, pk["wd43"], 2 * C, dLA))
     _wgrad(B, H, W, ctx.zb[:, C:], TAP_1x1, dG0, TAP_1x1, grads[bp.W3].view(C, 2 * C))
-    # branches
+    # branches (reduce1 first adds the gate-mix terms df*g / df*(1-g) into dL / dA in place)
     tmp = _e((B, H, P, C), F32, dev)
     d_o = _e((B * P * P, C), F32, dev)
-    ops.branch_bwd_reduce1(dz, ctx.L0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], ctx.o, P, bp.gamma.detach(), red1, dgam, tmp, d_o)
+    ops.branch_bwd_reduce1(dz, ctx.L0, ctx.G0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], bn3[0], bn3[1], ctx.o, P,
+                           bp.gamma.detach(), red1, dgam, tmp, d_o)
     dpooled = attention_backward(bp, pk, ctx, d_o, B, P * P, grads)
     ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
     dL0, dA0 = dF0, dG0     # both dead after the GEMMs above: reuse their storage

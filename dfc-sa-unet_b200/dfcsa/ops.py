@@ -26,7 +26,7 @@ def tc_eligible(segs, N, out):
 
 
 def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, bias=None, stats=None,
-              backend=BACKEND_TC, shadow=None, gate_mix=None):
+              backend=BACKEND_TC, shadow=None):
     """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm)."""
     p = L.ConvParams()
     p.B, p.H, p.W, p.n_seg = B, H, W, len(segs)
@@ -48,12 +48,6 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.stats = stats.data_ptr() if stats is not None else None
     p.shadow = shadow.data_ptr() if shadow is not None else None
     p.ld_shadow = _mat(shadow) if shadow is not None else 0
-    if gate_mix is not None:        # (df bf16 [M, C], g0 fp16 [M, C], scale3, shift3): DFCSA_EPI_GATE_MIX
-        df, g0, s3, t3 = gate_mix
-        p.epi_mode, p.epi_C = L.EPI_GATE_MIX, df.shape[1]
-        p.epi_df, p.ld_epi_df = df.data_ptr(), _mat(df)
-        p.epi_g0, p.ld_epi_g0 = g0.data_ptr(), _mat(g0)
-        p.epi_scale, p.epi_shift = s3.data_ptr(), t3.data_ptr()
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
            flops=2.0 * B * H * W * N * ktot,
@@ -192,10 +186,11 @@ def gate_mix_bwd_apply(dz, z, g0, s3, t3, mean3, invstd3, red3, dg0):
                                              L.ptr(red3), L.ptr(dg0), _i64(_mat(dg0)), L.stream())
 
 
-def branch_bwd_reduce1(dz, l0, B, H, W, s1, t1, mean1, invstd1, o, P, gamma, red1, dgamma, tmp, d_o):
+def branch_bwd_reduce1(dz, l0, g0, B, H, W, s1, t1, mean1, invstd1, s3, t3, o, P, gamma, red1, dgamma, tmp, d_o):
     Cn = l0.shape[1]
-    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), B, H, W, Cn, L.ptr(s1),
-                                             L.ptr(t1), L.ptr(mean1), L.ptr(invstd1), L.ptr(o), P, L.ptr(gamma), L.ptr(red1),
+    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), L.ptr(g0), _i64(_mat(g0)),
+                                             B, H, W, Cn, L.ptr(s1),
+                                             L.ptr(t1), L.ptr(mean1), L.ptr(invstd1), L.ptr(s3), L.ptr(t3), L.ptr(o), P, L.ptr(gamma), L.ptr(red1),
                                              L.ptr(dgamma), L.ptr(tmp), L.ptr(d_o), L.stream())
 
 

@@ -38,7 +38,6 @@ enum {
 };
 enum { DFCSA_OUT_DIRECT = 0, DFCSA_OUT_CONVT2x2 = 1 };
 enum { DFCSA_BACKEND_TC = 0, DFCSA_BACKEND_SIMT = 1 };
-enum { DFCSA_EPI_NONE = 0, DFCSA_EPI_GATE_MIX = 1 };
 
 int         dfcsa_version(void);
 const char* dfcsa_last_error(void);
@@ -82,13 +81,6 @@ typedef struct {
   void*   shadow;           /* optional bf16 copy of the result at the same coordinates (pitch ld_shadow): the operand
                                the weight-gradient GEMM reads later (kind::f16 cannot mix fp16 and bf16) */
   int64_t ld_shadow;
-  /* optional fused epilogue.  DFCSA_EPI_GATE_MIX (the dgrad GEMM that produces [dL | dA], N = 2*epi_C): adds the
-   * backward of fused = g*L + (1-g)*A (reference models/unet_dfc_sa_res.py:106) before the store:
-   *   out[m, c] += df[m, c]*g,  out[m, epi_C + c] += df[m, c]*(1-g),  g = sigmoid(g0[m, c]*epi_scale[c] + epi_shift[c]) */
-  int32_t epi_mode, epi_C;
-  const void* epi_df; int64_t ld_epi_df;   /* bf16 [M, epi_C] */
-  const void* epi_g0; int64_t ld_epi_g0;   /* fp16 [M, epi_C] (pre-BN gate conv output) */
-  const float* epi_scale; const float* epi_shift;
 } dfcsa_conv_params_t;
 
 int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);
@@ -218,20 +210,20 @@ int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const void* z, int6
                               const float* scale3, const float* shift3, const float* mean3, const float* invstd3,
                               double* red3, void* stream);
 /* pass 2: dG0 = gamma3*invstd3*(dS - mean(dS) - xhat3*mean(dS*xhat3)) -> dg0 (bf16).  Only df = dz[:, 0:C] is read: the
- * dL / dA columns of dz are produced afterwards by one two-segment dgrad GEMM over [dF0 | dG0] whose epilogue adds
- * df*g / df*(1-g) (DFCSA_EPI_GATE_MIX). */
+ * dL / dA columns of dz are produced afterwards by one two-segment dgrad GEMM over [dF0 | dG0] (no read-modify-write). */
 int dfcsa_gate_mix_bwd_apply(const void* dz, int64_t ld_dz, const void* z, int64_t ld_z,
                              const void* g0, int64_t ld_g0, int64_t M, int32_t C,
                              const float* scale3, const float* shift3, const float* mean3, const float* invstd3,
                              const float* gamma3, const double* red3,
                              void* dg0, int64_t ld_dg0, void* stream);
-/* branch backward, pass 1 (dz[:, C:3C] already holds the complete dL | dA: the dgrad GEMM's DFCSA_EPI_GATE_MIX epilogue
- * added the gate-mix terms):
+/* branch backward, pass 1.  First completes the gradients of the two branches in place with the gate-mix terms:
+ *   dL = dz[:,C:2C] += df*g,  dA = dz[:,2C:3C] += df*(1-g),  g = sigmoid(bn3(G0)), df = dz[:,0:C];  then
  *   red1 += (sum d1, sum d1*xhat1) with d1 = dL*[L>0];
  *   dgamma += sum dA*U (U = bilinear_up(o));  do = gamma * bilinear_up^T(dA)  ([B,P,P,C] fp32, separable, tmp [B,H,P,C]) */
-int dfcsa_branch_bwd_reduce1(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0,
+int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0, const void* g0, int64_t ld_g0,
                              int32_t B, int32_t H, int32_t W, int32_t C,
                              const float* scale1, const float* shift1, const float* mean1, const float* invstd1,
+                             const float* scale3, const float* shift3,
                              const float* o, int32_t P, const float* gamma,
                              double* red1, double* dgamma, float* tmp, float* d_o, void* stream);
 /* pass 2 (after the pooled-attention backward produced dpooled [B,P,P,C]):

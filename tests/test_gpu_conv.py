@@ -229,24 +229,3 @@ def test_wgrad_small_channel_kernels(cuda, case):
     ops.conv_wgrad(B, H, W, x.reshape(-1, Cc), xm, dy.reshape(-1, N), 0, dw, alpha=torch.tensor([0.5], device=dev), backend=1)
     torch.cuda.synchronize()
     assert _rel_err(dw, ref) < 2e-3
-
-
-@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
-@pytest.mark.parametrize("C,M", [(64, 1000), (128, 517)])
-def test_gate_mix_epilogue(cuda, C, M, backend):
-    """DFCSA_EPI_GATE_MIX: [dL | dA] = [dF0 | dG0] . w^T  +  (df*g | df*(1-g)),  g = sigmoid(g0*scale + shift)."""
-    from dfcsa import ops
-    g = torch.Generator().manual_seed(9)
-    dF0 = torch.randn(M, C, generator=g).cuda().bfloat16()
-    dG0 = torch.randn(M, C, generator=g).cuda().bfloat16()
-    w = (torch.randn(2 * C, 2 * C, generator=g) / (2 * C) ** 0.5).cuda()
-    df = torch.randn(M, C, generator=g).cuda().bfloat16()
-    g0 = torch.randn(M, C, generator=g).cuda().half()
-    s3, t3 = torch.rand(C, generator=g).cuda() + 0.5, torch.randn(C, generator=g).cuda()
-    wq = w.bfloat16() if backend == 0 else w
-    out = torch.empty(M, 2 * C, device=cuda, dtype=torch.bfloat16)
-    ops.conv_gemm(1, 1, M, [(dF0, 0), (dG0, 0)], wq, 2 * C, out, backend=backend, gate_mix=(df, g0, s3, t3))
-    torch.cuda.synchronize()
-    gate = torch.sigmoid(g0.float() * s3 + t3)
-    ref = torch.cat([dF0, dG0], 1).float() @ wq.float().t() + torch.cat([df.float() * gate, df.float() * (1 - gate)], 1)
-    assert _rel_err(out.float(), ref) < 6e-3      # bf16 output rounding
