@@ -178,3 +178,29 @@ def test_twelve_step_dice_trajectory(cuda):
         got = tr.train_step(img.cuda(), mask.cuda()).host()
         assert abs(got["dice"] - ref["dice"]) <= 1e-3, (step, got, ref["dice"])
         assert abs(got["loss"] - ref["loss"]) <= 5e-3, (step, got, ref["loss"])
+
+
+def test_cuda_graph_step_matches_eager(cuda):
+    """Trainer.train_step_graphed (capture on the third call, then replay) follows the eager trajectory."""
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    from dfcsa.selftest import set_gamma
+    from dfcsa.trainer import Trainer
+    cfg = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/dfcsa_test"}}
+    batches = [tuple(t.cuda() for t in O.synthetic_batch(2, 64, 64, seed=s)) for s in (1, 2)]
+    traj = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)
+        set_gamma(model, 0.5)
+        tr = Trainer(model, None, None, None, "cuda", cfg)
+        out = []
+        for step in range(6):
+            img, mask = batches[step % 2]
+            r = tr.train_step_graphed(img, mask) if graphed else tr.train_step(img, mask)
+            out.append(r.host())
+        traj.append(out)
+        if graphed:
+            assert any(g[1] is not None for g in tr._graphs.values())      # a graph was really captured
+    for a, b in zip(*traj):
+        assert abs(a["loss"] - b["loss"]) < 2e-3 and abs(a["dice"] - b["dice"]) < 2e-3, (a, b)

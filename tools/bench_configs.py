@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""Timings of the other BASELINE.json configurations on one B200 (bench.py is the headline metric only):
+
+  c1  DFC-SA-Res-Block P4, 224^2, batch 4, full train step (the reference's own CPU-runnable case) - latency bound
+  c2  pool-size sweep P4 / P16 / P32, 224^2, batch 64, train
+  c3  ablation 3 (UNet_FullResAttention), 224^2, batch 1, train
+  c4  512^2, 32 images per GPU (the per-GPU share of global batch 256 on 8 GPUs), train, + peak memory
+  c5  eval-mode batched inference at 1024^2, batch 1/2/4/8: images/s and p50 latency
+
+  python tools/bench_configs.py [c1 c2 ...] --out gpurun_out/configs.json
+All numbers are CUDA-event timings after warm-up, inputs resident on the device, synthetic structured images.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "dfc-sa-unet_b200")]
+
+import torch  # noqa: E402
+
+from dfcsa.modules import UNet_FullResAttention, UNetDFCSARes  # noqa: E402
+from dfcsa.selftest import set_gamma  # noqa: E402
+from dfcsa.trainer import Trainer  # noqa: E402
+from oracle import dfcsa_oracle as O  # noqa: E402   (synthetic_batch generator only)
+
+CFG = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/dfcsa_cfg"}}
+FEATURES = [64, 128, 256, 512]
+
+
+def batch(B, hw, seed=1):
+    parts = [O.synthetic_batch(min(8, B - i), hw, hw, seed=seed + i) for i in range(0, B, 8)]
+    return torch.cat([p[0] for p in parts]).cuda(), torch.cat([p[1] for p in parts]).cuda()
+
+
+def time_steps(fn, warmup, steps):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for e0, e1 in evs:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    ms = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    return {"ms_mean": sum(ms) / len(ms), "ms_p50": ms[len(ms) // 2], "ms_min": ms[0]}
+
+
+def train_case(model, B, hw, warmup=3, steps=8, graph=False):
+    torch.cuda.reset_peak_memory_stats()
+    tr = Trainer(model, None, None, None, "cuda", CFG)
+    img, mask = batch(B, hw)
+    step = (lambda: tr.train_step_graphed(img, mask)) if graph else (lambda: tr.train_step(img, mask))
+    t0 = time.time()
+    r = time_steps(step, warmup, steps)
+    r.update({"batch": B, "hw": hw, "img_per_s": B / (r["ms_mean"] * 1e-3), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+              "wall_s": time.time() - t0, "cuda_graph": graph})
+    del tr
+    torch.cuda.empty_cache()
+    return r
+
+
+def new_model(P=4, full_res=False):
+    torch.manual_seed(0)
+    m = UNet_FullResAttention(3, 1, FEATURES) if full_res else UNetDFCSARes(3, 1, FEATURES, pool_size=P, ablation_on_qk_channels=8)
+    set_gamma(m, 0.5)
+    return m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("cases", nargs="*", default=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--out", default="gpurun_out/configs.json")
+    args = ap.parse_args()
+    res = {}
+
+    def run(name, fn):
+        try:
+            res[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            res[name] = {"error": f"{type(e).__name__}: {e}"[:400]}
+            torch.cuda.empty_cache()
+        print(name, json.dumps(res[name]), flush=True)
+        json.dump(res, open(args.out, "w"), indent=1)
+
+    if "c1" in args.cases:
+        run("c1_p4_224_b4_train", lambda: train_case(new_model(4), 4, 224, steps=20))
+        if hasattr(Trainer, "train_step_graphed"):
+            run("c1_p4_224_b4_train_cudagraph", lambda: train_case(new_model(4), 4, 224, steps=20, graph=True))
+    if "c2" in args.cases:
+        for P in (4, 16, 32):
+            run(f"c2_p{P}_224_b64_train", lambda P=P: train_case(new_model(P), 64, 224, steps=5))
+    if "c3" in args.cases:
+        run("c3_fullres_224_b1_train", lambda: train_case(new_model(full_res=True), 1, 224, warmup=1, steps=2))
+    if "c4" in args.cases:
+        run("c4_p4_512_b32_train", lambda: train_case(new_model(4), 32, 512, warmup=2, steps=4))
+    if "c5" in args.cases:
+        model = new_model(4).cuda().eval()
+        for B in (1, 2, 4, 8):
+            def infer(B=B):
+                img, _ = batch(B, 1024)
+                with torch.no_grad():
+                    r = time_steps(lambda: model(img), 5, 30)
+                r.update({"batch": B, "hw": 1024, "img_per_s": B / (r["ms_mean"] * 1e-3), "p50_latency_ms": r["ms_p50"]})
+                return r
+            run(f"c5_p4_1024_b{B}_eval", infer)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
