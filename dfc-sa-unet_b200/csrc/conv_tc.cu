@@ -48,6 +48,7 @@ struct ConvTcArgs {
   uint32_t idesc;
   __nv_bfloat16* shadow;
   long long ld_shadow;
+  int wide_out, wide_shadow;   // 32-byte stores legal (16-bit tensor, pitch % 16 == 0, base 32-byte aligned, no accumulate)
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -61,6 +62,18 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvTcArgs& a, int tile) {
   t.h0 = (r % a.tiles_h) * a.h_t;
   t.tb = r / a.tiles_h;
   return t;
+}
+
+// 32 columns of a 16-bit tensor as two 32-byte (whole-sector) stores; dst is 32-byte aligned
+template <typename TOut>
+__device__ __forceinline__ void store_chunk_wide(TOut* dst, float (&v)[32]) {
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    float t[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t[i] = v[g * 16 + i];
+    store16_256<TOut>(dst + g * 16, t);
+  }
 }
 
 template <typename TOut>
@@ -263,13 +276,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(a.bias + cn + i);
         }
         if (valid) {
-          if (a.out_dtype == DFCSA_F16)
+          if (a.wide_out && ncols == 32) {
+            if (a.out_dtype == DFCSA_F16) store_chunk_wide<__half>(reinterpret_cast<__half*>(a.out) + pix * a.ld_out + cn, v);
+            else store_chunk_wide<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ld_out + cn, v);
+          } else if (a.out_dtype == DFCSA_F16)
             store_chunk<__half>(reinterpret_cast<__half*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
           else if (a.out_dtype == DFCSA_BF16)
             store_chunk<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
           else
             store_chunk<float>(reinterpret_cast<float*>(a.out) + pix * a.ld_out + cn, v, ncols, a.accumulate != 0);
-          if (a.shadow != nullptr) store_chunk<__nv_bfloat16>(a.shadow + pix * a.ld_shadow + cn, v, ncols, false);
+          if (a.shadow != nullptr) {
+            if (a.wide_shadow && ncols == 32) store_chunk_wide<__nv_bfloat16>(a.shadow + pix * a.ld_shadow + cn, v);
+            else store_chunk<__nv_bfloat16>(a.shadow + pix * a.ld_shadow + cn, v, ncols, false);
+          }
         }
         if (a.stats != nullptr) {
           float sq[32];
@@ -443,6 +462,8 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->shadow == nullptr || (!p->accumulate && p->ld_shadow % 8 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 15) == 0),
                   "conv_gemm_tc: bad shadow output");
   if (p->out_mode == DFCSA_OUT_CONVT2x2) { a.convt_co = p->N / 4; a.convt_h = p->H; a.convt_w = p->W; }
+  a.wide_out = p->out_dtype != DFCSA_F32 && !p->accumulate && p->ld_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 31) == 0;
+  a.wide_shadow = p->shadow != nullptr && p->ld_shadow % 16 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 31) == 0;
 
   const int smem_bytes = a.stages * stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;
