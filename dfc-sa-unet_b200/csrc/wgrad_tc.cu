@@ -40,6 +40,7 @@ struct WgradTcArgs {
   const float* alpha;
   uint32_t idesc;
   uint32_t tmem_cols;
+  int vec_red;             // dw rows are 16-byte aligned: red.global.add.v4.f32 (4x fewer L2 atomic operations)
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -177,9 +178,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           tmem_ld_wait();
           if (n < a.N) {
             float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap_out) * a.C + c0 + ch * 32;
+            if (a.vec_red) {      // ccols is a multiple of 64, so a 32-column chunk is always complete
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (ch * 32 + i < ccols) atomicAdd(dst + i, alpha * __uint_as_float(raw[i]));
+              for (int i = 0; i < 32; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                             :: "l"(dst + i), "f"(alpha * __uint_as_float(raw[i])), "f"(alpha * __uint_as_float(raw[i + 1])),
+                                "f"(alpha * __uint_as_float(raw[i + 2])), "f"(alpha * __uint_as_float(raw[i + 3])) : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (ch * 32 + i < ccols) atomicAdd(dst + i, alpha * __uint_as_float(raw[i]));
+            }
           }
         }
       }
@@ -304,6 +313,7 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.blocks_per_split = (a.pix_blocks + splits - 1) / splits;
   a.splits = static_cast<int>((a.pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split);
   a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
+  a.vec_red = ((reinterpret_cast<uintptr_t>(p->dw) & 15) == 0 && p->ld_dw % 4 == 0) ? 1 : 0;
   a.idesc = umma_idesc_f16(128, a.block_c, umma_fmt(p->dy_dtype), umma_fmt(p->x_dtype), 1, 1);
   a.tmem_cols = (a.block_n == 256 || a.dw3) ? 512 : (a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256);
 

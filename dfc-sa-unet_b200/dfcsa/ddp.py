@@ -14,6 +14,19 @@ import torch
 import torch.distributed as dist
 
 
+FLAT_ALIGN = 32      # every tensor starts on a 128-byte boundary of the flat gradient / momentum buffers
+
+
+def flat_offsets(params, align=FLAT_ALIGN):
+    """{param: (lo, hi)} element ranges inside the flat buffers and the padded total length (parameters() order; each
+    tensor 128-byte aligned so that the weight-gradient kernels can use 16-byte vector reductions into it)."""
+    offs, off = {}, 0
+    for p in params:
+        offs[p] = (off, off + p.numel())
+        off = (off + p.numel() + align - 1) // align * align
+    return offs, off
+
+
 def bucket_modules(net):
     """Groups of sub-modules in the order their backward completes (net_backward's after_stage(k) contract)."""
     return [[net.final_conv, net.up_conv1, net.up1], [net.up_conv2, net.up2], [net.up_conv3, net.up3], [net.up_conv4],
@@ -24,19 +37,15 @@ def bucket_ranges(net):
     """Per bucket, the maximal contiguous runs [(lo, hi), ...] of its parameters inside the flat gradient buffer
     (parameters() order).  In this network every bucket is a single run (up_k / up_conv_k / final_conv are adjacent
     in registration order); the function still checks that the buckets partition the buffer exactly."""
-    offs, off = {}, 0
-    for p in net.parameters():
-        offs[p] = (off, off + p.numel())
-        off += p.numel()
-    total = off
+    offs, total = flat_offsets(list(net.parameters()))
     done = torch.zeros(total, dtype=torch.bool) if total < (1 << 28) else None
     out = []
     for mods in bucket_modules(net):
         segs = sorted(offs[p] for m in mods for p in m.parameters())
-        # merge adjacent parameter ranges into maximal contiguous runs
+        # merge adjacent parameter ranges (alignment padding included) into maximal contiguous runs
         runs = []
         for lo, hi in segs:
-            if runs and runs[-1][1] == lo:
+            if runs and (runs[-1][1] + FLAT_ALIGN - 1) // FLAT_ALIGN * FLAT_ALIGN == lo:
                 runs[-1][1] = hi
             else:
                 runs.append([lo, hi])
@@ -46,7 +55,8 @@ def bucket_ranges(net):
                 assert not bool(done[lo:hi].any()), "a parameter belongs to two gradient buckets"
                 done[lo:hi] = True
     if done is not None:
-        assert bool(done.all()), "a parameter belongs to no gradient bucket"
+        for lo, hi in offs.values():
+            assert bool(done[lo:hi].all()), "a parameter belongs to no gradient bucket"
     return out
 
 

@@ -24,21 +24,21 @@ class FusedSGD(torch.optim.SGD):
             raise NotImplementedError("dfcsa.FusedSGD supports one param group (the reference uses one)")
         self._params = ps
         dev = ps[0].device
-        total = sum(p.numel() for p in ps)
+        from .ddp import flat_offsets
+        offsets, total = flat_offsets(ps)
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_mom = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grads, self._mom = {}, {}
-        off = 0
         table = (L.ParamDesc * len(ps))()
         for i, p in enumerate(ps):
             n = p.numel()
+            off = offsets[p][0]
             g = self.flat_grad[off:off + n].view(p.shape)
             m = self.flat_mom[off:off + n].view(p.shape)
             self.grads[p] = g
             self._mom[p] = m
             p.grad = g
             table[i].w, table[i].g, table[i].m, table[i].n = p.data_ptr(), g.data_ptr(), m.data_ptr(), n
-            off += n
         raw = bytes(table)
         self._table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
         self._max_n = max(p.numel() for p in ps)

@@ -18,17 +18,21 @@ def _small_net():
 
 
 def test_buckets_partition_the_flat_gradient_buffer_in_backward_order():
-    from dfcsa.ddp import bucket_modules, bucket_ranges
+    from dfcsa.ddp import FLAT_ALIGN, bucket_modules, bucket_ranges, flat_offsets
     net = _small_net()
     ranges = bucket_ranges(net)            # asserts: every parameter in exactly one bucket
     assert len(ranges) == 9 and all(len(r) == 1 for r in ranges)
-    total = sum(p.numel() for p in net.parameters())
-    assert sum(hi - lo for runs in ranges for lo, hi in runs) == total
-    # reverse execution order: the first bucket ends at the end of the buffer (final_conv), the last one starts at 0
-    assert ranges[0][0][1] == total and ranges[-1][0][0] == 0
+    offs, total = flat_offsets(list(net.parameters()))
+    assert all(lo % FLAT_ALIGN == 0 for lo, _ in offs.values())              # 128-byte aligned tensors
+    runs = [r[0] for r in ranges]
+    for lo, hi in offs.values():                                            # each tensor inside exactly one run
+        assert sum(1 for a, b in runs if a <= lo and hi <= b) == 1
+    assert all(a2 >= b1 for (a1, b1), (a2, b2) in zip(sorted(runs), sorted(runs)[1:]))   # runs do not overlap
+    # reverse execution order: the first bucket ends with the last tensor (final_conv.bias), the last one starts at 0
+    assert ranges[0][0][1] == max(hi for _, hi in offs.values()) and ranges[-1][0][0] == 0
     assert [type(m).__name__ for m in bucket_modules(net)[4]] == ["ConvTranspose2d"]      # {up4} precedes the bottleneck
     # the bottleneck bucket is the largest one (42 % of the bytes at full width)
-    sizes = [sum(hi - lo for lo, hi in runs) for runs in ranges]
+    sizes = [sum(hi - lo for lo, hi in runs_) for runs_ in ranges]
     assert sizes.index(max(sizes)) == 5
 
 
@@ -52,7 +56,7 @@ def _worker(rank, world, port, out_dir):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path[:0] = [root, os.path.join(root, "dfc-sa-unet_b200")]
-    from dfcsa.ddp import BucketReducer, bucket_ranges
+    from dfcsa.ddp import BucketReducer, bucket_ranges, flat_offsets
     from oracle import dfcsa_oracle as O
     torch.set_num_threads(1)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -61,7 +65,10 @@ def _worker(rank, world, port, out_dir):
     names = [n for n, _ in net.named_parameters()]
     img, mask = O.synthetic_batch(2 * world, 32, 32, seed=5)
     g = _shard_grads(sd, names, img[2 * rank:2 * rank + 2], mask[2 * rank:2 * rank + 2])
-    flat = torch.cat([t.reshape(-1) for t in g]).contiguous()
+    offs, total = flat_offsets(list(net.parameters()))
+    flat = torch.zeros(total)
+    for p, t in zip(net.parameters(), g):            # the layout FusedSGD.flat_grad uses
+        flat[offs[p][0]:offs[p][1]] = t.reshape(-1)
     red = BucketReducer(flat, bucket_ranges(net))
     calls = []
     for k in range(len(red.ranges)):        # the order net_backward's after_stage(k) fires in
@@ -69,7 +76,8 @@ def _worker(rank, world, port, out_dir):
         calls.append(k)
     red.finish()
     flat *= 1.0 / world                     # what the fused SGD kernel's grad_scale does
-    torch.save({"flat": flat, "calls": calls}, os.path.join(out_dir, f"r{rank}.pt"))
+    dense = torch.cat([flat[offs[p][0]:offs[p][1]] for p in net.parameters()])
+    torch.save({"flat": dense, "calls": calls}, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
 
