@@ -112,11 +112,25 @@ extern "C" int dfcsa_conv_wgrad(const dfcsa_wgrad_params_t* p, int backend, void
   DFCSA_CHECK_ARG(p->x != nullptr && p->dy != nullptr && p->dw != nullptr, "dfcsa_conv_wgrad: null pointer");
   DFCSA_CHECK_ARG(!(p->x_tap_mode == DFCSA_TAP_3x3 && p->dy_tap_mode != DFCSA_TAP_1x1) && p->x_tap_mode != DFCSA_TAP_2x2S2 &&
                   p->dy_tap_mode != DFCSA_TAP_3x3, "dfcsa_conv_wgrad: unsupported tap mode combination");
+  if (p->dy2 != nullptr) {
+    DFCSA_CHECK_ARG(p->x_tap_mode == DFCSA_TAP_1x1 && p->dy_tap_mode == DFCSA_TAP_1x1 && p->dw2 != nullptr && p->N2 > 0 &&
+                    p->c_begin2 >= 0 && p->c_begin2 < p->C, "dfcsa_conv_wgrad: bad second gradient (1x1 taps only)");
+  }
   if (backend == DFCSA_BACKEND_TC) return conv_wgrad_tc(p, static_cast<cudaStream_t>(stream));
   if (backend == DFCSA_BACKEND_SIMT) {
+    dfcsa_wgrad_params_t a = *p;
+    a.dy2 = nullptr; a.dw2 = nullptr;
     int rc = DFCSA_OK;
-    if (conv_wgrad_small(p, static_cast<cudaStream_t>(stream), &rc)) return rc;
-    return conv_wgrad_simt(p, static_cast<cudaStream_t>(stream));
+    if (!conv_wgrad_small(&a, static_cast<cudaStream_t>(stream), &rc)) rc = conv_wgrad_simt(&a, static_cast<cudaStream_t>(stream));
+    if (rc != DFCSA_OK || p->dy2 == nullptr) return rc;
+    // the fp32 path runs the second gradient as a launch of its own over the channel slice [c_begin2, C) of x
+    dfcsa_wgrad_params_t b = a;
+    b.x = static_cast<const char*>(p->x) + static_cast<size_t>(p->c_begin2) * dtype_size(p->x_dtype);
+    b.C = p->C - p->c_begin2;
+    b.dy = p->dy2; b.ld_dy = p->ld_dy2; b.N = p->N2;
+    b.dw = p->dw2; b.ld_dw = p->ld_dw2; b.alpha = p->alpha2;
+    if (conv_wgrad_small(&b, static_cast<cudaStream_t>(stream), &rc)) return rc;
+    return conv_wgrad_simt(&b, static_cast<cudaStream_t>(stream));
   }
   set_error("dfcsa_conv_wgrad: unknown backend %d", backend);
   return DFCSA_ERR_BAD_ARG;

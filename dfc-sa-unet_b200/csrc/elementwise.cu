@@ -135,9 +135,12 @@ static RedGeom red_geom(int C, int VEC) {
   g.chunks = (cv + g.CL - 1) / g.CL;
   return g;
 }
-static int red_blocks(long long items, int PL) {
+// blocks along x so that the whole grid (x * other_dims) is ONE full wave of `occ` resident blocks per SM: the kernels
+// are grid-stride loops, and 2.67 waves of short blocks cost a ~12 % tail
+static int red_blocks(long long items, int PL, int other_dims = 1, int occ = 4) {
   long long b = (items + PL - 1) / PL;
-  return static_cast<int>(std::max<long long>(1, std::min<long long>(b, 148 * 8)));
+  const long long wave = std::max<long long>(1, static_cast<long long>(num_sms()) * occ / other_dims);
+  return static_cast<int>(std::max<long long>(1, std::min<long long>(b, wave)));
 }
 
 // =============================================================================================
@@ -883,7 +886,7 @@ extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a
   const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_act_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL), g.chunks);
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks, 3), g.chunks);
   VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
                                                                      shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_act_fwd_kernel");
@@ -895,7 +898,7 @@ extern "C" int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int3
   DFCSA_CHECK_ARG(g0 && scale3 && shift3 && z && M > 0 && C > 0, "dfcsa_gate_mix_fwd: bad args");
   const bool v8 = vec8_ok(C, {ld_g0, ld_z, zb ? ld_zb : 0}, {g0, z, zb, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, 4), g.chunks);
   VEC_DISPATCH(v8, (gate_mix_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(g0), ld_g0, M, C, scale3, shift3, AM_(z), ld_z, GM_(zb), ld_zb,
                                                                    g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("gate_mix_fwd_kernel");
@@ -912,7 +915,7 @@ extern "C" int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r,
   const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
   DFCSA_CHECK_ARG(nwin < (1LL << 31), "dfcsa_block_out_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(nwin, g.PL), g.chunks);
+  dim3 grid(red_blocks(nwin, g.PL, g.chunks, 4), g.chunks);
   VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4, res_scale,
                                                                     AM_(y), ld_y, AM_(yp), ld_yp, GM_(yb), ld_yb, GM_(ypb), ld_ypb,
                                                                     g.CL, g.PL)));
@@ -931,7 +934,7 @@ extern "C" int dfcsa_block_out_bwd_reduce(const void* dskip, int64_t ld_dskip, c
                           {dskip, dyp, y, f0, r, dy_out, scale4, shift4, mean4, invstd4});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
-  dim3 grid(red_blocks(nwin, g.PL), g.chunks);
+  dim3 grid(red_blocks(nwin, g.PL, g.chunks, 3), g.chunks);
   VEC_DISPATCH(v8, (block_out_bwd_reduce_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dskip), ld_dskip, G_(dyp), ld_dyp, A_(y), ld_y, A_(f0), ld_f0,
                                                                            A_(r), ld_r, B, H, W, C, scale4, shift4, mean4, invstd4,
                                                                            GM_(dy_out), ld_dy, red4, drs, g.CL, g.PL)));
@@ -947,7 +950,7 @@ extern "C" int dfcsa_bn_bwd_apply(const void* dy, int64_t ld_dy, const void* x, 
   DFCSA_CHECK_ARG(dy && x && scale && shift && mean && invstd && red && dx && M > 0, "dfcsa_bn_bwd_apply: bad args");
   const bool v8 = vec8_ok(C, {ld_dy, ld_x, ld_dx}, {dy, x, dx, scale, shift, mean, invstd});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, 4), g.chunks);
   VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dy), ld_dy, A_(x), ld_x, M, C, scale, shift, mean, invstd, red,
                                                                    act_mode, GM_(dx), ld_dx, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
@@ -960,7 +963,7 @@ extern "C" int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const vo
   DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && M > 0, "dfcsa_gate_mix_bwd_reduce: bad args");
   const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0}, {dz, z, g0, scale3, shift3, mean3, invstd3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
   VEC_DISPATCH(v8, (gate_mix_bwd_reduce_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
                                                                           mean3, invstd3, red3, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("gate_mix_bwd_reduce_kernel");
@@ -975,7 +978,7 @@ extern "C" int dfcsa_gate_mix_bwd_apply(const void* dz, int64_t ld_dz, const voi
   DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && dg0 && M > 0, "dfcsa_gate_mix_bwd_apply: bad args");
   const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0, ld_dg0}, {dz, z, g0, dg0, scale3, shift3, mean3, invstd3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
   VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
                                                                          mean3, invstd3, red3, GM_(dg0), ld_dg0, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("gate_mix_bwd_apply_kernel");
@@ -993,7 +996,7 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
   const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_g0}, {dz, l0, g0, o, tmp, scale1, shift1, mean1, invstd1, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
-  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
   VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
                                                                          shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
@@ -1014,7 +1017,7 @@ extern "C" int dfcsa_branch_bwd_reduce2(const void* dz, int64_t ld_dz, const voi
   const bool v8 = vec8_ok(C, {ld_dz, ld_a0}, {dz, a0, dpooled, scale2, shift2, mean2, invstd2});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
-  dim3 grid(red_blocks(M, g.PL), g.chunks);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
   VEC_DISPATCH(v8, (branch_bwd_reduce2_kernel<VEC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2,
                                                                          invstd2, dpooled, P, red2, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce2_kernel");
@@ -1033,7 +1036,7 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
                           {dz, l0, a0, dl0, da0, dpooled, scale1, shift1, mean1, invstd1, scale2, shift2, mean2, invstd2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31) && H < 32768 && W < 32768, "dfcsa_branch_bwd_apply: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL), g.chunks, 2);
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks * 2, 3), g.chunks, 2);
   VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
                                                                        shift1, mean1, invstd1, red1, scale2, shift2, mean2, invstd2,
                                                                        red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL)));

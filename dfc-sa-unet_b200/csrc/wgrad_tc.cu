@@ -41,11 +41,17 @@ struct WgradTcArgs {
   uint32_t idesc;
   uint32_t tmem_cols;
   int vec_red;             // dw rows are 16-byte aligned: red.global.add.v4.f32 (4x fewer L2 atomic operations)
+  // second gradient over the same x (rows N1 .. N1+N2 of the virtual dy = [dy | dy2]; N1 % 64 == 0)
+  int N1;                  // rows of the first gradient (== N when there is no second one)
+  int c_begin2;
+  float* dw2; long long ld_dw2;
+  const float* alpha2;
+  int vec_red2;
 };
 
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
-                const __grid_constant__ WgradTcArgs a) {
+                const __grid_constant__ CUtensorMap map_dy2, const __grid_constant__ WgradTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -68,7 +74,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const int c0 = ct * a.block_c;
   const int kStages = a.stages, kStageBytes = a.stage_bytes, kABytes = a.a_bytes;
   const long long pb_beg = split * a.blocks_per_split;
-  const long long pb_end = min(a.pix_blocks, pb_beg + a.blocks_per_split);
+  // a tile of the second gradient whose x channels all lie below c_begin2 has nothing to compute
+  const bool dead = n0 >= a.N1 && c0 + a.block_c <= a.c_begin2;
+  const long long pb_end = dead ? pb_beg : min(a.pix_blocks, pb_beg + a.blocks_per_split);
   const int n_boxes_a = min((a.N - n0 + 63) / 64, a.block_n / 64);
   const int n_halves = (n_boxes_a + 1) / 2;
   const int n_boxes_b = min(a.block_c, a.C - c0) / 64;
@@ -82,6 +90,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&map_dy);
     tma_prefetch_desc(&map_x);
+    if (a.N1 < a.N) tma_prefetch_desc(&map_dy2);
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
@@ -110,6 +119,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         for (int j = 0; j < n_boxes_a; ++j) {
           if (a.dy_mode == DFCSA_TAP_2x2S2)
             tma_load_5d(sa + j * kBoxBytes, &map_dy, &full_bar[stage], n0 + j * 64, tap & 1, w0, tap >> 1, h0);
+          else if (n0 + j * 64 >= a.N1)
+            tma_load_5d(sa + j * kBoxBytes, &map_dy2, &full_bar[stage], n0 + j * 64 - a.N1, w0, h0, tb, 0);
           else
             tma_load_5d(sa + j * kBoxBytes, &map_dy, &full_bar[stage], n0 + j * 64, w0, h0, tb, 0);
         }
@@ -165,7 +176,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (pb_end > pb_beg) {
       mbar_wait(&done_bar, 0);
       tc_fence_after();
-      const float alpha = a.alpha ? __ldg(a.alpha) : 1.f;
+      const float alpha1 = a.alpha ? __ldg(a.alpha) : 1.f;
+      const float alpha2 = a.alpha2 ? __ldg(a.alpha2) : 1.f;
       const int ccols = min(a.block_c, a.C - c0);
       const int n_acc = a.dw3 ? 3 : n_halves;           // accumulators: the three dw taps, or the two 128-row halves
       for (int h = 0; h < n_acc; ++h) {
@@ -176,9 +188,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + acc_col + ch * 32 + (static_cast<uint32_t>(warp * 32) << 16), raw);
           tmem_ld_wait();
-          if (n < a.N) {
-            float* dst = a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap_out) * a.C + c0 + ch * 32;
-            if (a.vec_red) {      // ccols is a multiple of 64, so a 32-column chunk is always complete
+          const bool seg2 = n >= a.N1;
+          const int ccol = c0 + ch * 32;       // first x channel of this chunk
+          if (n < a.N && !(seg2 && ccol < a.c_begin2)) {
+            float* dst = seg2 ? a.dw2 + static_cast<long long>(n - a.N1) * a.ld_dw2 + (ccol - a.c_begin2)
+                              : a.dw + static_cast<long long>(n) * a.ld_dw + static_cast<long long>(tap_out) * a.C + ccol;
+            const float alpha = seg2 ? alpha2 : alpha1;
+            if (seg2 ? a.vec_red2 : a.vec_red) {      // ccols is a multiple of 64, so a 32-column chunk is always complete
 #pragma unroll
               for (int i = 0; i < 32; i += 4)
                 asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -230,10 +246,19 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
 
   WgradTcArgs a{};
   a.N = p->N; a.C = p->C;
+  a.N1 = p->N;
+  if (p->dy2 != nullptr) {
+    DFCSA_CHECK_ARG(p->N % 64 == 0 && p->N2 % 8 == 0 && p->c_begin2 % 32 == 0 && p->dy_dtype != DFCSA_F32 && p->ld_dy2 % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(p->dy2) & 15) == 0,
+                    "conv_wgrad_tc: second gradient needs N %% 64 == 0, N2 %% 8 == 0, c_begin2 %% 32 == 0 and 16-byte aligned dy2");
+    a.N = p->N + p->N2;        // rows of the virtual concatenation [dy | dy2]
+    a.c_begin2 = p->c_begin2; a.dw2 = p->dw2; a.ld_dw2 = p->ld_dw2; a.alpha2 = p->alpha2;
+    a.vec_red2 = ((reinterpret_cast<uintptr_t>(p->dw2) & 15) == 0 && p->ld_dw2 % 4 == 0) ? 1 : 0;
+  }
   a.x_mode = p->x_tap_mode; a.dy_mode = p->dy_tap_mode;
   a.taps = p->x_tap_mode == DFCSA_TAP_3x3 ? 9 : (p->dy_tap_mode == DFCSA_TAP_2x2S2 ? 4 : 1);
-  a.block_n = p->N >= 256 ? 256 : 128;
-  a.n_tiles = (p->N + a.block_n - 1) / a.block_n;
+  a.block_n = a.N >= 256 ? 256 : 128;
+  a.n_tiles = (a.N + a.block_n - 1) / a.block_n;
   a.a_bytes = (a.block_n / 64) * kBoxBytes;
   a.stage_bytes = a.a_bytes + kBMaxBytes;
   a.stages = a.block_n == 256 ? 3 : 4;
@@ -248,7 +273,7 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.c_tiles = (p->C + a.block_c - 1) / a.block_c;
 
   // ---- pixel-block geometry and tensor maps ----
-  CUtensorMap map_dy, map_x;
+  CUtensorMap map_dy, map_x, map_dy2;
   const uint64_t ldx = static_cast<uint64_t>(p->ld_x) * 2, ldy = static_cast<uint64_t>(p->ld_dy) * 2;
   uint64_t dims[5], strides[4];
   uint32_t box[5];
@@ -302,7 +327,15 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
     strides[0] = ldy; strides[1] = static_cast<uint64_t>(Mtot) * ldy; strides[2] = strides[1]; strides[3] = strides[1];
     rc = encode_tensor_map(&map_dy, p->dy_dtype, 5, p->dy, dims, strides, box, true);
     if (rc) return rc;
+    if (p->dy2 != nullptr) {
+      const uint64_t ldy2 = static_cast<uint64_t>(p->ld_dy2) * 2;
+      dims[0] = p->N2;
+      strides[0] = ldy2; strides[1] = static_cast<uint64_t>(Mtot) * ldy2; strides[2] = strides[1]; strides[3] = strides[1];
+      rc = encode_tensor_map(&map_dy2, p->dy_dtype, 5, p->dy2, dims, strides, box, true);
+      if (rc) return rc;
+    }
   }
+  if (p->dy2 == nullptr) map_dy2 = map_dy;
   a.box_bytes = a.w_t * a.h_t * 128;
   a.x_tx_bytes = a.dw3 ? a.x_box_bytes : a.box_bytes;
   a.pix_blocks = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
@@ -325,7 +358,7 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
   const long long grid = items * a.splits;
   DFCSA_CHECK_ARG(grid < (1LL << 31), "conv_wgrad_tc: grid too large");
-  wgrad_tc_kernel<<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, a);
+  wgrad_tc_kernel<<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, map_dy2, a);
   DFCSA_LAUNCH_CHECK("wgrad_tc_kernel");
   return DFCSA_OK;
 }

@@ -48,6 +48,8 @@ class WgradParams(C.Structure):
         ("dy", C.c_void_p), ("ld_dy", C.c_int64), ("N", C.c_int32), ("dy_dtype", C.c_int32), ("dy_tap_mode", C.c_int32),
         ("dw", C.c_void_p), ("ld_dw", C.c_int64),
         ("alpha", C.c_void_p),
+        ("dy2", C.c_void_p), ("ld_dy2", C.c_int64), ("N2", C.c_int32), ("c_begin2", C.c_int32),
+        ("dw2", C.c_void_p), ("ld_dw2", C.c_int64), ("alpha2", C.c_void_p),
     ]
 
 

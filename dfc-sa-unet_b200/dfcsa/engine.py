@@ -363,9 +363,13 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=Tr
     return ctx
 
 
-def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None):
+def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None, second=None):
+    """second = (dy2, dw2, c_begin2, alpha2): another 1x1 weight gradient over the same x, same launch."""
     tc = ops.wgrad_tc_eligible(x, dy) and x.dtype == dy.dtype
-    ops.conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=alpha, backend=BACKEND_TC if tc else BACKEND_SIMT)
+    if second is not None:
+        dy2 = second[0]
+        tc = tc and ops.wgrad_tc_eligible(x, dy2) and dy2.dtype == dy.dtype and dy.shape[1] % 64 == 0 and second[2] % 32 == 0
+    ops.conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=alpha, backend=BACKEND_TC if tc else BACKEND_SIMT, second=second)
 
 
 def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
@@ -396,7 +400,6 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     segs = [(dF0, TAP_1x1)]
     df = dz[:, :C]
     ops.conv_gemm(B, H, W, segs, pk["wd4f"], C, df, backend=_backend(segs, pk["wd4f"], C, df))
-    _wgrad(B, H, W, ctx.zb, TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 3 * C))
     # gate / mix
     ops.gate_mix_bwd_reduce(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3)
     dG0 = _e((M, C), BF16, dev)
@@ -406,7 +409,9 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     dLA = dz[:, C:]
     segs = [(dF0, TAP_1x1), (dG0, TAP_1x1)]
     ops.conv_gemm(B, H, W, segs, pk["wd43"], 2 * C, dLA, backend=_backend(segs, pk["wd43"], 2 * C, dLA))
-    _wgrad(B, H, W, ctx.zb[:, C:], TAP_1x1, dG0, TAP_1x1, grads[bp.W3].view(C, 2 * C))
+    # fusion-conv and gate-conv weight gradients in one launch: both read z = [f | L | A] (the gate conv only L | A)
+    _wgrad(B, H, W, ctx.zb, TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 3 * C),
+           second=(dG0, grads[bp.W3].view(C, 2 * C), C, None))
     # branches (reduce1 first adds the gate-mix terms df*g / df*(1-g) into dL / dA in place)
     tmp = _e((B, H, P, C), F32, dev)
     d_o = _e((B * P * P, C), F32, dev)
@@ -427,9 +432,12 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     dW1p = _z((C, 9 * Ci), F32, dev)
     _wgrad(B, H, W, xw, TAP_3x3, dL0, TAP_1x1, dW1p)
     ops.permute3(dW1p, grads[bp.W1], (C, Ci, 9), (9 * Ci, 1, Ci))
-    _wgrad(B, H, W, xw, TAP_1x1, dA0, TAP_1x1, grads[bp.W2].view(C, Ci))
+    # attention-branch 1x1 conv and residual 1x1 conv weight gradients in one launch over the block input
     if bp.W5 is not None:
-        _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1))
+        _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1),
+               second=(dA0, grads[bp.W2].view(C, Ci), 0, None))
+    else:
+        _wgrad(B, H, W, xw, TAP_1x1, dA0, TAP_1x1, grads[bp.W2].view(C, Ci))
     # conv biases in front of a train-mode BatchNorm have exactly zero gradient: grads[...] stay zero
 
 

@@ -55,18 +55,26 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
                 f"stats={int(stats is not None)} out={str(out.dtype)[6:]} mode={out_mode}")
 
 
-def conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw, alpha=None, backend=BACKEND_TC):
-    """dw[n, t*C + c] += alpha * sum_m dy[., n] * x[., c]   (dfcsa_conv_wgrad); dw is a 2-D fp32 view."""
+def conv_wgrad(B, H, W, x, x_mode, dy, dy_mode, dw, alpha=None, backend=BACKEND_TC, second=None):
+    """dw[n, t*C + c] += alpha * sum_m dy[., n] * x[., c]   (dfcsa_conv_wgrad); dw is a 2-D fp32 view.
+    second = (dy2, dw2, c_begin2, alpha2): a second 1x1 gradient over the same x in the same launch."""
     p = L.WgradParams()
     p.B, p.H, p.W = B, H, W
     p.x, p.ld_x, p.C, p.x_dtype, p.x_tap_mode = x.data_ptr(), _mat(x), x.shape[1], L.dt(x), x_mode
     p.dy, p.ld_dy, p.N, p.dy_dtype, p.dy_tap_mode = dy.data_ptr(), _mat(dy), dy.shape[1], L.dt(dy), dy_mode
     p.dw, p.ld_dw = dw.data_ptr(), dw.stride(0)
     p.alpha = alpha.data_ptr() if alpha is not None else None
+    flops2 = 0.0
+    if second is not None:
+        dy2, dw2, c_begin2, alpha2 = second
+        p.dy2, p.ld_dy2, p.N2, p.c_begin2 = dy2.data_ptr(), _mat(dy2), dy2.shape[1], c_begin2
+        p.dw2, p.ld_dw2 = dw2.data_ptr(), dw2.stride(0)
+        p.alpha2 = alpha2.data_ptr() if alpha2 is not None else None
+        flops2 = 2.0 * B * H * W * (x.shape[1] - c_begin2) * dy2.shape[1]
     taps = 9 if x_mode == TAP_3x3 else (4 if dy_mode == TAP_2x2S2 else 1)
     L.call("dfcsa_conv_wgrad", C.byref(p), backend, L.stream(), tag="wgrad_tc" if backend == BACKEND_TC else "wgrad_simt",
-           flops=2.0 * B * H * W * taps * x.shape[1] * dy.shape[1],
-           desc=f"M={B * H * W} {H}x{W} N={dy.shape[1]} C={x.shape[1]} taps={taps}")
+           flops=2.0 * B * H * W * taps * x.shape[1] * dy.shape[1] + flops2,
+           desc=f"M={B * H * W} {H}x{W} N={dy.shape[1]}{'+' + str(second[0].shape[1]) if second is not None else ''} C={x.shape[1]} taps={taps}")
 
 
 def wgrad_tc_eligible(x, dy):

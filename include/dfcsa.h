@@ -100,6 +100,11 @@ typedef struct {
   const void* dy; int64_t ld_dy; int32_t N;  int32_t dy_dtype; int32_t dy_tap_mode;
   float*  dw; int64_t ld_dw;
   const float* alpha;       /* optional device scalar multiplier */
+  /* optional second gradient that reads the SAME x in the same launch (1x1 taps only), e.g. [W4 ; W3] over z or
+   * [W5 ; W2] over the block input:   dw2[n, c - c_begin2] += alpha2 * sum_m dy2[m, n] * x[m, c],  c_begin2 <= c < C */
+  const void* dy2; int64_t ld_dy2; int32_t N2; int32_t c_begin2;
+  float*  dw2; int64_t ld_dw2;
+  const float* alpha2;
 } dfcsa_wgrad_params_t;
 
 int dfcsa_conv_wgrad(const dfcsa_wgrad_params_t* p, int backend, void* stream);

@@ -229,3 +229,21 @@ def test_wgrad_small_channel_kernels(cuda, case):
     ops.conv_wgrad(B, H, W, x.reshape(-1, Cc), xm, dy.reshape(-1, N), 0, dw, alpha=torch.tensor([0.5], device=dev), backend=1)
     torch.cuda.synchronize()
     assert _rel_err(dw, ref) < 2e-3
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+@pytest.mark.parametrize("C,N1,N2,cb,M", [(192, 64, 64, 64, 1500), (384, 128, 128, 128, 700), (128, 64, 64, 0, 900), (768, 256, 256, 256, 300)])
+def test_conv_wgrad_two_gradients_one_launch(cuda, C, N1, N2, cb, M, backend):
+    """dw[n, c] += a1 * sum_m dy[m, n] x[m, c]  and  dw2[n, c - cb] += sum_m dy2[m, n] x[m, c] (c >= cb) in one call."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(M, C, generator=g).cuda().bfloat16()
+    dy = torch.randn(M, N1, generator=g).cuda().bfloat16()
+    dy2 = torch.randn(M, N2, generator=g).cuda().bfloat16()
+    alpha = torch.tensor([0.25], device=cuda)
+    dw = torch.zeros(N1, C, device=cuda)
+    dw2 = torch.zeros(N2, C - cb, device=cuda)
+    ops.conv_wgrad(1, 1, M, x, 0, dy, 0, dw, alpha=alpha, backend=backend, second=(dy2, dw2, cb, None))
+    torch.cuda.synchronize()
+    assert _rel_err(dw, 0.25 * dy.float().t() @ x.float()) < 2e-3
+    assert _rel_err(dw2, dy2.float().t() @ x.float()[:, cb:]) < 2e-3
