@@ -316,33 +316,39 @@ sgemm_kernel(const dfcsa_sgemm_params_t p) {
 // ---------------------------------------------------------------------------------------------
 // softmax rows (one warp per row) and backward
 // ---------------------------------------------------------------------------------------------
-__global__ void softmax_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int cols) {
+__global__ void softmax_rows_kernel(const float* __restrict__ x, void* __restrict__ y, int ydt, long long rows, int cols) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
   const float* xr = x + row * cols;
-  float* yr = y + row * cols;
-  float mx = -INFINITY;
-  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, xr[c]);
+  // one pass for (max, sum) with the online rescaling, one pass to write: the row is read twice, not three times
+  float mx = -INFINITY, sum = 0.f;
+  for (int c = lane; c < cols; c += 32) {
+    const float v = xr[c];
+    const float m2 = fmaxf(mx, v);
+    sum = sum * __expf(mx - m2) + __expf(v - m2);
+    mx = m2;
+  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  float sum = 0.f;
-  for (int c = lane; c < cols; c += 32) sum += expf(xr[c] - mx);
-  sum = warp_sum(sum);
+  for (int o = 16; o > 0; o >>= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, mx, o), so = __shfl_xor_sync(0xffffffffu, sum, o);
+    const float m2 = fmaxf(mx, mo);     // lanes without elements carry (-inf, 0): avoid exp(-inf - -inf)
+    sum = sum * (mx == m2 ? 1.f : __expf(mx - m2)) + so * (mo == m2 ? 1.f : __expf(mo - m2));
+    mx = m2;
+  }
   const float inv = 1.f / sum;
-  for (int c = lane; c < cols; c += 32) yr[c] = expf(xr[c] - mx) * inv;
+  for (int c = lane; c < cols; c += 32) st_any(y, row * cols + c, ydt, __expf(xr[c] - mx) * inv);
 }
-__global__ void softmax_rows_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
-                                        float* __restrict__ dx, long long rows, int cols) {
+__global__ void softmax_rows_bwd_kernel(const void* __restrict__ y, int ydt, const float* __restrict__ dy,
+                                        void* __restrict__ dx, int dxdt, long long rows, int cols) {
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  const float* yr = y + row * cols;
   const float* dr = dy + row * cols;
   float dot = 0.f;
-  for (int c = lane; c < cols; c += 32) dot += yr[c] * dr[c];
+  for (int c = lane; c < cols; c += 32) dot += ld_any(y, row * cols + c, ydt) * dr[c];
   dot = warp_sum(dot);
-  for (int c = lane; c < cols; c += 32) dx[row * cols + c] = yr[c] * (dr[c] - dot);
+  for (int c = lane; c < cols; c += 32) st_any(dx, row * cols + c, dxdt, ld_any(y, row * cols + c, ydt) * (dr[c] - dot));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -443,17 +449,20 @@ extern "C" int dfcsa_sgemm(const dfcsa_sgemm_params_t* p, void* stream) {
   return DFCSA_OK;
 }
 
-extern "C" int dfcsa_softmax_rows(const float* x, float* y, int64_t rows, int32_t cols, void* stream) {
-  DFCSA_CHECK_ARG(rows > 0 && cols > 0, "dfcsa_softmax_rows: empty");
-  const int wpb = 8;
-  softmax_rows_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(x, y, rows, cols);
+extern "C" int dfcsa_softmax_rows(const float* x, void* y, int y_dtype, int64_t rows, int32_t cols, void* stream) {
+  DFCSA_CHECK_ARG(x && y && rows > 0 && cols > 0 && x != y, "dfcsa_softmax_rows: bad args");
+  const long long blocks = (rows + 7) / 8;
+  DFCSA_CHECK_ARG(blocks < (1LL << 31), "dfcsa_softmax_rows: too many rows");
+  softmax_rows_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, y_dtype, rows, cols);
   DFCSA_LAUNCH_CHECK("softmax_rows_kernel");
   return DFCSA_OK;
 }
-extern "C" int dfcsa_softmax_rows_bwd(const float* y, const float* dy, float* dx, int64_t rows, int32_t cols, void* stream) {
-  DFCSA_CHECK_ARG(rows > 0 && cols > 0, "dfcsa_softmax_rows_bwd: empty");
-  const int wpb = 8;
-  softmax_rows_bwd_kernel<<<static_cast<unsigned>((rows + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(y, dy, dx, rows, cols);
+extern "C" int dfcsa_softmax_rows_bwd(const void* y, int y_dtype, const float* dy, void* dx, int dx_dtype, int64_t rows,
+                                      int32_t cols, void* stream) {
+  DFCSA_CHECK_ARG(y && dy && dx && rows > 0 && cols > 0, "dfcsa_softmax_rows_bwd: bad args");
+  const long long blocks = (rows + 7) / 8;
+  DFCSA_CHECK_ARG(blocks < (1LL << 31), "dfcsa_softmax_rows_bwd: too many rows");
+  softmax_rows_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, y_dtype, dy, dx, dx_dtype, rows, cols);
   DFCSA_LAUNCH_CHECK("softmax_rows_bwd_kernel");
   return DFCSA_OK;
 }

@@ -229,20 +229,34 @@ def _attn_chunk(B, N):
 
 
 def _attn_probs(qkv, nb, N, Cq, nq, out):
-    """out[b] = softmax_j(q_i . k_j) for nb images; qkv: [nb*N, nq] fp32 rows (q | k | v)."""
+    """out[b] = softmax_j(q_i . k_j) for nb images; qkv: [nb*N, nq] rows (q | k | v).  fp32 qkv -> fp32 SIMT product;
+    fp16 qkv -> tcgen05 batched GEMM (out is then usually fp16 too)."""
     S = _e((nb, N, N), F32, qkv.device)
-    ops.sgemm(nb, N, N, Cq, qkv[:, :Cq], (N * nq, nq, 1), qkv[:, Cq:2 * Cq], (N * nq, 1, nq), S, (N * N, N, 1))
+    if qkv.dtype == F32:
+        ops.sgemm(nb, N, N, Cq, qkv[:, :Cq], (N * nq, nq, 1), qkv[:, Cq:2 * Cq], (N * nq, 1, nq), S, (N * N, N, 1))
+    else:
+        ops.bgemm(nb, N, N, Cq, qkv[:, :Cq], N * nq, nq, False, qkv[:, Cq:2 * Cq], N * nq, nq, False, S, N * N, N)
     ops.softmax_rows(S, out)
+
+
+_ATTN_TC_MIN_N = 64      # below this the attention products are a few KFLOP per image: fp32 FMA, no tensor cores
+
+
+def _attn_tc(bp, N):
+    return bp.C % 64 == 0 and N >= _ATTN_TC_MIN_N and N % 8 == 0
 
 
 def attention_forward(bp, pk, pooled, B, N, ctx=None):
     """q/k/v 1x1 convs (ONE tensor-core GEMM over [Wq ; Wk ; Wv]), softmax(q k^T), attn v on the pooled map
-    [B*N, C] (reference :28-34).  pooled is fp32; the GEMM reads an fp16 copy."""
+    [B*N, C] (reference :28-34).  pooled is fp32; the GEMM reads an fp16 copy.  For N >= 64 (pool_size >= 8 and
+    the full-resolution attention of ablation 3) q k^T and attn v run as tcgen05 batched GEMMs on fp16 copies of
+    q / k / v with the probabilities stored in fp16."""
     dev = pooled.device
     C, Cq = bp.C, bp.Cq
     BN = B * N
     nq = 2 * Cq + C
     tc = C % 64 == 0
+    tca = _attn_tc(bp, N)
     p16 = pooled
     if tc:
         p16 = _e((BN, C), F16, dev)
@@ -250,19 +264,28 @@ def attention_forward(bp, pk, pooled, B, N, ctx=None):
     qkv = _e((BN, nq), F32, dev)
     segs = [(p16, TAP_1x1)]
     ops.conv_gemm(1, 1, BN, segs, pk["wqkv"], nq, qkv, bias=pk["bqkv"], backend=_backend(segs, pk["wqkv"], nq, qkv))
+    qsrc = qkv
+    if tca:
+        qsrc = _e((BN, nq), F16, dev)
+        ops.cast2d(qkv, qsrc)
     # softmax(q k^T) v, a few images at a time when [N, N] is large (full-resolution attention: N = H*W)
-    keep_attn = ctx is not None and B * N * N * 4 <= _ATTN_SAVE_BYTES
-    attn = _e((B, N, N), F32, dev) if keep_attn else None
+    adt = F16 if tca else F32
+    keep_attn = ctx is not None and B * N * N * (2 if tca else 4) <= _ATTN_SAVE_BYTES
+    attn = _e((B, N, N), adt, dev) if keep_attn else None
     o = _e((B, N, C), F32, dev)
     ch = _attn_chunk(B, N)
     for b0 in range(0, B, ch):
         nb = min(ch, B - b0)
-        A = attn[b0:b0 + nb] if keep_attn else _e((nb, N, N), F32, dev)
-        _attn_probs(qkv[b0 * N:(b0 + nb) * N], nb, N, Cq, nq, A)
-        v = qkv[b0 * N:(b0 + nb) * N, 2 * Cq:]
-        ops.sgemm(nb, N, C, N, A, (N * N, N, 1), v, (N * nq, nq, 1), o[b0:b0 + nb], (N * C, C, 1))   # o[i,c] = sum_j attn[i,j] v[j,c]
+        rows = slice(b0 * N, (b0 + nb) * N)
+        A = attn[b0:b0 + nb] if keep_attn else _e((nb, N, N), adt, dev)
+        _attn_probs(qsrc[rows], nb, N, Cq, nq, A)
+        v = qsrc[rows, 2 * Cq:]
+        if tca:     # o[i,c] = sum_j attn[i,j] v[j,c]: A K-major, V read MN-major (rows = keys)
+            ops.bgemm(nb, N, C, N, A, N * N, N, False, v, N * nq, nq, True, o[b0:b0 + nb], N * C, C)
+        else:
+            ops.sgemm(nb, N, C, N, A, (N * N, N, 1), v, (N * nq, nq, 1), o[b0:b0 + nb], (N * C, C, 1))
     if ctx is not None:
-        ctx.qkv, ctx.attn = qkv, attn
+        ctx.qkv, ctx.attn, ctx.qkv16 = qkv, attn, (qsrc if tca else None)
         ctx.pooled_w = pooled
         if tc:
             ctx.pooled_w = _e((BN, C), BF16, dev)      # weight-gradient operand
@@ -276,28 +299,48 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
     C, Cq = bp.C, bp.Cq
     BN = B * N
     nq = 2 * Cq + C
+    tca = _attn_tc(bp, N)
     qkv, attn = ctx.qkv, ctx.attn
     dqkv = _e((BN, nq), F32, dev)
+    if tca:
+        qkvb, dob = _e((BN, nq), BF16, dev), _e((BN, C), BF16, dev)     # gradient-side operands are bf16
+        ops.cast2d(qkv, qkvb)
+        ops.cast2d(d_o, dob)
     ch = _attn_chunk(B, N)
     for b0 in range(0, B, ch):
         nb = min(ch, B - b0)
         rows = slice(b0 * N, (b0 + nb) * N)
-        q, k, v = qkv[rows, :Cq], qkv[rows, Cq:2 * Cq], qkv[rows, 2 * Cq:]
         dq, dk, dv = dqkv[rows, :Cq], dqkv[rows, Cq:2 * Cq], dqkv[rows, 2 * Cq:]
         if attn is not None:
             A = attn[b0:b0 + nb]
         else:                                  # not saved (too large): recompute the probabilities
-            A = _e((nb, N, N), F32, dev)
-            _attn_probs(qkv[rows], nb, N, Cq, nq, A)
-        do = d_o[rows]
-        ops.sgemm(nb, N, C, N, A, (N * N, 1, N), do, (N * C, C, 1), dv, (N * nq, nq, 1))       # dv[j,c] = sum_i attn[i,j] do[i,c]
-        dattn = _e((nb, N, N), F32, dev)
-        ops.sgemm(nb, N, N, C, do, (N * C, C, 1), v, (N * nq, 1, nq), dattn, (N * N, N, 1))     # dattn[i,j] = sum_c do[i,c] v[j,c]
-        dS = _e((nb, N, N), F32, dev)
-        ops.softmax_rows_bwd(A, dattn, dS)
-        del dattn
-        ops.sgemm(nb, N, Cq, N, dS, (N * N, N, 1), k, (N * nq, nq, 1), dq, (N * nq, nq, 1))    # dq[i,c] = sum_j dS[i,j] k[j,c]
-        ops.sgemm(nb, N, Cq, N, dS, (N * N, 1, N), q, (N * nq, nq, 1), dk, (N * nq, nq, 1))    # dk[j,c] = sum_i dS[i,j] q[i,c]
+            A = _e((nb, N, N), F16 if tca else F32, dev)
+            _attn_probs((ctx.qkv16 if tca else qkv)[rows], nb, N, Cq, nq, A)
+        if tca:
+            q, k, v = qkvb[rows, :Cq], qkvb[rows, Cq:2 * Cq], qkvb[rows, 2 * Cq:]
+            do = dob[rows]
+            Ab = _e((nb, N, N), BF16, dev)
+            ops.cast2d(A.view(nb * N, N), Ab.view(nb * N, N))
+            ops.bgemm(nb, N, C, N, Ab, N * N, N, True, do, N * C, C, True, dv, N * nq, nq)         # dv[j,c] = sum_i attn[i,j] do[i,c]
+            del Ab
+            dattn = _e((nb, N, N), F32, dev)
+            ops.bgemm(nb, N, N, C, do, N * C, C, False, v, N * nq, nq, False, dattn, N * N, N)     # dattn[i,j] = sum_c do[i,c] v[j,c]
+            dS = _e((nb, N, N), BF16, dev)
+            ops.softmax_rows_bwd(A, dattn, dS)
+            del dattn
+            ops.bgemm(nb, N, Cq, N, dS, N * N, N, False, k, N * nq, nq, True, dq, N * nq, nq)      # dq[i,c] = sum_j dS[i,j] k[j,c]
+            ops.bgemm(nb, N, Cq, N, dS, N * N, N, True, q, N * nq, nq, True, dk, N * nq, nq)       # dk[j,c] = sum_i dS[i,j] q[i,c]
+        else:
+            q, k, v = qkv[rows, :Cq], qkv[rows, Cq:2 * Cq], qkv[rows, 2 * Cq:]
+            do = d_o[rows]
+            ops.sgemm(nb, N, C, N, A, (N * N, 1, N), do, (N * C, C, 1), dv, (N * nq, nq, 1))       # dv[j,c] = sum_i attn[i,j] do[i,c]
+            dattn = _e((nb, N, N), F32, dev)
+            ops.sgemm(nb, N, N, C, do, (N * C, C, 1), v, (N * nq, 1, nq), dattn, (N * N, N, 1))     # dattn[i,j] = sum_c do[i,c] v[j,c]
+            dS = _e((nb, N, N), F32, dev)
+            ops.softmax_rows_bwd(A, dattn, dS)
+            del dattn
+            ops.sgemm(nb, N, Cq, N, dS, (N * N, N, 1), k, (N * nq, nq, 1), dq, (N * nq, nq, 1))    # dq[i,c] = sum_j dS[i,j] k[j,c]
+            ops.sgemm(nb, N, Cq, N, dS, (N * N, 1, N), q, (N * nq, nq, 1), dk, (N * nq, nq, 1))    # dk[j,c] = sum_i dS[i,j] q[i,c]
         del dS, A
     dq, dk, dv = dqkv[:, :Cq], dqkv[:, Cq:2 * Cq], dqkv[:, 2 * Cq:]
     for b, d in ((bp.bq, dq), (bp.bk, dk), (bp.bv, dv)):

@@ -109,13 +109,28 @@ def sgemm(batch, M, N, K, A, a_str, Bm, b_str, Cm, c_str, alpha=1.0, beta=0.0, b
 
 
 def softmax_rows(x, y):
+    """y = softmax(x) along the last dim; x fp32, y fp32 / fp16 / bf16."""
     rows, cols = x.numel() // x.shape[-1], x.shape[-1]
-    L.call("dfcsa_softmax_rows", L.ptr(x), L.ptr(y), C.c_int64(rows), cols, L.stream())
+    L.call("dfcsa_softmax_rows", L.ptr(x), L.ptr(y), L.dt(y), C.c_int64(rows), cols, L.stream())
 
 
 def softmax_rows_bwd(y, dy, dx):
+    """dx = y * (dy - rowsum(dy * y)); y fp32 / 16-bit, dy fp32, dx fp32 / 16-bit."""
     rows, cols = y.numel() // y.shape[-1], y.shape[-1]
-    L.call("dfcsa_softmax_rows_bwd", L.ptr(y), L.ptr(dy), L.ptr(dx), C.c_int64(rows), cols, L.stream())
+    L.call("dfcsa_softmax_rows_bwd", L.ptr(y), L.dt(y), L.ptr(dy), L.ptr(dx), L.dt(dx), C.c_int64(rows), cols, L.stream())
+
+
+def bgemm(batch, M, N, K, A, a_b, ld_a, a_mn, Bm, b_b, ld_b, b_mn, Cm, c_b, ld_c):
+    """C[b] = A[b] @ B[b] on tcgen05 (dfcsa_bgemm); operands 16-bit of one dtype, K-major or MN-major (see dfcsa.h)."""
+    p = L.BgemmParams()
+    p.batch, p.M, p.N, p.K = batch, M, N, K
+    p.A, p.a_b, p.ld_a, p.a_mn_major = A.data_ptr(), a_b, ld_a, 1 if a_mn else 0
+    p.B, p.b_b, p.ld_b, p.b_mn_major = Bm.data_ptr(), b_b, ld_b, 1 if b_mn else 0
+    p.ab_dtype = L.dt(A)
+    assert A.dtype == Bm.dtype
+    p.C, p.c_b, p.ld_c, p.c_dtype = Cm.data_ptr(), c_b, ld_c, L.dt(Cm)
+    L.call("dfcsa_bgemm", C.byref(p), L.stream(), tag="bgemm_tc", flops=2.0 * batch * M * N * K,
+           desc=f"b={batch} M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)}")
 
 
 def _i64(v):

@@ -141,9 +141,26 @@ typedef struct {
 } dfcsa_sgemm_params_t;
 int dfcsa_sgemm(const dfcsa_sgemm_params_t* p, void* stream);
 
-/* row softmax over the last dim (reference :31) and its backward  dS = A * (dA - rowsum(dA*A)) */
-int dfcsa_softmax_rows(const float* x, float* y, int64_t rows, int32_t cols, void* stream);
-int dfcsa_softmax_rows_bwd(const float* y, const float* dy, float* dx, int64_t rows, int32_t cols, void* stream);
+/* row softmax over the last dim (reference :31) and its backward  dS = A * (dA - rowsum(dA*A)).
+ * x / dy are fp32; y (and dx) may be fp32, fp16 or bf16 (the 16-bit forms feed the tensor-core attention GEMMs). */
+int dfcsa_softmax_rows(const float* x, void* y, int y_dtype, int64_t rows, int32_t cols, void* stream);
+int dfcsa_softmax_rows_bwd(const void* y, int y_dtype, const float* dy, void* dx, int dx_dtype, int64_t rows, int32_t cols,
+                           void* stream);
+
+/* Batched GEMM on tcgen05:  C[b] = A[b] * B[b],  b < batch,  A: M x K, B: K x N (as a matrix product), 16-bit operands of
+ * one dtype, fp32 accumulation.  Storage of an operand is either K-major (element (m,k) at base + b*a_b + m*ld_a + k)
+ * or MN-major (element (m,k) at base + b*a_b + k*ld_a + m): transposes are free.  C is row-major [M, N] with pitch ld_c.
+ * Used for the attention products softmax(Q K^T) V and their backward (reference models/unet_dfc_sa_res.py:30-33,
+ * models/unet_dfc_sa_ablation_attention.py:20-24) whenever N = P*P >= 64.  Pitches / batch strides in elements,
+ * multiples of 8; N % 8 == 0. */
+typedef struct {
+  int32_t batch, M, N, K;
+  const void* A; int64_t a_b, ld_a; int32_t a_mn_major;
+  const void* B; int64_t b_b, ld_b; int32_t b_mn_major;
+  int32_t ab_dtype;
+  void* C; int64_t c_b, ld_c; int32_t c_dtype;
+} dfcsa_bgemm_params_t;
+int dfcsa_bgemm(const dfcsa_bgemm_params_t* p, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BatchNorm2d (reference :60,67,75,82; ATen batch_norm semantics: biased variance for normalisation, unbiased

@@ -247,3 +247,51 @@ def test_conv_wgrad_two_gradients_one_launch(cuda, C, N1, N2, cb, M, backend):
     torch.cuda.synchronize()
     assert _rel_err(dw, 0.25 * dy.float().t() @ x.float()) < 2e-3
     assert _rel_err(dw2, dy2.float().t() @ x.float()[:, cb:]) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16], ids=["f16", "bf16"])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("batch,M,N,K", [(3, 200, 72, 8), (2, 256, 320, 256), (1, 130, 64, 200), (2, 64, 8, 64)])
+def test_bgemm_all_layouts(cuda, batch, M, N, K, a_mn, b_mn, dtype):
+    """dfcsa_bgemm: C[b] = A[b] @ B[b] with either operand stored K-major or MN-major, ragged M / K, tiny K and N."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(13)
+    A = torch.randn(batch, M, K, generator=g).cuda().to(dtype)
+    Bm = torch.randn(batch, K, N, generator=g).cuda().to(dtype)
+    ref = torch.bmm(A.float(), Bm.float())
+    pad = lambda n: (n + 7) // 8 * 8       # pitches must be multiples of 8 elements
+    if a_mn:       # stored [K, M]
+        As = torch.zeros(batch, K, pad(M), device=cuda, dtype=dtype); As[:, :, :M] = A.transpose(1, 2)
+        a_b, ld_a = K * pad(M), pad(M)
+    else:          # stored [M, K]
+        As = torch.zeros(batch, M, pad(K), device=cuda, dtype=dtype); As[:, :, :K] = A
+        a_b, ld_a = M * pad(K), pad(K)
+    if b_mn:       # stored [K, N]
+        Bs = torch.zeros(batch, K, pad(N), device=cuda, dtype=dtype); Bs[:, :, :N] = Bm
+        b_b, ld_b = K * pad(N), pad(N)
+    else:          # stored [N, K]
+        Bs = torch.zeros(batch, N, pad(K), device=cuda, dtype=dtype); Bs[:, :, :K] = Bm.transpose(1, 2)
+        b_b, ld_b = N * pad(K), pad(K)
+    for cdt, tol in ((torch.float32, 2e-3), (dtype, 1.2e-2)):
+        Cm = torch.full((batch, M, N), float("nan"), device=cuda, dtype=cdt)
+        ops.bgemm(batch, M, N, K, As, a_b, ld_a, a_mn, Bs, b_b, ld_b, b_mn, Cm, M * N, N)
+        torch.cuda.synchronize()
+        assert _rel_err(Cm, ref) < tol
+
+
+@pytest.mark.parametrize("cols", [16, 100, 4096])
+def test_softmax_rows_16bit(cuda, cols):
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(17)
+    x = (torch.randn(37, cols, generator=g) * 4).cuda()
+    ref = torch.softmax(x, -1)
+    for dt, tol in ((torch.float32, 1e-5), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)):
+        y = torch.empty(37, cols, device=cuda, dtype=dt)
+        ops.softmax_rows(x, y)
+        assert _rel_err(y, ref) < tol
+        dy = torch.randn(37, cols, generator=g).cuda()
+        dref = ref * (dy - (dy * ref).sum(-1, keepdim=True))
+        for ddt, dtol in ((torch.float32, 2e-2 if dt != torch.float32 else 1e-5), (torch.bfloat16, 2e-2)):
+            dx = torch.empty(37, cols, device=cuda, dtype=ddt)
+            ops.softmax_rows_bwd(y, dy, dx)
+            assert _rel_err(dx, dref) < dtol
