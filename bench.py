@@ -206,9 +206,10 @@ def run_dfcsa(args):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     loss_host = 0.0
-    for i in range(args.steps):
-        img = host[i % 2][0].to(dev, non_blocking=True)
-        msk = host[i % 2][1].to(dev, non_blocking=True)
+    # every step's images + masks cross PCIe inside the timed region; dfcsa.trainer.device_feeder (what Trainer.train_epoch
+    # uses) stages batch i+1 on a copy stream while batch i trains
+    from dfcsa.trainer import device_feeder
+    for img, msk in device_feeder((host[i % 2] for i in range(args.steps)), dev):
         r = tr.train_step(img, msk)
         loss_host = r.stats[:1].cpu().item()          # device -> host read of the step's loss
     t1.record()

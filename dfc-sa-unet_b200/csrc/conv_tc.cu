@@ -38,6 +38,9 @@ struct ConvTcArgs {
   int n_tiles_n, block_n, N;
   int stages;
   int kbs;          // K blocks (of 64) per pipeline stage: 2 for narrow tiles so one barrier round-trip feeds 8 MMAs
+  int dw3;          // 3x3 segments load ONE halo box (10 x 16 pixels) per kernel row and K block and read the three dw
+                    // taps from it through UMMA descriptors shifted by 128 bytes (pixel patch 8 x 16, SBO = 10 rows)
+  int stage_bytes;
   int a_box_bytes;  // bytes one activation TMA delivers
   void* out;
   long long ld_out;
@@ -126,8 +129,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int kb_bytes = kABytes + a.block_n * 128;
-  const int stage_bytes = a.kbs * kb_bytes;
+  const int stage_bytes = a.stage_bytes;
   const int total_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.n_tiles_n;
 
   // Rows a partial activation box never writes must read as zero for the MMA.
@@ -162,6 +164,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const uint32_t kb_tx = static_cast<uint32_t>(a.a_box_bytes + a.block_n * 128);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(a, tile);
+      if (a.dw3) {
+        constexpr int kHaloBytes = 10 * 16 * 128;      // 20 KiB: (8 + 2) x 16 pixels x 64 channels
+        const int bn_bytes = a.block_n * 128;
+        int k_base = 0;                                 // K offset (in 64-blocks) of the current segment in the packed weights
+        for (int s = 0; s < a.n_seg; ++s) {
+          const CUtensorMap* ma = (s == 0) ? &map_a0 : (s == 1) ? &map_a1 : &map_a2;
+          const bool m3 = a.seg_mode[s] == DFCSA_TAP_3x3;
+          const int rows = m3 ? 3 : 1;
+          for (int dh = 0; dh < rows; ++dh) {
+            for (int kb = 0; kb < a.seg_kb[s]; ++kb) {
+              if (lane == 0) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + kHaloBytes;
+                if (m3) {
+                  mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kHaloBytes + 3 * bn_bytes));
+                  tma_load_5d(sa, ma, &full_bar[stage], kb * kBlockK, tc.w0 - 1, tc.h0 + dh - 1, tc.tb, 0);
+                  for (int dw = 0; dw < 3; ++dw)
+                    tma_load_2d(sb + dw * bn_bytes, &map_b, &full_bar[stage],
+                                (k_base + (dh * 3 + dw) * a.seg_kb[s] + kb) * kBlockK, tc.nt * a.block_n);
+                } else {
+                  mbar_arrive_expect_tx(&full_bar[stage], static_cast<uint32_t>(kABytes + bn_bytes));
+                  tma_load_5d(sa, ma, &full_bar[stage], kb * kBlockK, tc.w0, tc.h0, tc.tb, 0);
+                  tma_load_2d(sb, &map_b, &full_bar[stage], (k_base + kb) * kBlockK, tc.nt * a.block_n);
+                }
+              }
+              __syncwarp();
+              if (++stage == a.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          k_base += (m3 ? 9 : 1) * a.seg_kb[s];
+        }
+        continue;
+      }
       int kb_global = 0, sub = 0;
       for (int s = 0; s < a.n_seg; ++s) {
         const CUtensorMap* ma = (s == 0) ? &map_a0 : (s == 1) ? &map_a1 : &map_a2;
@@ -201,6 +237,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
+      if (a.dw3) {
+        constexpr int kHaloBytes = 10 * 16 * 128;
+        const int bn_bytes = a.block_n * 128;
+        int items = 0;
+        for (int s = 0; s < a.n_seg; ++s) items += (a.seg_mode[s] == DFCSA_TAP_3x3 ? 3 : 1) * a.seg_kb[s];
+        int it = 0;
+        for (int s = 0; s < a.n_seg; ++s) {
+          const bool m3 = a.seg_mode[s] == DFCSA_TAP_3x3;
+          const int n_it = (m3 ? 3 : 1) * a.seg_kb[s];
+          for (int j = 0; j < n_it; ++j, ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
+              const uint32_t b_addr = a_addr + kHaloBytes;
+              if (m3) {
+                for (int dw = 0; dw < 3; ++dw) {
+#pragma unroll
+                  for (int k = 0; k < kBlockK / 16; ++k) {
+                    // patch row g = 8 consecutive pixels = one 8-row core group; groups are 10 box rows apart
+                    const uint64_t da = umma_smem_desc(a_addr + dw * 128 + k * 32, 16, 1280);
+                    const uint64_t db = umma_smem_desc(b_addr + dw * bn_bytes + k * 32, 16, 1024);
+                    umma_f16(d_tmem, da, db, a.idesc, (it | dw | k) != 0 ? 1u : 0u);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+                  const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+                  umma_f16(d_tmem, da, db, a.idesc, (it | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (it + 1 == items) umma_commit(&tmem_full_bar[as]);
+            }
+            __syncwarp();
+            if (++stage == a.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        as ^= 1; if (as == 0) aphase ^= 1;
+        continue;
+      }
       for (int kb = 0; kb < a.total_kb; kb += a.kbs) {
         const int nsub = min(a.kbs, a.total_kb - kb);
         mbar_wait(&full_bar[stage], phase);
@@ -385,10 +464,23 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   a.n_seg = p->n_seg;
   a.total_kb = ktot / 64;
   a.N = p->N;
+  // ---- n tiling (needed first: the halo-box variant of the 3x3 path needs block_n <= 128) ----
+  const int sms = num_sms();
+  int block_n;
+  if (p->N <= 256) block_n = (p->N + 31) / 32 * 32;
+  else {
+    int best_pad = 1 << 30; block_n = 256;
+    for (int bn = 256; bn >= 128; bn -= 32) {
+      int pad = (p->N + bn - 1) / bn * bn;
+      if (pad < best_pad) { best_pad = pad; block_n = bn; }
+    }
+  }
+  a.dw3 = (any3 && !any2 && block_n <= 128) ? 1 : 0;
   // ---- tile geometry ----
   if (any3) {
     a.H = p->H; a.W = p->W; a.tiles_b = p->B;
-    pick_spatial_tile(p->H, p->W, a.w_t, a.h_t);
+    if (a.dw3) { a.w_t = 8; a.h_t = 16; }
+    else pick_spatial_tile(p->H, p->W, a.w_t, a.h_t);
   } else if (any2) {
     a.H = p->B * p->H; a.W = p->W; a.tiles_b = 1;
     pick_spatial_tile(a.H, a.W, a.w_t, a.h_t);
@@ -401,22 +493,17 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   a.a_box_bytes = a.w_t * a.h_t * 128;
   const long long m_tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
 
-  // ---- n tiling ----
-  const int sms = num_sms();
-  int block_n;
-  if (p->N <= 256) block_n = (p->N + 31) / 32 * 32;
-  else {
-    int best_pad = 1 << 30; block_n = 256;
-    for (int bn = 256; bn >= 128; bn -= 32) {
-      int pad = (p->N + bn - 1) / bn * bn;
-      if (pad < best_pad) { best_pad = pad; block_n = bn; }
-    }
-  }
-  while (block_n > 64 && block_n % 64 == 0 && m_tiles * ((p->N + block_n - 1) / block_n) < sms) block_n /= 2;
+  while (!a.dw3 && block_n > 64 && block_n % 64 == 0 && m_tiles * ((p->N + block_n - 1) / block_n) < sms) block_n /= 2;
   a.block_n = block_n;
   a.n_tiles_n = (p->N + block_n - 1) / block_n;
-  a.kbs = (block_n <= 128 && a.total_kb >= 2) ? 2 : 1;
-  const int stage_bytes = a.kbs * (kABytes + block_n * 128);
+  if (a.dw3) {
+    a.kbs = 1;
+    a.stage_bytes = 10 * 16 * 128 + 3 * block_n * 128;
+  } else {
+    a.kbs = (block_n <= 128 && a.total_kb >= 2) ? 2 : 1;
+    a.stage_bytes = a.kbs * (kABytes + block_n * 128);
+  }
+  const int stage_bytes = a.stage_bytes;
   a.stages = std::min(kMaxStages, (kSmemBudget - 1024) / stage_bytes);
   a.idesc = umma_idesc_f16(kBlockM, block_n, umma_fmt(p->src_dtype), umma_fmt(p->w_dtype), 0, 0);
 
@@ -438,7 +525,7 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
       dims[0] = sg.channels; dims[1] = p->W; dims[2] = p->H; dims[3] = p->B; dims[4] = 1;
       strides[0] = ldb; strides[1] = static_cast<uint64_t>(p->W) * ldb; strides[2] = static_cast<uint64_t>(p->H) * p->W * ldb;
       strides[3] = static_cast<uint64_t>(p->B) * p->H * p->W * ldb;
-      box[0] = 64; box[1] = a.w_t; box[2] = a.h_t; box[3] = 1; box[4] = 1;
+      box[0] = 64; box[1] = (a.dw3 && sg.tap_mode == DFCSA_TAP_3x3) ? a.w_t + 2 : a.w_t; box[2] = a.h_t; box[3] = 1; box[4] = 1;
     } else {
       dims[0] = sg.channels; dims[1] = static_cast<uint64_t>(Mtot); dims[2] = 1; dims[3] = 1; dims[4] = 1;
       strides[0] = ldb; strides[1] = static_cast<uint64_t>(Mtot) * ldb; strides[2] = strides[1]; strides[3] = strides[1];

@@ -38,6 +38,39 @@ def reduce_buckets(net):
     return [[p for m in mods for p in m.parameters()] for mods in bucket_modules(net)]
 
 
+def device_feeder(batches, device):
+    """Yields (images, masks) on the device with ONE batch of look-ahead: the host->device copy of batch i+1 runs on a
+    copy stream while batch i trains (the reference copies synchronously inside the loop, utils/trainer.py:116-117).
+    `batches` yields (images, masks) host tensors (pinned memory makes the copies asynchronous)."""
+    device = torch.device(device)
+    copy_stream = torch.cuda.Stream(device=device)
+
+    def stage(pair):
+        with torch.cuda.stream(copy_stream):
+            img = pair[0].to(device, non_blocking=True)
+            msk = pair[1].to(device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return img, msk, ev
+
+    it = iter(batches)
+    try:
+        nxt = stage(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        img, msk, ev = nxt
+        cur = torch.cuda.current_stream(device)
+        cur.wait_event(ev)
+        img.record_stream(cur)
+        msk.record_stream(cur)
+        try:
+            nxt = stage(next(it))
+        except StopIteration:
+            nxt = None
+        yield img, msk
+
+
 class Trainer:
     def __init__(self, model, train_loader, val_loader, optimizer, device, config, log_every=10):
         self.config = config
@@ -130,9 +163,7 @@ class Trainer:
     def train_epoch(self, epoch):
         running = torch.zeros(5, dtype=torch.float32, device=self.device)
         nb = 0
-        for batch in self.train_loader:
-            images = batch["image"].to(self.device, non_blocking=True)
-            masks = batch["mask"].to(self.device, non_blocking=True)
+        for images, masks in device_feeder(((b["image"], b["mask"]) for b in self.train_loader), self.device):
             r = self.train_step(images, masks)
             running += r.stats
             nb += 1
