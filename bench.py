@@ -161,9 +161,12 @@ def run_dfcsa(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The step is replayed from a CUDA graph (Trainer.train_step_graphed, captured during warm-up): eager, the ~500
+    # launches of a step cost ~35 ms of host time against ~45 ms of GPU time, too close to hide reliably.
+    step = tr.train_step if args.no_graph else tr.train_step_graphed
     # ---------------- warm-up ----------------
     for i in range(max(args.warmup, 3)):
-        tr.train_step(*devb[i % 2])
+        step(*devb[i % 2])
     barrier()
 
     # ---------------- timed: inputs resident in HBM (no per-call instrumentation) ----------------
@@ -174,7 +177,7 @@ def run_dfcsa(args):
     e0.record()
     last = None
     for i in range(args.steps):
-        last = tr.train_step(*devb[i % 2])
+        last = step(*devb[i % 2])
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -206,11 +209,11 @@ def run_dfcsa(args):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     loss_host = 0.0
-    # every step's images + masks cross PCIe inside the timed region; dfcsa.trainer.device_feeder (what Trainer.train_epoch
-    # uses) stages batch i+1 on a copy stream while batch i trains
-    from dfcsa.trainer import device_feeder
-    for img, msk in device_feeder((host[i % 2] for i in range(args.steps)), dev):
-        r = tr.train_step(img, msk)
+    # every step's images + masks cross PCIe inside the timed region (pinned host -> the step's input buffers) and the
+    # loss comes back to the host
+    for i in range(args.steps):
+        r = step(*host[i % 2]) if not args.no_graph else tr.train_step(host[i % 2][0].to(dev, non_blocking=True),
+                                                                      host[i % 2][1].to(dev, non_blocking=True))
         loss_host = r.stats[:1].cpu().item()          # device -> host read of the step's loss
     t1.record()
     barrier()
@@ -245,7 +248,7 @@ def run_dfcsa(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "img": IMG, "pool_size": POOL,
-                       "parallelism": f"dp{world}" if world > 1 else "single",
+                       "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": not args.no_graph,
                        "l2": "activations touched per step (~20 GB at batch 64) exceed the 126 MB L2; two alternating input batches; no explicit flush"},
             "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4, "last_loss": loss_host},
@@ -260,9 +263,19 @@ def run_dfcsa(args):
             "cpu_baseline": cpu,
             "last_step": last.host() if last is not None else None,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing NCCL down: destroy_process_group() with a captured CUDA graph that still holds the
+        # communicator's kernels did not return on this stack (measured: the 2-GPU run printed its line and then sat
+        # until the job limit).  Every rank has finished its work and rank 0 has printed; a barrier, then a hard exit 0.
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -273,6 +286,7 @@ def main():
     ap.add_argument("--impl", default="dfcsa", choices=["dfcsa", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (default: the BASELINE config, 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--detail", default=None, help="write per-shape GEMM timings (JSON) to this path")
     args = ap.parse_args()
     if args.impl == "reference":
