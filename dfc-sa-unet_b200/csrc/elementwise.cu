@@ -4,6 +4,7 @@
 // Every kernel walks NHWC so that consecutive threads touch consecutive 16-byte channel vectors of a pixel.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace dfcsa {
 namespace {
@@ -125,6 +126,25 @@ __device__ __forceinline__ void block_scalar_reduce_add(float v, double* out) {
     if (lane == 0) atomicAdd(out, static_cast<double>(t));
   }
 }
+
+// Resident CTAs per SM each heavy streaming kernel is compiled for (register cap 65536 / (256 * occ)).  Measured on
+// B200 per kernel (profiles/README.md): the kernels with many live vectors (branch_bwd_reduce1 / reduce2 / apply) are
+// fastest at 2 (128 registers, no spills), the gate kernels at 3, block_out_bwd_reduce at 4.  DFCSA_EW_OCC overrides
+// all of them for experiments.
+static int ew_occ(int dflt) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("DFCSA_EW_OCC");
+    forced = e ? atoi(e) : 0;
+    if (forced < 2 || forced > 4) forced = 0;
+  }
+  return forced ? forced : dflt;
+}
+#define OCC_DISPATCH(dflt, ...)                                                  \
+  do { const int occ__ = ew_occ(dflt);                                           \
+       if (occ__ == 2) { constexpr int OCC = 2; __VA_ARGS__; }                   \
+       else if (occ__ == 4) { constexpr int OCC = 4; __VA_ARGS__; }              \
+       else { constexpr int OCC = 3; __VA_ARGS__; } } while (0)
 
 struct RedGeom { int CL, PL, chunks; };
 static RedGeom red_geom(int C, int VEC) {
@@ -271,8 +291,8 @@ __device__ __forceinline__ void bilerp_gather(const float* o, long long b, int y
   for (int v = 0; v < VEC; ++v) u[v] = w00 * a00[v] + w01 * a01[v] + w10 * a10[v] + w11 * a11[v];
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H, int W, int C,
                       const float* s1, const float* t1, const float* s2, const float* t2, const float* o, int P,
                       const float* gamma, act_t* z, long long ld_z, grad_t* zb, long long ld_zb, int CL, int PL) {
@@ -414,8 +434,8 @@ __device__ __forceinline__ void bn_bwd_coeffs(const float* scale, const float* m
   }
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_t* dyp, long long ld_dyp,
                             const act_t* y, long long ld_y, const act_t* f0, long long ld_f0, const act_t* r,
                             long long ld_r, int B, int H, int W, int C, const float* s4, const float* t4,
@@ -519,8 +539,8 @@ bn_bwd_apply_kernel(const grad_t* dy, long long ld_dy, const act_t* x, long long
   }
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0,
                            long long ld_g0, long long M, int C, const float* s3, const float* t3, const float* mean3,
                            const float* invstd3, double* red3, int CL, int PL) {
@@ -550,8 +570,8 @@ gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lo
   flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean3, invstd3, red3, s_red);
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, long long ld_z, const act_t* g0, long long ld_g0,
                           long long M, int C, const float* s3, const float* t3, const float* mean3, const float* invstd3,
                           const double* red3, grad_t* dg0, long long ld_dg0, int CL, int PL) {
@@ -576,8 +596,8 @@ gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lon
 }
 
 // pass 1 of the branch backward: gate-mix terms into dL / dA (in place) and the BN1 reductions
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* g0, long long ld_g0,
                           long long M, int C, const float* s1, const float* t1, const float* mean1,
                           const float* invstd1, const float* s3, const float* t3, double* red1, int CL, int PL) {
@@ -673,8 +693,8 @@ __device__ __forceinline__ void poolT_gather(const float* dp, unsigned b, int y,
   }
 }
 
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, long long ld_a0, int B, int H, int W,
                           int C, const float* s2, const float* t2, const float* mean2, const float* invstd2,
                           const float* dpooled, int P, double* red2, int CL, int PL) {
@@ -709,8 +729,8 @@ branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, lo
 }
 
 // pass 3: blockIdx.z = 0 -> dL0 from (dL, L0, BN1);  blockIdx.z = 1 -> dA0 from (dA + pool^T(dpooled), A0, BN2)
-template <int VEC>
-__global__ void __launch_bounds__(256, 3)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
 branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* a0,
                         long long ld_a0, int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
                         const float* invstd1, const double* red1, const float* s2, const float* t2, const float* mean2,
@@ -886,9 +906,9 @@ extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a
   const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_act_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks, 3), g.chunks);
-  VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
-                                                                     shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb, g.CL, g.PL)));
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks, ew_occ(3)), g.chunks);
+  OCC_DISPATCH(3, VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
+                                                                     shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_act_fwd_kernel");
   return DFCSA_OK;
 }
@@ -934,10 +954,10 @@ extern "C" int dfcsa_block_out_bwd_reduce(const void* dskip, int64_t ld_dskip, c
                           {dskip, dyp, y, f0, r, dy_out, scale4, shift4, mean4, invstd4});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
-  dim3 grid(red_blocks(nwin, g.PL, g.chunks, 3), g.chunks);
-  VEC_DISPATCH(v8, (block_out_bwd_reduce_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dskip), ld_dskip, G_(dyp), ld_dyp, A_(y), ld_y, A_(f0), ld_f0,
+  dim3 grid(red_blocks(nwin, g.PL, g.chunks, ew_occ(4)), g.chunks);
+  OCC_DISPATCH(4, VEC_DISPATCH(v8, (block_out_bwd_reduce_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(G_(dskip), ld_dskip, G_(dyp), ld_dyp, A_(y), ld_y, A_(f0), ld_f0,
                                                                            A_(r), ld_r, B, H, W, C, scale4, shift4, mean4, invstd4,
-                                                                           GM_(dy_out), ld_dy, red4, drs, g.CL, g.PL)));
+                                                                           GM_(dy_out), ld_dy, red4, drs, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("block_out_bwd_reduce_kernel");
   return DFCSA_OK;
 }
@@ -963,9 +983,9 @@ extern "C" int dfcsa_gate_mix_bwd_reduce(const void* dz, int64_t ld_dz, const vo
   DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && M > 0, "dfcsa_gate_mix_bwd_reduce: bad args");
   const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0}, {dz, z, g0, scale3, shift3, mean3, invstd3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
-  VEC_DISPATCH(v8, (gate_mix_bwd_reduce_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
-                                                                          mean3, invstd3, red3, g.CL, g.PL)));
+  dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(3)), g.chunks);
+  OCC_DISPATCH(3, VEC_DISPATCH(v8, (gate_mix_bwd_reduce_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
+                                                                          mean3, invstd3, red3, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("gate_mix_bwd_reduce_kernel");
   return DFCSA_OK;
 }
@@ -978,9 +998,9 @@ extern "C" int dfcsa_gate_mix_bwd_apply(const void* dz, int64_t ld_dz, const voi
   DFCSA_CHECK_ARG(dz && z && g0 && scale3 && shift3 && mean3 && invstd3 && red3 && dg0 && M > 0, "dfcsa_gate_mix_bwd_apply: bad args");
   const bool v8 = vec8_ok(C, {ld_dz, ld_z, ld_g0, ld_dg0}, {dz, z, g0, dg0, scale3, shift3, mean3, invstd3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
-  VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
-                                                                         mean3, invstd3, red3, GM_(dg0), ld_dg0, g.CL, g.PL)));
+  dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(3)), g.chunks);
+  OCC_DISPATCH(3, VEC_DISPATCH(v8, (gate_mix_bwd_apply_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(G_(dz), ld_dz, A_(z), ld_z, A_(g0), ld_g0, M, C, scale3, shift3,
+                                                                         mean3, invstd3, red3, GM_(dg0), ld_dg0, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("gate_mix_bwd_apply_kernel");
   return DFCSA_OK;
 }
@@ -996,9 +1016,9 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
   const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_g0}, {dz, l0, g0, o, tmp, scale1, shift1, mean1, invstd1, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
-  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
-                                                                         shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL)));
+  dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(2)), g.chunks);
+  OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
+                                                                         shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));
@@ -1017,9 +1037,9 @@ extern "C" int dfcsa_branch_bwd_reduce2(const void* dz, int64_t ld_dz, const voi
   const bool v8 = vec8_ok(C, {ld_dz, ld_a0}, {dz, a0, dpooled, scale2, shift2, mean2, invstd2});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
-  dim3 grid(red_blocks(M, g.PL, g.chunks, 3), g.chunks);
-  VEC_DISPATCH(v8, (branch_bwd_reduce2_kernel<VEC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2,
-                                                                         invstd2, dpooled, P, red2, g.CL, g.PL)));
+  dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(2)), g.chunks);
+  OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce2_kernel<VEC, OCC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2,
+                                                                         invstd2, dpooled, P, red2, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce2_kernel");
   return DFCSA_OK;
 }
@@ -1036,10 +1056,10 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
                           {dz, l0, a0, dl0, da0, dpooled, scale1, shift1, mean1, invstd1, scale2, shift2, mean2, invstd2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31) && H < 32768 && W < 32768, "dfcsa_branch_bwd_apply: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks * 2, 3), g.chunks, 2);
-  VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks * 2, ew_occ(2)), g.chunks, 2);
+  OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC, OCC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
                                                                        shift1, mean1, invstd1, red1, scale2, shift2, mean2, invstd2,
-                                                                       red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL)));
+                                                                       red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_apply_kernel");
   return DFCSA_OK;
 }

@@ -88,3 +88,21 @@ def test_full_res_attention_model_has_the_reference_state_dict_layout():
     assert set(sd.keys()) == set(want.keys())
     assert all(tuple(sd[k].shape) == tuple(want[k]) for k in sd)
     assert m.down1.attn_branch[3].pool_size is None
+
+
+def test_sliding_window_geometry_matches_the_reference_loop():
+    """dfcsa.inference.tile_boxes reproduces the tile coordinates of the reference's predict_large_image
+    (inference.py:124-132), including the shifted-back last tiles."""
+    from dfcsa.inference import tile_boxes
+    for h, w, tile, ov in ((1024, 1024, 224, 50), (500, 700, 224, 50), (224, 224, 224, 50), (300, 230, 224, 0)):
+        want = []
+        stride = tile - ov
+        for y in range(0, h, stride):
+            for x in range(0, w, stride):
+                y_end, x_end = min(y + tile, h), min(x + tile, w)
+                want.append((max(0, y_end - tile), y_end, max(0, x_end - tile), x_end))
+        assert tile_boxes(h, w, tile, ov) == want
+        cover = torch.zeros(h, w)
+        for y0, y1, x0, x1 in want:
+            cover[y0:y1, x0:x1] += 1
+        assert bool((cover > 0).all())

@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""Training entry point with the reference's command line (train.py:98-136 of YukiHataRin/DFC-SA-UNet) on the libdfcsa
+kernels:  python train.py --config configs/config_dfc-sa-res-block-p4.yaml [--resume ckpt.pth] [--loss bce_dice] ...
+
+Same YAML schema, same ModelFactory name, same optimizer hyper-parameters and checkpoint dictionary.  Data: the
+reference's DataLoaderFactory depends on a `datasets` package that is not part of its repository, so this script takes
+image / mask folders in the layout <dir>/images/* and <dir>/masks/* (same file stems), or --synthetic N to train on N
+generated batches (structured blobs, the distribution bench.py uses).  Multi-GPU: launch with torchrun; each rank reads
+its share of every batch and gradients are all-reduced per bucket over NCCL (dfcsa.trainer).
+"""
+import argparse
+import os
+import sys
+
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "dfc-sa-unet_b200")]
+
+from dfcsa.model_factory import ModelFactory  # noqa: E402
+from dfcsa.optim import FusedSGD  # noqa: E402
+from dfcsa.trainer import Trainer  # noqa: E402
+
+
+def normalize_path(path):
+    return path.replace("\\", "/")
+
+
+class FolderDataset(torch.utils.data.Dataset):
+    """<dir>/images/<stem>.* with <dir>/masks/<stem>.*; resized to img_size, ImageNet-normalised, mask binarised."""
+
+    def __init__(self, root, img_size):
+        from PIL import Image  # noqa: F401  (imported lazily: only this data path needs it)
+        self.root, self.size = normalize_path(root), tuple(img_size)
+        idir, mdir = os.path.join(self.root, "images"), os.path.join(self.root, "masks")
+        masks = {os.path.splitext(f)[0]: os.path.join(mdir, f) for f in sorted(os.listdir(mdir))}
+        self.items = [(os.path.join(idir, f), masks[os.path.splitext(f)[0]]) for f in sorted(os.listdir(idir))
+                      if os.path.splitext(f)[0] in masks]
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        import numpy as np
+        from PIL import Image
+        ip, mp = self.items[i]
+        img = np.asarray(Image.open(ip).convert("RGB").resize(self.size[::-1], Image.BILINEAR), dtype=np.float32) / 255.0
+        msk = np.asarray(Image.open(mp).convert("L").resize(self.size[::-1], Image.NEAREST), dtype=np.float32) / 255.0
+        img = (img - np.array([0.485, 0.456, 0.406], np.float32)) / np.array([0.229, 0.224, 0.225], np.float32)
+        return {"image": torch.from_numpy(img).permute(2, 0, 1).contiguous(), "mask": torch.from_numpy((msk > 0.5).astype(np.float32))[None]}
+
+
+class SyntheticBatches:
+    """n pre-batched synthetic items (image-correlated blob masks); iterable like a DataLoader."""
+
+    def __init__(self, n, batch, img_size, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        H, W = img_size
+        self.items = []
+        for _ in range(n):
+            low = torch.nn.functional.interpolate(torch.randn(batch, 1, 7, 7, generator=g), size=(H, W), mode="bicubic", align_corners=False)
+            self.items.append({"image": (0.5 * torch.randn(batch, 3, H, W, generator=g) + low).pin_memory(),
+                               "mask": (low > 0.3).float().pin_memory()})
+
+    def __iter__(self):
+        return iter(self.items)
+
+    def __len__(self):
+        return len(self.items)
+
+
+def main(config, resume_path=None, synthetic=0):
+    if not torch.cuda.is_available():
+        raise RuntimeError("dfcsa runs on CUDA (sm_100) only; there is no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=device)
+    tr_cfg, ds = config["training"], config.get("dataset", {})
+    bs, size = int(tr_cfg.get("batch_size", 4)), ds.get("img_size", [224, 224])
+    if synthetic:
+        train_loader, val_loader = SyntheticBatches(synthetic, bs, size, seed=local), SyntheticBatches(max(1, synthetic // 4), bs, size, seed=1000 + local)
+    else:
+        def mk(d, train):
+            dset = FolderDataset(d, size)
+            sampler = torch.utils.data.distributed.DistributedSampler(dset, shuffle=train) if world > 1 else None
+            return torch.utils.data.DataLoader(dset, batch_size=bs, shuffle=train and sampler is None, sampler=sampler,
+                                               num_workers=int(tr_cfg.get("num_workers", 2)), pin_memory=True, drop_last=train)
+        train_loader, val_loader = mk(ds["train_dir"], True), mk(ds["val_dir"], False)
+    model = ModelFactory.get_model(config).to(device)
+    optimizer = FusedSGD(model.parameters(), lr=float(tr_cfg.get("learning_rate", 0.01)), momentum=float(tr_cfg.get("momentum", 0.9)),
+                         weight_decay=float(tr_cfg.get("weight_decay", 1e-4)))           # reference train.py:73-78
+    trainer = Trainer(model=model, train_loader=train_loader, val_loader=val_loader, optimizer=optimizer, device=device, config=config)
+    if resume_path:
+        print(f"resuming from {resume_path}")
+        trainer.load_checkpoint(normalize_path(resume_path))
+    trainer.train()
+    if trainer.rank == 0 and trainer.train_losses:
+        print(f"final train loss {trainer.train_losses[-1]:.4f}  dice {trainer.train_dice_scores[-1]:.4f}")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser(description="Train segmentation model (DFC-SA-Res-Block on libdfcsa)")
+    ap.add_argument("--config", type=str, default="configs/config_dfc-sa-res-block-p4.yaml")
+    ap.add_argument("--resume", type=str)
+    ap.add_argument("--loss", type=str, choices=["dice", "tversky", "bce_dice", "joint"])
+    ap.add_argument("--alpha", type=float)
+    ap.add_argument("--beta", type=float)
+    ap.add_argument("--weight_bce", type=float)
+    ap.add_argument("--weight_dice", type=float)
+    ap.add_argument("--bce_weight", type=float)
+    ap.add_argument("--dice_weight", type=float)
+    ap.add_argument("--contour_weight", type=float)
+    ap.add_argument("--augmentation", type=lambda x: str(x).lower() == "true")
+    ap.add_argument("--synthetic", type=int, default=0, help="train on this many generated batches instead of dataset.train_dir")
+    ap.add_argument("--epochs", type=int, help="override training.num_epochs")
+    a = ap.parse_args()
+    with open(normalize_path(a.config), "r", encoding="utf-8") as f:
+        cfg = yaml.safe_load(f)
+    loss = cfg["training"].setdefault("loss", {"type": "dice", "params": {}})
+    loss.setdefault("params", {})
+    if a.loss is not None:
+        loss["type"] = a.loss
+    for k in ("alpha", "beta", "weight_bce", "weight_dice", "bce_weight", "dice_weight", "contour_weight"):
+        if getattr(a, k) is not None:
+            loss["params"][k] = getattr(a, k)
+    if a.augmentation is not None:
+        cfg.setdefault("dataset", {})["augmentation"] = a.augmentation
+    if a.epochs is not None:
+        cfg["training"]["num_epochs"] = a.epochs
+    main(cfg, a.resume, a.synthetic)
