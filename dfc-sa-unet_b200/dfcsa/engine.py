@@ -239,6 +239,7 @@ def _attn_probs(qkv, nb, N, Cq, nq, out):
     ops.softmax_rows(S, out)
 
 
+_ATTN_SMALL_MAX_N = 32   # up to here the whole attention core is one fp32 kernel per direction (dfcsa_attn_small_*)
 _ATTN_TC_MIN_N = 64      # below this the attention products are a few KFLOP per image: fp32 FMA, no tensor cores
 
 
@@ -268,6 +269,17 @@ def attention_forward(bp, pk, pooled, B, N, ctx=None):
     if tca:
         qsrc = _e((BN, nq), F16, dev)
         ops.cast2d(qkv, qsrc)
+    if N <= _ATTN_SMALL_MAX_N:          # one kernel per image batch: S, softmax and PV on the 16x16 maps of pool_size 4
+        attn = _e((B, N, N), F32, dev)
+        o = _e((B, N, C), F32, dev)
+        ops.attn_small_fwd(qkv, B, N, Cq, C, attn, o)
+        if ctx is not None:
+            ctx.qkv, ctx.attn, ctx.qkv16 = qkv, attn, None
+            ctx.pooled_w = pooled
+            if tc:
+                ctx.pooled_w = _e((BN, C), BF16, dev)      # weight-gradient operand
+                ops.cast2d(pooled, ctx.pooled_w)
+        return o
     # softmax(q k^T) v, a few images at a time when [N, N] is large (full-resolution attention: N = H*W)
     adt = F16 if tca else F32
     keep_attn = ctx is not None and B * N * N * (2 if tca else 4) <= _ATTN_SAVE_BYTES
@@ -307,7 +319,10 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
         ops.cast2d(qkv, qkvb)
         ops.cast2d(d_o, dob)
     ch = _attn_chunk(B, N)
-    for b0 in range(0, B, ch):
+    small = N <= _ATTN_SMALL_MAX_N
+    if small:
+        ops.attn_small_bwd(qkv, attn, d_o, B, N, Cq, C, dqkv)
+    for b0 in range(0, 0 if small else B, ch):
         nb = min(ch, B - b0)
         rows = slice(b0 * N, (b0 + nb) * N)
         dq, dk, dv = dqkv[rows, :Cq], dqkv[rows, Cq:2 * Cq], dqkv[rows, 2 * Cq:]

@@ -120,6 +120,14 @@ def softmax_rows_bwd(y, dy, dx):
     L.call("dfcsa_softmax_rows_bwd", L.ptr(y), L.dt(y), L.ptr(dy), L.ptr(dx), L.dt(dx), C.c_int64(rows), cols, L.stream())
 
 
+def attn_small_fwd(qkv, B, N, Cq, Cn, attn, o):
+    L.call("dfcsa_attn_small_fwd", L.ptr(qkv), _i64(qkv.stride(0)), B, N, Cq, Cn, L.ptr(attn), L.ptr(o), L.stream())
+
+
+def attn_small_bwd(qkv, attn, d_o, B, N, Cq, Cn, dqkv):
+    L.call("dfcsa_attn_small_bwd", L.ptr(qkv), _i64(qkv.stride(0)), L.ptr(attn), L.ptr(d_o), B, N, Cq, Cn, L.ptr(dqkv), L.stream())
+
+
 def bgemm(batch, M, N, K, A, a_b, ld_a, a_mn, Bm, b_b, ld_b, b_mn, Cm, c_b, ld_c):
     """C[b] = A[b] @ B[b] on tcgen05 (dfcsa_bgemm); operands 16-bit of one dtype, K-major or MN-major (see dfcsa.h)."""
     p = L.BgemmParams()

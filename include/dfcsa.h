@@ -147,6 +147,14 @@ int dfcsa_softmax_rows(const float* x, void* y, int y_dtype, int64_t rows, int32
 int dfcsa_softmax_rows_bwd(const void* y, int y_dtype, const float* dy, void* dx, int dx_dtype, int64_t rows, int32_t cols,
                            void* stream);
 
+/* The whole attention core for small pooled maps (N = P*P <= 32; P = 4 in the DFC-SA-Res-Block configs) in one kernel
+ * per direction, one CTA per image, fp32: attn = softmax(q k^T), o = attn v (reference models/unet_dfc_sa_res.py:28-34)
+ * and dq, dk, dv from d_o.  qkv / dqkv: [B*N, ld] rows (q[0:Cq] | k[Cq:2Cq] | v[2Cq:2Cq+C]); attn [B,N,N]; o, d_o [B*N, C]. */
+int dfcsa_attn_small_fwd(const float* qkv, int64_t ld, int32_t B, int32_t N, int32_t Cq, int32_t C,
+                         float* attn, float* o, void* stream);
+int dfcsa_attn_small_bwd(const float* qkv, int64_t ld, const float* attn, const float* d_o, int32_t B, int32_t N,
+                         int32_t Cq, int32_t C, float* dqkv, void* stream);
+
 /* Batched GEMM on tcgen05:  C[b] = A[b] * B[b],  b < batch,  A: M x K, B: K x N (as a matrix product), 16-bit operands of
  * one dtype, fp32 accumulation.  Storage of an operand is either K-major (element (m,k) at base + b*a_b + m*ld_a + k)
  * or MN-major (element (m,k) at base + b*a_b + k*ld_a + m): transposes are free.  C is row-major [M, N] with pitch ld_c.

@@ -295,3 +295,27 @@ def test_softmax_rows_16bit(cuda, cols):
             dx = torch.empty(37, cols, device=cuda, dtype=ddt)
             ops.softmax_rows_bwd(y, dy, dx)
             assert _rel_err(dx, dref) < dtol
+
+
+@pytest.mark.parametrize("B,N,Cq,C", [(3, 16, 8, 64), (2, 16, 128, 1024), (2, 9, 4, 40), (1, 32, 16, 128)])
+def test_attn_small_matches_torch(cuda, B, N, Cq, C):
+    """dfcsa_attn_small_fwd / bwd (one kernel per direction for N <= 32) against autograd of softmax(q k^T) v."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(21)
+    ld = 2 * Cq + C
+    qkv = torch.randn(B * N, ld, generator=g).cuda()
+    d_o = torch.randn(B * N, C, generator=g).cuda()
+    ref_in = qkv.clone().requires_grad_(True)
+    r = ref_in.view(B, N, ld)
+    q, k, v = r[..., :Cq], r[..., Cq:2 * Cq], r[..., 2 * Cq:]
+    attn_ref = torch.softmax(q @ k.transpose(1, 2), -1)
+    o_ref = attn_ref @ v
+    o_ref.backward(d_o.view(B, N, C))
+    attn = torch.empty(B, N, N, device=cuda)
+    o = torch.empty(B * N, C, device=cuda)
+    ops.attn_small_fwd(qkv, B, N, Cq, C, attn, o)
+    dqkv = torch.empty_like(qkv)
+    ops.attn_small_bwd(qkv, attn, d_o, B, N, Cq, C, dqkv)
+    torch.cuda.synchronize()
+    assert _rel_err(attn, attn_ref) < 1e-5 and _rel_err(o.view(B, N, C), o_ref) < 1e-5
+    assert _rel_err(dqkv, ref_in.grad) < 1e-4
