@@ -258,12 +258,17 @@ int conv_wgrad_small(const dfcsa_wgrad_params_t* p, cudaStream_t stream, int* rc
       wgrad_small_kernel<1, 3, float, __nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(p->x, p->ld_x, M, p->H, p->W, p->dy, p->ld_dy,
                                                                                        p->dw, p->ld_dw, 1, p->alpha);
     done = true;
-  } else if (p->N == 1 && p->x_tap_mode == DFCSA_TAP_1x1 && p->dy_dtype == DFCSA_BF16 && p->x_dtype == DFCSA_BF16 &&
+  } else if (p->N == 1 && p->x_tap_mode == DFCSA_TAP_1x1 && p->dy_dtype == DFCSA_BF16 &&
+             (p->x_dtype == DFCSA_BF16 || p->x_dtype == DFCSA_F16) &&
              p->C % 64 == 0 && p->ld_x % 2 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 3) == 0) {
     // narrow dy (1 channel), wide x: dw[0, c] = sum_m dy[m] * x[m, c]
     dim3 grid(small_blocks(M), p->C / 64);
-    wgrad_small_kernel<1, 1, __nv_bfloat16, __nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(p->dy, p->ld_dy, M, p->H, p->W, p->x,
-                                                                                           p->ld_x, p->dw, 1, 0, p->alpha);
+    if (p->x_dtype == DFCSA_BF16)
+      wgrad_small_kernel<1, 1, __nv_bfloat16, __nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(p->dy, p->ld_dy, M, p->H, p->W, p->x,
+                                                                                             p->ld_x, p->dw, 1, 0, p->alpha);
+    else
+      wgrad_small_kernel<1, 1, __nv_bfloat16, __half><<<grid, kWarps * 32, 0, stream>>>(p->dy, p->ld_dy, M, p->H, p->W, p->x,
+                                                                                      p->ld_x, p->dw, 1, 0, p->alpha);
     done = true;
   }
   if (!done) return 0;

@@ -12,6 +12,9 @@
 // One CTA per (tap row, n tile, c tile, pixel split); fp32 partials leave through atomics.  The n tile is 256 wide (two
 // M=128 accumulators that share every x box: 128 FLOP per byte staged from L2 instead of 85) when N >= 256, else 128.
 //   warps 0-3: epilogue (TMEM -> atomicAdd),  warp 4: TMA producer,  warp 5: TMEM alloc + MMA issuer
+// x may be fp16 (a forward activation) while dy is bf16 (a gradient): kind::f16 cannot mix the two formats, so warps
+// 0-3 - idle until the epilogue - rewrite every landed x box to bf16 in place in shared memory before the MMA warp
+// reads it.  That replaces the bf16 "shadow" copy of every activation the forward pass used to write to HBM.
 #include "common.cuh"
 #include <algorithm>
 #include <mutex>
@@ -40,6 +43,7 @@ struct WgradTcArgs {
   const float* alpha;
   uint32_t idesc;
   uint32_t tmem_cols;
+  int cvt_x;               // x arrives as fp16 and is converted to bf16 in shared memory (dy is bf16)
   int vec_red;             // dw rows are 16-byte aligned: red.global.add.v4.f32 (4x fewer L2 atomic operations)
   // second gradient over the same x (rows N1 .. N1+N2 of the virtual dy = [dy | dy2]; N1 % 64 == 0)
   int N1;                  // rows of the first gradient (== N when there is no second one)
@@ -55,6 +59,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t cvt_bar[kMaxStages];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t tmem_base_smem;
 
@@ -91,7 +96,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     tma_prefetch_desc(&map_dy);
     tma_prefetch_desc(&map_x);
     if (a.N1 < a.N) tma_prefetch_desc(&map_dy2);
-    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&cvt_bar[i], 128); }
     mbar_init(&done_bar, 1);
     fence_barrier_init();
   }
@@ -139,7 +144,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     int stage = 0; uint32_t phase = 0;
     bool first = true;
     for (long long pb = pb_beg; pb < pb_end; ++pb) {
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait(a.cvt_x ? &cvt_bar[stage] : &full_bar[stage], phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
@@ -172,6 +177,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (lane == 0) umma_commit(&done_bar);
     __syncwarp();
   } else {
+    // ===================== x: fp16 -> bf16 in place (only when the operand formats differ) =====================
+    if (a.cvt_x) {
+      int stage = 0; uint32_t phase = 0;
+      const int n16 = n_boxes_b * a.x_box_bytes / 16;
+      for (long long pb = pb_beg; pb < pb_end; ++pb) {
+        mbar_wait(&full_bar[stage], phase);
+        uint4* xs = reinterpret_cast<uint4*>(smem + stage * kStageBytes + kABytes);
+        for (int i = threadIdx.x; i < n16; i += 128) {
+          uint4 v = xs[i];
+          uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            const __nv_bfloat162 bb = __floats2bfloat162_rn(f.x, f.y);
+            w[j] = *reinterpret_cast<const uint32_t*>(&bb);
+          }
+          xs[i] = v;
+        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&cvt_bar[stage]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
     // ===================== epilogue =====================
     if (pb_end > pb_beg) {
       mbar_wait(&done_bar, 0);
@@ -236,7 +264,9 @@ void pick_patch(int H, int W, int& w_t, int& h_t) {
 
 int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->x_dtype != DFCSA_F32 && p->dy_dtype != DFCSA_F32, "conv_wgrad_tc: 16-bit operands required");
-  DFCSA_CHECK_ARG(p->x_dtype == p->dy_dtype, "conv_wgrad_tc: x and dy must share one 16-bit format (kind::f16 cannot mix fp16 and bf16)");
+  const bool cvt_x = p->x_dtype == DFCSA_F16 && p->dy_dtype == DFCSA_BF16;
+  DFCSA_CHECK_ARG(p->x_dtype == p->dy_dtype || cvt_x,
+                  "conv_wgrad_tc: x and dy must share one 16-bit format, or x fp16 with dy bf16 (converted in shared memory)");
   DFCSA_CHECK_ARG(p->C % 64 == 0 && p->N % 8 == 0, "conv_wgrad_tc: C must be a multiple of 64 and N of 8 (C=%d N=%d)", p->C, p->N);
   DFCSA_CHECK_ARG(p->ld_x % 8 == 0 && p->ld_dy % 8 == 0, "conv_wgrad_tc: pitches must be multiples of 8");
   DFCSA_CHECK_ARG((reinterpret_cast<uintptr_t>(p->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->dy) & 15) == 0,
@@ -347,7 +377,8 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.splits = static_cast<int>((a.pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split);
   a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
   a.vec_red = ((reinterpret_cast<uintptr_t>(p->dw) & 15) == 0 && p->ld_dw % 4 == 0) ? 1 : 0;
-  a.idesc = umma_idesc_f16(128, a.block_c, umma_fmt(p->dy_dtype), umma_fmt(p->x_dtype), 1, 1);
+  a.cvt_x = cvt_x ? 1 : 0;
+  a.idesc = umma_idesc_f16(128, a.block_c, umma_fmt(p->dy_dtype), umma_fmt(cvt_x ? DFCSA_BF16 : p->x_dtype), 1, 1);
   a.tmem_cols = (a.block_n == 256 || a.dw3) ? 512 : (a.block_c <= 64 ? 64 : a.block_c <= 128 ? 128 : 256);
 
   const int smem_bytes = a.stages * a.stage_bytes + 1024;

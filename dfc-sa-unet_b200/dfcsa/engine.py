@@ -4,10 +4,11 @@ Mirrors, kernel launch by kernel launch, the reference forward (models/unet_dfc_
 and the hand-derived backward of the same graph.  PyTorch is used only for device memory
 (torch.empty / zeros), streams and a few scalar copies; all arithmetic is in the CUDA library.
 
-Layout: activations NHWC fp16 [M, C] views (M = B*H*W), gradients NHWC bf16.  Every tensor that is also the operand
-of a weight-gradient GEMM has a bf16 "shadow" (kind::f16 tcgen05.mma cannot mix fp16 with bf16 operands - measured,
-see tools/tc_probe.cu probe 7).  torch.cat of the reference is zero-copy: producers write channel slices of one
-buffer ([f | L | A] inside a block, [up | skip] in the decoder).
+Layout: activations NHWC fp16 [M, C] views (M = B*H*W), gradients NHWC bf16.  kind::f16 tcgen05.mma cannot mix fp16
+with bf16 operands (measured, tools/tc_probe.cu probe 7); the weight-gradient kernel therefore converts its fp16
+activation tiles to bf16 in shared memory, so no bf16 copy of any activation is ever written to HBM.  torch.cat of the
+reference is zero-copy: producers write channel slices of one buffer ([f | L | A] inside a block, [up | skip] in the
+decoder).
 """
 import torch
 
@@ -275,10 +276,7 @@ def attention_forward(bp, pk, pooled, B, N, ctx=None):
         ops.attn_small_fwd(qkv, B, N, Cq, C, attn, o)
         if ctx is not None:
             ctx.qkv, ctx.attn, ctx.qkv16 = qkv, attn, None
-            ctx.pooled_w = pooled
-            if tc:
-                ctx.pooled_w = _e((BN, C), BF16, dev)      # weight-gradient operand
-                ops.cast2d(pooled, ctx.pooled_w)
+            ctx.pooled_w = p16                             # weight-gradient operand (fp16, or fp32 on the SIMT path)
         return o
     # softmax(q k^T) v, a few images at a time when [N, N] is large (full-resolution attention: N = H*W)
     adt = F16 if tca else F32
@@ -298,10 +296,7 @@ def attention_forward(bp, pk, pooled, B, N, ctx=None):
             ops.sgemm(nb, N, C, N, A, (N * N, N, 1), v, (N * nq, nq, 1), o[b0:b0 + nb], (N * C, C, 1))
     if ctx is not None:
         ctx.qkv, ctx.attn, ctx.qkv16 = qkv, attn, (qsrc if tca else None)
-        ctx.pooled_w = pooled
-        if tc:
-            ctx.pooled_w = _e((BN, C), BF16, dev)      # weight-gradient operand
-            ops.cast2d(pooled, ctx.pooled_w)
+        ctx.pooled_w = p16                                 # weight-gradient operand (fp16, or fp32 on the SIMT path)
     return o
 
 
@@ -376,9 +371,9 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
     return dp
 
 
-def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=True, save=True):
+def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     """One DynamicFusionConvAttnBlock.  x: [M, Ci] (fp16, or fp32 for the image); y / yp: fp16 output views (full
-    resolution / 2x2 max-pooled); yb / ypb: their bf16 shadows.  Returns the context the backward needs."""
+    resolution / 2x2 max-pooled).  Returns the context the backward needs."""
     dev = x.device
     C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
     M = B * H * W
@@ -399,31 +394,30 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, yb=None, ypb=None, training=Tr
     ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled)
     o = attention_forward(bp, pk, pooled, B, P * P, ctx)
     z = _e((M, 3 * C), F16, dev)
-    zb = _e((M, 3 * C), BF16, dev) if ctx is not None else None
-    ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z, zb)
+    ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z, None)
     # gate
     G0 = _e((M, C), F16, dev)
     zLA = z[:, C:]
     segs = [(zLA, TAP_1x1)]
     ops.conv_gemm(B, H, W, segs, pk["w3"], C, G0, stats=st[6 * C:8 * C] if training else None, backend=_backend(segs, pk["w3"], C, G0))
     bn3 = _bn_affine(bp.bn3, bp.b3, st[6 * C:7 * C] if training else None, st[7 * C:8 * C] if training else None, M, training, dev)
-    ops.gate_mix_fwd(G0, bn3[0], bn3[1], z, zb)
+    ops.gate_mix_fwd(G0, bn3[0], bn3[1], z, None)
     # fusion
     F0 = _e((M, C), F16, dev)
     segs = [(z, TAP_1x1)]
     ops.conv_gemm(B, H, W, segs, pk["w4"], C, F0, stats=st[8 * C:10 * C] if training else None, backend=_backend(segs, pk["w4"], C, F0))
     bn4 = _bn_affine(bp.bn4, bp.b4, st[8 * C:9 * C] if training else None, st[9 * C:10 * C] if training else None, M, training, dev)
-    ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp, yb, ypb if yp is not None else None)
+    ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp, None, None)
     if ctx is not None:
         ctx.B, ctx.H, ctx.W = B, H, W
-        ctx.L0, ctx.A0, ctx.R, ctx.G0, ctx.F0, ctx.z, ctx.zb, ctx.y, ctx.o = L0, A0, R, G0, F0, z, zb, y, o
+        ctx.L0, ctx.A0, ctx.R, ctx.G0, ctx.F0, ctx.z, ctx.y, ctx.o = L0, A0, R, G0, F0, z, y, o
         ctx.bn1, ctx.bn2, ctx.bn3, ctx.bn4 = bn1, bn2, bn3, bn4
     return ctx
 
 
 def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None, second=None):
     """second = (dy2, dw2, c_begin2, alpha2): another 1x1 weight gradient over the same x, same launch."""
-    tc = ops.wgrad_tc_eligible(x, dy) and x.dtype == dy.dtype
+    tc = ops.wgrad_tc_eligible(x, dy) and (x.dtype == dy.dtype or (x.dtype == F16 and dy.dtype == BF16))
     if second is not None:
         dy2 = second[0]
         tc = tc and ops.wgrad_tc_eligible(x, dy2) and dy2.dtype == dy.dtype and dy.shape[1] % 64 == 0 and second[2] % 32 == 0
@@ -431,7 +425,7 @@ def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None, second=None):
 
 
 def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
-    """Backward of block_forward.  xw: the block input as the weight-gradient operand (bf16 shadow, or the fp32 image).
+    """Backward of block_forward.  xw: the block input (fp16, or the fp32 image) as the weight-gradient operand.
     dskip: bf16 gradient w.r.t. y ([M, C] view, updated in place when dyp is given); dyp: bf16 gradient w.r.t. the
     max-pooled output or None; dx_out: bf16 [M, Ci] view that receives the input gradient, or None.
     grads: dict parameter -> fp32 gradient tensor (zero-initialised where the kernels accumulate)."""
@@ -468,7 +462,7 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     segs = [(dF0, TAP_1x1), (dG0, TAP_1x1)]
     ops.conv_gemm(B, H, W, segs, pk["wd43"], 2 * C, dLA, backend=_backend(segs, pk["wd43"], 2 * C, dLA))
     # fusion-conv and gate-conv weight gradients in one launch: both read z = [f | L | A] (the gate conv only L | A)
-    _wgrad(B, H, W, ctx.zb, TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 3 * C),
+    _wgrad(B, H, W, ctx.z, TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 3 * C),
            second=(dG0, grads[bp.W3].view(C, 2 * C), C, None))
     # branches (reduce1 first adds the gate-mix terms df*g / df*(1-g) into dL / dA in place)
     tmp = _e((B, H, P, C), F32, dev)
@@ -529,21 +523,17 @@ def net_forward(net, x_nchw, training, save=True):
     x0 = _e((Ms[0], Cin), F32, dev)
     ops.nchw_to_nhwc(x_nchw, x0, B, Cin, H, W)
     cat = [_e((Ms[i], 2 * f[i]), F16, dev) for i in range(4)]      # [up | skip] per level
-    catb = [_e((Ms[i], 2 * f[i]), BF16, dev) for i in range(4)] if keep else [None] * 4
     bctx = [None] * 9
-    xin, xinb = x0, x0
-    xs = []
+    xin = x0
+    xs = []              # the input of every block: the weight-gradient operand of its three input convs
     for i in range(4):   # encoder
         yp = _e((Ms[i + 1], f[i]), F16, dev)
-        ypb = _e((Ms[i + 1], f[i]), BF16, dev) if keep else None
-        xs.append(xinb)
-        bctx[i] = block_forward(bps[i], pks[i], xin, B, Hs[i], Ws[i], cat[i][:, f[i]:], yp,
-                                catb[i][:, f[i]:] if keep else None, ypb, training, keep)
-        xin, xinb = yp, ypb
+        xs.append(xin)
+        bctx[i] = block_forward(bps[i], pks[i], xin, B, Hs[i], Ws[i], cat[i][:, f[i]:], yp, training, keep)
+        xin = yp
     u = _e((Ms[4], 2 * f[3]), F16, dev)
-    ub = _e((Ms[4], 2 * f[3]), BF16, dev) if keep else None
-    xs.append(xinb)
-    bctx[4] = block_forward(bps[4], pks[4], xin, B, Hs[4], Ws[4], u, None, ub, None, training, keep)
+    xs.append(xin)
+    bctx[4] = block_forward(bps[4], pks[4], xin, B, Hs[4], Ws[4], u, None, training, keep)
     ups = [net.up4, net.up3, net.up2, net.up1]
     upk, uin = [], []
     for j, lvl in enumerate((3, 2, 1, 0)):   # decoder
@@ -554,16 +544,14 @@ def net_forward(net, x_nchw, training, save=True):
         segs = [(u, TAP_1x1)]
         dst = cat[lvl][:, :f[lvl]]
         ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, wt, 4 * Co_t, dst, out_mode=OUT_CONVT2x2, bias=up.bias.detach(),
-                      backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT,
-                      shadow=catb[lvl][:, :f[lvl]] if keep else None)
+                      backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT)
         if keep:
             upk.append(packs.up_bwd[j])
-            uin.append(ub)
+            uin.append(u)
         un = _e((Ms[lvl], f[lvl]), F16, dev)
-        unb = _e((Ms[lvl], f[lvl]), BF16, dev) if keep else None
-        xs.append(catb[lvl])
-        bctx[5 + j] = block_forward(bps[5 + j], pks[5 + j], cat[lvl], B, Hs[lvl], Ws[lvl], un, None, unb, None, training, keep)
-        u, ub = un, unb
+        xs.append(cat[lvl])
+        bctx[5 + j] = block_forward(bps[5 + j], pks[5 + j], cat[lvl], B, Hs[lvl], Ws[lvl], un, None, training, keep)
+        u = un
     # final 1x1 conv (Co = out_channels is tiny: fp32 SIMT path, logits in fp32)
     fc = net.final_conv
     Cout = fc.weight.shape[0]
@@ -579,7 +567,7 @@ def net_forward(net, x_nchw, training, save=True):
         torch._foreach_add_([m.num_batches_tracked for m in bns], 1)
     if keep:
         ctx.bps, ctx.pks, ctx.bctx, ctx.xs = bps, pks, bctx, xs
-        ctx.upk, ctx.uin, ctx.u_last, ctx.u_lastb = upk, uin, u, ub
+        ctx.upk, ctx.uin, ctx.u_last = upk, uin, u
         ctx.dims = (B, Cin, H, W, f, Hs, Ws, Ms)
         ctx.wdf = packs.wdf
     return logits, ctx
@@ -608,7 +596,7 @@ def net_backward(net, ctx, dlogits_nchw, grads, after_stage=None):
     # final conv backward (K = Cout is tiny: SIMT)
     du = _e((Ms[0], f[0]), BF16, dev)
     ops.conv_gemm(B, H, W, [(dl, TAP_1x1)], ctx.wdf, f[0], du, backend=BACKEND_SIMT)
-    ops.conv_wgrad(B, H, W, ctx.u_lastb, TAP_1x1, dl, TAP_1x1, grads[fc.weight].view(Cout, f[0]), backend=BACKEND_SIMT)
+    ops.conv_wgrad(B, H, W, ctx.u_last, TAP_1x1, dl, TAP_1x1, grads[fc.weight].view(Cout, f[0]), backend=BACKEND_SIMT)
     ops.colsum(dl, grads[fc.bias])
     ups = [net.up4, net.up3, net.up2, net.up1]
     dcat = [None] * 4

@@ -59,11 +59,7 @@ class _BlockFunction(torch.autograd.Function):
         M = B * H * W
         xin = engine._e((M, Ci), torch.float16 if bp.tc else torch.float32, dev)
         ops.nchw_to_nhwc(x.contiguous().float(), xin, B, Ci, H, W)
-        xb = None
-        if keep:
-            xb = engine._e((M, Ci), torch.bfloat16, dev) if bp.tc else xin
-            if bp.tc:
-                ops.cast2d(xin, xb)
+        xb = xin if keep else None      # the weight-gradient kernels read the fp16 (or fp32) input directly
         y = engine._e((M, bp.C), torch.float16, dev)
         bctx = engine.block_forward(bp, pk, xin, B, H, W, y, training=training, save=keep)
         out = engine._e((B, bp.C, H, W), torch.float32, dev)

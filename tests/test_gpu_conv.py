@@ -319,3 +319,31 @@ def test_attn_small_matches_torch(cuda, B, N, Cq, C):
     torch.cuda.synchronize()
     assert _rel_err(attn, attn_ref) < 1e-5 and _rel_err(o.view(B, N, C), o_ref) < 1e-5
     assert _rel_err(dqkv, ref_in.grad) < 1e-4
+
+
+@pytest.mark.parametrize("case", [(1, 32, 32, 128, 64, 1, 0), (2, 9, 11, 256, 320, 0, 0), (2, 6, 10, 128, 64, 0, 2), (1, 20, 20, 64, 128, 1, 0)])
+def test_conv_wgrad_fp16_activation_bf16_gradient(cuda, case):
+    """x fp16 (a forward activation) with dy bf16: the kernel converts the x tiles to bf16 in shared memory, so the result
+    equals the gradient computed from bf16-rounded x."""
+    from dfcsa import ops
+    B, H, W, Cc, N, xm, dm = case
+    g = torch.Generator().manual_seed(23)
+    x16 = torch.randn(B, H, W, Cc, generator=g).cuda().half()
+    xr = x16.bfloat16().float()                       # what the tensor core sees
+    if dm == 2:
+        dy = torch.randn(B, 2 * H, 2 * W, N, generator=g).cuda().bfloat16()
+        wt = torch.zeros(Cc, N, 2, 2, device=cuda, requires_grad=True)
+        y = F.conv_transpose2d(xr.permute(0, 3, 1, 2), wt, stride=2)
+        (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+        ref, taps = gw.permute(1, 2, 3, 0).reshape(N, 4 * Cc), 4
+    else:
+        dy = torch.randn(B, H, W, N, generator=g).cuda().bfloat16()
+        k = 3 if xm == 1 else 1
+        wt = torch.zeros(N, Cc, k, k, device=cuda, requires_grad=True)
+        y = F.conv2d(xr.permute(0, 3, 1, 2), wt, padding=k // 2)
+        (gw,) = torch.autograd.grad(y, wt, dy.float().permute(0, 3, 1, 2))
+        ref, taps = gw.permute(0, 2, 3, 1).reshape(N, k * k * Cc), k * k
+    dw = torch.zeros(N, taps * Cc, device=cuda)
+    ops.conv_wgrad(B, H, W, x16.reshape(-1, Cc), xm, dy.reshape(-1, N), dm, dw, backend=0)
+    torch.cuda.synchronize()
+    assert _rel_err(dw, ref) < 2e-3
