@@ -711,17 +711,33 @@ branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, lo
   if (pl < PL && c < C) {
     float sc[VEC], sh[VEC];
     ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh);
-    PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, H, W);
-    for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += gridDim.x * PL, it.next(H, W)) {
-      const long long m = m32;
-      float da[VEC], av[VEC], gp[VEC];
+    // two pixels per iteration: with 2 loads per pixel and 512 resident threads per SM a single pixel in flight per
+    // thread leaves only ~16 KB outstanding per SM, far below the ~45 KB the HBM latency-bandwidth product needs
+    const unsigned stride = gridDim.x * PL;
+    PixIter it0, it1;
+    it0.init(blockIdx.x * PL + pl, 2 * stride, H, W);
+    it1.init((blockIdx.x * PL + pl + stride) % M, 2 * stride, H, W);
+    for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += 2 * stride, it0.next(H, W), it1.next(H, W)) {
+      const long long m = m32, m1 = static_cast<long long>(m32) + stride;
+      const bool two = m1 < M;
+      float da[VEC], av[VEC], gp[VEC], da1[VEC], av1[VEC], gp1[VEC];
       ldv<VEC>(dz + m * ld_dz + 2 * C + c, da); ldv<VEC>(a0 + m * ld_a0 + c, av);
-      poolT_gather<VEC>(dpooled, it.b, it.y, it.x, P, C, c, tabs, gp);
+      if (two) { ldv<VEC>(dz + m1 * ld_dz + 2 * C + c, da1); ldv<VEC>(a0 + m1 * ld_a0 + c, av1); }
+      poolT_gather<VEC>(dpooled, it0.b, it0.y, it0.x, P, C, c, tabs, gp);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float d2 = fmaf(av[v], sc[v], sh[v]) > 0.f ? da[v] + gp[v] : 0.f;
         acc[0][v] += d2;
         acc[1][v] = fmaf(d2, av[v], acc[1][v]);
+      }
+      if (two) {
+        poolT_gather<VEC>(dpooled, it1.b, it1.y, it1.x, P, C, c, tabs, gp1);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const float d2 = fmaf(av1[v], sc[v], sh[v]) > 0.f ? da1[v] + gp1[v] : 0.f;
+          acc[0][v] += d2;
+          acc[1][v] = fmaf(d2, av1[v], acc[1][v]);
+        }
       }
     }
   }
@@ -753,14 +769,19 @@ branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long
   const long long ld_xs = abranch ? ld_a0 : ld_l0;
   grad_t* dst = abranch ? da0 + c : dl0 + c;
   const long long ld_dst = abranch ? ld_da0 : ld_dl0;
-  PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, H, W);
-  for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += gridDim.x * PL, it.next(H, W)) {
-    const long long m = m32;
-    float d[VEC], xv[VEC], o[VEC];
+  const unsigned stride = gridDim.x * PL;          // two pixels per iteration (see branch_bwd_reduce2_kernel)
+  PixIter it0, it1;
+  it0.init(blockIdx.x * PL + pl, 2 * stride, H, W);
+  it1.init((blockIdx.x * PL + pl + stride) % M, 2 * stride, H, W);
+  for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += 2 * stride, it0.next(H, W), it1.next(H, W)) {
+    const long long m = m32, m1 = static_cast<long long>(m32) + stride;
+    const bool two = m1 < M;
+    float d[VEC], xv[VEC], o[VEC], d1[VEC], xv1[VEC];
     ldv<VEC>(dsrc + m * ld_dz, d); ldv<VEC>(xsrc + m * ld_xs, xv);
+    if (two) { ldv<VEC>(dsrc + m1 * ld_dz, d1); ldv<VEC>(xsrc + m1 * ld_xs, xv1); }
     if (abranch) {
       float gp[VEC];
-      poolT_gather<VEC>(dpooled, it.b, it.y, it.x, P, C, c, tabs, gp);
+      poolT_gather<VEC>(dpooled, it0.b, it0.y, it0.x, P, C, c, tabs, gp);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) d[v] += gp[v];
     }
@@ -770,6 +791,20 @@ branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long
       o[v] = fmaf(sc[v], dd, fmaf(p[v], xv[v], q[v]));
     }
     stv<VEC>(dst + m * ld_dst, o);
+    if (two) {
+      if (abranch) {
+        float gp[VEC];
+        poolT_gather<VEC>(dpooled, it1.b, it1.y, it1.x, P, C, c, tabs, gp);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) d1[v] += gp[v];
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float dd = fmaf(xv1[v], sc[v], sh[v]) > 0.f ? d1[v] : 0.f;
+        o[v] = fmaf(sc[v], dd, fmaf(p[v], xv1[v], q[v]));
+      }
+      stv<VEC>(dst + m1 * ld_dst, o);
+    }
   }
 }
 
