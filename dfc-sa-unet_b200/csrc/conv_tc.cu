@@ -132,15 +132,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int stage_bytes = a.stage_bytes;
   const int total_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.n_tiles_n;
 
-  // Rows a partial activation box never writes must read as zero for the MMA.
-  {
-    uint4 z = make_uint4(0, 0, 0, 0);
-    uint4* p = reinterpret_cast<uint4*>(smem);
-    const int n16 = a.stages * stage_bytes / 16;
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) p[i] = z;
-    for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
-    fence_proxy_async();
-  }
+  // No zero fill of the stages: every B box is written in full by TMA (out-of-range rows arrive as zeros), and an
+  // activation-tile row a partial box leaves unwritten is a pixel row of the MMA's M axis - it can only reach its own
+  // output row, which the epilogue masks (valid == false) before anything is stored or summed.
+  for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     if (a.n_seg > 1) tma_prefetch_desc(&map_a1);

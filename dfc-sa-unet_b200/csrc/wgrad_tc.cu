@@ -43,6 +43,7 @@ struct WgradTcArgs {
   const float* alpha;
   uint32_t idesc;
   uint32_t tmem_cols;
+  int zero_fill;           // shared-memory stages must be zeroed first (partial pixel boxes)
   int cvt_x;               // x arrives as fp16 and is converted to bf16 in shared memory (dy is bf16)
   int vec_red;             // dw rows are 16-byte aligned: red.global.add.v4.f32 (4x fewer L2 atomic operations)
   // second gradient over the same x (rows N1 .. N1+N2 of the virtual dy = [dy | dy2]; N1 % 64 == 0)
@@ -86,7 +87,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const int n_halves = (n_boxes_a + 1) / 2;
   const int n_boxes_b = min(a.block_c, a.C - c0) / 64;
 
-  {
+  if (a.zero_fill) {
+    // only when a pixel box is partial (fewer than 64 pixels per box): the rows TMA never writes lie on the reduction
+    // axis of BOTH operands and must read as zero.  (An unwritten 64-channel block of dy only feeds output rows >= N,
+    // which are never stored.)
     uint4 z = make_uint4(0, 0, 0, 0);
     uint4* p = reinterpret_cast<uint4*>(smem);
     for (int i = threadIdx.x; i < a.stages * a.stage_bytes / 16; i += blockDim.x) p[i] = z;
@@ -368,6 +372,7 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   if (p->dy2 == nullptr) map_dy2 = map_dy;
   a.box_bytes = a.w_t * a.h_t * 128;
   a.x_tx_bytes = a.dw3 ? a.x_box_bytes : a.box_bytes;
+  a.zero_fill = (a.box_bytes < kBoxBytes) ? 1 : 0;
   a.pix_blocks = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
 
   const long long items = static_cast<long long>(a.taps) * a.n_tiles * a.c_tiles;
