@@ -114,6 +114,9 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// REG_STATS: the narrow-output variant that keeps the BatchNorm partial sums in registers (64 more registers per
+// epilogue thread - kept out of the general instantiation, whose epilogue got measurably slower at 166 registers)
+template <bool REG_STATS>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
@@ -305,6 +308,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int r = ew * 32 + lane;         // tile row == TMEM lane
     const int et = threadIdx.x - 128;
     const bool flush_each = a.n_tiles_n > 1;
+    // Narrow outputs (block_n <= 64, one n tile): every epilogue warp owns ONE fixed 32-column chunk for the whole
+    // kernel, so the BatchNorm partial sums stay in registers across tiles and the 2 x 31-shuffle transpose runs once
+    // per kernel instead of once per tile (these level-1 GEMMs are bound by the epilogue's instruction issue).
+    constexpr bool reg_stats = REG_STATS;
+    float rs[REG_STATS ? 32 : 1], rq[REG_STATS ? 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (REG_STATS ? 32 : 1); ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     int as = 0; uint32_t aphase = 0;
     int last_nt = 0;
     bool have_stats = false;
@@ -364,7 +374,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             else store_chunk<__nv_bfloat16>(a.shadow + pix * a.ld_shadow + cn, v, ncols, false);
           }
         }
-        if (a.stats != nullptr) {
+        if constexpr (REG_STATS) {
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { rs[i] += v[i]; rq[i] = fmaf(v[i], v[i], rq[i]); }
+          }
+        } else if (a.stats != nullptr) {
           float sq[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
@@ -395,6 +410,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
     (void)have_stats;
+    if constexpr (REG_STATS) {
+      if (half < a.block_n / 32) {       // this warp's chunk is ch == half
+        const float s1 = transpose_reduce32(rs, lane);
+        const float s2 = transpose_reduce32(rq, lane);
+        s_stats[ew][0][half * 32 + lane] += s1;
+        s_stats[ew][1][half * 32 + lane] += s2;
+      }
+    }
+    (void)reg_stats;
   }
   // final per-CTA flush of the BatchNorm partial sums (single n-tile case)
   tc_fence_before();
@@ -550,12 +574,17 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   const int smem_bytes = a.stages * stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(g_attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   const long long total_tiles = m_tiles * a.n_tiles_n;
   const int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
-  conv_tc_kernel<<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
+  if (p->stats != nullptr && a.n_tiles_n == 1 && a.block_n <= 64)
+    conv_tc_kernel<true><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
+  else
+    conv_tc_kernel<false><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
   DFCSA_LAUNCH_CHECK("conv_tc_kernel");
   return DFCSA_OK;
 }

@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 conv_smallk_kernel(const void* x, long long ld_x, long long M, int H, int W, const float* wgt, int N, void* out,
                    long long ld_out, const float* bias, double* stats) {
   constexpr int K = TAPS * CI;
-  __shared__ float s_patch[kWarps][32][K + 1];
+  constexpr int KP = (K + 4) / 4 * 4;      // row pitch: 16-byte multiple so a pixel's patch is read with LDS.128 broadcasts
+  __shared__ __align__(16) float s_patch[kWarps][32][KP];
   __shared__ float s_red[kWarps][2][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y * 64 + lane * 2;
@@ -78,11 +79,16 @@ conv_smallk_kernel(const void* x, long long ld_x, long long M, int H, int W, con
     const int cnt = static_cast<int>(min(32LL, M - m0));
     for (int p = 0; p < cnt; ++p) {
       float a0 = b0, a1 = b1;
+      float xr[KP];
+#pragma unroll
+      for (int k4 = 0; k4 < KP / 4; ++k4) {
+        const float4 t = *reinterpret_cast<const float4*>(&s_patch[warp][p][k4 * 4]);
+        xr[k4 * 4] = t.x; xr[k4 * 4 + 1] = t.y; xr[k4 * 4 + 2] = t.z; xr[k4 * 4 + 3] = t.w;
+      }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
-        const float xv = s_patch[warp][p][k];
-        a0 = fmaf(xv, wr[k].x, a0);
-        a1 = fmaf(xv, wr[k].y, a1);
+        a0 = fmaf(xr[k], wr[k].x, a0);
+        a1 = fmaf(xr[k], wr[k].y, a1);
       }
       st2<TO>(out, (m0 + p) * ld_out + n, a0, a1);
       s0 += a0; s1 += a1; q0 += a0 * a0; q1 += a1 * a1;
@@ -109,7 +115,8 @@ __global__ void __launch_bounds__(kWarps * 32)
 wgrad_small_kernel(const void* x, long long ld_x, long long M, int H, int W, const void* wide, long long ld_w, float* dw,
                    long long osw, long long osk, const float* alpha) {
   constexpr int K = TAPS * CI;
-  __shared__ float s_patch[kWarps][32][K + 1];
+  constexpr int KP = (K + 4) / 4 * 4;
+  __shared__ __align__(16) float s_patch[kWarps][32][KP];
   __shared__ float s_acc[kWarps][K][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = blockIdx.y * 64 + lane * 2;
@@ -122,13 +129,25 @@ wgrad_small_kernel(const void* x, long long ld_x, long long M, int H, int W, con
     load_patch<TAPS, CI, TX>(x, ld_x, m0 + lane, M, H, W, s_patch[warp][lane]);
     __syncwarp();
     const int cnt = static_cast<int>(min(32LL, M - m0));
-    for (int p = 0; p < cnt; ++p) {
-      const float2 d = ld2<TW>(wide, (m0 + p) * ld_w + n);
+    // four pixels per step: their wide-side loads are issued together (a dependent 500 ns load per pixel made this
+    // loop latency bound), and each pixel's patch comes from shared memory as LDS.128 broadcasts
+    for (int p0 = 0; p0 < 32; p0 += 4) {
+      float2 d[4];
 #pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float xv = s_patch[warp][p][k];
-        acc[k].x = fmaf(xv, d.x, acc[k].x);
-        acc[k].y = fmaf(xv, d.y, acc[k].y);
+      for (int u = 0; u < 4; ++u) d[u] = (p0 + u < cnt) ? ld2<TW>(wide, (m0 + p0 + u) * ld_w + n) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float xr[KP];
+#pragma unroll
+        for (int k4 = 0; k4 < KP / 4; ++k4) {
+          const float4 t = *reinterpret_cast<const float4*>(&s_patch[warp][p0 + u][k4 * 4]);
+          xr[k4 * 4] = t.x; xr[k4 * 4 + 1] = t.y; xr[k4 * 4 + 2] = t.z; xr[k4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          acc[k].x = fmaf(xr[k], d[u].x, acc[k].x);
+          acc[k].y = fmaf(xr[k], d[u].y, acc[k].y);
+        }
       }
     }
     __syncwarp();
