@@ -351,6 +351,29 @@ __global__ void softmax_rows_bwd_kernel(const void* __restrict__ y, int ydt, con
   for (int c = lane; c < cols; c += 32) st_any(dx, row * cols + c, dxdt, ld_any(y, row * cols + c, ydt) * (dr[c] - dot));
 }
 
+// dS = P * (dP - D) with the row constant D_i = sum_j dP_ij P_ij supplied by the caller as sum_c dO_ic O_ic (the same
+// number, since O = P V): ONE pass over the [rows, cols] matrices instead of two.  16 bytes per thread.
+__global__ void __launch_bounds__(256)
+softmax_bwd_d_kernel(const void* __restrict__ y, int ydt, const void* __restrict__ dy, int dydt, const float* __restrict__ D,
+                     void* __restrict__ dx, int dxdt, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / cols;
+    st_any(dx, i, dxdt, ld_any(y, i, ydt) * (ld_any(dy, i, dydt) - D[row]));
+  }
+}
+// out[r] = sum_c a[r, c] * b[r, c]  (one warp per row)
+__global__ void rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long rows, int cols, float* __restrict__ out) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s = fmaf(a[row * cols + c], b[row * cols + c], s);
+  s = warp_sum(s);
+  if (lane == 0) out[row] = s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // permute3 (weight re-layout with cast)
 // ---------------------------------------------------------------------------------------------
@@ -464,6 +487,24 @@ extern "C" int dfcsa_softmax_rows_bwd(const void* y, int y_dtype, const float* d
   DFCSA_CHECK_ARG(blocks < (1LL << 31), "dfcsa_softmax_rows_bwd: too many rows");
   softmax_rows_bwd_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(y, y_dtype, dy, dx, dx_dtype, rows, cols);
   DFCSA_LAUNCH_CHECK("softmax_rows_bwd_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_softmax_rows_bwd_d(const void* y, int y_dtype, const void* dy, int dy_dtype, const float* D, void* dx,
+                                        int dx_dtype, int64_t rows, int32_t cols, void* stream) {
+  DFCSA_CHECK_ARG(y && dy && D && dx && rows > 0 && cols > 0, "dfcsa_softmax_rows_bwd_d: bad args");
+  const long long total = rows * cols;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, 148LL * 32));
+  softmax_bwd_d_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(y, y_dtype, dy, dy_dtype, D, dx, dx_dtype, rows, cols);
+  DFCSA_LAUNCH_CHECK("softmax_bwd_d_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_rowdot(const float* a, const float* b, int64_t rows, int32_t cols, float* out, void* stream) {
+  DFCSA_CHECK_ARG(a && b && out && rows > 0 && cols > 0, "dfcsa_rowdot: bad args");
+  const long long blocks = (rows + 7) / 8;
+  DFCSA_CHECK_ARG(blocks < (1LL << 31), "dfcsa_rowdot: too many rows");
+  rowdot_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, rows, cols, out);
+  DFCSA_LAUNCH_CHECK("rowdot_kernel");
   return DFCSA_OK;
 }
 

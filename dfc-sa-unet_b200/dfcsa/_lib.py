@@ -87,7 +87,7 @@ class ParamDesc(C.Structure):
 SYMBOLS = [
     "dfcsa_version", "dfcsa_last_error", "dfcsa_device_ok",
     "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm", "dfcsa_bgemm", "dfcsa_attn_small_fwd", "dfcsa_attn_small_bwd",
-    "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd",
+    "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd", "dfcsa_softmax_rows_bwd_d", "dfcsa_rowdot",
     "dfcsa_bn_finalize", "dfcsa_bn_eval_affine",
     "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd",
     "dfcsa_block_out_bwd_reduce", "dfcsa_bn_bwd_apply", "dfcsa_gate_mix_bwd_reduce", "dfcsa_gate_mix_bwd_apply",

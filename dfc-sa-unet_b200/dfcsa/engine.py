@@ -313,6 +313,8 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
         qkvb, dob = _e((BN, nq), BF16, dev), _e((BN, C), BF16, dev)     # gradient-side operands are bf16
         ops.cast2d(qkv, qkvb)
         ops.cast2d(d_o, dob)
+        Drow = _e((BN,), F32, dev)       # D_i = sum_j dP_ij P_ij = sum_c dO_ic O_ic: makes the softmax backward one pass
+        ops.rowdot(d_o, ctx.o.view(BN, C), Drow)
     ch = _attn_chunk(B, N)
     small = N <= _ATTN_SMALL_MAX_N
     if small:
@@ -323,21 +325,26 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
         dq, dk, dv = dqkv[rows, :Cq], dqkv[rows, Cq:2 * Cq], dqkv[rows, 2 * Cq:]
         if attn is not None:
             A = attn[b0:b0 + nb]
-        else:                                  # not saved (too large): recompute the probabilities
-            A = _e((nb, N, N), F16 if tca else F32, dev)
-            _attn_probs((ctx.qkv16 if tca else qkv)[rows], nb, N, Cq, nq, A)
+        elif tca:                              # not saved (too large): recompute the probabilities, straight to bf16
+            A = _e((nb, N, N), BF16, dev)
+            _attn_probs(ctx.qkv16[rows], nb, N, Cq, nq, A)
+        else:
+            A = _e((nb, N, N), F32, dev)
+            _attn_probs(qkv[rows], nb, N, Cq, nq, A)
         if tca:
             q, k, v = qkvb[rows, :Cq], qkvb[rows, Cq:2 * Cq], qkvb[rows, 2 * Cq:]
             do = dob[rows]
-            Ab = _e((nb, N, N), BF16, dev)
-            ops.cast2d(A.view(nb * N, N), Ab.view(nb * N, N))
+            if A.dtype == BF16:
+                Ab = A
+            else:
+                Ab = _e((nb, N, N), BF16, dev)
+                ops.cast2d(A.view(nb * N, N), Ab.view(nb * N, N))
             ops.bgemm(nb, N, C, N, Ab, N * N, N, True, do, N * C, C, True, dv, N * nq, nq)         # dv[j,c] = sum_i attn[i,j] do[i,c]
-            del Ab
-            dattn = _e((nb, N, N), F32, dev)
+            dattn = _e((nb, N, N), BF16, dev)      # a gradient: bf16 like every other activation gradient
             ops.bgemm(nb, N, N, C, do, N * C, C, False, v, N * nq, nq, False, dattn, N * N, N)     # dattn[i,j] = sum_c do[i,c] v[j,c]
-            dS = _e((nb, N, N), BF16, dev)
-            ops.softmax_rows_bwd(A, dattn, dS)
-            del dattn
+            dS = dattn                             # in place: dS = P * (dP - D)
+            ops.softmax_rows_bwd_d(Ab, dattn, Drow[rows], dS)
+            del Ab
             ops.bgemm(nb, N, Cq, N, dS, N * N, N, False, k, N * nq, nq, True, dq, N * nq, nq)      # dq[i,c] = sum_j dS[i,j] k[j,c]
             ops.bgemm(nb, N, Cq, N, dS, N * N, N, True, q, N * nq, nq, True, dk, N * nq, nq)       # dk[j,c] = sum_i dS[i,j] q[i,c]
         else:

@@ -120,6 +120,18 @@ def softmax_rows_bwd(y, dy, dx):
     L.call("dfcsa_softmax_rows_bwd", L.ptr(y), L.dt(y), L.ptr(dy), L.ptr(dx), L.dt(dx), C.c_int64(rows), cols, L.stream())
 
 
+def softmax_rows_bwd_d(y, dy, D, dx):
+    """dx = y * (dy - D[row]) in one pass (dfcsa_softmax_rows_bwd_d); D from rowdot(d_o, o)."""
+    rows, cols = y.numel() // y.shape[-1], y.shape[-1]
+    L.call("dfcsa_softmax_rows_bwd_d", L.ptr(y), L.dt(y), L.ptr(dy), L.dt(dy), L.ptr(D), L.ptr(dx), L.dt(dx), C.c_int64(rows), cols,
+           L.stream())
+
+
+def rowdot(a, b, out):
+    rows, cols = a.numel() // a.shape[-1], a.shape[-1]
+    L.call("dfcsa_rowdot", L.ptr(a), L.ptr(b), C.c_int64(rows), cols, L.ptr(out), L.stream())
+
+
 def attn_small_fwd(qkv, B, N, Cq, Cn, attn, o):
     L.call("dfcsa_attn_small_fwd", L.ptr(qkv), _i64(qkv.stride(0)), B, N, Cq, Cn, L.ptr(attn), L.ptr(o), L.stream())
 

@@ -147,6 +147,13 @@ int dfcsa_softmax_rows(const float* x, void* y, int y_dtype, int64_t rows, int32
 int dfcsa_softmax_rows_bwd(const void* y, int y_dtype, const float* dy, void* dx, int dx_dtype, int64_t rows, int32_t cols,
                            void* stream);
 
+/* One-pass softmax backward for the large attention maps: dx = y * (dy - D[row]) with D[row] = sum_j dy*y supplied as
+ * sum_c dO[row, c] * O[row, c] (dfcsa_rowdot; identical because O = P V).  y / dy / dx: fp32 or 16-bit. */
+int dfcsa_softmax_rows_bwd_d(const void* y, int y_dtype, const void* dy, int dy_dtype, const float* D, void* dx, int dx_dtype,
+                             int64_t rows, int32_t cols, void* stream);
+/* out[r] = sum_c a[r, c] * b[r, c]  (fp32, dense rows) */
+int dfcsa_rowdot(const float* a, const float* b, int64_t rows, int32_t cols, float* out, void* stream);
+
 /* The whole attention core for small pooled maps (N = P*P <= 32; P = 4 in the DFC-SA-Res-Block configs) in one kernel
  * per direction, one CTA per image, fp32: attn = softmax(q k^T), o = attn v (reference models/unet_dfc_sa_res.py:28-34)
  * and dq, dk, dv from d_o.  qkv / dqkv: [B*N, ld] rows (q[0:Cq] | k[Cq:2Cq] | v[2Cq:2Cq+C]); attn [B,N,N]; o, d_o [B*N, C]. */
