@@ -164,6 +164,9 @@ def run_dfcsa(args):
     # The step is replayed from a CUDA graph (Trainer.train_step_graphed, captured during warm-up): eager, the ~500
     # launches of a step cost ~35 ms of host time against ~45 ms of GPU time, too close to hide reliably.
     step = tr.train_step if args.no_graph else tr.train_step_graphed
+    # clocks / throttle reasons are sampled from the start of the warm-up (nvidia-smi needs a moment to start) to the
+    # end of the timed region: every sample is under load
+    sampler = ClockSampler(local) if rank == 0 else None
     # ---------------- warm-up ----------------
     for i in range(max(args.warmup, 3)):
         step(*devb[i % 2])
@@ -171,7 +174,6 @@ def run_dfcsa(args):
 
     # ---------------- timed: inputs resident in HBM (no per-call instrumentation) ----------------
     launches0 = _lib.LAUNCHES
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -281,7 +283,7 @@ def run_dfcsa(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dfcsa", choices=["dfcsa", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (default: the BASELINE config, 64)")
