@@ -39,6 +39,12 @@ static inline size_t dtype_size(int dt) { return dt == DFCSA_F32 ? 4 : 2; }
 // 16-bit storage helpers.  Activations are fp16 ("act"), gradients bf16 ("grad"); the tensor core
 // sees both through kind::f16 with fp32 accumulation.
 // ---------------------------------------------------------------------------------------------
+// max / min that PROPAGATE NaN (max.NaN.f32): fmaxf / fminf return the non-NaN operand, which would silently turn a
+// poisoned activation into 0 (ReLU) or -65504 (fp16 saturation) and hide a diverged batch from the loss; with these a
+// NaN reaches the loss and the gradient norm, and the optimizer skips the step like the reference does.
+__device__ __forceinline__ float fmax_nan(float a, float b) { float d; asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ float fmin_nan(float a, float b) { float d; asm("min.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+
 template <typename T> struct Cvt;
 template <> struct Cvt<float> {
   __device__ __forceinline__ static float to_f(float v) { return v; }
@@ -48,7 +54,7 @@ template <> struct Cvt<__half> {
   __device__ __forceinline__ static float to_f(__half v) { return __half2float(v); }
   __device__ __forceinline__ static __half from_f(float v) {
     // saturate to the finite fp16 range so an outlier can never poison a BatchNorm with inf
-    v = fminf(fmaxf(v, -65504.f), 65504.f);
+    v = fmin_nan(fmax_nan(v, -65504.f), 65504.f);
     return __float2half_rn(v);
   }
 };

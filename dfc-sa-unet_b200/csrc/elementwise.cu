@@ -227,7 +227,7 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
     for (int x = lo; x < hi; ++x) {
       float t[VEC]; ldv<VEC>(row + x * ld, t);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] += fmaxf(fmaf(t[v], sc[v], sh[v]), 0.f);
+      for (int v = 0; v < VEC; ++v) acc[v] += fmax_nan(fmaf(t[v], sc[v], sh[v]), 0.f);
     }
     const float inv = 1.f / static_cast<float>(hi - lo);
     float* o = tmp + ((b * H + y) * P + j) * C + cv * VEC;
@@ -309,14 +309,14 @@ branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long lo
     float v0[VEC], outv[VEC];
     ldv<VEC>(l0 + static_cast<long long>(m) * ld_l0 + c, v0);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) outv[v] = fmaxf(fmaf(v0[v], sc1[v], sh1[v]), 0.f);
+    for (int v = 0; v < VEC; ++v) outv[v] = fmax_nan(fmaf(v0[v], sc1[v], sh1[v]), 0.f);
     stv<VEC>(z + static_cast<long long>(m) * ld_z + C + c, outv);
     if (zb != nullptr) stv<VEC>(zb + static_cast<long long>(m) * ld_zb + C + c, outv);
     float u[VEC];
     bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
     ldv<VEC>(a0 + static_cast<long long>(m) * ld_a0 + c, v0);
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmaxf(fmaf(v0[v], sc2[v], sh2[v]), 0.f);
+    for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmax_nan(fmaf(v0[v], sc2[v], sh2[v]), 0.f);
     stv<VEC>(z + static_cast<long long>(m) * ld_z + 2 * C + c, outv);
     if (zb != nullptr) stv<VEC>(zb + static_cast<long long>(m) * ld_zb + 2 * C + c, outv);
   }
@@ -373,7 +373,7 @@ block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long
       float fv[VEC], rv[VEC], ov[VEC];
       ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) ov[v] = fmaxf(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
+      for (int v = 0; v < VEC; ++v) ov[v] = fmax_nan(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
       stv<VEC>(y + m * ld_y + c, ov);
       if (yb != nullptr) stv<VEC>(yb + m * ld_yb + c, ov);
       // pool over the values as stored (fp16), so backward can recompute the argmax from y

@@ -16,8 +16,8 @@ bce_dice_sums_kernel(const float* __restrict__ x, const float* __restrict__ t, l
     const float xv = x[i], tv = t[i];
     const float p = from_logits ? sigmoidf_exact(xv) : xv;
     // nn.BCELoss: log terms clamped at -100 (ATen binary_cross_entropy)
-    const float lp = fmaxf(logf(p), -100.f);
-    const float l1p = fmaxf(logf(1.f - p), -100.f);
+    const float lp = fmax_nan(logf(p), -100.f);          // NaN-propagating, like ATen's std::max in BCELoss
+    const float l1p = fmax_nan(logf(1.f - p), -100.f);
     a[0] -= tv * lp + (1.f - tv) * l1p;
     a[1] += p * tv; a[2] += p; a[3] += tv;
     const float hard = p > 0.5f ? 1.f : 0.f;
@@ -104,8 +104,13 @@ sgd_step_kernel(const dfcsa_param_t* table, int n_tensors, long long max_n, cons
   const long long beg = static_cast<long long>(blockIdx.x) * kChunk;
   if (beg >= d.n) return;
   const long long end = min(static_cast<long long>(d.n), beg + kChunk);
+  // A non-finite gradient norm (NaN loss, overflow) skips the whole update, weights and momentum untouched: the
+  // device-side, rank-consistent form of the reference's "NaN loss -> skip this batch" (utils/trainer.py:134-139) - the
+  // norm is computed from the all-reduced gradients, so every rank takes the same decision without a host sync.
+  const double ss = *sumsq;
+  if (!(ss == ss) || ss > 1.7e308) return;
   // torch.nn.utils.clip_grad_norm_: coef = clamp(max_norm / (total_norm + 1e-6), max=1)
-  const float total = sqrtf(static_cast<float>(*sumsq)) * fabsf(gscale);
+  const float total = sqrtf(static_cast<float>(ss)) * fabsf(gscale);
   const float coef = max_norm > 0.f ? fminf(max_norm / (total + 1e-6f), 1.f) * gscale : gscale;
   for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const float w = d.w[i];

@@ -20,7 +20,7 @@ template <> __device__ __forceinline__ float2 ld2<__nv_bfloat16>(const void* p, 
 }
 template <typename T> __device__ __forceinline__ void st2(void* p, long long i, float a, float b);
 template <> __device__ __forceinline__ void st2<__half>(void* p, long long i, float a, float b) {
-  a = fminf(fmaxf(a, -65504.f), 65504.f); b = fminf(fmaxf(b, -65504.f), 65504.f);
+  a = fmin_nan(fmax_nan(a, -65504.f), 65504.f); b = fmin_nan(fmax_nan(b, -65504.f), 65504.f);
   *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p) + i) = __floats2half2_rn(a, b);
 }
 template <> __device__ __forceinline__ void st2<__nv_bfloat16>(void* p, long long i, float a, float b) {

@@ -317,7 +317,9 @@ int dfcsa_bce_dice_bwd(const float* x, const float* t, int64_t n, int from_logit
 typedef struct { float* w; float* g; float* m; int64_t n; } dfcsa_param_t;
 /* sumsq[0] += sum over all tensors of g^2 (double) */
 int dfcsa_grad_sumsq(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t max_n, double* sumsq, void* stream);
-/* c = min(1, max_norm/(sqrt(sumsq*gscale^2)+1e-6)); g = c*gscale*g + wd*w; m = first ? g : mom*m + g; w -= lr*m */
+/* c = min(1, max_norm/(sqrt(sumsq*gscale^2)+1e-6)); g = c*gscale*g + wd*w; m = first ? g : mom*m + g; w -= lr*m.
+ * If sumsq is NaN / inf the step is skipped entirely (the reference skips a batch whose loss is NaN,
+ * utils/trainer.py:134-139; here the decision is taken on the device from the reduced gradient norm). */
 int dfcsa_sgd_step(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t max_n, const double* sumsq,
                    float gscale, float max_norm, float lr, float momentum, float weight_decay, int first_step,
                    void* stream);

@@ -235,3 +235,27 @@ def test_batched_sliding_window_inference_matches_tile_by_tile(cuda):
                 counts[y0:y1, x0:x1] += 1
         want = canvas / np.maximum(counts, 1)
         assert np.abs(got - want).max() < 2e-3
+
+
+def test_non_finite_batch_is_skipped_on_the_device(cuda):
+    """reference utils/trainer.py:134-139 skips a batch whose loss is NaN; the fused step does the same without a host
+    sync: a non-finite gradient norm leaves weights and momentum untouched, and training continues afterwards."""
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    from dfcsa.trainer import Trainer
+    cfg = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/dfcsa_test"}}
+    torch.manual_seed(0)
+    tr = Trainer(UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8), None, None, None, "cuda", cfg)
+    img, mask = (t.cuda() for t in O.synthetic_batch(2, 64, 64, seed=1))
+    tr.train_step(img, mask)
+    before = [p.detach().clone() for p in tr.model.parameters()]
+    mom = tr.optimizer.flat_mom.clone()
+    bad = img.clone()
+    bad[0, 0, 3, 3] = float("nan")
+    r = tr.train_step(bad, mask).host()
+    assert r["loss"] != r["loss"]                                           # the loss of that batch is NaN
+    assert all(torch.equal(a, p.detach()) for a, p in zip(before, tr.model.parameters()))
+    assert torch.equal(mom, tr.optimizer.flat_mom)
+    r = tr.train_step(img, mask).host()                                      # and the next good batch trains normally
+    assert r["loss"] == r["loss"]
+    assert any(not torch.equal(a, p.detach()) for a, p in zip(before, tr.model.parameters()))
