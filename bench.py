@@ -235,6 +235,16 @@ def run_dfcsa(args):
         ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
         peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
         step_ms = ms / args.steps
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this same configuration
+        traffic, traffic_src = None, None
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic_r01.json")))["conv_tc"]
+            if B == BATCH:
+                traffic = t["traffic_bytes_per_launch"]
+                traffic_src = ("profiles/ncu_gemm_traffic_r01.csv: dram__bytes_read.sum + dram__bytes_write.sum over the 86 conv_tc launches "
+                               "of one step (33.2 GB; algorithmic operand + result bytes 34.4 GB)")
+        except Exception:  # noqa: BLE001
+            pass
         shares = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / ms_prof, "launches_per_step": v["launches"] / args.steps,
                       **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {})}
                   for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
@@ -258,7 +268,8 @@ def run_dfcsa(args):
             "clocks": clocks,
             "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd + dgrad + ConvT)", "bound": "tensor",
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
-                         "peak_source": f"{pk_src} bf16 sustained", "traffic": None,
+                         "peak_source": f"{pk_src} bf16 sustained", "traffic": traffic, "traffic_unit": "bytes per launch",
+                         "traffic_source": traffic_src,
                          "launches_per_step": conv["launches"] / args.steps, "ms_per_step": conv["ms"] / args.steps},
             "profiled_ms_per_step": ms_prof / args.steps,
             "kernels": shares,
