@@ -127,7 +127,7 @@ def run_dfcsa(args):
     from dfcsa.modules import UNetDFCSARes
     from dfcsa.selftest import set_gamma
     from dfcsa.trainer import Trainer
-    from oracle import dfcsa_oracle as O   # synthetic_batch generator + the cpu_baseline leg only
+    from dfcsa.synthetic import synthetic_batch
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -152,7 +152,7 @@ def run_dfcsa(args):
     # two distinct synthetic batches per rank (structured masks), generated in chunks on the host
     host = []
     for s in range(2):
-        imgs, masks = zip(*[O.synthetic_batch(16, IMG, IMG, seed=1000 * rank + 10 * s + j) for j in range((B + 15) // 16)])
+        imgs, masks = zip(*[synthetic_batch(16, IMG, IMG, seed=1000 * rank + 10 * s + j) for j in range((B + 15) // 16)])
         host.append((torch.cat(imgs)[:B].pin_memory(), torch.cat(masks)[:B].pin_memory()))
     devb = [(i.to(dev), m.to(dev)) for i, m in host]
 

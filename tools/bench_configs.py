@@ -24,7 +24,7 @@ import torch  # noqa: E402
 from dfcsa.modules import UNet_FullResAttention, UNetDFCSARes  # noqa: E402
 from dfcsa.selftest import set_gamma  # noqa: E402
 from dfcsa.trainer import Trainer  # noqa: E402
-from oracle import dfcsa_oracle as O  # noqa: E402   (synthetic_batch generator only)
+from dfcsa import synthetic as O  # noqa: E402
 
 CFG = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/dfcsa_cfg"}}
 FEATURES = [64, 128, 256, 512]

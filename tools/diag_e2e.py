@@ -6,7 +6,7 @@ import torch
 from dfcsa.modules import UNetDFCSARes
 from dfcsa.selftest import set_gamma
 from dfcsa.trainer import Trainer, device_feeder
-from oracle import dfcsa_oracle as O
+from dfcsa import synthetic as O
 
 torch.manual_seed(0)
 model = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)

@@ -7,7 +7,7 @@ import torch
 from dfcsa.modules import UNetDFCSARes
 from dfcsa.selftest import set_gamma
 from dfcsa.trainer import Trainer
-from oracle import dfcsa_oracle as O
+from dfcsa import synthetic as O
 
 cfg = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/x"}}
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32

@@ -55,13 +55,12 @@ class SyntheticBatches:
     """n pre-batched synthetic items (image-correlated blob masks); iterable like a DataLoader."""
 
     def __init__(self, n, batch, img_size, seed=0):
-        g = torch.Generator().manual_seed(seed)
+        from dfcsa.synthetic import synthetic_batch
         H, W = img_size
         self.items = []
-        for _ in range(n):
-            low = torch.nn.functional.interpolate(torch.randn(batch, 1, 7, 7, generator=g), size=(H, W), mode="bicubic", align_corners=False)
-            self.items.append({"image": (0.5 * torch.randn(batch, 3, H, W, generator=g) + low).pin_memory(),
-                               "mask": (low > 0.3).float().pin_memory()})
+        for i in range(n):
+            img, msk = synthetic_batch(batch, H, W, seed=seed * 100003 + i)
+            self.items.append({"image": img.pin_memory(), "mask": msk.pin_memory()})
 
     def __iter__(self):
         return iter(self.items)
