@@ -169,8 +169,11 @@ class Trainer:
     def train_epoch(self, epoch):
         running = torch.zeros(5, dtype=torch.float32, device=self.device)
         nb = 0
+        # training.cuda_graph: replay the step from a CUDA graph (one per batch shape; a ragged last batch is captured
+        # separately) - worth it when the batch is small enough for launch overhead to show
+        step = self.train_step_graphed if self.config.get("training", {}).get("cuda_graph", False) else self.train_step
         for images, masks in device_feeder(((b["image"], b["mask"]) for b in self.train_loader), self.device):
-            r = self.train_step(images, masks)
+            r = step(images, masks)
             running += r.stats
             nb += 1
         v = (running / max(nb, 1)).tolist()

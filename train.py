@@ -116,6 +116,7 @@ if __name__ == "__main__":
     ap.add_argument("--augmentation", type=lambda x: str(x).lower() == "true")
     ap.add_argument("--synthetic", type=int, default=0, help="train on this many generated batches instead of dataset.train_dir")
     ap.add_argument("--epochs", type=int, help="override training.num_epochs")
+    ap.add_argument("--cuda_graph", action="store_true", help="replay each training step from a CUDA graph")
     a = ap.parse_args()
     with open(normalize_path(a.config), "r", encoding="utf-8") as f:
         cfg = yaml.safe_load(f)
@@ -130,4 +131,6 @@ if __name__ == "__main__":
         cfg.setdefault("dataset", {})["augmentation"] = a.augmentation
     if a.epochs is not None:
         cfg["training"]["num_epochs"] = a.epochs
+    if a.cuda_graph:
+        cfg["training"]["cuda_graph"] = True
     main(cfg, a.resume, a.synthetic)
