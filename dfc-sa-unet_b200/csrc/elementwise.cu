@@ -863,6 +863,39 @@ colsum_kernel(const void* x, int dt, long long ld, long long M, int C, float* ou
     atomicAdd(out + c, t);
   }
 }
+// 16-bit inputs with C % 8 == 0: 16-byte loads, the (channel-lane, pixel-lane) layout of the other streaming kernels
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* x, long long ld, long long M, int C, float* out, int CL, int PL) {
+  __shared__ float s_red[256 * 8];
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * 8;
+  const int c = c_base + cl * 8;
+  float acc[8];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+  if (pl < PL && c < C) {
+    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
+      float t[8];
+      load8<T>(x + m * ld + c, t);
+#pragma unroll
+      for (int v = 0; v < 8; ++v) acc[v] += t[v];
+    }
+  }
+  const int row = CL * 8;
+  if (cl < CL && pl < PL) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) s_red[pl * row + cl * 8 + v] = acc[v];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < row; idx += blockDim.x) {
+    if (c_base + idx < C) {
+      float t = 0.f;
+      for (int p = 0; p < PL; ++p) t += s_red[p * row + idx];
+      atomicAdd(out + c_base + idx, t);
+    }
+  }
+}
 __global__ void cast2d_kernel(const void* x, int xdt, long long ld_x, void* y, int ydt, long long ld_y, long long M, int C) {
   const long long total = M * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -1115,6 +1148,14 @@ extern "C" int dfcsa_nhwc_to_nchw(const void* src, int src_dtype, int64_t ld, fl
 }
 extern "C" int dfcsa_colsum(const void* x, int x_dtype, int64_t ld, int64_t M, int32_t C, float* out, void* stream) {
   DFCSA_CHECK_ARG(x && out && M > 0 && C > 0, "dfcsa_colsum: bad args");
+  if (x_dtype != DFCSA_F32 && vec8_ok(C, {ld}, {x})) {
+    const RedGeom g = red_geom(C, 8);
+    dim3 grid(red_blocks(M, g.PL, g.chunks, 4), g.chunks);
+    if (x_dtype == DFCSA_F16) colsum_vec_kernel<__half><<<grid, 256, 0, ST>>>(reinterpret_cast<const __half*>(x), ld, M, C, out, g.CL, g.PL);
+    else colsum_vec_kernel<__nv_bfloat16><<<grid, 256, 0, ST>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, M, C, out, g.CL, g.PL);
+    DFCSA_LAUNCH_CHECK("colsum_vec_kernel");
+    return DFCSA_OK;
+  }
   dim3 grid(static_cast<unsigned>(std::max<long long>(1, std::min<long long>((M + 63) / 64, 148 * 4))), (C + 31) / 32);
   colsum_kernel<<<grid, 256, 0, ST>>>(x, x_dtype, ld, M, C, out);
   DFCSA_LAUNCH_CHECK("colsum_kernel");

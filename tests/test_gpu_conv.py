@@ -85,6 +85,9 @@ CASES = [
     (1, 16, 16, [128], "1", 64, {"bias": True, "out_dt": torch.float32}),
     (1, 16, 16, [64], "1", 128, {"accumulate": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
     (1, 4, 4, [512], "3", 1024, {}),                     # deep K, several n tiles
+    (3, 13, 21, [128], "3", 96, {"stats": True}),        # halo-box 3x3 path: ragged 8x16 patches, N not a power of two
+    (2, 17, 9, [64, 64], "31", 128, {"stats": True}),    # 3x3 + 1x1 segments through the halo-box path, W < 16
+    (1, 40, 24, [64], "3", 256, {"stats": True}),        # N = 256: the box-per-tap 3x3 path
 ]
 _MODE = {"1": 0, "3": 1, "2": 2}
 
@@ -347,3 +350,17 @@ def test_conv_wgrad_fp16_activation_bf16_gradient(cuda, case):
     ops.conv_wgrad(B, H, W, x16.reshape(-1, Cc), xm, dy.reshape(-1, N), dm, dw, backend=0)
     torch.cuda.synchronize()
     assert _rel_err(dw, ref) < 2e-3
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("M,C,ld", [(1000, 64, 128), (777, 320, 320), (5000, 8, 24), (300, 5, 5)])
+def test_colsum(cuda, M, C, ld, dt):
+    """dfcsa_colsum: out[c] += sum_m x[m, c] on a channel slice of a wider buffer (bias gradients)."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(29)
+    buf = torch.randn(M, ld, generator=g).cuda().to(dt)
+    x = buf[:, :C]
+    out = torch.full((C,), 0.5, device=cuda)
+    ops.colsum(x, out)
+    torch.cuda.synchronize()
+    assert _rel_err(out, x.float().sum(0) + 0.5) < 1e-4
