@@ -34,6 +34,9 @@ struct BgemmArgs {
   void* C; long long c_b, ld_c; int c_dtype;
   int wide;                 // 32-byte stores legal
   uint32_t idesc;
+  int epi_mode;             // DFCSA_BGEMM_EPI_*
+  float* rowstat;           // ROWSTATS: [batch, M, 2*n_tiles, 2] (max, sum of exp) partials, C is not written
+  const float* lse;         // EXP: [batch, M] log-sum-exp per row; C = exp(acc - lse)
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -147,6 +150,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const bool valid = m < a.M;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
+      float run_max = -INFINITY, run_sum = 0.f;                         // ROWSTATS: this thread's columns of the tile
+      const float row_lse = (a.epi_mode == DFCSA_BGEMM_EPI_EXP && valid) ? a.lse[b * a.M + m] : 0.f;
       for (int ch = half; ch < a.block_n / 32; ch += 2) {
         const int n0 = nt * a.block_n + ch * 32;
         if (n0 >= a.N) break;
@@ -154,6 +159,22 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + as * kAccStride + ch * 32 + (static_cast<uint32_t>(ew * 32) << 16), raw);
         tmem_ld_wait();
+        if (a.epi_mode == DFCSA_BGEMM_EPI_ROWSTATS) {
+          float cmax = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < ncols) cmax = fmaxf(cmax, __uint_as_float(raw[i]));
+          const float nmax = fmaxf(run_max, cmax);
+          float part = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (i < ncols) part += __expf(__uint_as_float(raw[i]) - nmax);
+          run_sum = run_sum * (run_max == nmax ? 1.f : __expf(run_max - nmax)) + part;
+          run_max = nmax;
+          continue;
+        }
+        if (a.epi_mode == DFCSA_BGEMM_EPI_EXP) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__expf(__uint_as_float(raw[i]) - row_lse));
+        }
         if (valid) {
           const long long off = b * a.c_b + static_cast<long long>(m) * a.ld_c + n0;
           if (a.c_dtype == DFCSA_F32) {
@@ -190,6 +211,10 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           }
         }
       }
+      if (a.epi_mode == DFCSA_BGEMM_EPI_ROWSTATS && valid) {
+        float* rs = a.rowstat + ((b * a.M + m) * (2LL * a.n_tiles) + 2 * nt + half) * 2;
+        rs[0] = run_max; rs[1] = run_sum;      // (-inf, 0) when this half had no columns
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
@@ -211,11 +236,14 @@ std::once_flag g_attr_once;
 int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->batch > 0 && p->M > 0 && p->N > 0 && p->K > 0, "dfcsa_bgemm: empty problem");
   DFCSA_CHECK_ARG(p->ab_dtype == DFCSA_F16 || p->ab_dtype == DFCSA_BF16, "dfcsa_bgemm: operands must be fp16 or bf16");
-  DFCSA_CHECK_ARG(p->A && p->B && p->C, "dfcsa_bgemm: null pointer");
+  DFCSA_CHECK_ARG(p->A && p->B && (p->C || p->epi_mode == DFCSA_BGEMM_EPI_ROWSTATS), "dfcsa_bgemm: null pointer");
+  DFCSA_CHECK_ARG(p->epi_mode == DFCSA_BGEMM_EPI_NONE || (p->epi_mode == DFCSA_BGEMM_EPI_ROWSTATS && p->rowstat) ||
+                  (p->epi_mode == DFCSA_BGEMM_EPI_EXP && p->lse), "dfcsa_bgemm: bad epilogue arguments");
   DFCSA_CHECK_ARG(p->ld_a % 8 == 0 && p->ld_b % 8 == 0 && p->a_b % 8 == 0 && p->b_b % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
                   "dfcsa_bgemm: operand pitches / batch strides must be multiples of 8 elements and bases 16-byte aligned");
-  DFCSA_CHECK_ARG(p->N % 8 == 0 && p->ld_c % 8 == 0 && p->c_b % 8 == 0 && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0,
+  DFCSA_CHECK_ARG(p->epi_mode == DFCSA_BGEMM_EPI_ROWSTATS ||
+                  (p->N % 8 == 0 && p->ld_c % 8 == 0 && p->c_b % 8 == 0 && (reinterpret_cast<uintptr_t>(p->C) & 15) == 0),
                   "dfcsa_bgemm: N, ld_c, c_b must be multiples of 8 and C 16-byte aligned");
   BgemmArgs a{};
   a.batch = p->batch; a.M = p->M; a.N = p->N; a.K = p->K;
@@ -237,6 +265,7 @@ int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
   a.stages = std::min(kMaxStages, (kSmemBudget - 1024) / stage_bytes);
   a.idesc = umma_idesc_f16(128, block_n, umma_fmt(p->ab_dtype), umma_fmt(p->ab_dtype), a.a_mn, a.b_mn);
   a.C = p->C; a.c_b = p->c_b; a.ld_c = p->ld_c; a.c_dtype = p->c_dtype;
+  a.epi_mode = p->epi_mode; a.rowstat = p->rowstat; a.lse = p->lse;
   a.wide = p->c_dtype != DFCSA_F32 && p->ld_c % 16 == 0 && p->c_b % 16 == 0 && (reinterpret_cast<uintptr_t>(p->C) & 31) == 0;
 
   CUtensorMap map_a, map_b;
@@ -275,6 +304,41 @@ int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
 }
 
 }  // namespace dfcsa
+
+namespace dfcsa {
+namespace {
+// lse[r] = log sum_j exp(S[r, j]) from the per-tile partials (max_i, sum_i) written by the ROWSTATS epilogue
+__global__ void lse_combine_kernel(const float* __restrict__ rowstat, int parts, long long rows, float* __restrict__ lse) {
+  const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* p = rowstat + r * parts * 2;
+  float mx = -INFINITY;
+  for (int i = 0; i < parts; ++i) mx = fmaxf(mx, p[2 * i]);
+  float s = 0.f;
+  for (int i = 0; i < parts; ++i) if (p[2 * i + 1] > 0.f) s += p[2 * i + 1] * __expf(p[2 * i] - mx);
+  lse[r] = mx + logf(s);
+}
+}  // namespace
+}  // namespace dfcsa
+
+extern "C" int dfcsa_bgemm_rowstat_parts(int32_t N) {
+  int block_n = N <= 256 ? (N + 31) / 32 * 32 : 256;
+  if (N > 256) {
+    int best_pad = 1 << 30;
+    for (int bn = 256; bn >= 128; bn -= 64) {
+      const int pad = (N + bn - 1) / bn * bn;
+      if (pad < best_pad) { best_pad = pad; block_n = bn; }
+    }
+  }
+  return 2 * ((N + block_n - 1) / block_n);
+}
+
+extern "C" int dfcsa_lse_combine(const float* rowstat, int32_t parts, int64_t rows, float* lse, void* stream) {
+  DFCSA_CHECK_ARG(rowstat && lse && parts > 0 && rows > 0, "dfcsa_lse_combine: bad args");
+  dfcsa::lse_combine_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowstat, parts, rows, lse);
+  DFCSA_LAUNCH_CHECK("lse_combine_kernel");
+  return DFCSA_OK;
+}
 
 extern "C" int dfcsa_bgemm(const dfcsa_bgemm_params_t* p, void* stream) {
   DFCSA_CHECK_ARG(p != nullptr, "dfcsa_bgemm: null params");

@@ -69,7 +69,8 @@ class BgemmParams(C.Structure):
                 ("A", C.c_void_p), ("a_b", C.c_int64), ("ld_a", C.c_int64), ("a_mn_major", C.c_int32),
                 ("B", C.c_void_p), ("b_b", C.c_int64), ("ld_b", C.c_int64), ("b_mn_major", C.c_int32),
                 ("ab_dtype", C.c_int32),
-                ("C", C.c_void_p), ("c_b", C.c_int64), ("ld_c", C.c_int64), ("c_dtype", C.c_int32)]
+                ("C", C.c_void_p), ("c_b", C.c_int64), ("ld_c", C.c_int64), ("c_dtype", C.c_int32),
+                ("epi_mode", C.c_int32), ("rowstat", C.c_void_p), ("lse", C.c_void_p)]
 
 
 class PackJob(C.Structure):
@@ -86,7 +87,7 @@ class ParamDesc(C.Structure):
 # every symbol include/dfcsa.h declares (the CPU test checks the .so exports exactly these)
 SYMBOLS = [
     "dfcsa_version", "dfcsa_last_error", "dfcsa_device_ok",
-    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm", "dfcsa_bgemm", "dfcsa_attn_small_fwd", "dfcsa_attn_small_bwd",
+    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm", "dfcsa_bgemm", "dfcsa_bgemm_rowstat_parts", "dfcsa_lse_combine", "dfcsa_attn_small_fwd", "dfcsa_attn_small_bwd",
     "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd", "dfcsa_softmax_rows_bwd_d", "dfcsa_rowdot",
     "dfcsa_bn_finalize", "dfcsa_bn_eval_affine",
     "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd",

@@ -232,11 +232,13 @@ def _attn_chunk(B, N):
 def _attn_probs(qkv, nb, N, Cq, nq, out):
     """out[b] = softmax_j(q_i . k_j) for nb images; qkv: [nb*N, nq] rows (q | k | v).  fp32 qkv -> fp32 SIMT product;
     fp16 qkv -> tcgen05 batched GEMM (out is then usually fp16 too)."""
+    if qkv.dtype != F32:
+        # two tensor-core passes over q k^T (K = Cq is tiny): row log-sum-exp, then exp(s - lse) stored directly as the
+        # 16-bit probabilities - the [N, N] fp32 logits never exist in HBM
+        ops.softmax_bgemm(nb, N, N, Cq, qkv[:, :Cq], N * nq, nq, qkv[:, Cq:2 * Cq], N * nq, nq, out)
+        return
     S = _e((nb, N, N), F32, qkv.device)
-    if qkv.dtype == F32:
-        ops.sgemm(nb, N, N, Cq, qkv[:, :Cq], (N * nq, nq, 1), qkv[:, Cq:2 * Cq], (N * nq, 1, nq), S, (N * N, N, 1))
-    else:
-        ops.bgemm(nb, N, N, Cq, qkv[:, :Cq], N * nq, nq, False, qkv[:, Cq:2 * Cq], N * nq, nq, False, S, N * N, N)
+    ops.sgemm(nb, N, N, Cq, qkv[:, :Cq], (N * nq, nq, 1), qkv[:, Cq:2 * Cq], (N * nq, 1, nq), S, (N * N, N, 1))
     ops.softmax_rows(S, out)
 
 

@@ -140,15 +140,31 @@ def attn_small_bwd(qkv, attn, d_o, B, N, Cq, Cn, dqkv):
     L.call("dfcsa_attn_small_bwd", L.ptr(qkv), _i64(qkv.stride(0)), L.ptr(attn), L.ptr(d_o), B, N, Cq, Cn, L.ptr(dqkv), L.stream())
 
 
-def bgemm(batch, M, N, K, A, a_b, ld_a, a_mn, Bm, b_b, ld_b, b_mn, Cm, c_b, ld_c):
+def softmax_bgemm(batch, M, N, K, A, a_b, ld_a, Bm, b_b, ld_b, out):
+    """out[b] = softmax_rows(A[b] @ B[b]^T) (both operands K-major) in two tcgen05 launches that never write the logits:
+    a row-statistics pass (ROWSTATS epilogue + dfcsa_lse_combine) and a pass whose epilogue stores exp(x - lse)."""
+    parts = L.lib().dfcsa_bgemm_rowstat_parts(N)
+    dev = A.device
+    rowstat = torch.empty((batch * M, parts, 2), dtype=torch.float32, device=dev)
+    lse = torch.empty((batch * M,), dtype=torch.float32, device=dev)
+    bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, None, 0, 0, epi=1, rowstat=rowstat)
+    L.call("dfcsa_lse_combine", L.ptr(rowstat), parts, C.c_int64(batch * M), L.ptr(lse), L.stream())
+    bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, out, M * N, N, epi=2, lse=lse)
+
+
+def bgemm(batch, M, N, K, A, a_b, ld_a, a_mn, Bm, b_b, ld_b, b_mn, Cm, c_b, ld_c, epi=0, rowstat=None, lse=None):
     """C[b] = A[b] @ B[b] on tcgen05 (dfcsa_bgemm); operands 16-bit of one dtype, K-major or MN-major (see dfcsa.h)."""
     p = L.BgemmParams()
+    p.epi_mode = epi
+    p.rowstat = rowstat.data_ptr() if rowstat is not None else None
+    p.lse = lse.data_ptr() if lse is not None else None
     p.batch, p.M, p.N, p.K = batch, M, N, K
     p.A, p.a_b, p.ld_a, p.a_mn_major = A.data_ptr(), a_b, ld_a, 1 if a_mn else 0
     p.B, p.b_b, p.ld_b, p.b_mn_major = Bm.data_ptr(), b_b, ld_b, 1 if b_mn else 0
     p.ab_dtype = L.dt(A)
     assert A.dtype == Bm.dtype
-    p.C, p.c_b, p.ld_c, p.c_dtype = Cm.data_ptr(), c_b, ld_c, L.dt(Cm)
+    if Cm is not None:
+        p.C, p.c_b, p.ld_c, p.c_dtype = Cm.data_ptr(), c_b, ld_c, L.dt(Cm)
     L.call("dfcsa_bgemm", C.byref(p), L.stream(), tag="bgemm_tc", flops=2.0 * batch * M * N * K,
            desc=f"b={batch} M={M} N={N} K={K} a_mn={int(a_mn)} b_mn={int(b_mn)}")
 

@@ -282,6 +282,24 @@ def test_bgemm_all_layouts(cuda, batch, M, N, K, a_mn, b_mn, dtype):
         assert _rel_err(Cm, ref) < tol
 
 
+@pytest.mark.parametrize("batch,N,K", [(2, 64, 8), (1, 200, 16), (3, 256, 8), (1, 1048, 64), (1, 3136, 8)])
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_softmax_bgemm(cuda, batch, N, K, dtype):
+    """softmax(q k^T) through the ROWSTATS / EXP epilogues of dfcsa_bgemm equals torch.softmax of the fp32 product of
+    the same 16-bit operands; rows sum to one; ragged tiles (N not a multiple of the tile) and multi-tile rows."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(23)
+    q = (torch.randn(batch, N, K, generator=g) * 1.5).cuda().to(dtype)
+    k = (torch.randn(batch, N, K, generator=g) * 1.5).cuda().to(dtype)
+    ref = torch.softmax(torch.bmm(q.float(), k.float().transpose(1, 2)), -1)
+    for odt, tol in ((torch.float16, 2e-3), (torch.bfloat16, 8e-3)):
+        out = torch.full((batch, N, N), float("nan"), device=cuda, dtype=odt)
+        ops.softmax_bgemm(batch, N, N, K, q, N * K, K, k, N * K, K, out)
+        torch.cuda.synchronize()
+        assert _rel_err(out, ref) < tol
+        assert (out.float().sum(-1) - 1).abs().max() < (4e-3 if odt == torch.float16 else 2e-2)
+
+
 @pytest.mark.parametrize("cols", [16, 100, 4096])
 def test_softmax_rows_16bit(cuda, cols):
     from dfcsa import ops
