@@ -34,9 +34,10 @@ struct BgemmArgs {
   void* C; long long c_b, ld_c; int c_dtype;
   int wide;                 // 32-byte stores legal
   uint32_t idesc;
-  int epi_mode;             // DFCSA_BGEMM_EPI_*
-  float* rowstat;           // ROWSTATS: [batch, M, 2*n_tiles, 2] (max, sum of exp) partials, C is not written
-  const float* lse;         // EXP: [batch, M] log-sum-exp per row; C = exp(acc - lse)
+  float* rowstat;           // ROWSTATS: [batch, 2*n_tiles, M, 2] (max, sum of exp) partials, C is not written
+  const float* rowvec;      // EXP: [batch, M] log-sum-exp per row, C = exp(acc - lse);  SOFTMAX_BWD: D, C = aux * (acc - D)
+  const void* aux;          // SOFTMAX_BWD: the probabilities, laid out like C
+  int aux_dtype;
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
@@ -46,6 +47,126 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void load_256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+__device__ __forceinline__ float f16bits_to_float(uint32_t w, int hi, int dtype) {
+  const unsigned short h = hi ? static_cast<unsigned short>(w >> 16) : static_cast<unsigned short>(w & 0xffffu);
+  if (dtype == DFCSA_F16) return __half2float(__ushort_as_half(h));
+  return __uint_as_float(static_cast<uint32_t>(h) << 16);
+}
+
+// What the epilogue does with one accumulator row (one thread = one row of the 128-row tile), 32 columns at a time.
+template <int EPI>
+struct EpiRow {
+  float run_max, run_sum;     // ROWSTATS (log2 domain)
+  float rowc;                 // EXP: lse * log2(e);  SOFTMAX_BWD: D
+
+  __device__ __forceinline__ void init(const BgemmArgs& a, long long b, int m, bool valid) {
+    run_max = -INFINITY; run_sum = 0.f; rowc = 0.f;
+    if (EPI == DFCSA_BGEMM_EPI_EXP && valid) rowc = a.rowvec[b * a.M + m] * kLog2e;
+    if (EPI == DFCSA_BGEMM_EPI_SOFTMAX_BWD && valid) rowc = a.rowvec[b * a.M + m];
+  }
+
+  // SOFTMAX_BWD: the 32 probabilities next to this chunk, 64 bytes per thread
+  __device__ __forceinline__ void prefetch(const BgemmArgs& a, long long off, int ncols, bool valid, uint32_t (&x)[16]) {
+    if (EPI != DFCSA_BGEMM_EPI_SOFTMAX_BWD) return;
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(a.aux) + off;
+    if (valid && a.wide && ncols == 32) {
+      load_256(src, x);
+      load_256(src + 16, x + 8);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (valid && g * 8 < ncols) v = __ldg(reinterpret_cast<const uint4*>(src + g * 8));
+        x[g * 4] = v.x; x[g * 4 + 1] = v.y; x[g * 4 + 2] = v.z; x[g * 4 + 3] = v.w;
+      }
+    }
+  }
+
+  __device__ __forceinline__ void chunk(const BgemmArgs& a, uint32_t (&raw)[32], const uint32_t (&x)[16], long long off, int ncols,
+                                        bool valid) {
+    if (EPI == DFCSA_BGEMM_EPI_ROWSTATS) {
+      float cmax = -INFINITY;
+      if (ncols == 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) cmax = fmaxf(cmax, __uint_as_float(raw[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i < ncols) cmax = fmaxf(cmax, __uint_as_float(raw[i]));
+      }
+      const float nmax = fmaxf(run_max, cmax * kLog2e);
+      float p0 = 0.f, p1 = 0.f;
+      if (ncols == 32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          p0 += ex2f(fmaf(__uint_as_float(raw[i]), kLog2e, -nmax));
+          p1 += ex2f(fmaf(__uint_as_float(raw[i + 1]), kLog2e, -nmax));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i < ncols) p0 += ex2f(fmaf(__uint_as_float(raw[i]), kLog2e, -nmax));
+      }
+      run_sum = run_sum * (run_max == nmax ? 1.f : ex2f(run_max - nmax)) + (p0 + p1);
+      run_max = nmax;
+      return;
+    }
+    if (EPI == DFCSA_BGEMM_EPI_EXP) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(ex2f(fmaf(__uint_as_float(raw[i]), kLog2e, -rowc)));
+    }
+    if (EPI == DFCSA_BGEMM_EPI_SOFTMAX_BWD) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        raw[i] = __float_as_uint(f16bits_to_float(x[i >> 1], i & 1, a.aux_dtype) * (__uint_as_float(raw[i]) - rowc));
+    }
+    if (!valid) return;
+    if (a.c_dtype == DFCSA_F32) {
+      float* dst = reinterpret_cast<float*>(a.C) + off;
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        if (g * 4 < ncols)
+          *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(raw[g * 4]), __uint_as_float(raw[g * 4 + 1]),
+                                                                __uint_as_float(raw[g * 4 + 2]), __uint_as_float(raw[g * 4 + 3]));
+      return;
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      if (g * 16 < ncols) {
+        float t[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(raw[g * 16 + i]);
+        if (a.wide && ncols - g * 16 >= 16) {
+          if (a.c_dtype == DFCSA_F16) store16_256<__half>(reinterpret_cast<__half*>(a.C) + off + g * 16, t);
+          else store16_256<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.C) + off + g * 16, t);
+        } else {
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            if (g * 16 + h8 * 8 < ncols) {
+              float u[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) u[i] = t[h8 * 8 + i];
+              if (a.c_dtype == DFCSA_F16) store8<__half>(reinterpret_cast<__half*>(a.C) + off + g * 16 + h8 * 8, u);
+              else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.C) + off + g * 16 + h8 * 8, u);
+            }
+          }
+        }
+      }
+    }
+  }
+};
+
+template <int EPI>
 __global__ void __launch_bounds__(384, 1)
 bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                 const __grid_constant__ BgemmArgs a) {
@@ -150,70 +271,44 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const bool valid = m < a.M;
       mbar_wait(&tmem_full_bar[as], aphase);
       tc_fence_after();
-      float run_max = -INFINITY, run_sum = 0.f;                         // ROWSTATS: this thread's columns of the tile
-      const float row_lse = (a.epi_mode == DFCSA_BGEMM_EPI_EXP && valid) ? a.lse[b * a.M + m] : 0.f;
-      for (int ch = half; ch < a.block_n / 32; ch += 2) {
-        const int n0 = nt * a.block_n + ch * 32;
-        if (n0 >= a.N) break;
-        const int ncols = min(32, a.N - n0);
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + as * kAccStride + ch * 32 + (static_cast<uint32_t>(ew * 32) << 16), raw);
-        tmem_ld_wait();
-        if (a.epi_mode == DFCSA_BGEMM_EPI_ROWSTATS) {
-          float cmax = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (i < ncols) cmax = fmaxf(cmax, __uint_as_float(raw[i]));
-          const float nmax = fmaxf(run_max, cmax);
-          float part = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) if (i < ncols) part += __expf(__uint_as_float(raw[i]) - nmax);
-          run_sum = run_sum * (run_max == nmax ? 1.f : __expf(run_max - nmax)) + part;
-          run_max = nmax;
-          continue;
-        }
-        if (a.epi_mode == DFCSA_BGEMM_EPI_EXP) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) raw[i] = __float_as_uint(__expf(__uint_as_float(raw[i]) - row_lse));
-        }
-        if (valid) {
-          const long long off = b * a.c_b + static_cast<long long>(m) * a.ld_c + n0;
-          if (a.c_dtype == DFCSA_F32) {
-            float* dst = reinterpret_cast<float*>(a.C) + off;
-#pragma unroll
-            for (int g = 0; g < 8; ++g)
-              if (g * 4 < ncols)
-                *reinterpret_cast<float4*>(dst + g * 4) = make_float4(__uint_as_float(raw[g * 4]), __uint_as_float(raw[g * 4 + 1]),
-                                                                      __uint_as_float(raw[g * 4 + 2]), __uint_as_float(raw[g * 4 + 3]));
-          } else {
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-              if (g * 16 < ncols) {
-                float t[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) t[i] = __uint_as_float(raw[g * 16 + i]);
-                if (a.wide && ncols - g * 16 >= 16) {
-                  if (a.c_dtype == DFCSA_F16) store16_256<__half>(reinterpret_cast<__half*>(a.C) + off + g * 16, t);
-                  else store16_256<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.C) + off + g * 16, t);
-                } else {
-#pragma unroll
-                  for (int h8 = 0; h8 < 2; ++h8) {
-                    if (g * 16 + h8 * 8 < ncols) {
-                      float u[8];
-#pragma unroll
-                      for (int i = 0; i < 8; ++i) u[i] = t[h8 * 8 + i];
-                      if (a.c_dtype == DFCSA_F16) store8<__half>(reinterpret_cast<__half*>(a.C) + off + g * 16 + h8 * 8, u);
-                      else store8<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(a.C) + off + g * 16 + h8 * 8, u);
-                    }
-                  }
-                }
-              }
-            }
-          }
-        }
+      const uint32_t t_row = tmem_base + as * kAccStride + (static_cast<uint32_t>(ew * 32) << 16);
+      const long long row_off = b * a.c_b + static_cast<long long>(m) * a.ld_c;
+      const int n_tile0 = nt * a.block_n;
+      const int nchunks = min(a.block_n, a.N - n_tile0 + 31) / 32;       // chunks of this tile that hold real columns
+      EpiRow<EPI> row;
+      row.init(a, b, m, valid);
+      // two register buffers: the tcgen05.ld (and the global loads of the softmax-backward operand) of the next chunk
+      // are in flight while the current one is processed
+      uint32_t r0[32], r1[32];
+      uint32_t x0[16], x1[16];
+      int ch = half;
+      if (ch < nchunks) {
+        tmem_ld_32x32(t_row + ch * 32, r0);
+        row.prefetch(a, row_off + n_tile0 + ch * 32, min(32, a.N - n_tile0 - ch * 32), valid, x0);
       }
-      if (a.epi_mode == DFCSA_BGEMM_EPI_ROWSTATS && valid) {
-        float* rs = a.rowstat + ((b * a.M + m) * (2LL * a.n_tiles) + 2 * nt + half) * 2;
-        rs[0] = run_max; rs[1] = run_sum;      // (-inf, 0) when this half had no columns
+      while (ch < nchunks) {
+        tmem_ld_wait();
+        int nx = ch + 2;
+        if (nx < nchunks) {
+          tmem_ld_32x32(t_row + nx * 32, r1);
+          row.prefetch(a, row_off + n_tile0 + nx * 32, min(32, a.N - n_tile0 - nx * 32), valid, x1);
+        }
+        row.chunk(a, r0, x0, row_off + n_tile0 + ch * 32, min(32, a.N - n_tile0 - ch * 32), valid);
+        ch = nx;
+        if (ch >= nchunks) break;
+        tmem_ld_wait();
+        nx = ch + 2;
+        if (nx < nchunks) {
+          tmem_ld_32x32(t_row + nx * 32, r0);
+          row.prefetch(a, row_off + n_tile0 + nx * 32, min(32, a.N - n_tile0 - nx * 32), valid, x0);
+        }
+        row.chunk(a, r1, x1, row_off + n_tile0 + ch * 32, min(32, a.N - n_tile0 - ch * 32), valid);
+        ch = nx;
+      }
+      if (EPI == DFCSA_BGEMM_EPI_ROWSTATS && valid) {
+        // partial (max, sum exp(x - max)) of this thread's columns; (-inf, 0) when it had none.  [batch, part, M, 2]
+        float* rs = a.rowstat + ((b * (2LL * a.n_tiles) + 2 * nt + half) * a.M + m) * 2;
+        *reinterpret_cast<float2*>(rs) = make_float2(row.run_max * kLn2, row.run_sum);
       }
       tc_fence_before();
       __syncwarp();
@@ -238,7 +333,10 @@ int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->ab_dtype == DFCSA_F16 || p->ab_dtype == DFCSA_BF16, "dfcsa_bgemm: operands must be fp16 or bf16");
   DFCSA_CHECK_ARG(p->A && p->B && (p->C || p->epi_mode == DFCSA_BGEMM_EPI_ROWSTATS), "dfcsa_bgemm: null pointer");
   DFCSA_CHECK_ARG(p->epi_mode == DFCSA_BGEMM_EPI_NONE || (p->epi_mode == DFCSA_BGEMM_EPI_ROWSTATS && p->rowstat) ||
-                  (p->epi_mode == DFCSA_BGEMM_EPI_EXP && p->lse), "dfcsa_bgemm: bad epilogue arguments");
+                  (p->epi_mode == DFCSA_BGEMM_EPI_EXP && p->rowvec) ||
+                  (p->epi_mode == DFCSA_BGEMM_EPI_SOFTMAX_BWD && p->rowvec && p->aux && p->c_dtype != DFCSA_F32 &&
+                   (p->aux_dtype == DFCSA_F16 || p->aux_dtype == DFCSA_BF16) && (reinterpret_cast<uintptr_t>(p->aux) & 15) == 0),
+                  "dfcsa_bgemm: bad epilogue arguments");
   DFCSA_CHECK_ARG(p->ld_a % 8 == 0 && p->ld_b % 8 == 0 && p->a_b % 8 == 0 && p->b_b % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(p->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(p->B) & 15) == 0,
                   "dfcsa_bgemm: operand pitches / batch strides must be multiples of 8 elements and bases 16-byte aligned");
@@ -265,8 +363,9 @@ int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
   a.stages = std::min(kMaxStages, (kSmemBudget - 1024) / stage_bytes);
   a.idesc = umma_idesc_f16(128, block_n, umma_fmt(p->ab_dtype), umma_fmt(p->ab_dtype), a.a_mn, a.b_mn);
   a.C = p->C; a.c_b = p->c_b; a.ld_c = p->ld_c; a.c_dtype = p->c_dtype;
-  a.epi_mode = p->epi_mode; a.rowstat = p->rowstat; a.lse = p->lse;
-  a.wide = p->c_dtype != DFCSA_F32 && p->ld_c % 16 == 0 && p->c_b % 16 == 0 && (reinterpret_cast<uintptr_t>(p->C) & 31) == 0;
+  a.rowstat = p->rowstat; a.rowvec = p->rowvec; a.aux = p->aux; a.aux_dtype = p->aux_dtype;
+  a.wide = p->c_dtype != DFCSA_F32 && p->ld_c % 16 == 0 && p->c_b % 16 == 0 && (reinterpret_cast<uintptr_t>(p->C) & 31) == 0 &&
+           (p->epi_mode != DFCSA_BGEMM_EPI_SOFTMAX_BWD || (reinterpret_cast<uintptr_t>(p->aux) & 31) == 0);
 
   CUtensorMap map_a, map_b;
   uint64_t dims[3], strides[2];
@@ -293,12 +392,20 @@ int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
   const int smem_bytes = a.stages * stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(g_attr_once, [] {
-    attr_err = cudaFuncSetAttribute(bgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    attr_err = cudaFuncSetAttribute(bgemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(bgemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(bgemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(bgemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(bgemm_tc_kernel)");
   const long long total_tiles = static_cast<long long>(p->batch) * a.m_tiles * a.n_tiles;
   const int grid = static_cast<int>(std::min<long long>(total_tiles, num_sms()));
-  bgemm_tc_kernel<<<grid, 384, smem_bytes, stream>>>(map_a, map_b, a);
+  switch (p->epi_mode) {
+    case DFCSA_BGEMM_EPI_ROWSTATS:    bgemm_tc_kernel<1><<<grid, 384, smem_bytes, stream>>>(map_a, map_b, a); break;
+    case DFCSA_BGEMM_EPI_EXP:         bgemm_tc_kernel<2><<<grid, 384, smem_bytes, stream>>>(map_a, map_b, a); break;
+    case DFCSA_BGEMM_EPI_SOFTMAX_BWD: bgemm_tc_kernel<3><<<grid, 384, smem_bytes, stream>>>(map_a, map_b, a); break;
+    default:                          bgemm_tc_kernel<0><<<grid, 384, smem_bytes, stream>>>(map_a, map_b, a); break;
+  }
   DFCSA_LAUNCH_CHECK("bgemm_tc_kernel");
   return DFCSA_OK;
 }
@@ -308,14 +415,21 @@ int bgemm_tc(const dfcsa_bgemm_params_t* p, cudaStream_t stream) {
 namespace dfcsa {
 namespace {
 // lse[r] = log sum_j exp(S[r, j]) from the per-tile partials (max_i, sum_i) written by the ROWSTATS epilogue
-__global__ void lse_combine_kernel(const float* __restrict__ rowstat, int parts, long long rows, float* __restrict__ lse) {
+// (rowstat is [batch, parts, M, 2]: consecutive threads = consecutive rows read consecutive float2)
+__global__ void lse_combine_kernel(const float* __restrict__ rowstat, int parts, int M, long long rows, float* __restrict__ lse) {
   const long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (r >= rows) return;
-  const float* p = rowstat + r * parts * 2;
-  float mx = -INFINITY;
-  for (int i = 0; i < parts; ++i) mx = fmaxf(mx, p[2 * i]);
-  float s = 0.f;
-  for (int i = 0; i < parts; ++i) if (p[2 * i + 1] > 0.f) s += p[2 * i + 1] * __expf(p[2 * i] - mx);
+  const long long b = r / M;
+  const float2* p = reinterpret_cast<const float2*>(rowstat) + b * parts * M + (r - b * M);
+  float mx = -INFINITY, s = 0.f;                 // online merge, one pass over the partials
+  for (int i = 0; i < parts; ++i) {
+    const float2 v = __ldg(p + static_cast<long long>(i) * M);
+    if (v.y > 0.f) {
+      const float nm = fmaxf(mx, v.x);
+      s = s * __expf(mx - nm) + v.y * __expf(v.x - nm);
+      mx = nm;
+    }
+  }
   lse[r] = mx + logf(s);
 }
 }  // namespace
@@ -333,9 +447,10 @@ extern "C" int dfcsa_bgemm_rowstat_parts(int32_t N) {
   return 2 * ((N + block_n - 1) / block_n);
 }
 
-extern "C" int dfcsa_lse_combine(const float* rowstat, int32_t parts, int64_t rows, float* lse, void* stream) {
-  DFCSA_CHECK_ARG(rowstat && lse && parts > 0 && rows > 0, "dfcsa_lse_combine: bad args");
-  dfcsa::lse_combine_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowstat, parts, rows, lse);
+extern "C" int dfcsa_lse_combine(const float* rowstat, int32_t parts, int32_t batch, int32_t M, float* lse, void* stream) {
+  DFCSA_CHECK_ARG(rowstat && lse && parts > 0 && batch > 0 && M > 0, "dfcsa_lse_combine: bad args");
+  const long long rows = static_cast<long long>(batch) * M;
+  dfcsa::lse_combine_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(rowstat, parts, M, rows, lse);
   DFCSA_LAUNCH_CHECK("lse_combine_kernel");
   return DFCSA_OK;
 }

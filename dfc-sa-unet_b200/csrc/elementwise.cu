@@ -53,6 +53,24 @@ __device__ __forceinline__ void bilerp_taps(int d, int P, int s, int& i0, int& i
   l1 = src - static_cast<float>(i0);
 }
 
+// flat item -> (cv, j, y, b) with extents (CV, P, H, *): 32-bit divisions whenever the item count allows (the 64-bit
+// ones cost more than the few loads of an item when the pooled grid is fine)
+__device__ __forceinline__ void decode4(long long i, bool small, int CV, int P, int H, int& cv, int& j, int& y, long long& b) {
+  if (small) {
+    unsigned u = static_cast<unsigned>(i);
+    unsigned q = u / static_cast<unsigned>(CV); cv = static_cast<int>(u - q * CV); u = q;
+    q = u / static_cast<unsigned>(P); j = static_cast<int>(u - q * P); u = q;
+    q = u / static_cast<unsigned>(H); y = static_cast<int>(u - q * H);
+    b = q;
+  } else {
+    cv = static_cast<int>(i % CV);
+    long long r = i / CV;
+    j = static_cast<int>(r % P); r /= P;
+    y = static_cast<int>(r % H);
+    b = r / H;
+  }
+}
+
 // (b, y, x) of pixel m for a grid-stride walk, advanced without divisions
 struct PixIter {
   unsigned x, y, b, sx, sy, sb;
@@ -213,11 +231,8 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
   const long long total = static_cast<long long>(B) * H * P * CV;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % CV);
-    long long r = i / CV;
-    const int j = static_cast<int>(r % P); r /= P;
-    const int y = static_cast<int>(r % H);
-    const long long b = r / H;
+    int cv, j, y; long long b;
+    decode4(i, total < (1LL << 31), CV, P, H, cv, j, y, b);
     int lo, hi; pool_win(j, W, P, lo, hi);
     float sc[VEC], sh[VEC], acc[VEC];
     ldf<VEC>(scale + cv * VEC, sc); ldf<VEC>(shift + cv * VEC, sh);
@@ -244,11 +259,8 @@ cols_reduce_kernel(const float* tmp, int B, int H, int P, int C, int mode, const
   float dot = 0.f;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(idx % C);
-    long long r = idx / C;
-    const int j = static_cast<int>(r % P); r /= P;
-    const int i = static_cast<int>(r % P);
-    const long long b = r / P;
+    int c, j, i; long long b;
+    decode4(idx, total < (1LL << 31), C, P, P, c, j, i, b);
     float acc = 0.f;
     if (mode == 0) {
       int lo, hi; pool_win(i, H, P, lo, hi);
@@ -644,11 +656,9 @@ __global__ void bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, in
   const float ratio = static_cast<float>(W) / static_cast<float>(P);
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % CV) * VEC;
-    long long r = i / CV;
-    const int px = static_cast<int>(r % P); r /= P;
-    const int y = static_cast<int>(r % H);
-    const long long b = r / H;
+    int c, px, y; long long b;
+    decode4(i, total < (1LL << 31), CV, P, H, c, px, y, b);
+    c *= VEC;
     int lo = static_cast<int>(floorf((px - 0.5f) * ratio - 0.5f)) - 1;
     int hi = static_cast<int>(ceilf((px + 1.5f) * ratio - 0.5f)) + 1;
     lo = max(lo, 0); hi = min(hi, W - 1);
@@ -912,6 +922,26 @@ __global__ void cast2d_kernel(const void* x, int xdt, long long ld_x, void* y, i
   }
 }
 
+// 8 elements per thread (16-byte accesses on the 16-bit side); C % 8 == 0, pitches % 8 == 0, 16-byte aligned bases
+template <typename TX, typename TY>
+__global__ void __launch_bounds__(256) cast2d_vec_kernel(const TX* __restrict__ x, long long ld_x, TY* __restrict__ y, long long ld_y,
+                                                         long long M, int C8) {
+  const long long total = M * C8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    long long m; int c;
+    if (total < (1LL << 31)) {
+      const unsigned ii = static_cast<unsigned>(i);
+      m = ii / static_cast<unsigned>(C8); c = static_cast<int>(ii - static_cast<unsigned>(m) * C8) * 8;
+    } else {
+      m = i / C8; c = static_cast<int>(i - m * C8) * 8;
+    }
+    float t[8];
+    load8<TX>(x + m * ld_x + c, t);
+    store8<TY>(y + m * ld_y + c, t);
+  }
+}
+
 static int ew_blocks(long long total) {
   return static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, 148LL * 32)));
 }
@@ -1164,6 +1194,21 @@ extern "C" int dfcsa_colsum(const void* x, int x_dtype, int64_t ld, int64_t M, i
 extern "C" int dfcsa_cast2d(const void* x, int x_dtype, int64_t ld_x, void* y, int y_dtype, int64_t ld_y, int64_t M,
                             int32_t C, void* stream) {
   DFCSA_CHECK_ARG(x && y && M > 0 && C > 0, "dfcsa_cast2d: bad args");
+  if (C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
+      x_dtype != y_dtype) {
+    const int C8 = C / 8;
+    const int blocks = ew_blocks(M * C8);
+#define DFCSA_CAST(TX, TY) cast2d_vec_kernel<TX, TY><<<blocks, 256, 0, ST>>>(reinterpret_cast<const TX*>(x), ld_x, reinterpret_cast<TY*>(y), ld_y, M, C8)
+    if (x_dtype == DFCSA_F32 && y_dtype == DFCSA_F16) DFCSA_CAST(float, __half);
+    else if (x_dtype == DFCSA_F32 && y_dtype == DFCSA_BF16) DFCSA_CAST(float, __nv_bfloat16);
+    else if (x_dtype == DFCSA_F16 && y_dtype == DFCSA_F32) DFCSA_CAST(__half, float);
+    else if (x_dtype == DFCSA_BF16 && y_dtype == DFCSA_F32) DFCSA_CAST(__nv_bfloat16, float);
+    else if (x_dtype == DFCSA_F16 && y_dtype == DFCSA_BF16) DFCSA_CAST(__half, __nv_bfloat16);
+    else DFCSA_CAST(__nv_bfloat16, __half);
+#undef DFCSA_CAST
+    DFCSA_LAUNCH_CHECK("cast2d_vec_kernel");
+    return DFCSA_OK;
+  }
   cast2d_kernel<<<ew_blocks(M * C), 256, 0, ST>>>(x, x_dtype, ld_x, y, y_dtype, ld_y, M, C);
   DFCSA_LAUNCH_CHECK("cast2d_kernel");
   return DFCSA_OK;

@@ -70,7 +70,8 @@ class BgemmParams(C.Structure):
                 ("B", C.c_void_p), ("b_b", C.c_int64), ("ld_b", C.c_int64), ("b_mn_major", C.c_int32),
                 ("ab_dtype", C.c_int32),
                 ("C", C.c_void_p), ("c_b", C.c_int64), ("ld_c", C.c_int64), ("c_dtype", C.c_int32),
-                ("epi_mode", C.c_int32), ("rowstat", C.c_void_p), ("lse", C.c_void_p)]
+                ("epi_mode", C.c_int32), ("rowstat", C.c_void_p), ("rowvec", C.c_void_p),
+                ("aux", C.c_void_p), ("aux_dtype", C.c_int32)]
 
 
 class PackJob(C.Structure):

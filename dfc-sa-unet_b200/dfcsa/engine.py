@@ -229,13 +229,14 @@ def _attn_chunk(B, N):
     return max(1, min(B, _ATTN_CHUNK_BYTES // (N * N * 4)))
 
 
-def _attn_probs(qkv, nb, N, Cq, nq, out):
+def _attn_probs(qkv, nb, N, Cq, nq, out, lse=None, have_lse=False):
     """out[b] = softmax_j(q_i . k_j) for nb images; qkv: [nb*N, nq] rows (q | k | v).  fp32 qkv -> fp32 SIMT product;
-    fp16 qkv -> tcgen05 batched GEMM (out is then usually fp16 too)."""
+    fp16 qkv -> tcgen05 batched GEMM (out is then usually fp16 too).  lse: optional [nb*N] fp32 that receives the row
+    log-sum-exp (have_lse: it already holds it - the backward recompute - and the statistics pass is skipped)."""
     if qkv.dtype != F32:
         # two tensor-core passes over q k^T (K = Cq is tiny): row log-sum-exp, then exp(s - lse) stored directly as the
         # 16-bit probabilities - the [N, N] fp32 logits never exist in HBM
-        ops.softmax_bgemm(nb, N, N, Cq, qkv[:, :Cq], N * nq, nq, qkv[:, Cq:2 * Cq], N * nq, nq, out)
+        ops.softmax_bgemm(nb, N, N, Cq, qkv[:, :Cq], N * nq, nq, qkv[:, Cq:2 * Cq], N * nq, nq, out, lse=lse, have_lse=have_lse)
         return
     S = _e((nb, N, N), F32, qkv.device)
     ops.sgemm(nb, N, N, Cq, qkv[:, :Cq], (N * nq, nq, 1), qkv[:, Cq:2 * Cq], (N * nq, 1, nq), S, (N * N, N, 1))
@@ -285,19 +286,21 @@ def attention_forward(bp, pk, pooled, B, N, ctx=None):
     keep_attn = ctx is not None and B * N * N * (2 if tca else 4) <= _ATTN_SAVE_BYTES
     attn = _e((B, N, N), adt, dev) if keep_attn else None
     o = _e((B, N, C), F32, dev)
+    # probabilities not kept: the backward recomputes them from the row log-sum-exp saved here (one GEMM pass, not two)
+    lse = _e((BN,), F32, dev) if (tca and ctx is not None and not keep_attn) else None
     ch = _attn_chunk(B, N)
     for b0 in range(0, B, ch):
         nb = min(ch, B - b0)
         rows = slice(b0 * N, (b0 + nb) * N)
         A = attn[b0:b0 + nb] if keep_attn else _e((nb, N, N), adt, dev)
-        _attn_probs(qsrc[rows], nb, N, Cq, nq, A)
+        _attn_probs(qsrc[rows], nb, N, Cq, nq, A, lse=lse[rows] if lse is not None else None)
         v = qsrc[rows, 2 * Cq:]
         if tca:     # o[i,c] = sum_j attn[i,j] v[j,c]: A K-major, V read MN-major (rows = keys)
             ops.bgemm(nb, N, C, N, A, N * N, N, False, v, N * nq, nq, True, o[b0:b0 + nb], N * C, C)
         else:
             ops.sgemm(nb, N, C, N, A, (N * N, N, 1), v, (N * nq, nq, 1), o[b0:b0 + nb], (N * C, C, 1))
     if ctx is not None:
-        ctx.qkv, ctx.attn, ctx.qkv16 = qkv, attn, (qsrc if tca else None)
+        ctx.qkv, ctx.attn, ctx.qkv16, ctx.lse = qkv, attn, (qsrc if tca else None), lse
         ctx.pooled_w = p16                                 # weight-gradient operand (fp16, or fp32 on the SIMT path)
     return o
 
@@ -329,7 +332,7 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
             A = attn[b0:b0 + nb]
         elif tca:                              # not saved (too large): recompute the probabilities, straight to bf16
             A = _e((nb, N, N), BF16, dev)
-            _attn_probs(ctx.qkv16[rows], nb, N, Cq, nq, A)
+            _attn_probs(ctx.qkv16[rows], nb, N, Cq, nq, A, lse=ctx.lse[rows], have_lse=True)
         else:
             A = _e((nb, N, N), F32, dev)
             _attn_probs(qkv[rows], nb, N, Cq, nq, A)
@@ -342,10 +345,10 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
                 Ab = _e((nb, N, N), BF16, dev)
                 ops.cast2d(A.view(nb * N, N), Ab.view(nb * N, N))
             ops.bgemm(nb, N, C, N, Ab, N * N, N, True, do, N * C, C, True, dv, N * nq, nq)         # dv[j,c] = sum_i attn[i,j] do[i,c]
-            dattn = _e((nb, N, N), BF16, dev)      # a gradient: bf16 like every other activation gradient
-            ops.bgemm(nb, N, N, C, do, N * C, C, False, v, N * nq, nq, False, dattn, N * N, N)     # dattn[i,j] = sum_c do[i,c] v[j,c]
-            dS = dattn                             # in place: dS = P * (dP - D)
-            ops.softmax_rows_bwd_d(Ab, dattn, Drow[rows], dS)
+            # dS = P * (dO V^T - D), the softmax backward in the epilogue of the dP product, written over P (bf16: a
+            # gradient like every other activation gradient); dP itself never exists in HBM
+            dS = Ab
+            ops.softmax_bwd_bgemm(nb, N, N, C, do, N * C, C, v, N * nq, nq, Ab, Drow[rows], dS)
             del Ab
             ops.bgemm(nb, N, Cq, N, dS, N * N, N, False, k, N * nq, nq, True, dq, N * nq, nq)      # dq[i,c] = sum_j dS[i,j] k[j,c]
             ops.bgemm(nb, N, Cq, N, dS, N * N, N, True, q, N * nq, nq, True, dk, N * nq, nq)       # dk[j,c] = sum_i dS[i,j] q[i,c]

@@ -140,24 +140,37 @@ def attn_small_bwd(qkv, attn, d_o, B, N, Cq, Cn, dqkv):
     L.call("dfcsa_attn_small_bwd", L.ptr(qkv), _i64(qkv.stride(0)), L.ptr(attn), L.ptr(d_o), B, N, Cq, Cn, L.ptr(dqkv), L.stream())
 
 
-def softmax_bgemm(batch, M, N, K, A, a_b, ld_a, Bm, b_b, ld_b, out):
+def softmax_bgemm(batch, M, N, K, A, a_b, ld_a, Bm, b_b, ld_b, out, lse=None, have_lse=False):
     """out[b] = softmax_rows(A[b] @ B[b]^T) (both operands K-major) in two tcgen05 launches that never write the logits:
-    a row-statistics pass (ROWSTATS epilogue + dfcsa_lse_combine) and a pass whose epilogue stores exp(x - lse)."""
-    parts = L.lib().dfcsa_bgemm_rowstat_parts(N)
+    a row-statistics pass (ROWSTATS epilogue + dfcsa_lse_combine -> lse [batch*M] fp32) and a pass whose epilogue stores
+    exp(x - lse).  With have_lse the statistics pass is skipped (the backward recompute reuses the forward's lse)."""
     dev = A.device
-    rowstat = torch.empty((batch * M, parts, 2), dtype=torch.float32, device=dev)
-    lse = torch.empty((batch * M,), dtype=torch.float32, device=dev)
-    bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, None, 0, 0, epi=1, rowstat=rowstat)
-    L.call("dfcsa_lse_combine", L.ptr(rowstat), parts, C.c_int64(batch * M), L.ptr(lse), L.stream())
-    bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, out, M * N, N, epi=2, lse=lse)
+    if lse is None:
+        assert not have_lse
+        lse = torch.empty((batch * M,), dtype=torch.float32, device=dev)
+    if not have_lse:
+        parts = L.lib().dfcsa_bgemm_rowstat_parts(N)
+        rowstat = torch.empty((batch, parts, M, 2), dtype=torch.float32, device=dev)
+        bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, None, 0, 0, epi=1, rowstat=rowstat)
+        L.call("dfcsa_lse_combine", L.ptr(rowstat), parts, batch, M, L.ptr(lse), L.stream())
+    bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, out, M * N, N, epi=2, rowvec=lse)
 
 
-def bgemm(batch, M, N, K, A, a_b, ld_a, a_mn, Bm, b_b, ld_b, b_mn, Cm, c_b, ld_c, epi=0, rowstat=None, lse=None):
+def softmax_bwd_bgemm(batch, M, N, K, dO, a_b, ld_a, V, b_b, ld_b, probs, D, dS):
+    """dS[b] = probs[b] * (dO[b] @ V[b]^T - D[b][:, None]) (both operands K-major): the softmax backward fused into the
+    epilogue of the dP product, D = rowdot(dO, O).  dS may be probs itself (same element size)."""
+    assert probs.shape == dS.shape and probs.is_contiguous() and dS.is_contiguous() and D.dtype == torch.float32
+    bgemm(batch, M, N, K, dO, a_b, ld_a, False, V, b_b, ld_b, False, dS, M * N, N, epi=3, rowvec=D, aux=probs)
+
+
+def bgemm(batch, M, N, K, A, a_b, ld_a, a_mn, Bm, b_b, ld_b, b_mn, Cm, c_b, ld_c, epi=0, rowstat=None, rowvec=None, aux=None):
     """C[b] = A[b] @ B[b] on tcgen05 (dfcsa_bgemm); operands 16-bit of one dtype, K-major or MN-major (see dfcsa.h)."""
     p = L.BgemmParams()
     p.epi_mode = epi
     p.rowstat = rowstat.data_ptr() if rowstat is not None else None
-    p.lse = lse.data_ptr() if lse is not None else None
+    p.rowvec = rowvec.data_ptr() if rowvec is not None else None
+    if aux is not None:
+        p.aux, p.aux_dtype = aux.data_ptr(), L.dt(aux)
     p.batch, p.M, p.N, p.K = batch, M, N, K
     p.A, p.a_b, p.ld_a, p.a_mn_major = A.data_ptr(), a_b, ld_a, 1 if a_mn else 0
     p.B, p.b_b, p.ld_b, p.b_mn_major = Bm.data_ptr(), b_b, ld_b, 1 if b_mn else 0

@@ -168,11 +168,13 @@ int dfcsa_attn_small_bwd(const float* qkv, int64_t ld, const float* attn, const 
  * Used for the attention products softmax(Q K^T) V and their backward (reference models/unet_dfc_sa_res.py:30-33,
  * models/unet_dfc_sa_ablation_attention.py:20-24) whenever N = P*P >= 64.  Pitches / batch strides in elements,
  * multiples of 8; N % 8 == 0. */
-/* Optional epilogues that make softmax(A B) a two-launch affair without ever writing the logits:
- *   ROWSTATS: nothing is stored in C; every tile writes (max, sum exp(x - max)) of its part of each row to
- *             rowstat[b, m, part, 2] (dfcsa_bgemm_rowstat_parts(N) parts per row); dfcsa_lse_combine -> lse[b, m];
- *   EXP:      C = exp(A B - lse[b, m])  (the normalised probabilities, usually 16-bit). */
-enum { DFCSA_BGEMM_EPI_NONE = 0, DFCSA_BGEMM_EPI_ROWSTATS = 1, DFCSA_BGEMM_EPI_EXP = 2 };
+/* Optional epilogues that keep the [N, N] intermediates of attention out of HBM:
+ *   ROWSTATS:    nothing is stored in C; every tile writes (max, sum exp(x - max)) of its part of each row to
+ *                rowstat[b, part, m, 2] (dfcsa_bgemm_rowstat_parts(N) parts per row); dfcsa_lse_combine -> lse[b, m];
+ *   EXP:         C = exp(A B - rowvec[b, m])       rowvec = lse: the normalised probabilities, usually 16-bit;
+ *   SOFTMAX_BWD: C = aux * (A B - rowvec[b, m])    aux = probabilities (16-bit, laid out like C; may alias C when the
+ *                element sizes match), rowvec = D = rowdot(dO, O): with A B = dO V^T this is dS, the softmax backward. */
+enum { DFCSA_BGEMM_EPI_NONE = 0, DFCSA_BGEMM_EPI_ROWSTATS = 1, DFCSA_BGEMM_EPI_EXP = 2, DFCSA_BGEMM_EPI_SOFTMAX_BWD = 3 };
 typedef struct {
   int32_t batch, M, N, K;
   const void* A; int64_t a_b, ld_a; int32_t a_mn_major;
@@ -181,11 +183,12 @@ typedef struct {
   void* C; int64_t c_b, ld_c; int32_t c_dtype;
   int32_t epi_mode;
   float* rowstat;
-  const float* lse;
+  const float* rowvec;
+  const void* aux; int32_t aux_dtype;
 } dfcsa_bgemm_params_t;
 int dfcsa_bgemm(const dfcsa_bgemm_params_t* p, void* stream);
 int dfcsa_bgemm_rowstat_parts(int32_t N);
-int dfcsa_lse_combine(const float* rowstat, int32_t parts, int64_t rows, float* lse, void* stream);
+int dfcsa_lse_combine(const float* rowstat, int32_t parts, int32_t batch, int32_t M, float* lse, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BatchNorm2d (reference :60,67,75,82; ATen batch_norm semantics: biased variance for normalisation, unbiased

@@ -300,6 +300,36 @@ def test_softmax_bgemm(cuda, batch, N, K, dtype):
         assert (out.float().sum(-1) - 1).abs().max() < (4e-3 if odt == torch.float16 else 2e-2)
 
 
+@pytest.mark.parametrize("batch,N,C", [(2, 64, 64), (1, 200, 128), (2, 1048, 64), (1, 3136, 64)])
+@pytest.mark.parametrize("pdt", [torch.float16, torch.bfloat16])
+def test_softmax_bwd_bgemm(cuda, batch, N, C, pdt):
+    """dS = P * (dO V^T - D) from the SOFTMAX_BWD epilogue of dfcsa_bgemm, in place over P when the types allow."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(29)
+    P = torch.softmax(torch.randn(batch, N, N, generator=g) * 2, -1).cuda().to(pdt)
+    dO = torch.randn(batch, N, C, generator=g).cuda().to(torch.bfloat16)
+    V = torch.randn(batch, N, C, generator=g).cuda().to(torch.bfloat16)
+    D = torch.randn(batch, N, generator=g).cuda()
+    ref = P.float() * (torch.bmm(dO.float(), V.float().transpose(1, 2)) - D[..., None])
+    dS = P.clone() if pdt == torch.bfloat16 else torch.full((batch, N, N), float("nan"), device=cuda, dtype=torch.bfloat16)
+    ops.softmax_bwd_bgemm(batch, N, N, C, dO, N * C, C, V, N * C, C, dS if pdt == torch.bfloat16 else P, D.view(-1), dS)
+    torch.cuda.synchronize()
+    assert _rel_err(dS, ref) < 8e-3
+
+
+@pytest.mark.parametrize("xdt,ydt", [(torch.float32, torch.float16), (torch.float32, torch.bfloat16), (torch.float16, torch.bfloat16),
+                                     (torch.float16, torch.float32), (torch.bfloat16, torch.float32)])
+@pytest.mark.parametrize("M,C,pad", [(37, 64, 0), (1000, 1024, 0), (50, 24, 8), (33, 20, 4)])
+def test_cast2d(cuda, xdt, ydt, M, C, pad):
+    """dfcsa_cast2d (vector and scalar paths, pitched rows): same values as torch's conversion."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(31)
+    xs = torch.randn(M, C + pad, generator=g).cuda().to(xdt)
+    ys = torch.zeros(M, C + pad, device=cuda, dtype=ydt)
+    ops.cast2d(xs[:, :C], ys[:, :C])
+    assert torch.equal(ys[:, :C], xs[:, :C].to(ydt)) and (ys[:, C:] == 0).all()
+
+
 @pytest.mark.parametrize("cols", [16, 100, 4096])
 def test_softmax_rows_16bit(cuda, cols):
     from dfcsa import ops

@@ -28,6 +28,7 @@ from dfcsa import synthetic as O  # noqa: E402
 
 CFG = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/dfcsa_cfg"}}
 FEATURES = [64, 128, 256, 512]
+PROFILE = False
 
 
 def batch(B, hw, seed=1):
@@ -56,6 +57,15 @@ def train_case(model, B, hw, warmup=3, steps=8, graph=False):
     step = (lambda: tr.train_step_graphed(img, mask)) if graph else (lambda: tr.train_step(img, mask))
     t0 = time.time()
     r = time_steps(step, warmup, steps)
+    if PROFILE:
+        from dfcsa import _lib
+        _lib.PROF = prof = _lib.Profiler()
+        tr.train_step(img, mask)
+        _lib.PROF = None
+        summ = sorted(prof.summary().items(), key=lambda kv: -kv[1]["ms"])
+        r["profile_ms"] = {k: round(v["ms"], 3) for k, v in summ[:14]}
+        det = sorted(prof.detail(tags=("bgemm_tc",)).items(), key=lambda kv: -kv[1]["ms"])
+        r["bgemm_ms"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in det[:12]}
     r.update({"batch": B, "hw": hw, "img_per_s": B / (r["ms_mean"] * 1e-3), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
               "wall_s": time.time() - t0, "cuda_graph": graph})
     del tr
@@ -74,7 +84,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("cases", nargs="*", default=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--out", default="gpurun_out/configs.json")
+    ap.add_argument("--profile", action="store_true", help="add per-entry-point CUDA-event times of one extra step")
     args = ap.parse_args()
+    global PROFILE
+    PROFILE = args.profile
     res = {}
 
     def run(name, fn):
@@ -91,7 +104,7 @@ def main():
         if hasattr(Trainer, "train_step_graphed"):
             run("c1_p4_224_b4_train_cudagraph", lambda: train_case(new_model(4), 4, 224, steps=20, graph=True))
     if "c2" in args.cases:
-        for P in (4, 16, 32):
+        for P in (4, 16, 32) if not os.environ.get("C2_P") else [int(os.environ["C2_P"])]:
             run(f"c2_p{P}_224_b64_train", lambda P=P: train_case(new_model(P), 64, 224, steps=5))
     if "c3" in args.cases:
         run("c3_fullres_224_b1_train", lambda: train_case(new_model(full_res=True), 1, 224, warmup=1, steps=2))
