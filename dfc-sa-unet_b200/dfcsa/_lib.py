@@ -97,6 +97,7 @@ SYMBOLS = [
     "dfcsa_nchw_to_nhwc", "dfcsa_nhwc_to_nchw", "dfcsa_colsum", "dfcsa_cast2d",
     "dfcsa_bce_dice_sums", "dfcsa_bce_dice_finalize", "dfcsa_bce_dice_bwd",
     "dfcsa_grad_sumsq", "dfcsa_sgd_step",
+    "dfcsa_preprocess", "dfcsa_preprocess_workspace_bytes",
 ]
 
 _lib = None
@@ -113,6 +114,7 @@ def lib():
         l = C.CDLL(LIB_PATH)
         l.dfcsa_last_error.restype = C.c_char_p
         l.dfcsa_version.restype = C.c_int
+        l.dfcsa_preprocess_workspace_bytes.restype = C.c_int64
         _lib = l
     return _lib
 
@@ -121,6 +123,11 @@ def check(rc, what=""):
     if rc != 0:
         msg = lib().dfcsa_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libdfcsa {what} failed (code {rc}): {msg}")
+
+
+class Sample(C.Structure):        # dfcsa_sample_t
+    _fields_ = [("img", C.c_void_p), ("mask", C.c_void_p), ("h", C.c_int32), ("w", C.c_int32), ("rot_mode", C.c_int32),
+                ("flip", C.c_int32), ("a", C.c_double * 6)]
 
 
 class Profiler:
@@ -153,7 +160,7 @@ class Profiler:
 PROF = None          # set to a Profiler() to time every ABI call
 LAUNCHES = 0         # kernels enqueued through the ABI (bench.py's gpu_launches)
 # entry points that enqueue more than one kernel
-_KERNELS = {"dfcsa_bnrelu_pool_fwd": 2, "dfcsa_branch_bwd_reduce1": 3}
+_KERNELS = {"dfcsa_bnrelu_pool_fwd": 2, "dfcsa_branch_bwd_reduce1": 3, "dfcsa_preprocess": 4}
 
 
 def call(name, *args, tag=None, flops=0.0, desc=""):

@@ -337,6 +337,32 @@ int dfcsa_sgd_step(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t ma
                    float gscale, float max_norm, float lr, float momentum, float weight_decay, int first_step,
                    void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * GPU-side data path: the reference's per-sample transform chain, utils/data_loader.py:25-74
+ * (ExtResize -> ExtRandomRotation -> ExtRandomHorizontalFlip -> ExtToTensor -> ExtNormalize, executed there by Pillow and
+ * torchvision in DataLoader workers), for a ragged batch of decoded uint8 images.  Bit-exact with Pillow 12.2: 22-bit
+ * fixed-point separable BILINEAR resize with byte intermediates, NEAREST resize by repeated-addition coordinates,
+ * double-precision BILINEAR rotation truncated to bytes, 16.16 fixed-point NEAREST rotation, then
+ * image = (byte / 255 - mean) / std (fp32, NCHW) and mask = (byte / 255 > 0.5).
+ * The random decisions stay on the host (the caller draws them in the reference's order and, like Image.rotate, turns an
+ * angle into rot_mode + the inverse affine matrix; dfcsa/data_loader.py: rotate_plan). */
+enum { DFCSA_ROT_NONE = 0, DFCSA_ROT_AFFINE = 1, DFCSA_ROT_90 = 2, DFCSA_ROT_180 = 3, DFCSA_ROT_270 = 4 };
+typedef struct {
+  const uint8_t* img;     /* device, [h, w, 3] RGB bytes, tightly packed */
+  const uint8_t* mask;    /* device, [h, w] bytes (mode "L"), or NULL */
+  int32_t h, w;           /* source size */
+  int32_t rot_mode;       /* DFCSA_ROT_*; 90 / 270 only for square outputs (as in Image.rotate) */
+  int32_t flip;           /* horizontal flip, applied after the rotation */
+  double a[6];            /* DFCSA_ROT_AFFINE: output -> input matrix in the resized image's pixel coordinates */
+} dfcsa_sample_t;
+int64_t dfcsa_preprocess_workspace_bytes(int32_t n, int32_t max_src_h, int32_t max_src_w, int32_t out_h, int32_t out_w);
+/* samples_dev: n records in device memory; mean3 / std3: host arrays; img_out [n, 3, out_h, out_w] fp32,
+ * mask_out [n, 1, out_h, out_w] fp32 or NULL; workspace: 256-byte aligned device scratch of at least
+ * dfcsa_preprocess_workspace_bytes(...) bytes.  Four launches, no synchronisation. */
+int dfcsa_preprocess(const dfcsa_sample_t* samples_dev, int32_t n, int32_t max_src_h, int32_t max_src_w, int32_t out_h,
+                     int32_t out_w, const float* mean3, const float* std3, float* img_out, float* mask_out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,9 @@
   c3  ablation 3 (UNet_FullResAttention), 224^2, batch 1, train
   c4  512^2, 32 images per GPU (the per-GPU share of global batch 256 on 8 GPUs), train, + peak memory
   c5  eval-mode batched inference at 1024^2, batch 1/2/4/8: images/s and p50 latency
+  c6  data path: 64 decoded 768x1024 photographs -> augmented, normalised 224^2 tensors on the GPU
+      (dfcsa_preprocess; sources resident in HBM, and end to end from pinned host memory) beside the same chain run by
+      Pillow + numpy on one host core, which is what each of the reference's DataLoader workers does
 
   python tools/bench_configs.py [c1 c2 ...] --out gpurun_out/configs.json
 All numbers are CUDA-event timings after warm-up, inputs resident on the device, synthetic structured images.
@@ -120,7 +123,49 @@ def main():
                 r.update({"batch": B, "hw": 1024, "img_per_s": B / (r["ms_mean"] * 1e-3), "p50_latency_ms": r["ms_p50"]})
                 return r
             run(f"c5_p4_1024_b{B}_eval", infer)
+    if "c6" in args.cases:
+        run("c6_datapath_768x1024_to_224_b64", datapath_case)
     print(json.dumps(res))
+
+
+def datapath_case(n=64, src_hw=(768, 1024), out=224):
+    import numpy as np
+    from dfcsa import data_loader as D
+    rng = np.random.default_rng(0)
+    imgs = [rng.integers(0, 256, (*src_hw, 3), dtype=np.uint8) for _ in range(n)]
+    masks = [(rng.random(src_hw) > 0.7).astype(np.uint8) * 255 for _ in range(n)]
+    np.random.seed(0)
+    params = D.draw_augmentation(n)
+    dimgs = [torch.from_numpy(a).cuda() for a in imgs]
+    dmasks = [torch.from_numpy(a).cuda() for a in masks]
+    r = time_steps(lambda: D.preprocess_batch(dimgs, dmasks, (out, out), params), 3, 10)
+    res = {"n": n, "src_hw": list(src_hw), "out": out, "gpu_ms_resident": r["ms_mean"], "gpu_img_per_s_resident": n / (r["ms_mean"] * 1e-3),
+           "src_bytes_per_batch": int(sum(a.nbytes for a in imgs) + sum(a.nbytes for a in masks))}
+    res["gpu_gb_per_s_resident"] = (res["src_bytes_per_batch"] + n * 4 * out * out * 4) / (r["ms_mean"] * 1e-3) / 1e9
+    pimgs = [torch.from_numpy(a).pin_memory() for a in imgs]
+    pmasks = [torch.from_numpy(a).pin_memory() for a in masks]
+    r = time_steps(lambda: D.preprocess_batch(pimgs, pmasks, (out, out), params), 2, 5)
+    res.update({"gpu_ms_from_host": r["ms_mean"], "gpu_img_per_s_from_host": n / (r["ms_mean"] * 1e-3)})
+    try:
+        from PIL import Image
+        mean, std = np.asarray(D.MEAN, np.float32)[:, None, None], np.asarray(D.STD, np.float32)[:, None, None]
+        k = 16
+        t0 = time.time()
+        for i in range(k):
+            im, mk = Image.fromarray(imgs[i]), Image.fromarray(masks[i])
+            im, mk = im.resize((out, out), Image.BILINEAR), mk.resize((out, out), Image.NEAREST)
+            rot, ang, flip = params[i]
+            if rot:
+                im, mk = im.rotate(ang, Image.BILINEAR), mk.rotate(ang, Image.NEAREST)
+            if flip:
+                im, mk = im.transpose(Image.FLIP_LEFT_RIGHT), mk.transpose(Image.FLIP_LEFT_RIGHT)
+            x = (np.asarray(im, np.float32).transpose(2, 0, 1) / np.float32(255) - mean) / std
+            m = ((np.asarray(mk, np.float32) / 255.0) > 0.5).astype(np.float32)
+        dt = time.time() - t0
+        res.update({"pillow_one_core_img_per_s": k / dt, "pillow_sample": f"{k} images, 1 thread"})
+    except ImportError:
+        res["pillow_one_core_img_per_s"] = None
+    return res
 
 
 if __name__ == "__main__":

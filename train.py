@@ -4,7 +4,8 @@ kernels:  python train.py --config configs/config_dfc-sa-res-block-p4.yaml [--re
 
 Same YAML schema, same ModelFactory name, same optimizer hyper-parameters and checkpoint dictionary.  Data: the
 reference's DataLoaderFactory depends on a `datasets` package that is not part of its repository, so this script takes
-image / mask folders in the layout <dir>/images/* and <dir>/masks/* (same file stems), or --synthetic N to train on N
+image / mask folders in the layout <dir>/images/* and <dir>/masks/* (same file stems; dfcsa.data_loader decodes on host
+threads and runs the reference's resize / rotation / flip / normalise chain on the GPU), or --synthetic N to train on N
 generated batches (structured blobs, the distribution bench.py uses).  Multi-GPU: launch with torchrun; each rank reads
 its share of every batch and gradients are all-reduced per bucket over NCCL (dfcsa.trainer).
 """
@@ -25,30 +26,6 @@ from dfcsa.trainer import Trainer  # noqa: E402
 
 def normalize_path(path):
     return path.replace("\\", "/")
-
-
-class FolderDataset(torch.utils.data.Dataset):
-    """<dir>/images/<stem>.* with <dir>/masks/<stem>.*; resized to img_size, ImageNet-normalised, mask binarised."""
-
-    def __init__(self, root, img_size):
-        from PIL import Image  # noqa: F401  (imported lazily: only this data path needs it)
-        self.root, self.size = normalize_path(root), tuple(img_size)
-        idir, mdir = os.path.join(self.root, "images"), os.path.join(self.root, "masks")
-        masks = {os.path.splitext(f)[0]: os.path.join(mdir, f) for f in sorted(os.listdir(mdir))}
-        self.items = [(os.path.join(idir, f), masks[os.path.splitext(f)[0]]) for f in sorted(os.listdir(idir))
-                      if os.path.splitext(f)[0] in masks]
-
-    def __len__(self):
-        return len(self.items)
-
-    def __getitem__(self, i):
-        import numpy as np
-        from PIL import Image
-        ip, mp = self.items[i]
-        img = np.asarray(Image.open(ip).convert("RGB").resize(self.size[::-1], Image.BILINEAR), dtype=np.float32) / 255.0
-        msk = np.asarray(Image.open(mp).convert("L").resize(self.size[::-1], Image.NEAREST), dtype=np.float32) / 255.0
-        img = (img - np.array([0.485, 0.456, 0.406], np.float32)) / np.array([0.229, 0.224, 0.225], np.float32)
-        return {"image": torch.from_numpy(img).permute(2, 0, 1).contiguous(), "mask": torch.from_numpy((msk > 0.5).astype(np.float32))[None]}
 
 
 class SyntheticBatches:
@@ -83,12 +60,14 @@ def main(config, resume_path=None, synthetic=0):
     if synthetic:
         train_loader, val_loader = SyntheticBatches(synthetic, bs, size, seed=local), SyntheticBatches(max(1, synthetic // 4), bs, size, seed=1000 + local)
     else:
-        def mk(d, train):
-            dset = FolderDataset(d, size)
-            sampler = torch.utils.data.distributed.DistributedSampler(dset, shuffle=train) if world > 1 else None
-            return torch.utils.data.DataLoader(dset, batch_size=bs, shuffle=train and sampler is None, sampler=sampler,
-                                               num_workers=int(tr_cfg.get("num_workers", 2)), pin_memory=True, drop_last=train)
-        train_loader, val_loader = mk(ds["train_dir"], True), mk(ds["val_dir"], False)
+        # decoded bytes go to the GPU; resize / rotation / flip / normalisation run there, bit-exact with the reference's
+        # PIL chain (dfcsa.data_loader, utils/data_loader.py:25-74 of the reference)
+        from dfcsa.data_loader import DataLoaderFactory
+        config["dataset"].setdefault("augmentation", False)
+        config["training"].setdefault("num_workers", 2)
+        config["training"].setdefault("batch_size", bs)
+        factory = DataLoaderFactory(config, device=device, rank=int(os.environ.get("RANK", "0")), world=world)
+        train_loader, val_loader = factory.get_train_loader(), factory.get_val_loader()
     model = ModelFactory.get_model(config).to(device)
     optimizer = FusedSGD(model.parameters(), lr=float(tr_cfg.get("learning_rate", 0.01)), momentum=float(tr_cfg.get("momentum", 0.9)),
                          weight_decay=float(tr_cfg.get("weight_decay", 1e-4)))           # reference train.py:73-78
