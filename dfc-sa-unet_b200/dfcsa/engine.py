@@ -59,6 +59,40 @@ class BlockParams:
         self.tc = (self.Ci % 64 == 0) and (self.C % 64 == 0)
 
 
+    kind = "dfc"
+
+    def bns(self):
+        return [self.bn1, self.bn2, self.bn3, self.bn4]
+
+
+class LocalBlockParams:
+    """LocalOnlyBlock (reference models/unet_dfc_sa_ablation_branches.py:72-101): relu(bn(conv3x3(x))) + res_scale * res(x),
+    the standard U-Net convolution block of the placement / branch ablations."""
+
+    kind = "local"
+
+    def __init__(self, mod):
+        cb = mod.conv_branch
+        self.mod = mod
+        self.W1, self.b1, self.bn1 = cb[0].weight, cb[0].bias, cb[1]
+        self.W5 = getattr(mod.residual_conv, "weight", None)
+        self.res_scale = mod.res_scale
+        self.Ci, self.C = self.W1.shape[1], self.W1.shape[0]
+        self.tc = (self.Ci % 64 == 0) and (self.C % 64 == 0)
+
+    def bns(self):
+        return [self.bn1]
+
+
+def make_block_params(mod):
+    """The engine-side view of one block module, by its structure (sub-module names are the reference's)."""
+    if hasattr(mod, "gate"):
+        return BlockParams(mod)
+    if hasattr(mod, "conv_branch") and not hasattr(mod, "attn_branch"):
+        return LocalBlockParams(mod)
+    raise NotImplementedError(f"dfcsa: no kernels for block type {type(mod).__name__}")
+
+
 class PackPlan:
     """Every weight re-layout of a network (fp32 masters -> packed 16-bit GEMM operands) as a device table of jobs that
     ONE dfcsa_pack_jobs launch executes per step.  Destination buffers are persistent, so the plan is built once per
@@ -107,6 +141,15 @@ def pack_block_weights(bp, training, need_dx, plan):
     W5 = bp.W5.detach() if bp.W5 is not None else torch.eye(C, dtype=F32, device=dev).view(C, C, 1, 1)
     pk["w1"] = _e((C, 9 * Ci), fdt, dev)
     plan.add(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
+    if bp.kind == "local":
+        pk["w5"] = _e((C, Ci), fdt, dev)
+        plan.add(W5, pk["w5"], (C, 1, Ci), (Ci, 0, 1))
+        if training and need_dx:
+            wd = _e((Ci, 10 * C), BF16 if bp.tc else F32, dev)       # [ci, (flipped tap, co) | co (res_scale*W5)]
+            plan.add(bp.W1.detach(), wd, (Ci, 9, C), (9, 1, Ci * 9), flip1=True, ld_dst=10 * C)
+            plan.add(W5, wd[:, 9 * C:], (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1), ld_dst=10 * C)
+            pk["wd15"] = wd
+        return pk
     pk["w25"] = _e((2 * C, Ci), fdt, dev)
     plan.add(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1))
     plan.add(W5, pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
@@ -158,7 +201,7 @@ class NetPacks:
         dev = next(net.parameters()).device
         self.sig = NetPacks.signature(net)
         self.plan = PackPlan(dev)
-        self.bps = [BlockParams(b) for b in _blocks(net)]
+        self.bps = [make_block_params(b) for b in _blocks(net)]
         self.pks = [pack_block_weights(bp, keep, i > 0, self.plan) for i, bp in enumerate(self.bps)]
         self.up_fwd, self.up_bwd = [], []
         for up in (net.up4, net.up3, net.up2, net.up1):
@@ -386,6 +429,8 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
 def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     """One DynamicFusionConvAttnBlock.  x: [M, Ci] (fp16, or fp32 for the image); y / yp: fp16 output views (full
     resolution / 2x2 max-pooled).  Returns the context the backward needs."""
+    if bp.kind == "local":
+        return _local_block_forward(bp, pk, x, B, H, W, y, yp, training, save)
     dev = x.device
     C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
     M = B * H * W
@@ -427,6 +472,49 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     return ctx
 
 
+def _local_block_forward(bp, pk, x, B, H, W, y, yp, training, save):
+    """LocalOnlyBlock: the DFC block's conv branch feeding the DFC block's output stage directly."""
+    dev = x.device
+    C, M = bp.C, B * H * W
+    ctx = BlockCtx() if (training and save) else None
+    st = _z((2 * C,), F64, dev) if training else None
+    L0, R = _e((M, C), F16, dev), _e((M, C), F16, dev)
+    segs3, segs1 = [(x, TAP_3x3)], [(x, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs3, pk["w1"], C, L0, stats=st, backend=_backend(segs3, pk["w1"], C, L0))
+    ops.conv_gemm(B, H, W, segs1, pk["w5"], C, R, backend=_backend(segs1, pk["w5"], C, R))
+    bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
+    ops.block_out_fwd(L0, R, B, H, W, bn1[0], bn1[1], bp.res_scale.detach(), y, yp, None, None)
+    if ctx is not None:
+        ctx.B, ctx.H, ctx.W = B, H, W
+        ctx.L0, ctx.R, ctx.y, ctx.bn1 = L0, R, y, bn1
+    return ctx
+
+
+def _local_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
+    dev = dskip.device if dskip is not None else dyp.device
+    B, H, W = ctx.B, ctx.H, ctx.W
+    C, Ci = bp.C, bp.Ci
+    M = B * H * W
+    red = _z((2 * C + 1,), F64, dev)
+    red1, drs = red[0:2 * C], red[2 * C:2 * C + 1]
+    bn1 = ctx.bn1
+    dy = dskip if dskip is not None else _e((M, C), BF16, dev)
+    # out = relu(bn1(L0)) + res_scale * R
+    ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.L0, ctx.R, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], dy, red1, drs)
+    dL0 = _e((M, C), BF16, dev)
+    ops.bn_bwd_apply(dy, ctx.L0, bn1[0], bn1[1], bn1[2], bn1[3], red1, 0, dL0)
+    ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
+    grads[bp.res_scale].copy_(drs[0])
+    if dx_out is not None:
+        segs = [(dL0, TAP_3x3), (dy, TAP_1x1)]
+        ops.conv_gemm(B, H, W, segs, pk["wd15"], Ci, dx_out, backend=_backend(segs, pk["wd15"], Ci, dx_out))
+    dW1p = _z((C, 9 * Ci), F32, dev)
+    _wgrad(B, H, W, xw, TAP_3x3, dL0, TAP_1x1, dW1p)
+    ops.permute3(dW1p, grads[bp.W1], (C, Ci, 9), (9 * Ci, 1, Ci))
+    if bp.W5 is not None:
+        _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1))
+
+
 def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None, second=None):
     """second = (dy2, dw2, c_begin2, alpha2): another 1x1 weight gradient over the same x, same launch."""
     tc = ops.wgrad_tc_eligible(x, dy) and (x.dtype == dy.dtype or (x.dtype == F16 and dy.dtype == BF16))
@@ -441,6 +529,8 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     dskip: bf16 gradient w.r.t. y ([M, C] view, updated in place when dyp is given); dyp: bf16 gradient w.r.t. the
     max-pooled output or None; dx_out: bf16 [M, Ci] view that receives the input gradient, or None.
     grads: dict parameter -> fp32 gradient tensor (zero-initialised where the kernels accumulate)."""
+    if bp.kind == "local":
+        return _local_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads)
     dev = dskip.device if dskip is not None else dyp.device
     B, H, W = ctx.B, ctx.H, ctx.W
     C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
@@ -575,8 +665,7 @@ def net_forward(net, x_nchw, training, save=True):
         logits = _e((B, Cout, H, W), F32, dev)
         ops.nhwc_to_nchw(logits_nhwc, logits, B, Cout, H, W)
     if training:
-        bns = [m for blk in _blocks(net) for m in (blk.conv_branch[1], blk.attn_branch[1], blk.gate[1], blk.fusion_conv[1])]
-        torch._foreach_add_([m.num_batches_tracked for m in bns], 1)
+        torch._foreach_add_([m.num_batches_tracked for bp in bps for m in bp.bns()], 1)
     if keep:
         ctx.bps, ctx.pks, ctx.bctx, ctx.xs = bps, pks, bctx, xs
         ctx.upk, ctx.uin, ctx.u_last = upk, uin, u

@@ -1,13 +1,13 @@
 """ModelFactory mirror (reference models/model_factory.py:14-186): the name -> class boundary of the hot path."""
 import torch
 
-from .modules import UNet_FullResAttention, UNetDFCSARes
+from .modules import (UNet_Baseline, UNet_BothStandardConv, UNet_DecoderOnlyDFC, UNet_EncoderOnlyDFC, UNet_FullResAttention,
+                      UNetDFCSARes)
 
 # names the reference factory knows (models/model_factory.py:94-183) that are outside the B200 hot path
 _OUT_OF_SCOPE = {
     "UNet", "TransformerUNet", "TransUNet", "ViTSegmentation", "ViT_Seg", "VisionTransformer",
-    "UNet_Baseline", "UNet_AttentionOnly", "UNet_AdditionFusion", "UNet_ConcatFusion",
-    "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv",
+    "UNet_AttentionOnly", "UNet_AdditionFusion", "UNet_ConcatFusion",
 }
 
 
@@ -48,6 +48,15 @@ class ModelFactory:
                                 pool_size=pool_size, ablation_on_qk_channels=qk)
         if name == "UNet_FullResAttention":                  # reference :174-175 (ablation 3)
             return UNet_FullResAttention(in_channels=in_channels, out_channels=out_channels, features=features)
+        # ablations 1(b) and 4 (reference :162-163, :178-183): the same kernels re-wired
+        if name == "UNet_Baseline":
+            return UNet_Baseline(in_channels, out_channels, features)
+        if name == "UNet_BothStandardConv":
+            return UNet_BothStandardConv(in_channels, out_channels, features)
+        if name == "UNet_EncoderOnlyDFC":
+            return UNet_EncoderOnlyDFC(in_channels, out_channels, features, pool_size)
+        if name == "UNet_DecoderOnlyDFC":
+            return UNet_DecoderOnlyDFC(in_channels, out_channels, features, pool_size)
         if name in _OUT_OF_SCOPE:
             raise NotImplementedError(f"dfcsa: model '{name}' is outside the DFC-SA-Res-Block hot path this library accelerates")
         raise ValueError(f"不支援的模型類型: {name}")   # reference models/model_factory.py:186

@@ -52,7 +52,7 @@ class _BlockFunction(torch.autograd.Function):
             raise RuntimeError("dfcsa: the block runs on CUDA tensors only (no CPU fallback)")
         training = block.training
         keep = training and need_grad
-        bp = engine.BlockParams(block)
+        bp = engine.make_block_params(block)
         plan = engine.PackPlan(dev)
         pk = engine.pack_block_weights(bp, keep, True, plan)
         plan.run()
@@ -184,3 +184,95 @@ class UNet_FullResAttention(UNetDFCSA):
 
     def __init__(self, in_channels, out_channels, features, **kwargs):
         super().__init__(in_channels, out_channels, features, full_res_attention=True)
+
+
+class LocalOnlyBlock(nn.Module):
+    """reference models/unet_dfc_sa_ablation_branches.py:72-101: relu(bn(conv3x3(x))) + res_scale * residual(x)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, **kwargs):
+        super().__init__()
+        if (kernel_size, stride, padding) != (3, 1, 1):
+            raise NotImplementedError("dfcsa: LocalOnlyBlock kernels implement the 3x3 / stride 1 / pad 1 convolution")
+        self.conv_branch = nn.Sequential(
+            nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding),
+            nn.BatchNorm2d(out_channels), nn.ReLU(inplace=True))
+        if in_channels != out_channels:
+            self.residual_conv = nn.Conv2d(in_channels, out_channels, kernel_size=1, bias=False)
+        else:
+            self.residual_conv = nn.Identity()
+        self.res_scale = nn.Parameter(torch.tensor(0.1))
+
+    def forward(self, x):
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        return _BlockFunction.apply(x, self, need_grad, *params)
+
+
+class _AblationUNet(nn.Module):
+    """The U-Net wiring shared by the ablation networks (reference models/unet_dfc_sa_ablation_branches.py:104-164 and the
+    three classes of models/unet_dfc_sa_ablation_placement.py): same sub-module names as UNetDFCSA, one block constructor
+    for the encoder + bottleneck and one for the decoder."""
+
+    def __init__(self, enc_block, dec_block, in_channels, out_channels, features):
+        super().__init__()
+        self.down1 = enc_block(in_channels, features[0])
+        self.pool1 = nn.MaxPool2d(2)
+        self.down2 = enc_block(features[0], features[1])
+        self.pool2 = nn.MaxPool2d(2)
+        self.down3 = enc_block(features[1], features[2])
+        self.pool3 = nn.MaxPool2d(2)
+        self.down4 = enc_block(features[2], features[3])
+        self.pool4 = nn.MaxPool2d(2)
+        self.bottleneck = enc_block(features[3], features[3] * 2)
+        self.up4 = nn.ConvTranspose2d(features[3] * 2, features[3], kernel_size=2, stride=2)
+        self.up_conv4 = dec_block(features[3] * 2, features[3])
+        self.up3 = nn.ConvTranspose2d(features[3], features[2], kernel_size=2, stride=2)
+        self.up_conv3 = dec_block(features[2] * 2, features[2])
+        self.up2 = nn.ConvTranspose2d(features[2], features[1], kernel_size=2, stride=2)
+        self.up_conv2 = dec_block(features[1] * 2, features[1])
+        self.up1 = nn.ConvTranspose2d(features[1], features[0], kernel_size=2, stride=2)
+        self.up_conv1 = dec_block(features[0] * 2, features[0])
+        self.final_conv = nn.Conv2d(features[0], out_channels, kernel_size=1)
+
+    def forward(self, x):
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _NetFunction.apply(x, self, need_grad, *params)
+
+
+def _dfc(pool_size):
+    return lambda i, o: DynamicFusionConvAttnBlock(i, o, pool_size=pool_size)
+
+
+def _local(i, o):
+    return LocalOnlyBlock(i, o)
+
+
+class UNet_Baseline(_AblationUNet):
+    """ablation 1(b), reference models/unet_dfc_sa_ablation_branches.py:166-168: LocalOnlyBlock everywhere."""
+
+    def __init__(self, in_channels, out_channels, features, **kwargs):
+        super().__init__(_local, _local, in_channels, out_channels, features)
+
+
+class UNet_BothStandardConv(_AblationUNet):
+    """ablation 4, reference models/unet_dfc_sa_ablation_placement.py:215-282: LocalOnlyBlock in encoder and decoder."""
+
+    def __init__(self, in_channels, out_channels, features, **kwargs):
+        super().__init__(_local, _local, in_channels, out_channels, features)
+
+
+class UNet_EncoderOnlyDFC(_AblationUNet):
+    """ablation 4, reference models/unet_dfc_sa_ablation_placement.py:83-147: DFC-SA blocks in the encoder + bottleneck,
+    LocalOnlyBlock in the decoder."""
+
+    def __init__(self, in_channels, out_channels, features, pool_size=8):
+        super().__init__(_dfc(pool_size), _local, in_channels, out_channels, features)
+
+
+class UNet_DecoderOnlyDFC(_AblationUNet):
+    """ablation 4, reference models/unet_dfc_sa_ablation_placement.py:149-213: LocalOnlyBlock in the encoder + bottleneck,
+    DFC-SA blocks in the decoder."""
+
+    def __init__(self, in_channels, out_channels, features, pool_size=8):
+        super().__init__(_local, _dfc(pool_size), in_channels, out_channels, features)

@@ -37,14 +37,19 @@ def grad_rel_l2(model, ref_grads):
 
 
 def forward_backward_parity(features=(64, 128, 256, 512), pool_size=4, qk=8, B=2, H=64, W=64, gamma=0.5, seed=0,
-                            full_res_attention=False):
+                            full_res_attention=False, model_name=None):
     """Returns dict(logit_maxabs, grad_rel_l2, loss, loss_ref) of dfcsa vs the oracle on identical weights/inputs.
-    full_res_attention: the ablation-3 network (UNet_FullResAttention) instead of DFC-SA-Res-Block."""
+    full_res_attention: the ablation-3 network (UNet_FullResAttention) instead of DFC-SA-Res-Block; model_name: one of
+    the other ModelFactory names (ablations 1(b) / 4, which hard-code channels // 8 query/key channels)."""
     O = _oracle()
     from .metrics import calculate_metrics
     from .modules import UNet_FullResAttention, UNetDFCSARes
     torch.manual_seed(seed)
-    if full_res_attention:
+    if model_name is not None:
+        from .model_factory import ModelFactory
+        model = ModelFactory.get_model({"model": {"name": model_name, "in_channels": 3, "out_channels": 1,
+                                                  "features": list(features), "pool_size": pool_size}})
+    elif full_res_attention:
         model = UNet_FullResAttention(3, 1, list(features))
     else:
         model = UNetDFCSARes(3, 1, list(features), pool_size=pool_size, ablation_on_qk_channels=qk)

@@ -149,9 +149,24 @@ def dfc_block(x, sd, prefix, pool_size, training=True, full_res_attention=False,
     return out + sd[p + ".res_scale"] * res                                                                                    # :114
 
 
+def local_only_block(x, sd, prefix, training=True, update_running=True):
+    """LocalOnlyBlock.forward (reference models/unet_dfc_sa_ablation_branches.py:92-101)."""
+    p = prefix
+    local = F.relu(batch_norm(F.conv2d(x, sd[p + ".conv_branch.0.weight"], sd[p + ".conv_branch.0.bias"], padding=1), sd,
+                              p + ".conv_branch.1", training, update_running=update_running))
+    res = F.conv2d(x, sd[p + ".residual_conv.weight"]) if (p + ".residual_conv.weight") in sd else x
+    return local + sd[p + ".res_scale"] * res
+
+
 def unet_forward(x, sd, pool_size, training=True, full_res_attention=False, update_running=True):
-    """UNetDFCSA.forward (reference models/unet_dfc_sa_res.py:161-204).  Channel widths come from the tensors."""
-    blk = lambda t, name: dfc_block(t, sd, name, pool_size, training, full_res_attention, update_running)
+    """UNetDFCSA.forward (reference models/unet_dfc_sa_res.py:161-204).  Channel widths come from the tensors.
+    The ablation networks share this wiring (models/unet_dfc_sa_ablation_branches.py:132-164,
+    models/unet_dfc_sa_ablation_placement.py:108-147 etc.) and differ only in the block type per position, which is read
+    off the state dict: a block without gate parameters is a LocalOnlyBlock."""
+    def blk(t, name):
+        if (name + ".gate.0.weight") in sd:
+            return dfc_block(t, sd, name, pool_size, training, full_res_attention, update_running)
+        return local_only_block(t, sd, name, training, update_running)
     d1 = blk(x, "down1"); p1 = F.max_pool2d(d1, 2, 2)      # :163-164
     d2 = blk(p1, "down2"); p2 = F.max_pool2d(d2, 2, 2)
     d3 = blk(p2, "down3"); p3 = F.max_pool2d(d3, 2, 2)

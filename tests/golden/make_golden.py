@@ -12,6 +12,9 @@ Fixtures (float32 .npz, a few hundred KB in total):
   net_eval.npz   same weights + the post-step running statistics, eval mode, second input: logits
   fullres.npz    UNet_FullResAttention (ablation 3) with the same weights on 1x3x32x32: logits
   metrics.npz    calculate_metrics('bce_dice') on random probabilities incl. saturated values
+  ablations.npz  (python tests/golden/make_golden.py ablations) UNet_Baseline / UNet_EncoderOnlyDFC / UNet_DecoderOnlyDFC
+                 / UNet_BothStandardConv (features [8,8,16,16], pool 4) on 2x3x32x32, gamma=0.5: weights, image, mask,
+                 logits, bce_dice loss and all parameter gradients, per model
 """
 import importlib.util
 import os
@@ -55,7 +58,37 @@ def structured(B, H, W, seed):
     return 0.5 * torch.randn(B, 3, H, W, generator=g) + low, (low > 0.3).float()
 
 
+def ablations():
+    ref, refm, refa = load_reference()
+    refb = sys.modules["refpkg.unet_dfc_sa_ablation_branches"]
+    refp = load("refpkg.unet_dfc_sa_ablation_placement", os.path.join(REF, "models/unet_dfc_sa_ablation_placement.py"))
+    img, mask = structured(2, 32, 32, 5)
+    d = {"image": img.numpy(), "mask": mask.numpy()}
+    for name, ctor in (("UNet_Baseline", lambda: refb.UNet_Baseline(3, 1, [8, 8, 16, 16])),
+                       ("UNet_EncoderOnlyDFC", lambda: refp.UNet_EncoderOnlyDFC(3, 1, [8, 8, 16, 16], pool_size=4)),
+                       ("UNet_DecoderOnlyDFC", lambda: refp.UNet_DecoderOnlyDFC(3, 1, [8, 8, 16, 16], pool_size=4)),
+                       ("UNet_BothStandardConv", lambda: refp.UNet_BothStandardConv(3, 1, [8, 8, 16, 16]))):
+        torch.manual_seed(0)
+        net = ctor()
+        with torch.no_grad():
+            for n, p in net.named_parameters():
+                if n.endswith("gamma"):
+                    p.fill_(0.5)
+        d.update(sd_np(net.state_dict(), f"{name}/w:"))
+        net.train()
+        logits = net(img)
+        m = refm.calculate_metrics(torch.sigmoid(logits), mask, "bce_dice", {})
+        m["loss"].backward()
+        d[f"{name}/logits"] = logits.detach().numpy()
+        d[f"{name}/loss"] = np.float32(m["loss"].item())
+        d.update({f"{name}/g:" + k: p.grad.numpy() for k, p in net.named_parameters()})
+    np.savez_compressed(os.path.join(HERE, "ablations.npz"), **d)
+    print("ablations.npz written")
+
+
 def main():
+    if sys.argv[1:] == ["ablations"]:
+        return ablations()
     ref, refm, refa = load_reference()
     torch.manual_seed(0)
 

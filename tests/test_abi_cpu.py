@@ -64,6 +64,15 @@ def test_factory_names_and_errors():
         ModelFactory.get_model({"model": {"name": "nope"}})
     with pytest.raises(NotImplementedError):
         ModelFactory.get_model({"model": {"name": "UNet"}})
+    # ablations 1(b) / 4: same state-dict keys and shapes as the reference classes (tests/golden/ablations.npz)
+    import numpy as np
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ablations.npz"))
+    for name in ("UNet_Baseline", "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv"):
+        m = ModelFactory.get_model({"model": {"name": name, "features": [8, 8, 16, 16], "pool_size": 4}})
+        ref = {k[len(name) + 3:]: z[k] for k in z.files if k.startswith(name + "/w:")}
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(ref.keys()) and all(tuple(sd[k].shape) == ref[k].shape for k in sd), name
 
 
 def test_no_cpu_fallback():

@@ -142,6 +142,42 @@ def test_full_resolution_attention_net_matches_oracle(cuda, hw, B, gamma):
     assert abs(r["loss"] - r["loss_ref"]) <= 2e-3, r
 
 
+ABLATIONS = ["UNet_Baseline", "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv"]
+
+
+@pytest.mark.parametrize("name", ABLATIONS)
+def test_ablation_nets_match_reference_golden(cuda, name):
+    """ablations 1(b) / 4: logits, loss and every parameter gradient produced by the unmodified reference classes
+    (tests/golden/ablations.npz, features [8, 8, 16, 16] incl. identity-residual blocks)."""
+    from dfcsa.metrics import calculate_metrics
+    from dfcsa.model_factory import ModelFactory
+    d = _load("ablations.npz")
+    model = ModelFactory.get_model({"model": {"name": name, "in_channels": 3, "out_channels": 1, "features": [8, 8, 16, 16], "pool_size": 4}})
+    ref_sd = {k[len(name) + 3:]: v for k, v in d.items() if k.startswith(name + "/w:")}
+    assert list(model.state_dict().keys()) == list(ref_sd.keys())
+    model.load_state_dict(ref_sd)
+    model = model.cuda().train()
+    logits = model(d["image"].cuda())
+    assert (logits.cpu() - d[name + "/logits"]).abs().max().item() <= 2e-2
+    m = calculate_metrics(torch.sigmoid(logits), d["mask"].cuda(), "bce_dice", {})
+    assert abs(float(m["loss"]) - float(d[name + "/loss"])) <= 2e-3
+    m["loss"].backward()
+    num = sum(((p.grad.cpu() - d[f"{name}/g:{n}"]) ** 2).sum() for n, p in model.named_parameters()).sqrt()
+    den = sum((d[f"{name}/g:{n}"] ** 2).sum() for n, _ in model.named_parameters()).sqrt()
+    assert (num / den).item() <= 3e-2, (num / den).item()
+
+
+@pytest.mark.parametrize("name", ABLATIONS[:3])
+def test_ablation_nets_full_width_match_oracle(cuda, name):
+    """the same networks at features [64, 128, 256, 512] (tcgen05 path) against the CPU oracle."""
+    from dfcsa.selftest import forward_backward_parity
+    r = forward_backward_parity(pool_size=4, B=2, H=64, W=64, gamma=0.5, model_name=name)
+    print(r)
+    assert r["logit_maxabs"] <= 2e-2, r
+    assert r["grad_rel_l2"] <= 3e-2, r
+    assert abs(r["loss"] - r["loss_ref"]) <= 2e-3, r
+
+
 def test_state_dict_layout_and_roundtrip(cuda):
     from oracle import dfcsa_oracle as O
     from dfcsa.modules import UNetDFCSARes
