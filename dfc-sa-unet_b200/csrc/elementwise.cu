@@ -358,11 +358,13 @@ gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const 
 }
 
 // y = relu(bn4(F0)) + rs*R, optional 2x2 max pool; one thread per 2x2 window and channel vector
-template <int VEC>
+// PLAIN (the addition / attention-only ablation blocks): y = F0 [+ F1] + rs*R, no BatchNorm / ReLU
+template <int VEC, bool PLAIN = false>
 __global__ void __launch_bounds__(256)
 block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long ld_r, int B, int H, int W, int C,
                      const float* s4, const float* t4, const float* res_scale, act_t* y, long long ld_y, act_t* yp,
-                     long long ld_yp, grad_t* yb, long long ld_yb, grad_t* ypb, long long ld_ypb, int CL, int PL) {
+                     long long ld_yp, grad_t* yb, long long ld_yb, grad_t* ypb, long long ld_ypb, int CL, int PL,
+                     const act_t* f1 = nullptr, long long ld_f1 = 0) {
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c = (blockIdx.y * CL + cl) * VEC;
   if (pl >= PL || c >= C) return;
@@ -371,7 +373,7 @@ block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long
   const unsigned nwin = static_cast<unsigned>(B) * Hw * Ww;
   const float rs = *res_scale;
   float sc[VEC], sh[VEC];
-  ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh);
+  if (!PLAIN) { ldf<VEC>(s4 + c, sc); ldf<VEC>(t4 + c, sh); }
   for (unsigned wi = blockIdx.x * PL + pl; wi < nwin; wi += gridDim.x * PL) {
     const unsigned xo = wi % Ww, q = wi / Ww, yo = q % Hw, b = q / Hw;
     float mx[VEC];
@@ -384,8 +386,18 @@ block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long
       const long long m = (static_cast<long long>(b) * H + yy) * W + xx;
       float fv[VEC], rv[VEC], ov[VEC];
       ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
+      if (PLAIN) {
+        if (f1 != nullptr) {
+          float gv[VEC]; ldv<VEC>(f1 + m * ld_f1 + c, gv);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) ov[v] = fmax_nan(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
+          for (int v = 0; v < VEC; ++v) fv[v] += gv[v];
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ov[v] = fv[v] + rs * rv[v];
+      } else {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) ov[v] = fmax_nan(fmaf(fv[v], sc[v], sh[v]), 0.f) + rs * rv[v];
+      }
       stv<VEC>(y + m * ld_y + c, ov);
       if (yb != nullptr) stv<VEC>(yb + m * ld_yb + c, ov);
       // pool over the values as stored (fp16), so backward can recompute the argmax from y
@@ -621,22 +633,27 @@ branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long lon
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
   if (pl < PL && c < C) {
+    const bool gated = g0 != nullptr;       // the ablation blocks without a gate: dL / dA are final as they arrive
     float sc[VEC], sh[VEC], sc3[VEC], sh3[VEC];
-    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh); ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3);
+    ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh);
+    if (gated) { ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3); }
     for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
       float dl[VEC], da[VEC], df[VEC], gv[VEC], lv[VEC];
-      ldv<VEC>(dz + m * ld_dz + C + c, dl); ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
-      ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(g0 + m * ld_g0 + c, gv);
+      ldv<VEC>(dz + m * ld_dz + C + c, dl);
       ldv<VEC>(l0 + m * ld_l0 + c, lv);
-      // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); rounded to the stored precision so that the sums see
-      // exactly what the later passes read back
+      if (gated) {
+        ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+        ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(g0 + m * ld_g0 + c, gv);
+        // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); rounded to the stored precision so that the sums see
+        // exactly what the later passes read back
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float gg = 1.f / (1.f + __expf(-fmaf(gv[v], sc3[v], sh3[v])));
-        dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
-        da[v] = fmaf(df[v], 1.f - gg, da[v]);
+        for (int v = 0; v < VEC; ++v) {
+          const float gg = 1.f / (1.f + __expf(-fmaf(gv[v], sc3[v], sh3[v])));
+          dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
+          da[v] = fmaf(df[v], 1.f - gg, da[v]);
+        }
+        stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
       }
-      stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
         const float d1 = fmaf(lv[v], sc[v], sh[v]) > 0.f ? dl[v] : 0.f;
@@ -1023,6 +1040,22 @@ extern "C" int dfcsa_gate_mix_fwd(const void* g0, int64_t ld_g0, int64_t M, int3
   return DFCSA_OK;
 }
 
+extern "C" int dfcsa_sum_out_fwd(const void* a, int64_t ld_a, const void* b, int64_t ld_b, const void* r, int64_t ld_r, int32_t B,
+                                 int32_t H, int32_t W, int32_t C, const float* res_scale, void* y, int64_t ld_y, void* yp,
+                                 int64_t ld_yp, void* stream) {
+  DFCSA_CHECK_ARG(a && r && res_scale && y, "dfcsa_sum_out_fwd: null pointer");
+  const bool v8 = vec8_ok(C, {ld_a, b ? ld_b : 0, ld_r, ld_y, yp ? ld_yp : 0}, {a, b, r, y, yp});
+  const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
+  DFCSA_CHECK_ARG(nwin < (1LL << 31), "dfcsa_sum_out_fwd: too many pixels");
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(nwin, g.PL, g.chunks, 4), g.chunks);
+  VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC, true><<<grid, 256, 0, ST>>>(A_(a), ld_a, A_(r), ld_r, B, H, W, C, nullptr, nullptr, res_scale,
+                                                                          AM_(y), ld_y, AM_(yp), ld_yp, nullptr, 0, nullptr, 0,
+                                                                          g.CL, g.PL, A_(b), ld_b)));
+  DFCSA_LAUNCH_CHECK("block_out_fwd_kernel<plain>");
+  return DFCSA_OK;
+}
+
 extern "C" int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r, int64_t ld_r, int32_t B, int32_t H,
                                    int32_t W, int32_t C, const float* scale4, const float* shift4, const float* res_scale,
                                    void* y, int64_t ld_y, void* yp, int64_t ld_yp, void* yb, int64_t ld_yb, void* ypb,
@@ -1108,8 +1141,8 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
                                         const float* mean1, const float* invstd1, const float* scale3, const float* shift3,
                                         const float* o, int32_t P, const float* gamma, double* red1, double* dgamma, float* tmp,
                                         float* d_o, void* stream) {
-  DFCSA_CHECK_ARG(dz && l0 && g0 && scale1 && shift1 && mean1 && invstd1 && scale3 && shift3 && o && gamma && red1 && dgamma && tmp && d_o,
-                  "dfcsa_branch_bwd_reduce1: null pointer");
+  DFCSA_CHECK_ARG(dz && l0 && scale1 && shift1 && mean1 && invstd1 && o && gamma && red1 && dgamma && tmp && d_o &&
+                  (g0 == nullptr || (scale3 && shift3)), "dfcsa_branch_bwd_reduce1: null pointer");
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_bwd_reduce1: too many pixels");
   const bool v8 = vec8_ok(C, {ld_dz, ld_l0, ld_g0}, {dz, l0, g0, o, tmp, scale1, shift1, mean1, invstd1, scale3, shift3});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
@@ -1194,8 +1227,7 @@ extern "C" int dfcsa_colsum(const void* x, int x_dtype, int64_t ld, int64_t M, i
 extern "C" int dfcsa_cast2d(const void* x, int x_dtype, int64_t ld_x, void* y, int y_dtype, int64_t ld_y, int64_t M,
                             int32_t C, void* stream) {
   DFCSA_CHECK_ARG(x && y && M > 0 && C > 0, "dfcsa_cast2d: bad args");
-  if (C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 &&
-      x_dtype != y_dtype) {
+  if (C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
     const int C8 = C / 8;
     const int blocks = ew_blocks(M * C8);
 #define DFCSA_CAST(TX, TY) cast2d_vec_kernel<TX, TY><<<blocks, 256, 0, ST>>>(reinterpret_cast<const TX*>(x), ld_x, reinterpret_cast<TY*>(y), ld_y, M, C8)
@@ -1204,7 +1236,10 @@ extern "C" int dfcsa_cast2d(const void* x, int x_dtype, int64_t ld_x, void* y, i
     else if (x_dtype == DFCSA_F16 && y_dtype == DFCSA_F32) DFCSA_CAST(__half, float);
     else if (x_dtype == DFCSA_BF16 && y_dtype == DFCSA_F32) DFCSA_CAST(__nv_bfloat16, float);
     else if (x_dtype == DFCSA_F16 && y_dtype == DFCSA_BF16) DFCSA_CAST(__half, __nv_bfloat16);
-    else DFCSA_CAST(__nv_bfloat16, __half);
+    else if (x_dtype == DFCSA_BF16 && y_dtype == DFCSA_F16) DFCSA_CAST(__nv_bfloat16, __half);
+    else if (x_dtype == DFCSA_F32) DFCSA_CAST(float, float);                 // same type: a pitched copy
+    else if (x_dtype == DFCSA_F16) DFCSA_CAST(__half, __half);
+    else DFCSA_CAST(__nv_bfloat16, __nv_bfloat16);
 #undef DFCSA_CAST
     DFCSA_LAUNCH_CHECK("cast2d_vec_kernel");
     return DFCSA_OK;

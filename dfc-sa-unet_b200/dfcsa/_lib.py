@@ -91,7 +91,7 @@ SYMBOLS = [
     "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm", "dfcsa_bgemm", "dfcsa_bgemm_rowstat_parts", "dfcsa_lse_combine", "dfcsa_attn_small_fwd", "dfcsa_attn_small_bwd",
     "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd", "dfcsa_softmax_rows_bwd_d", "dfcsa_rowdot",
     "dfcsa_bn_finalize", "dfcsa_bn_eval_affine",
-    "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd",
+    "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd", "dfcsa_sum_out_fwd",
     "dfcsa_block_out_bwd_reduce", "dfcsa_bn_bwd_apply", "dfcsa_gate_mix_bwd_reduce", "dfcsa_gate_mix_bwd_apply",
     "dfcsa_branch_bwd_reduce1", "dfcsa_branch_bwd_reduce2", "dfcsa_branch_bwd_apply", "dfcsa_bn_param_grads",
     "dfcsa_nchw_to_nhwc", "dfcsa_nhwc_to_nchw", "dfcsa_colsum", "dfcsa_cast2d",

@@ -84,10 +84,48 @@ class LocalBlockParams:
         return [self.bn1]
 
 
+class BranchBlockParams:
+    """The ablation blocks that keep the attention branch but not the gate:
+      "attn"    AttentionOnlyBlock   (reference models/unet_dfc_sa_ablation_branches.py:42-69)   y = A + rs*res
+      "add"     AdditionFusionBlock  (models/unet_dfc_sa_ablation_fusion.py:9-55)               y = L + A + rs*res
+      "concat"  ConcatFusionBlock    (models/unet_dfc_sa_ablation_fusion.py:58-108)             y = relu(bn(W4 [L|A])) + rs*res
+    with L = relu(bn1(conv3x3 x)), A = gamma * up(attn(pool(a))) + a, a = relu(bn2(conv1x1 x))."""
+
+    def __init__(self, mod, kind):
+        self.mod, self.kind = mod, kind
+        ab = mod.attn_branch
+        self.W2, self.b2, self.bn2 = ab[0].weight, ab[0].bias, ab[1]
+        att = ab[3]
+        self.att, self.gamma = att, att.gamma
+        self.Wq, self.bq = att.query_conv.weight, att.query_conv.bias
+        self.Wk, self.bk = att.key_conv.weight, att.key_conv.bias
+        self.Wv, self.bv = att.value_conv.weight, att.value_conv.bias
+        self.has_l = kind != "attn"
+        if self.has_l:
+            cb = mod.conv_branch
+            self.W1, self.b1, self.bn1 = cb[0].weight, cb[0].bias, cb[1]
+        if kind == "concat":
+            fu = mod.fusion_conv
+            self.W4, self.b4, self.bn4 = fu[0].weight, fu[0].bias, fu[1]
+        self.W5 = getattr(mod.residual_conv, "weight", None)
+        self.res_scale = mod.res_scale
+        self.Ci, self.C = self.W2.shape[1], self.W2.shape[0]
+        self.Cq = self.Wq.shape[0]
+        self.P = att.pool_size
+        self.tc = (self.Ci % 64 == 0) and (self.C % 64 == 0)
+
+    def bns(self):
+        return ([self.bn1] if self.has_l else []) + [self.bn2] + ([self.bn4] if self.kind == "concat" else [])
+
+
 def make_block_params(mod):
     """The engine-side view of one block module, by its structure (sub-module names are the reference's)."""
     if hasattr(mod, "gate"):
         return BlockParams(mod)
+    if hasattr(mod, "attn_branch"):
+        if hasattr(mod, "fusion_conv"):
+            return BranchBlockParams(mod, "concat")
+        return BranchBlockParams(mod, "add" if hasattr(mod, "conv_branch") else "attn")
     if hasattr(mod, "conv_branch") and not hasattr(mod, "attn_branch"):
         return LocalBlockParams(mod)
     raise NotImplementedError(f"dfcsa: no kernels for block type {type(mod).__name__}")
@@ -134,11 +172,13 @@ class PackPlan:
 def pack_block_weights(bp, training, need_dx, plan):
     """fp32 master weights -> packed K-major GEMM operands (forward: fp16 / fp32; dgrad: bf16 / fp32): allocates the
     persistent destination buffers and records the re-layout jobs in `plan`."""
-    dev = bp.W1.device
+    dev = bp.res_scale.device
     Ci, C = bp.Ci, bp.C
     fdt = F16 if bp.tc else F32
     pk = {}
     W5 = bp.W5.detach() if bp.W5 is not None else torch.eye(C, dtype=F32, device=dev).view(C, C, 1, 1)
+    if bp.kind in ("attn", "add", "concat"):
+        return _pack_branch_block(bp, pk, W5, training, need_dx, plan)
     pk["w1"] = _e((C, 9 * Ci), fdt, dev)
     plan.add(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
     if bp.kind == "local":
@@ -158,7 +198,64 @@ def pack_block_weights(bp, training, need_dx, plan):
     plan.add(bp.W3.detach(), pk["w3"], (C, 1, 2 * C), (2 * C, 0, 1))
     pk["w4"] = _e((C, 3 * C), gdt, dev)
     plan.add(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1))
-    # q/k/v 1x1 convs on the pooled map as ONE GEMM: rows [Wq ; Wk ; Wv], bias [bq | bk | bv]
+    _pack_attention(bp, pk, training, plan)
+    if training:
+        bdt = BF16 if C % 64 == 0 else F32
+        W4m, W3m = bp.W4.detach().view(C, 3 * C), bp.W3.detach().view(C, 2 * C)
+        pk["wd4f"] = _e((C, C), bdt, dev)           # df = dF0 . W4^T[0:C, :]:  wd4f[k, co] = W4[co, k]
+        plan.add(W4m, pk["wd4f"], (C, 1, C), (1, 0, 3 * C))
+        # [dL | dA] = [dF0 | dG0] . wd43^T with wd43[n, (co of W4 | co of W3)] = (W4[co, C + n] | W3[co, n])
+        pk["wd43"] = _e((2 * C, 2 * C), bdt, dev)
+        plan.add(W4m[:, C:], pk["wd43"], (2 * C, 1, C), (1, 0, 3 * C), ld_dst=2 * C)
+        plan.add(W3m, pk["wd43"][:, C:], (2 * C, 1, C), (1, 0, 2 * C), ld_dst=2 * C)
+        if need_dx:   # the first block never needs the gradient w.r.t. the image
+            pk["wd125"] = _pack_input_dgrad(bp, W5, plan, True)
+    return pk
+
+
+def _pack_input_dgrad(bp, W5, plan, has_l):
+    """dgrad operand of the convs that read the block input: [ci, (flipped tap, co of W1) | co (W2) | co (res_scale*W5)]."""
+    Ci, C = bp.Ci, bp.C
+    n = (11 if has_l else 2) * C
+    wd = _e((Ci, n), BF16 if bp.tc else F32, W5.device)
+    o = 0
+    if has_l:
+        plan.add(bp.W1.detach(), wd, (Ci, 9, C), (9, 1, Ci * 9), flip1=True, ld_dst=n)
+        o = 9 * C
+    plan.add(bp.W2.detach(), wd[:, o:], (Ci, 1, C), (1, 0, Ci), ld_dst=n)
+    plan.add(W5, wd[:, o + C:], (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1), ld_dst=n)
+    return wd
+
+
+def _pack_branch_block(bp, pk, W5, training, need_dx, plan):
+    dev = W5.device
+    Ci, C = bp.Ci, bp.C
+    fdt = F16 if bp.tc else F32
+    gdt = F16 if C % 64 == 0 else F32
+    if bp.has_l:
+        pk["w1"] = _e((C, 9 * Ci), fdt, dev)
+        plan.add(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9))
+    pk["w25"] = _e((2 * C, Ci), fdt, dev)
+    plan.add(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1))
+    plan.add(W5, pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
+    if bp.kind == "concat":
+        pk["w4c"] = _e((C, 2 * C), gdt, dev)
+        plan.add(bp.W4.detach(), pk["w4c"], (C, 1, 2 * C), (2 * C, 0, 1))
+    _pack_attention(bp, pk, training, plan)
+    if training:
+        if bp.kind == "concat":        # [dL | dA] = dF0 . W4:  wd4c[n, co] = W4[co, n]
+            pk["wd4c"] = _e((2 * C, C), BF16 if C % 64 == 0 else F32, dev)
+            plan.add(bp.W4.detach().view(C, 2 * C), pk["wd4c"], (2 * C, 1, C), (1, 0, 2 * C))
+        if need_dx:
+            pk["wd125"] = _pack_input_dgrad(bp, W5, plan, bp.has_l)
+    return pk
+
+
+def _pack_attention(bp, pk, training, plan):
+    """q/k/v 1x1 convs on the pooled map as ONE GEMM: rows [Wq ; Wk ; Wv], bias [bq | bk | bv] (+ the dgrad operand)."""
+    dev = bp.Wq.device
+    C = bp.C
+    gdt = F16 if C % 64 == 0 else F32
     Cq = bp.Cq
     nq = 2 * Cq + C
     pk["wqkv"] = _e((nq, C), gdt, dev)
@@ -177,21 +274,6 @@ def pack_block_weights(bp, training, need_dx, plan):
         plan.add(bp.Wk.detach(), wdq[:, Cq:2 * Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
         plan.add(bp.Wv.detach(), wdq[:, 2 * Cq:nq], (C, 1, C), (1, 0, C), ld_dst=kp)
         pk["wdqkv"] = wdq
-        W4m, W3m = bp.W4.detach().view(C, 3 * C), bp.W3.detach().view(C, 2 * C)
-        pk["wd4f"] = _e((C, C), bdt, dev)           # df = dF0 . W4^T[0:C, :]:  wd4f[k, co] = W4[co, k]
-        plan.add(W4m, pk["wd4f"], (C, 1, C), (1, 0, 3 * C))
-        # [dL | dA] = [dF0 | dG0] . wd43^T with wd43[n, (co of W4 | co of W3)] = (W4[co, C + n] | W3[co, n])
-        pk["wd43"] = _e((2 * C, 2 * C), bdt, dev)
-        plan.add(W4m[:, C:], pk["wd43"], (2 * C, 1, C), (1, 0, 3 * C), ld_dst=2 * C)
-        plan.add(W3m, pk["wd43"][:, C:], (2 * C, 1, C), (1, 0, 2 * C), ld_dst=2 * C)
-        if need_dx:   # the first block never needs the gradient w.r.t. the image
-            xdt = BF16 if bp.tc else F32
-            wd = _e((Ci, 11 * C), xdt, dev)            # [ci, (flipped tap, co) | co (W2) | co (res_scale*W5)]
-            plan.add(bp.W1.detach(), wd, (Ci, 9, C), (9, 1, Ci * 9), flip1=True, ld_dst=11 * C)
-            plan.add(bp.W2.detach(), wd[:, 9 * C:], (Ci, 1, C), (1, 0, Ci), ld_dst=11 * C)
-            plan.add(W5, wd[:, 10 * C:], (Ci, 1, C), (1, 0, Ci), scale=bp.res_scale.detach().reshape(1), ld_dst=11 * C)
-            pk["wd125"] = wd
-    return pk
 
 
 class NetPacks:
@@ -431,6 +513,8 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     resolution / 2x2 max-pooled).  Returns the context the backward needs."""
     if bp.kind == "local":
         return _local_block_forward(bp, pk, x, B, H, W, y, yp, training, save)
+    if bp.kind != "dfc":
+        return _branch_block_forward(bp, pk, x, B, H, W, y, yp, training, save)
     dev = x.device
     C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
     M = B * H * W
@@ -515,6 +599,104 @@ def _local_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
         _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1))
 
 
+def _branch_block_forward(bp, pk, x, B, H, W, y, yp, training, save):
+    """AttentionOnly / AdditionFusion / ConcatFusion blocks: the DFC block's two branches without the gate.  The
+    attention-only block has no conv branch; the two-branch kernels then run with the conv-branch operand aliased to the
+    attention branch's (its outputs are ignored)."""
+    dev = x.device
+    C, P = bp.C, _pool_side(bp, H, W)
+    M = B * H * W
+    ctx = BlockCtx() if (training and save) else None
+    st = _z((10 * C,), F64, dev) if training else None
+    AR = _e((M, 2 * C), F16, dev)
+    segs1 = [(x, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs1, pk["w25"], 2 * C, AR, stats=st[2 * C:6 * C] if training else None,
+                  backend=_backend(segs1, pk["w25"], 2 * C, AR))
+    A0, R = AR[:, :C], AR[:, C:]
+    bn2 = _bn_affine(bp.bn2, bp.b2, st[2 * C:3 * C] if training else None, st[4 * C:5 * C] if training else None, M, training, dev)
+    if bp.has_l:
+        L0 = _e((M, C), F16, dev)
+        segs3 = [(x, TAP_3x3)]
+        ops.conv_gemm(B, H, W, segs3, pk["w1"], C, L0, stats=st[0:2 * C] if training else None, backend=_backend(segs3, pk["w1"], C, L0))
+        bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
+    else:
+        L0, bn1 = A0, bn2
+    tmp = _e((B, H, P, C), F32, dev)
+    pooled = _e((B * P * P, C), F32, dev)
+    ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled)
+    o = attention_forward(bp, pk, pooled, B, P * P, ctx)
+    z = _e((M, 3 * C), F16, dev)            # [unused | L | A]
+    ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z, None)
+    F0 = bn4 = None
+    if bp.kind == "concat":
+        F0 = _e((M, C), F16, dev)
+        segs = [(z[:, C:], TAP_1x1)]
+        ops.conv_gemm(B, H, W, segs, pk["w4c"], C, F0, stats=st[8 * C:10 * C] if training else None, backend=_backend(segs, pk["w4c"], C, F0))
+        bn4 = _bn_affine(bp.bn4, bp.b4, st[8 * C:9 * C] if training else None, st[9 * C:10 * C] if training else None, M, training, dev)
+        ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp, None, None)
+    else:
+        ops.sum_out_fwd(z[:, 2 * C:], z[:, C:2 * C] if bp.has_l else None, R, B, H, W, bp.res_scale.detach(), y, yp)
+    if ctx is not None:
+        ctx.B, ctx.H, ctx.W = B, H, W
+        ctx.L0, ctx.A0, ctx.R, ctx.F0, ctx.z, ctx.y, ctx.o = L0, A0, R, F0, z, y, o
+        ctx.bn1, ctx.bn2, ctx.bn4 = bn1, bn2, bn4
+    return ctx
+
+
+def _branch_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
+    dev = dskip.device if dskip is not None else dyp.device
+    B, H, W = ctx.B, ctx.H, ctx.W
+    C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
+    M = B * H * W
+    red = _z((8 * C + 2,), F64, dev)
+    red1, red2, red4 = red[0:2 * C], red[2 * C:4 * C], red[6 * C:8 * C]
+    drs, dgam = red[8 * C:8 * C + 1], red[8 * C + 1:8 * C + 2]
+    bn1, bn2 = ctx.bn1, ctx.bn2
+    dy = dskip if dskip is not None else _e((M, C), BF16, dev)
+    dz = _e((M, 3 * C), BF16, dev)
+    dLA = dz[:, C:]
+    if bp.kind == "concat":
+        bn4 = ctx.bn4
+        ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.F0, ctx.R, B, H, W, bn4[0], bn4[1], bn4[2], bn4[3], dy, red4, drs)
+        dF0 = _e((M, C), BF16, dev)
+        ops.bn_bwd_apply(dy, ctx.F0, bn4[0], bn4[1], bn4[2], bn4[3], red4, 0, dF0)
+        ops.bn_param_grads(red4, C, grads[bp.bn4.weight], grads[bp.bn4.bias])
+        segs = [(dF0, TAP_1x1)]
+        ops.conv_gemm(B, H, W, segs, pk["wd4c"], 2 * C, dLA, backend=_backend(segs, pk["wd4c"], 2 * C, dLA))
+        _wgrad(B, H, W, ctx.z[:, C:], TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 2 * C))
+    else:
+        # y = [L +] A + rs*R: dL = dA = dy.  The output-stage reduction also gathers the pooled gradient and d res_scale;
+        # its BatchNorm sums (taken over y with bn2's constants here) are not used
+        ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.y, ctx.R, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dy, red4, drs)
+        ops.cast2d(dy, dz[:, C:2 * C])
+        ops.cast2d(dy, dz[:, 2 * C:])
+    tmp = _e((B, H, P, C), F32, dev)
+    d_o = _e((B * P * P, C), F32, dev)
+    ops.branch_bwd_reduce1(dz, ctx.L0, None, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], None, None, ctx.o, P,
+                           bp.gamma.detach(), red1, dgam, tmp, d_o)
+    dpooled = attention_backward(bp, pk, ctx, d_o, B, P * P, grads)
+    ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
+    dL0, dA0 = _e((M, C), BF16, dev), _e((M, C), BF16, dev)
+    ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
+    if bp.has_l:
+        ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
+    ops.bn_param_grads(red2, C, grads[bp.bn2.weight], grads[bp.bn2.bias])
+    grads[bp.gamma].copy_(dgam)
+    grads[bp.res_scale].copy_(drs[0])
+    if dx_out is not None:
+        segs = ([(dL0, TAP_3x3)] if bp.has_l else []) + [(dA0, TAP_1x1), (dy, TAP_1x1)]
+        ops.conv_gemm(B, H, W, segs, pk["wd125"], Ci, dx_out, backend=_backend(segs, pk["wd125"], Ci, dx_out))
+    if bp.has_l:
+        dW1p = _z((C, 9 * Ci), F32, dev)
+        _wgrad(B, H, W, xw, TAP_3x3, dL0, TAP_1x1, dW1p)
+        ops.permute3(dW1p, grads[bp.W1], (C, Ci, 9), (9 * Ci, 1, Ci))
+    if bp.W5 is not None:
+        _wgrad(B, H, W, xw, TAP_1x1, dy, TAP_1x1, grads[bp.W5].view(C, Ci), alpha=bp.res_scale.detach().reshape(1),
+               second=(dA0, grads[bp.W2].view(C, Ci), 0, None))
+    else:
+        _wgrad(B, H, W, xw, TAP_1x1, dA0, TAP_1x1, grads[bp.W2].view(C, Ci))
+
+
 def _wgrad(B, H, W, x, x_mode, dy, dy_mode, dw2d, alpha=None, second=None):
     """second = (dy2, dw2, c_begin2, alpha2): another 1x1 weight gradient over the same x, same launch."""
     tc = ops.wgrad_tc_eligible(x, dy) and (x.dtype == dy.dtype or (x.dtype == F16 and dy.dtype == BF16))
@@ -531,6 +713,8 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     grads: dict parameter -> fp32 gradient tensor (zero-initialised where the kernels accumulate)."""
     if bp.kind == "local":
         return _local_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads)
+    if bp.kind != "dfc":
+        return _branch_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads)
     dev = dskip.device if dskip is not None else dyp.device
     B, H, W = ctx.B, ctx.H, ctx.W
     C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)

@@ -1,13 +1,12 @@
 """ModelFactory mirror (reference models/model_factory.py:14-186): the name -> class boundary of the hot path."""
 import torch
 
-from .modules import (UNet_Baseline, UNet_BothStandardConv, UNet_DecoderOnlyDFC, UNet_EncoderOnlyDFC, UNet_FullResAttention,
-                      UNetDFCSARes)
+from .modules import (UNet_AdditionFusion, UNet_AttentionOnly, UNet_Baseline, UNet_BothStandardConv, UNet_ConcatFusion,
+                      UNet_DecoderOnlyDFC, UNet_EncoderOnlyDFC, UNet_FullResAttention, UNetDFCSARes)
 
 # names the reference factory knows (models/model_factory.py:94-183) that are outside the B200 hot path
 _OUT_OF_SCOPE = {
     "UNet", "TransformerUNet", "TransUNet", "ViTSegmentation", "ViT_Seg", "VisionTransformer",
-    "UNet_AttentionOnly", "UNet_AdditionFusion", "UNet_ConcatFusion",
 }
 
 
@@ -48,7 +47,13 @@ class ModelFactory:
                                 pool_size=pool_size, ablation_on_qk_channels=qk)
         if name == "UNet_FullResAttention":                  # reference :174-175 (ablation 3)
             return UNet_FullResAttention(in_channels=in_channels, out_channels=out_channels, features=features)
-        # ablations 1(b) and 4 (reference :162-163, :178-183): the same kernels re-wired
+        # ablations 1, 2 and 4 (reference :162-171, :178-183): the same kernels re-wired
+        if name == "UNet_AttentionOnly":
+            return UNet_AttentionOnly(in_channels, out_channels, features, pool_size)
+        if name == "UNet_AdditionFusion":
+            return UNet_AdditionFusion(in_channels, out_channels, features, pool_size)
+        if name == "UNet_ConcatFusion":
+            return UNet_ConcatFusion(in_channels, out_channels, features, pool_size)
         if name == "UNet_Baseline":
             return UNet_Baseline(in_channels, out_channels, features)
         if name == "UNet_BothStandardConv":

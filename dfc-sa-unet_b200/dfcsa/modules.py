@@ -208,6 +208,57 @@ class LocalOnlyBlock(nn.Module):
         return _BlockFunction.apply(x, self, need_grad, *params)
 
 
+class _AblationBlock(nn.Module):
+    def forward(self, x):
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        return _BlockFunction.apply(x, self, need_grad, *params)
+
+    @staticmethod
+    def _conv_branch(i, o):
+        return nn.Sequential(nn.Conv2d(i, o, kernel_size=3, stride=1, padding=1), nn.BatchNorm2d(o), nn.ReLU(inplace=True))
+
+    @staticmethod
+    def _attn_branch(i, o, pool_size):
+        return nn.Sequential(nn.Conv2d(i, o, kernel_size=1), nn.BatchNorm2d(o), nn.ReLU(inplace=True),
+                             LightSelfAttention(o, pool_size=pool_size))
+
+    def _residual(self, i, o):
+        self.residual_conv = nn.Conv2d(i, o, kernel_size=1, bias=False) if i != o else nn.Identity()
+        self.res_scale = nn.Parameter(torch.tensor(0.1))
+
+
+class AttentionOnlyBlock(_AblationBlock):
+    """reference models/unet_dfc_sa_ablation_branches.py:42-69: the attention branch + res_scale * residual."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, pool_size=8):
+        super().__init__()
+        self.attn_branch = self._attn_branch(in_channels, out_channels, pool_size)
+        self._residual(in_channels, out_channels)
+
+
+class AdditionFusionBlock(_AblationBlock):
+    """reference models/unet_dfc_sa_ablation_fusion.py:9-55: conv branch + attention branch + res_scale * residual."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, pool_size=8):
+        super().__init__()
+        self.conv_branch = self._conv_branch(in_channels, out_channels)
+        self.attn_branch = self._attn_branch(in_channels, out_channels, pool_size)
+        self._residual(in_channels, out_channels)
+
+
+class ConcatFusionBlock(_AblationBlock):
+    """reference models/unet_dfc_sa_ablation_fusion.py:58-108: 1x1 conv + BN + ReLU over [conv branch | attention branch]."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, pool_size=8):
+        super().__init__()
+        self.conv_branch = self._conv_branch(in_channels, out_channels)
+        self.attn_branch = self._attn_branch(in_channels, out_channels, pool_size)
+        self.fusion_conv = nn.Sequential(nn.Conv2d(out_channels * 2, out_channels, kernel_size=1), nn.BatchNorm2d(out_channels),
+                                         nn.ReLU(inplace=True))
+        self._residual(in_channels, out_channels)
+
+
 class _AblationUNet(nn.Module):
     """The U-Net wiring shared by the ablation networks (reference models/unet_dfc_sa_ablation_branches.py:104-164 and the
     three classes of models/unet_dfc_sa_ablation_placement.py): same sub-module names as UNetDFCSA, one block constructor
@@ -276,3 +327,27 @@ class UNet_DecoderOnlyDFC(_AblationUNet):
 
     def __init__(self, in_channels, out_channels, features, pool_size=8):
         super().__init__(_local, _dfc(pool_size), in_channels, out_channels, features)
+
+
+class UNet_AttentionOnly(_AblationUNet):
+    """ablation 1(a), reference models/unet_dfc_sa_ablation_branches.py:170-171."""
+
+    def __init__(self, in_channels, out_channels, features, pool_size=8):
+        blk = lambda i, o: AttentionOnlyBlock(i, o, pool_size=pool_size)
+        super().__init__(blk, blk, in_channels, out_channels, features)
+
+
+class UNet_AdditionFusion(_AblationUNet):
+    """ablation 2, reference models/unet_dfc_sa_ablation_fusion.py:102-104."""
+
+    def __init__(self, in_channels, out_channels, features, pool_size=8):
+        blk = lambda i, o: AdditionFusionBlock(i, o, pool_size=pool_size)
+        super().__init__(blk, blk, in_channels, out_channels, features)
+
+
+class UNet_ConcatFusion(_AblationUNet):
+    """ablation 2, reference models/unet_dfc_sa_ablation_fusion.py:106-108."""
+
+    def __init__(self, in_channels, out_channels, features, pool_size=8):
+        blk = lambda i, o: ConcatFusionBlock(i, o, pool_size=pool_size)
+        super().__init__(blk, blk, in_channels, out_channels, features)

@@ -228,6 +228,13 @@ def block_out_fwd(f0, r, B, H, W, s4, t4, res_scale, y, yp=None, yb=None, ypb=No
                                         L.ptr(ypb), _i64(_mat(ypb) if ypb is not None else 0), L.stream())
 
 
+def sum_out_fwd(a, b, r, B, H, W, res_scale, y, yp=None):
+    """y = a [+ b] + res_scale * r (+ 2x2 max pool into yp): the plain-sum output stage of the ablation blocks."""
+    Cn = a.shape[1]
+    L.call("dfcsa_sum_out_fwd", L.ptr(a), _i64(_mat(a)), L.ptr(b), _i64(_mat(b) if b is not None else 0), L.ptr(r), _i64(_mat(r)),
+           B, H, W, Cn, L.ptr(res_scale), L.ptr(y), _i64(_mat(y)), L.ptr(yp), _i64(_mat(yp) if yp is not None else 0), L.stream())
+
+
 def block_out_bwd_reduce(dskip, dyp, y, f0, r, B, H, W, s4, t4, mean4, invstd4, dy_out, red4, drs):
     Cn = f0.shape[1]
     L.call("dfcsa_block_out_bwd_reduce", 
@@ -260,7 +267,7 @@ def gate_mix_bwd_apply(dz, z, g0, s3, t3, mean3, invstd3, red3, dg0):
 
 def branch_bwd_reduce1(dz, l0, g0, B, H, W, s1, t1, mean1, invstd1, s3, t3, o, P, gamma, red1, dgamma, tmp, d_o):
     Cn = l0.shape[1]
-    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), L.ptr(g0), _i64(_mat(g0)),
+    L.call("dfcsa_branch_bwd_reduce1", L.ptr(dz), _i64(_mat(dz)), L.ptr(l0), _i64(_mat(l0)), L.ptr(g0), _i64(_mat(g0) if g0 is not None else 0),
                                              B, H, W, Cn, L.ptr(s1),
                                              L.ptr(t1), L.ptr(mean1), L.ptr(invstd1), L.ptr(s3), L.ptr(t3), L.ptr(o), P, L.ptr(gamma), L.ptr(red1),
                                              L.ptr(dgamma), L.ptr(tmp), L.ptr(d_o), L.stream())

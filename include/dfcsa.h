@@ -206,6 +206,13 @@ int dfcsa_bn_eval_affine(int32_t C, const float* gamma, const float* beta, const
                          const float* running_mean, const float* running_var, float eps,
                          float* scale, float* shift, void* stream);
 
+/* y = a [+ b] + res_scale * r with the optional 2x2 max pool: the output stage of the ablation blocks that end in a plain sum
+ * (AdditionFusionBlock, reference models/unet_dfc_sa_ablation_fusion.py:40-55; AttentionOnlyBlock,
+ * models/unet_dfc_sa_ablation_branches.py:60-69).  b may be NULL. */
+int dfcsa_sum_out_fwd(const void* a, int64_t ld_a, const void* b, int64_t ld_b, const void* r, int64_t ld_r, int32_t B,
+                      int32_t H, int32_t W, int32_t C, const float* res_scale, void* y, int64_t ld_y, void* yp,
+                      int64_t ld_yp, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Fused bandwidth kernels of the DFC-SA block forward (reference models/unet_dfc_sa_res.py:95-116, :20-39).
  * All activations fp16 NHWC, per-channel BN affine (scale, shift) fp32.

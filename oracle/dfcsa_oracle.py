@@ -158,6 +158,25 @@ def local_only_block(x, sd, prefix, training=True, update_running=True):
     return local + sd[p + ".res_scale"] * res
 
 
+def branch_ablation_block(x, sd, prefix, pool_size, training=True, update_running=True):
+    """AttentionOnlyBlock (reference models/unet_dfc_sa_ablation_branches.py:60-69), AdditionFusionBlock
+    (models/unet_dfc_sa_ablation_fusion.py:40-55) and ConcatFusionBlock (:88-100), told apart by their parameters."""
+    p = prefix
+    bn = lambda t, name: batch_norm(t, sd, p + name, training, update_running=update_running)
+    a = F.relu(bn(F.conv2d(x, sd[p + ".attn_branch.0.weight"], sd[p + ".attn_branch.0.bias"]), ".attn_branch.1"))
+    attn = light_self_attention(a, sd, p + ".attn_branch.3", pool_size)
+    res = F.conv2d(x, sd[p + ".residual_conv.weight"]) if (p + ".residual_conv.weight") in sd else x
+    if (p + ".conv_branch.0.weight") not in sd:
+        return attn + sd[p + ".res_scale"] * res                                   # attention only
+    local = F.relu(bn(F.conv2d(x, sd[p + ".conv_branch.0.weight"], sd[p + ".conv_branch.0.bias"], padding=1), ".conv_branch.1"))
+    if (p + ".fusion_conv.0.weight") in sd:                                        # concat fusion
+        fused = F.relu(bn(F.conv2d(torch.cat([local, attn], dim=1), sd[p + ".fusion_conv.0.weight"], sd[p + ".fusion_conv.0.bias"]),
+                          ".fusion_conv.1"))
+    else:                                                                          # addition fusion
+        fused = local + attn
+    return fused + sd[p + ".res_scale"] * res
+
+
 def unet_forward(x, sd, pool_size, training=True, full_res_attention=False, update_running=True):
     """UNetDFCSA.forward (reference models/unet_dfc_sa_res.py:161-204).  Channel widths come from the tensors.
     The ablation networks share this wiring (models/unet_dfc_sa_ablation_branches.py:132-164,
@@ -166,6 +185,8 @@ def unet_forward(x, sd, pool_size, training=True, full_res_attention=False, upda
     def blk(t, name):
         if (name + ".gate.0.weight") in sd:
             return dfc_block(t, sd, name, pool_size, training, full_res_attention, update_running)
+        if (name + ".attn_branch.0.weight") in sd:
+            return branch_ablation_block(t, sd, name, pool_size, training, update_running)
         return local_only_block(t, sd, name, training, update_running)
     d1 = blk(x, "down1"); p1 = F.max_pool2d(d1, 2, 2)      # :163-164
     d2 = blk(p1, "down2"); p2 = F.max_pool2d(d2, 2, 2)

@@ -13,7 +13,8 @@ Fixtures (float32 .npz, a few hundred KB in total):
   fullres.npz    UNet_FullResAttention (ablation 3) with the same weights on 1x3x32x32: logits
   metrics.npz    calculate_metrics('bce_dice') on random probabilities incl. saturated values
   ablations.npz  (python tests/golden/make_golden.py ablations) UNet_Baseline / UNet_EncoderOnlyDFC / UNet_DecoderOnlyDFC
-                 / UNet_BothStandardConv (features [8,8,16,16], pool 4) on 2x3x32x32, gamma=0.5: weights, image, mask,
+                 / UNet_BothStandardConv / UNet_AttentionOnly / UNet_AdditionFusion / UNet_ConcatFusion (features
+                 [8,8,16,16], pool 4) on 2x3x32x32, gamma=0.5: weights, image, mask,
                  logits, bce_dice loss and all parameter gradients, per model
 """
 import importlib.util
@@ -62,12 +63,16 @@ def ablations():
     ref, refm, refa = load_reference()
     refb = sys.modules["refpkg.unet_dfc_sa_ablation_branches"]
     refp = load("refpkg.unet_dfc_sa_ablation_placement", os.path.join(REF, "models/unet_dfc_sa_ablation_placement.py"))
+    reff = load("refpkg.unet_dfc_sa_ablation_fusion", os.path.join(REF, "models/unet_dfc_sa_ablation_fusion.py"))
     img, mask = structured(2, 32, 32, 5)
     d = {"image": img.numpy(), "mask": mask.numpy()}
     for name, ctor in (("UNet_Baseline", lambda: refb.UNet_Baseline(3, 1, [8, 8, 16, 16])),
                        ("UNet_EncoderOnlyDFC", lambda: refp.UNet_EncoderOnlyDFC(3, 1, [8, 8, 16, 16], pool_size=4)),
                        ("UNet_DecoderOnlyDFC", lambda: refp.UNet_DecoderOnlyDFC(3, 1, [8, 8, 16, 16], pool_size=4)),
-                       ("UNet_BothStandardConv", lambda: refp.UNet_BothStandardConv(3, 1, [8, 8, 16, 16]))):
+                       ("UNet_BothStandardConv", lambda: refp.UNet_BothStandardConv(3, 1, [8, 8, 16, 16])),
+                       ("UNet_AttentionOnly", lambda: refb.UNet_AttentionOnly(3, 1, [8, 8, 16, 16], pool_size=4)),
+                       ("UNet_AdditionFusion", lambda: reff.UNet_AdditionFusion(3, 1, [8, 8, 16, 16], pool_size=4)),
+                       ("UNet_ConcatFusion", lambda: reff.UNet_ConcatFusion(3, 1, [8, 8, 16, 16], pool_size=4))):
         torch.manual_seed(0)
         net = ctor()
         with torch.no_grad():

@@ -68,7 +68,8 @@ def test_factory_names_and_errors():
     import numpy as np
     import os
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ablations.npz"))
-    for name in ("UNet_Baseline", "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv"):
+    for name in ("UNet_Baseline", "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv",
+             "UNet_AttentionOnly", "UNet_AdditionFusion", "UNet_ConcatFusion"):
         m = ModelFactory.get_model({"model": {"name": name, "features": [8, 8, 16, 16], "pool_size": 4}})
         ref = {k[len(name) + 3:]: z[k] for k in z.files if k.startswith(name + "/w:")}
         sd = m.state_dict()

@@ -142,7 +142,8 @@ def test_full_resolution_attention_net_matches_oracle(cuda, hw, B, gamma):
     assert abs(r["loss"] - r["loss_ref"]) <= 2e-3, r
 
 
-ABLATIONS = ["UNet_Baseline", "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv"]
+ABLATIONS = ["UNet_Baseline", "UNet_EncoderOnlyDFC", "UNet_DecoderOnlyDFC", "UNet_BothStandardConv",
+             "UNet_AttentionOnly", "UNet_AdditionFusion", "UNet_ConcatFusion"]
 
 
 @pytest.mark.parametrize("name", ABLATIONS)
@@ -160,14 +161,14 @@ def test_ablation_nets_match_reference_golden(cuda, name):
     logits = model(d["image"].cuda())
     assert (logits.cpu() - d[name + "/logits"]).abs().max().item() <= 2e-2
     m = calculate_metrics(torch.sigmoid(logits), d["mask"].cuda(), "bce_dice", {})
-    assert abs(float(m["loss"]) - float(d[name + "/loss"])) <= 2e-3
+    assert abs(float(m["loss"].detach()) - float(d[name + "/loss"])) <= 2e-3
     m["loss"].backward()
     num = sum(((p.grad.cpu() - d[f"{name}/g:{n}"]) ** 2).sum() for n, p in model.named_parameters()).sqrt()
     den = sum((d[f"{name}/g:{n}"] ** 2).sum() for n, _ in model.named_parameters()).sqrt()
     assert (num / den).item() <= 3e-2, (num / den).item()
 
 
-@pytest.mark.parametrize("name", ABLATIONS[:3])
+@pytest.mark.parametrize("name", [n for n in ABLATIONS if n != "UNet_BothStandardConv"])
 def test_ablation_nets_full_width_match_oracle(cuda, name):
     """the same networks at features [64, 128, 256, 512] (tcgen05 path) against the CPU oracle."""
     from dfcsa.selftest import forward_backward_parity
