@@ -10,6 +10,8 @@ __device__ __forceinline__ float sigmoidf_exact(float x) { return 1.f / (1.f + e
 // sums: 0 bce_sum, 1 sum p*t, 2 sum p, 3 sum t, 4 sum [p>.5]*t, 5 sum [p>.5]
 __global__ void __launch_bounds__(256)
 bce_dice_sums_kernel(const float* __restrict__ x, const float* __restrict__ t, long long n, int from_logits, double* sums) {
+  // blockIdx.y = sample of the batched entry point (n elements and 8 sums per sample); 0 for the whole-batch one
+  x += static_cast<long long>(blockIdx.y) * n; t += static_cast<long long>(blockIdx.y) * n; sums += blockIdx.y * 8;
   float a[6] = {0, 0, 0, 0, 0, 0};
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -38,7 +40,11 @@ bce_dice_sums_kernel(const float* __restrict__ x, const float* __restrict__ t, l
   }
 }
 
-__global__ void bce_dice_finalize_kernel(const double* sums, long long n, float w_bce, float w_dice, float smooth, float* out) {
+__global__ void bce_dice_finalize_kernel(const double* sums, long long n, float w_bce, float w_dice, float smooth, float* out,
+                                         int n_samples = 1) {
+  const int smp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (smp >= n_samples) return;
+  sums += smp * 8; out += smp * 5;
   const double bce = sums[0] / static_cast<double>(n);
   const double dice_l = 1.0 - (2.0 * sums[1] + smooth) / (sums[2] + sums[3] + smooth);
   out[0] = static_cast<float>(w_bce * bce + w_dice * dice_l);
@@ -142,6 +148,21 @@ extern "C" int dfcsa_bce_dice_finalize(const double* sums, int64_t n, float w_bc
   DFCSA_CHECK_ARG(sums && out && n > 0, "dfcsa_bce_dice_finalize: bad args");
   bce_dice_finalize_kernel<<<1, 1, 0, ST>>>(sums, n, w_bce, w_dice, smooth, out);
   DFCSA_LAUNCH_CHECK("bce_dice_finalize_kernel");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_bce_dice_sums_batched(const float* x, const float* t, int64_t n_per_sample, int32_t n_samples, int from_logits,
+                                           double* sums, void* stream) {
+  DFCSA_CHECK_ARG(x && t && sums && n_per_sample > 0 && n_samples > 0 && n_samples <= 65535, "dfcsa_bce_dice_sums_batched: bad args");
+  dim3 grid(std::max(1, loss_blocks(n_per_sample) / std::max(1, n_samples / 4)), n_samples);
+  bce_dice_sums_kernel<<<grid, 256, 0, ST>>>(x, t, n_per_sample, from_logits, sums);
+  DFCSA_LAUNCH_CHECK("bce_dice_sums_kernel(batched)");
+  return DFCSA_OK;
+}
+extern "C" int dfcsa_bce_dice_finalize_batched(const double* sums, int64_t n_per_sample, int32_t n_samples, float w_bce, float w_dice,
+                                               float smooth, float* out, void* stream) {
+  DFCSA_CHECK_ARG(sums && out && n_per_sample > 0 && n_samples > 0, "dfcsa_bce_dice_finalize_batched: bad args");
+  bce_dice_finalize_kernel<<<(n_samples + 127) / 128, 128, 0, ST>>>(sums, n_per_sample, w_bce, w_dice, smooth, out, n_samples);
+  DFCSA_LAUNCH_CHECK("bce_dice_finalize_kernel(batched)");
   return DFCSA_OK;
 }
 extern "C" int dfcsa_bce_dice_bwd(const float* x, const float* t, int64_t n, int from_logits, const double* sums, float w_bce,

@@ -96,6 +96,7 @@ SYMBOLS = [
     "dfcsa_branch_bwd_reduce1", "dfcsa_branch_bwd_reduce2", "dfcsa_branch_bwd_apply", "dfcsa_bn_param_grads",
     "dfcsa_nchw_to_nhwc", "dfcsa_nhwc_to_nchw", "dfcsa_colsum", "dfcsa_cast2d",
     "dfcsa_bce_dice_sums", "dfcsa_bce_dice_finalize", "dfcsa_bce_dice_bwd",
+    "dfcsa_bce_dice_sums_batched", "dfcsa_bce_dice_finalize_batched",
     "dfcsa_grad_sumsq", "dfcsa_sgd_step",
     "dfcsa_preprocess", "dfcsa_preprocess_workspace_bytes",
 ]

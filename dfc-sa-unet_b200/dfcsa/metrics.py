@@ -40,6 +40,27 @@ def bce_dice_with_logits(logits, target, weight_bce=1.0, weight_dice=1.0, smooth
     return _BceDice.apply(logits, target, True, float(weight_bce), float(weight_dice), float(smooth))
 
 
+def per_sample_metrics(pred, target, loss_type="bce_dice", loss_params=None, from_logits=False):
+    """calculate_metrics of every sample on its own, in two launches, without leaving the device: fp32 [n, 5] =
+    (loss, bce, dice loss, hard IoU, hard Dice) per sample.  This is what the reference's validation loop computes with
+    one calculate_metrics call + three host syncs + three CPU copies per sample (utils/trainer.py:229-245)."""
+    loss_params = loss_params or {}
+    if loss_type == "bce_dice":
+        w_bce, w_dice = loss_params.get("weight_bce", 1.0), loss_params.get("weight_dice", 1.0)
+    elif loss_type == "dice":
+        w_bce, w_dice = 0.0, 1.0
+    else:
+        raise NotImplementedError(f"dfcsa: loss '{loss_type}' is outside the B200 hot path")
+    if not pred.is_cuda:
+        raise RuntimeError("dfcsa: loss kernels take CUDA tensors only (no CPU fallback)")
+    x, t = pred.detach().contiguous().float(), target.contiguous().float()
+    n = x.shape[0]
+    sums = torch.zeros((n, 8), dtype=torch.float64, device=x.device)
+    out = torch.empty((n, 5), dtype=torch.float32, device=x.device)
+    ops.bce_dice_per_sample(x, t, from_logits, float(w_bce), float(w_dice), 1.0, sums, out)
+    return out
+
+
 def calculate_metrics(pred, target, loss_type="dice", loss_params=None):
     """reference utils/metrics.py:211-263.  'bce_dice' (:245-249, the DFC-SA configs) and 'dice' (:239-240) run on
     the fused kernel; note the reference reads loss_params['weight_bce'/'weight_dice'] while its YAMLs spell the keys

@@ -319,6 +319,16 @@ def bce_dice_finalize(sums, n, w_bce, w_dice, smooth, out):
                                             L.ptr(out), L.stream())
 
 
+def bce_dice_per_sample(x, t, from_logits, w_bce, w_dice, smooth, sums, out):
+    """x, t: [n, ...] contiguous fp32; sums: zeroed double [n, 8]; out: fp32 [n, 5] = (loss, bce, dice loss, hard IoU, hard Dice)
+    of every sample on its own (dfcsa_bce_dice_sums_batched + dfcsa_bce_dice_finalize_batched)."""
+    n = x.shape[0]
+    per = x.numel() // n
+    L.call("dfcsa_bce_dice_sums_batched", L.ptr(x), L.ptr(t), _i64(per), n, 1 if from_logits else 0, L.ptr(sums), L.stream())
+    L.call("dfcsa_bce_dice_finalize_batched", L.ptr(sums), _i64(per), n, C.c_float(w_bce), C.c_float(w_dice), C.c_float(smooth),
+           L.ptr(out), L.stream())
+
+
 def bce_dice_bwd(x, t, from_logits, sums, w_bce, w_dice, smooth, gout, dx):
     L.call("dfcsa_bce_dice_bwd", L.ptr(x), L.ptr(t), _i64(x.numel()), 1 if from_logits else 0, L.ptr(sums),
                                        C.c_float(w_bce), C.c_float(w_dice), C.c_float(smooth), L.ptr(gout), L.ptr(dx),

@@ -181,17 +181,54 @@ class Trainer:
 
     @torch.no_grad()
     def validate_epoch(self, dataloader):
-        """reference utils/trainer.py:172-265 reduced to the aggregate numbers (no per-sample CPU copies)."""
+        """reference utils/trainer.py:172-265: mean loss / IoU / Dice over the batches plus the K best and K worst samples
+        by Dice (K = logging.save_best_worst_samples).  The reference re-evaluates every sample separately and copies
+        image, mask and prediction of EVERY sample to the host each epoch; here the per-sample metrics are one batched
+        kernel pair, the candidates for best / worst stay in two device-side pools of at most 2K samples, nothing is
+        synchronised inside the loop, and only the 2K winners are copied out at the end."""
+        from .metrics import per_sample_metrics
         self.model.eval()
-        tot, nb = [0.0, 0.0, 0.0], 0
+        K = int(self.config.get("logging", {}).get("save_best_worst_samples", 0) or 0)
+        dev = self.device
+        tot = torch.zeros(3, dtype=torch.float64, device=dev)
+        nb, seen, names = 0, 0, []
+        pool = None                 # (ids, metrics [m, 5], images, masks, outputs)
         for batch in dataloader:
-            images = batch["image"].to(self.device)
-            masks = batch["mask"].to(self.device)
-            m = calculate_metrics(torch.sigmoid(self.model(images)), masks, self.loss_type, self.loss_params)
-            tot[0] += float(m["loss"]); tot[1] += m["iou"]; tot[2] += m["dice"]
+            images = batch["image"].to(dev, non_blocking=True)
+            masks = batch["mask"].to(dev, non_blocking=True)
+            outputs = torch.sigmoid(self.model(images))
+            sm = per_sample_metrics(outputs, masks, self.loss_type, self.loss_params)
+            bm = per_sample_metrics(outputs.reshape(1, -1), masks.reshape(1, -1), self.loss_type, self.loss_params)[0]
+            ok = ~torch.isnan(bm[0])                                   # a NaN batch is skipped (reference :210-212)
+            tot += torch.where(ok, bm[[0, 3, 4]].double(), torch.zeros(3, dtype=torch.float64, device=dev))
             nb += 1
-        nb = max(nb, 1)
-        return tot[0] / nb, tot[1] / nb, tot[2] / nb, {}
+            b = images.shape[0]
+            names += list(batch.get("filename", [str(seen + i) for i in range(b)]))
+            if K > 0:
+                ids = torch.arange(seen, seen + b, device=dev)
+                sm = torch.where(ok, sm, torch.full_like(sm, float("nan")))
+                cand = (ids, sm, images, masks.float(), outputs)
+                pool = cand if pool is None else tuple(torch.cat([p, c]) for p, c in zip(pool, cand))
+                if pool[0].numel() > 2 * K:
+                    d = pool[1][:, 4]
+                    worst = torch.topk(torch.nan_to_num(d, nan=float("inf")), K, largest=False).indices
+                    best = torch.topk(torch.nan_to_num(d, nan=float("-inf")), K, largest=True).indices
+                    keep = torch.unique(torch.cat([worst, best]))
+                    pool = tuple(p[keep] for p in pool)
+            seen += b
+        mean = (tot / max(nb, 1)).tolist()                             # the epoch's only synchronisation
+        res = {"loss": mean[0], "iou": mean[1], "dice": mean[2], "best_samples": [], "worst_samples": []}
+        if K > 0 and pool is not None:
+            ids, sm, imgs, msks, outs = (p.cpu() for p in pool)
+            valid = ~torch.isnan(sm[:, 4])
+            order = [i for i in torch.argsort(sm[:, 4], stable=True).tolist() if valid[i]]      # ascending Dice (:251)
+
+            def sample(i):
+                return {"sample_idx": int(ids[i]), "image": imgs[i], "mask": msks[i], "output": outs[i], "filename": names[int(ids[i])],
+                        "metrics": {"loss": float(sm[i, 0]), "iou": float(sm[i, 3]), "dice": float(sm[i, 4])}}
+            res["worst_samples"] = [sample(i) for i in order[:K]]
+            res["best_samples"] = [sample(i) for i in order[-K:]]
+        return res
 
     def save_checkpoint(self, epoch, metrics, is_best=False):
         """reference utils/trainer.py:267-298 (same dict keys / file names); rank 0 only under data parallel."""
@@ -218,16 +255,67 @@ class Trainer:
             setattr(self, k, ckpt[k])
         return ckpt["epoch"]
 
-    def train(self):
-        best = -1.0
-        for epoch in range(self.num_epochs):
+    def train(self, resume_from=None):
+        """reference utils/trainer.py:326-460.  resume_from: checkpoint path; training continues at the epoch after the
+        checkpoint's with the metric histories it stored (the reference indexes the integer load_checkpoint returns,
+        :337-339, and then clears the histories, :342-350, so its resume path cannot run - this is the evident intent)."""
+        start_epoch = 0
+        if resume_from:
+            start_epoch = self.load_checkpoint(resume_from) + 1
+            if self.rank == 0:
+                print(f"從 epoch {start_epoch} 恢復訓練")
+        self.epochs = list(range(1, len(self.train_losses) + 1))
+        best = max(self.val_dice_scores) if self.val_dice_scores else 0.0
+        for epoch in range(start_epoch, self.num_epochs):
             tl, ti, td = self.train_epoch(epoch)
+            self.epochs.append(epoch + 1)
             self.train_losses.append(tl); self.train_iou_scores.append(ti); self.train_dice_scores.append(td)
-            if self.val_loader is not None:
-                vl, vi, vd, metrics = self.validate_epoch(self.val_loader)
-                self.val_losses.append(vl); self.val_iou_scores.append(vi); self.val_dice_scores.append(vd)
-                is_best = vd > best
-                best = max(best, vd)
-                freq = self.config["training"].get("save_checkpoint_freq", 100)
-                if (epoch + 1) % freq == 0 or is_best:
-                    self.save_checkpoint(epoch, metrics, is_best)
+            if self.rank == 0:
+                print(f"Epoch [{epoch + 1}/{self.num_epochs}]")
+                print(f"  Train Loss: {tl:.4f}, Dice: {td:.4f}, IoU: {ti:.4f}")
+            if self.val_loader is None:
+                continue
+            val = self.validate_epoch(self.val_loader)
+            self.val_losses.append(val["loss"]); self.val_iou_scores.append(val["iou"]); self.val_dice_scores.append(val["dice"])
+            self.best_val_loss = min(self.best_val_loss, val["loss"])
+            is_best = val["dice"] > best
+            best = max(best, val["dice"])
+            if self.rank == 0:
+                print(f"  Val Loss: {val['loss']:.4f}, Dice: {val['dice']:.4f}, IoU: {val['iou']:.4f}")
+            freq = self.config["training"].get("save_checkpoint_freq", 100)
+            if (epoch + 1) % freq == 0 or is_best:
+                self.save_checkpoint(epoch, _slim_metrics(val), is_best)
+            if self.rank == 0 and (val["best_samples"] or val["worst_samples"]):
+                for kind in ("best_samples", "worst_samples"):
+                    save_prediction_samples(val[kind], os.path.join(self.log_dir, f"epoch_{epoch + 1}", kind))
+        if self.rank == 0:
+            total = time.time() - self.start_time
+            print(f"Training completed in {int(total // 3600)}h {int(total % 3600 // 60)}m {int(total % 60)}s")
+            print(f"Best validation dice: {best:.4f}")
+
+
+def _slim_metrics(val):
+    """What goes into a checkpoint's 'metrics' entry: the numbers and file names, not the image tensors the reference
+    pickles into every checkpoint (utils/trainer.py:287 stores validate_epoch's whole return value)."""
+    slim = {k: val[k] for k in ("loss", "iou", "dice")}
+    for kind in ("best_samples", "worst_samples"):
+        slim[kind] = [{"filename": s["filename"], "metrics": s["metrics"]} for s in val.get(kind, [])]
+    return slim
+
+
+def save_prediction_samples(samples, out_dir, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """One PNG per sample: de-normalised image | ground truth | prediction (reference utils/visualization.py via
+    utils/trainer.py:413-447).  Needs Pillow; silently skipped without it (logging only, not on the hot path)."""
+    try:
+        from PIL import Image
+    except ImportError:
+        return
+    os.makedirs(out_dir, exist_ok=True)
+    m, s = torch.tensor(mean).view(3, 1, 1), torch.tensor(std).view(3, 1, 1)
+    for smp in samples:
+        img = smp["image"].float()
+        img = (img[:3] * s + m).clamp(0, 1) if img.shape[0] >= 3 else img[:1].expand(3, -1, -1).clamp(0, 1)
+        panels = [img, smp["mask"].float().expand(3, -1, -1), smp["output"].float().expand(3, -1, -1)]
+        strip = (torch.cat(panels, dim=2) * 255).round().byte().permute(1, 2, 0).contiguous().numpy()
+        stem = os.path.splitext(os.path.basename(str(smp["filename"])))[0]
+        Image.fromarray(strip).save(os.path.join(out_dir, f"{stem}_dice{smp['metrics']['dice']:.3f}.png"))

@@ -325,6 +325,13 @@ int dfcsa_bce_dice_sums(const float* x, const float* t, int64_t n, int from_logi
 /* out[0]=loss, out[1]=bce, out[2]=dice_loss, out[3]=hard iou, out[4]=hard dice  (fp32, device) */
 int dfcsa_bce_dice_finalize(const double* sums, int64_t n, float w_bce, float w_dice, float smooth,
                             float* out, void* stream);
+/* The same per SAMPLE (validation: the reference re-runs calculate_metrics on every sample of every batch and copies each
+ * to the host, utils/trainer.py:229-245): x, t are [n_samples, n_per_sample]; sums double[n_samples][8] (zeroed by the
+ * caller); out fp32 [n_samples][5] as above. */
+int dfcsa_bce_dice_sums_batched(const float* x, const float* t, int64_t n_per_sample, int32_t n_samples, int from_logits,
+                                double* sums, void* stream);
+int dfcsa_bce_dice_finalize_batched(const double* sums, int64_t n_per_sample, int32_t n_samples, float w_bce, float w_dice,
+                                    float smooth, float* out, void* stream);
 /* dx = gout * dloss/dx  (wrt logits if from_logits else wrt probabilities); gout optional device scalar */
 int dfcsa_bce_dice_bwd(const float* x, const float* t, int64_t n, int from_logits, const double* sums,
                        float w_bce, float w_dice, float smooth, const float* gout,

@@ -296,3 +296,54 @@ def test_non_finite_batch_is_skipped_on_the_device(cuda):
     r = tr.train_step(img, mask).host()                                      # and the next good batch trains normally
     assert r["loss"] == r["loss"]
     assert any(not torch.equal(a, p.detach()) for a, p in zip(before, tr.model.parameters()))
+
+
+def test_validation_loop_per_sample_metrics_and_resume(cuda, tmp_path):
+    """Trainer.validate_epoch / train(resume_from): the epoch means and the best / worst samples by Dice equal what the
+    reference's loop computes (utils/trainer.py:172-265: calculate_metrics per batch and again per sample - evaluated
+    here with the CPU oracle on the same probabilities); checkpoints keep no image tensors; resume continues the
+    histories at the next epoch."""
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    from dfcsa.trainer import Trainer
+    torch.manual_seed(0)
+    model = UNetDFCSARes(3, 1, [8, 16, 32, 64], pool_size=4)
+    batches = []
+    for i, b in enumerate((3, 3, 2)):
+        img, mask = O.synthetic_batch(b, 32, 32, seed=40 + i)
+        batches.append({"image": img, "mask": mask, "filename": [f"v{i}_{j}.png" for j in range(b)]})
+    cfg = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 2, "save_checkpoint_freq": 1},
+           "logging": {"log_dir": str(tmp_path / "run"), "save_best_worst_samples": 2}}
+    tr = Trainer(model, batches[:2], batches, None, "cuda", cfg)
+    val = tr.validate_epoch(batches)
+    # reference semantics, evaluated on the CPU from the same probabilities
+    model.eval()
+    per, ref_batch = [], []
+    with torch.no_grad():
+        for bt in batches:
+            p = torch.sigmoid(model(bt["image"].cuda())).cpu()
+            m = O.calculate_metrics(p, bt["mask"], "bce_dice", {})
+            ref_batch.append((float(m["loss"]), m["iou"], m["dice"]))
+            for j in range(p.shape[0]):
+                mj = O.calculate_metrics(p[j:j + 1], bt["mask"][j:j + 1], "bce_dice", {})
+                per.append((bt["filename"][j], float(mj["loss"]), mj["iou"], mj["dice"]))
+    for k, idx in (("loss", 0), ("iou", 1), ("dice", 2)):
+        assert abs(val[k] - sum(r[idx] for r in ref_batch) / len(ref_batch)) < 1e-4, k
+    per.sort(key=lambda r: r[3])
+    assert [s["filename"] for s in val["worst_samples"]] == [r[0] for r in per[:2]]
+    assert [s["filename"] for s in val["best_samples"]] == [r[0] for r in per[-2:]]
+    for s, r in zip(val["worst_samples"] + val["best_samples"], per[:2] + per[-2:]):
+        assert abs(s["metrics"]["loss"] - r[1]) < 1e-4 and abs(s["metrics"]["dice"] - r[3]) < 1e-5 and abs(s["metrics"]["iou"] - r[2]) < 1e-5
+        assert s["image"].shape == (3, 32, 32) and not s["image"].is_cuda and s["output"].shape == (1, 32, 32)
+    # two epochs, a checkpoint per epoch; then resume from the first one
+    tr.train()
+    assert len(tr.train_losses) == 2 and len(tr.val_dice_scores) == 2 and tr.epochs == [1, 2]
+    ck = torch.load(str(tmp_path / "run" / "checkpoints" / "checkpoint_epoch_1.pth"), weights_only=False)
+    assert ck["epoch"] == 0 and set(ck["metrics"]) == {"loss", "iou", "dice", "best_samples", "worst_samples"}
+    assert all(set(s) == {"filename", "metrics"} for s in ck["metrics"]["best_samples"])           # no tensors pickled
+    assert (tmp_path / "run" / "epoch_1" / "best_samples").is_dir()
+    torch.manual_seed(0)
+    tr2 = Trainer(UNetDFCSARes(3, 1, [8, 16, 32, 64], pool_size=4), batches[:2], batches, None, "cuda", cfg)
+    tr2.train(resume_from=str(tmp_path / "run" / "checkpoints" / "checkpoint_epoch_1.pth"))
+    assert tr2.epochs == [1, 2] and tr2.train_losses[0] == ck["train_losses"][0] and len(tr2.train_losses) == 2
+    assert abs(tr2.train_losses[1] - tr.train_losses[1]) < 5e-3        # same state, same batches -> same second epoch

@@ -72,10 +72,7 @@ def main(config, resume_path=None, synthetic=0):
     optimizer = FusedSGD(model.parameters(), lr=float(tr_cfg.get("learning_rate", 0.01)), momentum=float(tr_cfg.get("momentum", 0.9)),
                          weight_decay=float(tr_cfg.get("weight_decay", 1e-4)))           # reference train.py:73-78
     trainer = Trainer(model=model, train_loader=train_loader, val_loader=val_loader, optimizer=optimizer, device=device, config=config)
-    if resume_path:
-        print(f"resuming from {resume_path}")
-        trainer.load_checkpoint(normalize_path(resume_path))
-    trainer.train()
+    trainer.train(resume_from=normalize_path(resume_path) if resume_path else None)
     if trainer.rank == 0 and trainer.train_losses:
         print(f"final train loss {trainer.train_losses[-1]:.4f}  dice {trainer.train_dice_scores[-1]:.4f}")
 
