@@ -22,7 +22,17 @@ template <int VEC, typename T> __device__ __forceinline__ void stv(T* p, const f
 }
 template <int VEC> __device__ __forceinline__ void ldf(const float* p, float (&v)[VEC]) {
   if constexpr (VEC == 8) load8<float>(p, v);
-  else v[0] = p[0];
+  else if constexpr (VEC == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else v[0] = p[0];
+}
+template <int VEC> __device__ __forceinline__ void stf(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = v[i];
+  }
 }
 
 static inline bool vec8_ok(int C, std::initializer_list<long long> lds, std::initializer_list<const void*> ptrs) {
@@ -250,22 +260,38 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
     for (int v = 0; v < VEC; ++v) o[v] = acc[v] * inv;
   }
 }
-// out[b, i, j, c] = scale_out * sum_y wgt(i, y) * tmp[b, y, j, c]; mode 0: pool windows over y, mode 1: bilinear^T
+// out[b, i, j, c] = scale_out * sum_y wgt(i, y) * tmp[b, y, j, c]; mode 0: pool windows over y, mode 1: bilinear^T.
+// V channels per thread (4 with 16-byte accesses when C % 4 == 0): at fine pooled grids (P = 16 / 32, where the pooled
+// map of the deep levels is larger than the feature map) this pass is instruction bound, not bandwidth bound, and the
+// index decode + tap weights are per thread, not per channel.
+template <int V>
 __global__ void __launch_bounds__(256)
-cols_reduce_kernel(const float* tmp, int B, int H, int P, int C, int mode, const float* mul, float* out,
-                   const float* dot_with, double* dot_out) {
-  const long long total = static_cast<long long>(B) * P * P * C;
+cols_reduce_kernel(const float* __restrict__ tmp, int B, int H, int P, int C, int mode, const float* mul, float* __restrict__ out,
+                   const float* __restrict__ dot_with, double* dot_out) {
+  const int CV = C / V;
+  const long long total = static_cast<long long>(B) * P * P * CV;
   const float m = mul ? *mul : 1.f;
   float dot = 0.f;
   for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
     int c, j, i; long long b;
-    decode4(idx, total < (1LL << 31), C, P, P, c, j, i, b);
-    float acc = 0.f;
+    decode4(idx, total < (1LL << 31), CV, P, P, c, j, i, b);
+    c *= V;
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    const float* col = tmp + (b * H * P + j) * C + c;          // + y * P * C
+    const long long ystride = static_cast<long long>(P) * C;
     if (mode == 0) {
       int lo, hi; pool_win(i, H, P, lo, hi);
-      for (int y = lo; y < hi; ++y) acc += tmp[((b * H + y) * P + j) * C + c];
-      acc /= static_cast<float>(hi - lo);
+      for (int y = lo; y < hi; ++y) {
+        float t[V]; ldf<V>(col + y * ystride, t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] += t[v];
+      }
+      const float den = static_cast<float>(hi - lo);
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[v] /= den;
     } else {
       const float ratio = static_cast<float>(H) / static_cast<float>(P);
       int lo = static_cast<int>(floorf((i - 0.5f) * ratio - 0.5f)) - 1;
@@ -276,11 +302,23 @@ cols_reduce_kernel(const float* tmp, int B, int H, int P, int C, int mode, const
         float wgt = 0.f;
         if (i0 == i) wgt += 1.f - l1;
         if (i1 == i) wgt += l1;
-        if (wgt != 0.f) acc += wgt * tmp[((b * H + y) * P + j) * C + c];
+        if (wgt != 0.f) {
+          float t[V]; ldf<V>(col + y * ystride, t);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] += wgt * t[v];
+        }
       }
     }
-    out[idx] = acc * m;
-    if (dot_with != nullptr) dot = fmaf(acc, dot_with[idx], dot);
+    const long long o = idx * V;
+    float r[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) r[v] = acc[v] * m;
+    stf<V>(out + o, r);
+    if (dot_with != nullptr) {
+      float w[V]; ldf<V>(dot_with + o, w);
+#pragma unroll
+      for (int v = 0; v < V; ++v) dot = fmaf(acc[v], w[v], dot);
+    }
   }
   if (dot_out != nullptr) block_scalar_reduce_add(dot, dot_out);   // <unscaled result, dot_with>
 }
@@ -1008,7 +1046,10 @@ extern "C" int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int3
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
   VEC_DISPATCH(v8, (pool_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(a0), ld, B, H, W, C, scale, shift, P, tmp)));
   DFCSA_LAUNCH_CHECK("pool_rows_kernel");
-  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0)
+    cols_reduce_kernel<4><<<ew_blocks(static_cast<long long>(B) * P * P * (C / 4)), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
+  else
+    cols_reduce_kernel<1><<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
   DFCSA_LAUNCH_CHECK("cols_reduce_kernel");
   return DFCSA_OK;
 }
@@ -1155,7 +1196,10 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
   VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));
   DFCSA_LAUNCH_CHECK("bilerpT_rows_kernel");
   // dgamma = sum dA*U = <bilinear_up^T(dA), o>: a dot product over the small pooled map instead of a gather per pixel
-  cols_reduce_kernel<<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
+    cols_reduce_kernel<4><<<ew_blocks(static_cast<long long>(B) * P * P * (C / 4)), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);
+  else
+    cols_reduce_kernel<1><<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);
   DFCSA_LAUNCH_CHECK("cols_reduce_kernel(bilerpT)");
   return DFCSA_OK;
 }
