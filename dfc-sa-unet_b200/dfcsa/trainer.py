@@ -41,34 +41,55 @@ def reduce_buckets(net):
 def device_feeder(batches, device):
     """Yields (images, masks) on the device with ONE batch of look-ahead: the host->device copy of batch i+1 runs on a
     copy stream while batch i trains (the reference copies synchronously inside the loop, utils/trainer.py:116-117).
-    `batches` yields (images, masks) host tensors (pinned memory makes the copies asynchronous)."""
+    `batches` yields (images, masks) host tensors (pinned memory makes the copies asynchronous); batches that already
+    live on the device (dfcsa.data_loader) pass straight through.
+
+    The copies land in two persistent staging buffers per shape, re-used alternately: allocating per batch on the copy
+    stream makes the caching allocator fall back to cudaMalloc (blocks freed across streams are not immediately
+    re-usable), which synchronises the device every step.  A buffer is overwritten only after an event recorded when the
+    consumer asks for the NEXT batch, i.e. after everything that reads it has been enqueued."""
     device = torch.device(device)
     copy_stream = torch.cuda.Stream(device=device)
+    slots = [None, None]          # [images, masks, consumed event or None]
 
-    def stage(pair):
+    def stage(pair, k):
+        if pair[0].is_cuda:
+            return pair[0], pair[1], None, None
+        slot = slots[k]
+        if slot is None or slot[0].shape != pair[0].shape or slot[0].dtype != pair[0].dtype or slot[1].shape != pair[1].shape \
+                or slot[1].dtype != pair[1].dtype:
+            slot = slots[k] = [torch.empty(pair[0].shape, dtype=pair[0].dtype, device=device),
+                               torch.empty(pair[1].shape, dtype=pair[1].dtype, device=device), None]
+            copy_stream.wait_stream(torch.cuda.current_stream(device))     # the fresh blocks may have had earlier users
         with torch.cuda.stream(copy_stream):
-            img = pair[0].to(device, non_blocking=True)
-            msk = pair[1].to(device, non_blocking=True)
+            if slot[2] is not None:
+                copy_stream.wait_event(slot[2])
+            slot[0].copy_(pair[0], non_blocking=True)
+            slot[1].copy_(pair[1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return img, msk, ev
+        return slot[0], slot[1], ev, slot
 
     it = iter(batches)
     try:
-        nxt = stage(next(it))
+        nxt = stage(next(it), 0)
     except StopIteration:
         return
+    k = 0
     while nxt is not None:
-        img, msk, ev = nxt
+        img, msk, ev, slot = nxt
         cur = torch.cuda.current_stream(device)
-        cur.wait_event(ev)
-        img.record_stream(cur)
-        msk.record_stream(cur)
+        if ev is not None:
+            cur.wait_event(ev)
+        k ^= 1
         try:
-            nxt = stage(next(it))
+            nxt = stage(next(it), k)
         except StopIteration:
             nxt = None
         yield img, msk
+        if slot is not None:                    # the consumer is back for more: its reads of this buffer are enqueued
+            slot[2] = torch.cuda.Event()
+            slot[2].record(torch.cuda.current_stream(device))
 
 
 class Trainer:
