@@ -368,6 +368,7 @@ def _attn_probs(qkv, nb, N, Cq, nq, out, lse=None, have_lse=False):
     ops.softmax_rows(S, out)
 
 
+_ATTN_FUSED = True       # forward attention without the N^2 round trip when the probabilities are not kept for backward
 _ATTN_SMALL_MAX_N = 32   # up to here the whole attention core is one fp32 kernel per direction (dfcsa_attn_small_*)
 _ATTN_TC_MIN_N = 64      # below this the attention products are a few KFLOP per image: fp32 FMA, no tensor cores
 
@@ -408,13 +409,20 @@ def attention_forward(bp, pk, pooled, B, N, ctx=None):
         return o
     # softmax(q k^T) v, a few images at a time when [N, N] is large (full-resolution attention: N = H*W)
     adt = F16 if tca else F32
-    keep_attn = ctx is not None and B * N * N * (2 if tca else 4) <= _ATTN_SAVE_BYTES
+    # exp + P V in one kernel whenever the shape allows: the probabilities are then never stored in the forward pass and the
+    # backward rebuilds them (straight to bf16, the type it needs) from the saved row log-sum-exp
+    fused = tca and C <= 128 and 8 <= Cq <= 64 and _ATTN_FUSED
+    keep_attn = ctx is not None and not fused and B * N * N * (2 if tca else 4) <= _ATTN_SAVE_BYTES
     attn = _e((B, N, N), adt, dev) if keep_attn else None
     o = _e((B, N, C), F32, dev)
     # probabilities not kept: the backward recomputes them from the row log-sum-exp saved here (one GEMM pass, not two)
-    lse = _e((BN,), F32, dev) if (tca and ctx is not None and not keep_attn) else None
+    lse = _e((BN,), F32, dev) if (tca and not keep_attn) else None
+    if fused:
+        # row statistics, then exp + P V in one kernel: the [N, N] probabilities never reach HBM in the forward pass
+        ops.attn_row_lse(B, N, Cq, qsrc, nq, lse)
+        ops.attn_pv_fused(qsrc, B, N, Cq, C, lse, o)
     ch = _attn_chunk(B, N)
-    for b0 in range(0, B, ch):
+    for b0 in range(0, 0 if fused else B, ch):
         nb = min(ch, B - b0)
         rows = slice(b0 * N, (b0 + nb) * N)
         A = attn[b0:b0 + nb] if keep_attn else _e((nb, N, N), adt, dev)

@@ -156,6 +156,21 @@ def softmax_bgemm(batch, M, N, K, A, a_b, ld_a, Bm, b_b, ld_b, out, lse=None, ha
     bgemm(batch, M, N, K, A, a_b, ld_a, False, Bm, b_b, ld_b, False, out, M * N, N, epi=2, rowvec=lse)
 
 
+def attn_row_lse(batch, N, Cq, qkv, ld, lse):
+    """lse[b*N + i] = log sum_j exp(q_i . k_j) for fp16 rows (q | k | v) of pitch ld: the statistics pass alone."""
+    parts = L.lib().dfcsa_bgemm_rowstat_parts(N)
+    rowstat = torch.empty((batch, parts, N, 2), dtype=torch.float32, device=qkv.device)
+    bgemm(batch, N, N, Cq, qkv[:, :Cq], N * ld, ld, False, qkv[:, Cq:2 * Cq], N * ld, ld, False, None, 0, 0, epi=1, rowstat=rowstat)
+    L.call("dfcsa_lse_combine", L.ptr(rowstat), parts, batch, N, L.ptr(lse), L.stream())
+
+
+def attn_pv_fused(qkv, batch, N, Cq, Cn, lse, o):
+    """o[b] = exp(q k^T - lse) v in ONE tcgen05 kernel, the probabilities never leave the SM (dfcsa_attn_pv_fused)."""
+    assert qkv.dtype == torch.float16 and qkv.stride(1) == 1 and o.is_contiguous() and o.dtype == torch.float32
+    L.call("dfcsa_attn_pv_fused", L.ptr(qkv), _i64(qkv.stride(0)), batch, N, Cq, Cn, L.ptr(lse), L.ptr(o), L.stream(),
+           tag="attn_pv_fused", flops=2.0 * batch * N * N * (Cq + Cn), desc=f"b={batch} N={N} Cq={Cq} C={Cn}")
+
+
 def softmax_bwd_bgemm(batch, M, N, K, dO, a_b, ld_a, V, b_b, ld_b, probs, D, dS):
     """dS[b] = probs[b] * (dO[b] @ V[b]^T - D[b][:, None]) (both operands K-major): the softmax backward fused into the
     epilogue of the dP product, D = rowdot(dO, O).  dS may be probs itself (same element size)."""

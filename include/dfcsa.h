@@ -190,6 +190,14 @@ int dfcsa_bgemm(const dfcsa_bgemm_params_t* p, void* stream);
 int dfcsa_bgemm_rowstat_parts(int32_t N);
 int dfcsa_lse_combine(const float* rowstat, int32_t parts, int32_t batch, int32_t M, float* lse, void* stream);
 
+/* Fused attention forward for large N:  o[b] = exp(q k^T - lse) v  with the [N, N] probabilities kept on chip (TMEM ->
+ * registers -> shared memory as the A operand of the second tcgen05 product) - reference models/unet_dfc_sa_res.py:30-33,
+ * models/unet_dfc_sa_ablation_attention.py:20-24.  qkv: fp16 rows (q[Cq] | k[Cq] | v[C]) with pitch ld, [batch*N] rows;
+ * lse: [batch*N] row log-sum-exp of q k^T (DFCSA_BGEMM_EPI_ROWSTATS pass + dfcsa_lse_combine); o: fp32 [batch, N, C].
+ * 8 <= Cq <= 64, C in {64, 128}. */
+int dfcsa_attn_pv_fused(const void* qkv, int64_t ld, int32_t batch, int32_t N, int32_t Cq, int32_t C, const float* lse,
+                        float* o, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * BatchNorm2d (reference :60,67,75,82; ATen batch_norm semantics: biased variance for normalisation, unbiased
  * for running_var, momentum 0.1, eps 1e-5).

@@ -330,6 +330,28 @@ def test_cast2d(cuda, xdt, ydt, M, C, pad):
     assert torch.equal(ys[:, :C], xs[:, :C].to(ydt)) and (ys[:, C:] == 0).all()
 
 
+@pytest.mark.parametrize("batch,N,Cq,C", [(1, 128, 8, 64), (2, 200, 8, 64), (1, 1048, 16, 128), (3, 64, 8, 64), (1, 3136, 8, 64),
+                                           (1, 12544, 16, 128)])
+def test_attn_pv_fused(cuda, batch, N, Cq, C):
+    """dfcsa_attn_pv_fused: softmax(q k^T) v with the probabilities kept on chip, against torch on the same fp16 operands
+    (ragged last tiles, several images, both channel widths)."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(37)
+    nq = 2 * Cq + C
+    qkv = torch.randn(batch * N, nq, generator=g).cuda()
+    qkv[:, :2 * Cq] *= 1.3
+    q16 = qkv.half()
+    q, k, v = (t.float().view(batch, N, -1) for t in (q16[:, :Cq], q16[:, Cq:2 * Cq], q16[:, 2 * Cq:]))
+    ref = torch.bmm(torch.softmax(torch.bmm(q, k.transpose(1, 2)), -1), v)
+    lse = torch.empty(batch * N, device=cuda)
+    ops.attn_row_lse(batch, N, Cq, q16, nq, lse)
+    assert torch.allclose(lse.view(batch, N), torch.logsumexp(torch.bmm(q, k.transpose(1, 2)), -1), atol=2e-3)
+    o = torch.full((batch, N, C), float("nan"), device=cuda)
+    ops.attn_pv_fused(q16, batch, N, Cq, C, lse, o)
+    torch.cuda.synchronize()
+    assert _rel_err(o, ref) < 3e-3
+
+
 @pytest.mark.parametrize("cols", [16, 100, 4096])
 def test_softmax_rows_16bit(cuda, cols):
     from dfcsa import ops

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """The five batched-GEMM launches of one full-resolution attention block (N = H*W keys, one image), timed with CUDA
-events: row statistics, exp, P V, P^T dO, softmax-backward dS, dS K, dS^T Q.  Run under ncu for the per-kernel picture.
+events: row statistics, exp, P V (separately and as the fused forward kernel), P^T dO, softmax-backward dS, dS K, dS^T Q.  Run under ncu for the per-kernel picture.
 
   python tools/attn_probe.py [--n 50176] [--c 64] [--cq 8] [--reps 3]
 """
@@ -43,6 +43,7 @@ def main():
         ("lse_combine", parts * N * 8.0, lambda: L.call("dfcsa_lse_combine", L.ptr(rowstat), parts, 1, N, L.ptr(lse), L.stream())),
         ("exp -> P fp16 (write N^2)", 2.0 * N * N, lambda: ops.bgemm(1, N, N, Cq, q, N * nq, nq, False, k, N * nq, nq, False, P, N * N, N, epi=2, rowvec=lse)),
         ("o = P v (read N^2, K-major A)", 2.0 * N * N, lambda: ops.bgemm(1, N, C, N, P, N * N, N, False, v, N * nq, nq, True, o, N * C, C)),
+        ("fused exp + P v (no N^2 traffic)", 0.0, lambda: ops.attn_pv_fused(qkv, 1, N, Cq, C, lse, o[0:1])),
         ("exp -> P bf16 (write N^2)", 2.0 * N * N, lambda: ops.bgemm(1, N, N, Cq, q, N * nq, nq, False, k, N * nq, nq, False, Pb, N * N, N, epi=2, rowvec=lse)),
         ("dv = P^T dO (read N^2, MN-major A)", 2.0 * N * N, lambda: ops.bgemm(1, N, C, N, Pb, N * N, N, True, do, N * C, C, True, dqkv[:, 2 * Cq:], N * nq, nq)),
         ("dS = P*(dO v^T - D) in place (r+w N^2)", 4.0 * N * N, lambda: ops.softmax_bwd_bgemm(1, N, N, C, do, N * C, C, vb, N * nq, nq, Pb, D, Pb)),
