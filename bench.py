@@ -43,8 +43,8 @@ def cpu_reference_step_time(steps, warmup, batch=4, threads=None):
     import torch
     from oracle import dfcsa_oracle as O
     O.USE_ATEN_OPS = True           # same ATen calls as the reference (batch_norm, adaptive_avg_pool2d, interpolate)
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(threads or os.cpu_count() or 1)
     torch.manual_seed(0)
     sd = O.init_state_dict(features=FEATURES, qk=QK, seed=0)
     for k in O.param_names(sd):
