@@ -73,7 +73,7 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 1 && lane == 0) {
     mbar_init(&q_full, 1); mbar_init(&q_empty, 1); mbar_init(&o_full, 1); mbar_init(&o_empty, 8);
     for (int i = 0; i < a.stages; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 8); mbar_init(&p_full[i], 8); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&tmem_base_smem, 512);
@@ -170,40 +170,47 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     }
   } else if (warp >= 4) {
     // ===================== softmax + epilogue =====================
+    // The two groups of four warps own one S / P buffer each and take alternate key tiles, so the two warps that share
+    // an SM sub-partition are out of phase: one's barrier / tcgen05.ld / fence latency overlaps the other's exp work.
     const int q4 = (warp - 4) & 3;        // TMEM lane quadrant = rows q4*32 .. +32 of the query tile
-    const int half = (warp - 4) >> 2;     // which 64 keys of the 128-key tile / which half of the C output columns
+    const int half = (warp - 4) >> 2;     // group: key tiles j = half (mod 2), buffer `half`; half of the C output columns
     const int row = q4 * 32 + lane;
     const uint32_t t_lane = static_cast<uint32_t>(q4 * 32) << 16;
-    uint32_t sph[2] = {0, 0}, pph[2] = {0, 0}, ophase = 0;
+    uint32_t sph = 0, pph = 0, ophase = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = static_cast<int>(tile % a.m_tiles);
       const long long b = tile / a.m_tiles;
       const int m = mt * 128 + row;
       const bool valid = m < a.N;
       const float lse2 = valid ? a.lse[b * a.N + m] * kLog2e : 0.f;
-      for (int j = 0; j < a.key_tiles; ++j) {
-        const int buf = j & 1;
-        mbar_wait(&s_full[buf], sph[buf]); sph[buf] ^= 1;
+      for (int j = half; j < a.key_tiles; j += 2) {
+        const int buf = half;
+        mbar_wait(&s_full[buf], sph); sph ^= 1;
         tc_fence_after();
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32(tmem_base + buf * 128 + half * 64 + t_lane, r0);
-        tmem_ld_32x32(tmem_base + buf * 128 + half * 64 + 32 + t_lane, r1);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[buf]);
-        uint32_t pk[32];
+        // 128 keys in four chunks of 32; the tcgen05.ld of chunk c+1 is in flight while chunk c is exponentiated
+        uint32_t ra[32], rb[32];
+        const uint32_t t_s = tmem_base + buf * 128 + t_lane;
+        auto chunk = [&](uint32_t (&r)[32], uint32_t (&nxt)[32], const int c) {
+          tmem_ld_wait();
+          if (c < 3) tmem_ld_32x32(t_s + (c + 1) * 32, nxt);
+          else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[buf]);
+          }
+          uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          pk[i] = pack_h2(ex2f(fmaf(__uint_as_float(r0[2 * i]), kLog2e, -lse2)), ex2f(fmaf(__uint_as_float(r0[2 * i + 1]), kLog2e, -lse2)));
-          pk[16 + i] = pack_h2(ex2f(fmaf(__uint_as_float(r1[2 * i]), kLog2e, -lse2)), ex2f(fmaf(__uint_as_float(r1[2 * i + 1]), kLog2e, -lse2)));
-        }
-        mbar_wait(&p_empty[buf], pph[buf] ^ 1); pph[buf] ^= 1;
-        // K block `half` of the P tile: row = query, 8 chunks of 8 keys, chunk c stored at position c ^ (row & 7)
-        uint8_t* prow = p_smem + buf * kPBytes + half * 16384 + row * 128;
+          for (int i = 0; i < 16; ++i)
+            pk[i] = pack_h2(ex2f(fmaf(__uint_as_float(r[2 * i]), kLog2e, -lse2)), ex2f(fmaf(__uint_as_float(r[2 * i + 1]), kLog2e, -lse2)));
+          if (c == 0) { mbar_wait(&p_empty[buf], pph ^ 1); pph ^= 1; }
+          // K block c/2 of the P tile: row = query, 8 chunks of 8 keys per 128-byte row, chunk x stored at x ^ (row & 7)
+          uint8_t* prow = p_smem + buf * kPBytes + (c >> 1) * 16384 + row * 128;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          for (int x = 0; x < 4; ++x)
+            *reinterpret_cast<uint4*>(prow + ((((c & 1) * 4 + x) ^ (row & 7)) << 4)) = make_uint4(pk[4 * x], pk[4 * x + 1], pk[4 * x + 2], pk[4 * x + 3]);
+        };
+        tmem_ld_32x32(t_s, ra);
+        chunk(ra, rb, 0); chunk(rb, ra, 1); chunk(ra, rb, 2); chunk(rb, ra, 3);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[buf]);

@@ -369,6 +369,7 @@ def _attn_probs(qkv, nb, N, Cq, nq, out, lse=None, have_lse=False):
 
 
 _ATTN_FUSED = True       # forward attention without the N^2 round trip when the probabilities are not kept for backward
+_ATTN_FUSED_BWD = True   # ... and the backward without any N^2 tensor (dfcsa_attn_bwd_fused)
 _ATTN_SMALL_MAX_N = 32   # up to here the whole attention core is one fp32 kernel per direction (dfcsa_attn_small_*)
 _ATTN_TC_MIN_N = 64      # below this the attention products are a few KFLOP per image: fp32 FMA, no tensor cores
 
@@ -457,7 +458,10 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
     small = N <= _ATTN_SMALL_MAX_N
     if small:
         ops.attn_small_bwd(qkv, attn, d_o, B, N, Cq, C, dqkv)
-    for b0 in range(0, 0 if small else B, ch):
+    fused = (not small) and tca and attn is None and ctx.lse is not None and C <= 128 and Cq <= 32 and _ATTN_FUSED_BWD
+    if fused:       # dq | dk | dv without a single [N, N] tensor in HBM: P and dS are rebuilt on chip, tile by tile
+        ops.attn_bwd_fused(ctx.qkv16, qkvb, dob, B, N, Cq, C, ctx.lse, Drow, dqkv)
+    for b0 in range(0, 0 if (small or fused) else B, ch):
         nb = min(ch, B - b0)
         rows = slice(b0 * N, (b0 + nb) * N)
         dq, dk, dv = dqkv[rows, :Cq], dqkv[rows, Cq:2 * Cq], dqkv[rows, 2 * Cq:]

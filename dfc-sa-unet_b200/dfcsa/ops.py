@@ -171,6 +171,15 @@ def attn_pv_fused(qkv, batch, N, Cq, Cn, lse, o):
            tag="attn_pv_fused", flops=2.0 * batch * N * N * (Cq + Cn), desc=f"b={batch} N={N} Cq={Cq} C={Cn}")
 
 
+def attn_bwd_fused(qkv16, qkvb, dO, batch, N, Cq, Cn, lse, D, dqkv):
+    """dq | dk | dv (fp32 rows of dqkv) from the fp16 forward operands, their bf16 copies, dO (bf16), the forward's row
+    log-sum-exp and D = rowdot(dO, O): two tcgen05 kernels, no [N, N] tensor in HBM (dfcsa_attn_bwd_fused)."""
+    assert qkv16.dtype == torch.float16 and qkvb.dtype == torch.bfloat16 and dO.dtype == torch.bfloat16 and dqkv.dtype == torch.float32
+    L.call("dfcsa_attn_bwd_fused", L.ptr(qkv16), _i64(qkv16.stride(0)), L.ptr(qkvb), _i64(qkvb.stride(0)), L.ptr(dO), _i64(dO.stride(0)),
+           batch, N, Cq, Cn, L.ptr(lse), L.ptr(D), L.ptr(dqkv), _i64(dqkv.stride(0)), L.stream(),
+           tag="attn_bwd_fused", flops=2.0 * batch * N * N * (3 * Cq + 2 * Cn + Cq + Cn), desc=f"b={batch} N={N} Cq={Cq} C={Cn}")
+
+
 def softmax_bwd_bgemm(batch, M, N, K, dO, a_b, ld_a, V, b_b, ld_b, probs, D, dS):
     """dS[b] = probs[b] * (dO[b] @ V[b]^T - D[b][:, None]) (both operands K-major): the softmax backward fused into the
     epilogue of the dP product, D = rowdot(dO, O).  dS may be probs itself (same element size)."""

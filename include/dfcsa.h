@@ -198,6 +198,15 @@ int dfcsa_lse_combine(const float* rowstat, int32_t parts, int32_t batch, int32_
 int dfcsa_attn_pv_fused(const void* qkv, int64_t ld, int32_t batch, int32_t N, int32_t Cq, int32_t C, const float* lse,
                         float* o, void* stream);
 
+/* Fused attention backward for large N (autograd of the same reference lines): with P = exp(q k^T - lse) and
+ * D = rowdot(dO, O):  dV = P^T dO,  dS = P o (dO V^T - D),  dQ = dS K,  dK = dS^T Q - two tcgen05 kernels (one per
+ * accumulation direction) that rebuild P and dS tile by tile on chip; no [N, N] tensor is read or written.
+ * qkv16: the forward's fp16 rows (q | k | v), pitch ld16; qkvb: the same rows in bf16, pitch ldb; dO: bf16 [batch*N, C],
+ * pitch ld_do; dqkv: fp32 rows (dq[Cq] | dk[Cq] | dv[C]) with pitch ld_out.  Cq in {8,...,32}, C in {64, 128}, N % 8 == 0. */
+int dfcsa_attn_bwd_fused(const void* qkv16, int64_t ld16, const void* qkvb, int64_t ldb, const void* dO, int64_t ld_do,
+                         int32_t batch, int32_t N, int32_t Cq, int32_t C, const float* lse, const float* D,
+                         float* dqkv, int64_t ld_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * BatchNorm2d (reference :60,67,75,82; ATen batch_norm semantics: biased variance for normalisation, unbiased
  * for running_var, momentum 0.1, eps 1e-5).

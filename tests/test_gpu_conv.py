@@ -352,6 +352,33 @@ def test_attn_pv_fused(cuda, batch, N, Cq, C):
     assert _rel_err(o, ref) < 3e-3
 
 
+@pytest.mark.parametrize("batch,N,Cq,C", [(1, 128, 8, 64), (2, 200, 8, 64), (1, 1048, 16, 128), (3, 64, 8, 64), (1, 3136, 8, 64),
+                                           (1, 6272, 16, 128)])
+def test_attn_bwd_fused(cuda, batch, N, Cq, C):
+    """dfcsa_attn_bwd_fused: dq / dk / dv of o = softmax(q k^T) v against torch autograd on the same fp16 operands
+    (ragged last tiles in both directions, several images, both channel widths)."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(41)
+    nq = 2 * Cq + C
+    qkv = torch.randn(batch * N, nq, generator=g).cuda()
+    qkv[:, :2 * Cq] *= 1.3
+    q16 = qkv.half()
+    x = q16.float().view(batch, N, nq).clone().requires_grad_(True)
+    q, k, v = x[..., :Cq], x[..., Cq:2 * Cq], x[..., 2 * Cq:]
+    S = torch.bmm(q, k.transpose(1, 2))
+    o = torch.bmm(torch.softmax(S, -1), v)
+    dO = (torch.randn(batch, N, C, generator=g) * 0.05).cuda().bfloat16()
+    o.backward(dO.float())
+    ref = x.grad.view(batch * N, nq)
+    lse = torch.logsumexp(S.detach(), -1).reshape(-1).contiguous()
+    D = (dO.float() * o.detach()).sum(-1).reshape(-1).contiguous()
+    dqkv = torch.full((batch * N, nq), float("nan"), device=cuda)
+    ops.attn_bwd_fused(q16, q16.bfloat16(), dO.view(batch * N, C), batch, N, Cq, C, lse, D, dqkv)
+    torch.cuda.synchronize()
+    for name, lo, hi in (("dq", 0, Cq), ("dk", Cq, 2 * Cq), ("dv", 2 * Cq, nq)):
+        assert _rel_err(dqkv[:, lo:hi], ref[:, lo:hi]) < 2e-2, name
+
+
 @pytest.mark.parametrize("cols", [16, 100, 4096])
 def test_softmax_rows_16bit(cuda, cols):
     from dfcsa import ops

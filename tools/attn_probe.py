@@ -46,6 +46,7 @@ def main():
         ("fused exp + P v (no N^2 traffic)", 0.0, lambda: ops.attn_pv_fused(qkv, 1, N, Cq, C, lse, o[0:1])),
         ("exp -> P bf16 (write N^2)", 2.0 * N * N, lambda: ops.bgemm(1, N, N, Cq, q, N * nq, nq, False, k, N * nq, nq, False, Pb, N * N, N, epi=2, rowvec=lse)),
         ("dv = P^T dO (read N^2, MN-major A)", 2.0 * N * N, lambda: ops.bgemm(1, N, C, N, Pb, N * N, N, True, do, N * C, C, True, dqkv[:, 2 * Cq:], N * nq, nq)),
+        ("fused backward dq | dk | dv (2 kernels)", 0.0, lambda: ops.attn_bwd_fused(qkv, qkvb, do, 1, N, Cq, C, lse, D, dqkv)),
         ("dS = P*(dO v^T - D) in place (r+w N^2)", 4.0 * N * N, lambda: ops.softmax_bwd_bgemm(1, N, N, C, do, N * C, C, vb, N * nq, nq, Pb, D, Pb)),
         ("dq = dS k (read N^2, K-major A)", 2.0 * N * N, lambda: ops.bgemm(1, N, Cq, N, Pb, N * N, N, False, kb, N * nq, nq, True, dqkv[:, :Cq], N * nq, nq)),
         ("dk = dS^T q (read N^2, MN-major A)", 2.0 * N * N, lambda: ops.bgemm(1, N, Cq, N, Pb, N * N, N, True, qb, N * nq, nq, True, dqkv[:, Cq:2 * Cq], N * nq, nq)),
