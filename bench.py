@@ -200,7 +200,7 @@ def run_dfcsa(args):
     _lib.PROF = None
     kern = prof.summary() if prof else {}
     if prof and args.detail:
-        det = prof.detail()
+        det = prof.detail(tags=("conv_tc", "wgrad_tc", "conv_simt", "wgrad_simt"))
         rows = sorted(({"shape": k, "ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                         "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} for k, v in det.items()), key=lambda r: -r["ms_per_step"])
         os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)

@@ -129,12 +129,20 @@ wgrad_small_kernel(const void* x, long long ld_x, long long M, int H, int W, con
     load_patch<TAPS, CI, TX>(x, ld_x, m0 + lane, M, H, W, s_patch[warp][lane]);
     __syncwarp();
     const int cnt = static_cast<int>(min(32LL, M - m0));
-    // four pixels per step: their wide-side loads are issued together (a dependent 500 ns load per pixel made this
-    // loop latency bound), and each pixel's patch comes from shared memory as LDS.128 broadcasts
+    // four pixels per step, and the wide-side loads of the NEXT step are issued before the FMAs of this one (a
+    // dependent ~500 ns load per step left this loop latency bound); each pixel's patch comes from shared memory as
+    // LDS.128 broadcasts
+    float2 dn[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) dn[u] = (u < cnt) ? ld2<TW>(wide, (m0 + u) * ld_w + n) : make_float2(0.f, 0.f);
     for (int p0 = 0; p0 < 32; p0 += 4) {
       float2 d[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) d[u] = (p0 + u < cnt) ? ld2<TW>(wide, (m0 + p0 + u) * ld_w + n) : make_float2(0.f, 0.f);
+      for (int u = 0; u < 4; ++u) d[u] = dn[u];
+      if (p0 + 4 < 32) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dn[u] = (p0 + 4 + u < cnt) ? ld2<TW>(wide, (m0 + p0 + 4 + u) * ld_w + n) : make_float2(0.f, 0.f);
+      }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float xr[KP];
@@ -165,42 +173,132 @@ wgrad_small_kernel(const void* x, long long ld_x, long long M, int H, int W, con
   }
 }
 
-// out[m, n] = sum_c x[m, c] * w[n, c] + bias[n], N <= 4, C % 64 == 0: 8 lanes per pixel, 16-byte loads
+// out[m, n] = sum_c x[m, c] * w[n, c] + bias[n], N <= 4, C % 64 == 0: 8 lanes per pixel, 16-byte loads, four pixels
+// (four independent loads) in flight per thread - one load per thread left the C = 64 final conv at 40 % of copy bandwidth
 template <typename TX>
 __global__ void __launch_bounds__(256)
 conv_smalln_kernel(const TX* x, long long ld_x, long long M, int C, const float* wgt, int N, float* out, long long ld_out,
                    const float* bias) {
+  constexpr int UNR = 4;
   extern __shared__ float s_w[];   // [N][C]
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) s_w[i] = wgt[i];
   __syncthreads();
-  const int sub = threadIdx.x & 7;
-  const long long pix_per_iter = static_cast<long long>(gridDim.x) * (blockDim.x / 8);
-  for (long long m = static_cast<long long>(blockIdx.x) * (blockDim.x / 8) + (threadIdx.x >> 3); m < (M + 3) / 4 * 4; m += pix_per_iter) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (m < M) {
-      for (int c0 = sub * 8; c0 < C; c0 += 64) {
-        float v[8];
-        load8<TX>(x + m * ld_x + c0, v);
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const long long stride = static_cast<long long>(gridDim.x) * 32;
+  for (long long mb = static_cast<long long>(blockIdx.x) * 32; mb < M; mb += stride * UNR) {
+    float acc[UNR][4];
 #pragma unroll
-        for (int nn = 0; nn < 4; ++nn) {
-          if (nn < N) {
+    for (int u = 0; u < UNR; ++u)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[nn] = fmaf(v[j], s_w[nn * C + c0 + j], acc[nn]);
-          }
+      for (int nn = 0; nn < 4; ++nn) acc[u][nn] = 0.f;
+    for (int c0 = sub * 8; c0 < C; c0 += 64) {
+      uint4 raw[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const long long m = mb + u * stride + pl;
+        raw[u] = m < M ? *reinterpret_cast<const uint4*>(x + m * ld_x + c0) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const TX* e = reinterpret_cast<const TX*>(&raw[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v = Cvt<TX>::to_f(e[j]);
+#pragma unroll
+          for (int nn = 0; nn < 4; ++nn)
+            if (nn < N) acc[u][nn] = fmaf(v, s_w[nn * C + c0 + j], acc[u][nn]);
         }
       }
     }
 #pragma unroll
-    for (int nn = 0; nn < 4; ++nn) {
-      acc[nn] += __shfl_xor_sync(0xffffffffu, acc[nn], 1);
-      acc[nn] += __shfl_xor_sync(0xffffffffu, acc[nn], 2);
-      acc[nn] += __shfl_xor_sync(0xffffffffu, acc[nn], 4);
-    }
-    if (m < M && sub < N) {
-      const float r = sub == 0 ? acc[0] : sub == 1 ? acc[1] : sub == 2 ? acc[2] : acc[3];
-      out[m * ld_out + sub] = r + (bias ? bias[sub] : 0.f);
+    for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+      for (int nn = 0; nn < 4; ++nn) {
+        acc[u][nn] += __shfl_xor_sync(0xffffffffu, acc[u][nn], 1);
+        acc[u][nn] += __shfl_xor_sync(0xffffffffu, acc[u][nn], 2);
+        acc[u][nn] += __shfl_xor_sync(0xffffffffu, acc[u][nn], 4);
+      }
+      const long long m = mb + u * stride + pl;
+      if (m < M && sub < N) {
+        const float r = sub == 0 ? acc[u][0] : sub == 1 ? acc[u][1] : sub == 2 ? acc[u][2] : acc[u][3];
+        out[m * ld_out + sub] = r + (bias ? bias[sub] : 0.f);
+      }
     }
   }
+}
+
+// dw[(n0 + c) * osw + k * osk] += alpha * sum_m wide[m, n0 + c] * narrow[m, k]   (1x1 taps, K <= 3 narrow channels)
+// The wide rows are read as 16-byte vectors: 8 lanes per pixel, 32 pixels per block and step, UNR steps in flight per
+// thread (64 bytes), so that a resident set of 4 blocks keeps ~64 KB per SM on the way - the 2-channel-per-lane kernel
+// above had 4 x 4 bytes per lane in flight and ran at a fifth of copy bandwidth on the first / last layer gradients.
+template <int K, typename TN, typename TW>
+__global__ void __launch_bounds__(256, K == 1 ? 4 : 3)
+wgrad_narrow_kernel(const TN* __restrict__ narrow, long long ld_n, long long M, const TW* __restrict__ wide, long long ld_w,
+                    float* dw, long long osw, long long osk, const float* alpha) {
+  constexpr int UNR = 4;
+  __shared__ float s_red[8][K][64];
+  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long n0 = static_cast<long long>(blockIdx.y) * 64;
+  const TW* wbase = wide + n0 + sub * 8;
+  float acc[K][8];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * 32;
+  for (long long mb = static_cast<long long>(blockIdx.x) * 32; mb < M; mb += stride * UNR) {
+    uint4 raw[UNR];
+    float nv[UNR][K];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long m = mb + u * stride + pl;
+      if (m < M) {
+        raw[u] = *reinterpret_cast<const uint4*>(wbase + m * ld_w);
+#pragma unroll
+        for (int k = 0; k < K; ++k) nv[u][k] = Cvt<TN>::to_f(narrow[m * ld_n + k]);
+      } else {
+        raw[u] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) nv[u][k] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const TW* e = reinterpret_cast<const TW*>(&raw[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float w = Cvt<TW>::to_f(e[j]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k][j] = fmaf(nv[u][k], w, acc[k][j]);
+      }
+    }
+  }
+  // the four pixel lanes of a warp, then the eight warps
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[k][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 8) s_red[warp][k][sub * 8 + j] = v;
+    }
+  __syncthreads();
+  const float al = alpha ? *alpha : 1.f;
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) {
+    const int k = i / 64, c = i % 64;
+    float v = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) v += s_red[w2][k][c];
+    atomicAdd(dw + (n0 + c) * osw + static_cast<long long>(k) * osk, al * v);
+  }
+}
+
+// one wave of `per_sm` resident 256-thread blocks per SM, split over the 64-channel groups of blockIdx.y
+int narrow_blocks(long long M, int groups_y, int per_sm) {
+  const long long want = std::max<long long>(1, static_cast<long long>(per_sm) * num_sms() / std::max(1, groups_y));
+  return static_cast<int>(std::max<long long>(1, std::min<long long>((M + 127) / 128, want)));
 }
 
 int small_blocks(long long M) {
@@ -220,7 +318,7 @@ int conv_gemm_small(const dfcsa_conv_params_t* p, cudaStream_t stream, int* rc_o
   if (sg.tap_mode == DFCSA_TAP_1x1 && p->N <= 4 && sg.channels % 64 == 0 && sg.channels <= 1024 && p->w_dtype == DFCSA_F32 &&
       p->out_dtype == DFCSA_F32 && p->src_dtype != DFCSA_F32 && p->stats == nullptr && sg.ld % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(sg.ptr) & 15) == 0) {
-    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((M + 31) / 32, 148LL * 8)));
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((M + 127) / 128, 8LL * num_sms())));
     const size_t smem = static_cast<size_t>(p->N) * sg.channels * sizeof(float);
     if (p->src_dtype == DFCSA_F16)
       conv_smalln_kernel<__half><<<blocks, 256, smem, stream>>>(reinterpret_cast<const __half*>(sg.ptr), sg.ld, M, sg.channels,
@@ -270,9 +368,14 @@ int conv_wgrad_small(const dfcsa_wgrad_params_t* p, cudaStream_t stream, int* rc
   if (p->C == 3 && p->x_dtype == DFCSA_F32 && p->dy_dtype == DFCSA_BF16 && p->N % 64 == 0 && p->ld_dy % 2 == 0 &&
       (reinterpret_cast<uintptr_t>(p->dy) & 3) == 0) {
     dim3 grid(small_blocks(M), p->N / 64);
+    const bool vec_dy = p->ld_dy % 8 == 0 && (reinterpret_cast<uintptr_t>(p->dy) & 15) == 0;
     if (p->x_tap_mode == DFCSA_TAP_3x3)
       wgrad_small_kernel<9, 3, float, __nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(p->x, p->ld_x, M, p->H, p->W, p->dy, p->ld_dy,
                                                                                        p->dw, p->ld_dw, 1, p->alpha);
+    else if (vec_dy)
+      wgrad_narrow_kernel<3, float, __nv_bfloat16><<<dim3(narrow_blocks(M, p->N / 64, 3), p->N / 64), 256, 0, stream>>>(
+          reinterpret_cast<const float*>(p->x), p->ld_x, M, reinterpret_cast<const __nv_bfloat16*>(p->dy), p->ld_dy, p->dw, p->ld_dw, 1,
+          p->alpha);
     else
       wgrad_small_kernel<1, 3, float, __nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(p->x, p->ld_x, M, p->H, p->W, p->dy, p->ld_dy,
                                                                                        p->dw, p->ld_dw, 1, p->alpha);
@@ -282,7 +385,16 @@ int conv_wgrad_small(const dfcsa_wgrad_params_t* p, cudaStream_t stream, int* rc
              p->C % 64 == 0 && p->ld_x % 2 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 3) == 0) {
     // narrow dy (1 channel), wide x: dw[0, c] = sum_m dy[m] * x[m, c]
     dim3 grid(small_blocks(M), p->C / 64);
-    if (p->x_dtype == DFCSA_BF16)
+    const bool vec_x = p->ld_x % 8 == 0 && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
+    const dim3 ngrid(narrow_blocks(M, p->C / 64, 4), p->C / 64);
+    const __nv_bfloat16* dy1 = reinterpret_cast<const __nv_bfloat16*>(p->dy);
+    if (vec_x && p->x_dtype == DFCSA_BF16)
+      wgrad_narrow_kernel<1, __nv_bfloat16, __nv_bfloat16><<<ngrid, 256, 0, stream>>>(
+          dy1, p->ld_dy, M, reinterpret_cast<const __nv_bfloat16*>(p->x), p->ld_x, p->dw, 1, 0, p->alpha);
+    else if (vec_x)
+      wgrad_narrow_kernel<1, __nv_bfloat16, __half><<<ngrid, 256, 0, stream>>>(
+          dy1, p->ld_dy, M, reinterpret_cast<const __half*>(p->x), p->ld_x, p->dw, 1, 0, p->alpha);
+    else if (p->x_dtype == DFCSA_BF16)
       wgrad_small_kernel<1, 1, __nv_bfloat16, __nv_bfloat16><<<grid, kWarps * 32, 0, stream>>>(p->dy, p->ld_dy, M, p->H, p->W, p->x,
                                                                                              p->ld_x, p->dw, 1, 0, p->alpha);
     else

@@ -375,11 +375,24 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.zero_fill = (a.box_bytes < kBoxBytes) ? 1 : 0;
   a.pix_blocks = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
 
+  // Pixel splits: the kernel needs a whole SM per CTA (shared memory + 512 TMEM columns), so a grid of 2*SMs + 1 CTAs
+  // costs three waves, not two (measured: 297 CTAs of the level-1 3x3 gradient kept every SM idle for a third of the
+  // launch).  Pick the split count whose grid fills 1..4 whole waves at the lowest cost
+  //   waves * (pixel blocks per CTA + fixed cost of a CTA: prologue, pipeline fill, atomic epilogue ~ 8 blocks).
   const long long items = static_cast<long long>(a.taps) * a.n_tiles * a.c_tiles;
-  long long splits = std::max<long long>(1, (2LL * num_sms() + items - 1) / items);
-  splits = std::min(splits, std::max<long long>(1, a.pix_blocks / 4));
-  a.blocks_per_split = (a.pix_blocks + splits - 1) / splits;
-  a.splits = static_cast<int>((a.pix_blocks + a.blocks_per_split - 1) / a.blocks_per_split);
+  const long long sms = num_sms();
+  static const int force_waves = [] { const char* e = getenv("DFCSA_WGRAD_WAVES"); return e ? atoi(e) : 0; }();
+  long long best_cost = -1;
+  for (int k = 1; k <= 4; ++k) {
+    if (force_waves > 0 && k != force_waves) continue;
+    long long s = std::max<long long>(1, k * sms / items);
+    s = std::min(s, std::max<long long>(1, a.pix_blocks / 4));
+    const long long bps = (a.pix_blocks + s - 1) / s;
+    s = (a.pix_blocks + bps - 1) / bps;
+    const long long waves = (items * s + sms - 1) / sms;
+    const long long cost = waves * (bps + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; a.blocks_per_split = bps; a.splits = static_cast<int>(s); }
+  }
   a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
   a.vec_red = ((reinterpret_cast<uintptr_t>(p->dw) & 15) == 0 && p->ld_dw % 4 == 0) ? 1 : 0;
   a.cvt_x = cvt_x ? 1 : 0;

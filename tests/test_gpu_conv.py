@@ -142,6 +142,9 @@ WG_CASES = [
     (1, 28, 28, 128, 64, 1, 0),
     (2, 6, 10, 128, 64, 0, 2),
     (1, 4, 4, 512, 128, 1, 0),
+    # enough pixel blocks for the wave-aware split selection to choose several CTAs per (tap row, tile)
+    (4, 64, 64, 128, 64, 1, 0),
+    (1, 96, 96, 192, 128, 0, 0),
 ]
 
 
@@ -202,6 +205,7 @@ SMALL_CASES = [
     (2, 7, 9, [64], "1", 1, {"out_dt": torch.float32, "bias": True}),
     (2, 7, 9, [128], "1", 2, {"out_dt": torch.float32, "bias": True, "src_dt": torch.bfloat16}),
     (2, 7, 9, [1], "1", 64, {"src_dt": torch.bfloat16, "out_dt": torch.bfloat16}),
+    (2, 40, 41, [64], "1", 1, {"out_dt": torch.float32, "bias": True}),      # several pixels in flight per thread, ragged tail
 ]
 
 
@@ -214,7 +218,9 @@ def test_conv_small_channel_kernels(cuda, case):
     assert serr < 2e-3, f"BN statistics rel err {serr}"
 
 
-@pytest.mark.parametrize("case", [(2, 9, 11, 3, 64, 1), (1, 20, 33, 3, 128, 0), (2, 7, 9, 64, 1, 0)], ids=["x3_3x3", "x3_1x1", "dy1"])
+@pytest.mark.parametrize("case", [(2, 9, 11, 3, 64, 1), (1, 20, 33, 3, 128, 0), (2, 7, 9, 64, 1, 0), (3, 50, 47, 3, 64, 1),
+                                  (4, 64, 61, 3, 64, 0), (2, 48, 50, 64, 1, 0), (1, 30, 31, 128, 1, 0)],
+                         ids=["x3_3x3", "x3_1x1", "dy1", "x3_3x3_big", "x3_1x1_big", "dy1_big", "dy1_c128"])
 def test_wgrad_small_channel_kernels(cuda, case):
     from dfcsa import ops
     dev = cuda
