@@ -51,6 +51,7 @@ struct ConvTcArgs {
   uint32_t idesc;
   __nv_bfloat16* shadow;
   long long ld_shadow;
+  int fixed_nt;     // gridDim.x is a multiple of n_tiles_n: a CTA sees ONE n tile for the whole kernel (nt == blockIdx.x % n_tiles_n)
   int wide_out, wide_shadow;   // 32-byte stores legal (16-bit tensor, pitch % 16 == 0, base 32-byte aligned, no accumulate)
 };
 
@@ -127,7 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_stats[4][2][256];   // [TMEM lane quarter][sum | sumsq][column]: one writer warp per entry
+  __shared__ __align__(16) float s_stats[4][2][256];   // [TMEM lane quarter][sum | sumsq][column]: one writer warp per entry
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,7 +139,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   // No zero fill of the stages: every B box is written in full by TMA (out-of-range rows arrive as zeros), and an
   // activation-tile row a partial box leaves unwritten is a pixel row of the MMA's M axis - it can only reach its own
   // output row, which the epilogue masks (valid == false) before anything is stored or summed.
-  for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) (&s_stats[0][0][0])[i] = 0.f;
+  // Without BatchNorm statistics the s_stats array is free: it holds the bias (indexed by GEMM column n; for a ConvT
+  // the bias repeats every convt_co columns) so the epilogue reads it as shared-memory broadcasts.
+  const bool bias_smem = a.bias != nullptr && a.stats == nullptr && a.N <= 4 * 2 * 256 && a.N % 32 == 0;
+  for (int i = threadIdx.x; i < 4 * 2 * 256; i += blockDim.x) {
+    float b = 0.f;
+    if (bias_smem && i < a.N) b = a.bias[a.out_mode == DFCSA_OUT_CONVT2x2 ? i % a.convt_co : i];
+    (&s_stats[0][0][0])[i] = b;
+  }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a0);
     if (a.n_seg > 1) tma_prefetch_desc(&map_a1);
@@ -307,7 +315,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int half = (warp - 4) >> 2;     // which half of the column chunks this warp takes
     const int r = ew * 32 + lane;         // tile row == TMEM lane
     const int et = threadIdx.x - 128;
-    const bool flush_each = a.n_tiles_n > 1;
+    const bool flush_each = a.n_tiles_n > 1 && !a.fixed_nt;
     // Narrow outputs (block_n <= 64, one n tile): every epilogue warp owns ONE fixed 32-column chunk for the whole
     // kernel, so the BatchNorm partial sums stay in registers across tiles and the 2 x 31-shuffle transpose runs once
     // per kernel instead of once per tile (these level-1 GEMMs are bound by the epilogue's instruction issue).
@@ -326,11 +334,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       long long row_off;
       if (a.out_mode == DFCSA_OUT_CONVT2x2) {
         // flattened input pixel m -> (b, i, j); quadrant added per chunk below
-        const long long m = (static_cast<long long>(tc.tb) * a.H + h) * a.W + w;
-        const int j = static_cast<int>(m % a.convt_w);
-        const long long t2 = m / a.convt_w;
-        const int i = static_cast<int>(t2 % a.convt_h);
-        const long long b = t2 / a.convt_h;
+        // (the host checks that the pixel count fits 31 bits: 32-bit divisions, ~10x cheaper than the 64-bit ones)
+        const unsigned m = (static_cast<unsigned>(tc.tb) * a.H + h) * a.W + w;
+        const unsigned j = m % static_cast<unsigned>(a.convt_w);
+        const unsigned t2 = m / static_cast<unsigned>(a.convt_w);
+        const unsigned i = t2 % static_cast<unsigned>(a.convt_h);
+        const long long b = t2 / static_cast<unsigned>(a.convt_h);
         row_off = ((b * 2 * a.convt_h + 2 * i) * (2LL * a.convt_w) + 2 * j);  // pixel index of quadrant (0,0)
       } else {
         row_off = (static_cast<long long>(tc.tb) * a.H + h) * a.W + w;
@@ -355,7 +364,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           cn = n0 - q * a.convt_co;
           pix += (q >> 1) * (2LL * a.convt_w) + (q & 1);
         }
-        if (a.bias != nullptr) {
+        if (bias_smem) {          // whole 32-column chunk, staged once per CTA: 8 LDS.128 broadcasts instead of 32 loads
+          const float4* bs = reinterpret_cast<const float4*>(&s_stats[0][0][0] + n0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 t = bs[i];
+            v[i * 4] += t.x; v[i * 4 + 1] += t.y; v[i * 4 + 2] += t.z; v[i * 4 + 3] += t.w;
+          }
+        } else if (a.bias != nullptr) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(a.bias + cn + i);
         }
@@ -423,11 +439,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   // final per-CTA flush of the BatchNorm partial sums (single n-tile case)
   tc_fence_before();
   __syncthreads();
-  if (a.stats != nullptr && a.n_tiles_n == 1 && blockIdx.x < total_tiles) {
+  if (a.stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && blockIdx.x < total_tiles) {
+    const int n_base = (blockIdx.x % a.n_tiles_n) * a.block_n;     // 0 for a single n tile
     for (int c = threadIdx.x; c < a.block_n; c += blockDim.x) {
-      if (c < a.N) {
-        atomicAdd(a.stats + c, static_cast<double>(s_stats[0][0][c] + s_stats[1][0][c] + s_stats[2][0][c] + s_stats[3][0][c]));
-        atomicAdd(a.stats + a.N + c, static_cast<double>(s_stats[0][1][c] + s_stats[1][1][c] + s_stats[2][1][c] + s_stats[3][1][c]));
+      const int n = n_base + c;
+      if (n < a.N) {
+        atomicAdd(a.stats + n, static_cast<double>(s_stats[0][0][c] + s_stats[1][0][c] + s_stats[2][0][c] + s_stats[3][0][c]));
+        atomicAdd(a.stats + a.N + n, static_cast<double>(s_stats[0][1][c] + s_stats[1][1][c] + s_stats[2][1][c] + s_stats[3][1][c]));
       }
     }
   }
@@ -513,6 +531,16 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   const long long m_tiles = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
 
   while (!a.dw3 && block_n > 64 && block_n % 64 == 0 && m_tiles * ((p->N + block_n - 1) / block_n) < sms) block_n /= 2;
+  // BatchNorm statistics on a short-K 1x1 GEMM: the kernel is bound by the epilogue's instruction issue (the shuffle
+  // transpose-reduce of the general path costs ~4x the store path), not by the tensor pipe.  Use 64-wide n tiles with
+  // a grid that is a multiple of the n-tile count, so every CTA keeps ONE n tile and the register-resident statistics
+  // variant applies; the n tiles of one pixel tile run side by side on neighbouring CTAs and share its A box through L2.
+  static const int fix_nt_max_kb = [] { const char* e = getenv("DFCSA_CONV_FIXNT_MAXKB"); return e ? atoi(e) : 2; }();
+  if (p->stats != nullptr && !any3 && !any2 && p->out_mode == DFCSA_OUT_DIRECT && p->N % 64 == 0 && p->N > 64 && p->N / 64 <= sms &&
+      a.total_kb <= fix_nt_max_kb) {
+    block_n = 64;
+    a.fixed_nt = 1;
+  }
   a.block_n = block_n;
   a.n_tiles_n = (p->N + block_n - 1) / block_n;
   if (a.dw3) {
@@ -580,8 +608,9 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   const long long total_tiles = m_tiles * a.n_tiles_n;
-  const int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
-  if (p->stats != nullptr && a.n_tiles_n == 1 && a.block_n <= 64)
+  int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
+  if (a.fixed_nt) grid = static_cast<int>(std::min<long long>(total_tiles, static_cast<long long>(sms / a.n_tiles_n) * a.n_tiles_n));
+  if (p->stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && a.block_n <= 64)
     conv_tc_kernel<true><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
   else
     conv_tc_kernel<false><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);

@@ -704,16 +704,26 @@ branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long lon
 }
 
 // bilinear^T along x: tmp[b, y, px, c] = sum_x wx(x, px) * dA[b, y, x, c]
+// `parts` lanes share one output: lane `part` takes every parts-th pixel of the ~2*W/P wide window with four
+// independent loads in flight, and the partial sums meet through shuffles (the lanes of one output are `group` = CV *
+// parts consecutive threads, a power of two <= 32).  One thread per output walked the 116-pixel window of level 1 with
+// a single dependent load in flight: 226 us for 411 MB (ncu), 0.28 of copy bandwidth.
 template <int VEC>
-__global__ void bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int C, int P, float* tmp) {
+__global__ void __launch_bounds__(256)
+bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int C, int P, float* tmp, int parts) {
   const int CV = C / VEC;
-  const long long total = static_cast<long long>(B) * H * P * CV;
+  const int group = CV * parts;
+  const long long total = static_cast<long long>(B) * H * P * group;
+  const bool small = total < (1LL << 31);
   const float ratio = static_cast<float>(W) / static_cast<float>(P);
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    int c, px, y; long long b;
-    decode4(i, total < (1LL << 31), CV, P, H, c, px, y, b);
-    c *= VEC;
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < total;
+       base += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const bool active = i < total;           // groups are aligned and total % group == 0: a group is active as a whole
+    int lg, px, y; long long b;
+    decode4(active ? i : total - 1, small, group, P, H, lg, px, y, b);
+    const int part = lg / CV;
+    const int c = (lg - part * CV) * VEC;
     int lo = static_cast<int>(floorf((px - 0.5f) * ratio - 0.5f)) - 1;
     int hi = static_cast<int>(ceilf((px + 1.5f) * ratio - 0.5f)) + 1;
     lo = max(lo, 0); hi = min(hi, W - 1);
@@ -721,21 +731,44 @@ __global__ void bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, in
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
     const grad_t* row = dz + ((b * H + y) * W) * ld_dz + 2 * C + c;
-    for (int x = lo; x <= hi; ++x) {
-      int x0, x1; float lx; bilerp_taps(x, P, W, x0, x1, lx);
-      float wgt = 0.f;
-      if (x0 == px) wgt += 1.f - lx;
-      if (x1 == px) wgt += lx;
-      if (wgt != 0.f) {
-        float d[VEC]; ldv<VEC>(row + x * ld_dz, d);
+    for (int x = lo + part; x <= hi; x += 4 * parts) {
+      float d[4][VEC], wg[4];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] += wgt * d[v];
+      for (int u = 0; u < 4; ++u) {
+        const int xx = x + u * parts;
+        const bool ok = xx <= hi;
+        const int xc = ok ? xx : hi;
+        int x0, x1; float lx; bilerp_taps(xc, P, W, x0, x1, lx);
+        float wgt = 0.f;
+        if (x0 == px) wgt += 1.f - lx;
+        if (x1 == px) wgt += lx;
+        wg[u] = ok ? wgt : 0.f;
+        ldv<VEC>(row + xc * ld_dz, d[u]);
       }
-    }
-    float* o = tmp + ((b * H + y) * P + px) * C + c;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) o[v] = acc[v];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] = fmaf(wg[u], d[u][v], acc[v]);
+    }
+    for (int off = CV; off < group; off <<= 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[v] += __shfl_xor_sync(0xffffffffu, acc[v], off);
+    }
+    if (active && part == 0) {
+      float* o = tmp + ((b * H + y) * P + px) * C + c;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) o[v] = acc[v];
+    }
   }
+}
+
+// lanes per output of bilerpT_rows_kernel: CV * parts must be a power of two <= 32, and a part should keep >= 8 pixels
+static int bilerpT_parts(int CV, int W, int P) {
+  if (CV <= 0 || (CV & (CV - 1)) != 0 || CV >= 32) return 1;
+  const int window = 2 * ((W + P - 1) / P) + 4;
+  int parts = 1;
+  while (parts * 2 * CV <= 32 && parts * 2 * 8 <= window) parts *= 2;
+  return parts;
 }
 
 // adaptive_avg_pool^T gather of dpooled at pixel (y, x)
@@ -816,9 +849,9 @@ branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long
                         long long ld_a0, int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
                         const float* invstd1, const double* red1, const float* s2, const float* t2, const float* mean2,
                         const float* invstd2, const double* red2, const float* dpooled, int P, grad_t* dl0,
-                        long long ld_dl0, grad_t* da0, long long ld_da0, int CL, int PL) {
+                        long long ld_dl0, grad_t* da0, long long ld_da0, int CL, int PL, int z_off) {
   extern __shared__ unsigned char s_dyn[];
-  const bool abranch = blockIdx.z == 1;
+  const bool abranch = blockIdx.z + z_off == 1;
   PoolTabs tabs{};
   if (abranch) tabs = build_pool_tabs(s_dyn, H, W, P);
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
@@ -1192,8 +1225,9 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
   OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
                                                                          shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
-  const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp)));
+  const int parts = bilerpT_parts(v8 ? C / 8 : C, W, P);
+  const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C) * parts;
+  VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts)));
   DFCSA_LAUNCH_CHECK("bilerpT_rows_kernel");
   // dgamma = sum dA*U = <bilinear_up^T(dA), o>: a dot product over the small pooled map instead of a gather per pixel
   if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
@@ -1231,10 +1265,22 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
                           {dz, l0, a0, dl0, da0, dpooled, scale1, shift1, mean1, invstd1, scale2, shift2, mean2, invstd2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31) && H < 32768 && W < 32768, "dfcsa_branch_bwd_apply: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks * 2, ew_occ(2)), g.chunks, 2);
+  // The L branch is a plain BatchNorm + ReLU backward: it runs on the light bn_bwd_apply_kernel (4 resident blocks per
+  // SM, 0.97 of copy bandwidth at level 1) instead of sharing the register budget of the pool^T gather of the A branch
+  // (2 resident blocks, 0.63); the coefficients and the arithmetic are the same, so the result is bit-identical.
+  static const bool split = [] { const char* e = getenv("DFCSA_SPLIT_APPLY"); return e ? atoi(e) != 0 : true; }();
+  const long long M = static_cast<long long>(B) * H * W;
+  if (split) {
+    dim3 gl(red_blocks(M, g.PL, g.chunks, 4), g.chunks);
+    VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<gl, 256, 0, ST>>>(G_(dz) + C, ld_dz, A_(l0), ld_l0, M, C, scale1, shift1, mean1, invstd1,
+                                                                   red1, 0, GM_(dl0), ld_dl0, g.CL, g.PL)));
+    DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  }
+  const int nz = split ? 1 : 2;
+  dim3 grid(red_blocks(M, g.PL, g.chunks * nz, ew_occ(2)), g.chunks, nz);
   OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC, OCC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
                                                                        shift1, mean1, invstd1, red1, scale2, shift2, mean2, invstd2,
-                                                                       red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL))));
+                                                                       red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL, split ? 1 : 0))));
   DFCSA_LAUNCH_CHECK("branch_bwd_apply_kernel");
   return DFCSA_OK;
 }

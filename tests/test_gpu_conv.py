@@ -88,6 +88,9 @@ CASES = [
     (3, 13, 21, [128], "3", 96, {"stats": True}),        # halo-box 3x3 path: ragged 8x16 patches, N not a power of two
     (2, 17, 9, [64, 64], "31", 128, {"stats": True}),    # 3x3 + 1x1 segments through the halo-box path, W < 16
     (1, 40, 24, [64], "3", 256, {"stats": True}),        # N = 256: the box-per-tap 3x3 path
+    (2, 40, 40, [64], "1", 256, {"stats": True}),        # short-K statistics GEMM: 64-wide n tiles, one n tile per CTA
+    (4, 64, 64, [128], "1", 128, {"stats": True}),       # same, more tiles than SMs (several pixel tiles per CTA)
+    (1, 24, 24, [128], "1", 192, {"bias": True}),        # bias staged in shared memory (no statistics)
 ]
 _MODE = {"1": 0, "3": 1, "2": 2}
 
@@ -467,3 +470,73 @@ def test_colsum(cuda, M, C, ld, dt):
     ops.colsum(x, out)
     torch.cuda.synchronize()
     assert _rel_err(out, x.float().sum(0) + 0.5) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,H,W,C,P", [(2, 56, 56, 64, 4), (1, 40, 36, 128, 4), (2, 32, 32, 64, 8), (1, 24, 24, 256, 16),
+                                       (1, 20, 28, 40, 4), (1, 7, 9, 64, 4), (1, 112, 112, 64, 4)])
+def test_branch_backward_passes_match_torch(cuda, B, H, W, C, P):
+    """branch_bwd_reduce1 (BN1 sums, bilinear^T of dA split over several lanes per output, d gamma) and branch_bwd_apply
+    (L branch on the plain BatchNorm-backward kernel, A branch with the pool^T gather) against autograd, tensor by tensor."""
+    from dfcsa import ops
+    dev = cuda
+    g = torch.Generator().manual_seed(11)
+    M = B * H * W
+    dz = torch.randn(M, 3 * C, generator=g).to(dev).bfloat16()
+    l0 = torch.randn(M, C, generator=g).to(dev).half()
+    a0 = torch.randn(M, C, generator=g).to(dev).half()
+    o = torch.randn(B, P, P, C, generator=g).to(dev)
+    dpooled = torch.randn(B, P, P, C, generator=g).to(dev)
+    gamma = torch.tensor([0.7], device=dev)
+
+    def bn(x):
+        mean = x.float().mean(0)
+        var = x.float().var(0, unbiased=False)
+        invstd = (var + 1e-5).rsqrt()
+        w = torch.rand(C, generator=g).to(dev) + 0.5
+        b = 0.3 * torch.randn(C, generator=g).to(dev)
+        return (w * invstd).contiguous(), (b - mean * w * invstd).contiguous(), mean.contiguous(), invstd.contiguous()
+
+    bn1, bn2 = bn(l0), bn(a0)
+    red = torch.zeros(4 * C + 2, device=dev, dtype=torch.float64)
+    red1, red2, dgam = red[:2 * C], red[2 * C:4 * C], red[4 * C + 1:4 * C + 2]
+    tmp = torch.empty(B, H, P, C, device=dev)
+    d_o = torch.empty(B * P * P, C, device=dev)
+    ops.branch_bwd_reduce1(dz, l0, None, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], None, None, o, P, gamma, red1, dgam, tmp, d_o)
+    ops.branch_bwd_reduce2(dz, a0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
+    dl0 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    da0 = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+    ops.branch_bwd_apply(dz, l0, a0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dl0, da0)
+    torch.cuda.synchronize()
+
+    # ---- reference (fp32 autograd) ----
+    dL = dz[:, C:2 * C].float()
+    dA = dz[:, 2 * C:].float()
+    o_n = o.permute(0, 3, 1, 2).clone().requires_grad_(True)
+    U = F.interpolate(o_n, size=(H, W), mode="bilinear", align_corners=False)
+    dA_n = dA.view(B, H, W, C).permute(0, 3, 1, 2)
+    s = (U * dA_n).sum()
+    s.backward()
+    d_o_ref = (0.7 * o_n.grad).permute(0, 2, 3, 1).reshape(B * P * P, C)
+    assert _rel_err(d_o, d_o_ref) < 1e-4
+    assert abs(float(dgam) - float(s)) <= 1e-4 * float((U * dA_n).abs().sum()) + 1e-3
+
+    def bn_bwd(d, x, bnp):
+        sc, sh, mean, invstd = bnp
+        xf = x.float()
+        dm = torch.where(xf * sc + sh > 0, d, torch.zeros_like(d))
+        xhat = (xf - mean) * invstd
+        k1 = dm.mean(0)
+        k2 = (dm * xhat).mean(0)
+        return sc * (dm - k1 - xhat * k2), dm.sum(0), (dm * xhat).sum(0)
+
+    dl0_ref, s1a, s1b = bn_bwd(dL, l0, bn1)
+    assert _rel_err(red1[:C].float(), s1a) < 1e-3 and _rel_err(red1[C:].float(), s1b) < 1e-3
+    assert _rel_err(dl0, dl0_ref) < 6e-3
+    dp_n = dpooled.permute(0, 3, 1, 2).clone()
+    x_n = torch.zeros(B, C, H, W, device=dev, requires_grad=True)
+    (F.adaptive_avg_pool2d(x_n, P) * dp_n).sum().backward()
+    dA_tot = dA + x_n.grad.permute(0, 2, 3, 1).reshape(M, C)
+    da0_ref, s2a, s2b = bn_bwd(dA_tot, a0, bn2)
+    assert _rel_err(red2[:C].float(), s2a) < 1e-3 and _rel_err(red2[C:].float(), s2b) < 1e-3
+    assert _rel_err(da0, da0_ref) < 6e-3
