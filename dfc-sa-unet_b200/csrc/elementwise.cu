@@ -20,6 +20,22 @@ template <int VEC, typename T> __device__ __forceinline__ void stv(T* p, const f
   if constexpr (VEC == 8) store8<T>(p, v);
   else p[0] = Cvt<T>::from_f(v[0]);
 }
+// raw 16-bit channel vectors: several loads in flight cost 4 registers each until they are converted at their use
+template <int VEC, typename T> struct RawV { uint4 r; };
+template <typename T> struct RawV<1, T> { T r; };
+template <int VEC, typename T> __device__ __forceinline__ RawV<VEC, T> ldraw(const T* p) {
+  RawV<VEC, T> w;
+  if constexpr (VEC == 8) w.r = *reinterpret_cast<const uint4*>(p);
+  else w.r = p[0];
+  return w;
+}
+template <int VEC, typename T> __device__ __forceinline__ void cvtraw(const RawV<VEC, T>& w, float (&v)[VEC]) {
+  if constexpr (VEC == 8) {
+    const T* e = reinterpret_cast<const T*>(&w.r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = Cvt<T>::to_f(e[i]);
+  } else v[0] = Cvt<T>::to_f(w.r);
+}
 template <int VEC> __device__ __forceinline__ void ldf(const float* p, float (&v)[VEC]) {
   if constexpr (VEC == 8) load8<float>(p, v);
   else if constexpr (VEC == 4) {
@@ -343,9 +359,10 @@ __device__ __forceinline__ void bilerp_gather(const float* o, long long b, int y
 
 template <int VEC, int OCC>
 __global__ void __launch_bounds__(256, OCC)
-branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long long ld_a0, int B, int H, int W, int C,
-                      const float* s1, const float* t1, const float* s2, const float* t2, const float* o, int P,
-                      const float* gamma, act_t* z, long long ld_z, grad_t* zb, long long ld_zb, int CL, int PL) {
+branch_act_fwd_kernel(const act_t* __restrict__ l0, long long ld_l0, const act_t* __restrict__ a0, long long ld_a0, int B, int H,
+                      int W, int C, const float* s1, const float* t1, const float* s2, const float* t2, const float* o, int P,
+                      const float* gamma, act_t* __restrict__ z, long long ld_z, grad_t* __restrict__ zb, long long ld_zb, int CL,
+                      int PL) {
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c = (blockIdx.y * CL + cl) * VEC;
   if (pl >= PL || c >= C) return;
@@ -353,22 +370,44 @@ branch_act_fwd_kernel(const act_t* l0, long long ld_l0, const act_t* a0, long lo
   const float gm = *gamma;
   float sc1[VEC], sh1[VEC], sc2[VEC], sh2[VEC];
   ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2);
-  PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, H, W);
-  for (unsigned m = blockIdx.x * PL + pl; m < M; m += gridDim.x * PL, it.next(H, W)) {
-    const unsigned x = it.x, y = it.y, b = it.b;
-    float v0[VEC], outv[VEC];
-    ldv<VEC>(l0 + static_cast<long long>(m) * ld_l0 + c, v0);
+  // kActPix pixels per iteration with all their loads issued before the first store: one pixel at a time (L0, store,
+  // then A0 - the store to z kept the second load from moving up) left 16 bytes in flight per thread, ~12 KB per SM,
+  // and the kernel at 0.61 of copy bandwidth.  The raw vectors cost 8 registers per pixel, so the kernel is built for
+  // two resident blocks per SM (118 registers): 512 threads x 96 bytes = 48 KB on the way per SM.
+  constexpr int kActPix = 3;
+  const unsigned start = blockIdx.x * PL + pl, stride = gridDim.x * PL;
+  PixIter it[kActPix];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) outv[v] = fmax_nan(fmaf(v0[v], sc1[v], sh1[v]), 0.f);
-    stv<VEC>(z + static_cast<long long>(m) * ld_z + C + c, outv);
-    if (zb != nullptr) stv<VEC>(zb + static_cast<long long>(m) * ld_zb + C + c, outv);
-    float u[VEC];
-    bilerp_gather<VEC>(o, b, y, x, H, W, P, C, c, u);
-    ldv<VEC>(a0 + static_cast<long long>(m) * ld_a0 + c, v0);
+  for (int u = 0; u < kActPix; ++u) it[u].init((start + u * stride) % M, kActPix * stride, H, W);
+  for (unsigned m32 = start; m32 < M; m32 += kActPix * stride) {
+    RawV<VEC, act_t> lraw[kActPix], araw[kActPix];
+    bool ok[kActPix];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) outv[v] = gm * u[v] + fmax_nan(fmaf(v0[v], sc2[v], sh2[v]), 0.f);
-    stv<VEC>(z + static_cast<long long>(m) * ld_z + 2 * C + c, outv);
-    if (zb != nullptr) stv<VEC>(zb + static_cast<long long>(m) * ld_zb + 2 * C + c, outv);
+    for (int u = 0; u < kActPix; ++u) {
+      const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
+      ok[u] = m < M;
+      if (ok[u]) { lraw[u] = ldraw<VEC>(l0 + m * ld_l0 + c); araw[u] = ldraw<VEC>(a0 + m * ld_a0 + c); }
+    }
+#pragma unroll
+    for (int u = 0; u < kActPix; ++u) {
+      if (ok[u]) {
+        const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
+        float outv[VEC], xin[VEC];
+        cvtraw<VEC>(lraw[u], xin);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) outv[v] = fmax_nan(fmaf(xin[v], sc1[v], sh1[v]), 0.f);
+        stv<VEC>(z + m * ld_z + C + c, outv);
+        if (zb != nullptr) stv<VEC>(zb + m * ld_zb + C + c, outv);
+        float up[VEC];
+        bilerp_gather<VEC>(o, it[u].b, it[u].y, it[u].x, H, W, P, C, c, up);
+        cvtraw<VEC>(araw[u], xin);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) outv[v] = gm * up[v] + fmax_nan(fmaf(xin[v], sc2[v], sh2[v]), 0.f);
+        stv<VEC>(z + m * ld_z + 2 * C + c, outv);
+        if (zb != nullptr) stv<VEC>(zb + m * ld_zb + 2 * C + c, outv);
+      }
+      it[u].next(H, W);
+    }
   }
 }
 
@@ -771,6 +810,8 @@ static int bilerpT_parts(int CV, int W, int P) {
   return parts;
 }
 
+constexpr int kPixInFlight = 4;   // pixels per grid-stride step in the A-branch backward kernels
+
 // adaptive_avg_pool^T gather of dpooled at pixel (y, x)
 template <int VEC>
 __device__ __forceinline__ void poolT_gather(const float* dp, unsigned b, int y, int x, int P, int C, int c,
@@ -809,99 +850,90 @@ branch_bwd_reduce2_kernel(const grad_t* dz, long long ld_dz, const act_t* a0, lo
   if (pl < PL && c < C) {
     float sc[VEC], sh[VEC];
     ldf<VEC>(s2 + c, sc); ldf<VEC>(t2 + c, sh);
-    // two pixels per iteration: with 2 loads per pixel and 512 resident threads per SM a single pixel in flight per
-    // thread leaves only ~16 KB outstanding per SM, far below the ~45 KB the HBM latency-bandwidth product needs
-    const unsigned stride = gridDim.x * PL;
-    PixIter it0, it1;
-    it0.init(blockIdx.x * PL + pl, 2 * stride, H, W);
-    it1.init((blockIdx.x * PL + pl + stride) % M, 2 * stride, H, W);
-    for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += 2 * stride, it0.next(H, W), it1.next(H, W)) {
-      const long long m = m32, m1 = static_cast<long long>(m32) + stride;
-      const bool two = m1 < M;
-      float da[VEC], av[VEC], gp[VEC], da1[VEC], av1[VEC], gp1[VEC];
-      ldv<VEC>(dz + m * ld_dz + 2 * C + c, da); ldv<VEC>(a0 + m * ld_a0 + c, av);
-      if (two) { ldv<VEC>(dz + m1 * ld_dz + 2 * C + c, da1); ldv<VEC>(a0 + m1 * ld_a0 + c, av1); }
-      poolT_gather<VEC>(dpooled, it0.b, it0.y, it0.x, P, C, c, tabs, gp);
+    // kPixInFlight pixels per iteration, every load issued before the first use: with 2 loads per pixel and 512 resident
+    // threads per SM one pixel in flight leaves ~16 KB outstanding per SM, two 32 KB - the HBM latency-bandwidth
+    // product needs ~45 KB (two pixels: 0.46 of copy bandwidth at level 1, ncu)
+    const unsigned start = blockIdx.x * PL + pl, stride = gridDim.x * PL;
+    PixIter it[kPixInFlight];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float d2 = fmaf(av[v], sc[v], sh[v]) > 0.f ? da[v] + gp[v] : 0.f;
-        acc[0][v] += d2;
-        acc[1][v] = fmaf(d2, av[v], acc[1][v]);
+    for (int u = 0; u < kPixInFlight; ++u) it[u].init((start + u * stride) % M, kPixInFlight * stride, H, W);
+    for (unsigned m32 = start; m32 < M; m32 += kPixInFlight * stride) {
+      RawV<VEC, grad_t> draw[kPixInFlight];
+      RawV<VEC, act_t> araw[kPixInFlight];
+      bool ok[kPixInFlight];
+#pragma unroll
+      for (int u = 0; u < kPixInFlight; ++u) {
+        const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
+        ok[u] = m < M;
+        if (ok[u]) { draw[u] = ldraw<VEC>(dz + m * ld_dz + 2 * C + c); araw[u] = ldraw<VEC>(a0 + m * ld_a0 + c); }
       }
-      if (two) {
-        poolT_gather<VEC>(dpooled, it1.b, it1.y, it1.x, P, C, c, tabs, gp1);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const float d2 = fmaf(av1[v], sc[v], sh[v]) > 0.f ? da1[v] + gp1[v] : 0.f;
-          acc[0][v] += d2;
-          acc[1][v] = fmaf(d2, av1[v], acc[1][v]);
+      for (int u = 0; u < kPixInFlight; ++u) {
+        if (ok[u]) {
+          float gp[VEC], da[VEC], av[VEC];
+          poolT_gather<VEC>(dpooled, it[u].b, it[u].y, it[u].x, P, C, c, tabs, gp);
+          cvtraw<VEC>(draw[u], da); cvtraw<VEC>(araw[u], av);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float d2 = fmaf(av[v], sc[v], sh[v]) > 0.f ? da[v] + gp[v] : 0.f;
+            acc[0][v] += d2;
+            acc[1][v] = fmaf(d2, av[v], acc[1][v]);
+          }
         }
+        it[u].next(H, W);
       }
     }
   }
   flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean2, invstd2, red2, s_red);
 }
 
-// pass 3: blockIdx.z = 0 -> dL0 from (dL, L0, BN1);  blockIdx.z = 1 -> dA0 from (dA + pool^T(dpooled), A0, BN2)
+// pass 3, A branch: dA0 from (dA + pool^T(dpooled), A0, BN2).  (The L branch, dL0 from (dL, L0, BN1), is a plain BatchNorm
+// + ReLU backward and runs on bn_bwd_apply_kernel.)
 template <int VEC, int OCC>
 __global__ void __launch_bounds__(256, OCC)
-branch_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* a0,
-                        long long ld_a0, int B, int H, int W, int C, const float* s1, const float* t1, const float* mean1,
-                        const float* invstd1, const double* red1, const float* s2, const float* t2, const float* mean2,
-                        const float* invstd2, const double* red2, const float* dpooled, int P, grad_t* dl0,
-                        long long ld_dl0, grad_t* da0, long long ld_da0, int CL, int PL, int z_off) {
+branch_bwd_apply_kernel(const grad_t* __restrict__ dz, long long ld_dz, const act_t* __restrict__ a0, long long ld_a0, int B, int H,
+                        int W, int C, const float* s2, const float* t2, const float* mean2, const float* invstd2,
+                        const double* red2, const float* dpooled, int P, grad_t* __restrict__ da0, long long ld_da0, int CL,
+                        int PL) {
   extern __shared__ unsigned char s_dyn[];
-  const bool abranch = blockIdx.z + z_off == 1;
-  PoolTabs tabs{};
-  if (abranch) tabs = build_pool_tabs(s_dyn, H, W, P);
+  const PoolTabs tabs = build_pool_tabs(s_dyn, H, W, P);
   const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
   const int c = (blockIdx.y * CL + cl) * VEC;
   if (pl >= PL || c >= C) return;
   const unsigned M = static_cast<unsigned>(B) * H * W;
-  const double invn = 1.0 / static_cast<double>(M);
   float sc[VEC], sh[VEC], p[VEC], q[VEC];
-  if (abranch) { bn_bwd_coeffs<VEC>(s2, mean2, invstd2, red2, C, c, invn, sc, p, q); ldf<VEC>(t2 + c, sh); }
-  else         { bn_bwd_coeffs<VEC>(s1, mean1, invstd1, red1, C, c, invn, sc, p, q); ldf<VEC>(t1 + c, sh); }
-  const grad_t* dsrc = dz + (abranch ? 2 * C : C) + c;
-  const act_t* xsrc = abranch ? a0 + c : l0 + c;
-  const long long ld_xs = abranch ? ld_a0 : ld_l0;
-  grad_t* dst = abranch ? da0 + c : dl0 + c;
-  const long long ld_dst = abranch ? ld_da0 : ld_dl0;
-  const unsigned stride = gridDim.x * PL;          // two pixels per iteration (see branch_bwd_reduce2_kernel)
-  PixIter it0, it1;
-  it0.init(blockIdx.x * PL + pl, 2 * stride, H, W);
-  it1.init((blockIdx.x * PL + pl + stride) % M, 2 * stride, H, W);
-  for (unsigned m32 = blockIdx.x * PL + pl; m32 < M; m32 += 2 * stride, it0.next(H, W), it1.next(H, W)) {
-    const long long m = m32, m1 = static_cast<long long>(m32) + stride;
-    const bool two = m1 < M;
-    float d[VEC], xv[VEC], o[VEC], d1[VEC], xv1[VEC];
-    ldv<VEC>(dsrc + m * ld_dz, d); ldv<VEC>(xsrc + m * ld_xs, xv);
-    if (two) { ldv<VEC>(dsrc + m1 * ld_dz, d1); ldv<VEC>(xsrc + m1 * ld_xs, xv1); }
-    if (abranch) {
-      float gp[VEC];
-      poolT_gather<VEC>(dpooled, it0.b, it0.y, it0.x, P, C, c, tabs, gp);
+  bn_bwd_coeffs<VEC>(s2, mean2, invstd2, red2, C, c, 1.0 / static_cast<double>(M), sc, p, q);
+  ldf<VEC>(t2 + c, sh);
+  const grad_t* dsrc = dz + 2 * C + c;
+  const unsigned start = blockIdx.x * PL + pl, stride = gridDim.x * PL;   // kPixInFlight pixels per iteration (see reduce2)
+  PixIter it[kPixInFlight];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) d[v] += gp[v];
+  for (int u = 0; u < kPixInFlight; ++u) it[u].init((start + u * stride) % M, kPixInFlight * stride, H, W);
+  for (unsigned m32 = start; m32 < M; m32 += kPixInFlight * stride) {
+    RawV<VEC, grad_t> draw[kPixInFlight];
+    RawV<VEC, act_t> xraw[kPixInFlight];
+    bool ok[kPixInFlight];
+#pragma unroll
+    for (int u = 0; u < kPixInFlight; ++u) {
+      const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
+      ok[u] = m < M;
+      if (ok[u]) { draw[u] = ldraw<VEC>(dsrc + m * ld_dz); xraw[u] = ldraw<VEC>(a0 + m * ld_a0 + c); }
     }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
-      o[v] = fmaf(sc[v], dd, fmaf(p[v], xv[v], q[v]));
-    }
-    stv<VEC>(dst + m * ld_dst, o);
-    if (two) {
-      if (abranch) {
-        float gp[VEC];
-        poolT_gather<VEC>(dpooled, it1.b, it1.y, it1.x, P, C, c, tabs, gp);
+    for (int u = 0; u < kPixInFlight; ++u) {
+      if (ok[u]) {
+        const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
+        float gp[VEC], o[VEC], d[VEC], xv[VEC];
+        poolT_gather<VEC>(dpooled, it[u].b, it[u].y, it[u].x, P, C, c, tabs, gp);
+        cvtraw<VEC>(draw[u], d); cvtraw<VEC>(xraw[u], xv);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) d1[v] += gp[v];
+        for (int v = 0; v < VEC; ++v) {
+          const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] + gp[v] : 0.f;
+          o[v] = fmaf(sc[v], dd, fmaf(p[v], xv[v], q[v]));
+        }
+        stv<VEC>(da0 + m * ld_da0 + c, o);
       }
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float dd = fmaf(xv1[v], sc[v], sh[v]) > 0.f ? d1[v] : 0.f;
-        o[v] = fmaf(sc[v], dd, fmaf(p[v], xv1[v], q[v]));
-      }
-      stv<VEC>(dst + m1 * ld_dst, o);
+      it[u].next(H, W);
     }
   }
 }
@@ -1095,8 +1127,9 @@ extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a
   const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_act_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
-  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks, ew_occ(3)), g.chunks);
-  OCC_DISPATCH(3, VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
+  static const int act_occ = [] { const char* e = getenv("DFCSA_ACT_OCC"); return e ? atoi(e) : 2; }();
+  dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks, ew_occ(act_occ)), g.chunks);
+  OCC_DISPATCH(act_occ, VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
                                                                      shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_act_fwd_kernel");
   return DFCSA_OK;
@@ -1267,20 +1300,16 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   // The L branch is a plain BatchNorm + ReLU backward: it runs on the light bn_bwd_apply_kernel (4 resident blocks per
   // SM, 0.97 of copy bandwidth at level 1) instead of sharing the register budget of the pool^T gather of the A branch
-  // (2 resident blocks, 0.63); the coefficients and the arithmetic are the same, so the result is bit-identical.
-  static const bool split = [] { const char* e = getenv("DFCSA_SPLIT_APPLY"); return e ? atoi(e) != 0 : true; }();
+  // (measured together: 0.63); the coefficients and the arithmetic are the same as in the fused version.
   const long long M = static_cast<long long>(B) * H * W;
-  if (split) {
-    dim3 gl(red_blocks(M, g.PL, g.chunks, 4), g.chunks);
-    VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<gl, 256, 0, ST>>>(G_(dz) + C, ld_dz, A_(l0), ld_l0, M, C, scale1, shift1, mean1, invstd1,
-                                                                   red1, 0, GM_(dl0), ld_dl0, g.CL, g.PL)));
-    DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
-  }
-  const int nz = split ? 1 : 2;
-  dim3 grid(red_blocks(M, g.PL, g.chunks * nz, ew_occ(2)), g.chunks, nz);
-  OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC, OCC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1,
-                                                                       shift1, mean1, invstd1, red1, scale2, shift2, mean2, invstd2,
-                                                                       red2, dpooled, P, GM_(dl0), ld_dl0, GM_(da0), ld_da0, g.CL, g.PL, split ? 1 : 0))));
+  dim3 gl(red_blocks(M, g.PL, g.chunks, 4), g.chunks);
+  VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<gl, 256, 0, ST>>>(G_(dz) + C, ld_dz, A_(l0), ld_l0, M, C, scale1, shift1, mean1, invstd1,
+                                                                 red1, 0, GM_(dl0), ld_dl0, g.CL, g.PL)));
+  DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(2)), g.chunks);
+  OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC, OCC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(
+                                        G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2, invstd2, red2, dpooled, P,
+                                        GM_(da0), ld_da0, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_apply_kernel");
   return DFCSA_OK;
 }
