@@ -410,10 +410,17 @@ pack_jobs_kernel(const dfcsa_pack_job_t* jobs, int n_jobs, const long long* chun
     for (int u = 0; u < 4; ++u) {
       const long long i = base + u * 256 + threadIdx.x;
       if (i < total) {
-        const long long i2 = i % j.D2;
-        const long long r = i / j.D2;
-        const long long i1 = r % j.D1;
-        const long long i0 = r / j.D1;
+        long long i0, i1, i2;
+        if (total < (1LL << 31)) {        // every weight tensor of the network: two 32-bit divisions instead of four 64-bit ones
+          const unsigned iu = static_cast<unsigned>(i), d2 = static_cast<unsigned>(j.D2), d1 = static_cast<unsigned>(j.D1);
+          const unsigned r = iu / d2, q = r / d1;
+          i2 = iu - r * d2; i1 = r - q * d1; i0 = q;
+        } else {
+          i2 = i % j.D2;
+          const long long r = i / j.D2;
+          i1 = r % j.D1;
+          i0 = r / j.D1;
+        }
         const long long i1s = j.flip1 ? j.D1 - 1 - i1 : i1;
         st_any(j.dst, i0 * j.ld_dst + i1 * j.D2 + i2, j.dst_dtype, sc * ld_any(j.src, i0 * j.s0 + i1s * j.s1 + i2 * j.s2, j.src_dtype));
       }

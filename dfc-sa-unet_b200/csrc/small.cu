@@ -129,20 +129,12 @@ wgrad_small_kernel(const void* x, long long ld_x, long long M, int H, int W, con
     load_patch<TAPS, CI, TX>(x, ld_x, m0 + lane, M, H, W, s_patch[warp][lane]);
     __syncwarp();
     const int cnt = static_cast<int>(min(32LL, M - m0));
-    // four pixels per step, and the wide-side loads of the NEXT step are issued before the FMAs of this one (a
-    // dependent ~500 ns load per step left this loop latency bound); each pixel's patch comes from shared memory as
-    // LDS.128 broadcasts
-    float2 dn[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) dn[u] = (u < cnt) ? ld2<TW>(wide, (m0 + u) * ld_w + n) : make_float2(0.f, 0.f);
+    // four pixels per step: their wide-side loads are issued together (a dependent 500 ns load per pixel made this
+    // loop latency bound), and each pixel's patch comes from shared memory as LDS.128 broadcasts
     for (int p0 = 0; p0 < 32; p0 += 4) {
       float2 d[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) d[u] = dn[u];
-      if (p0 + 4 < 32) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dn[u] = (p0 + 4 + u < cnt) ? ld2<TW>(wide, (m0 + p0 + 4 + u) * ld_w + n) : make_float2(0.f, 0.f);
-      }
+      for (int u = 0; u < 4; ++u) d[u] = (p0 + u < cnt) ? ld2<TW>(wide, (m0 + p0 + u) * ld_w + n) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float xr[KP];
@@ -173,56 +165,40 @@ wgrad_small_kernel(const void* x, long long ld_x, long long M, int H, int W, con
   }
 }
 
-// out[m, n] = sum_c x[m, c] * w[n, c] + bias[n], N <= 4, C % 64 == 0: 8 lanes per pixel, 16-byte loads, four pixels
-// (four independent loads) in flight per thread - one load per thread left the C = 64 final conv at 40 % of copy bandwidth
+// out[m, n] = sum_c x[m, c] * w[n, c] + bias[n], N <= 4, C % 64 == 0: 8 lanes per pixel, 16-byte loads
 template <typename TX>
 __global__ void __launch_bounds__(256)
 conv_smalln_kernel(const TX* x, long long ld_x, long long M, int C, const float* wgt, int N, float* out, long long ld_out,
                    const float* bias) {
-  constexpr int UNR = 4;
   extern __shared__ float s_w[];   // [N][C]
   for (int i = threadIdx.x; i < N * C; i += blockDim.x) s_w[i] = wgt[i];
   __syncthreads();
-  const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const long long stride = static_cast<long long>(gridDim.x) * 32;
-  for (long long mb = static_cast<long long>(blockIdx.x) * 32; mb < M; mb += stride * UNR) {
-    float acc[UNR][4];
+  const int sub = threadIdx.x & 7;
+  const long long pix_per_iter = static_cast<long long>(gridDim.x) * (blockDim.x / 8);
+  for (long long m = static_cast<long long>(blockIdx.x) * (blockDim.x / 8) + (threadIdx.x >> 3); m < (M + 3) / 4 * 4; m += pix_per_iter) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < M) {
+      for (int c0 = sub * 8; c0 < C; c0 += 64) {
+        float v[8];
+        load8<TX>(x + m * ld_x + c0, v);
 #pragma unroll
-    for (int u = 0; u < UNR; ++u)
+        for (int nn = 0; nn < 4; ++nn) {
+          if (nn < N) {
 #pragma unroll
-      for (int nn = 0; nn < 4; ++nn) acc[u][nn] = 0.f;
-    for (int c0 = sub * 8; c0 < C; c0 += 64) {
-      uint4 raw[UNR];
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const long long m = mb + u * stride + pl;
-        raw[u] = m < M ? *reinterpret_cast<const uint4*>(x + m * ld_x + c0) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const TX* e = reinterpret_cast<const TX*>(&raw[u]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = Cvt<TX>::to_f(e[j]);
-#pragma unroll
-          for (int nn = 0; nn < 4; ++nn)
-            if (nn < N) acc[u][nn] = fmaf(v, s_w[nn * C + c0 + j], acc[u][nn]);
+            for (int j = 0; j < 8; ++j) acc[nn] = fmaf(v[j], s_w[nn * C + c0 + j], acc[nn]);
+          }
         }
       }
     }
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-#pragma unroll
-      for (int nn = 0; nn < 4; ++nn) {
-        acc[u][nn] += __shfl_xor_sync(0xffffffffu, acc[u][nn], 1);
-        acc[u][nn] += __shfl_xor_sync(0xffffffffu, acc[u][nn], 2);
-        acc[u][nn] += __shfl_xor_sync(0xffffffffu, acc[u][nn], 4);
-      }
-      const long long m = mb + u * stride + pl;
-      if (m < M && sub < N) {
-        const float r = sub == 0 ? acc[u][0] : sub == 1 ? acc[u][1] : sub == 2 ? acc[u][2] : acc[u][3];
-        out[m * ld_out + sub] = r + (bias ? bias[sub] : 0.f);
-      }
+    for (int nn = 0; nn < 4; ++nn) {
+      acc[nn] += __shfl_xor_sync(0xffffffffu, acc[nn], 1);
+      acc[nn] += __shfl_xor_sync(0xffffffffu, acc[nn], 2);
+      acc[nn] += __shfl_xor_sync(0xffffffffu, acc[nn], 4);
+    }
+    if (m < M && sub < N) {
+      const float r = sub == 0 ? acc[0] : sub == 1 ? acc[1] : sub == 2 ? acc[2] : acc[3];
+      out[m * ld_out + sub] = r + (bias ? bias[sub] : 0.f);
     }
   }
 }
@@ -318,7 +294,7 @@ int conv_gemm_small(const dfcsa_conv_params_t* p, cudaStream_t stream, int* rc_o
   if (sg.tap_mode == DFCSA_TAP_1x1 && p->N <= 4 && sg.channels % 64 == 0 && sg.channels <= 1024 && p->w_dtype == DFCSA_F32 &&
       p->out_dtype == DFCSA_F32 && p->src_dtype != DFCSA_F32 && p->stats == nullptr && sg.ld % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(sg.ptr) & 15) == 0) {
-    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((M + 127) / 128, 8LL * num_sms())));
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((M + 31) / 32, 148LL * 8)));
     const size_t smem = static_cast<size_t>(p->N) * sg.channels * sizeof(float);
     if (p->src_dtype == DFCSA_F16)
       conv_smalln_kernel<__half><<<blocks, 256, smem, stream>>>(reinterpret_cast<const __half*>(sg.ptr), sg.ld, M, sg.channels,

@@ -161,7 +161,7 @@ class Profiler:
 PROF = None          # set to a Profiler() to time every ABI call
 LAUNCHES = 0         # kernels enqueued through the ABI (bench.py's gpu_launches)
 # entry points that enqueue more than one kernel
-_KERNELS = {"dfcsa_bnrelu_pool_fwd": 2, "dfcsa_branch_bwd_reduce1": 3, "dfcsa_preprocess": 4, "dfcsa_attn_bwd_fused": 2}
+_KERNELS = {"dfcsa_bnrelu_pool_fwd": 2, "dfcsa_branch_bwd_reduce1": 3, "dfcsa_preprocess": 4, "dfcsa_attn_bwd_fused": 2, "dfcsa_branch_bwd_apply": 2}
 
 
 def call(name, *args, tag=None, flops=0.0, desc=""):
