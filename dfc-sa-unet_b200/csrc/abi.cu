@@ -85,6 +85,14 @@ using namespace dfcsa;
 extern "C" int dfcsa_version(void) { return DFCSA_VERSION; }
 extern "C" const char* dfcsa_last_error(void) { return g_err; }
 
+extern "C" int dfcsa_wgrad_plan(int64_t items, int64_t pix_blocks, int32_t sms, int32_t* splits, int64_t* blocks_per_split) {
+  DFCSA_CHECK_ARG(items > 0 && pix_blocks > 0 && sms > 0 && splits && blocks_per_split, "dfcsa_wgrad_plan: bad args");
+  long long bps = 0;
+  *splits = wgrad_pick_splits(items, pix_blocks, sms, 0, &bps);
+  *blocks_per_split = bps;
+  return DFCSA_OK;
+}
+
 extern "C" int dfcsa_device_ok(void) {
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;

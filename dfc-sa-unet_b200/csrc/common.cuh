@@ -32,6 +32,7 @@ int encode_tensor_map(CUtensorMap* map, int dtype, int rank, const void* base,
                       const uint32_t* box, bool swizzle128);
 
 int num_sms();
+int wgrad_pick_splits(long long items, long long pix_blocks, int sms, int force_waves, long long* blocks_per_split);
 
 static inline size_t dtype_size(int dt) { return dt == DFCSA_F32 ? 4 : 2; }
 

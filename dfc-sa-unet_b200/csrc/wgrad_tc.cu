@@ -266,6 +266,28 @@ void pick_patch(int H, int W, int& w_t, int& h_t) {
 
 }  // namespace
 
+// Pixel splits: the kernel needs a whole SM per CTA (shared memory + 512 TMEM columns), so a grid of 2*SMs + 1 CTAs
+// costs three waves, not two (measured: 297 CTAs of the level-1 3x3 gradient kept every SM idle for a third of the
+// launch).  Pick the split count whose grid fills 1..4 whole waves at the lowest cost
+//   waves * (pixel blocks per CTA + fixed cost of a CTA: prologue, pipeline fill, atomic epilogue ~ 8 blocks).
+// items = independent (tap row, n tile, c tile) work items; returns the split count, *blocks_per_split = pixel blocks
+// of one CTA.  force_waves > 0 restricts the choice to that wave count (experiments).
+int wgrad_pick_splits(long long items, long long pix_blocks, int sms, int force_waves, long long* blocks_per_split) {
+  long long best_cost = -1, best_s = 1, best_bps = pix_blocks;
+  for (int k = 1; k <= 4; ++k) {
+    if (force_waves > 0 && k != force_waves) continue;
+    long long s = std::max<long long>(1, static_cast<long long>(k) * sms / items);
+    s = std::min(s, std::max<long long>(1, pix_blocks / 4));
+    const long long bps = (pix_blocks + s - 1) / s;
+    s = (pix_blocks + bps - 1) / bps;
+    const long long waves = (items * s + sms - 1) / sms;
+    const long long cost = waves * (bps + 8);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; best_bps = bps; }
+  }
+  *blocks_per_split = best_bps;
+  return static_cast<int>(best_s);
+}
+
 int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->x_dtype != DFCSA_F32 && p->dy_dtype != DFCSA_F32, "conv_wgrad_tc: 16-bit operands required");
   const bool cvt_x = p->x_dtype == DFCSA_F16 && p->dy_dtype == DFCSA_BF16;
@@ -375,24 +397,11 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   a.zero_fill = (a.box_bytes < kBoxBytes) ? 1 : 0;
   a.pix_blocks = static_cast<long long>(a.tiles_w) * a.tiles_h * a.tiles_b;
 
-  // Pixel splits: the kernel needs a whole SM per CTA (shared memory + 512 TMEM columns), so a grid of 2*SMs + 1 CTAs
-  // costs three waves, not two (measured: 297 CTAs of the level-1 3x3 gradient kept every SM idle for a third of the
-  // launch).  Pick the split count whose grid fills 1..4 whole waves at the lowest cost
-  //   waves * (pixel blocks per CTA + fixed cost of a CTA: prologue, pipeline fill, atomic epilogue ~ 8 blocks).
   const long long items = static_cast<long long>(a.taps) * a.n_tiles * a.c_tiles;
-  const long long sms = num_sms();
   static const int force_waves = [] { const char* e = getenv("DFCSA_WGRAD_WAVES"); return e ? atoi(e) : 0; }();
-  long long best_cost = -1;
-  for (int k = 1; k <= 4; ++k) {
-    if (force_waves > 0 && k != force_waves) continue;
-    long long s = std::max<long long>(1, k * sms / items);
-    s = std::min(s, std::max<long long>(1, a.pix_blocks / 4));
-    const long long bps = (a.pix_blocks + s - 1) / s;
-    s = (a.pix_blocks + bps - 1) / bps;
-    const long long waves = (items * s + sms - 1) / sms;
-    const long long cost = waves * (bps + 8);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; a.blocks_per_split = bps; a.splits = static_cast<int>(s); }
-  }
+  long long bps = 0;
+  a.splits = wgrad_pick_splits(items, a.pix_blocks, num_sms(), force_waves, &bps);
+  a.blocks_per_split = bps;
   a.dw = p->dw; a.ld_dw = p->ld_dw; a.alpha = p->alpha;
   a.vec_red = ((reinterpret_cast<uintptr_t>(p->dw) & 15) == 0 && p->ld_dw % 4 == 0) ? 1 : 0;
   a.cvt_x = cvt_x ? 1 : 0;

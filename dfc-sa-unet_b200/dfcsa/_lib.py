@@ -88,7 +88,7 @@ class ParamDesc(C.Structure):
 # every symbol include/dfcsa.h declares (the CPU test checks the .so exports exactly these)
 SYMBOLS = [
     "dfcsa_version", "dfcsa_last_error", "dfcsa_device_ok",
-    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm", "dfcsa_bgemm", "dfcsa_bgemm_rowstat_parts", "dfcsa_lse_combine", "dfcsa_attn_pv_fused", "dfcsa_attn_bwd_fused", "dfcsa_attn_small_fwd", "dfcsa_attn_small_bwd",
+    "dfcsa_conv_gemm", "dfcsa_conv_wgrad", "dfcsa_wgrad_plan", "dfcsa_permute3", "dfcsa_pack_jobs", "dfcsa_sgemm", "dfcsa_bgemm", "dfcsa_bgemm_rowstat_parts", "dfcsa_lse_combine", "dfcsa_attn_pv_fused", "dfcsa_attn_bwd_fused", "dfcsa_attn_small_fwd", "dfcsa_attn_small_bwd",
     "dfcsa_softmax_rows", "dfcsa_softmax_rows_bwd", "dfcsa_softmax_rows_bwd_d", "dfcsa_rowdot",
     "dfcsa_bn_finalize", "dfcsa_bn_eval_affine",
     "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd", "dfcsa_sum_out_fwd",

@@ -109,6 +109,12 @@ typedef struct {
 
 int dfcsa_conv_wgrad(const dfcsa_wgrad_params_t* p, int backend, void* stream);
 
+/* Host-only (no CUDA call): the pixel-split choice of the tcgen05 weight-gradient launch for `items` independent
+ * (tap row, n tile, c tile) work items over `pix_blocks` 64-pixel blocks on a device with `sms` SMs.  The kernel runs
+ * one CTA per SM, so the grid items * splits is chosen to fill 1..4 WHOLE waves (a grid of 2*sms + 1 CTAs would cost
+ * three).  Exposed so that the choice can be regression-tested without a GPU. */
+int dfcsa_wgrad_plan(int64_t items, int64_t pix_blocks, int32_t sms, int32_t* splits, int64_t* blocks_per_split);
+
 /* dst[i0*ld_dst + i1*D2 + i2] = scale * src[i0*s0 + i1'*s1 + i2*s2], i1' = flip ? D1-1-i1 : i1
  * (ld_dst = 0 means a dense destination, ld_dst = D1*D2).
  * Re-lays fp32 master weights ([Co,Ci,kh,kw], ConvT [Ci,Co,2,2]) into the packed K-major GEMM operands

@@ -116,3 +116,30 @@ def test_sliding_window_geometry_matches_the_reference_loop():
         for y0, y1, x0, x1 in want:
             cover[y0:y1, x0:x1] += 1
         assert bool((cover > 0).all())
+
+
+def test_wgrad_pixel_splits_fill_whole_waves():
+    """dfcsa_wgrad_plan (the split choice of the tcgen05 weight-gradient launch, host arithmetic only): the kernel runs one
+    CTA per SM, so for every (items, pixel blocks) of the network's shapes the grid must not spill a few CTAs into an
+    extra wave (the 2*SMs + 1 = 297-CTA grids of the first build ran three waves), every pixel block must be covered
+    exactly once, and no SM may sit idle while the work could be split further."""
+    from dfcsa import _lib
+    lib = _lib.lib()
+    sms = 148
+    splits, bps = ctypes.c_int32(), ctypes.c_int64()
+    # (items, pixel blocks) of the 224^2 batch-64 training step (profiles/gemm_shapes_r01_p.json) plus edge cases
+    cases = [(3, 50176), (24, 3136), (6, 12544), (1, 50176), (96, 784), (2, 12544), (6, 3136), (24, 784), (3, 12544),
+             (4, 12544), (96, 196), (16, 784), (32, 196), (8, 784), (1, 16), (4, 16), (16, 16), (1, 1), (400, 7), (149, 1000)]
+    for items, pix in cases:
+        assert lib.dfcsa_wgrad_plan(ctypes.c_int64(items), ctypes.c_int64(pix), sms, ctypes.byref(splits), ctypes.byref(bps)) == 0
+        s, b = splits.value, bps.value
+        assert s >= 1 and b >= 1 and (s - 1) * b < pix <= s * b, (items, pix, s, b)       # exact cover, no empty split
+        grid = items * s
+        waves = -(-grid // sms)
+        if items <= sms and pix >= 4 * (sms // items):
+            # enough work to fill the machine: the last wave must be (nearly) full - at most 1/8 of the SMs idle in it
+            assert grid > (waves - 1) * sms + sms * 7 // 8 or grid == waves * sms or waves * sms - grid < items, (items, pix, s, b, grid)
+        # never the "a few CTAs too many" pattern when the item count leaves a choice (items = sms + 1 cannot avoid it)
+        if items <= sms // 2:
+            assert grid % sms == 0 or grid % sms > sms // 2 or grid < sms, (items, pix, grid)
+    assert lib.dfcsa_wgrad_plan(ctypes.c_int64(0), ctypes.c_int64(5), sms, ctypes.byref(splits), ctypes.byref(bps)) == 1
