@@ -159,19 +159,42 @@ class GpuLoader:
     transforms the current one.  Under data parallelism every rank takes its own slice of each epoch's order."""
 
     def __init__(self, dataset, batch_size, img_size, augment, shuffle, num_workers=2, device="cuda", drop_last=False,
-                 rank=0, world=1):
+                 rank=0, world=1, shard_batches=False):
         self.dataset, self.batch_size, self.img_size = dataset, int(batch_size), tuple(img_size)
         self.augment, self.shuffle, self.device, self.drop_last = augment, shuffle, device, drop_last
         self.num_workers = max(1, int(num_workers))
         self.rank, self.world, self.epoch = int(rank), int(world), 0
+        # shard_batches (validation): the batches of the single-process loader are dealt out whole, batch k to rank
+        # k % world, so every per-batch metric equals the reference's and their all-reduced mean is the single-process
+        # epoch mean; ranks may then see different batch counts, which is fine because the validation loop issues its
+        # collectives only after the loop.  Training shards SAMPLES and must give every rank the same number of batches
+        # (each train step issues per-bucket all-reduces): see rank_batches().
+        self.shard_batches = bool(shard_batches) and self.world > 1
 
-    def _count(self):
-        n = len(self.dataset)
-        return (n - self.rank + self.world - 1) // self.world if self.world > 1 else n
+    @staticmethod
+    def rank_batches(order, batch_size, rank, world, drop_last, shard_batches=False):
+        """The index batches rank `rank` of `world` runs for one epoch's sample `order`.  Sample sharding follows
+        torch's DistributedSampler: with drop_last the order is truncated to a multiple of world * batch_size, otherwise
+        it is padded (wrapping around) to a multiple of world - either way every rank gets the same number of batches of
+        the same sizes, so the per-step collectives can never be left waiting for a rank that ran out of data."""
+        bs = int(batch_size)
+        if world > 1 and not shard_batches:
+            if drop_last:
+                order = order[:len(order) // (world * bs) * (world * bs)]
+            elif order:
+                total = (len(order) + world - 1) // world * world
+                order = (order * ((total + len(order) - 1) // len(order)))[:total]
+            order = order[rank::world]
+        batches = [order[i:i + bs] for i in range(0, len(order), bs)]
+        if drop_last and batches and len(batches[-1]) < bs:
+            batches.pop()
+        if world > 1 and shard_batches:
+            batches = batches[rank::world]
+        return batches
 
     def __len__(self):
-        n = self._count()
-        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+        return len(self.rank_batches(list(range(len(self.dataset))), self.batch_size, self.rank, self.world, self.drop_last,
+                                     self.shard_batches))
 
     def __iter__(self):
         n = len(self.dataset)
@@ -181,10 +204,7 @@ class GpuLoader:
         else:
             order = torch.randperm(n).tolist() if self.shuffle else list(range(n))
         self.epoch += 1
-        order = order[self.rank::self.world]
-        batches = [order[i:i + self.batch_size] for i in range(0, len(order), self.batch_size)]
-        if self.drop_last and batches and len(batches[-1]) < self.batch_size:
-            batches.pop()
+        batches = self.rank_batches(order, self.batch_size, self.rank, self.world, self.drop_last, self.shard_batches)
         with ThreadPoolExecutor(self.num_workers) as pool:
             pending, pending_idx = None, None
             for idx in batches + [None]:
@@ -194,7 +214,7 @@ class GpuLoader:
                     params = draw_augmentation(len(pairs)) if self.augment else None
                     img, mask = preprocess_batch([p[0] for p in pairs], [p[1] for p in pairs], self.img_size, params, device=self.device)
                     names = [self.dataset.filename(i) for i in pending_idx] if hasattr(self.dataset, "filename") else [str(i) for i in pending_idx]
-                    yield {"image": img, "mask": mask, "filename": names}
+                    yield {"image": img, "mask": mask, "filename": names, "index": list(pending_idx)}
                 pending, pending_idx = nxt, idx
 
 
@@ -219,5 +239,7 @@ class DataLoaderFactory:
 
     def get_val_loader(self):
         ds = SegmentationDataset(self.val_dir, img_size=self.img_size)
+        # validation: whole batches are dealt out to the ranks and Trainer.validate_epoch all-reduces the sums, so the
+        # reported metrics, best_val_loss and the is_best decision are those of the full validation set on every rank
         return GpuLoader(ds, self.batch_size, self.img_size, augment=False, shuffle=False, num_workers=self.num_workers,
-                         device=self.device, rank=self.rank, world=self.world)
+                         device=self.device, rank=self.rank, world=self.world, shard_batches=True)

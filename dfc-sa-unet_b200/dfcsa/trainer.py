@@ -127,7 +127,19 @@ class Trainer:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self._reducer = BucketReducer(self.optimizer.flat_grad, bucket_ranges(self.model)) if self.world > 1 else None
+        self.sync_replicas()
         self._graphs = {}       # (input shapes) -> [calls, CUDAGraph, static image, static mask, static stats]
+
+    def sync_replicas(self):
+        """Data parallel: every replica starts from rank 0's parameters, BatchNorm buffers and momentum (in place, so the
+        flat-buffer views and the device pointer tables stay valid).  Identical seeds usually make this a no-op, but a
+        rank whose pretrained / resume checkpoint failed to load would otherwise train a diverged replica silently."""
+        if self.world <= 1:
+            return
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=0)
+            dist.broadcast(self.optimizer.flat_mom, src=0)
 
     # ------------------------------------------------------------------------------------------------------------
     def train_step(self, images, masks):
@@ -142,12 +154,17 @@ class Trainer:
         stats = torch.empty(5, dtype=torch.float32, device=dev)
         t = masks.contiguous().float()
         ops.bce_dice_sums(logits, t, True, sums)
+        w_dice_bwd = self.w_dice
         if self.world > 1 and self.config.get("training", {}).get("global_batch_dice", False):
             dist.all_reduce(sums)           # exact global-batch Dice / BCE; n scales with world
             n = n * self.world
+            # With global sums bce_dice_bwd yields the exact derivative of the GLOBAL Dice term for every local logit, so
+            # the NCCL SUM over ranks is already the whole Dice gradient; the BCE term (local 1/n) still needs the
+            # 1/world average.  step(grad_scale=1/world) divides both: pre-multiply the Dice term by world.
+            w_dice_bwd = self.w_dice * self.world
         ops.bce_dice_finalize(sums, n, self.w_bce, self.w_dice, 1.0, stats)
         dlogits = torch.empty_like(logits)
-        ops.bce_dice_bwd(logits, t, True, sums, self.w_bce, self.w_dice, 1.0, None, dlogits)
+        ops.bce_dice_bwd(logits, t, True, sums, self.w_bce, w_dice_bwd, 1.0, None, dlogits)
         if self.world == 1:
             engine.net_backward(net, ctx, dlogits, opt.grads)
             opt.step()
@@ -189,15 +206,21 @@ class Trainer:
     # ------------------------------------------------------------------------------------------------------------
     def train_epoch(self, epoch):
         running = torch.zeros(5, dtype=torch.float32, device=self.device)
+        good = torch.zeros((), dtype=torch.float32, device=self.device)
         nb = 0
         # training.cuda_graph: replay the step from a CUDA graph (one per batch shape; a ragged last batch is captured
         # separately) - worth it when the batch is small enough for launch overhead to show
         step = self.train_step_graphed if self.config.get("training", {}).get("cuda_graph", False) else self.train_step
         for images, masks in device_feeder(((b["image"], b["mask"]) for b in self.train_loader), self.device):
             r = step(images, masks)
-            running += r.stats
+            # a batch with a non-finite loss is skipped by the device-side update (sgd_step) AND left out of the epoch
+            # means, like the reference's `continue` before accumulating (utils/trainer.py:134-139); no host sync
+            ok = torch.isfinite(r.stats[0])
+            running += torch.where(ok, r.stats, torch.zeros_like(r.stats))
+            good += ok.to(torch.float32)
             nb += 1
-        v = (running / max(nb, 1)).tolist()
+        v = (running / good.clamp(min=1.0)).tolist()
+        self.skipped_batches = nb - int(good.item())
         return v[0], v[3], v[4]
 
     @torch.no_grad()
@@ -212,7 +235,7 @@ class Trainer:
         K = int(self.config.get("logging", {}).get("save_best_worst_samples", 0) or 0)
         dev = self.device
         tot = torch.zeros(3, dtype=torch.float64, device=dev)
-        nb, seen, names = 0, 0, []
+        nb, seen, names, gidx = 0, 0, [], []
         pool = None                 # (ids, metrics [m, 5], images, masks, outputs)
         for batch in dataloader:
             images = batch["image"].to(dev, non_blocking=True)
@@ -225,6 +248,7 @@ class Trainer:
             nb += 1
             b = images.shape[0]
             names += list(batch.get("filename", [str(seen + i) for i in range(b)]))
+            gidx += [int(i) for i in batch.get("index", range(seen, seen + b))]      # position in the full validation set
             if K > 0:
                 ids = torch.arange(seen, seen + b, device=dev)
                 sm = torch.where(ok, sm, torch.full_like(sm, float("nan")))
@@ -237,18 +261,36 @@ class Trainer:
                     keep = torch.unique(torch.cat([worst, best]))
                     pool = tuple(p[keep] for p in pool)
             seen += b
+        # Data parallel with a batch-sharded loader (GpuLoader(shard_batches=True)): every rank holds the per-batch sums
+        # of its share of the reference's batches; one all-reduce of (sums, batch count) gives every rank the
+        # full-set means the reference computes, so best_val_loss / is_best / the histories agree across ranks.  The
+        # collectives sit after the loop, so ranks with different batch counts cannot dead-lock.
+        sharded = self.world > 1 and getattr(dataloader, "shard_batches", False)
+        if sharded:
+            red = torch.cat([tot, torch.tensor([float(nb)], dtype=torch.float64, device=dev)])
+            dist.all_reduce(red)
+            tot, nb = red[:3], int(round(float(red[3])))
         mean = (tot / max(nb, 1)).tolist()                             # the epoch's only synchronisation
         res = {"loss": mean[0], "iou": mean[1], "dice": mean[2], "best_samples": [], "worst_samples": []}
-        if K > 0 and pool is not None:
-            ids, sm, imgs, msks, outs = (p.cpu() for p in pool)
-            valid = ~torch.isnan(sm[:, 4])
-            order = [i for i in torch.argsort(sm[:, 4], stable=True).tolist() if valid[i]]      # ascending Dice (:251)
+        if K > 0 and (pool is not None or sharded):
+            cands = []
+            if pool is not None:
+                ids, sm, imgs, msks, outs = (p.cpu() for p in pool)
+                valid = ~torch.isnan(sm[:, 4])
+                order = [i for i in torch.argsort(sm[:, 4], stable=True).tolist() if valid[i]]      # ascending Dice (:251)
 
-            def sample(i):
-                return {"sample_idx": int(ids[i]), "image": imgs[i], "mask": msks[i], "output": outs[i], "filename": names[int(ids[i])],
-                        "metrics": {"loss": float(sm[i, 0]), "iou": float(sm[i, 3]), "dice": float(sm[i, 4])}}
-            res["worst_samples"] = [sample(i) for i in order[:K]]
-            res["best_samples"] = [sample(i) for i in order[-K:]]
+                def sample(i):
+                    return {"sample_idx": gidx[int(ids[i])], "image": imgs[i], "mask": msks[i], "output": outs[i],
+                            "filename": names[int(ids[i])],
+                            "metrics": {"loss": float(sm[i, 0]), "iou": float(sm[i, 3]), "dice": float(sm[i, 4])}}
+                cands = [sample(i) for i in order[:K]] + [sample(i) for i in order[K:][-K:]]
+            if sharded:      # K worst + K best of every rank -> the global K worst / K best (ties: dataset order, as a stable sort)
+                allc = [None] * self.world
+                dist.all_gather_object(allc, cands)
+                cands = [c for rank_c in allc for c in rank_c]
+            cands.sort(key=lambda c: (c["metrics"]["dice"], c["sample_idx"]))
+            res["worst_samples"] = cands[:K]
+            res["best_samples"] = cands[-K:]
         return res
 
     def save_checkpoint(self, epoch, metrics, is_best=False):
@@ -274,6 +316,7 @@ class Trainer:
         for k in ("train_losses", "val_losses", "train_dice_scores", "val_dice_scores", "train_iou_scores", "val_iou_scores",
                   "best_val_loss"):
             setattr(self, k, ckpt[k])
+        self.sync_replicas()
         return ckpt["epoch"]
 
     def train(self, resume_from=None):

@@ -99,3 +99,106 @@ def test_gloo_world2_bucketed_allreduce_matches_mean_of_shard_gradients(tmp_path
         ref = g if ref is None else ref + g
     ref /= world
     assert torch.allclose(outs[0]["flat"], ref, rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("n,world,bs", [(127, 2, 64), (128, 2, 64), (129, 2, 64), (10, 4, 3), (7, 8, 2), (1000, 8, 64), (5, 2, 8),
+                                        (64, 3, 7), (1, 2, 1)])
+@pytest.mark.parametrize("drop_last", [True, False])
+def test_train_sharding_gives_every_rank_the_same_batches(n, world, bs, drop_last):
+    """Every train step issues per-bucket all-reduces, so all ranks must run the same number of steps with the same
+    batch sizes whatever n / world / batch size are (the order[rank::world] slicing of round 1 could leave low ranks one
+    step ahead and hang the job: n=127, world=2, bs=64)."""
+    from dfcsa.data_loader import GpuLoader
+    order = list(range(n))
+    per_rank = [GpuLoader.rank_batches(order, bs, r, world, drop_last) for r in range(world)]
+    shapes = [[len(b) for b in br] for br in per_rank]
+    assert all(s == shapes[0] for s in shapes), shapes
+    seen = [i for br in per_rank for b in br for i in b]
+    if drop_last:
+        assert all(len(b) == bs for br in per_rank for b in br)
+        assert len(seen) == len(set(seen)) == n // (world * bs) * (world * bs)          # no duplicates, whole global batches
+    else:
+        assert set(seen) == set(order)                                                  # every sample is visited
+        assert len(seen) == (n + world - 1) // world * world                            # padded by wrapping around
+    # __len__ agrees with the iteration
+    ld = GpuLoader(order, bs, (8, 8), augment=False, shuffle=False, drop_last=drop_last, rank=world - 1, world=world)
+    assert len(ld) == len(per_rank[-1])
+
+
+@pytest.mark.parametrize("n,world,bs", [(10, 2, 3), (9, 4, 2), (3, 4, 2)])
+def test_validation_batch_sharding_deals_out_the_reference_batches(n, world, bs):
+    from dfcsa.data_loader import GpuLoader
+    order = list(range(n))
+    single = GpuLoader.rank_batches(order, bs, 0, 1, False)
+    dealt = [GpuLoader.rank_batches(order, bs, r, world, False, shard_batches=True) for r in range(world)]
+    assert sorted(b for br in dealt for b in br) == sorted(single)            # the same batches, each on exactly one rank
+    assert all(br == single[r::world] for r, br in enumerate(dealt))
+
+
+class _FakeVal:
+    """Stands in for the model + metric kernels in Trainer.validate_epoch's reduction logic (CPU, gloo)."""
+    shard_batches = True
+
+    def __init__(self, batches):
+        self.batches = batches
+
+    def __iter__(self):
+        return iter(self.batches)
+
+
+def _val_worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "dfc-sa-unet_b200")]
+    from dfcsa import metrics as M
+    from dfcsa import trainer as T
+    from dfcsa.data_loader import GpuLoader
+    from oracle import dfcsa_oracle as O
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def per_sample(p, t, loss_type, params):        # CPU stand-in for the batched CUDA metric kernels
+        rows = []
+        for j in range(p.shape[0]):
+            m = O.calculate_metrics(p[j:j + 1].reshape(1, 1, 1, -1), t[j:j + 1].reshape(1, 1, 1, -1).float(), "bce_dice", {})
+            rows.append([float(m["loss"]), 0.0, 0.0, m["iou"], m["dice"]])
+        return torch.tensor(rows)
+    M.per_sample_metrics = per_sample
+    n, bs = 7, 2
+    g = torch.Generator().manual_seed(3)
+    logit = torch.randn(n, 1, 8, 8, generator=g) * 2
+    mask = (torch.rand(n, 1, 8, 8, generator=g) > 0.5).float()
+    mine = GpuLoader.rank_batches(list(range(n)), bs, rank, world, False, shard_batches=True)
+    batches = [{"image": logit[b], "mask": mask[b], "filename": [f"s{i}" for i in b], "index": b} for b in mine]
+    tr = T.Trainer.__new__(T.Trainer)
+    tr.world, tr.rank, tr.device = world, rank, torch.device("cpu")
+    tr.config = {"logging": {"save_best_worst_samples": 2}}
+    tr.loss_type, tr.loss_params = "bce_dice", {}
+    tr.model = torch.nn.Identity()                  # "logits" are fed in as the images
+    res = tr.validate_epoch(_FakeVal(batches))
+    torch.save({k: res[k] for k in ("loss", "iou", "dice")} |
+               {"worst": [s["filename"] for s in res["worst_samples"]], "best": [s["filename"] for s in res["best_samples"]]},
+               os.path.join(out_dir, f"v{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_gloo_world2_validation_reduces_to_the_full_set_metrics(tmp_path):
+    """under data parallel the validation metrics (and with them best_val_loss / is_best) must be those of
+    the FULL validation set on every rank, not of rank 0's shard."""
+    from oracle import dfcsa_oracle as O
+    world = 2
+    mp.spawn(_val_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"v{r}.pt") for r in range(world)]
+    assert outs[0] == outs[1]                                                  # every rank reports the same numbers
+    n, bs = 7, 2
+    g = torch.Generator().manual_seed(3)
+    logit = torch.randn(n, 1, 8, 8, generator=g) * 2
+    mask = (torch.rand(n, 1, 8, 8, generator=g) > 0.5).float()
+    p = torch.sigmoid(logit)
+    per_batch = [O.calculate_metrics(p[i:i + bs], mask[i:i + bs], "bce_dice", {}) for i in range(0, n, bs)]
+    for k in ("loss", "iou", "dice"):
+        assert abs(outs[0][k] - sum(float(m[k]) for m in per_batch) / len(per_batch)) < 1e-5, k
+    dice = sorted((O.calculate_metrics(p[i:i + 1], mask[i:i + 1], "bce_dice", {})["dice"], i) for i in range(n))
+    assert outs[0]["worst"] == [f"s{i}" for _, i in dice[:2]] and outs[0]["best"] == [f"s{i}" for _, i in dice[-2:]]

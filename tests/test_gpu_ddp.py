@@ -38,15 +38,22 @@ def _model():
     return m
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, global_dice=False):
     _setup_paths()
+    import copy
     import torch.distributed as dist
     from dfcsa.trainer import Trainer
     from oracle import dfcsa_oracle as O
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
-    tr = Trainer(_model(), None, None, None, f"cuda:{rank}", CFG)
+    cfg = copy.deepcopy(CFG)
+    cfg["training"]["global_batch_dice"] = global_dice
+    model = _model()
+    if rank == 1:       # a replica that starts from different weights must be overwritten by rank 0's (Trainer.sync_replicas)
+        with torch.no_grad():
+            model.final_conv.weight.add_(1.0)
+    tr = Trainer(model, None, None, None, f"cuda:{rank}", cfg)
     img, mask = O.synthetic_batch(2 * world, 64, 64, seed=7)
     for _ in range(2):
         r = tr.train_step(img[2 * rank:2 * rank + 2].cuda(), mask[2 * rank:2 * rank + 2].cuda())
@@ -58,7 +65,11 @@ def _worker(rank, world, port, out_dir):
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_nccl_step_matches_single_process_average(cuda, tmp_path):
+@pytest.mark.parametrize("global_dice", [False, True])
+def test_two_rank_nccl_step_matches_single_process_average(cuda, tmp_path, global_dice):
+    """global_dice=True (training.global_batch_dice): the loss sums are all-reduced, so the loss is BCE over the global
+    batch + ONE Dice ratio over the global batch; its gradient is sum_r J_r^T [w_bce (p - t) / (world n) + w_dice dDice_global]
+    (the Dice part used to come out world times too small)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -66,7 +77,7 @@ def test_two_rank_nccl_step_matches_single_process_average(cuda, tmp_path):
     from dfcsa.optim import FusedSGD
     from oracle import dfcsa_oracle as O
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), global_dice), nprocs=world, join=True)
     outs = [torch.load(tmp_path / f"r{r}.pt") for r in range(world)]
     assert torch.equal(outs[0]["flat"], outs[1]["flat"])        # replicas stay bit-identical
     # single-process emulation of the same two steps with the library's own kernels
@@ -77,6 +88,14 @@ def test_two_rank_nccl_step_matches_single_process_average(cuda, tmp_path):
         opt.zero_grad()
         acc = torch.zeros_like(opt.flat_grad)
         state = {k: v.clone() for k, v in net.state_dict().items() if "running" in k or "tracked" in k}
+        gsums = torch.zeros(8, dtype=torch.float64, device="cuda")
+        if global_dice:       # the all-reduced loss sums: a forward pass of every shard first (BN buffers restored below)
+            for r in range(world):
+                net.load_state_dict(state, strict=False)
+                net.train()
+                with torch.no_grad():
+                    lg, _ = engine.net_forward(net, img[2 * r:2 * r + 2].cuda(), True, save=False)
+                ops.bce_dice_sums(lg, mask[2 * r:2 * r + 2].cuda().float(), True, gsums)
         for r in range(world):
             net.load_state_dict(state, strict=False)              # every replica starts from the same BN buffers
             opt.flat_grad.zero_()
@@ -86,11 +105,14 @@ def test_two_rank_nccl_step_matches_single_process_average(cuda, tmp_path):
             sums = torch.zeros(8, dtype=torch.float64, device="cuda")
             ops.bce_dice_sums(logits, t, True, sums)
             dlogits = torch.empty_like(logits)
-            ops.bce_dice_bwd(logits, t, True, sums, 1.0, 1.0, 1.0, None, dlogits)
+            if global_dice:     # exact gradient of the global loss w.r.t. this shard's logits: BCE 1/(world n), Dice from the global sums
+                ops.bce_dice_bwd(logits, t, True, gsums, 1.0 / world, 1.0, 1.0, None, dlogits)
+            else:
+                ops.bce_dice_bwd(logits, t, True, sums, 1.0, 1.0, 1.0, None, dlogits)
             engine.net_backward(net, ctx, dlogits, opt.grads)
             acc += opt.flat_grad
         opt.flat_grad.copy_(acc)
-        opt.step(grad_scale=1.0 / world)
+        opt.step(grad_scale=1.0 if global_dice else 1.0 / world)
     ref = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).cpu()
     # atomics in the weight-gradient / BN reductions make the last bits run-to-run variable
     err = (outs[0]["flat"] - ref).norm() / ref.norm()
