@@ -29,6 +29,21 @@ TRAIN_GFLOP_PER_IMG = 201.658      # conv/convT/bmm MACs x2, fw
 METRIC = "train img/s @224^2 DFC-SA-Res-Block"
 WORKLOAD = ("DFC-SA-Res-Block P4/qk8 features[64,128,256,512], 224x224, batch 64 per GPU, "
             "fwd + bce_dice + bwd + clip(1.0) + SGD(mom .9, wd 1e-4)")
+SCALING, MICRO = "weak", 1
+
+
+def select_config(name, gpus):
+    """--config c2 (default): BASELINE.json configs[1], the headline (weak scaling, 64 images of 224^2 per GPU).
+    --config c4: configs[3], 512x512 with a GLOBAL batch of 256 over N GPUs (strong scaling: 256 / N images per GPU; above
+    64 per GPU the step runs as micro-batches of 64 with the gradients summed before one clip + SGD step, because the
+    saved activations of 128 images of 512^2 exceed the 180 GB of one B200)."""
+    global IMG, BATCH, TRAIN_GFLOP_PER_IMG, METRIC, WORKLOAD, SCALING, MICRO
+    if name == "c4":
+        IMG, BATCH, TRAIN_GFLOP_PER_IMG, SCALING = 512, 256 // gpus, 1052.650, "strong"
+        MICRO = max(1, BATCH // 64)
+        METRIC = "train img/s @512^2 DFC-SA-Res-Block, global batch 256"
+        WORKLOAD = ("DFC-SA-Res-Block P4/qk8 features[64,128,256,512], 512x512, GLOBAL batch 256 (strong scaling), "
+                    "fwd + bce_dice + bwd + clip(1.0) + SGD(mom .9, wd 1e-4)")
 
 
 def peaks():
@@ -38,45 +53,143 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def cpu_reference_step_time(steps, warmup, batch=4, threads=None):
-    """The reference's CPU implementation of the step (oracle port: torch fp32 on the host cores)."""
+def workload_config(batch, world, graph=True):
+    """`config` of the JSON line - identical for the dfcsa arm and the reference arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": batch, "global_batch": batch * world, "img": IMG, "pool_size": POOL,
+            "micro_batches": MICRO, "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": graph,
+            "l2": "activations touched per step (~20 GB at batch 64) exceed the 126 MB L2; two alternating input batches; no explicit flush"}
+
+
+def reference_step_fn(device, autocast_bf16=False):
+    """One training iteration of the UNMODIFIED reference (classes loaded from baseline/_ref/ by file path), written as
+    the reference's own loop does it (utils/trainer.py:120-151, optimizer from train.py:73-78):
+    zero_grad -> model(images) -> sigmoid -> calculate_metrics('bce_dice') -> backward -> clip_grad_norm_(1.0) -> SGD step."""
     import torch
-    from oracle import dfcsa_oracle as O
-    O.USE_ATEN_OPS = True           # same ATen calls as the reference (batch_norm, adaptive_avg_pool2d, interpolate)
+    from baseline import refload
+    ref, refm, _ = refload.load()
+    torch.manual_seed(0)
+    model = ref.UNetDFCSARes(3, 1, FEATURES, pool_size=POOL, ablation_on_qk_channels=QK)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("gamma"):
+                p.fill_(0.5)
+    model = model.to(device).train()
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    params = {"bce_weight": 0.5, "dice_weight": 0.5}
+
+    def step(images, masks):
+        opt.zero_grad()
+        with torch.autocast(device_type=torch.device(device).type, dtype=torch.bfloat16, enabled=autocast_bf16):
+            outputs = torch.sigmoid(model(images))
+        m = refm.calculate_metrics(outputs.float(), masks, "bce_dice", params)
+        m["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        opt.step()
+        return m
+    return step
+
+
+def cpu_reference_step_time(steps, warmup, batch=16, threads=None):
+    """The reference's CPU implementation of the step on the host cores: the unmodified reference classes from
+    baseline/_ref/ when they travelled with the snapshot (kind "reference"), else the oracle port (kind "port")."""
+    import torch
+    from baseline import refload
     # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
     torch.set_num_threads(threads or os.cpu_count() or 1)
-    torch.manual_seed(0)
-    sd = O.init_state_dict(features=FEATURES, qk=QK, seed=0)
-    for k in O.param_names(sd):
-        if k.endswith("gamma"):
-            sd[k].fill_(0.5)
-    img, mask = O.synthetic_batch(batch, IMG, IMG, seed=1)
-    bufs, times = None, []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        r = O.train_step(sd, bufs, img, mask, pool_size=POOL)
-        bufs = r["bufs"]
-        if i >= warmup:
-            times.append(time.perf_counter() - t0)
-    return times, batch, torch.get_num_threads()
+    from dfcsa.synthetic import synthetic_batch
+    img, mask = synthetic_batch(batch, IMG, IMG, seed=1)
+    times = []
+    if refload.available():
+        kind = "reference"
+        step = reference_step_fn("cpu")
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            step(img, mask)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        kind = "port"
+        from oracle import dfcsa_oracle as O
+        O.USE_ATEN_OPS = True           # same ATen calls as the reference (batch_norm, adaptive_avg_pool2d, interpolate)
+        sd = O.init_state_dict(features=FEATURES, qk=QK, seed=0)
+        for k in O.param_names(sd):
+            if k.endswith("gamma"):
+                sd[k].fill_(0.5)
+        bufs = None
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            r = O.train_step(sd, bufs, img, mask, pool_size=POOL)
+            bufs = r["bufs"]
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times, batch, torch.get_num_threads(), kind
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the step on this box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, min(args.steps, 3))
-    times, b, cores = cpu_reference_step_time(steps, 1)
+    b = args.ref_batch
+    times, b, cores, kind = cpu_reference_step_time(steps, 1, batch=b)
     per = sum(times) / len(times)
     val = b / per
+    sample = (f"{steps} full train steps of {b} images of the {args.batch}-image step (1 warm-up), torch fp32 on {cores} host threads; "
+              + ("unmodified reference classes from baseline/_ref" if kind == "reference" else "oracle port (baseline/_ref absent)"))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "img/s", "n_gpus": args.gpus, "steps": steps,
             "warmup": 1, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": f"batch {b} of the 64-image step on the host CPU"},
-            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": "port",
-                             "sample": f"{steps} full train steps of batch {b} (1 warm-up), torch fp32 on {cores} threads"},
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.batch, args.gpus, not args.no_graph),
+            "cpu_baseline": {"value": val, "unit": "img/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def reference_gpu_numbers(batch, steps=5, warmup=3, device="cuda"):
+    """The bar SURVEY.md 2.2 / 8(d7) names: the UNMODIFIED reference executed by eager PyTorch on this B200, same step, same
+    batch, (a) PyTorch defaults (fp32 tensors; cuDNN convolutions may use TF32) and (b) under torch.autocast(bfloat16).
+    Inputs resident on the device; CUDA events."""
+    import torch
+    from dfcsa.synthetic import synthetic_batch
+    imgs, masks = zip(*[synthetic_batch(16, IMG, IMG, seed=10 + j) for j in range((batch + 15) // 16)])
+    img, mask = torch.cat(imgs)[:batch].to(device), torch.cat(masks)[:batch].to(device)
+    out = {"batch": batch, "torch": torch.__version__, "cudnn_allow_tf32": bool(torch.backends.cudnn.allow_tf32),
+           "matmul_allow_tf32": bool(torch.backends.cuda.matmul.allow_tf32)}
+    for name, ac in (("tf32_default", False), ("bf16_autocast", True)):
+        try:
+            step = reference_step_fn(device, autocast_bf16=ac)
+            for _ in range(warmup):
+                step(img, mask)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                m = step(img, mask)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"img_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "loss": float(m["loss"]),
+                         "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
+            del step
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_reference_gpu(args):
+    """--impl reference-gpu: one JSON line with the eager-PyTorch-on-B200 numbers of the unmodified reference."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from baseline import refload
+    if not refload.available() or not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref or a CUDA device is missing"}))
+        return
+    r = reference_gpu_numbers(args.batch, steps=max(1, min(args.steps, 10)), warmup=max(args.warmup, 3))
+    best = max((v["img_per_s"] for v in r.values() if isinstance(v, dict) and "img_per_s" in v), default=None)
+    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": best, "unit": "img/s", "n_gpus": 1, "higher_is_better": True,
+                      "data": "synthetic", "config": workload_config(args.batch, 1, False), "reference_gpu": r}))
 
 
 class ClockSampler:
@@ -163,7 +276,8 @@ def run_dfcsa(args):
 
     # The step is replayed from a CUDA graph (Trainer.train_step_graphed, captured during warm-up): eager, the ~500
     # launches of a step cost ~35 ms of host time against ~45 ms of GPU time, too close to hide reliably.
-    step = tr.train_step if args.no_graph else tr.train_step_graphed
+    step_fn = tr.train_step if args.no_graph else tr.train_step_graphed
+    step = (lambda i, m: step_fn(i, m, MICRO)) if MICRO > 1 else step_fn
     # clocks / throttle reasons are sampled from the start of the warm-up (nvidia-smi needs a moment to start) to the
     # end of the timed region: every sample is under load
     sampler = ClockSampler(local) if rank == 0 else None
@@ -193,7 +307,7 @@ def run_dfcsa(args):
     barrier()
     p0.record()
     for i in range(args.steps):
-        tr.train_step(*devb[i % 2])
+        tr.train_step(*devb[i % 2], MICRO)
     p1.record()
     barrier()
     ms_prof = p0.elapsed_time(p1)
@@ -215,7 +329,7 @@ def run_dfcsa(args):
     # loss comes back to the host
     for i in range(args.steps):
         r = step(*host[i % 2]) if not args.no_graph else tr.train_step(host[i % 2][0].to(dev, non_blocking=True),
-                                                                      host[i % 2][1].to(dev, non_blocking=True))
+                                                                      host[i % 2][1].to(dev, non_blocking=True), MICRO)
         loss_host = r.stats[:1].cpu().item()          # device -> host read of the step's loss
     t1.record()
     barrier()
@@ -226,6 +340,7 @@ def run_dfcsa(args):
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t_all.tolist()
 
+    last_host = last.host() if last is not None else None
     if rank == 0:
         pk, pk_src = peaks()
         total_imgs = B * world * args.steps
@@ -239,7 +354,7 @@ def run_dfcsa(args):
         traffic, traffic_src = None, None
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic_r01.json")))["conv_tc"]
-            if B == BATCH:
+            if B == 64 and IMG == 224:
                 traffic = t["traffic_bytes_per_launch"]
                 traffic_src = ("profiles/ncu_gemm_traffic_r01.csv: dram__bytes_read.sum + dram__bytes_write.sum over the 86 conv_tc launches "
                                "of one step (33.2 GB; algorithmic operand + result bytes 34.4 GB)")
@@ -249,19 +364,27 @@ def run_dfcsa(args):
                       **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {})}
                   for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
         # CPU baseline: the oracle port of the same step on this box's host cores (bounded sample)
+        # (rank 0 at N = 1 only: under torchrun the other ranks would spin in the NCCL barrier on the same host cores)
         cpu = None
-        if not args.no_cpu_baseline:
-            times, cb, cores = cpu_reference_step_time(2, 1)
-            cpu = {"value": cb / min(times), "unit": "img/s", "cores": cores, "kind": "port",
-                   "sample": f"batch {cb} of the 64-image step, 1 warm-up + best of 2, torch fp32 oracle on {cores} threads"}
+        if not args.no_cpu_baseline and world == 1:
+            times, cb, cores, kind = cpu_reference_step_time(2, 1, batch=args.ref_batch)
+            cpu = {"value": cb / min(times), "unit": "img/s", "cores": cores, "kind": kind,
+                   "sample": f"{cb} images of the {B}-image step, 1 warm-up + best of 2 full train steps, torch fp32 on {cores} host threads ("
+                             + ("unmodified reference classes from baseline/_ref)" if kind == "reference" else "oracle port)")}
+        # the bar: the unmodified reference in eager PyTorch on this same GPU (after everything of ours has been timed)
+        ref_gpu = None
+        if not args.no_reference_gpu and world == 1:
+            from baseline import refload
+            if refload.available():
+                del tr, model, devb
+                torch.cuda.empty_cache()
+                ref_gpu = reference_gpu_numbers(B, steps=5, warmup=3, device=dev)
         in_bytes = sum(t.numel() * t.element_size() for t in host[0])
         line = {
             "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": SCALING, "vs_baseline": None,
             "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "img": IMG, "pool_size": POOL,
-                       "parallelism": f"dp{world}" if world > 1 else "single", "cuda_graph": not args.no_graph,
-                       "l2": "activations touched per step (~20 GB at batch 64) exceed the 126 MB L2; two alternating input batches; no explicit flush"},
+            "config": workload_config(B, world, not args.no_graph),
             "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
             "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4, "last_loss": loss_host},
             "gpu_launches": launches,
@@ -274,7 +397,8 @@ def run_dfcsa(args):
             "profiled_ms_per_step": ms_prof / args.steps,
             "kernels": shares,
             "cpu_baseline": cpu,
-            "last_step": last.host() if last is not None else None,
+            "reference_gpu": ref_gpu,
+            "last_step": last_host,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -296,14 +420,26 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="dfcsa", choices=["dfcsa", "reference"])
-    ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU (default: the BASELINE config, 64)")
+    ap.add_argument("--impl", default="dfcsa", choices=["dfcsa", "reference", "reference-gpu"])
+    ap.add_argument("--ref-batch", type=int, default=16, help="images per step of the bounded CPU sample (reference arm / cpu_baseline)")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the eager-PyTorch-on-this-GPU run of the unmodified reference")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"], help="BASELINE.json workload: c2 = 224^2, 64 per GPU (headline); "
+                    "c4 = 512^2, global batch 256 over the GPUs (strong scaling)")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the selected BASELINE config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--detail", default=None, help="write per-shape GEMM timings (JSON) to this path")
     args = ap.parse_args()
+    select_config(args.config, args.gpus)
+    if args.batch is None:
+        args.batch = BATCH
+    elif args.config == "c4":
+        global MICRO
+        MICRO = max(1, args.batch // 64)
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_dfcsa(args)
 

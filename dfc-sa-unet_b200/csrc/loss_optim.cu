@@ -127,6 +127,18 @@ sgd_step_kernel(const dfcsa_param_t* table, int n_tensors, long long max_n, cons
   }
 }
 
+// dst += src over a flat fp32 buffer (gradient accumulation across micro-batches)
+__global__ void __launch_bounds__(256) accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, long long n4, long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 d = reinterpret_cast<float4*>(dst)[i];
+    const float4 s = reinterpret_cast<const float4*>(src)[i];
+    d.x += s.x; d.y += s.y; d.z += s.z; d.w += s.w;
+    reinterpret_cast<float4*>(dst)[i] = d;
+  }
+  for (long long i = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
+
 }  // namespace
 }  // namespace dfcsa
 
@@ -192,5 +204,14 @@ extern "C" int dfcsa_sgd_step(const dfcsa_param_t* table_dev, int32_t n_tensors,
   dim3 grid(static_cast<unsigned>((max_n + kChunk - 1) / kChunk), n_tensors);
   sgd_step_kernel<<<grid, 256, 0, ST>>>(table_dev, n_tensors, max_n, sumsq, gscale, max_norm, lr, momentum, weight_decay, first_step);
   DFCSA_LAUNCH_CHECK("sgd_step_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_accumulate(float* dst, const float* src, int64_t n, void* stream) {
+  DFCSA_CHECK_ARG(dst && src && n > 0, "dfcsa_accumulate: bad args");
+  const bool v4 = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  const long long n4 = v4 ? n / 4 : 0;
+  accumulate_kernel<<<loss_blocks(n / 4 + 1), 256, 0, ST>>>(dst, src, n4, n);
+  DFCSA_LAUNCH_CHECK("accumulate_kernel");
   return DFCSA_OK;
 }

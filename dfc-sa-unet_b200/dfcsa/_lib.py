@@ -97,8 +97,9 @@ SYMBOLS = [
     "dfcsa_nchw_to_nhwc", "dfcsa_nhwc_to_nchw", "dfcsa_colsum", "dfcsa_cast2d",
     "dfcsa_bce_dice_sums", "dfcsa_bce_dice_finalize", "dfcsa_bce_dice_bwd",
     "dfcsa_bce_dice_sums_batched", "dfcsa_bce_dice_finalize_batched",
-    "dfcsa_grad_sumsq", "dfcsa_sgd_step",
+    "dfcsa_grad_sumsq", "dfcsa_sgd_step", "dfcsa_accumulate",
     "dfcsa_preprocess", "dfcsa_preprocess_workspace_bytes",
+    "dfcsa_resize_bilinear", "dfcsa_resize_bilinear_bwd", "dfcsa_adaptive_pool", "dfcsa_adaptive_pool_bwd",
 ]
 
 _lib = None

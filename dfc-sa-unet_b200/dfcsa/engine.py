@@ -807,15 +807,14 @@ def net_forward(net, x_nchw, training, save=True):
     if not x_nchw.is_cuda:
         raise RuntimeError("dfcsa: the model runs on CUDA tensors only (no CPU fallback)")
     B, Cin, H, W = x_nchw.shape
-    if H % 16 or W % 16:
-        raise NotImplementedError("dfcsa: H and W must be multiples of 16 (the reference's bilinear re-size fallback at "
-                                  "models/unet_dfc_sa_res.py:180-181 is not on the 224/512/1024 hot path)")
+    if H < 16 or W < 16:
+        raise ValueError("dfcsa: the network pools four times; H and W must be at least 16")
     x_nchw = x_nchw.contiguous().float()
     packs = NetPacks.get(net, keep)
     bps, pks = packs.bps, packs.pks
     f = [bps[i].C for i in range(4)]
     ctx = NetCtx() if keep else None
-    Hs = [H >> i for i in range(5)]
+    Hs = [H >> i for i in range(5)]      # MaxPool2d(2, 2) floors odd sides (reference :164-173)
     Ws = [W >> i for i in range(5)]
     Ms = [B * Hs[i] * Ws[i] for i in range(5)]
     x0 = _e((Ms[0], Cin), F32, dev)
@@ -840,9 +839,14 @@ def net_forward(net, x_nchw, training, save=True):
         tc = Ci_t % 64 == 0 and Co_t % 64 == 0
         wt = packs.up_fwd[j]
         segs = [(u, TAP_1x1)]
-        dst = cat[lvl][:, :f[lvl]]
+        # the ConvT output is (2h, 2w); when a side of this level is odd (inputs that are not multiples of 16) the
+        # reference re-sizes it to the skip tensor's size with bilinear interpolation (:180-181) - off the hot path
+        resized = (2 * Hs[lvl + 1], 2 * Ws[lvl + 1]) != (Hs[lvl], Ws[lvl])
+        dst = _e((4 * Ms[lvl + 1], f[lvl]), F16, dev) if resized else cat[lvl][:, :f[lvl]]
         ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, wt, 4 * Co_t, dst, out_mode=OUT_CONVT2x2, bias=up.bias.detach(),
                       backend=BACKEND_TC if (tc and ops.tc_eligible(segs, 4 * Co_t, dst)) else BACKEND_SIMT)
+        if resized:
+            ops.resize_bilinear(dst, B, 2 * Hs[lvl + 1], 2 * Ws[lvl + 1], cat[lvl][:, :f[lvl]], Hs[lvl], Ws[lvl])
         if keep:
             upk.append(packs.up_bwd[j])
             uin.append(u)
@@ -906,6 +910,10 @@ def net_backward(net, ctx, dlogits_nchw, grads, after_stage=None):
         up = ups[j]
         Ci_t, Co_t = up.weight.shape[0], up.weight.shape[1]
         dup = dcat[lvl][:, :f[lvl]]
+        if (2 * Hs[lvl + 1], 2 * Ws[lvl + 1]) != (Hs[lvl], Ws[lvl]):       # backward of the bilinear re-size (:180-181)
+            dup_t = _e((4 * Ms[lvl + 1], f[lvl]), BF16, dev)
+            ops.resize_bilinear_bwd(dup, B, 2 * Hs[lvl + 1], 2 * Ws[lvl + 1], dup_t, Hs[lvl], Ws[lvl])
+            dup = dup_t
         du = _e((Ms[lvl + 1], Ci_t), BF16, dev)
         segs = [(dup, TAP_2x2S2)]
         ops.conv_gemm(B, Hs[lvl + 1], Ws[lvl + 1], segs, ctx.upk[j], Ci_t, du, backend=_backend(segs, ctx.upk[j], Ci_t, du))

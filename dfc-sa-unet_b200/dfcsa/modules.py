@@ -12,8 +12,85 @@ import torch.nn as nn
 from . import engine, ops
 
 
+class _AttnParams:
+    """engine-side view of a stand-alone attention module (the fields engine.attention_forward / _backward read)."""
+
+    def __init__(self, att):
+        self.att, self.gamma = att, att.gamma
+        self.Wq, self.bq = att.query_conv.weight, att.query_conv.bias
+        self.Wk, self.bk = att.key_conv.weight, att.key_conv.bias
+        self.Wv, self.bv = att.value_conv.weight, att.value_conv.bias
+        self.C, self.Cq, self.P = self.Wv.shape[0], self.Wq.shape[0], att.pool_size
+
+
+class _AttnFunction(torch.autograd.Function):
+    """LightSelfAttention.forward on its own (reference models/unet_dfc_sa_res.py:20-39): adaptive pool -> q/k/v 1x1 convs,
+    softmax(q k^T), attn v (the same engine.attention_forward the fused block uses) -> gamma * bilinear_up(out) + x.
+    Inside DynamicFusionConvAttnBlock the pool and the up-sample are fused into the block's streaming kernels; this
+    stand-alone form uses the general dfcsa_adaptive_pool / dfcsa_resize_bilinear kernels (fp32 at the module boundary)."""
+
+    @staticmethod
+    def forward(ctx, x, att, need_grad, *params):
+        if not x.is_cuda:
+            raise RuntimeError("dfcsa: the attention module runs on CUDA tensors only (no CPU fallback)")
+        B, C, H, W = x.shape
+        dev = x.device
+        ap = _AttnParams(att)
+        if C != ap.C:
+            raise ValueError(f"dfcsa: attention built for {ap.C} channels got {C}")
+        P = ap.P if ap.P is not None else H
+        if ap.P is None and H != W:
+            raise NotImplementedError("dfcsa: full-resolution attention is implemented for square feature maps")
+        M, N = B * H * W, P * P
+        x2 = engine._e((M, C), torch.float32, dev)
+        ops.nchw_to_nhwc(x.contiguous().float(), x2, B, C, H, W)
+        pooled = engine._e((B * N, C), torch.float32, dev)
+        ops.adaptive_pool(x2, B, H, W, P, pooled)                                   # :24
+        plan, pk = engine.PackPlan(dev), {}
+        engine._pack_attention(ap, pk, need_grad, plan)
+        plan.run()
+        actx = engine.BlockCtx() if need_grad else None
+        o = engine.attention_forward(ap, pk, pooled, B, N, actx)                     # :28-34
+        out2 = engine._e((M, C), torch.float32, dev)
+        ops.resize_bilinear(o.view(B * N, C), B, P, P, out2, H, W, alpha=att.gamma.detach(), add=x2)     # :36-38
+        out = engine._e((B, C, H, W), torch.float32, dev)
+        ops.nhwc_to_nchw(out2, out, B, C, H, W)
+        if need_grad:
+            actx.o = o
+        ctx.ap, ctx.pk, ctx.actx, ctx.dims, ctx.params = ap, pk, actx, (B, C, H, W, P), params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        if ctx.actx is None:
+            raise RuntimeError("dfcsa: backward through an attention module that ran in no-grad mode")
+        B, C, H, W, P = ctx.dims
+        ap, actx = ctx.ap, ctx.actx
+        dev = dout.device
+        M, N = B * H * W, P * P
+        dy2 = engine._e((M, C), torch.float32, dev)
+        ops.nchw_to_nhwc(dout.contiguous().float(), dy2, B, C, H, W)
+        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        o2 = actx.o.view(B * N, C)
+        # d gamma = sum dout * up(o)
+        U = engine._e((M, C), torch.float32, dev)
+        ops.resize_bilinear(o2, B, P, P, U, H, W)
+        rd = engine._e((M, 1), torch.float32, dev)
+        ops.rowdot(dy2, U, rd)
+        ops.colsum(rd, grads[ap.gamma])
+        d_o = engine._e((B * N, C), torch.float32, dev)
+        ops.resize_bilinear_bwd(dy2, B, P, P, d_o, H, W, alpha=ap.gamma.detach())
+        dpooled = engine.attention_backward(ap, ctx.pk, actx, d_o, B, N, grads)
+        dx2 = engine._e((M, C), torch.float32, dev)
+        ops.adaptive_pool_bwd(dpooled, B, H, W, P, dx2, add=dy2)
+        dx = engine._e((B, C, H, W), torch.float32, dev)
+        ops.nhwc_to_nchw(dx2, dx, B, C, H, W)
+        return (dx, None, None) + tuple(grads[p] for p in ctx.params)
+
+
 class LightSelfAttention(nn.Module):
-    """reference models/unet_dfc_sa_res.py:5-39 (parameter container; the math runs inside the block kernels)."""
+    """reference models/unet_dfc_sa_res.py:5-39.  Inside a DFC-SA block the math runs fused in the block kernels; called on
+    its own (the reference class is an ordinary module) it runs through _AttnFunction."""
 
     def __init__(self, channels, pool_size=8, ablation_on_qk_channels=8):
         super().__init__()
@@ -24,7 +101,9 @@ class LightSelfAttention(nn.Module):
         self.gamma = nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
-        raise RuntimeError("dfcsa.LightSelfAttention is fused into DynamicFusionConvAttnBlock's kernels; call the block")
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        return _AttnFunction.apply(x, self, need_grad, *params)
 
 
 class FullResolutionAttention(nn.Module):
@@ -40,7 +119,9 @@ class FullResolutionAttention(nn.Module):
         self.gamma = nn.Parameter(torch.zeros(1))
 
     def forward(self, x):
-        raise RuntimeError("dfcsa.FullResolutionAttention is fused into FullResAttnDFCBlock's kernels; call the block")
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        return _AttnFunction.apply(x, self, need_grad, *params)
 
 
 class _BlockFunction(torch.autograd.Function):

@@ -367,3 +367,32 @@ def sgd_step(table, n_tensors, max_n, sumsq, gscale, max_norm, lr, momentum, wei
     L.call("dfcsa_sgd_step", L.ptr(table), n_tensors, _i64(max_n), L.ptr(sumsq), C.c_float(gscale), C.c_float(max_norm),
                                    C.c_float(lr), C.c_float(momentum), C.c_float(weight_decay), 1 if first_step else 0,
                                    L.stream())
+
+
+def resize_bilinear(src, B, Hi, Wi, dst, Ho, Wo, alpha=None, add=None):
+    """dst = alpha * bilinear(src: Hi x Wi -> Ho x Wo) + add on [M, C] NHWC views (dfcsa_resize_bilinear)."""
+    L.call("dfcsa_resize_bilinear", L.ptr(src), L.dt(src), _i64(_mat(src)), B, Hi, Wi, src.shape[1], L.ptr(dst), L.dt(dst), _i64(_mat(dst)),
+           Ho, Wo, L.ptr(alpha), L.ptr(add), L.dt(add) if add is not None else 0, _i64(_mat(add) if add is not None else 0), L.stream())
+
+
+def resize_bilinear_bwd(ddst, B, Hi, Wi, dsrc, Ho, Wo, alpha=None):
+    """dsrc = alpha * bilinear^T(ddst)  (dfcsa_resize_bilinear_bwd); ddst on the Ho x Wo grid, dsrc on Hi x Wi."""
+    L.call("dfcsa_resize_bilinear_bwd", L.ptr(ddst), L.dt(ddst), _i64(_mat(ddst)), B, Hi, Wi, dsrc.shape[1], L.ptr(dsrc), L.dt(dsrc),
+           _i64(_mat(dsrc)), Ho, Wo, L.ptr(alpha), L.stream())
+
+
+def adaptive_pool(src, B, H, W, P, pooled):
+    """pooled [B*P*P, C] fp32 = adaptive_avg_pool2d(src, P)  (dfcsa_adaptive_pool)."""
+    L.call("dfcsa_adaptive_pool", L.ptr(src), L.dt(src), _i64(_mat(src)), B, H, W, src.shape[1], P, L.ptr(pooled), L.stream())
+
+
+def adaptive_pool_bwd(dpooled, B, H, W, P, dst, add=None):
+    """dst = add + adaptive_avg_pool2d^T(dpooled)  (dfcsa_adaptive_pool_bwd)."""
+    L.call("dfcsa_adaptive_pool_bwd", L.ptr(dpooled), B, H, W, dst.shape[1], P, L.ptr(add), L.dt(add) if add is not None else 0,
+           _i64(_mat(add) if add is not None else 0), L.ptr(dst), L.dt(dst), _i64(_mat(dst)), L.stream())
+
+
+def accumulate(dst, src):
+    """dst += src on flat fp32 buffers (dfcsa_accumulate)."""
+    assert dst.dtype == torch.float32 and src.dtype == torch.float32 and dst.numel() == src.numel()
+    L.call("dfcsa_accumulate", L.ptr(dst), L.ptr(src), _i64(dst.numel()), L.stream())

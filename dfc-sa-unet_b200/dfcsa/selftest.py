@@ -77,6 +77,33 @@ def forward_backward_parity(features=(64, 128, 256, 512), pool_size=4, qk=8, B=2
     }
 
 
+def eval_parity(features=(64, 128, 256, 512), pool_size=4, qk=8, B=2, H=224, W=224, gamma=0.5, seed=0):
+    """Eval-mode (running-statistics BatchNorm, reference inference.py:100) logits of dfcsa vs the oracle.  The running
+    statistics are a realistic trained state: exactly the batch statistics of one synthetic batch (one oracle training
+    forward from the (0, 1) initial buffers, momentum step undone); the compared forward runs on a DIFFERENT batch."""
+    O = _oracle()
+    from .modules import UNetDFCSARes
+    torch.manual_seed(seed)
+    model = UNetDFCSARes(3, 1, list(features), pool_size=pool_size, ablation_on_qk_channels=qk)
+    set_gamma(model, gamma)
+    sd = oracle_state(model)
+    img, _ = O.synthetic_batch(B, H, W, seed=1)
+    with torch.no_grad():
+        O.unet_forward(img, sd, pool_size, training=True)
+        for k in sd:
+            if k.endswith("running_mean"):
+                sd[k] = sd[k] / 0.1
+            elif k.endswith("running_var"):
+                sd[k] = (sd[k] - 0.9) / 0.1
+        img2, _ = O.synthetic_batch(B, H, W, seed=2)
+        ref = O.unet_forward(img2, sd, pool_size, training=False)
+        model.load_state_dict(sd)
+        model = model.cuda().eval()
+        logits = model(img2.cuda())
+        torch.cuda.synchronize()
+    return {"logit_maxabs": float((logits.cpu() - ref).abs().max()), "logit_ref_absmax": float(ref.abs().max())}
+
+
 def smoke():
     if not torch.cuda.is_available():
         raise RuntimeError("dfcsa smoke() needs a CUDA device")

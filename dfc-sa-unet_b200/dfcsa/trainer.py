@@ -142,11 +142,47 @@ class Trainer:
             dist.broadcast(self.optimizer.flat_mom, src=0)
 
     # ------------------------------------------------------------------------------------------------------------
-    def train_step(self, images, masks):
-        """reference utils/trainer.py:116-151 for one batch already on the device.  Returns StepResult (device scalars)."""
+    def train_step(self, images, masks, micro_batches=1):
+        """reference utils/trainer.py:116-151 for one batch already on the device.  Returns StepResult (device scalars).
+
+        micro_batches = k > 1 (not in the reference): the batch is run as k consecutive forward/backward passes whose
+        gradients are summed before ONE clip + SGD step - for per-GPU batches whose activations exceed one forward's memory
+        (C4: 128 / 256 images of 512^2 per GPU).  Loss, BatchNorm statistics and Dice are then those of each micro-batch
+        (the gradient is the mean of the k micro-batch gradients, the returned stats their mean)."""
         net, opt = self.model, self.optimizer
         net.train()
         opt.zero_grad()
+        k = int(micro_batches)
+        if k <= 1:
+            stats = self._forward_backward(images, masks, self._reducer.reduce if self.world > 1 else None)
+        else:
+            if images.shape[0] % k:
+                raise ValueError(f"dfcsa: batch of {images.shape[0]} does not split into {k} equal micro-batches")
+            if getattr(self, "_accum", None) is None:
+                self._accum = torch.empty_like(opt.flat_grad)
+            stats = None
+            for i, (im, mk) in enumerate(zip(images.chunk(k), masks.chunk(k))):
+                st = self._forward_backward(im, mk, None)
+                stats = st if stats is None else stats + st
+                if i == 0:
+                    self._accum.copy_(opt.flat_grad)
+                elif i < k - 1:
+                    ops.accumulate(self._accum, opt.flat_grad)
+                if i < k - 1:
+                    opt.flat_grad.zero_()           # the kernels expect zero-initialised gradient tensors
+            ops.accumulate(opt.flat_grad, self._accum)
+            stats = stats / k
+            if self.world > 1:                      # all buckets after the last micro-batch (1 ms of NVLink time per step)
+                for b in range(len(self._reducer.ranges)):
+                    self._reducer.reduce(b)
+        if self.world > 1:
+            self._reducer.finish()
+        opt.step(grad_scale=1.0 / (self.world * max(k, 1)))
+        return StepResult(stats)
+
+    def _forward_backward(self, images, masks, after_stage):
+        """forward, sigmoid + bce_dice, backward of one (micro-)batch into the optimizer's flat gradient buffer."""
+        net, opt = self.model, self.optimizer
         logits, ctx = engine.net_forward(net, images, True, save=True)
         dev = logits.device
         n = logits.numel()
@@ -165,35 +201,29 @@ class Trainer:
         ops.bce_dice_finalize(sums, n, self.w_bce, self.w_dice, 1.0, stats)
         dlogits = torch.empty_like(logits)
         ops.bce_dice_bwd(logits, t, True, sums, self.w_bce, w_dice_bwd, 1.0, None, dlogits)
-        if self.world == 1:
-            engine.net_backward(net, ctx, dlogits, opt.grads)
-            opt.step()
-        else:
-            engine.net_backward(net, ctx, dlogits, opt.grads, after_stage=self._reducer.reduce)
-            self._reducer.finish()
-            opt.step(grad_scale=1.0 / self.world)
-        return StepResult(stats)
+        engine.net_backward(net, ctx, dlogits, opt.grads, after_stage=after_stage)
+        return stats
 
-    def train_step_graphed(self, images, masks):
+    def train_step_graphed(self, images, masks, micro_batches=1):
         """train_step replayed from a CUDA graph (one graph per input shape).  Every libdfcsa entry point only enqueues
         work and all buffers come from PyTorch's allocator, so the ~600 launches of a step are captured as they are;
         replaying them removes the host-side launch cost that dominates small batches (the reference's batch-4 config).
         The first two calls per shape run eagerly (lazy one-time state settles: packed-weight buffers, momentum
         initialisation, kernel attributes); the third call captures and replays.  images / masks may live in (pinned)
         host memory: they are copied straight into the graph's static input buffers."""
-        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype)
+        key = (tuple(images.shape), images.dtype, tuple(masks.shape), masks.dtype, int(micro_batches))
         from . import _lib
         g = self._graphs.setdefault(key, [0, None, None, None, None, 0])
         g[0] += 1
         if g[0] <= 2:
-            return self.train_step(images.to(self.device, non_blocking=True), masks.to(self.device, non_blocking=True))
+            return self.train_step(images.to(self.device, non_blocking=True), masks.to(self.device, non_blocking=True), micro_batches)
         if g[1] is None:
             g[2], g[3] = images.to(self.device).clone(), masks.to(self.device).clone()
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.LAUNCHES
             with torch.cuda.graph(graph):
-                g[4] = self.train_step(g[2], g[3]).stats
+                g[4] = self.train_step(g[2], g[3], micro_batches).stats
             g[5] = _lib.LAUNCHES - n0        # libdfcsa kernels inside the graph (capturing does not run them)
             _lib.LAUNCHES = n0
             g[1] = graph

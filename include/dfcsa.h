@@ -337,7 +337,31 @@ int dfcsa_colsum(const void* x, int x_dtype, int64_t ld, int64_t M, int32_t C, f
 /* y = cast(x) elementwise on [M, C] matrices with pitches */
 int dfcsa_cast2d(const void* x, int x_dtype, int64_t ld_x, void* y, int y_dtype, int64_t ld_y,
                  int64_t M, int32_t C, void* stream);
-/* dx[m, c] (+)= maxpool2x2 backward of dyp routed to the argmax of y (used when a block is run stand-alone) */
+
+/* ------------------------------------------------------------------------------------------------------------
+ * General bilinear re-size and adaptive average pool on NHWC tensors of any storage dtype (one thread per output, no
+ * tuning: both users are OFF the 224 / 512 / 1024 hot path).
+ *   - the reference's re-size after a ConvTranspose2d whose output does not match the skip tensor, i.e. inputs whose side
+ *     is not a multiple of 16 (models/unet_dfc_sa_res.py:180-181, F.interpolate(..., mode="bilinear", align_corners=False));
+ *   - LightSelfAttention / FullResolutionAttention called as modules of their own (models/unet_dfc_sa_res.py:20-39):
+ *     adaptive_avg_pool2d (:24) without the BatchNorm + ReLU the block kernels fuse in front of it, and
+ *     gamma * interpolate(out) + x (:36-38).
+ * resize:      dst[b,y,x,c] = alpha * bilinear(src: Hi x Wi -> Ho x Wo)[b,y,x,c] + add[b,y,x,c]   (alpha: optional device
+ *              scalar, add: optional tensor laid out like dst)
+ * resize_bwd:  dsrc = alpha * bilinear^T(ddst)          (every element of dsrc is written)
+ * pool:        pooled[b,i,j,c] (fp32, dense [B,P,P,C]) = adaptive_avg_pool2d(src, P)
+ * pool_bwd:    dst = add + adaptive_avg_pool2d^T(dpooled)   (add optional)
+ * ---------------------------------------------------------------------------------------------------------- */
+int dfcsa_resize_bilinear(const void* src, int src_dtype, int64_t ld_src, int32_t B, int32_t Hi, int32_t Wi, int32_t C,
+                          void* dst, int dst_dtype, int64_t ld_dst, int32_t Ho, int32_t Wo, const float* alpha,
+                          const void* add, int add_dtype, int64_t ld_add, void* stream);
+int dfcsa_resize_bilinear_bwd(const void* ddst, int ddst_dtype, int64_t ld_ddst, int32_t B, int32_t Hi, int32_t Wi, int32_t C,
+                              void* dsrc, int dsrc_dtype, int64_t ld_dsrc, int32_t Ho, int32_t Wo, const float* alpha,
+                              void* stream);
+int dfcsa_adaptive_pool(const void* src, int src_dtype, int64_t ld_src, int32_t B, int32_t H, int32_t W, int32_t C, int32_t P,
+                        float* pooled, void* stream);
+int dfcsa_adaptive_pool_bwd(const float* dpooled, int32_t B, int32_t H, int32_t W, int32_t C, int32_t P, const void* add,
+                            int add_dtype, int64_t ld_add, void* dst, int dst_dtype, int64_t ld_dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * bce_dice loss (reference utils/trainer.py:124 sigmoid; utils/metrics.py:74-78 BCELoss + dice_loss :19-24;
@@ -373,6 +397,10 @@ int dfcsa_grad_sumsq(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t 
 int dfcsa_sgd_step(const dfcsa_param_t* table_dev, int32_t n_tensors, int64_t max_n, const double* sumsq,
                    float gscale, float max_norm, float lr, float momentum, float weight_decay, int first_step,
                    void* stream);
+
+/* dst[i] += src[i] over flat fp32 buffers: gradient accumulation across the micro-batches of one optimizer step (the C4
+ * configuration's 128 / 256 images per GPU at 512^2 exceed one forward's activation memory; not in the reference) */
+int dfcsa_accumulate(float* dst, const float* src, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------------
  * GPU-side data path: the reference's per-sample transform chain, utils/data_loader.py:25-74

@@ -16,6 +16,13 @@ Fixtures (float32 .npz, a few hundred KB in total):
                  / UNet_BothStandardConv / UNet_AttentionOnly / UNet_AdditionFusion / UNet_ConcatFusion (features
                  [8,8,16,16], pool 4) on 2x3x32x32, gamma=0.5: weights, image, mask,
                  logits, bce_dice loss and all parameter gradients, per model
+  round2.npz     (python tests/golden/make_golden.py round2) fixtures added in round 2, all from the unmodified reference:
+                 lsa16/, lsa64/   LightSelfAttention called on its own (16 ch, pool 4 on 14x14; 64 ch, pool 8 on 20x20), gamma
+                                  0.5: x, r, out, d x and parameter gradients of sum(out * r)
+                 odd/             UNetDFCSARes([4,8,16,32], pool 4, qk 4) on 2x3x76x92 - NOT multiples of 16, so two of the
+                                  four ConvTranspose outputs go through the bilinear re-size of :180-181: logits, loss, grads
+                 n64/             the same network on 4x3x64x64 (64 samples per channel in the bottleneck BatchNorms)
+                 p16/             pool_size 16 on 2x3x64x64: pooled map larger than the feature map at levels 4-5 (8 -> 16, 4 -> 16)
 """
 import importlib.util
 import os
@@ -91,9 +98,46 @@ def ablations():
     print("ablations.npz written")
 
 
+def round2():
+    ref, refm, refa = load_reference()
+    d = {}
+    for tag, C, P, hw in (("lsa16", 16, 4, 14), ("lsa64", 64, 8, 20)):
+        torch.manual_seed(3)
+        att = ref.LightSelfAttention(C, pool_size=P, ablation_on_qk_channels=8)
+        with torch.no_grad():
+            att.gamma.fill_(0.5)
+        x = torch.randn(2, C, hw, hw, requires_grad=True)
+        r = torch.randn(2, C, hw, hw)
+        out = att(x)
+        (out * r).sum().backward()
+        d.update(sd_np(att.state_dict(), f"{tag}/w:"))
+        d.update({f"{tag}/x": x.detach().numpy(), f"{tag}/r": r.numpy(), f"{tag}/out": out.detach().numpy(), f"{tag}/dx": x.grad.numpy()})
+        d.update({f"{tag}/g:" + k: p.grad.numpy() for k, p in att.named_parameters()})
+    for tag, P, B, H, W, seed in (("odd", 4, 2, 76, 92, 21), ("n64", 4, 4, 64, 64, 22), ("p16", 16, 2, 64, 64, 23)):
+        torch.manual_seed(0)
+        net = ref.UNetDFCSARes(3, 1, [4, 8, 16, 32], pool_size=P, ablation_on_qk_channels=4)
+        with torch.no_grad():
+            for n, p in net.named_parameters():
+                if n.endswith("gamma"):
+                    p.fill_(0.5)
+        d.update(sd_np(net.state_dict(), "net/w:"))        # same seed, and the shapes do not depend on pool_size: stored once
+        img, mask = structured(B, H, W, seed)
+        net.train()
+        logits = net(img)
+        m = refm.calculate_metrics(torch.sigmoid(logits), mask, "bce_dice", {})
+        m["loss"].backward()
+        d.update({f"{tag}/image": img.numpy(), f"{tag}/mask": mask.numpy(), f"{tag}/logits": logits.detach().numpy(),
+                  f"{tag}/loss": np.float32(m["loss"].item())})
+        d.update({f"{tag}/g:" + k: p.grad.numpy() for k, p in net.named_parameters()})
+    np.savez_compressed(os.path.join(HERE, "round2.npz"), **d)
+    print("round2.npz written")
+
+
 def main():
     if sys.argv[1:] == ["ablations"]:
         return ablations()
+    if sys.argv[1:] == ["round2"]:
+        return round2()
     ref, refm, refa = load_reference()
     torch.manual_seed(0)
 
