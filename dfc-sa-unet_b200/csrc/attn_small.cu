@@ -55,7 +55,7 @@ attn_small_fwd_kernel(const float* __restrict__ qkv, long long ld, int N, int Cq
 
 __global__ void __launch_bounds__(256)
 attn_small_bwd_kernel(const float* __restrict__ qkv, long long ld, const float* __restrict__ attn,
-                      const float* __restrict__ d_o, int N, int Cq, int C, float* __restrict__ dqkv) {
+                      const float* __restrict__ d_o, int N, int Cq, int C, float* __restrict__ dqkv, float* dbq, float* dbk, float* dbv) {
   __shared__ float sA[kMaxN][kMaxN + 1];    // probabilities
   __shared__ float sD[kMaxN][kMaxN + 1];    // d attn, then dS
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,6 +91,12 @@ attn_small_bwd_kernel(const float* __restrict__ qkv, long long ld, const float* 
     }
 #pragma unroll
     for (int j = 0; j < kMaxN; ++j) if (j < N) dbase[static_cast<long long>(j) * ld + 2 * Cq + c] = acc[j];
+    if (dbv != nullptr) {      // bias gradient of the value conv: column sum of dv over tokens (and, by atomics, images)
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxN; ++j) if (j < N) t += acc[j];
+      atomicAdd(dbv + c, t);
+    }
   }
   __syncthreads();
   // dq[i][c] = sum_j dS[i][j] k[j][c];  dk[j][c] = sum_i dS[i][j] q[i][c]
@@ -103,6 +109,7 @@ attn_small_bwd_kernel(const float* __restrict__ qkv, long long ld, const float* 
     }
     dbase[static_cast<long long>(r) * ld + c] = dq;
     dbase[static_cast<long long>(r) * ld + Cq + c] = dk;
+    if (dbq != nullptr) { atomicAdd(dbq + c, dq); atomicAdd(dbk + c, dk); }
   }
 }
 
@@ -121,10 +128,11 @@ extern "C" int dfcsa_attn_small_fwd(const float* qkv, int64_t ld, int32_t B, int
 }
 
 extern "C" int dfcsa_attn_small_bwd(const float* qkv, int64_t ld, const float* attn, const float* d_o, int32_t B, int32_t N,
-                                    int32_t Cq, int32_t C, float* dqkv, void* stream) {
+                                    int32_t Cq, int32_t C, float* dqkv, float* dbq, float* dbk, float* dbv, void* stream) {
   DFCSA_CHECK_ARG(qkv && attn && d_o && dqkv && B > 0 && N > 0 && N <= kMaxN && Cq > 0 && C > 0 && ld >= 2 * Cq + C,
                   "dfcsa_attn_small_bwd: bad args (N must be <= 32)");
-  attn_small_bwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(qkv, ld, attn, d_o, N, Cq, C, dqkv);
+  DFCSA_CHECK_ARG((dbq == nullptr) == (dbk == nullptr), "dfcsa_attn_small_bwd: dbq and dbk go together");
+  attn_small_bwd_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(qkv, ld, attn, d_o, N, Cq, C, dqkv, dbq, dbk, dbv);
   DFCSA_LAUNCH_CHECK("attn_small_bwd_kernel");
   return DFCSA_OK;
 }

@@ -247,6 +247,22 @@ __global__ void bn_param_grads_kernel(const double* red, int C, float* dgamma, f
   dgamma[c] = static_cast<float>(red[C + c]);
 }
 
+struct BlockGradPtrs { float* g[4]; float* b[4]; float* drs; float* dgam; };
+__global__ void block_param_grads_kernel(const double* red, int C, BlockGradPtrs o) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (o.b[i] != nullptr) o.b[i][c] = static_cast<float>(red[2 * i * C + c]);
+      if (o.g[i] != nullptr) o.g[i][c] = static_cast<float>(red[(2 * i + 1) * C + c]);
+    }
+  }
+  if (c == 0) {
+    if (o.drs != nullptr) *o.drs = static_cast<float>(red[8 * C]);
+    if (o.dgam != nullptr) *o.dgam = static_cast<float>(red[8 * C + 1]);
+  }
+}
+
 // =============================================================================================
 // forward: bn+relu -> adaptive pool (separable)
 // =============================================================================================
@@ -1100,6 +1116,17 @@ extern "C" int dfcsa_bn_param_grads(const double* red, int32_t C, float* dgamma,
   DFCSA_CHECK_ARG(red && dgamma && dbeta && C > 0, "dfcsa_bn_param_grads: bad args");
   bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST>>>(red, C, dgamma, dbeta);
   DFCSA_LAUNCH_CHECK("bn_param_grads_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_block_param_grads(const double* red, int32_t C, float* dg1, float* db1, float* dg2, float* db2, float* dg3,
+                                       float* db3, float* dg4, float* db4, float* drs, float* dgam, void* stream) {
+  DFCSA_CHECK_ARG(red && C > 0, "dfcsa_block_param_grads: bad args");
+  BlockGradPtrs o;
+  o.g[0] = dg1; o.b[0] = db1; o.g[1] = dg2; o.b[1] = db2; o.g[2] = dg3; o.b[2] = db3; o.g[3] = dg4; o.b[3] = db4;
+  o.drs = drs; o.dgam = dgam;
+  block_param_grads_kernel<<<(C + 127) / 128, 128, 0, ST>>>(red, C, o);
+  DFCSA_LAUNCH_CHECK("block_param_grads_kernel");
   return DFCSA_OK;
 }
 

@@ -16,10 +16,10 @@
 // 0-3 - idle until the epilogue - rewrite every landed x box to bf16 in place in shared memory before the MMA warp
 // reads it.  That replaces the bf16 "shadow" copy of every activation the forward pass used to write to HBM.
 // The kernel is bound by the 128 B/clk shared-memory port (profiles/ncu_wgrad_tc_r01_final.csv): operand re-reads of every
-// UMMA + that rewrite + the TMA writes.  wgrad_tc_kernel<true> (DFCSA_WGRAD_XREG=1; written at the end of round 1 without
-// GPU time left, NOT yet run on a GPU and therefore off by default) moves x through registers instead: global load ->
-// convert -> one swizzled store.  The default instantiation <false> compiles to the same SASS as before the template.
-// To try it: DFCSA_WGRAD_XREG=1 python -m pytest tests/test_gpu_conv.py -k wgrad, then bench.py.
+// UMMA + that rewrite + the TMA writes.  Measured dead end (round 2, profiles/bench_r02_a_xreg.json): moving x through
+// registers instead (four warps: 16-byte global loads two pixel blocks ahead -> convert -> one swizzled store) was correct
+// but 4x SLOWER (32.3 ms against 7.7 ms per step over the 56 launches) - 128 threads cannot keep enough bytes in flight to
+// replace a TMA box; the variant was removed.
 #include "common.cuh"
 #include <algorithm>
 #include <mutex>
@@ -57,16 +57,8 @@ struct WgradTcArgs {
   float* dw2; long long ld_dw2;
   const float* alpha2;
   int vec_red2;
-  // experimental (DFCSA_WGRAD_XREG=1, off by default): the x boxes do not come through TMA; the four conversion warps
-  // read them with 16-byte global loads two pixel blocks ahead, convert fp16 -> bf16 in registers and store them once in
-  // the swizzled layout - one shared-memory pass for x instead of three (TMA write + read + rewrite)
-  int xreg;
-  const __half* xg; long long ld_x;      // x as a pixel-major matrix
-  int img_w, img_h;                      // extents of the pixel grid the boxes are cut from
-  long long m_tot;
 };
 
-template <bool XREG>
 __global__ void __launch_bounds__(192, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const __grid_constant__ CUtensorMap map_dy2, const __grid_constant__ WgradTcArgs a) {
@@ -126,7 +118,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   if (warp == 4) {
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
-    const uint32_t tx_bytes = static_cast<uint32_t>(n_boxes_a * a.box_bytes + (XREG ? 0 : n_boxes_b * a.x_tx_bytes));
+    const uint32_t tx_bytes = static_cast<uint32_t>(n_boxes_a * a.box_bytes + n_boxes_b * a.x_tx_bytes);
     for (long long pb = pb_beg; pb < pb_end; ++pb) {
       const int tw = static_cast<int>(pb % a.tiles_w);
       const long long r = pb / a.tiles_w;
@@ -146,15 +138,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           else
             tma_load_5d(sa + j * kBoxBytes, &map_dy, &full_bar[stage], n0 + j * 64, w0, h0, tb, 0);
         }
-        if constexpr (!XREG) {
-          for (int j = 0; j < n_boxes_b; ++j) {
-            if (a.dw3)   // tap == dh: rows h0+dh-1 .., columns w0-1 .. w0+16 (halo of one pixel on each side)
-              tma_load_5d(sb + j * a.x_box_bytes, &map_x, &full_bar[stage], c0 + j * 64, w0 - 1, h0 + tap - 1, tb, 0);
-            else
-              tma_load_5d(sb + j * kBoxBytes, &map_x, &full_bar[stage], c0 + j * 64, w0, h0, tb, 0);
-          }
-        } else {
-          (void)sb;
+        for (int j = 0; j < n_boxes_b; ++j) {
+          if (a.dw3)   // tap == dh: rows h0+dh-1 .., columns w0-1 .. w0+16 (halo of one pixel on each side)
+            tma_load_5d(sb + j * a.x_box_bytes, &map_x, &full_bar[stage], c0 + j * 64, w0 - 1, h0 + tap - 1, tb, 0);
+          else
+            tma_load_5d(sb + j * kBoxBytes, &map_x, &full_bar[stage], c0 + j * 64, w0, h0, tb, 0);
         }
       }
       __syncwarp();
@@ -165,12 +153,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     int stage = 0; uint32_t phase = 0;
     bool first = true;
     for (long long pb = pb_beg; pb < pb_end; ++pb) {
-      if constexpr (XREG) {     // dy arrives by TMA (full_bar), x from the loader warps (cvt_bar)
-        mbar_wait(&full_bar[stage], phase);
-        mbar_wait(&cvt_bar[stage], phase);
-      } else {
-        mbar_wait(a.cvt_x ? &cvt_bar[stage] : &full_bar[stage], phase);
-      }
+      mbar_wait(a.cvt_x ? &cvt_bar[stage] : &full_bar[stage], phase);
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
@@ -203,92 +186,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     if (lane == 0) umma_commit(&done_bar);
     __syncwarp();
   } else {
-    if constexpr (XREG) {
-      // ===================== x: global -> registers -> bf16 -> swizzled shared memory =====================
-      // 16-byte chunk idx = (box j, box row r, chunk q) with q fastest: a thread keeps q = threadIdx.x & 7 and walks
-      // rows rl = (threadIdx.x >> 3) + 16 i over the boxes; the row's pixel follows from the block geometry, a pixel
-      // outside the image (halo, ragged patch, tail block) is stored as zeros like TMA's fill.
-      constexpr int kMaxIt = 16;                       // 4 boxes x 64 rows x 8 chunks / 128 threads
-      const int rows = a.dw3 ? 72 : 64;
-      const int n_rows = n_boxes_b * rows;             // box rows of one stage
-      const int q = threadIdx.x & 7, rl0 = threadIdx.x >> 3;
-      const int x_pitch = a.dw3 ? a.x_box_bytes : kBoxBytes;
-      auto issue = [&](long long pb, uint4 (&buf)[kMaxIt]) {
-        const int tw = static_cast<int>(pb % a.tiles_w);
-        const long long rr = pb / a.tiles_w;
-        const int th = static_cast<int>(rr % a.tiles_h);
-        const int tb = static_cast<int>(rr / a.tiles_h);
-        const int w0 = tw * a.w_t, h0 = th * a.h_t;
-#pragma unroll
-        for (int i = 0; i < kMaxIt; ++i) {
-          const int rl = rl0 + 16 * i;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (rl < n_rows) {
-            const int j = rl / rows, r = rl - j * rows;
-            long long m; bool ok;
-            if (a.dw3) {
-              const int hh = r / 18, ww = r - hh * 18;
-              const int w = w0 - 1 + ww, h = h0 + tap - 1 + hh;
-              ok = w >= 0 && w < a.img_w && h >= 0 && h < a.img_h;
-              m = (static_cast<long long>(tb) * a.img_h + h) * a.img_w + w;
-            } else if (a.dy_mode == DFCSA_TAP_2x2S2) {
-              const int hh = r / a.w_t, ww = r - hh * a.w_t;
-              const int w = w0 + ww, h = h0 + hh;
-              ok = hh < a.h_t && w < a.img_w && h < a.img_h;
-              m = static_cast<long long>(h) * a.img_w + w;
-            } else {
-              m = pb * 64 + r;
-              ok = m < a.m_tot;
-            }
-            if (ok) v = __ldg(reinterpret_cast<const uint4*>(a.xg + m * a.ld_x + c0 + j * 64 + q * 8));
-          }
-          buf[i] = v;
-        }
-      };
-      auto store = [&](int stage, const uint4 (&buf)[kMaxIt]) {
-        uint8_t* sb = smem + stage * kStageBytes + kABytes;
-#pragma unroll
-        for (int i = 0; i < kMaxIt; ++i) {
-          const int rl = rl0 + 16 * i;
-          if (rl < n_rows) {
-            const int j = rl / rows, r = rl - j * rows;
-            uint4 v = buf[i];
-            uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[e]));
-              const __nv_bfloat162 bb = __floats2bfloat162_rn(f.x, f.y);
-              w[e] = *reinterpret_cast<const uint32_t*>(&bb);
-            }
-            // 128-byte swizzle on absolute addresses: every box starts on a 1024-byte boundary
-            *reinterpret_cast<uint4*>(sb + j * x_pitch + r * 128 + ((q ^ (r & 7)) << 4)) = v;
-          }
-        }
-      };
-      uint4 buf0[kMaxIt], buf1[kMaxIt];
-      const long long nblk = pb_end - pb_beg;
-      if (nblk > 0) issue(pb_beg, buf0);
-      if (nblk > 1) issue(pb_beg + 1, buf1);
-      int stage = 0; uint32_t phase = 0;
-      for (long long k = 0; k < nblk; k += 2) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        store(stage, buf0);
-        fence_proxy_async();
-        mbar_arrive(&cvt_bar[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
-        if (k + 2 < nblk) issue(pb_beg + k + 2, buf0);
-        if (k + 1 < nblk) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          store(stage, buf1);
-          fence_proxy_async();
-          mbar_arrive(&cvt_bar[stage]);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
-          if (k + 3 < nblk) issue(pb_beg + k + 3, buf1);
-        }
-      }
-    }
     // ===================== x: fp16 -> bf16 in place (only when the operand formats differ) =====================
-    if (!XREG && a.cvt_x) {
+    if (a.cvt_x) {
       int stage = 0; uint32_t phase = 0;
       const int n16 = n_boxes_b * a.x_box_bytes / 16;
       for (long long pb = pb_beg; pb < pb_end; ++pb) {
@@ -517,22 +416,12 @@ int conv_wgrad_tc(const dfcsa_wgrad_params_t* p, cudaStream_t stream) {
   const int smem_bytes = a.stages * a.stage_bytes + 1024;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(g_attr_once, [] {
-    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (4 * kBoxBytes + kBMaxBytes) + 1024);  // == 4 stages of the 128-wide tile
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (4 * kBoxBytes + kBMaxBytes) + 1024);
+    attr_err = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * (4 * kBoxBytes + kBMaxBytes) + 1024);  // == 4 stages of the 128-wide tile
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(wgrad_tc_kernel)");
   const long long grid = items * a.splits;
   DFCSA_CHECK_ARG(grid < (1LL << 31), "conv_wgrad_tc: grid too large");
-  static const bool want_xreg = [] { const char* e = getenv("DFCSA_WGRAD_XREG"); return e && atoi(e) != 0; }();
-  if (want_xreg && cvt_x && Mtot * p->ld_x < (1LL << 40)) {
-    a.xreg = 1;
-    a.xg = reinterpret_cast<const __half*>(p->x); a.ld_x = p->ld_x; a.m_tot = Mtot;
-    a.img_w = p->W; a.img_h = p->dy_tap_mode == DFCSA_TAP_2x2S2 ? p->B * p->H : p->H;
-    wgrad_tc_kernel<true><<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, map_dy2, a);
-  } else {
-    wgrad_tc_kernel<false><<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, map_dy2, a);
-  }
+  wgrad_tc_kernel<<<static_cast<unsigned>(grid), 192, smem_bytes, stream>>>(map_dy, map_x, map_dy2, a);
   DFCSA_LAUNCH_CHECK("wgrad_tc_kernel");
   return DFCSA_OK;
 }

@@ -23,8 +23,50 @@ def _e(shape, dtype, dev):
     return torch.empty(shape, dtype=dtype, device=dev)
 
 
+class ZeroArena:
+    """Zero-initialised scratch of one pass (forward or backward) of a network, carved from ONE persistent buffer that a
+    single memset clears at the start of the pass: the BatchNorm statistic sums, the backward reduction buffers and the
+    packed 3x3 / ConvT weight-gradient accumulators were ~70 separate torch.zeros fill kernels per step (250 launches
+    in the round-1 smoke trace).  The first pass sizes the buffer (requests fall back to torch.zeros until it exists)."""
+    ALIGN = 256
+
+    def __init__(self, dev):
+        self.dev, self.buf, self.off, self.need = dev, None, 0, 0
+
+    def begin(self):
+        if self.need > (self.buf.numel() if self.buf is not None else 0):
+            self.buf = torch.zeros(self.need, dtype=torch.uint8, device=self.dev)
+        elif self.buf is not None and self.off > 0:
+            self.buf[:self.off].zero_()
+        self.off = self.need = 0
+
+    def take(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        nbytes = (n * torch.empty((), dtype=dtype).element_size() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.need += nbytes
+        if self.buf is None or self.off + nbytes > self.buf.numel():
+            return torch.zeros(shape, dtype=dtype, device=self.dev)
+        v = self.buf[self.off:self.off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(shape)
+        self.off += nbytes
+        return v
+
+
+_ARENA = None        # the ZeroArena of the pass being enqueued (net_forward / net_backward set it)
+
+
 def _z(shape, dtype, dev):
+    if _ARENA is not None and _ARENA.dev == dev:
+        return _ARENA.take(shape if isinstance(shape, (tuple, list)) else (shape,), dtype)
     return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+def _net_arena(net, which, dev):
+    a = net.__dict__.setdefault("_dfcsa_arena", {}).get(which)
+    if a is None or a.dev != dev:
+        a = net.__dict__["_dfcsa_arena"][which] = ZeroArena(dev)
+    return a
 
 
 def _backend(segs, w, N, out):
@@ -269,7 +311,7 @@ def _pack_attention(bp, pk, training, plan):
     if training:
         bdt = BF16 if C % 64 == 0 else F32
         kp = (nq + 63) // 64 * 64 if C % 64 == 0 else nq      # K of the dgrad GEMM, zero-padded to the UMMA K block
-        wdq = _z((C, kp), bdt, dev)                 # [c, (q | k | v | pad)] = [Wq ; Wk ; Wv]^T
+        wdq = torch.zeros((C, kp), dtype=bdt, device=dev)      # [c, (q | k | v | pad)] = [Wq ; Wk ; Wv]^T (persistent)
         plan.add(bp.Wq.detach(), wdq[:, :Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
         plan.add(bp.Wk.detach(), wdq[:, Cq:2 * Cq], (C, 1, Cq), (1, 0, C), ld_dst=kp)
         plan.add(bp.Wv.detach(), wdq[:, 2 * Cq:nq], (C, 1, C), (1, 0, C), ld_dst=kp)
@@ -456,8 +498,8 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
         ops.rowdot(d_o, ctx.o.view(BN, C), Drow)
     ch = _attn_chunk(B, N)
     small = N <= _ATTN_SMALL_MAX_N
-    if small:
-        ops.attn_small_bwd(qkv, attn, d_o, B, N, Cq, C, dqkv)
+    if small:          # the kernel also accumulates the q / k / v bias gradients (column sums of dq / dk / dv)
+        ops.attn_small_bwd(qkv, attn, d_o, B, N, Cq, C, dqkv, grads[bp.bq], grads[bp.bk], grads[bp.bv])
     fused = (not small) and tca and attn is None and ctx.lse is not None and C <= 128 and Cq <= 32 and _ATTN_FUSED_BWD
     if fused:       # dq | dk | dv without a single [N, N] tensor in HBM: P and dS are rebuilt on chip, tile by tile
         ops.attn_bwd_fused(ctx.qkv16, qkvb, dob, B, N, Cq, C, ctx.lse, Drow, dqkv)
@@ -502,8 +544,9 @@ def attention_backward(bp, pk, ctx, d_o, B, N, grads):
             ops.sgemm(nb, N, Cq, N, dS, (N * N, 1, N), q, (N * nq, nq, 1), dk, (N * nq, nq, 1))    # dk[j,c] = sum_i dS[i,j] q[i,c]
         del dS, A
     dq, dk, dv = dqkv[:, :Cq], dqkv[:, Cq:2 * Cq], dqkv[:, 2 * Cq:]
-    for b, d in ((bp.bq, dq), (bp.bk, dk), (bp.bv, dv)):
-        ops.colsum(d, grads[b])
+    if not small:
+        for b, d in ((bp.bq, dq), (bp.bk, dk), (bp.bv, dv)):
+            ops.colsum(d, grads[b])
     # dpooled = dqkv . [Wq ; Wk ; Wv]  and the three weight gradients, on the tensor cores when C allows
     wdq = pk["wdqkv"]
     kp = wdq.shape[1]
@@ -591,16 +634,15 @@ def _local_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     B, H, W = ctx.B, ctx.H, ctx.W
     C, Ci = bp.C, bp.Ci
     M = B * H * W
-    red = _z((2 * C + 1,), F64, dev)
-    red1, drs = red[0:2 * C], red[2 * C:2 * C + 1]
+    red = _z((8 * C + 2,), F64, dev)       # the layout dfcsa_block_param_grads reads: [red1 | - | - | - | d res_scale | -]
+    red1, drs = red[0:2 * C], red[8 * C:8 * C + 1]
     bn1 = ctx.bn1
     dy = dskip if dskip is not None else _e((M, C), BF16, dev)
     # out = relu(bn1(L0)) + res_scale * R
     ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.L0, ctx.R, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], dy, red1, drs)
     dL0 = _e((M, C), BF16, dev)
     ops.bn_bwd_apply(dy, ctx.L0, bn1[0], bn1[1], bn1[2], bn1[3], red1, 0, dL0)
-    ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
-    grads[bp.res_scale].copy_(drs[0])
+    ops.block_param_grads(red, C, [(grads[bp.bn1.weight], grads[bp.bn1.bias]), None, None, None], drs=grads[bp.res_scale])
     if dx_out is not None:
         segs = [(dL0, TAP_3x3), (dy, TAP_1x1)]
         ops.conv_gemm(B, H, W, segs, pk["wd15"], Ci, dx_out, backend=_backend(segs, pk["wd15"], Ci, dx_out))
@@ -672,7 +714,6 @@ def _branch_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
         ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.F0, ctx.R, B, H, W, bn4[0], bn4[1], bn4[2], bn4[3], dy, red4, drs)
         dF0 = _e((M, C), BF16, dev)
         ops.bn_bwd_apply(dy, ctx.F0, bn4[0], bn4[1], bn4[2], bn4[3], red4, 0, dF0)
-        ops.bn_param_grads(red4, C, grads[bp.bn4.weight], grads[bp.bn4.bias])
         segs = [(dF0, TAP_1x1)]
         ops.conv_gemm(B, H, W, segs, pk["wd4c"], 2 * C, dLA, backend=_backend(segs, pk["wd4c"], 2 * C, dLA))
         _wgrad(B, H, W, ctx.z[:, C:], TAP_1x1, dF0, TAP_1x1, grads[bp.W4].view(C, 2 * C))
@@ -690,11 +731,10 @@ def _branch_block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
     dL0, dA0 = _e((M, C), BF16, dev), _e((M, C), BF16, dev)
     ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
-    if bp.has_l:
-        ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
-    ops.bn_param_grads(red2, C, grads[bp.bn2.weight], grads[bp.bn2.bias])
-    grads[bp.gamma].copy_(dgam)
-    grads[bp.res_scale].copy_(drs[0])
+    ops.block_param_grads(red, C, [(grads[bp.bn1.weight], grads[bp.bn1.bias]) if bp.has_l else None,
+                                   (grads[bp.bn2.weight], grads[bp.bn2.bias]), None,
+                                   (grads[bp.bn4.weight], grads[bp.bn4.bias]) if bp.kind == "concat" else None],
+                          drs=grads[bp.res_scale], dgam=grads[bp.gamma])
     if dx_out is not None:
         segs = ([(dL0, TAP_3x3)] if bp.has_l else []) + [(dA0, TAP_1x1), (dy, TAP_1x1)]
         ops.conv_gemm(B, H, W, segs, pk["wd125"], Ci, dx_out, backend=_backend(segs, pk["wd125"], Ci, dx_out))
@@ -744,7 +784,6 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     ops.block_out_bwd_reduce(dskip, dyp, ctx.y, ctx.F0, ctx.R, B, H, W, bn4[0], bn4[1], bn4[2], bn4[3], dy, red4, drs)
     dF0 = _e((M, C), BF16, dev)
     ops.bn_bwd_apply(dy, ctx.F0, bn4[0], bn4[1], bn4[2], bn4[3], red4, 0, dF0)
-    ops.bn_param_grads(red4, C, grads[bp.bn4.weight], grads[bp.bn4.bias])
     # fusion conv, part 1: df = dF0 . W4^T[:, 0:C]  (the gate-mix backward only needs df)
     dz = _e((M, 3 * C), BF16, dev)
     segs = [(dF0, TAP_1x1)]
@@ -754,7 +793,6 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     ops.gate_mix_bwd_reduce(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3)
     dG0 = _e((M, C), BF16, dev)
     ops.gate_mix_bwd_apply(dz, ctx.z, ctx.G0, bn3[0], bn3[1], bn3[2], bn3[3], red3, dG0)
-    ops.bn_param_grads(red3, C, grads[bp.bn3.weight], grads[bp.bn3.bias])
     # fusion conv part 2 + gate conv in ONE dgrad GEMM: [dL' | dA'] = [dF0 | dG0] . [W4^T[:, C:3C] ; W3^T]
     dLA = dz[:, C:]
     segs = [(dF0, TAP_1x1), (dG0, TAP_1x1)]
@@ -771,10 +809,9 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
     dL0, dA0 = dF0, dG0     # both dead after the GEMMs above: reuse their storage
     ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
-    ops.bn_param_grads(red1, C, grads[bp.bn1.weight], grads[bp.bn1.bias])
-    ops.bn_param_grads(red2, C, grads[bp.bn2.weight], grads[bp.bn2.bias])
-    grads[bp.gamma].copy_(dgam)
-    grads[bp.res_scale].copy_(drs[0])
+    # every small parameter gradient of the block (4 x BatchNorm weight / bias, gamma, res_scale) in one launch
+    ops.block_param_grads(red, C, [(grads[bn.weight], grads[bn.bias]) for bn in (bp.bn1, bp.bn2, bp.bn3, bp.bn4)],
+                          drs=grads[bp.res_scale], dgam=grads[bp.gamma])
     # the three convs that read x
     if dx_out is not None:
         segs = [(dL0, TAP_3x3), (dA0, TAP_1x1), (dy, TAP_1x1)]
@@ -811,6 +848,19 @@ def net_forward(net, x_nchw, training, save=True):
         raise ValueError("dfcsa: the network pools four times; H and W must be at least 16")
     x_nchw = x_nchw.contiguous().float()
     packs = NetPacks.get(net, keep)
+    global _ARENA
+    if training:
+        _ARENA = _net_arena(net, "fwd", dev)
+        _ARENA.begin()
+    try:
+        return _net_forward(net, x_nchw, training, keep, packs)
+    finally:
+        _ARENA = None
+
+
+def _net_forward(net, x_nchw, training, keep, packs):
+    dev = x_nchw.device
+    B, Cin, H, W = x_nchw.shape
     bps, pks = packs.bps, packs.pks
     f = [bps[i].C for i in range(4)]
     ctx = NetCtx() if keep else None
@@ -881,6 +931,16 @@ def net_param_list(net):
 def net_backward(net, ctx, dlogits_nchw, grads, after_stage=None):
     """Backward of net_forward: fills grads[param] (fp32, must be zero-initialised) for every parameter.
     after_stage(k), if given, is called when the k-th gradient bucket of trainer.reduce_buckets() is complete."""
+    global _ARENA
+    _ARENA = _net_arena(net, "bwd", dlogits_nchw.device)
+    _ARENA.begin()
+    try:
+        return _net_backward(net, ctx, dlogits_nchw, grads, after_stage)
+    finally:
+        _ARENA = None
+
+
+def _net_backward(net, ctx, dlogits_nchw, grads, after_stage):
     stage = [0]
 
     def done():

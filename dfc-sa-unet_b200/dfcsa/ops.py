@@ -136,8 +136,10 @@ def attn_small_fwd(qkv, B, N, Cq, Cn, attn, o):
     L.call("dfcsa_attn_small_fwd", L.ptr(qkv), _i64(qkv.stride(0)), B, N, Cq, Cn, L.ptr(attn), L.ptr(o), L.stream())
 
 
-def attn_small_bwd(qkv, attn, d_o, B, N, Cq, Cn, dqkv):
-    L.call("dfcsa_attn_small_bwd", L.ptr(qkv), _i64(qkv.stride(0)), L.ptr(attn), L.ptr(d_o), B, N, Cq, Cn, L.ptr(dqkv), L.stream())
+def attn_small_bwd(qkv, attn, d_o, B, N, Cq, Cn, dqkv, dbq=None, dbk=None, dbv=None):
+    """dbq / dbk / dbv: optional bias-gradient tensors the kernel ACCUMULATES the column sums of dq / dk / dv into."""
+    L.call("dfcsa_attn_small_bwd", L.ptr(qkv), _i64(qkv.stride(0)), L.ptr(attn), L.ptr(d_o), B, N, Cq, Cn, L.ptr(dqkv),
+           L.ptr(dbq), L.ptr(dbk), L.ptr(dbv), L.stream())
 
 
 def softmax_bgemm(batch, M, N, K, A, a_b, ld_a, Bm, b_b, ld_b, out, lse=None, have_lse=False):
@@ -224,6 +226,15 @@ def bn_eval_affine(gamma, beta, conv_bias, rmean, rvar, eps, scale, shift):
 
 def bn_param_grads(red, Cn, dgamma, dbeta):
     L.call("dfcsa_bn_param_grads", L.ptr(red), Cn, L.ptr(dgamma), L.ptr(dbeta), L.stream())
+
+
+def block_param_grads(red, Cn, bn_grads, drs=None, dgam=None):
+    """all small parameter gradients of one block from its reduction buffer in one launch (dfcsa_block_param_grads).
+    bn_grads: four (dgamma, dbeta) pairs or None, in the order of the buffer's four BatchNorm slots."""
+    args = []
+    for pair in bn_grads:
+        args += [L.ptr(pair[0]), L.ptr(pair[1])] if pair is not None else [None, None]
+    L.call("dfcsa_block_param_grads", L.ptr(red), Cn, *args, L.ptr(drs), L.ptr(dgam), L.stream())
 
 
 def bnrelu_pool_fwd(a0, B, H, W, scale, shift, P, tmp, pooled):

@@ -165,8 +165,10 @@ int dfcsa_rowdot(const float* a, const float* b, int64_t rows, int32_t cols, flo
  * and dq, dk, dv from d_o.  qkv / dqkv: [B*N, ld] rows (q[0:Cq] | k[Cq:2Cq] | v[2Cq:2Cq+C]); attn [B,N,N]; o, d_o [B*N, C]. */
 int dfcsa_attn_small_fwd(const float* qkv, int64_t ld, int32_t B, int32_t N, int32_t Cq, int32_t C,
                          float* attn, float* o, void* stream);
+/* dbq / dbk / dbv (optional, fp32 [Cq] / [Cq] / [C], ACCUMULATED with atomics): the bias gradients of the q / k / v
+ * convolutions = column sums of dq / dk / dv over tokens and images, so no separate reduction pass is needed. */
 int dfcsa_attn_small_bwd(const float* qkv, int64_t ld, const float* attn, const float* d_o, int32_t B, int32_t N,
-                         int32_t Cq, int32_t C, float* dqkv, void* stream);
+                         int32_t Cq, int32_t C, float* dqkv, float* dbq, float* dbk, float* dbv, void* stream);
 
 /* Batched GEMM on tcgen05:  C[b] = A[b] * B[b],  b < batch,  A: M x K, B: K x N (as a matrix product), 16-bit operands of
  * one dtype, fp32 accumulation.  Storage of an operand is either K-major (element (m,k) at base + b*a_b + m*ld_a + k)
@@ -323,6 +325,11 @@ int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void* l0, int64_
                            void* dl0, int64_t ld_dl0, void* da0, int64_t ld_da0, void* stream);
 /* BN affine gradients from a reduction: dgamma = red[C:2C], dbeta = red[0:C] (fp32 out) */
 int dfcsa_bn_param_grads(const double* red, int32_t C, float* dgamma, float* dbeta, void* stream);
+/* The same for ALL small parameter gradients of one block in one launch.  red is the block's backward reduction buffer
+ * [red1 (2C) | red2 (2C) | red3 (2C) | red4 (2C) | d res_scale | d gamma] (double); output k of BatchNorm i is written only
+ * when its pointer is non-NULL: dbeta_i = red_i[0:C], dgamma_i = red_i[C:2C]; *drs = red[8C], *dgam = red[8C+1]. */
+int dfcsa_block_param_grads(const double* red, int32_t C, float* dg1, float* db1, float* dg2, float* db2, float* dg3,
+                            float* db3, float* dg4, float* db4, float* drs, float* dgam, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Layout / misc
