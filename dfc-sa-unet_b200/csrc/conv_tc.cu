@@ -53,6 +53,7 @@ struct ConvTcArgs {
   long long ld_shadow;
   int fixed_nt;     // gridDim.x is a multiple of n_tiles_n: a CTA sees ONE n tile for the whole kernel (nt == blockIdx.x % n_tiles_n)
   int wide_out, wide_shadow;   // 32-byte stores legal (16-bit tensor, pitch % 16 == 0, base 32-byte aligned, no accumulate)
+  int act_cols;     // ReLU on the output columns n < act_cols (0: no activation)
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -375,6 +376,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (i < ncols) v[i] += __ldg(a.bias + cn + i);
         }
+        if (n0 < a.act_cols) {      // folded conv + BatchNorm + ReLU of the inference path
+#pragma unroll
+          for (int i = 0; i < 32; ++i) if (n0 + i < a.act_cols) v[i] = fmax_nan(v[i], 0.f);
+        }
         if (valid) {
           if (a.wide_out && ncols == 32) {
             if (a.out_dtype == DFCSA_F16) store_chunk_wide<__half>(reinterpret_cast<__half*>(a.out) + pix * a.ld_out + cn, v);
@@ -596,6 +601,9 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->shadow == nullptr || (!p->accumulate && p->ld_shadow % 8 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 15) == 0),
                   "conv_gemm_tc: bad shadow output");
   if (p->out_mode == DFCSA_OUT_CONVT2x2) { a.convt_co = p->N / 4; a.convt_h = p->H; a.convt_w = p->W; }
+  DFCSA_CHECK_ARG(p->act == 0 || (p->act == 1 && p->out_mode == DFCSA_OUT_DIRECT && !p->accumulate && p->stats == nullptr),
+                  "conv_gemm_tc: the ReLU epilogue needs a direct, non-accumulating output without statistics");
+  a.act_cols = p->act ? (p->act_cols > 0 ? p->act_cols : p->N) : 0;
   a.wide_out = p->out_dtype != DFCSA_F32 && !p->accumulate && p->ld_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 31) == 0;
   a.wide_shadow = p->shadow != nullptr && p->ld_shadow % 16 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 31) == 0;
 

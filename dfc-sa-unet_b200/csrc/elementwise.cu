@@ -384,8 +384,10 @@ branch_act_fwd_kernel(const act_t* __restrict__ l0, long long ld_l0, const act_t
   if (pl >= PL || c >= C) return;
   const unsigned M = static_cast<unsigned>(B) * H * W;
   const float gm = *gamma;
+  const bool has_l = l0 != nullptr;       // inference path: L is written by the folded conv + ReLU, only A is computed here
   float sc1[VEC], sh1[VEC], sc2[VEC], sh2[VEC];
-  ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2);
+  if (has_l) { ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); }
+  ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2);
   // kActPix pixels per iteration with all their loads issued before the first store: one pixel at a time (L0, store,
   // then A0 - the store to z kept the second load from moving up) left 16 bytes in flight per thread, ~12 KB per SM,
   // and the kernel at 0.61 of copy bandwidth.  The raw vectors cost 8 registers per pixel, so the kernel is built for
@@ -402,18 +404,20 @@ branch_act_fwd_kernel(const act_t* __restrict__ l0, long long ld_l0, const act_t
     for (int u = 0; u < kActPix; ++u) {
       const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
       ok[u] = m < M;
-      if (ok[u]) { lraw[u] = ldraw<VEC>(l0 + m * ld_l0 + c); araw[u] = ldraw<VEC>(a0 + m * ld_a0 + c); }
+      if (ok[u]) { if (has_l) lraw[u] = ldraw<VEC>(l0 + m * ld_l0 + c); araw[u] = ldraw<VEC>(a0 + m * ld_a0 + c); }
     }
 #pragma unroll
     for (int u = 0; u < kActPix; ++u) {
       if (ok[u]) {
         const long long m = static_cast<long long>(m32) + static_cast<long long>(u) * stride;
         float outv[VEC], xin[VEC];
-        cvtraw<VEC>(lraw[u], xin);
+        if (has_l) {
+          cvtraw<VEC>(lraw[u], xin);
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) outv[v] = fmax_nan(fmaf(xin[v], sc1[v], sh1[v]), 0.f);
-        stv<VEC>(z + m * ld_z + C + c, outv);
-        if (zb != nullptr) stv<VEC>(zb + m * ld_zb + C + c, outv);
+          for (int v = 0; v < VEC; ++v) outv[v] = fmax_nan(fmaf(xin[v], sc1[v], sh1[v]), 0.f);
+          stv<VEC>(z + m * ld_z + C + c, outv);
+          if (zb != nullptr) stv<VEC>(zb + m * ld_zb + C + c, outv);
+        }
         float up[VEC];
         bilerp_gather<VEC>(o, it[u].b, it[u].y, it[u].x, H, W, P, C, c, up);
         cvtraw<VEC>(araw[u], xin);
@@ -1150,8 +1154,8 @@ extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a
                                     int32_t W, int32_t C, const float* scale1, const float* shift1, const float* scale2,
                                     const float* shift2, const float* o, int32_t P, const float* gamma, void* z,
                                     int64_t ld_z, void* zb, int64_t ld_zb, void* stream) {
-  DFCSA_CHECK_ARG(l0 && a0 && scale1 && shift1 && scale2 && shift2 && o && gamma && z, "dfcsa_branch_act_fwd: null pointer");
-  const bool v8 = vec8_ok(C, {ld_l0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
+  DFCSA_CHECK_ARG(a0 && (l0 == nullptr || (scale1 && shift1)) && scale2 && shift2 && o && gamma && z, "dfcsa_branch_act_fwd: null pointer");
+  const bool v8 = vec8_ok(C, {l0 ? ld_l0 : 0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_act_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   static const int act_occ = [] { const char* e = getenv("DFCSA_ACT_OCC"); return e ? atoi(e) : 2; }();

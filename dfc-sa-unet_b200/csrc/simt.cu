@@ -139,6 +139,7 @@ conv_simt_kernel(const SimtConvArgs a) {
         pix = (b * 2 * p.H + 2 * h + (q >> 1)) * (2LL * p.W) + 2 * w + (q & 1);
       }
       if (p.bias != nullptr) v += p.bias[cn];
+      if (p.act == 1 && n < (p.act_cols > 0 ? p.act_cols : p.N)) v = fmax_nan(v, 0.f);
       const long long o = pix * p.ld_out + cn;
       if (p.accumulate) v += ld_any(p.out, o, p.out_dtype);
       st_any(p.out, o, p.out_dtype, v);
@@ -405,7 +406,7 @@ pack_jobs_kernel(const dfcsa_pack_job_t* jobs, int n_jobs, const long long* chun
     const dfcsa_pack_job_t j = jobs[lo];
     const long long total = j.D0 * j.D1 * j.D2;
     const long long base = (ch - chunk_prefix[lo]) * 1024;
-    const float sc = j.scale ? *j.scale : 1.f;
+    const float sc0 = j.scale ? *j.scale : 1.f;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const long long i = base + u * 256 + threadIdx.x;
@@ -422,6 +423,7 @@ pack_jobs_kernel(const dfcsa_pack_job_t* jobs, int n_jobs, const long long* chun
           i0 = r / j.D1;
         }
         const long long i1s = j.flip1 ? j.D1 - 1 - i1 : i1;
+        const float sc = j.row_scale ? sc0 * j.row_scale[i0] : sc0;
         st_any(j.dst, i0 * j.ld_dst + i1 * j.D2 + i2, j.dst_dtype, sc * ld_any(j.src, i0 * j.s0 + i1s * j.s1 + i2 * j.s2, j.src_dtype));
       }
     }

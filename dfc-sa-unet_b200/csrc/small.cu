@@ -59,7 +59,7 @@ constexpr int kWarps = 4;
 template <int TAPS, int CI, typename TX, typename TO>
 __global__ void __launch_bounds__(kWarps * 32)
 conv_smallk_kernel(const void* x, long long ld_x, long long M, int H, int W, const float* wgt, int N, void* out,
-                   long long ld_out, const float* bias, double* stats) {
+                   long long ld_out, const float* bias, double* stats, int act_cols) {
   constexpr int K = TAPS * CI;
   constexpr int KP = (K + 4) / 4 * 4;      // row pitch: 16-byte multiple so a pixel's patch is read with LDS.128 broadcasts
   __shared__ __align__(16) float s_patch[kWarps][32][KP];
@@ -90,6 +90,8 @@ conv_smallk_kernel(const void* x, long long ld_x, long long M, int H, int W, con
         a0 = fmaf(xr[k], wr[k].x, a0);
         a1 = fmaf(xr[k], wr[k].y, a1);
       }
+      if (n < act_cols) a0 = fmax_nan(a0, 0.f);          // folded conv + BatchNorm + ReLU (inference path)
+      if (n + 1 < act_cols) a1 = fmax_nan(a1, 0.f);
       st2<TO>(out, (m0 + p) * ld_out + n, a0, a1);
       s0 += a0; s1 += a1; q0 += a0 * a0; q1 += a1 * a1;
     }
@@ -288,10 +290,12 @@ int small_blocks(long long M) {
 int conv_gemm_small(const dfcsa_conv_params_t* p, cudaStream_t stream, int* rc_out) {
   *rc_out = DFCSA_OK;
   if (p->n_seg != 1 || p->out_mode != DFCSA_OUT_DIRECT || p->accumulate || p->shadow != nullptr) return 0;
+  if (p->act != 0 && (p->act != 1 || p->stats != nullptr)) return 0;
+  const int act_cols = p->act ? (p->act_cols > 0 ? p->act_cols : p->N) : 0;
   const dfcsa_seg_t& sg = p->seg[0];
   const long long M = static_cast<long long>(p->B) * p->H * p->W;
   // ---- tiny N (final 1x1 conv) ----
-  if (sg.tap_mode == DFCSA_TAP_1x1 && p->N <= 4 && sg.channels % 64 == 0 && sg.channels <= 1024 && p->w_dtype == DFCSA_F32 &&
+  if (act_cols == 0 && sg.tap_mode == DFCSA_TAP_1x1 && p->N <= 4 && sg.channels % 64 == 0 && sg.channels <= 1024 && p->w_dtype == DFCSA_F32 &&
       p->out_dtype == DFCSA_F32 && p->src_dtype != DFCSA_F32 && p->stats == nullptr && sg.ld % 8 == 0 &&
       (reinterpret_cast<uintptr_t>(sg.ptr) & 15) == 0) {
     const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((M + 31) / 32, 148LL * 8)));
@@ -316,7 +320,7 @@ int conv_gemm_small(const dfcsa_conv_params_t* p, cudaStream_t stream, int* rc_o
   const float* w = reinterpret_cast<const float*>(p->w);
 #define LAUNCH_SMALLK(TAPS, CI, TX, TO)                                                                                   \
   conv_smallk_kernel<TAPS, CI, TX, TO><<<grid, kWarps * 32, 0, stream>>>(sg.ptr, sg.ld, M, p->H, p->W, w, p->N, p->out, p->ld_out, \
-                                                                         p->bias, p->stats)
+                                                                         p->bias, p->stats, act_cols)
   bool done = false;
   if (sg.channels == 3 && p->src_dtype == DFCSA_F32 && sg.tap_mode == DFCSA_TAP_3x3) {
     if (p->out_dtype == DFCSA_F16) LAUNCH_SMALLK(9, 3, float, __half); else LAUNCH_SMALLK(9, 3, float, __nv_bfloat16);

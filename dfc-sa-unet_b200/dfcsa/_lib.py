@@ -38,6 +38,7 @@ class ConvParams(C.Structure):
         ("out_mode", C.c_int32), ("accumulate", C.c_int32),
         ("bias", C.c_void_p), ("stats", C.c_void_p),
         ("shadow", C.c_void_p), ("ld_shadow", C.c_int64),
+        ("act", C.c_int32), ("act_cols", C.c_int32),
     ]
 
 
@@ -78,7 +79,8 @@ class PackJob(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("scale", C.c_void_p),
                 ("D0", C.c_int64), ("D1", C.c_int64), ("D2", C.c_int64),
                 ("s0", C.c_int64), ("s1", C.c_int64), ("s2", C.c_int64), ("ld_dst", C.c_int64),
-                ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32), ("flip1", C.c_int32), ("pad_", C.c_int32)]
+                ("src_dtype", C.c_int32), ("dst_dtype", C.c_int32), ("flip1", C.c_int32), ("pad_", C.c_int32),
+                ("row_scale", C.c_void_p)]
 
 
 class ParamDesc(C.Structure):

@@ -184,9 +184,9 @@ class PackPlan:
         self.keep = []          # tensors whose storage the table points into
         self._table = None
 
-    def add(self, src, dst, D, s, flip1=False, scale=None, ld_dst=0):
-        self.jobs.append((src, dst, tuple(D), tuple(s), flip1, scale, ld_dst or D[1] * D[2]))
-        self.keep += [src, dst, scale]
+    def add(self, src, dst, D, s, flip1=False, scale=None, ld_dst=0, row_scale=None):
+        self.jobs.append((src, dst, tuple(D), tuple(s), flip1, scale, ld_dst or D[1] * D[2], row_scale))
+        self.keep += [src, dst, scale, row_scale]
 
     def run(self):
         if not self.jobs:
@@ -195,10 +195,11 @@ class PackPlan:
             from . import _lib as L
             tab = (L.PackJob * len(self.jobs))()
             prefix, tot = [0], 0
-            for i, (src, dst, D, st, flip1, scale, ld) in enumerate(self.jobs):
+            for i, (src, dst, D, st, flip1, scale, ld, row_scale) in enumerate(self.jobs):
                 j = tab[i]
                 j.src, j.dst = src.data_ptr(), dst.data_ptr()
                 j.scale = scale.data_ptr() if scale is not None else None
+                j.row_scale = row_scale.data_ptr() if row_scale is not None else None
                 j.D0, j.D1, j.D2 = D
                 j.s0, j.s1, j.s2 = st
                 j.ld_dst = ld
@@ -252,6 +253,42 @@ def pack_block_weights(bp, training, need_dx, plan):
         plan.add(W3m, pk["wd43"][:, C:], (2 * C, 1, C), (1, 0, 2 * C), ld_dst=2 * C)
         if need_dx:   # the first block never needs the gradient w.r.t. the image
             pk["wd125"] = _pack_input_dgrad(bp, W5, plan, True)
+    return pk
+
+
+WEIGHTS_EPOCH = 0    # bumped whenever a libdfcsa kernel rewrites parameters / BatchNorm buffers behind torch's back (raw pointers)
+
+
+def pack_block_weights_folded(bp, plan, affines):
+    """Inference-mode operands of one DFC-SA block (reference inference.py:100 runs the network in eval mode): every
+    BatchNorm uses its running statistics, so it is an affine map per channel, y = s * conv(x) + t with
+    s = gamma / sqrt(running_var + eps), t = beta + (conv_bias - running_mean) * s.  s is folded into the rows of the packed
+    weight matrix (dfcsa_pack_jobs row_scale), t is the GEMM's bias, ReLU is the GEMM's epilogue: conv + BN + ReLU is ONE
+    launch and the four affine / activation passes of the training path disappear.
+    `affines` collects (bn, conv_bias, scale_out, shift_out) for dfcsa_bn_eval_affine, run before the pack jobs."""
+    dev = bp.res_scale.device
+    Ci, C = bp.Ci, bp.C
+    fdt = F16 if bp.tc else F32
+    gdt = F16 if C % 64 == 0 else F32
+    pk = {"folded": True}
+    W5 = bp.W5.detach() if bp.W5 is not None else torch.eye(C, dtype=F32, device=dev).view(C, C, 1, 1)
+    s = _e((4, C), F32, dev)
+    pk["t1"], pk["t3"], pk["t4"] = _e((C,), F32, dev), _e((C,), F32, dev), _e((C,), F32, dev)
+    pk["b25"] = torch.zeros((2 * C,), dtype=F32, device=dev)          # [t2 | 0]: the residual conv has no bias and no BN
+    affines += [(bp.bn1, bp.b1, s[0], pk["t1"]), (bp.bn2, bp.b2, s[1], pk["b25"][:C]), (bp.bn3, bp.b3, s[2], pk["t3"]),
+                (bp.bn4, bp.b4, s[3], pk["t4"])]
+    pk["w1"] = _e((C, 9 * Ci), fdt, dev)
+    plan.add(bp.W1.detach(), pk["w1"], (C, 9, Ci), (Ci * 9, 1, 9), row_scale=s[0])
+    pk["w25"] = _e((2 * C, Ci), fdt, dev)
+    plan.add(bp.W2.detach(), pk["w25"][:C], (C, 1, Ci), (Ci, 0, 1), row_scale=s[1])
+    plan.add(W5, pk["w25"][C:], (C, 1, Ci), (Ci, 0, 1))
+    pk["w3"] = _e((C, 2 * C), gdt, dev)
+    plan.add(bp.W3.detach(), pk["w3"], (C, 1, 2 * C), (2 * C, 0, 1), row_scale=s[2])
+    pk["w4"] = _e((C, 3 * C), gdt, dev)
+    plan.add(bp.W4.detach(), pk["w4"], (C, 1, 3 * C), (3 * C, 0, 1), row_scale=s[3])
+    _pack_attention(bp, pk, False, plan)
+    pk["ones"], pk["zeros"] = torch.ones((C,), dtype=F32, device=dev), torch.zeros((C,), dtype=F32, device=dev)
+    pk["scales"] = s
     return pk
 
 
@@ -321,12 +358,16 @@ def _pack_attention(bp, pk, training, plan):
 class NetPacks:
     """Persistent packed operands of a whole UNetDFCSA + the plan that refreshes them (cached on the module)."""
 
-    def __init__(self, net, keep):
+    def __init__(self, net, keep, fold=False):
         dev = next(net.parameters()).device
         self.sig = NetPacks.signature(net)
         self.plan = PackPlan(dev)
         self.bps = [make_block_params(b) for b in _blocks(net)]
-        self.pks = [pack_block_weights(bp, keep, i > 0, self.plan) for i, bp in enumerate(self.bps)]
+        self.fold, self.affines, self.content = fold, [], None
+        # fold: inference-mode operands with the running-statistics BatchNorms folded in (DFC-SA blocks; the ablation
+        # block types keep the unfolded eval path)
+        self.pks = [pack_block_weights_folded(bp, self.plan, self.affines) if (fold and bp.kind == "dfc") else
+                    pack_block_weights(bp, keep, i > 0, self.plan) for i, bp in enumerate(self.bps)]
         self.up_fwd, self.up_bwd = [], []
         for up in (net.up4, net.up3, net.up2, net.up1):
             Ci_t, Co_t = up.weight.shape[0], up.weight.shape[1]
@@ -350,12 +391,29 @@ class NetPacks:
         return tuple(p.data_ptr() for p in net.parameters())
 
     @staticmethod
-    def get(net, keep):
+    def content_signature(net):
+        """changes whenever parameters or BatchNorm buffers may have changed: torch's in-place version counters (optimizer
+        steps of torch.optim, load_state_dict, manual edits) + WEIGHTS_EPOCH for writes through raw pointers (FusedSGD, the
+        running-statistics update of a training forward)."""
+        return (WEIGHTS_EPOCH, sum(t._version for t in net.parameters()) + sum(t._version for t in net.buffers()))
+
+    @staticmethod
+    def get(net, keep, fold=False):
         cache = net.__dict__.setdefault("_dfcsa_packs", {})
-        pk = cache.get(keep)
+        key = (keep, fold)
+        pk = cache.get(key)
         if pk is None or pk.sig != NetPacks.signature(net):
-            pk = cache[keep] = NetPacks(net, keep)
-        pk.plan.run()
+            pk = cache[key] = NetPacks(net, keep, fold)
+        if fold:        # inference: weights rarely change between calls - re-fold only when they did
+            content = NetPacks.content_signature(net)
+            if pk.content != content:
+                for bn, conv_bias, scale, shift in pk.affines:
+                    ops.bn_eval_affine(bn.weight.detach(), bn.bias.detach(), conv_bias.detach() if conv_bias is not None else None,
+                                       bn.running_mean, bn.running_var, BN_EPS, scale, shift)
+                pk.plan.run()
+                pk.content = content
+        else:
+            pk.plan.run()
         return pk
 
 
@@ -570,6 +628,8 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
         return _local_block_forward(bp, pk, x, B, H, W, y, yp, training, save)
     if bp.kind != "dfc":
         return _branch_block_forward(bp, pk, x, B, H, W, y, yp, training, save)
+    if pk.get("folded"):
+        return _dfc_block_forward_folded(bp, pk, x, B, H, W, y, yp)
     dev = x.device
     C, Ci, P = bp.C, bp.Ci, _pool_side(bp, H, W)
     M = B * H * W
@@ -609,6 +669,37 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
         ctx.L0, ctx.A0, ctx.R, ctx.G0, ctx.F0, ctx.z, ctx.y, ctx.o = L0, A0, R, G0, F0, z, y, o
         ctx.bn1, ctx.bn2, ctx.bn3, ctx.bn4 = bn1, bn2, bn3, bn4
     return ctx
+
+
+def _dfc_block_forward_folded(bp, pk, x, B, H, W, y, yp):
+    """Inference-mode DynamicFusionConvAttnBlock with the BatchNorms folded into the GEMMs (pack_block_weights_folded):
+    4 GEMMs with bias (+ ReLU) epilogues and 4 streaming passes (pool 1 E, A = gamma * up(o) + a 2 E, gate mix 4 E, residual
+    sum + max pool 3.25 E); no statistics, no affine passes, no pre-BatchNorm tensors (L0 / A0 / F0 never exist)."""
+    dev = x.device
+    C, P = bp.C, _pool_side(bp, H, W)
+    M = B * H * W
+    ones, zeros = pk["ones"], pk["zeros"]
+    z = _e((M, 3 * C), F16, dev)            # [f | L | A]
+    AR = _e((M, 2 * C), F16, dev)           # [a | R]
+    L = z[:, C:2 * C]
+    segs3, segs1 = [(x, TAP_3x3)], [(x, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs3, pk["w1"], C, L, bias=pk["t1"], act=1, backend=_backend(segs3, pk["w1"], C, L))
+    ops.conv_gemm(B, H, W, segs1, pk["w25"], 2 * C, AR, bias=pk["b25"], act=1, act_cols=C, backend=_backend(segs1, pk["w25"], 2 * C, AR))
+    a, R = AR[:, :C], AR[:, C:]
+    tmp = _e((B, H, P, C), F32, dev)
+    pooled = _e((B * P * P, C), F32, dev)
+    ops.bnrelu_pool_fwd(a, B, H, W, ones, zeros, P, tmp, pooled)        # a >= 0 already: the fused affine + ReLU is the identity
+    o = attention_forward(bp, pk, pooled, B, P * P, None)
+    ops.branch_act_fwd(None, a, B, H, W, None, None, ones, zeros, o, P, bp.gamma.detach(), z, None)   # A = gamma * up(o) + a
+    G = _e((M, C), F16, dev)
+    segs = [(z[:, C:], TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["w3"], C, G, bias=pk["t3"], backend=_backend(segs, pk["w3"], C, G))
+    ops.gate_mix_fwd(G, ones, zeros, z, None)                            # f = sigmoid(G) L + (1 - sigmoid(G)) A
+    F = _e((M, C), F16, dev)
+    segs = [(z, TAP_1x1)]
+    ops.conv_gemm(B, H, W, segs, pk["w4"], C, F, bias=pk["t4"], act=1, backend=_backend(segs, pk["w4"], C, F))
+    ops.sum_out_fwd(F, None, R, B, H, W, bp.res_scale.detach(), y, yp)   # y = F + res_scale * R (+ 2x2 max pool)
+    return None
 
 
 def _local_block_forward(bp, pk, x, B, H, W, y, yp, training, save):
@@ -847,9 +938,10 @@ def net_forward(net, x_nchw, training, save=True):
     if H < 16 or W < 16:
         raise ValueError("dfcsa: the network pools four times; H and W must be at least 16")
     x_nchw = x_nchw.contiguous().float()
-    packs = NetPacks.get(net, keep)
-    global _ARENA
+    packs = NetPacks.get(net, keep, fold=not training)
+    global _ARENA, WEIGHTS_EPOCH
     if training:
+        WEIGHTS_EPOCH += 1          # bn_finalize rewrites the running statistics through raw pointers
         _ARENA = _net_arena(net, "fwd", dev)
         _ARENA.begin()
     try:
@@ -922,6 +1014,30 @@ def _net_forward(net, x_nchw, training, keep, packs):
         ctx.dims = (B, Cin, H, W, f, Hs, Ws, Ms)
         ctx.wdf = packs.wdf
     return logits, ctx
+
+
+def eval_forward_graphed(net, x_nchw):
+    """Inference forward replayed from a CUDA graph (one per input shape; opt-in with `net.eval_cuda_graph = True`): the
+    ~150 launches of a folded eval forward cost more host time than GPU time at batch 1 (C5's p50 latency).  The first two
+    calls per shape run eagerly, the third captures.  Folded operands live in persistent buffers, so when the weights
+    change they are re-folded in place before the replay and the graph stays valid.  Returns a fresh tensor."""
+    cache = net.__dict__.setdefault("_dfcsa_eval_graphs", {})
+    key = (tuple(x_nchw.shape), str(x_nchw.device))
+    e = cache.setdefault(key, [0, None, None, None])
+    e[0] += 1
+    if e[0] <= 2:
+        return net_forward(net, x_nchw, False, save=False)[0]
+    NetPacks.get(net, False, fold=True)          # re-fold (eagerly, outside the graph) if parameters / buffers changed
+    if e[1] is None:
+        e[2] = x_nchw.detach().float().contiguous().clone()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            e[3] = net_forward(net, e[2], False, save=False)[0]
+        e[1] = g
+    e[2].copy_(x_nchw, non_blocking=True)
+    e[1].replay()
+    return e[3].clone()
 
 
 def net_param_list(net):

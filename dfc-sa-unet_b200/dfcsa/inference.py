@@ -55,8 +55,8 @@ def predict_large_image(model, image, tile_size, overlap, device, use_tta=False,
     for b in boxes:                                                   # group by tile shape (edge cases of small images)
         groups.setdefault((b[1] - b[0], b[3] - b[2]), []).append(b)
     for (th, tw), bs in groups.items():
-        if th % 16 or tw % 16:
-            raise NotImplementedError("dfcsa: tile sides must be multiples of 16 (4 max-pool levels; reference tile_size 224)")
+        if th < 16 or tw < 16:
+            raise ValueError("dfcsa: tile sides must be at least 16 (4 max-pool levels; reference tile_size 224)")
         for i in range(0, len(bs), batch_tiles):
             chunk = bs[i:i + batch_tiles]
             x = torch.stack([full[:, y0:y1, x0:x1] for (y0, y1, x0, x1) in chunk])

@@ -201,7 +201,10 @@ class DynamicFusionConvAttnBlock(nn.Module):
 class _NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, net, need_grad, *params):
-        logits, nctx = engine.net_forward(net, x, net.training, save=need_grad)
+        if not net.training and not need_grad and getattr(net, "eval_cuda_graph", False) and x.is_cuda:
+            logits, nctx = engine.eval_forward_graphed(net, x), None      # inference replayed from a CUDA graph (opt-in)
+        else:
+            logits, nctx = engine.net_forward(net, x, net.training, save=need_grad)
         ctx.net, ctx.nctx, ctx.params = net, nctx, params
         return logits
 

@@ -26,7 +26,7 @@ def tc_eligible(segs, N, out):
 
 
 def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, bias=None, stats=None,
-              backend=BACKEND_TC, shadow=None):
+              backend=BACKEND_TC, shadow=None, act=0, act_cols=0):
     """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm)."""
     p = L.ConvParams()
     p.B, p.H, p.W, p.n_seg = B, H, W, len(segs)
@@ -48,6 +48,7 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.stats = stats.data_ptr() if stats is not None else None
     p.shadow = shadow.data_ptr() if shadow is not None else None
     p.ld_shadow = _mat(shadow) if shadow is not None else 0
+    p.act, p.act_cols = act, act_cols
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
            flops=2.0 * B * H * W * N * ktot,
@@ -243,8 +244,8 @@ def bnrelu_pool_fwd(a0, B, H, W, scale, shift, P, tmp, pooled):
 
 
 def branch_act_fwd(l0, a0, B, H, W, s1, t1, s2, t2, o, P, gamma, z, zb=None):
-    Cn = l0.shape[1]
-    L.call("dfcsa_branch_act_fwd", L.ptr(l0), _i64(_mat(l0)), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s1),
+    Cn = a0.shape[1]
+    L.call("dfcsa_branch_act_fwd", L.ptr(l0), _i64(_mat(l0) if l0 is not None else 0), L.ptr(a0), _i64(_mat(a0)), B, H, W, Cn, L.ptr(s1),
                                          L.ptr(t1), L.ptr(s2), L.ptr(t2), L.ptr(o), P, L.ptr(gamma), L.ptr(z),
                                          _i64(_mat(z)), L.ptr(zb), _i64(_mat(zb) if zb is not None else 0), L.stream())
 

@@ -71,6 +71,8 @@ class FusedSGD(torch.optim.SGD):
             for p in self._params:
                 self.state[p]["momentum_buffer"] = self._mom[p]
             self._first = False
+        from . import engine
+        engine.WEIGHTS_EPOCH += 1       # the kernel rewrote the parameters through raw pointers: folded inference operands are stale
         return None
 
     def load_state_dict(self, state_dict):

@@ -81,6 +81,12 @@ typedef struct {
   void*   shadow;           /* optional bf16 copy of the result at the same coordinates (pitch ld_shadow): the operand
                                the weight-gradient GEMM reads later (kind::f16 cannot mix fp16 and bf16) */
   int64_t ld_shadow;
+  /* Epilogue activation, applied after the bias and before the store (inference path: eval-mode BatchNorm is folded into
+   * the packed weights and the bias, reference inference.py:100, so conv + BN + ReLU is ONE launch):
+   * act = 0 none, 1 ReLU on the output columns n < act_cols (act_cols = 0: all N; the attention-branch and residual
+   * 1x1 convs share one GEMM over [W2 ; W5] and only the first half has a ReLU).  DIRECT output mode only. */
+  int32_t act;
+  int32_t act_cols;
 } dfcsa_conv_params_t;
 
 int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);
@@ -129,6 +135,8 @@ typedef struct {
   const void* src; void* dst; const float* scale;
   int64_t D0, D1, D2, s0, s1, s2, ld_dst;
   int32_t src_dtype, dst_dtype, flip1, pad_;
+  const float* row_scale;   /* optional [D0]: dst row i0 is additionally multiplied by row_scale[i0] (BatchNorm scale folded
+                               into the output channels of a forward weight matrix for the inference path) */
 } dfcsa_pack_job_t;
 int dfcsa_pack_jobs(const dfcsa_pack_job_t* jobs_dev, int32_t n_jobs, const int64_t* chunk_prefix_dev,
                     int64_t total_chunks, void* stream);
@@ -248,7 +256,8 @@ int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int32_t H, int3
                           const float* scale, const float* shift, int32_t P,
                           float* tmp, float* pooled, void* stream);
 /* L = relu(bn1(L0)) -> z[:, C:2C];  A = gamma*bilinear_up(o) + relu(bn2(A0)) -> z[:, 2C:3C]
- * (reference :97,:99,:36,:38).  o is [B, P, P, C] fp32.  zb: optional bf16 shadow of z (same channel offsets). */
+ * (reference :97,:99,:36,:38).  o is [B, P, P, C] fp32.  zb: optional bf16 shadow of z (same channel offsets).
+ * l0 may be NULL: only the A half is computed (inference path: L comes straight out of the folded conv + ReLU). */
 int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a0, int64_t ld_a0,
                          int32_t B, int32_t H, int32_t W, int32_t C,
                          const float* scale1, const float* shift1, const float* scale2, const float* shift2,

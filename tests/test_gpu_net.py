@@ -427,3 +427,45 @@ def test_validation_loop_per_sample_metrics_and_resume(cuda, tmp_path):
     tr2.train(resume_from=str(tmp_path / "run" / "checkpoints" / "checkpoint_epoch_1.pth"))
     assert tr2.epochs == [1, 2] and tr2.train_losses[0] == ck["train_losses"][0] and len(tr2.train_losses) == 2
     assert abs(tr2.train_losses[1] - tr.train_losses[1]) < 5e-3        # same state, same batches -> same second epoch
+
+
+def test_eval_cuda_graph_matches_eager_and_tracks_weight_changes(cuda):
+    """net.eval_cuda_graph = True: the folded inference forward replayed from a CUDA graph equals the eager one, and after
+    the weights change (in-place torch update, or a FusedSGD step through raw pointers) the folded operands are rebuilt
+    before the next replay."""
+    from oracle import dfcsa_oracle as O
+    from dfcsa.modules import UNetDFCSARes
+    from dfcsa.selftest import set_gamma
+    from dfcsa.trainer import Trainer
+    torch.manual_seed(0)
+    model = UNetDFCSARes(3, 1, [64, 128, 256, 512], pool_size=4, ablation_on_qk_channels=8)
+    set_gamma(model, 0.5)
+    model = model.cuda().eval()
+    img = O.synthetic_batch(2, 64, 64, seed=5)[0].cuda()
+    img2 = O.synthetic_batch(2, 64, 64, seed=6)[0].cuda()
+    with torch.no_grad():
+        want, want2 = model(img).clone(), model(img2).clone()
+        model.eval_cuda_graph = True
+        for _ in range(3):
+            got = model(img)
+        assert model.__dict__["_dfcsa_eval_graphs"][((2, 3, 64, 64), str(img.device))][1] is not None      # really captured
+        assert torch.equal(got, want)
+        assert torch.equal(model(img2), want2)                               # replay with new input data
+        # in-place weight change through torch
+        model.final_conv.bias.add_(0.25)
+        assert torch.allclose(model(img), want + 0.25, atol=1e-6)
+        model.down2.conv_branch[1].running_var.mul_(4.0)                     # a BatchNorm buffer: folded scale changes
+        model.eval_cuda_graph = False
+        eager = model(img).clone()
+        model.eval_cuda_graph = True
+        assert torch.equal(model(img), eager) and not torch.allclose(eager, want + 0.25, atol=1e-3)
+    # a training step (FusedSGD writes the parameters through raw pointers), then inference again
+    cfg = {"training": {"loss": {"type": "bce_dice", "params": {}}, "num_epochs": 1}, "logging": {"log_dir": "/tmp/dfcsa_test"}}
+    tr = Trainer(model, None, None, None, "cuda", cfg)
+    im, mk = (t.cuda() for t in O.synthetic_batch(2, 64, 64, seed=7))
+    tr.train_step(im, mk)
+    model.eval()
+    with torch.no_grad():
+        graphed = model(img).clone()
+        model.eval_cuda_graph = False
+        assert torch.equal(model(img), graphed) and not torch.equal(graphed, eager)

@@ -115,14 +115,16 @@ def main():
         run("c4_p4_512_b32_train", lambda: train_case(new_model(4), 32, 512, warmup=2, steps=4))
     if "c5" in args.cases:
         model = new_model(4).cuda().eval()
-        for B in (1, 2, 4, 8):
-            def infer(B=B):
-                img, _ = batch(B, 1024)
-                with torch.no_grad():
-                    r = time_steps(lambda: model(img), 5, 30)
-                r.update({"batch": B, "hw": 1024, "img_per_s": B / (r["ms_mean"] * 1e-3), "p50_latency_ms": r["ms_p50"]})
-                return r
-            run(f"c5_p4_1024_b{B}_eval", infer)
+        for graph in (False, True):
+            model.eval_cuda_graph = graph
+            for B in (1, 2, 4, 8):
+                def infer(B=B):
+                    img, _ = batch(B, 1024)
+                    with torch.no_grad():
+                        r = time_steps(lambda: model(img), 10, 50)
+                    r.update({"batch": B, "hw": 1024, "img_per_s": B / (r["ms_mean"] * 1e-3), "p50_latency_ms": r["ms_p50"], "cuda_graph": graph})
+                    return r
+                run(f"c5_p4_1024_b{B}_eval" + ("_cudagraph" if graph else ""), infer)
     if "c6" in args.cases:
         run("c6_datapath_768x1024_to_224_b64", datapath_case)
     print(json.dumps(res))
