@@ -266,30 +266,48 @@ __global__ void block_param_grads_kernel(const double* red, int C, BlockGradPtrs
 // =============================================================================================
 // forward: bn+relu -> adaptive pool (separable)
 // =============================================================================================
-template <int VEC>
+// MASKS: two more planes behind tmp ([3][B, H, P, C]): the row means of m = [bn(a0) > 0] and of m * a0.  Pooled like the
+// activation itself they give, per pooling window w, mean_w(m) and mean_w(m a0), from which the backward gets the
+// pool^T(dpooled) part of the BatchNorm-2 reductions without a gather pass over the feature map:
+//   sum_pix poolT(dp)[pix] m[pix]      = sum_w dp[w] mean_w(m)
+//   sum_pix poolT(dp)[pix] m[pix] a0   = sum_w dp[w] mean_w(m a0)          (dfcsa_pool_window_terms)
+template <int VEC, bool MASKS>
 __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, int W, int C, const float* scale,
                                  const float* shift, int P, float* tmp) {
   const int CV = C / VEC;
   const long long total = static_cast<long long>(B) * H * P * CV;
+  const long long plane = static_cast<long long>(B) * H * P * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     int cv, j, y; long long b;
     decode4(i, total < (1LL << 31), CV, P, H, cv, j, y, b);
     int lo, hi; pool_win(j, W, P, lo, hi);
-    float sc[VEC], sh[VEC], acc[VEC];
+    float sc[VEC], sh[VEC], acc[VEC], am[MASKS ? VEC : 1], ax[MASKS ? VEC : 1];
     ldf<VEC>(scale + cv * VEC, sc); ldf<VEC>(shift + cv * VEC, sh);
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+#pragma unroll
+    for (int v = 0; v < (MASKS ? VEC : 1); ++v) { am[v] = 0.f; ax[v] = 0.f; }
     const act_t* row = a0 + ((b * H + y) * W) * ld + cv * VEC;
     for (int x = lo; x < hi; ++x) {
       float t[VEC]; ldv<VEC>(row + x * ld, t);
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[v] += fmax_nan(fmaf(t[v], sc[v], sh[v]), 0.f);
+      for (int v = 0; v < VEC; ++v) {
+        const float bnv = fmaf(t[v], sc[v], sh[v]);
+        acc[v] += fmax_nan(bnv, 0.f);
+        if constexpr (MASKS) {
+          if (bnv > 0.f) { am[v] += 1.f; ax[v] += t[v]; }
+        }
+      }
     }
     const float inv = 1.f / static_cast<float>(hi - lo);
     float* o = tmp + ((b * H + y) * P + j) * C + cv * VEC;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) o[v] = acc[v] * inv;
+    if constexpr (MASKS) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { o[plane + v] = am[v] * inv; o[2 * plane + v] = ax[v] * inv; }
+    }
   }
 }
 // out[b, i, j, c] = scale_out * sum_y wgt(i, y) * tmp[b, y, j, c]; mode 0: pool windows over y, mode 1: bilinear^T.
@@ -958,6 +976,79 @@ branch_bwd_apply_kernel(const grad_t* __restrict__ dz, long long ld_dz, const ac
   }
 }
 
+// red += (sum d m, sum d m xhat) with m = [bn(x) > 0]: the BatchNorm + ReLU backward reduction over a plain (dy, x) pair -
+// what is left of branch_bwd_reduce2 once the pool^T(dpooled) part comes from the window means (no gather per pixel)
+template <int VEC, int OCC>
+__global__ void __launch_bounds__(256, OCC)
+bn_bwd_reduce_kernel(const grad_t* __restrict__ dy, long long ld_dy, const act_t* __restrict__ x, long long ld_x, long long M, int C,
+                     const float* scale, const float* shift, const float* mean, const float* invstd, double* red, int CL, int PL) {
+  __shared__ float s_red[2 * 256 * VEC];
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * VEC;
+  const int c = c_base + cl * VEC;
+  float acc[2][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
+  if (pl < PL && c < C) {
+    float sc[VEC], sh[VEC];
+    ldf<VEC>(scale + c, sc); ldf<VEC>(shift + c, sh);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    for (long long m0 = static_cast<long long>(blockIdx.x) * PL + pl; m0 < M; m0 += kPixInFlight * stride) {
+      RawV<VEC, grad_t> draw[kPixInFlight];
+      RawV<VEC, act_t> xraw[kPixInFlight];
+      bool ok[kPixInFlight];
+#pragma unroll
+      for (int u = 0; u < kPixInFlight; ++u) {
+        const long long m = m0 + u * stride;
+        ok[u] = m < M;
+        if (ok[u]) { draw[u] = ldraw<VEC>(dy + m * ld_dy + c); xraw[u] = ldraw<VEC>(x + m * ld_x + c); }
+      }
+#pragma unroll
+      for (int u = 0; u < kPixInFlight; ++u) {
+        if (ok[u]) {
+          float d[VEC], xv[VEC];
+          cvtraw<VEC>(draw[u], d); cvtraw<VEC>(xraw[u], xv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float dm = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
+            acc[0][v] += dm;
+            acc[1][v] = fmaf(dm, xv[v], acc[1][v]);
+          }
+        }
+      }
+    }
+  }
+  flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean, invstd, red, s_red);
+}
+
+// red[c] += sum_{b,w} dp m_mean;  red[C + c] += invstd (sum dp ma_mean - mean sum dp m_mean)   over the [B, P, P] windows
+__global__ void __launch_bounds__(256)
+pool_window_terms_kernel(const float* __restrict__ dp, const float* __restrict__ means, long long BW, int C, const float* mean,
+                         const float* invstd, double* red) {
+  // block: 32 channels x 8 window lanes
+  const int cl = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cl;
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    const float* mm = means;                       // mean_w(m)
+    const float* ma = means + BW * C;              // mean_w(m a0)
+    for (long long w = static_cast<long long>(blockIdx.x) * 8 + wl; w < BW; w += static_cast<long long>(gridDim.x) * 8) {
+      const float d = dp[w * C + c];
+      s0 = fmaf(d, mm[w * C + c], s0);
+      s1 = fmaf(d, ma[w * C + c], s1);
+    }
+  }
+  __shared__ float s[2][8][33];
+  s[0][wl][cl] = s0; s[1][wl][cl] = s1;
+  __syncthreads();
+  if (wl == 0 && c < C) {
+    float t0 = 0.f, t1 = 0.f;
+    for (int p = 0; p < 8; ++p) { t0 += s[0][p][cl]; t1 += s[1][p][cl]; }
+    atomicAdd(red + c, static_cast<double>(t0));
+    atomicAdd(red + C + c, static_cast<double>(invstd[c]) * (static_cast<double>(t1) - static_cast<double>(mean[c]) * static_cast<double>(t0)));
+  }
+}
+
 // =============================================================================================
 // layout / misc
 // =============================================================================================
@@ -1136,17 +1227,45 @@ extern "C" int dfcsa_block_param_grads(const double* red, int32_t C, float* dg1,
 
 extern "C" int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int32_t H, int32_t W, int32_t C,
                                      const float* scale, const float* shift, int32_t P, float* tmp, float* pooled,
-                                     void* stream) {
+                                     int32_t with_masks, void* stream) {
   DFCSA_CHECK_ARG(a0 && scale && shift && tmp && pooled && B > 0 && H > 0 && W > 0 && C > 0 && P > 0, "dfcsa_bnrelu_pool_fwd: bad args");
   const bool v8 = vec8_ok(C, {ld}, {a0, scale, shift, tmp});
   const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C);
-  VEC_DISPATCH(v8, (pool_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(A_(a0), ld, B, H, W, C, scale, shift, P, tmp)));
-  DFCSA_LAUNCH_CHECK("pool_rows_kernel");
-  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0)
-    cols_reduce_kernel<4><<<ew_blocks(static_cast<long long>(B) * P * P * (C / 4)), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
+  if (with_masks)
+    VEC_DISPATCH(v8, (pool_rows_kernel<VEC, true><<<ew_blocks(total), 256, 0, ST>>>(A_(a0), ld, B, H, W, C, scale, shift, P, tmp)));
   else
-    cols_reduce_kernel<1><<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
+    VEC_DISPATCH(v8, (pool_rows_kernel<VEC, false><<<ew_blocks(total), 256, 0, ST>>>(A_(a0), ld, B, H, W, C, scale, shift, P, tmp)));
+  DFCSA_LAUNCH_CHECK("pool_rows_kernel");
+  // with_masks: tmp / pooled hold three planes ([3][B, ...]); the column pass sees them as 3 B images
+  const int Bc = with_masks ? 3 * B : B;
+  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0)
+    cols_reduce_kernel<4><<<ew_blocks(static_cast<long long>(Bc) * P * P * (C / 4)), 256, 0, ST>>>(tmp, Bc, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
+  else
+    cols_reduce_kernel<1><<<ew_blocks(static_cast<long long>(Bc) * P * P * C), 256, 0, ST>>>(tmp, Bc, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
   DFCSA_LAUNCH_CHECK("cols_reduce_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_bn_bwd_reduce(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t M, int32_t C,
+                                   const float* scale, const float* shift, const float* mean, const float* invstd, double* red,
+                                   void* stream) {
+  DFCSA_CHECK_ARG(dy && x && scale && shift && mean && invstd && red && M > 0 && C > 0, "dfcsa_bn_bwd_reduce: bad args");
+  const bool v8 = vec8_ok(C, {ld_dy, ld_x}, {dy, x, scale, shift, mean, invstd});
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(3)), g.chunks);
+  OCC_DISPATCH(3, VEC_DISPATCH(v8, (bn_bwd_reduce_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(G_(dy), ld_dy, A_(x), ld_x, M, C, scale, shift, mean, invstd,
+                                                                                        red, g.CL, g.PL))));
+  DFCSA_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return DFCSA_OK;
+}
+
+extern "C" int dfcsa_pool_window_terms(const float* dpooled, const float* means, int32_t B, int32_t P, int32_t C, const float* mean,
+                                       const float* invstd, double* red, void* stream) {
+  DFCSA_CHECK_ARG(dpooled && means && mean && invstd && red && B > 0 && P > 0 && C > 0, "dfcsa_pool_window_terms: bad args");
+  const long long BW = static_cast<long long>(B) * P * P;
+  dim3 grid(static_cast<unsigned>(std::max<long long>(1, std::min<long long>((BW + 63) / 64, 148 * 2))), (C + 31) / 32);
+  pool_window_terms_kernel<<<grid, 256, 0, ST>>>(dpooled, means, BW, C, mean, invstd, red);
+  DFCSA_LAUNCH_CHECK("pool_window_terms_kernel");
   return DFCSA_OK;
 }
 

@@ -96,6 +96,7 @@ SYMBOLS = [
     "dfcsa_bnrelu_pool_fwd", "dfcsa_branch_act_fwd", "dfcsa_gate_mix_fwd", "dfcsa_block_out_fwd", "dfcsa_sum_out_fwd",
     "dfcsa_block_out_bwd_reduce", "dfcsa_bn_bwd_apply", "dfcsa_gate_mix_bwd_reduce", "dfcsa_gate_mix_bwd_apply",
     "dfcsa_branch_bwd_reduce1", "dfcsa_branch_bwd_reduce2", "dfcsa_branch_bwd_apply", "dfcsa_bn_param_grads", "dfcsa_block_param_grads",
+    "dfcsa_bn_bwd_reduce", "dfcsa_pool_window_terms",
     "dfcsa_nchw_to_nhwc", "dfcsa_nhwc_to_nchw", "dfcsa_colsum", "dfcsa_cast2d",
     "dfcsa_bce_dice_sums", "dfcsa_bce_dice_finalize", "dfcsa_bce_dice_bwd",
     "dfcsa_bce_dice_sums_batched", "dfcsa_bce_dice_finalize_batched",

@@ -468,6 +468,8 @@ def _attn_probs(qkv, nb, N, Cq, nq, out, lse=None, have_lse=False):
     ops.softmax_rows(S, out)
 
 
+import os as _os
+_WINDOW_TERMS = _os.environ.get("DFCSA_OLD_REDUCE2", "0") != "1"    # A/B switch for measurements (old: gather pass branch_bwd_reduce2)
 _ATTN_FUSED = True       # forward attention without the N^2 round trip when the probabilities are not kept for backward
 _ATTN_FUSED_BWD = True   # ... and the backward without any N^2 tensor (dfcsa_attn_bwd_fused)
 _ATTN_SMALL_MAX_N = 32   # up to here the whole attention core is one fp32 kernel per direction (dfcsa_attn_small_*)
@@ -644,10 +646,12 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     A0, R = AR[:, :C], AR[:, C:]
     bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
     bn2 = _bn_affine(bp.bn2, bp.b2, st[2 * C:3 * C] if training else None, st[4 * C:5 * C] if training else None, M, training, dev)
-    # pooled self-attention
-    tmp = _e((B, H, P, C), F32, dev)
-    pooled = _e((B * P * P, C), F32, dev)
-    ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled)
+    # pooled self-attention (when the backward will run, the pooling pass also emits the window means of the ReLU mask)
+    masks = ctx is not None and _WINDOW_TERMS
+    tmp = _e((3 if masks else 1, B, H, P, C), F32, dev)
+    pooled3 = _e((3 if masks else 1, B * P * P, C), F32, dev)
+    pooled = pooled3[0]
+    ops.bnrelu_pool_fwd(A0, B, H, W, bn2[0], bn2[1], P, tmp, pooled3, with_masks=masks)
     o = attention_forward(bp, pk, pooled, B, P * P, ctx)
     z = _e((M, 3 * C), F16, dev)
     ops.branch_act_fwd(L0, A0, B, H, W, bn1[0], bn1[1], bn2[0], bn2[1], o, P, bp.gamma.detach(), z, None)
@@ -668,6 +672,7 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
         ctx.B, ctx.H, ctx.W = B, H, W
         ctx.L0, ctx.A0, ctx.R, ctx.G0, ctx.F0, ctx.z, ctx.y, ctx.o = L0, A0, R, G0, F0, z, y, o
         ctx.bn1, ctx.bn2, ctx.bn3, ctx.bn4 = bn1, bn2, bn3, bn4
+        ctx.win_means = pooled3[1:] if masks else None
     return ctx
 
 
@@ -897,7 +902,13 @@ def block_backward(bp, pk, ctx, xw, dskip, dyp, dx_out, grads):
     ops.branch_bwd_reduce1(dz, ctx.L0, ctx.G0, B, H, W, bn1[0], bn1[1], bn1[2], bn1[3], bn3[0], bn3[1], ctx.o, P,
                            bp.gamma.detach(), red1, dgam, tmp, d_o)
     dpooled = attention_backward(bp, pk, ctx, d_o, B, P * P, grads)
-    ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
+    if ctx.win_means is not None:
+        # BatchNorm-2 sums without a gather pass: the dA part from a plain (dA, A0) reduction, the pool^T(dpooled) part
+        # from the window means the forward pooling emitted (adaptive_avg_pool^T is linear)
+        ops.bn_bwd_reduce(dz[:, 2 * C:], ctx.A0, bn2[0], bn2[1], bn2[2], bn2[3], red2)
+        ops.pool_window_terms(dpooled, ctx.win_means, B, P, C, bn2[2], bn2[3], red2)
+    else:
+        ops.branch_bwd_reduce2(dz, ctx.A0, B, H, W, bn2[0], bn2[1], bn2[2], bn2[3], dpooled, P, red2)
     dL0, dA0 = dF0, dG0     # both dead after the GEMMs above: reuse their storage
     ops.branch_bwd_apply(dz, ctx.L0, ctx.A0, B, H, W, bn1, red1, bn2, red2, dpooled, P, dL0, dA0)
     # every small parameter gradient of the block (4 x BatchNorm weight / bias, gamma, res_scale) in one launch

@@ -238,9 +238,21 @@ def block_param_grads(red, Cn, bn_grads, drs=None, dgam=None):
     L.call("dfcsa_block_param_grads", L.ptr(red), Cn, *args, L.ptr(drs), L.ptr(dgam), L.stream())
 
 
-def bnrelu_pool_fwd(a0, B, H, W, scale, shift, P, tmp, pooled):
+def bnrelu_pool_fwd(a0, B, H, W, scale, shift, P, tmp, pooled, with_masks=False):
+    """with_masks: tmp [3, B, H, P, C] and pooled [3, B*P*P, C] - plane 0 the pooled activation, planes 1 / 2 the window means
+    of the ReLU mask and of mask * A0 (for pool_window_terms in the backward pass)."""
     L.call("dfcsa_bnrelu_pool_fwd", L.ptr(a0), _i64(_mat(a0)), B, H, W, a0.shape[1], L.ptr(scale), L.ptr(shift), P,
-                                          L.ptr(tmp), L.ptr(pooled), L.stream())
+                                          L.ptr(tmp), L.ptr(pooled), 1 if with_masks else 0, L.stream())
+
+
+def bn_bwd_reduce(dy, x, scale, shift, mean, invstd, red):
+    M, Cn = x.shape
+    L.call("dfcsa_bn_bwd_reduce", L.ptr(dy), _i64(_mat(dy)), L.ptr(x), _i64(_mat(x)), _i64(M), Cn, L.ptr(scale), L.ptr(shift),
+           L.ptr(mean), L.ptr(invstd), L.ptr(red), L.stream())
+
+
+def pool_window_terms(dpooled, means, B, P, Cn, mean, invstd, red):
+    L.call("dfcsa_pool_window_terms", L.ptr(dpooled), L.ptr(means), B, P, Cn, L.ptr(mean), L.ptr(invstd), L.ptr(red), L.stream())
 
 
 def branch_act_fwd(l0, a0, B, H, W, s1, t1, s2, t2, o, P, gamma, z, zb=None):

@@ -251,10 +251,13 @@ int dfcsa_sum_out_fwd(const void* a, int64_t ld_a, const void* b, int64_t ld_b, 
  * All activations fp16 NHWC, per-channel BN affine (scale, shift) fp32.
  * ---------------------------------------------------------------------------------------------------------- */
 /* a = relu(bn2(A0)); pooled = adaptive_avg_pool2d(a, P) (reference :24).  Separable: rows then columns.
- * tmp is [B, H, P, C] fp32 scratch; pooled is [B, P, P, C] fp32. */
+ * tmp is [B, H, P, C] fp32 scratch; pooled is [B, P, P, C] fp32.
+ * with_masks != 0 (training): tmp and pooled hold THREE planes, [3][B, H, P, C] and [3][B, P, P, C]: plane 0 as above,
+ * plane 1 = the window means of m = [bn2(A0) > 0], plane 2 = the window means of m * A0 - what dfcsa_pool_window_terms
+ * needs in the backward pass. */
 int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int32_t H, int32_t W, int32_t C,
                           const float* scale, const float* shift, int32_t P,
-                          float* tmp, float* pooled, void* stream);
+                          float* tmp, float* pooled, int32_t with_masks, void* stream);
 /* L = relu(bn1(L0)) -> z[:, C:2C];  A = gamma*bilinear_up(o) + relu(bn2(A0)) -> z[:, 2C:3C]
  * (reference :97,:99,:36,:38).  o is [B, P, P, C] fp32.  zb: optional bf16 shadow of z (same channel offsets).
  * l0 may be NULL: only the A half is computed (inference path: L comes straight out of the folded conv + ReLU). */
@@ -323,6 +326,16 @@ int dfcsa_branch_bwd_reduce2(const void* dz, int64_t ld_dz, const void* a0, int6
                              int32_t B, int32_t H, int32_t W, int32_t C,
                              const float* scale2, const float* shift2, const float* mean2, const float* invstd2,
                              const float* dpooled, int32_t P, double* red2, void* stream);
+/* The same reduction without a gather pass.  adaptive_avg_pool^T is linear, so its part of the two sums only needs the
+ * per-window means the forward pooling pass can emit (dfcsa_bnrelu_pool_fwd with_masks):
+ *   sum_pix poolT(dp)[pix] m[pix] = sum_w dp[w] mean_w(m),   sum_pix poolT(dp)[pix] m[pix] A0[pix] = sum_w dp[w] mean_w(m A0)
+ * bn_bwd_reduce:     red += (sum d m, sum d m xhat), m = [x*scale+shift > 0], over a plain (dy, x) pair (here: dA, A0);
+ * pool_window_terms: red += the window part; means = planes 1 and 2 of the forward's pooled buffer ([2][B, P, P, C]). */
+int dfcsa_bn_bwd_reduce(const void* dy, int64_t ld_dy, const void* x, int64_t ld_x, int64_t M, int32_t C,
+                        const float* scale, const float* shift, const float* mean, const float* invstd, double* red,
+                        void* stream);
+int dfcsa_pool_window_terms(const float* dpooled, const float* means, int32_t B, int32_t P, int32_t C, const float* mean,
+                            const float* invstd, double* red, void* stream);
 /* pass 3: dL0, dA0 (bf16) from the two reductions */
 int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void* l0, int64_t ld_l0,
                            const void* a0, int64_t ld_a0, int32_t B, int32_t H, int32_t W, int32_t C,

@@ -454,7 +454,9 @@ def test_eval_cuda_graph_matches_eager_and_tracks_weight_changes(cuda):
         # in-place weight change through torch
         model.final_conv.bias.add_(0.25)
         assert torch.allclose(model(img), want + 0.25, atol=1e-6)
-        model.down2.conv_branch[1].running_var.mul_(4.0)                     # a BatchNorm buffer: folded scale changes
+        for bn in (model.down1.fusion_conv[1], model.up_conv1.fusion_conv[1], model.up_conv1.conv_branch[1]):
+            bn.running_mean.add_(0.5)                                        # BatchNorm buffers: the folded biases change
+            bn.running_var.mul_(4.0)                                         # ... and the folded weight scales
         model.eval_cuda_graph = False
         eager = model(img).clone()
         model.eval_cuda_graph = True

@@ -243,3 +243,41 @@ def test_branch_backward_at_every_pool_regime(cuda, B, H, W, C, P):
     da0_ref, s2a, s2b = bn_bwd(dA + _nhwc2d(x_n.grad), a0, bn2)
     assert _rel(red2[:C], s2a) < 1e-3 and _rel(red2[C:], s2b) < 2e-3
     assert _rel(da0, da0_ref) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,P", SP)
+def test_window_terms_reduction_equals_gather_reduction(cuda, B, H, W, C, P):
+    """The BatchNorm-2 backward sums without a gather pass: dfcsa_bn_bwd_reduce over (dA, A0) + dfcsa_pool_window_terms over
+    the window means emitted by dfcsa_bnrelu_pool_fwd(with_masks) equal branch_bwd_reduce2's per-pixel pool^T gather (and the
+    torch reference), including overlapping windows (s = 14, P = 4) and pooled maps larger than the feature map."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(107)
+    M = B * H * W
+    dz = torch.randn(M, 3 * C, generator=g).to(cuda).bfloat16()
+    a0 = torch.randn(M, C, generator=g).to(cuda).half()
+    dpooled = torch.randn(B * P * P, C, generator=g).to(cuda)
+    bn2 = _bn_stats(a0, g, cuda)
+    tmp = torch.empty(3, B, H, P, C, device=cuda)
+    pooled3 = torch.empty(3, B * P * P, C, device=cuda)
+    ops.bnrelu_pool_fwd(a0, B, H, W, bn2[0], bn2[1], P, tmp, pooled3, with_masks=True)
+    red_new = torch.zeros(2 * C, device=cuda, dtype=torch.float64)
+    ops.bn_bwd_reduce(dz[:, 2 * C:], a0, *bn2, red_new)
+    ops.pool_window_terms(dpooled, pooled3[1:], B, P, C, bn2[2], bn2[3], red_new)
+    red_old = torch.zeros(2 * C, device=cuda, dtype=torch.float64)
+    ops.branch_bwd_reduce2(dz, a0, B, H, W, *bn2, dpooled, P, red_old)
+    torch.cuda.synchronize()
+    # plane 0 is the ordinary pooled activation, planes 1 / 2 the pooled mask and mask * A0
+    sc, sh, mean, invstd = bn2
+    bnv = _nchw(a0, B, H, W) * sc.view(1, C, 1, 1) + sh.view(1, C, 1, 1)
+    m = (bnv > 0).float()
+    assert _rel(pooled3[0], _nhwc2d(F.adaptive_avg_pool2d(torch.relu(bnv), P))) < 1e-5
+    assert _rel(pooled3[1], _nhwc2d(F.adaptive_avg_pool2d(m, P))) < 1e-5
+    assert _rel(pooled3[2], _nhwc2d(F.adaptive_avg_pool2d(m * _nchw(a0, B, H, W), P))) < 1e-5
+    # torch reference of the two sums
+    x_n = torch.zeros(B, C, H, W, device=cuda, requires_grad=True)
+    (F.adaptive_avg_pool2d(x_n, P) * dpooled.view(B, P, P, C).permute(0, 3, 1, 2)).sum().backward()
+    d = (dz[:, 2 * C:].float() + _nhwc2d(x_n.grad)) * _nhwc2d(m)
+    xhat = (a0.float() - mean) * invstd
+    for red in (red_new, red_old):
+        assert _rel(red[:C], d.sum(0)) < 1e-3 and _rel(red[C:], (d * xhat).sum(0)) < 2e-3
+    assert _rel(red_new, red_old) < 1e-3

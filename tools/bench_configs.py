@@ -123,6 +123,16 @@ def main():
                     with torch.no_grad():
                         r = time_steps(lambda: model(img), 10, 50)
                     r.update({"batch": B, "hw": 1024, "img_per_s": B / (r["ms_mean"] * 1e-3), "p50_latency_ms": r["ms_p50"], "cuda_graph": graph})
+                    if PROFILE and not graph:
+                        from dfcsa import _lib
+                        _lib.PROF = prof = _lib.Profiler()
+                        with torch.no_grad():
+                            model(img)
+                        _lib.PROF = None
+                        summ = sorted(prof.summary().items(), key=lambda kv: -kv[1]["ms"])
+                        r["profile_ms"] = {k: [round(v["ms"], 3), v["launches"]] for k, v in summ[:16]}
+                        det = sorted(prof.detail(tags=("conv_tc", "conv_simt")).items(), key=lambda kv: -kv[1]["ms"])
+                        r["gemm_ms"] = {k: [round(v["ms"], 3), round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)] for k, v in det[:24]}
                     return r
                 run(f"c5_p4_1024_b{B}_eval" + ("_cudagraph" if graph else ""), infer)
     if "c6" in args.cases:
