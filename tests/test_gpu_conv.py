@@ -428,6 +428,14 @@ def test_attn_small_matches_torch(cuda, B, N, Cq, C):
     torch.cuda.synchronize()
     assert _rel_err(attn, attn_ref) < 1e-5 and _rel_err(o.view(B, N, C), o_ref) < 1e-5
     assert _rel_err(dqkv, ref_in.grad) < 1e-4
+    # the optional bias-gradient outputs ACCUMULATE the column sums of dq / dk / dv (q / k / v conv biases)
+    dbq, dbk, dbv = torch.full((Cq,), 0.5, device=cuda), torch.zeros(Cq, device=cuda), torch.zeros(C, device=cuda)
+    dqkv2 = torch.empty_like(qkv)
+    ops.attn_small_bwd(qkv, attn, d_o, B, N, Cq, C, dqkv2, dbq, dbk, dbv)
+    torch.cuda.synchronize()
+    gsum = ref_in.grad.sum(0)
+    assert torch.equal(dqkv2, dqkv)
+    assert _rel_err(dbq, gsum[:Cq] + 0.5) < 1e-4 and _rel_err(dbk, gsum[Cq:2 * Cq]) < 1e-4 and _rel_err(dbv, gsum[2 * Cq:]) < 1e-4
 
 
 @pytest.mark.parametrize("case", [(1, 32, 32, 128, 64, 1, 0), (2, 9, 11, 256, 320, 0, 0), (2, 6, 10, 128, 64, 0, 2), (1, 20, 20, 64, 128, 1, 0)])
@@ -540,3 +548,58 @@ def test_branch_backward_passes_match_torch(cuda, B, H, W, C, P):
     da0_ref, s2a, s2b = bn_bwd(dA_tot, a0, bn2)
     assert _rel_err(red2[:C].float(), s2a) < 1e-3 and _rel_err(red2[C:].float(), s2b) < 1e-3
     assert _rel_err(da0, da0_ref) < 6e-3
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+@pytest.mark.parametrize("case", [(2, 12, 12, [128], "1", 128, 64), (1, 20, 20, [64], "3", 64, 0), (2, 9, 11, [64], "1", 192, 72),
+                                  (1, 16, 16, [64, 64], "31", 128, 0)])
+def test_conv_gemm_bias_relu_epilogue(cuda, case, backend):
+    """Inference path: bias + ReLU on the output columns n < act_cols in the GEMM epilogue (BatchNorm folded into the packed
+    weights, reference inference.py:100 eval mode), both backends, against torch."""
+    from dfcsa import ops
+    B, H, W, cins, modes, N, act_cols = case
+    g = torch.Generator().manual_seed(31)
+    segs, ref, wparts = [], 0, []
+    for c, m in zip(cins, modes):
+        x = torch.randn(B, H, W, c, generator=g).to(cuda).half()
+        k = 3 if m == "3" else 1
+        wt = (torch.randn(N, c, k, k, generator=g) / (k * k * c) ** 0.5).to(cuda).half()
+        ref = ref + F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=k // 2)
+        segs.append((x.reshape(-1, c), _MODE[m]))
+        wparts.append(_pack_fwd(wt))
+    w = torch.cat(wparts, dim=1).contiguous()
+    if backend == ops.BACKEND_SIMT:
+        w = w.float()
+    bias = torch.randn(N, generator=g).to(cuda)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, N) + bias
+    nrelu = act_cols or N
+    ref[:, :nrelu] = torch.relu(ref[:, :nrelu])
+    out = torch.zeros(B * H * W, N, device=cuda, dtype=torch.float16)
+    ops.conv_gemm(B, H, W, segs, w, N, out, bias=bias, backend=backend, act=1, act_cols=act_cols)
+    torch.cuda.synchronize()
+    assert _rel_err(out, ref) < 4e-3
+    assert bool((out[:, :nrelu] >= 0).all())
+    if nrelu < N:
+        assert bool((out[:, nrelu:] < 0).any())           # the columns past act_cols stay linear
+
+
+@pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
+def test_fp16_outputs_saturate_instead_of_overflowing(cuda, backend):
+    """Precision policy: forward activations are stored in fp16; a result beyond +-65504 is clamped to the
+    largest finite value (never inf, which would poison the next BatchNorm), and a NaN input still propagates so that the
+    optimizer's non-finite check skips the step."""
+    from dfcsa import ops
+    B, H, W, C, N = 1, 8, 16, 64, 64
+    x = torch.full((B * H * W, C), 3000.0, device=cuda, dtype=torch.float16)
+    x[1::2] = -3000.0
+    w = torch.ones(N, C, device=cuda, dtype=torch.float16 if backend == ops.BACKEND_TC else torch.float32)
+    out = torch.zeros(B * H * W, N, device=cuda, dtype=torch.float16)
+    st = torch.zeros(2 * N, device=cuda, dtype=torch.float64)
+    ops.conv_gemm(B, H, W, [(x, ops.TAP_1x1)], w, N, out, stats=st, backend=backend)      # |sum| = 192000 > 65504
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out).all()) and float(out.max()) == 65504.0 and float(out.min()) == -65504.0
+    assert bool(torch.isfinite(st).all())
+    x[5, 3] = float("nan")
+    ops.conv_gemm(B, H, W, [(x, ops.TAP_1x1)], w, N, out, backend=backend)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(out[5]).all()) and bool(torch.isfinite(out[6]).all())
