@@ -282,8 +282,20 @@ def run_dfcsa(args):
     # end of the timed region: every sample is under load
     sampler = ClockSampler(local) if rank == 0 else None
     # ---------------- warm-up ----------------
+    # big configurations (c4: ~95 GB of activations per forward): the per-kernel CUDA-event profile is taken during the
+    # second (eager) warm-up call, because a later eager step beside the captured graph's private memory pool does not fit
+    prof_early = args.config == "c4" and rank == 0
+    prof = None
     for i in range(max(args.warmup, 3)):
+        if prof_early and i == 1:
+            prof = _lib.Profiler()
+            _lib.PROF = prof
+            pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            pe0.record()
         step(*devb[i % 2])
+        if prof_early and i == 1:
+            pe1.record()
+            _lib.PROF = None
     barrier()
 
     # ---------------- timed: inputs resident in HBM (no per-call instrumentation) ----------------
@@ -301,21 +313,26 @@ def run_dfcsa(args):
     launches = _lib.LAUNCHES - launches0
 
     # ---------------- the same steps again with a CUDA-event pair around every ABI call (per-kernel shares) ----------
-    prof = _lib.Profiler() if rank == 0 else None
-    _lib.PROF = prof
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    p0.record()
-    for i in range(args.steps):
-        tr.train_step(*devb[i % 2], MICRO)
-    p1.record()
-    barrier()
-    ms_prof = p0.elapsed_time(p1)
-    _lib.PROF = None
+    prof_steps = args.steps
+    if args.config == "c4":
+        prof_steps = 1
+        ms_prof = pe0.elapsed_time(pe1) if prof is not None else 0.0
+    else:
+        prof = _lib.Profiler() if rank == 0 else None
+        _lib.PROF = prof
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        p0.record()
+        for i in range(args.steps):
+            tr.train_step(*devb[i % 2], MICRO)
+        p1.record()
+        barrier()
+        ms_prof = p0.elapsed_time(p1)
+        _lib.PROF = None
     kern = prof.summary() if prof else {}
     if prof and args.detail:
         det = prof.detail(tags=("conv_tc", "wgrad_tc", "conv_simt", "wgrad_simt"))
-        rows = sorted(({"shape": k, "ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+        rows = sorted(({"shape": k, "ms_per_step": v["ms"] / prof_steps, "launches_per_step": v["launches"] / prof_steps,
                         "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} for k, v in det.items()), key=lambda r: -r["ms_per_step"])
         os.makedirs(os.path.dirname(os.path.abspath(args.detail)), exist_ok=True)
         json.dump(rows, open(args.detail, "w"), indent=1)
@@ -360,7 +377,7 @@ def run_dfcsa(args):
                                "of one step (33.2 GB; algorithmic operand + result bytes 34.4 GB)")
         except Exception:  # noqa: BLE001
             pass
-        shares = {k: {"ms_per_step": v["ms"] / args.steps, "share": v["ms"] / ms_prof, "launches_per_step": v["launches"] / args.steps,
+        shares = {k: {"ms_per_step": v["ms"] / prof_steps, "share": v["ms"] / ms_prof, "launches_per_step": v["launches"] / prof_steps,
                       **({"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} if v["flops"] > 0 and v["ms"] > 0 else {})}
                   for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
         # CPU baseline: the oracle port of the same step on this box's host cores (bounded sample)
@@ -393,8 +410,8 @@ def run_dfcsa(args):
                          "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak else None,
                          "peak_source": f"{pk_src} bf16 sustained", "traffic": traffic, "traffic_unit": "bytes per launch",
                          "traffic_source": traffic_src,
-                         "launches_per_step": conv["launches"] / args.steps, "ms_per_step": conv["ms"] / args.steps},
-            "profiled_ms_per_step": ms_prof / args.steps,
+                         "launches_per_step": conv["launches"] / prof_steps, "ms_per_step": conv["ms"] / prof_steps},
+            "profiled_ms_per_step": ms_prof / prof_steps,
             "kernels": shares,
             "cpu_baseline": cpu,
             "reference_gpu": ref_gpu,

@@ -58,6 +58,12 @@ static inline bool vec8_ok(int C, std::initializer_list<long long> lds, std::ini
   return true;
 }
 
+constexpr int kGatePix = 2;   // pixels per grid-stride step in the gate kernels
+
+// sigmoid with the fast reciprocal (the IEEE division costs ~10 issue slots per element; the gate kernels are bound by
+// instruction issue + memory latency together, profiles/ncu_block1_sections_r02.csv)
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+
 // adaptive_avg_pool2d window of output index i: [lo, hi)
 __device__ __forceinline__ void pool_win(int i, int s, int P, int& lo, int& hi) {
   lo = (i * s) / P;
@@ -289,14 +295,24 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
 #pragma unroll
     for (int v = 0; v < (MASKS ? VEC : 1); ++v) { am[v] = 0.f; ax[v] = 0.f; }
     const act_t* row = a0 + ((b * H + y) * W) * ld + cv * VEC;
-    for (int x = lo; x < hi; ++x) {
-      float t[VEC]; ldv<VEC>(row + x * ld, t);
+    // four pixels of the window per step with their loads issued together: one dependent 16-byte load per thread at a time
+    // left this pass at 0.4 - 0.6 of copy bandwidth (ncu: 34 % occupancy, long-scoreboard stalls)
+    for (int x = lo; x < hi; x += 4) {
+      RawV<VEC, act_t> raw[4];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float bnv = fmaf(t[v], sc[v], sh[v]);
-        acc[v] += fmax_nan(bnv, 0.f);
-        if constexpr (MASKS) {
-          if (bnv > 0.f) { am[v] += 1.f; ax[v] += t[v]; }
+      for (int u = 0; u < 4; ++u) raw[u] = ldraw<VEC>(row + min(x + u, hi - 1) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (x + u < hi) {
+          float t[VEC]; cvtraw<VEC>(raw[u], t);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float bnv = fmaf(t[v], sc[v], sh[v]);
+            acc[v] += fmax_nan(bnv, 0.f);
+            if constexpr (MASKS) {
+              if (bnv > 0.f) { am[v] += 1.f; ax[v] += t[v]; }
+            }
+          }
         }
       }
     }
@@ -458,17 +474,32 @@ gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const 
   if (pl >= PL || c >= C) return;
   float sc[VEC], sh[VEC];
   ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh);
-  for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-    float g[VEC], l[VEC], a[VEC], f[VEC];
-    ldv<VEC>(g0 + m * ld_g0 + c, g);
-    ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a);
+  // kGatePix pixels per step, every load issued before the first use (see branch_act_fwd_kernel): the sigmoid makes the
+  // compute phase long enough that one pixel at a time leaves the memory pipe idle a third of the time
+  const long long stride = static_cast<long long>(gridDim.x) * PL;
+  for (long long m0 = static_cast<long long>(blockIdx.x) * PL + pl; m0 < M; m0 += kGatePix * stride) {
+    RawV<VEC, act_t> graw[kGatePix], lraw[kGatePix], araw[kGatePix];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
-      f[v] = gg * l[v] + (1.f - gg) * a[v];
+    for (int u = 0; u < kGatePix; ++u) {
+      const long long m = min(m0 + u * stride, M - 1);
+      graw[u] = ldraw<VEC>(g0 + m * ld_g0 + c);
+      lraw[u] = ldraw<VEC>(z + m * ld_z + C + c); araw[u] = ldraw<VEC>(z + m * ld_z + 2 * C + c);
     }
-    stv<VEC>(z + m * ld_z + c, f);
-    if (zb != nullptr) stv<VEC>(zb + m * ld_zb + c, f);
+#pragma unroll
+    for (int u = 0; u < kGatePix; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        float g[VEC], l[VEC], a[VEC], f[VEC];
+        cvtraw<VEC>(graw[u], g); cvtraw<VEC>(lraw[u], l); cvtraw<VEC>(araw[u], a);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const float gg = fast_sigmoid(fmaf(g[v], sc[v], sh[v]));
+          f[v] = gg * l[v] + (1.f - gg) * a[v];
+        }
+        stv<VEC>(z + m * ld_z + c, f);
+        if (zb != nullptr) stv<VEC>(zb + m * ld_zb + c, f);
+      }
+    }
   }
 }
 
@@ -693,16 +724,30 @@ gate_mix_bwd_reduce_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lo
   if (pl < PL && c < C) {
     float sc[VEC], sh[VEC];
     ldf<VEC>(s3 + c, sc); ldf<VEC>(t3 + c, sh);
-    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      float df[VEC], l[VEC], a[VEC], g[VEC];
-      ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a);
-      ldv<VEC>(g0 + m * ld_g0 + c, g);
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    for (long long m0 = static_cast<long long>(blockIdx.x) * PL + pl; m0 < M; m0 += kGatePix * stride) {
+      RawV<VEC, grad_t> draw[kGatePix];
+      RawV<VEC, act_t> lraw[kGatePix], araw[kGatePix], graw[kGatePix];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
-        const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
-        acc[0][v] += ds;
-        acc[1][v] = fmaf(ds, g[v], acc[1][v]);
+      for (int u = 0; u < kGatePix; ++u) {
+        const long long m = min(m0 + u * stride, M - 1);
+        draw[u] = ldraw<VEC>(dz + m * ld_dz + c);
+        lraw[u] = ldraw<VEC>(z + m * ld_z + C + c); araw[u] = ldraw<VEC>(z + m * ld_z + 2 * C + c);
+        graw[u] = ldraw<VEC>(g0 + m * ld_g0 + c);
+      }
+#pragma unroll
+      for (int u = 0; u < kGatePix; ++u) {
+        if (m0 + u * stride < M) {
+          float df[VEC], l[VEC], a[VEC], g[VEC];
+          cvtraw<VEC>(draw[u], df); cvtraw<VEC>(lraw[u], l); cvtraw<VEC>(araw[u], a); cvtraw<VEC>(graw[u], g);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float gg = fast_sigmoid(fmaf(g[v], sc[v], sh[v]));
+            const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
+            acc[0][v] += ds;
+            acc[1][v] = fmaf(ds, g[v], acc[1][v]);
+          }
+        }
       }
     }
   }
@@ -720,17 +765,32 @@ gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lon
   float sc[VEC], sh[VEC], p[VEC], q[VEC];
   bn_bwd_coeffs<VEC>(s3, mean3, invstd3, red3, C, c, 1.0 / static_cast<double>(M), sc, p, q);
   ldf<VEC>(t3 + c, sh);
-  for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-    float df[VEC], l[VEC], a[VEC], g[VEC], o[VEC];
-    ldv<VEC>(dz + m * ld_dz + c, df);
-    ldv<VEC>(z + m * ld_z + C + c, l); ldv<VEC>(z + m * ld_z + 2 * C + c, a); ldv<VEC>(g0 + m * ld_g0 + c, g);
+  const long long stride = static_cast<long long>(gridDim.x) * PL;
+  for (long long m0 = static_cast<long long>(blockIdx.x) * PL + pl; m0 < M; m0 += kGatePix * stride) {
+    RawV<VEC, grad_t> draw[kGatePix];
+    RawV<VEC, act_t> lraw[kGatePix], araw[kGatePix], graw[kGatePix];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      const float gg = 1.f / (1.f + __expf(-fmaf(g[v], sc[v], sh[v])));
-      const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
-      o[v] = fmaf(sc[v], ds, fmaf(p[v], g[v], q[v]));
+    for (int u = 0; u < kGatePix; ++u) {
+      const long long m = min(m0 + u * stride, M - 1);
+      draw[u] = ldraw<VEC>(dz + m * ld_dz + c);
+      lraw[u] = ldraw<VEC>(z + m * ld_z + C + c); araw[u] = ldraw<VEC>(z + m * ld_z + 2 * C + c);
+      graw[u] = ldraw<VEC>(g0 + m * ld_g0 + c);
     }
-    stv<VEC>(dg0 + m * ld_dg0 + c, o);
+#pragma unroll
+    for (int u = 0; u < kGatePix; ++u) {
+      const long long m = m0 + u * stride;
+      if (m < M) {
+        float df[VEC], l[VEC], a[VEC], g[VEC], o[VEC];
+        cvtraw<VEC>(draw[u], df); cvtraw<VEC>(lraw[u], l); cvtraw<VEC>(araw[u], a); cvtraw<VEC>(graw[u], g);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          const float gg = fast_sigmoid(fmaf(g[v], sc[v], sh[v]));
+          const float ds = df[v] * (l[v] - a[v]) * gg * (1.f - gg);
+          o[v] = fmaf(sc[v], ds, fmaf(p[v], g[v], q[v]));
+        }
+        stv<VEC>(dg0 + m * ld_dg0 + c, o);
+      }
+    }
   }
 }
 
@@ -763,7 +823,7 @@ branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long lon
         // exactly what the later passes read back
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-          const float gg = 1.f / (1.f + __expf(-fmaf(gv[v], sc3[v], sh3[v])));
+          const float gg = fast_sigmoid(fmaf(gv[v], sc3[v], sh3[v]));
           dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
           da[v] = fmaf(df[v], 1.f - gg, da[v]);
         }

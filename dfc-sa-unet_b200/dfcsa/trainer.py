@@ -22,6 +22,9 @@ from .metrics import bce_dice_with_logits, calculate_metrics
 from .optim import FusedSGD
 
 
+_DDP_OVERLAP = os.environ.get("DFCSA_DDP_OVERLAP", "1") != "0"     # per-bucket all-reduce overlapped with the backward pass
+
+
 class StepResult:
     __slots__ = ("stats",)
 
@@ -154,7 +157,11 @@ class Trainer:
         opt.zero_grad()
         k = int(micro_batches)
         if k <= 1:
-            stats = self._forward_backward(images, masks, self._reducer.reduce if self.world > 1 else None)
+            overlap = self.world > 1 and self.config.get("training", {}).get("ddp_overlap", _DDP_OVERLAP)
+            stats = self._forward_backward(images, masks, self._reducer.reduce if overlap else None)
+            if self.world > 1 and not overlap:      # every bucket after the backward pass, nothing shares the SMs with it
+                for b in range(len(self._reducer.ranges)):
+                    self._reducer.reduce(b)
         else:
             if images.shape[0] % k:
                 raise ValueError(f"dfcsa: batch of {images.shape[0]} does not split into {k} equal micro-batches")
