@@ -54,6 +54,7 @@ struct ConvTcArgs {
   int fixed_nt;     // gridDim.x is a multiple of n_tiles_n: a CTA sees ONE n tile for the whole kernel (nt == blockIdx.x % n_tiles_n)
   int wide_out, wide_shadow;   // 32-byte stores legal (16-bit tensor, pitch % 16 == 0, base 32-byte aligned, no accumulate)
   int act_cols;     // ReLU on the output columns n < act_cols (0: no activation)
+  int stats_cols;   // BatchNorm sums only for the output columns n < stats_cols
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -395,6 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             else store_chunk<__nv_bfloat16>(a.shadow + pix * a.ld_shadow + cn, v, ncols, false);
           }
         }
+        if (n0 >= a.stats_cols) continue;       // e.g. the residual half of the [W2 ; W5] GEMM: no BatchNorm behind it
         if constexpr (REG_STATS) {
           if (valid) {
 #pragma unroll
@@ -604,6 +606,7 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   DFCSA_CHECK_ARG(p->act == 0 || (p->act == 1 && p->out_mode == DFCSA_OUT_DIRECT && !p->accumulate && p->stats == nullptr),
                   "conv_gemm_tc: the ReLU epilogue needs a direct, non-accumulating output without statistics");
   a.act_cols = p->act ? (p->act_cols > 0 ? p->act_cols : p->N) : 0;
+  a.stats_cols = p->stats != nullptr ? ((p->stats_cols > 0 && p->stats_cols % 32 == 0) ? p->stats_cols : p->N) : 0;
   a.wide_out = p->out_dtype != DFCSA_F32 && !p->accumulate && p->ld_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 31) == 0;
   a.wide_shadow = p->shadow != nullptr && p->ld_shadow % 16 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 31) == 0;
 

@@ -38,7 +38,7 @@ class ConvParams(C.Structure):
         ("out_mode", C.c_int32), ("accumulate", C.c_int32),
         ("bias", C.c_void_p), ("stats", C.c_void_p),
         ("shadow", C.c_void_p), ("ld_shadow", C.c_int64),
-        ("act", C.c_int32), ("act_cols", C.c_int32),
+        ("act", C.c_int32), ("act_cols", C.c_int32), ("stats_cols", C.c_int32), ("pad_", C.c_int32),
     ]
 
 

@@ -642,7 +642,7 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     ops.conv_gemm(B, H, W, segs3, pk["w1"], C, L0, stats=st[0:2 * C] if training else None,
                   backend=_backend(segs3, pk["w1"], C, L0))
     ops.conv_gemm(B, H, W, segs1, pk["w25"], 2 * C, AR, stats=st[2 * C:6 * C] if training else None,
-                  backend=_backend(segs1, pk["w25"], 2 * C, AR))
+                  backend=_backend(segs1, pk["w25"], 2 * C, AR), stats_cols=C)       # only A0 feeds a BatchNorm
     A0, R = AR[:, :C], AR[:, C:]
     bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
     bn2 = _bn_affine(bp.bn2, bp.b2, st[2 * C:3 * C] if training else None, st[4 * C:5 * C] if training else None, M, training, dev)

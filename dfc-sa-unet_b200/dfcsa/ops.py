@@ -26,7 +26,7 @@ def tc_eligible(segs, N, out):
 
 
 def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, bias=None, stats=None,
-              backend=BACKEND_TC, shadow=None, act=0, act_cols=0):
+              backend=BACKEND_TC, shadow=None, act=0, act_cols=0, stats_cols=0):
     """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm)."""
     p = L.ConvParams()
     p.B, p.H, p.W, p.n_seg = B, H, W, len(segs)
@@ -48,7 +48,7 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.stats = stats.data_ptr() if stats is not None else None
     p.shadow = shadow.data_ptr() if shadow is not None else None
     p.ld_shadow = _mat(shadow) if shadow is not None else 0
-    p.act, p.act_cols = act, act_cols
+    p.act, p.act_cols, p.stats_cols = act, act_cols, stats_cols
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
            flops=2.0 * B * H * W * N * ktot,

@@ -87,6 +87,10 @@ typedef struct {
    * 1x1 convs share one GEMM over [W2 ; W5] and only the first half has a ReLU).  DIRECT output mode only. */
   int32_t act;
   int32_t act_cols;
+  /* statistics only for the output columns n < stats_cols (0 = all N): the GEMM over [W2 ; W5] feeds a BatchNorm with
+   * its first half only, the residual half needs no sums (stats keeps its [2*N] layout) */
+  int32_t stats_cols;
+  int32_t pad_;
 } dfcsa_conv_params_t;
 
 int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);
