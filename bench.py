@@ -370,11 +370,11 @@ def run_dfcsa(args):
         # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this same configuration
         traffic, traffic_src = None, None
         try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic_r01.json")))["conv_tc"]
+            t = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_traffic_r02.json")))["conv_tc"]
             if B == 64 and IMG == 224:
                 traffic = t["traffic_bytes_per_launch"]
-                traffic_src = ("profiles/ncu_gemm_traffic_r01.csv: dram__bytes_read.sum + dram__bytes_write.sum over the 86 conv_tc launches "
-                               "of one step (33.2 GB; algorithmic operand + result bytes 34.4 GB)")
+                traffic_src = ("profiles/ncu_conv_tc_traffic_r02.csv: dram__bytes_read.sum + dram__bytes_write.sum over the 86 conv_tc launches "
+                               "of one step (33.9 GB; algorithmic operand + result bytes 34.4 GB)")
         except Exception:  # noqa: BLE001
             pass
         shares = {k: {"ms_per_step": v["ms"] / prof_steps, "share": v["ms"] / ms_prof, "launches_per_step": v["launches"] / prof_steps,

@@ -95,12 +95,27 @@ __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
 // 16 x 16-bit from 16 fp32: ONE 32-byte store per thread (st.global.v8.b32, sm_100+), i.e. a whole DRAM sector -
 // a row-per-thread epilogue that writes 16 bytes at a time makes L2 fill the other half of every sector from DRAM
 // (measured with ncu: +25 % DRAM reads on the level-1 GEMMs).  p must be 32-byte aligned.
+// two floats -> packed 16-bit pair.  fp16: convert first (an out-of-range value becomes +-inf), then clamp the PAIR to the
+// finite range with NaN-propagating half2 min / max - 3 instructions per pair instead of 5 (two float clamps per element);
+// the GEMM epilogue is bound by instruction issue on the short-K shapes (ncu: ~440 warp instructions per tile and warp).
+template <typename T> __device__ __forceinline__ uint32_t pack2_sat(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2_sat<__half>(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  const __half2 hi = __half2half2(__ushort_as_half(static_cast<unsigned short>(0x7BFF)));   //  65504
+  const __half2 lo = __half2half2(__ushort_as_half(static_cast<unsigned short>(0xFBFF)));   // -65504
+  h = __hmax2_nan(__hmin2_nan(h, hi), lo);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+template <> __device__ __forceinline__ uint32_t pack2_sat<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 template <typename T>
 __device__ __forceinline__ void store16_256(T* p, const float (&v)[16]) {
   uint32_t w[8];
-  T* e = reinterpret_cast<T*>(w);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) e[i] = Cvt<T>::from_f(v[i]);
+  for (int i = 0; i < 8; ++i) w[i] = pack2_sat<T>(v[2 * i], v[2 * i + 1]);
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                :: "l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
 }

@@ -61,6 +61,10 @@ struct TileCoord { int nt, w0, h0, tb; };
 
 __device__ __forceinline__ TileCoord tile_coord(const ConvTcArgs& a, int tile) {
   TileCoord t;
+  if (a.n_tiles_n == 1) {
+    t.nt = 0;
+    if (a.tiles_h == 1 && a.tiles_b == 1) { t.w0 = tile * a.w_t; t.h0 = 0; t.tb = 0; return t; }   // flattened 1x1 GEMM: no divisions
+  }
   t.nt = tile % a.n_tiles_n;
   int mt = tile / a.n_tiles_n;
   t.w0 = (mt % a.tiles_w) * a.w_t;
@@ -328,9 +332,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int as = 0; uint32_t aphase = 0;
     int last_nt = 0;
     bool have_stats = false;
+    const int dw = r % a.w_t, dh = r / a.w_t;       // this thread's pixel inside every tile
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(a, tile);
-      const int dw = r % a.w_t, dh = r / a.w_t;
       const int w = tc.w0 + dw, h = tc.h0 + dh;
       const bool valid = (r < a.w_t * a.h_t) && (w < a.W) && (h < a.H);
       long long row_off;

@@ -308,9 +308,14 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
 #pragma unroll
           for (int v = 0; v < VEC; ++v) {
             const float bnv = fmaf(t[v], sc[v], sh[v]);
-            acc[v] += fmax_nan(bnv, 0.f);
             if constexpr (MASKS) {
+              // sum relu(bn(a0)) = scale * sum m a0 + shift * sum m: with the two mask sums the activation sum is free
+              // (this pass is bound by instruction issue: ~60 instructions per 16-byte load left 0.5 of copy bandwidth)
+              // (a NaN in A0 does not reach the pooled value this way; it still reaches the loss through A = ... + relu(bn2 A0),
+              // whose max propagates NaN, so the optimizer's non-finite check sees it)
               if (bnv > 0.f) { am[v] += 1.f; ax[v] += t[v]; }
+            } else {
+              acc[v] += fmax_nan(bnv, 0.f);
             }
           }
         }
@@ -319,7 +324,7 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
     const float inv = 1.f / static_cast<float>(hi - lo);
     float* o = tmp + ((b * H + y) * P + j) * C + cv * VEC;
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) o[v] = acc[v] * inv;
+    for (int v = 0; v < VEC; ++v) o[v] = (MASKS ? fmaf(sc[v], ax[v], sh[v] * am[v]) : acc[v]) * inv;
     if constexpr (MASKS) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) { o[plane + v] = am[v] * inv; o[2 * plane + v] = ax[v] * inv; }

@@ -212,7 +212,12 @@ class _NetFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         if ctx.nctx is None:
             raise RuntimeError("dfcsa: backward through a network that ran in eval / no-grad mode")
-        grads = {p: torch.zeros_like(p) for p in ctx.params}
+        # one zeroed flat buffer carved into per-parameter views (128-byte aligned, the layout FusedSGD uses): one memset
+        # instead of a fill kernel per parameter tensor (235 of them)
+        from .ddp import flat_offsets
+        offs, total = flat_offsets(list(ctx.params))
+        flat = torch.zeros(total, dtype=torch.float32, device=dlogits.device)
+        grads = {p: flat[offs[p][0]:offs[p][1]].view(p.shape) for p in ctx.params}
         engine.net_backward(ctx.net, ctx.nctx, dlogits, grads)
         ctx.nctx = None
         return (None, None, None) + tuple(grads[p] for p in ctx.params)
