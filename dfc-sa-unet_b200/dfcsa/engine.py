@@ -647,7 +647,9 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
     bn2 = _bn_affine(bp.bn2, bp.b2, st[2 * C:3 * C] if training else None, st[4 * C:5 * C] if training else None, M, training, dev)
     # pooled self-attention (when the backward will run, the pooling pass also emits the window means of the ReLU mask)
-    masks = ctx is not None and _WINDOW_TERMS
+    # (only for coarse pooled maps, P <= 8: the two extra planes of the separable pooling pass cost [B, H, P, C] fp32 each,
+    # which at P = 16 / 32 is more than the gather pass they replace - measured: P32 step 48.2 -> 50.4 ms with them)
+    masks = ctx is not None and _WINDOW_TERMS and P <= 8
     tmp = _e((3 if masks else 1, B, H, P, C), F32, dev)
     pooled3 = _e((3 if masks else 1, B * P * P, C), F32, dev)
     pooled = pooled3[0]
