@@ -107,6 +107,7 @@ extern "C" int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* 
     DFCSA_CHECK_ARG(p->seg[s].ptr != nullptr, "dfcsa_conv_gemm: null segment %d", s);
   if (backend == DFCSA_BACKEND_TC) return conv_gemm_tc(p, static_cast<cudaStream_t>(stream));
   if (backend == DFCSA_BACKEND_SIMT) {
+    DFCSA_CHECK_ARG(p->bn == nullptr, "dfcsa_conv_gemm: the BatchNorm fold needs DFCSA_BACKEND_TC (call dfcsa_bn_finalize)");
     int rc = DFCSA_OK;   // the tiny-K / tiny-N layers (first conv, final conv) have bandwidth-shaped kernels of their own
     if (conv_gemm_small(p, static_cast<cudaStream_t>(stream), &rc)) return rc;
     return conv_gemm_simt(p, static_cast<cudaStream_t>(stream));

@@ -55,6 +55,8 @@ struct ConvTcArgs {
   int wide_out, wide_shadow;   // 32-byte stores legal (16-bit tensor, pitch % 16 == 0, base 32-byte aligned, no accumulate)
   int act_cols;     // ReLU on the output columns n < act_cols (0: no activation)
   int stats_cols;   // BatchNorm sums only for the output columns n < stats_cols
+  int has_bn;       // fold the BatchNorm finalize into this launch (last CTA by ticket)
+  dfcsa_bn_fold_t bn;
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -464,6 +466,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (a.has_bn) {
+    // BatchNorm finalize by the last CTA: every CTA's double atomics above are ordered before its ticket by the fence; the
+    // CTA that draws the last ticket therefore sees the complete sums (read with ld.global.cg, i.e. from L2 where the
+    // atomics were performed).  Nobody waits, so CTAs need not be co-resident.
+    __shared__ unsigned s_ticket;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.bn.ticket, 1u);
+    __syncthreads();
+    if (s_ticket == gridDim.x - 1) {
+      __threadfence();
+      const double n = static_cast<double>(a.bn.count);
+      for (int c = threadIdx.x; c < a.bn.channels; c += blockDim.x) {
+        const double mean = __ldcg(a.stats + c) / n;
+        double var = __ldcg(a.stats + a.N + c) / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double invstd = rsqrt(var + static_cast<double>(a.bn.eps));
+        const float g = a.bn.gamma[c];
+        a.bn.scale[c] = static_cast<float>(g * invstd);
+        a.bn.shift[c] = static_cast<float>(a.bn.beta[c] - mean * g * invstd);
+        a.bn.mean[c] = static_cast<float>(mean);
+        a.bn.invstd[c] = static_cast<float>(invstd);
+        if (a.bn.running_mean != nullptr) {
+          const double b = a.bn.conv_bias ? a.bn.conv_bias[c] : 0.0;
+          const double mom = a.bn.momentum;
+          a.bn.running_mean[c] = static_cast<float>((1.0 - mom) * a.bn.running_mean[c] + mom * (mean + b));
+          const double unb = a.bn.count > 1 ? var * n / (n - 1.0) : var;
+          a.bn.running_var[c] = static_cast<float>((1.0 - mom) * a.bn.running_var[c] + mom * unb);
+        }
+      }
+    }
+  }
 }
 
 std::once_flag g_attr_once;
@@ -611,6 +645,13 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
                   "conv_gemm_tc: the ReLU epilogue needs a direct, non-accumulating output without statistics");
   a.act_cols = p->act ? (p->act_cols > 0 ? p->act_cols : p->N) : 0;
   a.stats_cols = p->stats != nullptr ? ((p->stats_cols > 0 && p->stats_cols % 32 == 0) ? p->stats_cols : p->N) : 0;
+  if (p->bn != nullptr) {
+    const dfcsa_bn_fold_t& b = *p->bn;
+    DFCSA_CHECK_ARG(p->stats != nullptr && b.gamma && b.beta && b.scale && b.shift && b.mean && b.invstd && b.ticket && b.count > 0 &&
+                    b.channels > 0 && b.channels <= a.stats_cols, "conv_gemm_tc: bad BatchNorm fold (needs stats, outputs, a ticket)");
+    a.has_bn = 1;
+    a.bn = b;
+  }
   a.wide_out = p->out_dtype != DFCSA_F32 && !p->accumulate && p->ld_out % 16 == 0 && (reinterpret_cast<uintptr_t>(p->out) & 31) == 0;
   a.wide_shadow = p->shadow != nullptr && p->ld_shadow % 16 == 0 && (reinterpret_cast<uintptr_t>(p->shadow) & 31) == 0;
 

@@ -28,6 +28,14 @@ class Seg(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("ld", C.c_int64), ("channels", C.c_int32), ("tap_mode", C.c_int32)]
 
 
+class BnFold(C.Structure):        # dfcsa_bn_fold_t
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("conv_bias", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p),
+                ("momentum", C.c_float), ("eps", C.c_float), ("count", C.c_int64),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("invstd", C.c_void_p),
+                ("ticket", C.c_void_p), ("channels", C.c_int32), ("pad_", C.c_int32)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_seg", C.c_int32),
@@ -39,6 +47,7 @@ class ConvParams(C.Structure):
         ("bias", C.c_void_p), ("stats", C.c_void_p),
         ("shadow", C.c_void_p), ("ld_shadow", C.c_int64),
         ("act", C.c_int32), ("act_cols", C.c_int32), ("stats_cols", C.c_int32), ("pad_", C.c_int32),
+        ("bn", C.c_void_p),
     ]
 
 

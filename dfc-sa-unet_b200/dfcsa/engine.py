@@ -10,6 +10,8 @@ activation tiles to bf16 in shared memory, so no bf16 copy of any activation is 
 reference is zero-copy: producers write channel slices of one buffer ([f | L | A] inside a block, [up | skip] in the
 decoder).
 """
+import os as _os
+
 import torch
 
 from . import ops
@@ -446,6 +448,24 @@ def _bn_affine(bn, conv_bias, s_sum, s_sq, count, training, dev):
     return aff
 
 
+def _conv_bn(B, H, W, segs, w, N, out, st, bn, conv_bias, training, dev, **kw):
+    """conv_gemm followed by the BatchNorm affine of its first bn.num_features output columns (scale, shift, mean, invstd).
+    Training on the tcgen05 backend: the finalize is folded into the GEMM launch (its last CTA computes it, dfcsa_bn_fold_t);
+    SIMT backend: a dfcsa_bn_finalize launch; eval: running statistics."""
+    backend = _backend(segs, w, N, out)
+    Cn = bn.weight.numel()
+    M = B * H * W
+    if training and backend == BACKEND_TC and _BN_FOLD:
+        aff = _e((4, Cn), F32, dev)
+        fold = ops.bn_fold(bn.weight.detach(), bn.bias.detach(), conv_bias.detach() if conv_bias is not None else None,
+                           bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, M, aff, _z((1,), torch.int32, dev))
+        ops.conv_gemm(B, H, W, segs, w, N, out, stats=st, backend=backend, bn=fold, **kw)
+        return aff
+    ops.conv_gemm(B, H, W, segs, w, N, out, stats=st if training else None, backend=backend, **kw)
+    return _bn_affine(bn, conv_bias, st[0:Cn] if training else None, st[N:N + Cn] if training else None, M, training, dev)
+
+
+_BN_FOLD = _os.environ.get("DFCSA_BN_FOLD", "1") != "0"     # A/B switch: "0" = separate dfcsa_bn_finalize launches
 _ATTN_SAVE_BYTES = 4 << 30     # keep softmax(q k^T) for backward only below this size; above it backward recomputes it
 _ATTN_CHUNK_BYTES = 12 << 30   # images are processed in chunks so that one [chunk, N, N] fp32 buffer stays below this
 
@@ -468,7 +488,6 @@ def _attn_probs(qkv, nb, N, Cq, nq, out, lse=None, have_lse=False):
     ops.softmax_rows(S, out)
 
 
-import os as _os
 _WINDOW_TERMS = _os.environ.get("DFCSA_OLD_REDUCE2", "0") != "1"    # A/B switch for measurements (old: gather pass branch_bwd_reduce2)
 _ATTN_FUSED = True       # forward attention without the N^2 round trip when the probabilities are not kept for backward
 _ATTN_FUSED_BWD = True   # ... and the backward without any N^2 tensor (dfcsa_attn_bwd_fused)
@@ -639,13 +658,10 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     st = _z((10 * C,), F64, dev) if training else None
     L0, AR = _e((M, C), F16, dev), _e((M, 2 * C), F16, dev)
     segs3, segs1 = [(x, TAP_3x3)], [(x, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs3, pk["w1"], C, L0, stats=st[0:2 * C] if training else None,
-                  backend=_backend(segs3, pk["w1"], C, L0))
-    ops.conv_gemm(B, H, W, segs1, pk["w25"], 2 * C, AR, stats=st[2 * C:6 * C] if training else None,
-                  backend=_backend(segs1, pk["w25"], 2 * C, AR), stats_cols=C)       # only A0 feeds a BatchNorm
+    bn1 = _conv_bn(B, H, W, segs3, pk["w1"], C, L0, st[0:2 * C] if training else None, bp.bn1, bp.b1, training, dev)
+    bn2 = _conv_bn(B, H, W, segs1, pk["w25"], 2 * C, AR, st[2 * C:6 * C] if training else None, bp.bn2, bp.b2, training, dev,
+                   stats_cols=C)                                                       # only A0 feeds a BatchNorm
     A0, R = AR[:, :C], AR[:, C:]
-    bn1 = _bn_affine(bp.bn1, bp.b1, st[0:C] if training else None, st[C:2 * C] if training else None, M, training, dev)
-    bn2 = _bn_affine(bp.bn2, bp.b2, st[2 * C:3 * C] if training else None, st[4 * C:5 * C] if training else None, M, training, dev)
     # pooled self-attention (when the backward will run, the pooling pass also emits the window means of the ReLU mask)
     # (only for coarse pooled maps, P <= 8: the two extra planes of the separable pooling pass cost [B, H, P, C] fp32 each,
     # which at P = 16 / 32 is more than the gather pass they replace - measured: P32 step 48.2 -> 50.4 ms with them)
@@ -661,14 +677,12 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     G0 = _e((M, C), F16, dev)
     zLA = z[:, C:]
     segs = [(zLA, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["w3"], C, G0, stats=st[6 * C:8 * C] if training else None, backend=_backend(segs, pk["w3"], C, G0))
-    bn3 = _bn_affine(bp.bn3, bp.b3, st[6 * C:7 * C] if training else None, st[7 * C:8 * C] if training else None, M, training, dev)
+    bn3 = _conv_bn(B, H, W, segs, pk["w3"], C, G0, st[6 * C:8 * C] if training else None, bp.bn3, bp.b3, training, dev)
     ops.gate_mix_fwd(G0, bn3[0], bn3[1], z, None)
     # fusion
     F0 = _e((M, C), F16, dev)
     segs = [(z, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["w4"], C, F0, stats=st[8 * C:10 * C] if training else None, backend=_backend(segs, pk["w4"], C, F0))
-    bn4 = _bn_affine(bp.bn4, bp.b4, st[8 * C:9 * C] if training else None, st[9 * C:10 * C] if training else None, M, training, dev)
+    bn4 = _conv_bn(B, H, W, segs, pk["w4"], C, F0, st[8 * C:10 * C] if training else None, bp.bn4, bp.b4, training, dev)
     ops.block_out_fwd(F0, R, B, H, W, bn4[0], bn4[1], bp.res_scale.detach(), y, yp, None, None)
     if ctx is not None:
         ctx.B, ctx.H, ctx.W = B, H, W

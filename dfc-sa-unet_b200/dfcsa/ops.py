@@ -26,7 +26,7 @@ def tc_eligible(segs, N, out):
 
 
 def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, bias=None, stats=None,
-              backend=BACKEND_TC, shadow=None, act=0, act_cols=0, stats_cols=0):
+              backend=BACKEND_TC, shadow=None, act=0, act_cols=0, stats_cols=0, bn=None):
     """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm)."""
     p = L.ConvParams()
     p.B, p.H, p.W, p.n_seg = B, H, W, len(segs)
@@ -49,6 +49,8 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.shadow = shadow.data_ptr() if shadow is not None else None
     p.ld_shadow = _mat(shadow) if shadow is not None else 0
     p.act, p.act_cols, p.stats_cols = act, act_cols, stats_cols
+    if bn is not None:      # L.BnFold: BatchNorm finalize inside this launch (kept alive until the call returns)
+        p.bn = C.addressof(bn)
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
            flops=2.0 * B * H * W * N * ktot,
@@ -218,6 +220,18 @@ def bn_finalize(s_sum, s_sq, count, gamma, beta, conv_bias, rmean, rvar, momentu
     L.call("dfcsa_bn_finalize", L.ptr(s_sum), L.ptr(s_sq), _i64(count), Cn, L.ptr(gamma), L.ptr(beta),
                                       L.ptr(conv_bias), L.ptr(rmean), L.ptr(rvar), C.c_float(momentum), C.c_float(eps),
                                       L.ptr(scale), L.ptr(shift), L.ptr(mean), L.ptr(invstd), L.stream())
+
+
+def bn_fold(gamma, beta, conv_bias, rmean, rvar, momentum, eps, count, aff, ticket):
+    """dfcsa_bn_fold_t for conv_gemm(bn=...): aff is the [4, C] (scale, shift, mean, invstd) tensor, ticket a zeroed int32 [1]."""
+    b = L.BnFold()
+    b.gamma, b.beta = gamma.data_ptr(), beta.data_ptr()
+    b.conv_bias = conv_bias.data_ptr() if conv_bias is not None else None
+    b.running_mean, b.running_var = rmean.data_ptr(), rvar.data_ptr()
+    b.momentum, b.eps, b.count = momentum, eps, count
+    b.scale, b.shift, b.mean, b.invstd = (aff[i].data_ptr() for i in range(4))
+    b.ticket, b.channels = ticket.data_ptr(), gamma.numel()
+    return b
 
 
 def bn_eval_affine(gamma, beta, conv_bias, rmean, rvar, eps, scale, shift):

@@ -63,6 +63,20 @@ typedef struct {
   int32_t     tap_mode;/* DFCSA_TAP_* */
 } dfcsa_seg_t;
 
+/* BatchNorm finalize folded into the GEMM that produces the statistics (tcgen05 backend only): the LAST CTA to flush its
+ * partial sums (a ticket counter, no waiting) turns the complete sums into scale / shift / mean / invstd and updates the
+ * running statistics - exactly what dfcsa_bn_finalize does as a launch of its own, minus the launch and the dependency
+ * bubble behind every convolution (36 per training step).  Channels = the first `channels` output columns. */
+typedef struct {
+  const float* gamma; const float* beta; const float* conv_bias;   /* conv_bias optional */
+  float* running_mean; float* running_var;                         /* optional */
+  float momentum, eps;
+  int64_t count;                                                   /* samples per channel (= M) */
+  float* scale; float* shift; float* mean; float* invstd;          /* outputs, [channels] each */
+  uint32_t* ticket;                                                /* device counter, zero before the launch */
+  int32_t channels; int32_t pad_;
+} dfcsa_bn_fold_t;
+
 typedef struct {
   int32_t B, H, W;          /* output pixel grid; M = B*H*W */
   int32_t n_seg;
@@ -91,6 +105,8 @@ typedef struct {
    * its first half only, the residual half needs no sums (stats keeps its [2*N] layout) */
   int32_t stats_cols;
   int32_t pad_;
+  const dfcsa_bn_fold_t* bn;  /* optional (host pointer, read during the call): fold the BatchNorm finalize into this launch;
+                                 needs stats and DFCSA_BACKEND_TC */
 } dfcsa_conv_params_t;
 
 int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);
