@@ -168,7 +168,7 @@ def reference_gpu_numbers(batch, steps=5, warmup=3, device="cuda"):
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / steps
-            out[name] = {"img_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "loss": float(m["loss"]),
+            out[name] = {"img_per_s": batch / (ms * 1e-3), "ms_per_step": ms, "loss": float(m["loss"].detach()),
                          "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30}
             del step
         except Exception as e:  # noqa: BLE001

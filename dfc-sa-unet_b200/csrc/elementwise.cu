@@ -470,6 +470,80 @@ branch_act_fwd_kernel(const act_t* __restrict__ l0, long long ld_l0, const act_t
   }
 }
 
+// Row-walk variant of branch_act_fwd for coarse pooled maps (W / P >= 8, 16-byte channel vectors): a thread owns channel
+// vector cv of one row segment (b, y, k) and walks its pixels along x.  The bilinear taps of the pooled attention output,
+// already interpolated along y and scaled by gamma, live in two register vectors that are reloaded only when the x cell
+// changes (about P times per row) instead of four 32-byte gathers per pixel - those held the per-pixel kernel at 0.77 of
+// copy bandwidth in training and at 0.35 in the inference path, where only the A half is computed (ncu: L1 throughput 76 %).
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC)
+branch_act_rows_kernel(const act_t* __restrict__ l0, long long ld_l0, const act_t* __restrict__ a0, long long ld_a0, int B, int H,
+                       int W, int C, const float* s1, const float* t1, const float* s2, const float* t2, const float* __restrict__ o,
+                       int P, const float* gamma, act_t* __restrict__ z, long long ld_z, int nseg) {
+  constexpr int VEC = 8;
+  const int CV = C / VEC;
+  const long long total = static_cast<long long>(B) * H * nseg * CV;
+  const bool has_l = l0 != nullptr;
+  const float gm = *gamma;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int cv, k, y; long long b;
+    decode4(i, total < (1LL << 31), CV, nseg, H, cv, k, y, b);
+    const int c = cv * VEC;
+    const int xlo = static_cast<int>(static_cast<long long>(k) * W / nseg), xhi = static_cast<int>(static_cast<long long>(k + 1) * W / nseg);
+    float sc1[VEC], sh1[VEC], sc2[VEC], sh2[VEC];
+    if (has_l) { ldf<VEC>(s1 + c, sc1); ldf<VEC>(t1 + c, sh1); }
+    ldf<VEC>(s2 + c, sc2); ldf<VEC>(t2 + c, sh2);
+    int y0, y1; float ly;
+    bilerp_taps(y, P, H, y0, y1, ly);
+    const float* ob = o + b * P * P * C + c;
+    const long long mrow = (b * H + y) * W;
+    float c0v[VEC], c1v[VEC];
+    int cur_x0 = -1;
+    for (int x = xlo; x < xhi; x += 4) {
+      RawV<VEC, act_t> lraw[4], araw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long m = mrow + min(x + u, xhi - 1);
+        if (has_l) lraw[u] = ldraw<VEC>(l0 + m * ld_l0 + c);
+        araw[u] = ldraw<VEC>(a0 + m * ld_a0 + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int xx = x + u;
+        if (xx < xhi) {
+          int x0, x1; float lx;
+          bilerp_taps(xx, P, W, x0, x1, lx);
+          if (x0 != cur_x0) {          // new x cell: y-interpolate the two tap columns once
+            float a00[VEC], a01[VEC], a10[VEC], a11[VEC];
+            ldf<VEC>(ob + (y0 * P + x0) * C, a00); ldf<VEC>(ob + (y0 * P + x1) * C, a01);
+            ldf<VEC>(ob + (y1 * P + x0) * C, a10); ldf<VEC>(ob + (y1 * P + x1) * C, a11);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              c0v[v] = gm * fmaf(ly, a10[v] - a00[v], a00[v]);
+              c1v[v] = gm * fmaf(ly, a11[v] - a01[v], a01[v]);
+            }
+            cur_x0 = x0;
+          }
+          const long long m = mrow + xx;
+          float outv[VEC], xin[VEC];
+          if (has_l) {
+            cvtraw<VEC>(lraw[u], xin);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) outv[v] = fmax_nan(fmaf(xin[v], sc1[v], sh1[v]), 0.f);
+            stv<VEC>(z + m * ld_z + C + c, outv);
+          }
+          cvtraw<VEC>(araw[u], xin);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            outv[v] = fmaf(lx, c1v[v] - c0v[v], c0v[v]) + fmax_nan(fmaf(xin[v], sc2[v], sh2[v]), 0.f);
+          stv<VEC>(z + m * ld_z + 2 * C + c, outv);
+        }
+      }
+    }
+  }
+}
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const float* s3, const float* t3, act_t* z,
@@ -1041,6 +1115,77 @@ branch_bwd_apply_kernel(const grad_t* __restrict__ dz, long long ld_dz, const ac
   }
 }
 
+// Row-walk variant of the A-branch apply pass (see branch_act_rows_kernel): the pool^T(dpooled) vector of a pixel depends only
+// on the pooling windows that contain it, so a thread walking a row segment re-gathers it only when the window set changes
+// (about P times per row) instead of for every pixel.
+template <int OCC>
+__global__ void __launch_bounds__(256, OCC)
+branch_bwd_apply_rows_kernel(const grad_t* __restrict__ dz, long long ld_dz, const act_t* __restrict__ a0, long long ld_a0, int B, int H,
+                             int W, int C, const float* s2, const float* t2, const float* mean2, const float* invstd2,
+                             const double* red2, const float* __restrict__ dpooled, int P, grad_t* __restrict__ da0, long long ld_da0,
+                             int nseg) {
+  constexpr int VEC = 8;
+  extern __shared__ unsigned char s_dyn[];
+  const PoolTabs tabs = build_pool_tabs(s_dyn, H, W, P);
+  const int CV = C / VEC;
+  const long long total = static_cast<long long>(B) * H * nseg * CV;
+  const double invn = 1.0 / (static_cast<double>(B) * H * W);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    int cv, k, y; long long b;
+    decode4(i, total < (1LL << 31), CV, nseg, H, cv, k, y, b);
+    const int c = cv * VEC;
+    const int xlo = static_cast<int>(static_cast<long long>(k) * W / nseg), xhi = static_cast<int>(static_cast<long long>(k + 1) * W / nseg);
+    float sc[VEC], sh[VEC], p[VEC], q[VEC];
+    bn_bwd_coeffs<VEC>(s2, mean2, invstd2, red2, C, c, invn, sc, p, q);
+    ldf<VEC>(t2 + c, sh);
+    const int ty = tabs.yt[y];
+    const int ilo = ty & 0xffff, ihi = ty >> 16;
+    const float* dpb = dpooled + b * P * P * C + c;
+    const long long mrow = (b * H + y) * W;
+    const grad_t* dsrc = dz + 2 * C + c;
+    float gp[VEC];
+    int cur_key = -1;
+    for (int x = xlo; x < xhi; x += 4) {
+      RawV<VEC, grad_t> draw[4];
+      RawV<VEC, act_t> xraw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long m = mrow + min(x + u, xhi - 1);
+        draw[u] = ldraw<VEC>(dsrc + m * ld_dz); xraw[u] = ldraw<VEC>(a0 + m * ld_a0 + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int xx = x + u;
+        if (xx < xhi) {
+          const int key = tabs.xt[xx];
+          if (key != cur_key) {        // the set of pooling windows over this pixel changed: gather their gradients once
+            const int jlo = key & 0xffff, jhi = key >> 16;
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) gp[v] = 0.f;
+            for (int wi = ilo; wi <= ihi; ++wi)
+              for (int wj = jlo; wj <= jhi; ++wj) {
+                const float wgt = tabs.wy[wi] * tabs.wx[wj];
+                float t[VEC]; ldf<VEC>(dpb + (wi * P + wj) * C, t);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) gp[v] = fmaf(wgt, t[v], gp[v]);
+              }
+            cur_key = key;
+          }
+          float d[VEC], xv[VEC], ov[VEC];
+          cvtraw<VEC>(draw[u], d); cvtraw<VEC>(xraw[u], xv);
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float dd = fmaf(xv[v], sc[v], sh[v]) > 0.f ? d[v] + gp[v] : 0.f;
+            ov[v] = fmaf(sc[v], dd, fmaf(p[v], xv[v], q[v]));
+          }
+          stv<VEC>(da0 + (mrow + xx) * ld_da0 + c, ov);
+        }
+      }
+    }
+  }
+}
+
 // red += (sum d m, sum d m xhat) with m = [bn(x) > 0]: the BatchNorm + ReLU backward reduction over a plain (dy, x) pair -
 // what is left of branch_bwd_reduce2 once the pool^T(dpooled) part comes from the window means (no gather per pixel)
 template <int VEC, int OCC>
@@ -1341,8 +1486,20 @@ extern "C" int dfcsa_branch_act_fwd(const void* l0, int64_t ld_l0, const void* a
   DFCSA_CHECK_ARG(a0 && (l0 == nullptr || (scale1 && shift1)) && scale2 && shift2 && o && gamma && z, "dfcsa_branch_act_fwd: null pointer");
   const bool v8 = vec8_ok(C, {l0 ? ld_l0 : 0, ld_a0, ld_z, zb ? ld_zb : 0}, {l0, a0, z, zb, o, scale1, shift1, scale2, shift2});
   DFCSA_CHECK_ARG(static_cast<long long>(B) * H * W < (1LL << 31), "dfcsa_branch_act_fwd: too many pixels");
-  const RedGeom g = red_geom(C, v8 ? 8 : 1);
   static const int act_occ = [] { const char* e = getenv("DFCSA_ACT_OCC"); return e ? atoi(e) : 2; }();
+  static const bool rows_ok = [] { const char* e = getenv("DFCSA_ACT_ROWS"); return !e || atoi(e) != 0; }();
+  if (rows_ok && v8 && zb == nullptr && W / P >= 8) {
+    // row segments: at least P per row (one per pooled cell), more when the batch is small, never shorter than 8 pixels
+    const long long per_seg = static_cast<long long>(B) * H * (C / 8);
+    int nseg = static_cast<int>(std::min<long long>(W / 8, std::max<long long>(P, (150000 + per_seg - 1) / per_seg)));
+    const long long total = per_seg * nseg;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 2 * 8)));
+    branch_act_rows_kernel<2><<<blocks, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2, shift2, o, P, gamma,
+                                                      AM_(z), ld_z, nseg);
+    DFCSA_LAUNCH_CHECK("branch_act_rows_kernel");
+    return DFCSA_OK;
+  }
+  const RedGeom g = red_geom(C, v8 ? 8 : 1);
   dim3 grid(red_blocks(static_cast<long long>(B) * H * W, g.PL, g.chunks, ew_occ(act_occ)), g.chunks);
   OCC_DISPATCH(act_occ, VEC_DISPATCH(v8, (branch_act_fwd_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(A_(l0), ld_l0, A_(a0), ld_a0, B, H, W, C, scale1, shift1, scale2,
                                                                      shift2, o, P, gamma, AM_(z), ld_z, GM_(zb), ld_zb, g.CL, g.PL))));
@@ -1521,6 +1678,17 @@ extern "C" int dfcsa_branch_bwd_apply(const void* dz, int64_t ld_dz, const void*
   VEC_DISPATCH(v8, (bn_bwd_apply_kernel<VEC><<<gl, 256, 0, ST>>>(G_(dz) + C, ld_dz, A_(l0), ld_l0, M, C, scale1, shift1, mean1, invstd1,
                                                                  red1, 0, GM_(dl0), ld_dl0, g.CL, g.PL)));
   DFCSA_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  static const bool rows_ok = [] { const char* e = getenv("DFCSA_ACT_ROWS"); return !e || atoi(e) != 0; }();
+  if (rows_ok && v8 && W / P >= 8) {
+    const long long per_seg = static_cast<long long>(B) * H * (C / 8);
+    const int nseg = static_cast<int>(std::min<long long>(W / 8, std::max<long long>(P, (150000 + per_seg - 1) / per_seg)));
+    const long long total = per_seg * nseg;
+    const int blocks = static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, static_cast<long long>(num_sms()) * 2 * 8)));
+    branch_bwd_apply_rows_kernel<2><<<blocks, 256, pool_tabs_bytes(H, W, P), ST>>>(G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2,
+                                                                                   mean2, invstd2, red2, dpooled, P, GM_(da0), ld_da0, nseg);
+    DFCSA_LAUNCH_CHECK("branch_bwd_apply_rows_kernel");
+    return DFCSA_OK;
+  }
   dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(2)), g.chunks);
   OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_apply_kernel<VEC, OCC><<<grid, 256, pool_tabs_bytes(H, W, P), ST>>>(
                                         G_(dz), ld_dz, A_(a0), ld_a0, B, H, W, C, scale2, shift2, mean2, invstd2, red2, dpooled, P,
