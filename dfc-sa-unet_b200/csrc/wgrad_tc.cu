@@ -19,7 +19,9 @@
 // UMMA + that rewrite + the TMA writes.  Measured dead end (round 2, profiles/bench_r02_a_xreg.json): moving x through
 // registers instead (four warps: 16-byte global loads two pixel blocks ahead -> convert -> one swizzled store) was correct
 // but 4x SLOWER (32.3 ms against 7.7 ms per step over the 56 launches) - 128 threads cannot keep enough bytes in flight to
-// replace a TMA box; the variant was removed.
+// replace a TMA box; the variant was removed.  A timing-only run with the rewrite switched off (wrong numbers on purpose,
+// profiles/bench_r02_k_nocvt.json) puts its whole cost at 0.35 ms of the 7.8 ms per step: the rewrite overlaps the MMAs, so
+// fp16 gradients with a loss scale (x and dy in one format) would buy ~1 %, not the third its wavefront share suggests.
 #include "common.cuh"
 #include <algorithm>
 #include <mutex>
