@@ -255,6 +255,58 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------------------------------------
+// PTX: CTA pairs (cta_group::2).  Two CTAs of a cluster of 2 (the SMs of one TPC) run ONE tcgen05.mma of M = 256: each CTA
+// stages its own 128 rows of A and HALF of the B tile, so per CTA the shared-memory traffic of the B operand (TMA fill +
+// UMMA reads) is halved.  Only the leader (cluster rank 0) issues the MMAs; the peer's TMA loads signal the LEADER's
+// mbarrier (same shared-memory offset, bit 24 of the shared::cluster address cleared), tcgen05.commit multicasts its
+// arrival to both CTAs, and the peer's epilogue warps arrive on the leader's "accumulator drained" barrier remotely.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address -> the same offset in the even CTA of the pair
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {  // the same warp of BOTH CTAs, same dst offset
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+               :: "r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2cta(void* dst, const CUtensorMap* m, uint64_t* bar,
+                                                 int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask),
+         "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+// arrive on the LEADER's copy of a barrier (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
 // UMMA shared-memory matrix descriptor, 128-byte swizzle.
 //   K-major  operand: rows (M or N index) are 128 B apart, 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major operand: 64 contiguous M/N elements per 128 B row, rows = K index; 8-K-row groups SBO apart,

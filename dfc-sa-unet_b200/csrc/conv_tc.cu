@@ -55,6 +55,7 @@ struct ConvTcArgs {
   int wide_out, wide_shadow;   // 32-byte stores legal (16-bit tensor, pitch % 16 == 0, base 32-byte aligned, no accumulate)
   int act_cols;     // ReLU on the output columns n < act_cols (0: no activation)
   int stats_cols;   // BatchNorm sums only for the output columns n < stats_cols
+  int two_cta;      // CTA pairs: M = 256 per tcgen05.mma (cta_group::2), each CTA stages half of the B tile
   int has_bn;       // fold the BatchNorm finalize into this launch (last CTA by ticket)
   dfcsa_bn_fold_t bn;
 };
@@ -71,6 +72,19 @@ __device__ __forceinline__ TileCoord tile_coord(const ConvTcArgs& a, int tile) {
   int mt = tile / a.n_tiles_n;
   t.w0 = (mt % a.tiles_w) * a.w_t;
   int r = mt / a.tiles_w;
+  t.h0 = (r % a.tiles_h) * a.h_t;
+  t.tb = r / a.tiles_h;
+  return t;
+}
+
+// CTA pairs: pair tile pt = (pair of adjacent m tiles, n tile); CTA `rank` of the pair owns m tile 2 * mp + rank, which may lie
+// past the last one (odd tile count): its TMA boxes are then out of range (zero fill) and its rows are masked (tb >= tiles_b)
+__device__ __forceinline__ TileCoord tile_coord_pair(const ConvTcArgs& a, int pt, int rank) {
+  TileCoord t;
+  t.nt = pt % a.n_tiles_n;
+  const int mt = 2 * (pt / a.n_tiles_n) + rank;
+  t.w0 = (mt % a.tiles_w) * a.w_t;
+  const int r = mt / a.tiles_w;
   t.h0 = (r % a.tiles_h) * a.h_t;
   t.tb = r / a.tiles_h;
   return t;
@@ -125,7 +139,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 
 // REG_STATS: the narrow-output variant that keeps the BatchNorm partial sums in registers (64 more registers per
 // epilogue thread - kept out of the general instantiation, whose epilogue got measurably slower at 166 registers)
-template <bool REG_STATS>
+template <bool REG_STATS, bool TWO = false>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
@@ -142,7 +156,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const int lane = threadIdx.x & 31;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int stage_bytes = a.stage_bytes;
-  const int total_tiles = a.tiles_w * a.tiles_h * a.tiles_b * a.n_tiles_n;
+  // TWO: the two CTAs of a cluster work on one 256-pixel x block_n tile; `cta` / `n_cta` count pairs, `total_tiles` pair tiles
+  const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cta = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_cta = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_tiles = TWO ? ((a.tiles_w * a.tiles_h * a.tiles_b + 1) / 2) * a.n_tiles_n
+                              : a.tiles_w * a.tiles_h * a.tiles_b * a.n_tiles_n;
 
   // No zero fill of the stages: every B box is written in full by TMA (out-of-range rows arrive as zeros), and an
   // activation-tile row a partial box leaves unwritten is a pixel row of the MMA's M axis - it can only reach its own
@@ -163,12 +182,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < a.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+    // the leader's "accumulator drained" barrier collects the epilogue warps of BOTH CTAs of a pair
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], TWO ? 16 : 8); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (warp == 2) { if constexpr (TWO) tmem_alloc_2cta(&tmem_base_smem, kTmemCols); else tmem_alloc(&tmem_base_smem, kTmemCols); }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
@@ -176,8 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===================== TMA producer =====================
     int stage = 0; uint32_t phase = 0;
     const uint32_t kb_tx = static_cast<uint32_t>(a.a_box_bytes + a.block_n * 128);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(a, tile);
+    for (int tile = cta; tile < total_tiles; tile += n_cta) {
+      const TileCoord tc = TWO ? tile_coord_pair(a, tile, rank) : tile_coord(a, tile);
       if (a.dw3) {
         constexpr int kHaloBytes = 10 * 16 * 128;      // 20 KiB: (8 + 2) x 16 pixels x 64 channels
         const int bn_bytes = a.block_n * 128;
@@ -224,14 +244,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           else { c1 = tc.w0; c2 = tc.h0; c3 = tc.tb; c4 = 0; }
           for (int kb = 0; kb < a.seg_kb[s]; ++kb) {
             if (lane == 0) {
-              if (sub == 0) {
+              if constexpr (TWO) {
+                // each CTA loads its own 128 pixel rows of A and its HALF of the B tile; both signal the leader's barrier,
+                // which expects the bytes of both (the peer's bytes may land before the leader has armed the phase: the
+                // transaction count just goes negative for a moment)
+                const int bh = a.block_n / 2;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_arrive_expect_tx(&full_bar[stage], kb_tx * static_cast<uint32_t>(min(a.kbs, a.total_kb - kb_global)));
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(kABytes + bh * 128));
+                uint8_t* sa = smem + stage * stage_bytes;
+                uint8_t* sb = sa + kABytes;
+                tma_load_5d_2cta(sa, ma, &full_bar[stage], kb * kBlockK, c1, c2, c3, c4);
+                tma_load_2d_2cta(sb, &map_b, &full_bar[stage], kb_global * kBlockK, tc.nt * a.block_n + rank * bh);
+              } else {
+                if (sub == 0) {
+                  mbar_wait(&empty_bar[stage], phase ^ 1);
+                  mbar_arrive_expect_tx(&full_bar[stage], kb_tx * static_cast<uint32_t>(min(a.kbs, a.total_kb - kb_global)));
+                }
+                uint8_t* sa = smem + stage * stage_bytes + sub * kABytes;
+                uint8_t* sb = smem + stage * stage_bytes + a.kbs * kABytes + sub * (a.block_n * 128);
+                tma_load_5d(sa, ma, &full_bar[stage], kb * kBlockK, c1, c2, c3, c4);
+                tma_load_2d(sb, &map_b, &full_bar[stage], kb_global * kBlockK, tc.nt * a.block_n);
               }
-              uint8_t* sa = smem + stage * stage_bytes + sub * kABytes;
-              uint8_t* sb = smem + stage * stage_bytes + a.kbs * kABytes + sub * (a.block_n * 128);
-              tma_load_5d(sa, ma, &full_bar[stage], kb * kBlockK, c1, c2, c3, c4);
-              tma_load_2d(sb, &map_b, &full_bar[stage], kb_global * kBlockK, tc.nt * a.block_n);
             }
             __syncwarp();
             ++kb_global;
@@ -243,11 +276,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && (!TWO || rank == 0)) {
+    // ===================== MMA issuer (pairs: the leader CTA only) =====================
     int stage = 0; uint32_t phase = 0;
     int as = 0; uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < total_tiles; tile += n_cta) {
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * kAccStride;
@@ -301,16 +334,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + a.kbs * kABytes;
-          for (int sub = 0; sub < nsub; ++sub) {
+          if constexpr (TWO) {
+            // one M = 256 instruction per 16 channels: rows 0-127 from this CTA's A tile, 128-255 from the peer's (same
+            // shared-memory offsets), the N columns split between the two CTAs' B halves; accumulators in both CTAs' TMEM
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t da = umma_smem_desc(a_addr + sub * kABytes + k * 32, 16, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + sub * (a.block_n * 128) + k * 32, 16, 1024);
-              umma_f16(d_tmem, da, db, a.idesc, (kb | sub | k) != 0 ? 1u : 0u);
+              const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
+              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_f16_2cta(d_tmem, da, db, a.idesc, (kb | k) != 0 ? 1u : 0u);
             }
+            umma_commit_2cta(&empty_bar[stage]);                  // frees the stage in both CTAs
+            if (kb + nsub >= a.total_kb) umma_commit_2cta(&tmem_full_bar[as]);
+          } else {
+            for (int sub = 0; sub < nsub; ++sub) {
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t da = umma_smem_desc(a_addr + sub * kABytes + k * 32, 16, 1024);
+                const uint64_t db = umma_smem_desc(b_addr + sub * (a.block_n * 128) + k * 32, 16, 1024);
+                umma_f16(d_tmem, da, db, a.idesc, (kb | sub | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb + nsub >= a.total_kb) umma_commit(&tmem_full_bar[as]);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb + nsub >= a.total_kb) umma_commit(&tmem_full_bar[as]);
         }
         __syncwarp();
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
@@ -335,10 +381,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     int last_nt = 0;
     bool have_stats = false;
     const int dw = r % a.w_t, dh = r / a.w_t;       // this thread's pixel inside every tile
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(a, tile);
+    for (int tile = cta; tile < total_tiles; tile += n_cta) {
+      const TileCoord tc = TWO ? tile_coord_pair(a, tile, rank) : tile_coord(a, tile);
       const int w = tc.w0 + dw, h = tc.h0 + dh;
-      const bool valid = (r < a.w_t * a.h_t) && (w < a.W) && (h < a.H);
+      const bool valid = (r < a.w_t * a.h_t) && (w < a.W) && (h < a.H) && (!TWO || tc.tb < a.tiles_b);
       long long row_off;
       if (a.out_mode == DFCSA_OUT_CONVT2x2) {
         // flattened input pixel m -> (b, i, j); quadrant added per chunk below
@@ -421,7 +467,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+      if (lane == 0) { if constexpr (TWO) mbar_arrive_leader(&tmem_empty_bar[as]); else mbar_arrive(&tmem_empty_bar[as]); }
       as ^= 1; if (as == 0) aphase ^= 1;
       last_nt = tc.nt;
       if (a.stats != nullptr && flush_each) {
@@ -451,8 +497,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
   // final per-CTA flush of the BatchNorm partial sums (single n-tile case)
   tc_fence_before();
-  __syncthreads();
-  if (a.stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && blockIdx.x < total_tiles) {
+  // pairs: neither CTA may free its TMEM / leave while the other still runs MMAs on its shared memory or reads the accumulators
+  if constexpr (TWO) cluster_sync_all(); else __syncthreads();
+  if (a.stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && cta < total_tiles) {
     const int n_base = (blockIdx.x % a.n_tiles_n) * a.block_n;     // 0 for a single n tile
     for (int c = threadIdx.x; c < a.block_n; c += blockDim.x) {
       const int n = n_base + c;
@@ -464,7 +511,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   }
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (TWO) tmem_dealloc_2cta(tmem_base, kTmemCols); else tmem_dealloc(tmem_base, kTmemCols);
   }
   if (a.has_bn) {
     // BatchNorm finalize by the last CTA: every CTA's double atomics above are ordered before its ticket by the fence; the
@@ -588,16 +635,22 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   }
   a.block_n = block_n;
   a.n_tiles_n = (p->N + block_n - 1) / block_n;
+  // CTA pairs for the wide, deep GEMMs (levels 3-5): with a 128 x 256 tile per CTA the shared-memory port carries 96 B/clk
+  // of UMMA operand reads plus 94 B/clk of TMA fill - above its 128 B/clk, which is why ncu shows the tensor pipe at 56-60 %
+  // on these shapes.  A pair shares the B tile (each CTA stages and reads half of it): 64 + 62 B/clk.
+  static const bool pairs_ok = [] { const char* e = getenv("DFCSA_CONV_2CTA"); return !e || atoi(e) != 0; }();
+  a.two_cta = (pairs_ok && !a.dw3 && block_n == 256 && p->N % 256 == 0 && p->out_mode == DFCSA_OUT_DIRECT && m_tiles >= 2 &&
+               a.total_kb >= 4 && sms >= 2) ? 1 : 0;
   if (a.dw3) {
     a.kbs = 1;
     a.stage_bytes = 10 * 16 * 128 + 3 * block_n * 128;
   } else {
     a.kbs = (block_n <= 128 && a.total_kb >= 2) ? 2 : 1;
-    a.stage_bytes = a.kbs * (kABytes + block_n * 128);
+    a.stage_bytes = a.kbs * (kABytes + (a.two_cta ? block_n / 2 : block_n) * 128);
   }
   const int stage_bytes = a.stage_bytes;
   a.stages = std::min(kMaxStages, (kSmemBudget - 1024) / stage_bytes);
-  a.idesc = umma_idesc_f16(kBlockM, block_n, umma_fmt(p->src_dtype), umma_fmt(p->w_dtype), 0, 0);
+  a.idesc = umma_idesc_f16(a.two_cta ? 2 * kBlockM : kBlockM, block_n, umma_fmt(p->src_dtype), umma_fmt(p->w_dtype), 0, 0);
 
   // ---- tensor maps ----
   CUtensorMap maps[3];
@@ -630,7 +683,7 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   {
     uint64_t dims[2] = {static_cast<uint64_t>(ktot), static_cast<uint64_t>(p->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ktot) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(block_n)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(a.two_cta ? block_n / 2 : block_n)};
     int rc = encode_tensor_map(&map_b, p->w_dtype, 2, p->w, dims, strides, box, true);
     if (rc) return rc;
   }
@@ -661,12 +714,26 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
     attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   const long long total_tiles = m_tiles * a.n_tiles_n;
   int grid = static_cast<int>(std::min<long long>(total_tiles, sms));
   if (a.fixed_nt) grid = static_cast<int>(std::min<long long>(total_tiles, static_cast<long long>(sms / a.n_tiles_n) * a.n_tiles_n));
-  if (p->stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && a.block_n <= 64)
+  if (a.two_cta) {
+    // clusters of two CTAs (the SMs of one TPC); one pair per pair tile, at most sms / 2 pairs
+    const long long pair_tiles = (m_tiles + 1) / 2 * a.n_tiles_n;
+    const int pairs = static_cast<int>(std::min<long long>(pair_tiles, sms / 2));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(384); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, maps[0], maps[1], maps[2], map_b, a);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(conv_tc_kernel<pairs>)");
+  } else if (p->stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && a.block_n <= 64)
     conv_tc_kernel<true><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
   else
     conv_tc_kernel<false><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);

@@ -91,6 +91,13 @@ CASES = [
     (2, 40, 40, [64], "1", 256, {"stats": True}),        # short-K statistics GEMM: 64-wide n tiles, one n tile per CTA
     (4, 64, 64, [128], "1", 128, {"stats": True}),       # same, more tiles than SMs (several pixel tiles per CTA)
     (1, 24, 24, [128], "1", 192, {"bias": True}),        # bias staged in shared memory (no statistics)
+    # CTA pairs (cta_group::2, M = 256 per MMA): 256-wide n tiles with K >= 256
+    (3, 17, 19, [256], "1", 512, {"stats": True}),       # flat 1x1, 8 pixel tiles, two n tiles, statistics flushed per tile
+    (1, 30, 30, [128, 128], "11", 256, {}),              # two segments, one n tile
+    (5, 9, 9, [64], "3", 256, {"stats": True}),          # 3x3 box per tap, ODD number of pixel tiles: the peer of the last pair is masked
+    (2, 24, 24, [256], "3", 512, {"bias": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
+    (1, 64, 64, [512], "1", 1024, {"accumulate": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
+    (2, 33, 31, [64, 64, 128], "311", 256, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),  # dgrad-like, ragged
 ]
 _MODE = {"1": 0, "3": 1, "2": 2}
 
