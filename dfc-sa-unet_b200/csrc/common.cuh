@@ -302,9 +302,14 @@ __device__ __forceinline__ void tma_load_5d_2cta(void* dst, const CUtensorMap* m
          "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
-// arrive on the LEADER's copy of a barrier (from either CTA of the pair)
+// arrive on the LEADER's (cluster rank 0) copy of a barrier, from either CTA of the pair: mapa translates the local address
+// into the shared::cluster address of the same offset in rank 0.  (Masking bit 24 of the local address, which is what the
+// .cta_group::2 TMA form accepts for its mbarrier operand, does NOT redirect a plain mbarrier.arrive: measured - the peer's
+// arrivals stayed in the peer and the leader's third tile waited forever.)
 __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(smem_u32(bar) & kPeerBitMask) : "memory");
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(0u));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(remote) : "memory");
 }
 
 // UMMA shared-memory matrix descriptor, 128-byte swizzle.

@@ -98,6 +98,8 @@ CASES = [
     (2, 24, 24, [256], "3", 512, {"bias": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
     (1, 64, 64, [512], "1", 1024, {"accumulate": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
     (2, 33, 31, [64, 64, 128], "311", 256, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),  # dgrad-like, ragged
+    (8, 64, 64, [256], "1", 256, {"stats": True}),       # 256 pixel tiles = 128 pair tiles on 74 pairs: several tiles per pair,
+    (4, 112, 112, [256], "1", 256, {}),                  # ... and 392 tiles: both TMEM accumulators are reused (needs the peer's remote arrivals)
 ]
 _MODE = {"1": 0, "3": 1, "2": 2}
 
