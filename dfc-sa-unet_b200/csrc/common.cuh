@@ -177,7 +177,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      printf("dfcsa: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      printf("dfcsa: mbarrier wait timed out (block %d,%d of %d thread %d of %d, barrier 0x%x parity %u)\n", blockIdx.x, blockIdx.y,
+             gridDim.x, threadIdx.x, blockDim.x, smem_u32(bar), parity);
       __trap();
     }
   }

@@ -250,7 +250,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 // transaction count just goes negative for a moment)
                 const int bh = a.block_n / 2;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(kABytes + bh * 128));
+                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * static_cast<uint32_t>(a.a_box_bytes + bh * 128));
                 uint8_t* sa = smem + stage * stage_bytes;
                 uint8_t* sb = sa + kABytes;
                 tma_load_5d_2cta(sa, ma, &full_bar[stage], kb * kBlockK, c1, c2, c3, c4);
