@@ -639,8 +639,12 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   // of UMMA operand reads plus 94 B/clk of TMA fill - above its 128 B/clk, which is why ncu shows the tensor pipe at 56-60 %
   // on these shapes.  A pair shares the B tile (each CTA stages and reads half of it): 64 + 62 B/clk.
   static const bool pairs_ok = [] { const char* e = getenv("DFCSA_CONV_2CTA"); return !e || atoi(e) != 0; }();
+  // Measured (profiles/gemm_shapes_r02_l_*.json): K >= 1024 gains 5-8 % (e.g. 28^2 N=512 K=9216: 947 -> 1019 TFLOP/s, 56^2 N=256
+  // K=4608: 994 -> 1070), K <= 512 loses up to 25 % (the pair handshake per tile outweighs the saved operand traffic), hence
+  // the K threshold (DFCSA_CONV_2CTA_MINKB overrides it for experiments).
+  static const int pairs_min_kb = [] { const char* e = getenv("DFCSA_CONV_2CTA_MINKB"); return e ? atoi(e) : 16; }();
   a.two_cta = (pairs_ok && !a.dw3 && block_n == 256 && p->N % 256 == 0 && p->out_mode == DFCSA_OUT_DIRECT && m_tiles >= 2 &&
-               a.total_kb >= 4 && sms >= 2) ? 1 : 0;
+               a.total_kb >= pairs_min_kb && sms >= 2) ? 1 : 0;
   if (a.dw3) {
     a.kbs = 1;
     a.stage_bytes = 10 * 16 * 128 + 3 * block_n * 128;

@@ -98,14 +98,14 @@ CASES = [
     (2, 24, 24, [256], "3", 512, {"bias": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
     (1, 64, 64, [512], "1", 1024, {"accumulate": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
     (2, 33, 31, [64, 64, 128], "311", 256, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),  # dgrad-like, ragged
-    (8, 64, 64, [256], "1", 256, {"stats": True}),       # 256 pixel tiles = 128 pair tiles on 74 pairs: several tiles per pair,
-    (4, 112, 112, [256], "1", 256, {}),                  # ... and 392 tiles: both TMEM accumulators are reused (needs the peer's remote arrivals)
+    (8, 64, 64, [1024], "1", 256, {"stats": True}),      # 256 pixel tiles = 128 pair tiles on 74 pairs: several tiles per pair,
+    (4, 112, 112, [1024], "1", 256, {}),                 # ... and 392 tiles: both TMEM accumulators are reused (needs the peer's remote arrivals)
     (4, 112, 112, [128, 128, 128], "311", 256, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),  # level-2 dgrad at batch 4
-    (4, 112, 112, [256], "1", 256, {"stats": True}),     # level-2 [W2 ; W5] GEMM at batch 4
+    (4, 112, 112, [1024], "1", 256, {"stats": True}),    # wide 1x1 with statistics at batch 4
     (4, 56, 56, [256, 256, 256], "311", 512, {"out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),    # level-3 dgrad
     (4, 56, 56, [512], "3", 256, {"stats": True}),       # level-3 decoder 3x3
-    (1, 151, 128, [256], "1", 512, {"stats": True}),     # 151 pixel tiles (odd): the peer CTA of the last pair has no tile, two n tiles
-    (5, 75, 75, [64], "3", 256, {"stats": True}),   # 3x3 spatial tiles smaller than 128 pixels, odd tile count
+    (1, 151, 128, [1024], "1", 512, {"stats": True}),    # 151 pixel tiles (odd): the peer CTA of the last pair has no tile, two n tiles
+    (5, 75, 75, [128], "3", 256, {"stats": True}),       # 3x3 spatial tiles smaller than 128 pixels, odd tile count (K = 1152)
 ]
 _MODE = {"1": 0, "3": 1, "2": 2}
 
