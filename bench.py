@@ -8,8 +8,8 @@ Workload at N GPUs (weak scaling): configs[1] of BASELINE.json - DFC-SA-Res-Bloc
 qk 8), 224x224, batch 64 per GPU, one full training step = forward + sigmoid/bce_dice + backward + clip_grad_norm(1.0)
 + SGD(momentum .9, wd 1e-4), synthetic structured images, random-init weights.
 One JSON line on rank 0.  `value` = images/s with the batch already resident in HBM (CUDA events, max over ranks);
-`e2e` = the same step through the public Trainer API fed from pinned HOST buffers (H2D of images+masks and a D2H read
-of the loss inside the timed region); `roofline` = the tcgen05 implicit-GEMM conv kernel (algorithmic FLOPs / its
+`e2e` = the same step through the public Trainer API fed from pinned HOST buffers (every step's H2D of images+masks,
+through the look-ahead feeder of Trainer.train_epoch, and a D2H read of every step's loss inside the timed region); `roofline` = the tcgen05 implicit-GEMM conv kernel (algorithmic FLOPs / its
 CUDA-event time inside the timed steps) against the measured bf16 peak; `cpu_baseline` = the oracle port of the
 reference step timed on this box's host cores on a bounded sample.
 """
@@ -342,12 +342,24 @@ def run_dfcsa(args):
     t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     loss_host = 0.0
-    # every step's images + masks cross PCIe inside the timed region (pinned host -> the step's input buffers) and the
-    # loss comes back to the host
-    for i in range(args.steps):
-        r = step(*host[i % 2]) if not args.no_graph else tr.train_step(host[i % 2][0].to(dev, non_blocking=True),
-                                                                      host[i % 2][1].to(dev, non_blocking=True), MICRO)
-        loss_host = r.stats[:1].cpu().item()          # device -> host read of the step's loss
+    # every step's images + masks cross PCIe inside the timed region (pinned host -> device staging buffers) and every
+    # step's loss comes back to the host.  The copies go through trainer.device_feeder, the look-ahead feeder that
+    # Trainer.train_epoch itself uses (the copy of batch i+1 runs on a copy stream while batch i trains; the generator
+    # starts inside the timed region, so all K copies are counted); the loss of step i is read back asynchronously into
+    # pinned memory and consumed after step i+1 has been enqueued, so the device never waits for the host.
+    from dfcsa.trainer import device_feeder
+    loss_pin = torch.empty(args.steps, dtype=torch.float32).pin_memory()
+    evs = []
+    for i, (im, mk) in enumerate(device_feeder((host[j % 2] for j in range(args.steps)), dev)):
+        r = step(im, mk) if not args.no_graph else tr.train_step(im, mk, MICRO)
+        loss_pin[i:i + 1].copy_(r.stats[:1].detach(), non_blocking=True)     # device -> host read of the step's loss
+        ev = torch.cuda.Event(); ev.record(); evs.append(ev)
+        if i > 0:
+            evs[i - 1].synchronize()
+            loss_host = float(loss_pin[i - 1])
+    if evs:
+        evs[-1].synchronize()
+        loss_host = float(loss_pin[args.steps - 1])
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
@@ -374,7 +386,7 @@ def run_dfcsa(args):
             if B == 64 and IMG == 224:
                 traffic = t["traffic_bytes_per_launch"]
                 traffic_src = ("profiles/ncu_conv_tc_traffic_r02.csv: dram__bytes_read.sum + dram__bytes_write.sum over the 86 conv_tc launches "
-                               "of one step (33.9 GB; algorithmic operand + result bytes 34.4 GB)")
+                               "of one step (33.8 GB; algorithmic operand + result bytes 34.4 GB)")
         except Exception:  # noqa: BLE001
             pass
         shares = {k: {"ms_per_step": v["ms"] / prof_steps, "share": v["ms"] / ms_prof, "launches_per_step": v["launches"] / prof_steps,
@@ -403,7 +415,8 @@ def run_dfcsa(args):
             "dtype": "fp16 fwd / bf16 bwd operands, fp32 accumulate", "data": "synthetic",
             "config": workload_config(B, world, not args.no_graph),
             "model_tflops": value * TRAIN_GFLOP_PER_IMG / 1e3 / world,
-            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4, "last_loss": loss_host},
+            "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4, "last_loss": loss_host,
+                    "feed": "trainer.device_feeder: H2D of batch i+1 on a copy stream while batch i trains; loss read one step late"},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv fwd + dgrad + ConvT)", "bound": "tensor",
