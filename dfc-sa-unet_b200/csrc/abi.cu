@@ -108,6 +108,8 @@ extern "C" int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* 
   if (backend == DFCSA_BACKEND_TC) return conv_gemm_tc(p, static_cast<cudaStream_t>(stream));
   if (backend == DFCSA_BACKEND_SIMT) {
     DFCSA_CHECK_ARG(p->bn == nullptr, "dfcsa_conv_gemm: the BatchNorm fold needs DFCSA_BACKEND_TC (call dfcsa_bn_finalize)");
+    DFCSA_CHECK_ARG(p->epi == nullptr || p->epi->mode == DFCSA_EPI_NONE,
+                    "dfcsa_conv_gemm: the fused gate-mix / residual epilogue needs DFCSA_BACKEND_TC (call dfcsa_gate_mix_fwd / dfcsa_sum_out_fwd)");
     int rc = DFCSA_OK;   // the tiny-K / tiny-N layers (first conv, final conv) have bandwidth-shaped kernels of their own
     if (conv_gemm_small(p, static_cast<cudaStream_t>(stream), &rc)) return rc;
     return conv_gemm_simt(p, static_cast<cudaStream_t>(stream));

@@ -58,6 +58,10 @@ struct ConvTcArgs {
   int two_cta;      // CTA pairs: M = 256 per tcgen05.mma (cta_group::2), each CTA stages half of the B tile
   int has_bn;       // fold the BatchNorm finalize into this launch (last CTA by ticket)
   dfcsa_bn_fold_t bn;
+  int epi_mode;     // DFCSA_EPI_*: fused inference epilogue (conv_tc_kernel<false, false, true> only)
+  const __half* epi_p; const __half* epi_q;
+  long long ld_epi;
+  const float* epi_scale;
 };
 
 struct TileCoord { int nt, w0, h0, tb; };
@@ -139,7 +143,7 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 
 // REG_STATS: the narrow-output variant that keeps the BatchNorm partial sums in registers (64 more registers per
 // epilogue thread - kept out of the general instantiation, whose epilogue got measurably slower at 166 registers)
-template <bool REG_STATS, bool TWO = false>
+template <bool REG_STATS, bool TWO = false, bool EPI = false>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
@@ -433,6 +437,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 32; ++i) if (n0 + i < a.act_cols) v[i] = fmax_nan(v[i], 0.f);
         }
+        if constexpr (EPI) {
+          // fused inference epilogues (own instantiation: the training epilogue keeps its register budget).  The second
+          // operands are the rows this tile's TMA loads brought through L2 a moment ago (gate mix) or a tensor the
+          // separate pass would have read anyway (residual).
+          if (valid && ncols == 32) {
+            const uint4* pp = reinterpret_cast<const uint4*>(a.epi_p + pix * a.ld_epi + cn);
+            uint4 pr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pr[i] = __ldg(pp + i);
+            const __half2* ph = reinterpret_cast<const __half2*>(pr);
+            if (a.epi_mode == DFCSA_EPI_GATE_MIX) {
+              const uint4* qp = reinterpret_cast<const uint4*>(a.epi_q + pix * a.ld_epi + cn);
+              uint4 qr[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) qr[i] = __ldg(qp + i);
+              const __half2* qh = reinterpret_cast<const __half2*>(qr);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 l = __half22float2(ph[i]), q = __half22float2(qh[i]);
+                const float g0 = __fdividef(1.f, 1.f + __expf(-v[2 * i])), g1 = __fdividef(1.f, 1.f + __expf(-v[2 * i + 1]));
+                v[2 * i] = fmaf(g0, l.x - q.x, q.x);
+                v[2 * i + 1] = fmaf(g1, l.y - q.y, q.y);
+              }
+            } else {
+              const float sc = __ldg(a.epi_scale);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float2 l = __half22float2(ph[i]);
+                v[2 * i] = fmaf(sc, l.x, v[2 * i]);
+                v[2 * i + 1] = fmaf(sc, l.y, v[2 * i + 1]);
+              }
+            }
+          }
+        }
         if (valid) {
           if (a.wide_out && ncols == 32) {
             if (a.out_dtype == DFCSA_F16) store_chunk_wide<__half>(reinterpret_cast<__half*>(a.out) + pix * a.ld_out + cn, v);
@@ -644,7 +682,7 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
   // the K threshold (DFCSA_CONV_2CTA_MINKB overrides it for experiments).
   static const int pairs_min_kb = [] { const char* e = getenv("DFCSA_CONV_2CTA_MINKB"); return e ? atoi(e) : 16; }();
   a.two_cta = (pairs_ok && !a.dw3 && block_n == 256 && p->N % 256 == 0 && p->out_mode == DFCSA_OUT_DIRECT && m_tiles >= 2 &&
-               a.total_kb >= pairs_min_kb && sms >= 2) ? 1 : 0;
+               a.total_kb >= pairs_min_kb && sms >= 2 && !(p->epi != nullptr && p->epi->mode != DFCSA_EPI_NONE)) ? 1 : 0;
   if (a.dw3) {
     a.kbs = 1;
     a.stage_bytes = 10 * 16 * 128 + 3 * block_n * 128;
@@ -702,6 +740,18 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
                   "conv_gemm_tc: the ReLU epilogue needs a direct, non-accumulating output without statistics");
   a.act_cols = p->act ? (p->act_cols > 0 ? p->act_cols : p->N) : 0;
   a.stats_cols = p->stats != nullptr ? ((p->stats_cols > 0 && p->stats_cols % 32 == 0) ? p->stats_cols : p->N) : 0;
+  if (p->epi != nullptr && p->epi->mode != DFCSA_EPI_NONE) {
+    const dfcsa_conv_epi_t& e = *p->epi;
+    DFCSA_CHECK_ARG((e.mode == DFCSA_EPI_GATE_MIX && e.p && e.q) || (e.mode == DFCSA_EPI_RESIDUAL && e.p && e.scale),
+                    "conv_gemm_tc: bad fused epilogue (gate mix needs p and q, residual needs p and scale)");
+    DFCSA_CHECK_ARG(p->out_mode == DFCSA_OUT_DIRECT && !p->accumulate && p->stats == nullptr && p->shadow == nullptr &&
+                    p->out_dtype == DFCSA_F16 && p->N % 32 == 0 && e.ld % 8 == 0 &&
+                    (reinterpret_cast<uintptr_t>(e.p) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.q) & 15) == 0,
+                    "conv_gemm_tc: the fused epilogue needs a direct fp16 output with N % 32 == 0, no statistics, 16-byte aligned operand rows");
+    a.epi_mode = e.mode;
+    a.epi_p = reinterpret_cast<const __half*>(e.p); a.epi_q = reinterpret_cast<const __half*>(e.q);
+    a.ld_epi = e.ld; a.epi_scale = e.scale;
+  }
   if (p->bn != nullptr) {
     const dfcsa_bn_fold_t& b = *p->bn;
     DFCSA_CHECK_ARG(p->stats != nullptr && b.gamma && b.beta && b.scale && b.shift && b.mean && b.invstd && b.ticket && b.count > 0 &&
@@ -720,6 +770,8 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
       attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     if (attr_err == cudaSuccess)
       attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
   });
   if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(conv_tc_kernel)");
   const long long total_tiles = m_tiles * a.n_tiles_n;
@@ -737,7 +789,9 @@ int conv_gemm_tc(const dfcsa_conv_params_t* p, cudaStream_t stream) {
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<false, true>, maps[0], maps[1], maps[2], map_b, a);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx(conv_tc_kernel<pairs>)");
-  } else if (p->stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && a.block_n <= 64)
+  } else if (a.epi_mode != DFCSA_EPI_NONE)
+    conv_tc_kernel<false, false, true><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
+  else if (p->stats != nullptr && (a.n_tiles_n == 1 || a.fixed_nt) && a.block_n <= 64)
     conv_tc_kernel<true><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);
   else
     conv_tc_kernel<false><<<grid, 384, smem_bytes, stream>>>(maps[0], maps[1], maps[2], map_b, a);

@@ -36,6 +36,14 @@ class BnFold(C.Structure):        # dfcsa_bn_fold_t
                 ("ticket", C.c_void_p), ("channels", C.c_int32), ("pad_", C.c_int32)]
 
 
+EPI_NONE, EPI_GATE_MIX, EPI_RESIDUAL = 0, 1, 2
+
+
+class ConvEpi(C.Structure):       # dfcsa_conv_epi_t
+    _fields_ = [("mode", C.c_int32), ("pad_", C.c_int32), ("p", C.c_void_p), ("q", C.c_void_p), ("ld", C.c_int64),
+                ("scale", C.c_void_p)]
+
+
 class ConvParams(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("n_seg", C.c_int32),
@@ -47,7 +55,7 @@ class ConvParams(C.Structure):
         ("bias", C.c_void_p), ("stats", C.c_void_p),
         ("shadow", C.c_void_p), ("ld_shadow", C.c_int64),
         ("act", C.c_int32), ("act_cols", C.c_int32), ("stats_cols", C.c_int32), ("pad_", C.c_int32),
-        ("bn", C.c_void_p),
+        ("bn", C.c_void_p), ("epi", C.c_void_p),
     ]
 
 

@@ -692,6 +692,9 @@ def block_forward(bp, pk, x, B, H, W, y, yp=None, training=True, save=True):
     return ctx
 
 
+_EVAL_EPI = _os.environ.get("DFCSA_EVAL_EPI", "1") != "0"     # A/B switch: "0" = separate gate-mix / residual passes
+
+
 def _dfc_block_forward_folded(bp, pk, x, B, H, W, y, yp):
     """Inference-mode DynamicFusionConvAttnBlock with the BatchNorms folded into the GEMMs (pack_block_weights_folded):
     4 GEMMs with bias (+ ReLU) epilogues and 4 streaming passes (pool 1 E, A = gamma * up(o) + a 2 E, gate mix 4 E, residual
@@ -712,14 +715,25 @@ def _dfc_block_forward_folded(bp, pk, x, B, H, W, y, yp):
     ops.bnrelu_pool_fwd(a, B, H, W, ones, zeros, P, tmp, pooled)        # a >= 0 already: the fused affine + ReLU is the identity
     o = attention_forward(bp, pk, pooled, B, P * P, None)
     ops.branch_act_fwd(None, a, B, H, W, None, None, ones, zeros, o, P, bp.gamma.detach(), z, None)   # A = gamma * up(o) + a
-    G = _e((M, C), F16, dev)
     segs = [(z[:, C:], TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["w3"], C, G, bias=pk["t3"], backend=_backend(segs, pk["w3"], C, G))
-    ops.gate_mix_fwd(G, ones, zeros, z, None)                            # f = sigmoid(G) L + (1 - sigmoid(G)) A
-    F = _e((M, C), F16, dev)
+    f = z[:, :C]
+    if _EVAL_EPI and C % 32 == 0 and _backend(segs, pk["w3"], C, f) == BACKEND_TC:
+        # f = sigmoid(G) L + (1 - sigmoid(G)) A from the gate conv's epilogue (L, A: the rows its own TMA loads just pulled
+        # through L2): the gate logits never reach HBM and the 4 E mixing pass is gone
+        ops.conv_gemm(B, H, W, segs, pk["w3"], C, f, bias=pk["t3"], epi=("gate_mix", z[:, C:2 * C], z[:, 2 * C:]))
+    else:
+        G = _e((M, C), F16, dev)
+        ops.conv_gemm(B, H, W, segs, pk["w3"], C, G, bias=pk["t3"], backend=_backend(segs, pk["w3"], C, G))
+        ops.gate_mix_fwd(G, ones, zeros, z, None)                        # f = sigmoid(G) L + (1 - sigmoid(G)) A
     segs = [(z, TAP_1x1)]
-    ops.conv_gemm(B, H, W, segs, pk["w4"], C, F, bias=pk["t4"], act=1, backend=_backend(segs, pk["w4"], C, F))
-    ops.sum_out_fwd(F, None, R, B, H, W, bp.res_scale.detach(), y, yp)   # y = F + res_scale * R (+ 2x2 max pool)
+    if _EVAL_EPI and yp is None and C % 32 == 0 and y.dtype == F16 and _backend(segs, pk["w4"], C, y) == BACKEND_TC:
+        # blocks without a max pool behind them (decoder, bottleneck): y = relu(F) + res_scale * R from the fusion conv's
+        # epilogue; F never reaches HBM
+        ops.conv_gemm(B, H, W, segs, pk["w4"], C, y, bias=pk["t4"], act=1, epi=("residual", R, bp.res_scale.detach().reshape(1)))
+    else:
+        F = _e((M, C), F16, dev)
+        ops.conv_gemm(B, H, W, segs, pk["w4"], C, F, bias=pk["t4"], act=1, backend=_backend(segs, pk["w4"], C, F))
+        ops.sum_out_fwd(F, None, R, B, H, W, bp.res_scale.detach(), y, yp)   # y = F + res_scale * R (+ 2x2 max pool)
     return None
 
 

@@ -26,8 +26,10 @@ def tc_eligible(segs, N, out):
 
 
 def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, bias=None, stats=None,
-              backend=BACKEND_TC, shadow=None, act=0, act_cols=0, stats_cols=0, bn=None):
-    """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm)."""
+              backend=BACKEND_TC, shadow=None, act=0, act_cols=0, stats_cols=0, bn=None, epi=None):
+    """out[m, n] (+)= sum_seg sum_tap sum_c seg[pix(m,tap), c] * w[n, k]   (dfcsa_conv_gemm).
+    epi = ("gate_mix", p, q): out = s p + (1 - s) q with s = sigmoid(result);  ("residual", p, scale): out = result + scale p
+    (fused inference epilogues, tensor-core backend only)."""
     p = L.ConvParams()
     p.B, p.H, p.W, p.n_seg = B, H, W, len(segs)
     for i, (m, mode) in enumerate(segs):
@@ -51,6 +53,15 @@ def conv_gemm(B, H, W, segs, w, N, out, out_mode=OUT_DIRECT, accumulate=False, b
     p.act, p.act_cols, p.stats_cols = act, act_cols, stats_cols
     if bn is not None:      # L.BnFold: BatchNorm finalize inside this launch (kept alive until the call returns)
         p.bn = C.addressof(bn)
+    if epi is not None:
+        e = L.ConvEpi()
+        if epi[0] == "gate_mix":
+            e.mode, e.p, e.q, e.ld = L.EPI_GATE_MIX, epi[1].data_ptr(), epi[2].data_ptr(), _mat(epi[1])
+            assert _mat(epi[2]) == e.ld and epi[1].dtype == epi[2].dtype == torch.float16
+        else:
+            e.mode, e.p, e.ld, e.scale = L.EPI_RESIDUAL, epi[1].data_ptr(), _mat(epi[1]), epi[2].data_ptr()
+            assert epi[1].dtype == torch.float16 and epi[2].dtype == torch.float32
+        p.epi = C.addressof(e)
     ktot = sum(m.shape[1] * (1 if mode == TAP_1x1 else 9 if mode == TAP_3x3 else 4) for m, mode in segs)
     L.call("dfcsa_conv_gemm", C.byref(p), backend, L.stream(), tag="conv_tc" if backend == BACKEND_TC else "conv_simt",
            flops=2.0 * B * H * W * N * ktot,

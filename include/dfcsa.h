@@ -77,6 +77,21 @@ typedef struct {
   int32_t channels; int32_t pad_;
 } dfcsa_bn_fold_t;
 
+/* Optional fused inference epilogue of dfcsa_conv_gemm (DFCSA_BACKEND_TC, fp16 DIRECT output, no statistics, no accumulate),
+ * applied to the result after the bias and the activation:
+ *   DFCSA_EPI_GATE_MIX : out = s * p + (1 - s) * q,  s = sigmoid(result).  With p = local_feat, q = attn_feat the gate conv
+ *                        writes `fused` itself (reference models/unet_dfc_sa_res.py:104-106); the gate logits never reach HBM
+ *   DFCSA_EPI_RESIDUAL : out = result + scale[0] * p.  With p = residual_conv(x) the fusion conv writes the block output
+ *                        (reference :110-114); the fusion conv's own output never reaches HBM
+ * p, q: fp16 [M, N] views with row pitch ld (elements), 16-byte aligned rows; scale: device pointer to one float. */
+enum { DFCSA_EPI_NONE = 0, DFCSA_EPI_GATE_MIX = 1, DFCSA_EPI_RESIDUAL = 2 };
+typedef struct {
+  int32_t mode; int32_t pad_;
+  const void* p; const void* q;
+  int64_t ld;
+  const float* scale;
+} dfcsa_conv_epi_t;
+
 typedef struct {
   int32_t B, H, W;          /* output pixel grid; M = B*H*W */
   int32_t n_seg;
@@ -107,6 +122,7 @@ typedef struct {
   int32_t pad_;
   const dfcsa_bn_fold_t* bn;  /* optional (host pointer, read during the call): fold the BatchNorm finalize into this launch;
                                  needs stats and DFCSA_BACKEND_TC */
+  const dfcsa_conv_epi_t* epi; /* optional (host pointer, read during the call): fused inference epilogue, see above */
 } dfcsa_conv_params_t;
 
 int dfcsa_conv_gemm(const dfcsa_conv_params_t* p, int backend, void* stream);

@@ -39,7 +39,8 @@ def test_bad_arguments_return_error_codes_not_crashes():
 def test_struct_layouts_match_header():
     from dfcsa import _lib
     assert ctypes.sizeof(_lib.Seg) == 24
-    assert ctypes.sizeof(_lib.ConvParams) == 16 + 3 * 24 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 16 + 16 + 8
+    assert ctypes.sizeof(_lib.ConvParams) == 16 + 3 * 24 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 16 + 16 + 8 + 8
+    assert ctypes.sizeof(_lib.ConvEpi) == 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(_lib.BnFold) == 5 * 8 + 8 + 8 + 5 * 8 + 8
     assert ctypes.sizeof(_lib.PackJob) == 3 * 8 + 7 * 8 + 4 * 4 + 8
     assert ctypes.sizeof(_lib.WgradParams) == 16 + 32 + 32 + 16 + 8 + 24 + 16 + 8

@@ -601,6 +601,56 @@ def test_conv_gemm_bias_relu_epilogue(cuda, case, backend):
         assert bool((out[:, nrelu:] < 0).any())           # the columns past act_cols stay linear
 
 
+@pytest.mark.parametrize("B,H,W,C", [(1, 16, 16, 64), (2, 24, 40, 64), (1, 56, 56, 128), (2, 14, 14, 512), (1, 20, 28, 256)])
+def test_conv_gemm_gate_mix_epilogue(cuda, B, H, W, C):
+    """Inference path: the gate conv over [L | A] writes fused = s L + (1 - s) A, s = sigmoid(conv + bias), from its epilogue
+    (reference models/unet_dfc_sa_res.py:104-106), into the first C columns of the same [f | L | A] buffer it reads."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(41)
+    M = B * H * W
+    z = torch.randn(M, 3 * C, generator=g).to(cuda).half()
+    z[:, :C] = 0
+    wt = (torch.randn(C, 2 * C, 1, 1, generator=g) / (2 * C) ** 0.5 * 3).to(cuda).half()
+    bias = torch.randn(C, generator=g).to(cuda)
+    L, A = z[:, C:2 * C].float(), z[:, 2 * C:].float()
+    G = z[:, C:].float() @ wt.float().reshape(C, 2 * C).t() + bias
+    s = torch.sigmoid(G)
+    ref = s * L + (1 - s) * A
+    ops.conv_gemm(B, H, W, [(z[:, C:], 0)], _pack_fwd(wt), C, z[:, :C], bias=bias, epi=("gate_mix", z[:, C:2 * C], z[:, 2 * C:]))
+    torch.cuda.synchronize()
+    assert _rel_err(z[:, :C], ref) < 4e-3
+    assert torch.equal(z[:, C:2 * C].float(), L) and torch.equal(z[:, 2 * C:].float(), A)      # operands untouched
+
+
+@pytest.mark.parametrize("B,H,W,C", [(1, 16, 16, 64), (2, 24, 40, 64), (1, 56, 56, 128), (2, 14, 14, 512), (1, 20, 28, 1024)])
+def test_conv_gemm_residual_epilogue(cuda, B, H, W, C):
+    """Inference path: the fusion conv over [f | L | A] writes relu(conv + bias) + res_scale * R from its epilogue
+    (reference models/unet_dfc_sa_res.py:110-114), R being the second half of the [a | R] buffer (pitch 2C) and the
+    output a channel slice of a wider (concatenation) buffer."""
+    from dfcsa import ops
+    g = torch.Generator().manual_seed(43)
+    M = B * H * W
+    z = torch.randn(M, 3 * C, generator=g).to(cuda).half()
+    AR = torch.randn(M, 2 * C, generator=g).to(cuda).half()
+    wt = (torch.randn(C, 3 * C, 1, 1, generator=g) / (3 * C) ** 0.5).to(cuda).half()
+    bias = torch.randn(C, generator=g).to(cuda)
+    rs = torch.tensor([0.37], device=cuda)
+    ref = torch.relu(z.float() @ wt.float().reshape(C, 3 * C).t() + bias) + 0.37 * AR[:, C:].float()
+    ybuf = torch.zeros(M, 2 * C, device=cuda, dtype=torch.float16)
+    ops.conv_gemm(B, H, W, [(z, 0)], _pack_fwd(wt), C, ybuf[:, C:], bias=bias, act=1, epi=("residual", AR[:, C:], rs))
+    torch.cuda.synchronize()
+    assert _rel_err(ybuf[:, C:], ref) < 4e-3
+    assert bool((ybuf[:, :C] == 0).all())
+
+
+def test_fused_epilogue_needs_the_tensor_core_backend(cuda):
+    from dfcsa import ops
+    z = torch.zeros(256, 192, device=cuda, dtype=torch.float16)
+    w = torch.zeros(64, 128, device=cuda)
+    with pytest.raises(RuntimeError, match="DFCSA_BACKEND_TC"):
+        ops.conv_gemm(1, 16, 16, [(z[:, 64:], 0)], w, 64, z[:, :64], backend=ops.BACKEND_SIMT, epi=("gate_mix", z[:, 64:128], z[:, 128:]))
+
+
 @pytest.mark.parametrize("backend", [1, 0], ids=["simt", "tc"])
 def test_fp16_outputs_saturate_instead_of_overflowing(cuda, backend):
     """Precision policy: forward activations are stored in fp16; a result beyond +-65504 is clamped to the
