@@ -131,8 +131,8 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int kb = 0; kb < 2; ++kb) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = umma_smem_desc(p_addr + kb * 16384 + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(v_addr + kb * nb * 8192 + k * 2048, 8192, 1024);
+            const uint64_t da = umma_desc_add(umma_smem_desc(p_addr + kb * 16384, 16, 1024), k * 32);
+            const uint64_t db = umma_desc_add(umma_smem_desc(v_addr + kb * nb * 8192, 8192, 1024), k * 2048);
             umma_f16(tmem_o, da, db, a.idesc_o, (i | kb | k) != 0 ? 1u : 0u);
           }
         }
@@ -153,8 +153,8 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           const uint32_t k_addr = smem_u32(kv_smem + stage * stage_bytes);
           const int ksteps = (a.Cq + 15) / 16;          // the K block is zero beyond Cq
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = umma_smem_desc(q_addr + k * 32, 16, 1024);
-            const uint64_t db = umma_smem_desc(k_addr + k * 32, 16, 1024);
+            const uint64_t da = umma_desc_add(umma_smem_desc(q_addr, 16, 1024), k * 32);
+            const uint64_t db = umma_desc_add(umma_smem_desc(k_addr, 16, 1024), k * 32);
             umma_f16(tmem_base + buf * 128, da, db, a.idesc_s, k != 0 ? 1u : 0u);
           }
           umma_commit(&s_full[buf]);

@@ -146,7 +146,7 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
         const uint32_t kb_addr = smem_u32(st_smem + pstage * stage_bytes + 8192);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_dq, umma_smem_desc(ds_addr + k * 32, 16, 1024), umma_smem_desc(kb_addr + k * 2048, 8192, 1024), a.idesc_acc0,
+          umma_f16(tmem_dq, umma_desc_add(umma_smem_desc(ds_addr, 16, 1024), k * 32), umma_desc_add(umma_smem_desc(kb_addr, 8192, 1024), k * 2048), a.idesc_acc0,
                    (i | k) != 0 ? 1u : 0u);
         umma_commit(&ds_empty[buf]);
         umma_commit(&kv_empty[pstage]);
@@ -165,12 +165,12 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
           const uint32_t k16 = smem_u32(st_smem + stage * stage_bytes);
           const uint32_t vb = k16 + 16384;
           for (int k = 0; k < ksteps; ++k)
-            umma_f16(tmem_base + buf * 64, umma_smem_desc(q_addr + k * 32, 16, 1024), umma_smem_desc(k16 + k * 32, 16, 1024), a.idesc_s, k != 0 ? 1u : 0u);
+            umma_f16(tmem_base + buf * 64, umma_desc_add(umma_smem_desc(q_addr, 16, 1024), k * 32), umma_desc_add(umma_smem_desc(k16, 16, 1024), k * 32), a.idesc_s, k != 0 ? 1u : 0u);
           for (int jn = 0; jn < nb; ++jn)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_dp + buf * 64, umma_smem_desc(do_addr + jn * 16384 + k * 32, 16, 1024),
-                       umma_smem_desc(vb + jn * 8192 + k * 32, 16, 1024), a.idesc_dp, (jn | k) != 0 ? 1u : 0u);
+              umma_f16(tmem_dp + buf * 64, umma_desc_add(umma_smem_desc(do_addr + jn * 16384, 16, 1024), k * 32),
+                       umma_desc_add(umma_smem_desc(vb + jn * 8192, 16, 1024), k * 32), a.idesc_dp, (jn | k) != 0 ? 1u : 0u);
           umma_commit(&sd_full[buf]);
           if (j + 1 == a.tiles64) umma_commit(&a_empty);
         }
@@ -339,10 +339,10 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
         const uint32_t qb = s0 + 8192, dob = s0 + 16384;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_dv, umma_smem_desc(pt + k * 32, 16, 1024), umma_smem_desc(dob + k * 2048, 8192, 1024), a.idesc_acc1, (i | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_dv, umma_desc_add(umma_smem_desc(pt, 16, 1024), k * 32), umma_desc_add(umma_smem_desc(dob, 8192, 1024), k * 2048), a.idesc_acc1, (i | k) != 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_dk, umma_smem_desc(dst + k * 32, 16, 1024), umma_smem_desc(qb + k * 2048, 8192, 1024), a.idesc_acc0, (i | k) != 0 ? 1u : 0u);
+          umma_f16(tmem_dk, umma_desc_add(umma_smem_desc(dst, 16, 1024), k * 32), umma_desc_add(umma_smem_desc(qb, 8192, 1024), k * 2048), a.idesc_acc0, (i | k) != 0 ? 1u : 0u);
         umma_commit(&ds_empty[buf]);
         umma_commit(&kv_empty[pstage]);
       }
@@ -360,12 +360,12 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
           const uint32_t q16 = smem_u32(st_smem + stage * stage_bytes);
           const uint32_t dob = q16 + 16384;
           for (int k = 0; k < ksteps; ++k)
-            umma_f16(tmem_base + buf * 64, umma_smem_desc(k_addr + k * 32, 16, 1024), umma_smem_desc(q16 + k * 32, 16, 1024), a.idesc_s, k != 0 ? 1u : 0u);
+            umma_f16(tmem_base + buf * 64, umma_desc_add(umma_smem_desc(k_addr, 16, 1024), k * 32), umma_desc_add(umma_smem_desc(q16, 16, 1024), k * 32), a.idesc_s, k != 0 ? 1u : 0u);
           for (int jn = 0; jn < nb; ++jn)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16(tmem_dp + buf * 64, umma_smem_desc(v_addr + jn * 16384 + k * 32, 16, 1024),
-                       umma_smem_desc(dob + jn * 8192 + k * 32, 16, 1024), a.idesc_dp, (jn | k) != 0 ? 1u : 0u);
+              umma_f16(tmem_dp + buf * 64, umma_desc_add(umma_smem_desc(v_addr + jn * 16384, 16, 1024), k * 32),
+                       umma_desc_add(umma_smem_desc(dob + jn * 8192, 16, 1024), k * 32), a.idesc_dp, (jn | k) != 0 ? 1u : 0u);
           umma_commit(&sd_full[buf]);
           if (i + 1 == a.tiles64) umma_commit(&a_empty);
         }

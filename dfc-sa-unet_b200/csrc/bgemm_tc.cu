@@ -245,8 +245,8 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t da = a.a_mn ? umma_smem_desc(a_addr + k * 2048, 8192, 1024) : umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t db = a.b_mn ? umma_smem_desc(b_addr + k * 2048, 8192, 1024) : umma_smem_desc(b_addr + k * 32, 16, 1024);
+            const uint64_t da = a.a_mn ? umma_desc_add(umma_smem_desc(a_addr, 8192, 1024), k * 2048) : umma_desc_add(umma_smem_desc(a_addr, 16, 1024), k * 32);
+            const uint64_t db = a.b_mn ? umma_desc_add(umma_smem_desc(b_addr, 8192, 1024), k * 2048) : umma_desc_add(umma_smem_desc(b_addr, 16, 1024), k * 32);
             umma_f16(d_tmem, da, db, a.idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);

@@ -327,6 +327,15 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// The same descriptor `bytes` further into the tile.  Only the 14-bit start-address field (units of 16 B) moves, and a tile
+// inside the CTA's shared-memory window cannot carry out of it, so this is ONE 32-bit add on the low word - the issuing
+// thread builds the descriptor of a stage once and derives every k step / tap from it by a constant (building each one
+// from the address cost ~10 dependent uniform-datapath instructions per tcgen05.mma: at N <= 128 the single issuing
+// thread, not the tensor pipe, set the pace).
+__device__ __forceinline__ uint64_t umma_desc_add(uint64_t d, uint32_t bytes) {
+  const uint32_t lo = static_cast<uint32_t>(d) + (bytes >> 4);
+  return (d & 0xFFFFFFFF00000000ull) | static_cast<uint64_t>(lo);
+}
 // UMMA instruction descriptor for kind::f16: fp32 accumulator, per-operand fp16(0)/bf16(1) format and
 // K(0)/MN(1) majorness, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ inline uint32_t umma_idesc_f16(int m, int n, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {

@@ -303,23 +303,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (lane == 0) {
               const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
               const uint32_t b_addr = a_addr + kHaloBytes;
+              // one descriptor per operand and stage; every tap / k step is a constant further on (umma_desc_add)
               if (m3) {
+                // patch row g = 8 consecutive pixels = one 8-row core group; groups are 10 box rows apart
+                const uint64_t da0 = umma_smem_desc(a_addr, 16, 1280);
+                uint64_t db0 = umma_smem_desc(b_addr, 16, 1024);
+#pragma unroll
                 for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
-                  for (int k = 0; k < kBlockK / 16; ++k) {
-                    // patch row g = 8 consecutive pixels = one 8-row core group; groups are 10 box rows apart
-                    const uint64_t da = umma_smem_desc(a_addr + dw * 128 + k * 32, 16, 1280);
-                    const uint64_t db = umma_smem_desc(b_addr + dw * bn_bytes + k * 32, 16, 1024);
-                    umma_f16(d_tmem, da, db, a.idesc, (it | dw | k) != 0 ? 1u : 0u);
-                  }
+                  for (int k = 0; k < kBlockK / 16; ++k)
+                    umma_f16(d_tmem, umma_desc_add(da0, dw * 128 + k * 32), umma_desc_add(db0, k * 32), a.idesc,
+                             (dw | k) != 0 ? 1u : (it != 0 ? 1u : 0u));
+                  db0 = umma_desc_add(db0, bn_bytes);
                 }
               } else {
+                const uint64_t da0 = umma_smem_desc(a_addr, 16, 1024), db0 = umma_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-                  const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-                  umma_f16(d_tmem, da, db, a.idesc, (it | k) != 0 ? 1u : 0u);
-                }
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16(d_tmem, umma_desc_add(da0, k * 32), umma_desc_add(db0, k * 32), a.idesc, k != 0 ? 1u : (it != 0 ? 1u : 0u));
               }
               umma_commit(&empty_bar[stage]);
               if (it + 1 == items) umma_commit(&tmem_full_bar[as]);
@@ -338,25 +339,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         if (lane == 0) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + a.kbs * kABytes;
+          uint64_t da0 = umma_smem_desc(a_addr, 16, 1024), db0 = umma_smem_desc(b_addr, 16, 1024);
           if constexpr (TWO) {
             // one M = 256 instruction per 16 channels: rows 0-127 from this CTA's A tile, 128-255 from the peer's (same
             // shared-memory offsets), the N columns split between the two CTAs' B halves; accumulators in both CTAs' TMEM
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t da = umma_smem_desc(a_addr + k * 32, 16, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_f16_2cta(d_tmem, da, db, a.idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16_2cta(d_tmem, umma_desc_add(da0, k * 32), umma_desc_add(db0, k * 32), a.idesc, k != 0 ? 1u : (kb != 0 ? 1u : 0u));
             umma_commit_2cta(&empty_bar[stage]);                  // frees the stage in both CTAs
             if (kb + nsub >= a.total_kb) umma_commit_2cta(&tmem_full_bar[as]);
           } else {
+            const uint32_t b_sub = static_cast<uint32_t>(a.block_n * 128);
             for (int sub = 0; sub < nsub; ++sub) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                const uint64_t da = umma_smem_desc(a_addr + sub * kABytes + k * 32, 16, 1024);
-                const uint64_t db = umma_smem_desc(b_addr + sub * (a.block_n * 128) + k * 32, 16, 1024);
-                umma_f16(d_tmem, da, db, a.idesc, (kb | sub | k) != 0 ? 1u : 0u);
-              }
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16(d_tmem, umma_desc_add(da0, k * 32), umma_desc_add(db0, k * 32), a.idesc, k != 0 ? 1u : ((kb | sub) != 0 ? 1u : 0u));
+              da0 = umma_desc_add(da0, kABytes);
+              db0 = umma_desc_add(db0, b_sub);
             }
             umma_commit(&empty_bar[stage]);
             if (kb + nsub >= a.total_kb) umma_commit(&tmem_full_bar[as]);

@@ -160,23 +160,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       if (lane == 0) {
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
         const uint32_t b_addr = a_addr + kABytes;
+        // one descriptor per operand and stage; every k step / tap is a constant further on (umma_desc_add)
+        const uint32_t acc0 = first ? 0u : 1u;
         if (a.dw3) {
+          const uint64_t da0 = umma_smem_desc(a_addr, kBoxBytes, 1024);
+          const uint64_t db0 = umma_smem_desc(b_addr, a.x_box_bytes, 1024);
+#pragma unroll
           for (int dw = 0; dw < 3; ++dw) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // patch row k: 16 dy pixels against x pixels shifted by dw inside the 18-wide row
-              const uint64_t da = umma_smem_desc(a_addr + k * 2048, kBoxBytes, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + (k * 18 + dw) * 128, a.x_box_bytes, 1024);
-              umma_f16(tmem_base + dw * 128, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
-            }
+            for (int k = 0; k < 4; ++k)     // patch row k: 16 dy pixels against x pixels shifted by dw inside the 18-wide row
+              umma_f16(tmem_base + dw * 128, umma_desc_add(da0, k * 2048), umma_desc_add(db0, (k * 18 + dw) * 128), a.idesc,
+                       k == 0 ? acc0 : 1u);
           }
         } else {
+          uint64_t da0 = umma_smem_desc(a_addr, kBoxBytes, 1024);
+          const uint64_t db0 = umma_smem_desc(b_addr, kBoxBytes, 1024);
           for (int h = 0; h < n_halves; ++h) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {   // 16 pixels (rows) per instruction = 2 KiB
-              const uint64_t da = umma_smem_desc(a_addr + h * 2 * kBoxBytes + k * 2048, kBoxBytes, 1024);
-              const uint64_t db = umma_smem_desc(b_addr + k * 2048, kBoxBytes, 1024);
-              umma_f16(tmem_base + h * 256, da, db, a.idesc, (first && k == 0) ? 0u : 1u);
-            }
+            for (int k = 0; k < 4; ++k)     // 16 pixels (rows) per instruction = 2 KiB
+              umma_f16(tmem_base + h * 256, umma_desc_add(da0, k * 2048), umma_desc_add(db0, k * 2048), a.idesc, k == 0 ? acc0 : 1u);
+            da0 = umma_desc_add(da0, 2 * kBoxBytes);
           }
         }
         umma_commit(&empty_bar[stage]);

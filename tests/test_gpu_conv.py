@@ -106,6 +106,15 @@ CASES = [
     (4, 56, 56, [512], "3", 256, {"stats": True}),       # level-3 decoder 3x3
     (1, 151, 128, [1024], "1", 512, {"stats": True}),    # 151 pixel tiles (odd): the peer CTA of the last pair has no tile, two n tiles
     (5, 75, 75, [128], "3", 256, {"stats": True}),       # 3x3 spatial tiles smaller than 128 pixels, odd tile count (K = 1152)
+    # resident weights (one n tile, >= 4 pixel tiles per SM, the weight tile fits beside three activation stages)
+    (2, 224, 224, [128], "3", 64, {"stats": True}),      # level-1 decoder 3x3: 147 KB of weights, 3 halo stages
+    (2, 200, 200, [64, 64], "31", 64, {"bias": True}),   # halo path, two segments (the k-block offsets of the second one)
+    (2, 224, 224, [128], "1", 64, {"stats": True}),      # flat 1x1, two k blocks per stage
+    (3, 180, 180, [192], "1", 64, {}),                   # K = 192: an odd number of k blocks with two per stage
+    (2, 224, 224, [128], "1", 128, {"stats": True}),     # short-K statistics GEMM: one 64-wide n tile per CTA, each with its own resident half
+    (2, 224, 224, [64, 64], "11", 128, {"accumulate": True, "out_dt": torch.bfloat16, "src_dt": torch.bfloat16, "w_dt": torch.bfloat16}),
+    (2, 160, 160, [64], "3", 128, {"stats": True}),      # level-2 encoder 3x3 (N = 128, halo path)
+    (2, 160, 160, [384], "1", 128, {"stats": True}),     # level-2 fusion conv: 98 KB of weights
 ]
 _MODE = {"1": 0, "3": 1, "2": 2}
 

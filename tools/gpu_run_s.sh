@@ -1,0 +1,8 @@
+#!/bin/bash
+# round-2 GPU session S (1 GPU): ncu --set full with source counters of the level-1 decoder 3x3 conv (N = 64, K = 1152) and the level-2 one
+mkdir -p gpurun_out
+CMD="python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline --no-reference-gpu"
+timeout 600 $CMD > gpurun_out/s_plain.log 2>&1 || exit 1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 300 -c 1 -f -o gpurun_out/s_ncu_conv_n64_k1152 $CMD > gpurun_out/s_ncu1.log 2>&1
+tail -n 3 gpurun_out/s_ncu1.log
+ls -la gpurun_out/s_*
