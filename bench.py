@@ -338,28 +338,35 @@ def run_dfcsa(args):
         json.dump(rows, open(args.detail, "w"), indent=1)
 
     # ---------------- timed: end to end from pinned host memory ----------------
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    loss_host = 0.0
     # every step's images + masks cross PCIe inside the timed region (pinned host -> device staging buffers) and every
     # step's loss comes back to the host.  The copies go through trainer.device_feeder, the look-ahead feeder that
     # Trainer.train_epoch itself uses (the copy of batch i+1 runs on a copy stream while batch i trains; the generator
     # starts inside the timed region, so all K copies are counted); the loss of step i is read back asynchronously into
     # pinned memory and consumed after step i+1 has been enqueued, so the device never waits for the host.
     from dfcsa.trainer import device_feeder
-    loss_pin = torch.empty(args.steps, dtype=torch.float32).pin_memory()
-    evs = []
-    for i, (im, mk) in enumerate(device_feeder((host[j % 2] for j in range(args.steps)), dev)):
-        r = step(im, mk) if not args.no_graph else tr.train_step(im, mk, MICRO)
-        loss_pin[i:i + 1].copy_(r.stats[:1].detach(), non_blocking=True)     # device -> host read of the step's loss
-        ev = torch.cuda.Event(); ev.record(); evs.append(ev)
-        if i > 0:
-            evs[i - 1].synchronize()
-            loss_host = float(loss_pin[i - 1])
-    if evs:
-        evs[-1].synchronize()
-        loss_host = float(loss_pin[args.steps - 1])
+    loss_pin = torch.empty(max(args.steps, 2), dtype=torch.float32).pin_memory()
+
+    def e2e_pass(n):
+        evs, loss = [], 0.0
+        for i, (im, mk) in enumerate(device_feeder((host[j % 2] for j in range(n)), dev)):
+            r = step(im, mk) if not args.no_graph else tr.train_step(im, mk, MICRO)
+            loss_pin[i:i + 1].copy_(r.stats[:1].detach(), non_blocking=True)     # device -> host read of the step's loss
+            ev = torch.cuda.Event(); ev.record(); evs.append(ev)
+            if i > 0:
+                evs[i - 1].synchronize()
+                loss = float(loss_pin[i - 1])
+        if evs:
+            evs[-1].synchronize()
+            loss = float(loss_pin[n - 1])
+        return loss
+
+    # two untimed steps through the same path: the feeder's staging buffers come out of the caching allocator (a first
+    # cudaMalloc inside a 10-step timed region cost up to 7 ms per step in round-2 sessions Q / R / U), the copy stream exists
+    e2e_pass(2)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    loss_host = e2e_pass(args.steps)
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)

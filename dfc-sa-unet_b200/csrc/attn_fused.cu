@@ -89,14 +89,14 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = static_cast<int>(tile % a.m_tiles);
       const int b = static_cast<int>(tile / a.m_tiles);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_wait(&q_empty, qphase ^ 1);
         mbar_arrive_expect_tx(&q_full, kQBytes);
         tma_load_3d(q_smem, &map_q, &q_full, 0, mt * 128, b);
       }
       qphase ^= 1;
       for (int j = 0; j < a.key_tiles; ++j) {
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&kv_full[stage], static_cast<uint32_t>(stage_bytes));
           uint8_t* sk = kv_smem + stage * stage_bytes;
@@ -124,7 +124,7 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_wait(&p_full[buf], pph[buf]); pph[buf] ^= 1;
       if (i == 0) { mbar_wait(&o_empty, ophase ^ 1); ophase ^= 1; }
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t p_addr = smem_u32(p_smem + buf * kPBytes);
         const uint32_t v_addr = smem_u32(kv_smem + pstage * stage_bytes + kKBytes);
 #pragma unroll
@@ -149,7 +149,7 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         mbar_wait(&kv_full[stage], phase);
         mbar_wait(&s_empty[buf], sph[buf] ^ 1); sph[buf] ^= 1;
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t k_addr = smem_u32(kv_smem + stage * stage_bytes);
           const int ksteps = (a.Cq + 15) / 16;          // the K block is zero beyond Cq
           for (int k = 0; k < ksteps; ++k) {
@@ -165,7 +165,7 @@ attn_pv_fused_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         if (j >= 1) pv(j - 1);
       }
       pv(a.key_tiles - 1);
-      if (lane == 0) umma_commit(&o_full);
+      if (elect_one()) umma_commit(&o_full);
       __syncwarp();
     }
   } else if (warp >= 4) {

@@ -111,7 +111,7 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
     int stage = 0; uint32_t phase = 0, aphase = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int mt = static_cast<int>(tile % a.tiles128), b = static_cast<int>(tile / a.tiles128);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_wait(&a_empty, aphase ^ 1);
         mbar_arrive_expect_tx(&a_full, static_cast<uint32_t>(16384 + nb * 16384));
         tma_load_3d(q_smem, &map_q16, &a_full, 0, mt * 128, b);
@@ -119,7 +119,7 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
       }
       aphase ^= 1;
       for (int j = 0; j < a.tiles64; ++j) {
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&kv_full[stage], static_cast<uint32_t>(stage_bytes));
           uint8_t* s0 = st_smem + stage * stage_bytes;
@@ -141,7 +141,7 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
       mbar_wait(&ds_full[buf], pph[buf]); pph[buf] ^= 1;
       if (i == 0) { mbar_wait(&o_empty, ophase ^ 1); ophase ^= 1; }
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t ds_addr = smem_u32(ds_smem + buf * 16384);
         const uint32_t kb_addr = smem_u32(st_smem + pstage * stage_bytes + 8192);
 #pragma unroll
@@ -161,7 +161,7 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
         mbar_wait(&kv_full[stage], phase);
         mbar_wait(&sd_empty[buf], sph[buf] ^ 1); sph[buf] ^= 1;
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t k16 = smem_u32(st_smem + stage * stage_bytes);
           const uint32_t vb = k16 + 16384;
           for (int k = 0; k < ksteps; ++k)
@@ -179,7 +179,7 @@ attn_dq_fused_kernel(const __grid_constant__ CUtensorMap map_q16, const __grid_c
         if (j >= 1) acc(j - 1);
       }
       acc(a.tiles64 - 1);
-      if (lane == 0) umma_commit(&o_full);
+      if (elect_one()) umma_commit(&o_full);
       __syncwarp();
     }
   } else if (warp >= 4) {
@@ -299,7 +299,7 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
     int stage = 0; uint32_t phase = 0, aphase = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int kt = static_cast<int>(tile % a.tiles128), b = static_cast<int>(tile / a.tiles128);
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_wait(&a_empty, aphase ^ 1);
         mbar_arrive_expect_tx(&a_full, static_cast<uint32_t>(16384 + nb * 16384));
         tma_load_3d(k_smem, &map_k16, &a_full, 0, kt * 128, b);
@@ -307,7 +307,7 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
       }
       aphase ^= 1;
       for (int i = 0; i < a.tiles64; ++i) {
-        if (lane == 0) {
+        if (elect_one()) {
           const int nvalid = min(64, a.N - i * 64);
           mbar_wait(&kv_empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&kv_full[stage], static_cast<uint32_t>(tile_bytes + 8 * nvalid));
@@ -333,7 +333,7 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
       mbar_wait(&ds_full[buf], pph[buf]); pph[buf] ^= 1;
       if (i == 0) { mbar_wait(&o_empty, ophase ^ 1); ophase ^= 1; }
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t pt = smem_u32(pt_smem + buf * 16384), dst = smem_u32(dst_smem + buf * 16384);
         const uint32_t s0 = smem_u32(st_smem + pstage * stage_bytes);
         const uint32_t qb = s0 + 8192, dob = s0 + 16384;
@@ -356,7 +356,7 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
         mbar_wait(&kv_full[stage], phase);
         mbar_wait(&sd_empty[buf], sph[buf] ^ 1); sph[buf] ^= 1;
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t q16 = smem_u32(st_smem + stage * stage_bytes);
           const uint32_t dob = q16 + 16384;
           for (int k = 0; k < ksteps; ++k)
@@ -374,7 +374,7 @@ attn_dkdv_fused_kernel(const __grid_constant__ CUtensorMap map_k16, const __grid
         if (i >= 1) acc(i - 1);
       }
       acc(a.tiles64 - 1);
-      if (lane == 0) umma_commit(&o_full);
+      if (elect_one()) umma_commit(&o_full);
       __syncwarp();
     }
   } else if (warp >= 4) {

@@ -207,7 +207,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       const int b = static_cast<int>(r / a.m_tiles);
       const int m0 = mt * 128, n0 = nt * a.block_n;
       for (int kb = 0; kb < a.total_kb; ++kb) {
-        if (lane == 0) {
+        if (elect_one()) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], tx);
           uint8_t* sa = smem + stage * stage_bytes;
@@ -240,7 +240,7 @@ bgemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       for (int kb = 0; kb < a.total_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + kABytes;
 #pragma unroll

@@ -212,7 +212,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int rows = m3 ? 3 : 1;
           for (int dh = 0; dh < rows; ++dh) {
             for (int kb = 0; kb < a.seg_kb[s]; ++kb) {
-              if (lane == 0) {
+              if (elect_one()) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * stage_bytes;
                 uint8_t* sb = sa + kHaloBytes;
@@ -247,7 +247,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           else if (mode == DFCSA_TAP_3x3) { c1 = tc.w0 + (t % 3) - 1; c2 = tc.h0 + (t / 3) - 1; c3 = tc.tb; c4 = 0; }
           else { c1 = tc.w0; c2 = tc.h0; c3 = tc.tb; c4 = 0; }
           for (int kb = 0; kb < a.seg_kb[s]; ++kb) {
-            if (lane == 0) {
+            if (elect_one()) {
               if constexpr (TWO) {
                 // each CTA loads its own 128 pixel rows of A and its HALF of the B tile; both signal the leader's barrier,
                 // which expects the bytes of both (the peer's bytes may land before the leader has armed the phase: the
@@ -300,7 +300,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int j = 0; j < n_it; ++j, ++it) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
               const uint32_t b_addr = a_addr + kHaloBytes;
               // one descriptor per operand and stage; every tap / k step is a constant further on (umma_desc_add)
@@ -336,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         const int nsub = min(a.kbs, a.total_kb - kb);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
           const uint32_t b_addr = a_addr + a.kbs * kABytes;
           uint64_t da0 = umma_smem_desc(a_addr, 16, 1024), db0 = umma_smem_desc(b_addr, 16, 1024);

@@ -127,7 +127,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       const int th = static_cast<int>(r % a.tiles_h);
       const int tb = static_cast<int>(r / a.tiles_h);
       const int w0 = tw * a.w_t, h0 = th * a.h_t;
-      if (lane == 0) {
+      if (elect_one()) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
         uint8_t* sa = smem + stage * kStageBytes;
@@ -157,7 +157,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     for (long long pb = pb_beg; pb < pb_end; ++pb) {
       mbar_wait(a.cvt_x ? &cvt_bar[stage] : &full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
         const uint32_t b_addr = a_addr + kABytes;
         // one descriptor per operand and stage; every k step / tap is a constant further on (umma_desc_add)
@@ -165,10 +165,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         if (a.dw3) {
           const uint64_t da0 = umma_smem_desc(a_addr, kBoxBytes, 1024);
           const uint64_t db0 = umma_smem_desc(b_addr, a.x_box_bytes, 1024);
+          // k outer, tap inner: consecutive instructions accumulate into different TMEM tiles and share the dy operand
+          // (measured 1 % faster than tap outer once the issue path was short, profiles/bench_r02_u_*.json)
 #pragma unroll
-          for (int dw = 0; dw < 3; ++dw) {
+          for (int k = 0; k < 4; ++k) {     // patch row k: 16 dy pixels against x pixels shifted by dw inside the 18-wide row
 #pragma unroll
-            for (int k = 0; k < 4; ++k)     // patch row k: 16 dy pixels against x pixels shifted by dw inside the 18-wide row
+            for (int dw = 0; dw < 3; ++dw)
               umma_f16(tmem_base + dw * 128, umma_desc_add(da0, k * 2048), umma_desc_add(db0, (k * 18 + dw) * 128), a.idesc,
                        k == 0 ? acc0 : 1u);
           }
@@ -188,7 +190,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       __syncwarp();
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
-    if (lane == 0) umma_commit(&done_bar);
+    if (elect_one()) umma_commit(&done_bar);
     __syncwarp();
   } else {
     // ===================== x: fp16 -> bf16 in place (only when the operand formats differ) =====================
