@@ -297,6 +297,7 @@ __global__ void pool_rows_kernel(const act_t* a0, long long ld, int B, int H, in
     const act_t* row = a0 + ((b * H + y) * W) * ld + cv * VEC;
     // four pixels of the window per step with their loads issued together: one dependent 16-byte load per thread at a time
     // left this pass at 0.4 - 0.6 of copy bandwidth (ncu: 34 % occupancy, long-scoreboard stalls)
+    // (eight in flight: 0.1274 -> 0.1259 ms at level 1, not kept)
     for (int x = lo; x < hi; x += 4) {
       RawV<VEC, act_t> raw[4];
 #pragma unroll
@@ -390,6 +391,80 @@ cols_reduce_kernel(const float* __restrict__ tmp, int B, int H, int P, int C, in
 #pragma unroll
       for (int v = 0; v < V; ++v) dot = fmaf(acc[v], w[v], dot);
     }
+  }
+  if (dot_out != nullptr) block_scalar_reduce_add(dot, dot_out);   // <unscaled result, dot_with>
+}
+
+// The same reduction with ONE CTA per pooled cell (b, i, j): CV = C / V channel vectors x 256 / CV row parts, the parts meet
+// in shared memory.  For coarse pooled maps (P = 4 at 224^2: 1024 cells x 16 channel vectors, each walking 56 - 116 rows
+// with one dependent load in flight) the thread-per-output kernel above is a latency chain on 64 CTAs: 45 us for the
+// 14.7 MB of tmp at level 1 (ncu: 12 % of the warp slots active).
+template <int V>
+__global__ void __launch_bounds__(256)
+cols_reduce_par_kernel(const float* __restrict__ tmp, int B, int H, int P, int C, int mode, const float* mul,
+                       float* __restrict__ out, const float* __restrict__ dot_with, double* dot_out) {
+  __shared__ __align__(16) float s_part[256 * V];
+  const int CV = C / V;                       // divides 256 (host)
+  const int parts = 256 / CV;
+  const int cv = threadIdx.x % CV, part = threadIdx.x / CV;
+  const float m = mul ? *mul : 1.f;
+  const long long cells = static_cast<long long>(B) * P * P;
+  const long long ystride = static_cast<long long>(P) * C;
+  float dot = 0.f;
+  for (long long cell = blockIdx.x; cell < cells; cell += gridDim.x) {
+    const int j = static_cast<int>(cell % P);
+    const int i = static_cast<int>((cell / P) % P);
+    const long long b = cell / (static_cast<long long>(P) * P);
+    const float* col = tmp + (b * H * P + j) * C + cv * V;          // + y * P * C
+    float acc[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.f;
+    float den = 1.f;
+    if (mode == 0) {
+      int lo, hi; pool_win(i, H, P, lo, hi);
+      for (int y = lo + part; y < hi; y += parts) {
+        float t[V]; ldf<V>(col + y * ystride, t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] += t[v];
+      }
+      den = static_cast<float>(hi - lo);
+    } else {
+      const float ratio = static_cast<float>(H) / static_cast<float>(P);
+      int lo = static_cast<int>(floorf((i - 0.5f) * ratio - 0.5f)) - 1;
+      int hi = static_cast<int>(ceilf((i + 1.5f) * ratio - 0.5f)) + 1;
+      lo = max(lo, 0); hi = min(hi, H - 1);
+      for (int y = lo + part; y <= hi; y += parts) {
+        int i0, i1; float l1; bilerp_taps(y, P, H, i0, i1, l1);
+        float wgt = 0.f;
+        if (i0 == i) wgt += 1.f - l1;
+        if (i1 == i) wgt += l1;
+        if (wgt != 0.f) {
+          float t[V]; ldf<V>(col + y * ystride, t);
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[v] += wgt * t[v];
+        }
+      }
+    }
+    stf<V>(s_part + threadIdx.x * V, acc);
+    __syncthreads();
+    if (part == 0) {
+      for (int p2 = 1; p2 < parts; ++p2) {
+        float t[V]; ldf<V>(s_part + (p2 * CV + cv) * V, t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[v] += t[v];
+      }
+      float r[V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) { if (mode == 0) acc[v] /= den; r[v] = acc[v] * m; }
+      const long long o = cell * C + cv * V;
+      stf<V>(out + o, r);
+      if (dot_with != nullptr) {
+        float w[V]; ldf<V>(dot_with + o, w);
+#pragma unroll
+        for (int v = 0; v < V; ++v) dot = fmaf(acc[v], w[v], dot);
+      }
+    }
+    __syncthreads();
   }
   if (dot_out != nullptr) block_scalar_reduce_add(dot, dot_out);   // <unscaled result, dot_with>
 }
@@ -584,8 +659,10 @@ gate_mix_fwd_kernel(const act_t* g0, long long ld_g0, long long M, int C, const 
 
 // y = relu(bn4(F0)) + rs*R, optional 2x2 max pool; one thread per 2x2 window and channel vector
 // PLAIN (the addition / attention-only ablation blocks): y = F0 [+ F1] + rs*R, no BatchNorm / ReLU
-template <int VEC, bool PLAIN = false>
-__global__ void __launch_bounds__(256)
+// PRE: the eight (twelve) loads of a window are issued before its first store - a store to y orders the next pixel's loads
+// behind it (same element type, may alias), which makes a window four dependent round trips.
+template <int VEC, bool PLAIN = false, bool PRE = false>
+__global__ void __launch_bounds__(256, PRE ? 3 : 4)
 block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long ld_r, int B, int H, int W, int C,
                      const float* s4, const float* t4, const float* res_scale, act_t* y, long long ld_y, act_t* yp,
                      long long ld_yp, grad_t* yb, long long ld_yb, grad_t* ypb, long long ld_ypb, int CL, int PL,
@@ -604,16 +681,30 @@ block_out_fwd_kernel(const act_t* f0, long long ld_f0, const act_t* r, long long
     float mx[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) mx[v] = -INFINITY;
+    RawV<VEC, act_t> fraw[PRE ? 4 : 1], rraw[PRE ? 4 : 1], graw[PRE && PLAIN ? 4 : 1];
+    if constexpr (PRE) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // edge windows of odd maps: the clamped duplicate is loaded and dropped
+        const unsigned yy = min(2 * yo + (k >> 1), static_cast<unsigned>(H) - 1), xx = min(2 * xo + (k & 1), static_cast<unsigned>(W) - 1);
+        const long long m = (static_cast<long long>(b) * H + yy) * W + xx;
+        fraw[k] = ldraw<VEC>(f0 + m * ld_f0 + c); rraw[k] = ldraw<VEC>(r + m * ld_r + c);
+        if constexpr (PLAIN) { if (f1 != nullptr) graw[k] = ldraw<VEC>(f1 + m * ld_f1 + c); }
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const unsigned yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
       if (yy >= static_cast<unsigned>(H) || xx >= static_cast<unsigned>(W)) continue;
       const long long m = (static_cast<long long>(b) * H + yy) * W + xx;
       float fv[VEC], rv[VEC], ov[VEC];
-      ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv);
+      if constexpr (PRE) { cvtraw<VEC>(fraw[k], fv); cvtraw<VEC>(rraw[k], rv); }
+      else { ldv<VEC>(f0 + m * ld_f0 + c, fv); ldv<VEC>(r + m * ld_r + c, rv); }
       if (PLAIN) {
         if (f1 != nullptr) {
-          float gv[VEC]; ldv<VEC>(f1 + m * ld_f1 + c, gv);
+          float gv[VEC];
+          if constexpr (PRE && PLAIN) cvtraw<VEC>(graw[k], gv);
+          else ldv<VEC>(f1 + m * ld_f1 + c, gv);
 #pragma unroll
           for (int v = 0; v < VEC; ++v) fv[v] += gv[v];
         }
@@ -763,6 +854,104 @@ block_out_bwd_reduce_kernel(const grad_t* dskip, long long ld_dskip, const grad_
   block_scalar_reduce_add(drs_acc, drs);
 }
 
+// The same pass for the blocks with a max pool behind them, every load of a 2x2 window issued before the first use.  Above,
+// the in-place store of dy (dy_out == dskip) orders the loads of the next pixel behind it, so a window is four dependent
+// round trips after the argmax loads: 0.70 of copy bandwidth on the encoder blocks against 0.92 on the decoder blocks.
+// 17 sixteen-byte loads in flight per thread: two resident CTAs per SM.
+template <int VEC>
+__global__ void __launch_bounds__(256, 2)
+block_out_bwd_reduce_pre_kernel(const grad_t* dskip, long long ld_dskip, const grad_t* dyp, long long ld_dyp,
+                                const act_t* y, long long ld_y, const act_t* f0, long long ld_f0, const act_t* r,
+                                long long ld_r, int B, int H, int W, int C, const float* s4, const float* t4,
+                                const float* mean4, const float* invstd4, grad_t* dy_out, long long ld_dy, double* red4,
+                                double* drs, int CL, int PL) {
+  __shared__ float s_red[2 * 256 * VEC];
+  __shared__ __align__(16) float s_aff[2 * 32 * VEC];     // (scale, shift) of the CTA's channels: read at use, not held in registers
+  const int cl = threadIdx.x % CL, pl = threadIdx.x / CL;
+  const int c_base = blockIdx.y * CL * VEC;
+  const int c = c_base + cl * VEC;
+  const bool active = pl < PL && c < C;
+  const int Hw = (H + 1) / 2, Ww = (W + 1) / 2;
+  const int Hp = H / 2, Wp = W / 2;
+  const unsigned nwin = static_cast<unsigned>(B) * Hw * Ww;
+  float acc[2][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { acc[0][v] = 0.f; acc[1][v] = 0.f; }
+  float drs_acc = 0.f;
+  if (threadIdx.x < CL * VEC && c_base + threadIdx.x < C) {
+    s_aff[threadIdx.x] = s4[c_base + threadIdx.x];
+    s_aff[32 * VEC + threadIdx.x] = t4[c_base + threadIdx.x];
+  }
+  __syncthreads();
+  if (active) {
+    PixIter it; it.init(blockIdx.x * PL + pl, gridDim.x * PL, Hw, Ww);
+    for (unsigned wi = blockIdx.x * PL + pl; wi < nwin; wi += gridDim.x * PL, it.next(Hw, Ww)) {
+      const int xo = it.x, yo = it.y;
+      const long long b = it.b;
+      const bool pooled = yo < Hp && xo < Wp;         // dyp is given (host); edge windows of odd maps have no pooled cell
+      RawV<VEC, act_t> yraw[4], fraw[4], rraw[4];
+      RawV<VEC, grad_t> draw[4], gpraw;
+      long long mk[4];
+      bool ok[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int yy = 2 * yo + (k >> 1), xx = 2 * xo + (k & 1);
+        ok[k] = yy < H && xx < W;
+        mk[k] = (b * H + min(yy, H - 1)) * W + min(xx, W - 1);   // clamped duplicates are loaded and dropped, never stored
+        yraw[k] = ldraw<VEC>(y + mk[k] * ld_y + c);
+        if (dskip != nullptr) draw[k] = ldraw<VEC>(dskip + mk[k] * ld_dskip + c);
+        fraw[k] = ldraw<VEC>(f0 + mk[k] * ld_f0 + c);
+        rraw[k] = ldraw<VEC>(r + mk[k] * ld_r + c);
+      }
+      gpraw = ldraw<VEC>(dyp + ((b * Hp + min(yo, Hp - 1)) * Wp + min(xo, Wp - 1)) * ld_dyp + c);
+      // argmax of the stored y over the window (first maximum in scan order, like ATen's max_pool2d)
+      int arg[VEC];
+      float gp[VEC], best[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) { best[v] = -INFINITY; arg[v] = 0; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float yv[VEC]; cvtraw<VEC>(yraw[k], yv);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) if (yv[v] > best[v]) { best[v] = yv[v]; arg[v] = k; }
+      }
+      cvtraw<VEC>(gpraw, gp);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (!ok[k]) continue;
+        float d[VEC];
+        if (dskip != nullptr) cvtraw<VEC>(draw[k], d);
+        else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[v] = 0.f;
+        }
+        if (pooled) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) if (arg[v] == k) d[v] += gp[v];
+        }
+        if (dy_out != dskip || pooled) {
+          // round to the stored precision first, so the sums see exactly what the later passes read
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) d[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(d[v]));
+          stv<VEC>(dy_out + mk[k] * ld_dy + c, d);
+        }
+        float fv[VEC], rv[VEC], sc[VEC], sh[VEC];
+        cvtraw<VEC>(fraw[k], fv); cvtraw<VEC>(rraw[k], rv);
+        ldf<VEC>(s_aff + cl * VEC, sc); ldf<VEC>(s_aff + 32 * VEC + cl * VEC, sh);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          drs_acc = fmaf(d[v], rv[v], drs_acc);
+          const float d4 = fmaf(fv[v], sc[v], sh[v]) > 0.f ? d[v] : 0.f;
+          acc[0][v] += d4;
+          acc[1][v] = fmaf(d4, fv[v], acc[1][v]);
+        }
+      }
+    }
+  }
+  flush_bn_partials<VEC>(acc, cl, pl, CL, PL, c_base, C, mean4, invstd4, red4, s_red);
+  block_scalar_reduce_add(drs_acc, drs);
+}
+
 // dx = scale * (d - k1 - xhat*k2), d = dy * [relu mask] (act_mode 0) or dy (act_mode 2)
 template <int VEC>
 __global__ void __launch_bounds__(256, 4)
@@ -873,8 +1062,10 @@ gate_mix_bwd_apply_kernel(const grad_t* dz, long long ld_dz, const act_t* z, lon
   }
 }
 
-// pass 1 of the branch backward: gate-mix terms into dL / dA (in place) and the BN1 reductions
-template <int VEC, int OCC>
+// pass 1 of the branch backward: gate-mix terms into dL / dA (in place) and the BN1 reductions.
+// PIX pixels per grid-stride step with every load issued before the first use, like the gate kernels: five 16-byte loads
+// per pixel and a sigmoid per element leave the memory pipe idle between steps when one pixel is walked at a time.
+template <int VEC, int OCC, int PIX>
 __global__ void __launch_bounds__(256, OCC)
 branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long long ld_l0, const act_t* g0, long long ld_g0,
                           long long M, int C, const float* s1, const float* t1, const float* mean1,
@@ -891,28 +1082,47 @@ branch_bwd_reduce1_kernel(grad_t* dz, long long ld_dz, const act_t* l0, long lon
     float sc[VEC], sh[VEC], sc3[VEC], sh3[VEC];
     ldf<VEC>(s1 + c, sc); ldf<VEC>(t1 + c, sh);
     if (gated) { ldf<VEC>(s3 + c, sc3); ldf<VEC>(t3 + c, sh3); }
-    for (long long m = static_cast<long long>(blockIdx.x) * PL + pl; m < M; m += static_cast<long long>(gridDim.x) * PL) {
-      float dl[VEC], da[VEC], df[VEC], gv[VEC], lv[VEC];
-      ldv<VEC>(dz + m * ld_dz + C + c, dl);
-      ldv<VEC>(l0 + m * ld_l0 + c, lv);
-      if (gated) {
-        ldv<VEC>(dz + m * ld_dz + 2 * C + c, da);
-        ldv<VEC>(dz + m * ld_dz + c, df); ldv<VEC>(g0 + m * ld_g0 + c, gv);
-        // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); rounded to the stored precision so that the sums see
-        // exactly what the later passes read back
+    const long long stride = static_cast<long long>(gridDim.x) * PL;
+    for (long long m0 = static_cast<long long>(blockIdx.x) * PL + pl; m0 < M; m0 += PIX * stride) {
+      RawV<VEC, grad_t> dlraw[PIX], daraw[PIX], dfraw[PIX];
+      RawV<VEC, act_t> lraw[PIX], graw[PIX];
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          const float gg = fast_sigmoid(fmaf(gv[v], sc3[v], sh3[v]));
-          dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
-          da[v] = fmaf(df[v], 1.f - gg, da[v]);
+      for (int u = 0; u < PIX; ++u) {
+        const long long m = min(m0 + u * stride, M - 1);   // a clamped duplicate is loaded and dropped, never stored
+        dlraw[u] = ldraw<VEC>(dz + m * ld_dz + C + c);
+        lraw[u] = ldraw<VEC>(l0 + m * ld_l0 + c);
+        if (gated) {
+          daraw[u] = ldraw<VEC>(dz + m * ld_dz + 2 * C + c);
+          dfraw[u] = ldraw<VEC>(dz + m * ld_dz + c);
+          graw[u] = ldraw<VEC>(g0 + m * ld_g0 + c);
         }
-        stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
       }
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        const float d1 = fmaf(lv[v], sc[v], sh[v]) > 0.f ? dl[v] : 0.f;
-        acc[0][v] += d1;
-        acc[1][v] = fmaf(d1, lv[v], acc[1][v]);
+      for (int u = 0; u < PIX; ++u) {
+        const long long m = m0 + u * stride;
+        if (m < M) {
+          float dl[VEC], lv[VEC];
+          cvtraw<VEC>(dlraw[u], dl); cvtraw<VEC>(lraw[u], lv);
+          if (gated) {
+            float da[VEC], df[VEC], gv[VEC];
+            cvtraw<VEC>(daraw[u], da); cvtraw<VEC>(dfraw[u], df); cvtraw<VEC>(graw[u], gv);
+            // fused = g*L + (1-g)*A  ->  dL += df*g, dA += df*(1-g); rounded to the stored precision so that the sums see
+            // exactly what the later passes read back
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+              const float gg = fast_sigmoid(fmaf(gv[v], sc3[v], sh3[v]));
+              dl[v] = Cvt<grad_t>::to_f(Cvt<grad_t>::from_f(fmaf(df[v], gg, dl[v])));
+              da[v] = fmaf(df[v], 1.f - gg, da[v]);
+            }
+            stv<VEC>(dz + m * ld_dz + C + c, dl); stv<VEC>(dz + m * ld_dz + 2 * C + c, da);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            const float d1 = fmaf(lv[v], sc[v], sh[v]) > 0.f ? dl[v] : 0.f;
+            acc[0][v] += d1;
+            acc[1][v] = fmaf(d1, lv[v], acc[1][v]);
+          }
+        }
       }
     }
   }
@@ -978,10 +1188,83 @@ bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int 
   }
 }
 
+// The same pass with every pixel loaded ONCE: the lanes of a group take source cell j of row (b, y), i.e. the pixels whose
+// LEFT bilinear tap is j (decided by bilerp_taps itself, the analytic range only brackets them), and keep two sums -
+// (1 - lx) d for output j and lx d for output j + 1.  The two halves of an output meet in shared memory (P * group
+// divides the CTA, so a row never straddles two CTAs).  The two-sided window above loads and weighs every pixel twice
+// and is bound by instruction issue (ncu at level 1: 73 % issue-active, 126 us for 411 MB).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+bilerpT_rows1_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int C, int P, float* tmp, int parts) {
+  __shared__ __align__(16) float s_b[256 * VEC];
+  const int CV = C / VEC;
+  const int group = CV * parts;
+  const long long total = static_cast<long long>(B) * H * P * group;
+  const bool small = total < (1LL << 31);
+  const float ratio = static_cast<float>(W) / static_cast<float>(P);
+  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < total;
+       base += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long i = base + threadIdx.x;
+    const bool active = i < total;           // P * group divides 256 and total: a row is active as a whole
+    int lg, j, y; long long b;
+    decode4(active ? i : total - 1, small, group, P, H, lg, j, y, b);
+    const int part = lg / CV;
+    const int c = (lg - part * CV) * VEC;
+    // x0 == j  <=>  src in [j, j + 1) (src clamped at 0: cell 0 starts at pixel 0; the last cell runs to the end)
+    int lo = j == 0 ? 0 : static_cast<int>(floorf((j + 0.5f) * ratio - 0.5f)) - 1;
+    int hi = j == P - 1 ? W - 1 : static_cast<int>(ceilf((j + 1.5f) * ratio - 0.5f)) + 1;
+    lo = max(lo, 0); hi = min(hi, W - 1);
+    float acc_a[VEC], acc_b[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { acc_a[v] = 0.f; acc_b[v] = 0.f; }
+    const grad_t* row = dz + ((b * H + y) * W) * ld_dz + 2 * C + c;
+    for (int x = lo + part; x <= hi; x += 4 * parts) {
+      RawV<VEC, grad_t> raw[4];
+      float wa[4], wb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int xx = x + u * parts;
+        const bool ok = xx <= hi;
+        const int xc = ok ? xx : hi;
+        int x0, x1; float lx; bilerp_taps(xc, P, W, x0, x1, lx);
+        const bool mine = ok && x0 == j;
+        // the last cell's right tap is the cell itself (x1 clamps to P - 1)
+        wa[u] = mine ? (x1 == j ? 1.f : 1.f - lx) : 0.f;
+        wb[u] = mine && x1 != j ? lx : 0.f;
+        raw[u] = ldraw<VEC>(row + xc * ld_dz);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float d[VEC]; cvtraw<VEC>(raw[u], d);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { acc_a[v] = fmaf(wa[u], d[v], acc_a[v]); acc_b[v] = fmaf(wb[u], d[v], acc_b[v]); }
+      }
+    }
+    for (int off = CV; off < group; off <<= 1) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        acc_a[v] += __shfl_xor_sync(0xffffffffu, acc_a[v], off);
+        acc_b[v] += __shfl_xor_sync(0xffffffffu, acc_b[v], off);
+      }
+    }
+    if (part == 0) stf<VEC>(s_b + threadIdx.x * VEC, acc_b);
+    __syncthreads();
+    if (active && part == 0) {
+      if (j > 0) {
+        float t[VEC]; ldf<VEC>(s_b + (threadIdx.x - group) * VEC, t);      // cell j - 1 of the same row: `group` threads back
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc_a[v] += t[v];
+      }
+      stf<VEC>(tmp + ((b * H + y) * P + j) * C + c, acc_a);
+    }
+    __syncthreads();
+  }
+}
+
 // lanes per output of bilerpT_rows_kernel: CV * parts must be a power of two <= 32, and a part should keep >= 8 pixels
-static int bilerpT_parts(int CV, int W, int P) {
+static int bilerpT_parts(int CV, int W, int P, bool one_cell = false) {
   if (CV <= 0 || (CV & (CV - 1)) != 0 || CV >= 32) return 1;
-  const int window = 2 * ((W + P - 1) / P) + 4;
+  const int window = (one_cell ? 1 : 2) * ((W + P - 1) / P) + 4;
   int parts = 1;
   while (parts * 2 * CV <= 32 && parts * 2 * 8 <= window) parts *= 2;
   return parts;
@@ -1386,6 +1669,19 @@ __global__ void __launch_bounds__(256) cast2d_vec_kernel(const TX* __restrict__ 
 static int ew_blocks(long long total) {
   return static_cast<int>(std::max<long long>(1, std::min<long long>((total + 255) / 256, 148LL * 32)));
 }
+static bool bout_fwd_pre() {
+  static const bool on = [] { const char* e = getenv("DFCSA_BOUT_FWD_PRE"); return !e || atoi(e) != 0; }();
+  return on;
+}
+// cols_reduce_par_kernel: C / 4 channel vectors must divide the CTA, and the rows of a window must be worth splitting
+static bool cols_par_ok(int C, int H, int P) {
+  static const bool on = [] { const char* e = getenv("DFCSA_COLS_PAR"); return !e || atoi(e) != 0; }();
+  const int cv = C / 4;
+  return on && C % 4 == 0 && cv <= 256 && 256 % cv == 0 && H / P >= 8;
+}
+static int cols_par_blocks(int B, int P) {
+  return static_cast<int>(std::min<long long>(static_cast<long long>(B) * P * P, 148LL * 8));
+}
 
 }  // namespace
 }  // namespace dfcsa
@@ -1448,7 +1744,9 @@ extern "C" int dfcsa_bnrelu_pool_fwd(const void* a0, int64_t ld, int32_t B, int3
   DFCSA_LAUNCH_CHECK("pool_rows_kernel");
   // with_masks: tmp / pooled hold three planes ([3][B, ...]); the column pass sees them as 3 B images
   const int Bc = with_masks ? 3 * B : B;
-  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0)
+  if (cols_par_ok(C, H, P) && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0)
+    cols_reduce_par_kernel<4><<<cols_par_blocks(Bc, P), 256, 0, ST>>>(tmp, Bc, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
+  else if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0)
     cols_reduce_kernel<4><<<ew_blocks(static_cast<long long>(Bc) * P * P * (C / 4)), 256, 0, ST>>>(tmp, Bc, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
   else
     cols_reduce_kernel<1><<<ew_blocks(static_cast<long long>(Bc) * P * P * C), 256, 0, ST>>>(tmp, Bc, H, P, C, 0, nullptr, pooled, nullptr, nullptr);
@@ -1527,6 +1825,14 @@ extern "C" int dfcsa_sum_out_fwd(const void* a, int64_t ld_a, const void* b, int
   const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
   DFCSA_CHECK_ARG(nwin < (1LL << 31), "dfcsa_sum_out_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  if (bout_fwd_pre() && v8) {
+    dim3 grid3(red_blocks(nwin, g.PL, g.chunks, 3), g.chunks);
+    block_out_fwd_kernel<8, true, true><<<grid3, 256, 0, ST>>>(A_(a), ld_a, A_(r), ld_r, B, H, W, C, nullptr, nullptr, res_scale,
+                                                               AM_(y), ld_y, AM_(yp), ld_yp, nullptr, 0, nullptr, 0,
+                                                               g.CL, g.PL, A_(b), ld_b);
+    DFCSA_LAUNCH_CHECK("block_out_fwd_kernel<plain, pre>");
+    return DFCSA_OK;
+  }
   dim3 grid(red_blocks(nwin, g.PL, g.chunks, 4), g.chunks);
   VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC, true><<<grid, 256, 0, ST>>>(A_(a), ld_a, A_(r), ld_r, B, H, W, C, nullptr, nullptr, res_scale,
                                                                           AM_(y), ld_y, AM_(yp), ld_yp, nullptr, 0, nullptr, 0,
@@ -1545,6 +1851,13 @@ extern "C" int dfcsa_block_out_fwd(const void* f0, int64_t ld_f0, const void* r,
   const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
   DFCSA_CHECK_ARG(nwin < (1LL << 31), "dfcsa_block_out_fwd: too many pixels");
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
+  if (bout_fwd_pre() && v8) {
+    dim3 grid3(red_blocks(nwin, g.PL, g.chunks, 3), g.chunks);
+    block_out_fwd_kernel<8, false, true><<<grid3, 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4, res_scale,
+                                                                AM_(y), ld_y, AM_(yp), ld_yp, GM_(yb), ld_yb, GM_(ypb), ld_ypb, g.CL, g.PL);
+    DFCSA_LAUNCH_CHECK("block_out_fwd_kernel<pre>");
+    return DFCSA_OK;
+  }
   dim3 grid(red_blocks(nwin, g.PL, g.chunks, 4), g.chunks);
   VEC_DISPATCH(v8, (block_out_fwd_kernel<VEC><<<grid, 256, 0, ST>>>(A_(f0), ld_f0, A_(r), ld_r, B, H, W, C, scale4, shift4, res_scale,
                                                                     AM_(y), ld_y, AM_(yp), ld_yp, GM_(yb), ld_yb, GM_(ypb), ld_ypb,
@@ -1564,6 +1877,15 @@ extern "C" int dfcsa_block_out_bwd_reduce(const void* dskip, int64_t ld_dskip, c
                           {dskip, dyp, y, f0, r, dy_out, scale4, shift4, mean4, invstd4});
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long nwin = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2);
+  static const bool pre_ok = [] { const char* e = getenv("DFCSA_BOUT_PRE"); return !e || atoi(e) != 0; }();
+  if (pre_ok && v8 && dyp != nullptr && H >= 2 && W >= 2) {
+    dim3 grid2(red_blocks(nwin, g.PL, g.chunks, 2), g.chunks);
+    block_out_bwd_reduce_pre_kernel<8><<<grid2, 256, 0, ST>>>(G_(dskip), ld_dskip, G_(dyp), ld_dyp, A_(y), ld_y, A_(f0), ld_f0, A_(r), ld_r,
+                                                              B, H, W, C, scale4, shift4, mean4, invstd4, GM_(dy_out), ld_dy, red4, drs,
+                                                              g.CL, g.PL);
+    DFCSA_LAUNCH_CHECK("block_out_bwd_reduce_pre_kernel");
+    return DFCSA_OK;
+  }
   dim3 grid(red_blocks(nwin, g.PL, g.chunks, ew_occ(4)), g.chunks);
   OCC_DISPATCH(4, VEC_DISPATCH(v8, (block_out_bwd_reduce_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(G_(dskip), ld_dskip, G_(dyp), ld_dyp, A_(y), ld_y, A_(f0), ld_f0,
                                                                            A_(r), ld_r, B, H, W, C, scale4, shift4, mean4, invstd4,
@@ -1627,15 +1949,31 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
   const RedGeom g = red_geom(C, v8 ? 8 : 1);
   const long long M = static_cast<long long>(B) * H * W;
   dim3 grid(red_blocks(M, g.PL, g.chunks, ew_occ(2)), g.chunks);
-  OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC, OCC><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
-                                                                         shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL))));
+  static const bool two_pix = [] { const char* e = getenv("DFCSA_RED1_PIX"); return !e || atoi(e) != 1; }();
+  if (two_pix)
+    OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC, OCC, 2><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
+                                                                              shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL))));
+  else
+    OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC, OCC, 1><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
+                                                                              shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
-  const int parts = bilerpT_parts(v8 ? C / 8 : C, W, P);
-  const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C) * parts;
-  VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts)));
+  // coarse pooled maps (W / P >= 8): every pixel loaded once, one source cell per thread group
+  static const bool one_cell_ok = [] { const char* e = getenv("DFCSA_BILERPT_ONE_CELL"); return !e || atoi(e) != 0; }();
+  const int parts1 = bilerpT_parts(C / 8, W, P, true);
+  const int cvs = C / 8;
+  if (one_cell_ok && v8 && W / P >= 8 && (cvs & (cvs - 1)) == 0 && cvs <= 32 && 256 % (P * cvs * parts1) == 0) {
+    const long long total = static_cast<long long>(B) * H * P * cvs * parts1;
+    bilerpT_rows1_kernel<8><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts1);
+  } else {
+    const int parts = bilerpT_parts(v8 ? C / 8 : C, W, P);
+    const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C) * parts;
+    VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts)));
+  }
   DFCSA_LAUNCH_CHECK("bilerpT_rows_kernel");
   // dgamma = sum dA*U = <bilinear_up^T(dA), o>: a dot product over the small pooled map instead of a gather per pixel
-  if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
+  if (cols_par_ok(C, H, P) && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
+    cols_reduce_par_kernel<4><<<cols_par_blocks(B, P), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);
+  else if (C % 4 == 0 && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
     cols_reduce_kernel<4><<<ew_blocks(static_cast<long long>(B) * P * P * (C / 4)), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);
   else
     cols_reduce_kernel<1><<<ew_blocks(static_cast<long long>(B) * P * P * C), 256, 0, ST>>>(tmp, B, H, P, C, 1, gamma, d_o, o, dgamma);

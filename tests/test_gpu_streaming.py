@@ -11,7 +11,10 @@ pytestmark = pytest.mark.gpu
 
 # (B, H, W, C, P)
 SP = [(2, 14, 14, 64, 4), (2, 14, 14, 128, 16), (1, 14, 14, 64, 32), (1, 28, 28, 64, 32), (2, 7, 7, 64, 3),
-      (1, 224, 224, 64, 4), (1, 9, 13, 40, 4), (1, 7, 5, 12, 8)]
+      (1, 224, 224, 64, 4), (1, 9, 13, 40, 4), (1, 7, 5, 12, 8),
+      # coarse pooled maps (H / P, W / P >= 8): the one-cell bilinear^T rows kernel and the CTA-per-cell column reductions,
+      # with 16 / 32 channel vectors, a row count that leaves half a CTA idle, P = 8, and P = 3 (falls back to the two-sided rows)
+      (1, 33, 72, 128, 4), (1, 72, 64, 256, 8), (3, 40, 48, 64, 3)]
 
 
 def _rel(a, b):
@@ -123,7 +126,8 @@ def test_block_out_and_sum_out_fwd(cuda, B, H, W, C, pool):
 
 
 @pytest.mark.parametrize("src", ["skip", "pool", "both"])
-@pytest.mark.parametrize("B,H,W,C", [(2, 14, 14, 64), (1, 28, 28, 128), (1, 112, 112, 64), (2, 8, 10, 40), (1, 56, 56, 256)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 14, 14, 64), (1, 28, 28, 128), (1, 112, 112, 64), (2, 8, 10, 40), (1, 56, 56, 256),
+                                     (1, 9, 13, 64), (2, 7, 5, 16), (1, 3, 2, 8)])
 def test_block_out_bwd_reduce_and_bn_bwd_apply(cuda, B, H, W, C, src):
     """dfcsa_block_out_bwd_reduce: dy = dskip + maxpool2x2^T(dyp) (argmax recomputed from the stored y, first maximum in
     scan order like ATen), BN4 reductions over d4 = dy [bn4(F0) > 0], d res_scale = sum dy R; then dfcsa_bn_bwd_apply:
