@@ -1188,83 +1188,13 @@ bilerpT_rows_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int 
   }
 }
 
-// The same pass with every pixel loaded ONCE: the lanes of a group take source cell j of row (b, y), i.e. the pixels whose
-// LEFT bilinear tap is j (decided by bilerp_taps itself, the analytic range only brackets them), and keep two sums -
-// (1 - lx) d for output j and lx d for output j + 1.  The two halves of an output meet in shared memory (P * group
-// divides the CTA, so a row never straddles two CTAs).  The two-sided window above loads and weighs every pixel twice
-// and is bound by instruction issue (ncu at level 1: 73 % issue-active, 126 us for 411 MB).
-template <int VEC>
-__global__ void __launch_bounds__(256)
-bilerpT_rows1_kernel(const grad_t* dz, long long ld_dz, int B, int H, int W, int C, int P, float* tmp, int parts) {
-  __shared__ __align__(16) float s_b[256 * VEC];
-  const int CV = C / VEC;
-  const int group = CV * parts;
-  const long long total = static_cast<long long>(B) * H * P * group;
-  const bool small = total < (1LL << 31);
-  const float ratio = static_cast<float>(W) / static_cast<float>(P);
-  for (long long base = static_cast<long long>(blockIdx.x) * blockDim.x; base < total;
-       base += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long i = base + threadIdx.x;
-    const bool active = i < total;           // P * group divides 256 and total: a row is active as a whole
-    int lg, j, y; long long b;
-    decode4(active ? i : total - 1, small, group, P, H, lg, j, y, b);
-    const int part = lg / CV;
-    const int c = (lg - part * CV) * VEC;
-    // x0 == j  <=>  src in [j, j + 1) (src clamped at 0: cell 0 starts at pixel 0; the last cell runs to the end)
-    int lo = j == 0 ? 0 : static_cast<int>(floorf((j + 0.5f) * ratio - 0.5f)) - 1;
-    int hi = j == P - 1 ? W - 1 : static_cast<int>(ceilf((j + 1.5f) * ratio - 0.5f)) + 1;
-    lo = max(lo, 0); hi = min(hi, W - 1);
-    float acc_a[VEC], acc_b[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) { acc_a[v] = 0.f; acc_b[v] = 0.f; }
-    const grad_t* row = dz + ((b * H + y) * W) * ld_dz + 2 * C + c;
-    for (int x = lo + part; x <= hi; x += 4 * parts) {
-      RawV<VEC, grad_t> raw[4];
-      float wa[4], wb[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int xx = x + u * parts;
-        const bool ok = xx <= hi;
-        const int xc = ok ? xx : hi;
-        int x0, x1; float lx; bilerp_taps(xc, P, W, x0, x1, lx);
-        const bool mine = ok && x0 == j;
-        // the last cell's right tap is the cell itself (x1 clamps to P - 1)
-        wa[u] = mine ? (x1 == j ? 1.f : 1.f - lx) : 0.f;
-        wb[u] = mine && x1 != j ? lx : 0.f;
-        raw[u] = ldraw<VEC>(row + xc * ld_dz);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float d[VEC]; cvtraw<VEC>(raw[u], d);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { acc_a[v] = fmaf(wa[u], d[v], acc_a[v]); acc_b[v] = fmaf(wb[u], d[v], acc_b[v]); }
-      }
-    }
-    for (int off = CV; off < group; off <<= 1) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        acc_a[v] += __shfl_xor_sync(0xffffffffu, acc_a[v], off);
-        acc_b[v] += __shfl_xor_sync(0xffffffffu, acc_b[v], off);
-      }
-    }
-    if (part == 0) stf<VEC>(s_b + threadIdx.x * VEC, acc_b);
-    __syncthreads();
-    if (active && part == 0) {
-      if (j > 0) {
-        float t[VEC]; ldf<VEC>(s_b + (threadIdx.x - group) * VEC, t);      // cell j - 1 of the same row: `group` threads back
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc_a[v] += t[v];
-      }
-      stf<VEC>(tmp + ((b * H + y) * P + j) * C + c, acc_a);
-    }
-    __syncthreads();
-  }
-}
-
+// Measured and not kept (session AI / AJ, profiles/experiments/): a one-cell variant - each lane group walks only the pixels
+// whose LEFT tap is its cell, keeps (1 - lx) d and lx d as two sums, neighbours meet in shared memory - loads every pixel
+// once and issues 25 % fewer instructions, yet takes the same 127 us at level 1 (ncu: issue 54 %, DRAM 3.2 TB/s).
 // lanes per output of bilerpT_rows_kernel: CV * parts must be a power of two <= 32, and a part should keep >= 8 pixels
-static int bilerpT_parts(int CV, int W, int P, bool one_cell = false) {
+static int bilerpT_parts(int CV, int W, int P) {
   if (CV <= 0 || (CV & (CV - 1)) != 0 || CV >= 32) return 1;
-  const int window = (one_cell ? 1 : 2) * ((W + P - 1) / P) + 4;
+  const int window = 2 * ((W + P - 1) / P) + 4;
   int parts = 1;
   while (parts * 2 * CV <= 32 && parts * 2 * 8 <= window) parts *= 2;
   return parts;
@@ -1957,18 +1887,9 @@ extern "C" int dfcsa_branch_bwd_reduce1(void* dz, int64_t ld_dz, const void* l0,
     OCC_DISPATCH(2, VEC_DISPATCH(v8, (branch_bwd_reduce1_kernel<VEC, OCC, 1><<<grid, 256, 0, ST>>>(GM_(dz), ld_dz, A_(l0), ld_l0, A_(g0), ld_g0, M, C, scale1,
                                                                               shift1, mean1, invstd1, scale3, shift3, red1, g.CL, g.PL))));
   DFCSA_LAUNCH_CHECK("branch_bwd_reduce1_kernel");
-  // coarse pooled maps (W / P >= 8): every pixel loaded once, one source cell per thread group
-  static const bool one_cell_ok = [] { const char* e = getenv("DFCSA_BILERPT_ONE_CELL"); return !e || atoi(e) != 0; }();
-  const int parts1 = bilerpT_parts(C / 8, W, P, true);
-  const int cvs = C / 8;
-  if (one_cell_ok && v8 && W / P >= 8 && (cvs & (cvs - 1)) == 0 && cvs <= 32 && 256 % (P * cvs * parts1) == 0) {
-    const long long total = static_cast<long long>(B) * H * P * cvs * parts1;
-    bilerpT_rows1_kernel<8><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts1);
-  } else {
-    const int parts = bilerpT_parts(v8 ? C / 8 : C, W, P);
-    const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C) * parts;
-    VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts)));
-  }
+  const int parts = bilerpT_parts(v8 ? C / 8 : C, W, P);
+  const long long total = static_cast<long long>(B) * H * P * (v8 ? C / 8 : C) * parts;
+  VEC_DISPATCH(v8, (bilerpT_rows_kernel<VEC><<<ew_blocks(total), 256, 0, ST>>>(G_(dz), ld_dz, B, H, W, C, P, tmp, parts)));
   DFCSA_LAUNCH_CHECK("bilerpT_rows_kernel");
   // dgamma = sum dA*U = <bilinear_up^T(dA), o>: a dot product over the small pooled map instead of a gather per pixel
   if (cols_par_ok(C, H, P) && ((reinterpret_cast<uintptr_t>(tmp) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(o)) & 15) == 0)
