@@ -10,8 +10,9 @@ qk 8), 224x224, batch 64 per GPU, one full training step = forward + sigmoid/bce
 One JSON line on rank 0.  `value` = images/s with the batch already resident in HBM (CUDA events, max over ranks);
 `e2e` = the same step through the public Trainer API fed from pinned HOST buffers (every step's H2D of images+masks,
 through the look-ahead feeder of Trainer.train_epoch, and a D2H read of every step's loss inside the timed region); `roofline` = the tcgen05 implicit-GEMM conv kernel (algorithmic FLOPs / its
-CUDA-event time inside the timed steps) against the measured bf16 peak; `cpu_baseline` = the oracle port of the
-reference step timed on this box's host cores on a bounded sample.
+CUDA-event time inside the timed steps) against the measured bf16 peak; `cpu_baseline` = the unmodified reference classes
+(baseline/_ref, kind "reference"; the oracle port only if those files did not travel) running the same step on this box's host
+cores on a bounded sample; `reference_gpu` = the same unmodified classes in eager PyTorch on this GPU (the bar of SURVEY 2.2).
 """
 import argparse
 import json
